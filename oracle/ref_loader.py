@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference modules of the pillar hot path.
+
+Only usable where /root/reference exists (the build container).  It is used by
+``tests/golden/make_golden.py`` to generate the committed golden vectors and by the
+``-m "not gpu"`` tests that re-check the oracle restatement against the live reference.
+Nothing under ``lidar_vision_vqa_b200/`` may import this file; ``bench.py`` and the ``-m gpu``
+tests never touch /root/reference (it does not exist on the GPU box).
+
+The reference package ``pcdet`` cannot be imported as a package (its ``__init__`` files pull
+spconv / easydict / SharedArray / compiled ops, none installed).  The three files on the hot path
+depend only on torch, so they are loaded by path under a stub parent package:
+
+  src/lidar-encoder/pcdet/models/backbones_3d/vfe/vfe_template.py          (VFETemplate)
+  src/lidar-encoder/pcdet/models/backbones_3d/vfe/pillar_vfe.py            (PFNLayer, PillarVFE)
+  src/lidar-encoder/pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py    (DynamicPillarVFE, ...Simple2D)
+  src/lidar-encoder/pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py
+
+``dynamic_pillar_vfe.py`` needs ``torch_scatter`` (not installed) and calls ``.cuda()`` in its
+constructor; :func:`load_reference` installs a minimal ``torch_scatter`` shim built on
+``Tensor.scatter_reduce`` / ``index_add`` and, when no GPU is present, makes ``Tensor.cuda`` the
+identity while the constructor runs.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("LVVQA_REFERENCE_ROOT", "/root/reference")
+_PCDET = os.path.join(REFERENCE_ROOT, "src", "lidar-encoder", "pcdet")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(_PCDET, "models", "backbones_3d", "vfe", "pillar_vfe.py"))
+
+
+class AttrDict(dict):
+    """Stand-in for easydict.EasyDict (not installed): attribute access + .get()."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:  # pragma: no cover
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _install_torch_scatter_shim():
+    """scatter_mean / scatter_max with torch_scatter's (src, index, dim) -> out semantics, dim=0 only."""
+    import torch
+
+    if "torch_scatter" in sys.modules:
+        return
+    mod = types.ModuleType("torch_scatter")
+
+    def scatter_mean(src, index, dim=0):
+        assert dim == 0
+        n = int(index.max().item()) + 1 if index.numel() else 0
+        out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        out.index_add_(0, index, src)
+        cnt = torch.zeros(n, dtype=src.dtype, device=src.device)
+        cnt.index_add_(0, index, torch.ones_like(index, dtype=src.dtype))
+        return out / cnt.clamp(min=1).view(-1, *([1] * (src.dim() - 1)))
+
+    def scatter_max(src, index, dim=0):
+        assert dim == 0
+        n = int(index.max().item()) + 1 if index.numel() else 0
+        out = torch.full((n,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype, device=src.device)
+        idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
+        out = out.scatter_reduce(0, idx, src, reduce="amax", include_self=True)
+        return out, None
+
+    mod.scatter_mean = scatter_mean
+    mod.scatter_max = scatter_max
+    sys.modules["torch_scatter"] = mod
+
+
+def _load(modname: str, relpath: str):
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(_PCDET, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_CACHE = {}
+
+
+def load_reference():
+    """Returns a namespace with the reference classes (PillarVFE, PFNLayer, PointPillarScatter, ...)."""
+    if "ns" in _CACHE:
+        return _CACHE["ns"]
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+    _install_torch_scatter_shim()
+    for name in ("_ref_pcdet", "_ref_pcdet.vfe", "_ref_pcdet.map_to_bev"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = []  # mark as package so relative imports resolve
+        sys.modules[name] = pkg
+    _load("_ref_pcdet.vfe.vfe_template", "models/backbones_3d/vfe/vfe_template.py")
+    pv = _load("_ref_pcdet.vfe.pillar_vfe", "models/backbones_3d/vfe/pillar_vfe.py")
+    dv = _load("_ref_pcdet.vfe.dynamic_pillar_vfe", "models/backbones_3d/vfe/dynamic_pillar_vfe.py")
+    sc = _load("_ref_pcdet.map_to_bev.pointpillar_scatter", "models/backbones_2d/map_to_bev/pointpillar_scatter.py")
+    ns = types.SimpleNamespace(
+        PFNLayer=pv.PFNLayer,
+        PillarVFE=pv.PillarVFE,
+        DynamicPillarVFE=dv.DynamicPillarVFE,
+        DynamicPillarVFESimple2D=dv.DynamicPillarVFESimple2D,
+        PointPillarScatter=sc.PointPillarScatter,
+        PointPillarScatter3d=sc.PointPillarScatter3d,
+        AttrDict=AttrDict,
+    )
+    _CACHE["ns"] = ns
+    return ns
+
+
+@contextlib.contextmanager
+def cuda_is_identity():
+    """The dynamic VFE constructors call ``.cuda()`` on three small tensors; on a CPU-only host make that a no-op."""
+    import torch
+
+    if torch.cuda.is_available():
+        yield
+        return
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
