@@ -1,0 +1,148 @@
+/*
+ * pillars_b200.h -- C ABI of libpillars_b200.so: the B200 (sm_100a) pillar LiDAR-encoder hot path.
+ *
+ * Drop-in boundary.  The reference (Advaith-Sajeev/LiDAR-Vision-VQA, src/lidar-encoder = vendored OpenPCDet)
+ * has no native code on this path: grouping is a third-party CPU call, the feature net and the BEV scatter
+ * are eager PyTorch.  Its native-extension idiom elsewhere is "pybind11 function -> raw-pointer launcher on the
+ * default stream" (src/lidar-encoder/pcdet/ops/ingroup_inds/src/ingroup_inds.cpp:15-54,
+ * ingroup_inds_kernel.cu:47-77).  This header is that launcher layer for the pillar path, as plain C so that
+ * Python binds it with ctypes (INTEGRATION.md shows the stub a maintainer adds to pcdet).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the caller's current device unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued on it and
+ *     the call returns without synchronising;
+ *   - return value: 0 on success, otherwise a cudaError_t value or a negative PILLARS_E_* code;
+ *     pillars_last_error() returns a thread-local message.  Nothing throws.
+ *   - no hidden device allocation: scratch comes from the caller's workspace, sized by
+ *     pillars_workspace_bytes().  The workspace content is opaque and may be reused by the next call
+ *     on the same stream.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point fails.
+ *
+ * Entry point                          replaces (reference file:line, paths under src/lidar-encoder/pcdet/)
+ *   pillars_frame_offsets              datasets/dataset.py:237-244        (batch-index column of the collated points)
+ *   pillars_voxelize                   datasets/processor/data_processor.py:16-61,133-180
+ *                                      (VoxelGeneratorWrapper.generate -> spconv point_to_voxel) + the collate of
+ *                                      datasets/dataset.py:232-244
+ *   pillars_pfn_dense                  models/backbones_3d/vfe/pillar_vfe.py:94-123 (PillarVFE.forward) with
+ *                                      :29-49 (PFNLayer.forward), eval mode
+ *   pillars_scatter_bev                models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37
+ *                                      (PointPillarScatter.forward)
+ *   pillars_encode_bev                 the three above fused: raw points -> pillar_features, voxel_coords,
+ *                                      spatial_features, i.e. module_list[vfe, map_to_bev] of
+ *                                      models/detectors/pointpillar.py:9-11 fed by `points` the way
+ *                                      models/backbones_3d/vfe/dynamic_pillar_vfe.py:90-142 is
+ */
+#ifndef PILLARS_B200_H_
+#define PILLARS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PILLARS_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define PILLARS_E_BADARG (-1)      /* NULL pointer, bad size, unsupported combination */
+#define PILLARS_E_WORKSPACE (-2)   /* workspace too small / misaligned */
+#define PILLARS_E_UNSUPPORTED (-3) /* shape outside what the kernels are instantiated for */
+#define PILLARS_E_NODEVICE (-4)    /* no CUDA device / not an sm_100 part */
+
+/* Voxel grid + grouping limits: the `transform_points_to_voxels` block of a PCDet yaml
+ * (data_processor.py:133-149).  range/voxel are the fp32 values spconv stores; grid = round((max-min)/voxel)
+ * computed by the caller exactly as data_processor.py:135-136 does. */
+typedef struct pillars_grid {
+    float range[6];     /* xmin ymin zmin xmax ymax zmax */
+    float voxel[3];     /* vx vy vz */
+    int32_t grid[3];    /* nx ny nz */
+    int32_t max_points; /* MAX_POINTS_PER_VOXEL (P) */
+    int32_t max_voxels; /* MAX_NUMBER_OF_VOXELS, per frame */
+} pillars_grid_t;
+
+/* One PFN layer in eval mode (pillar_vfe.py:8-49) with BatchNorm folded by the caller:
+ *   y = relu( (x . W^T) * scale + shift ),  scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+ * (USE_NORM false: scale = 1, shift = linear.bias).  Feature layout of x follows pillar_vfe.py:105-113. */
+typedef struct pillars_pfn {
+    int32_t c_point;          /* C: channels of a raw point incl. xyz (num_point_features) */
+    int32_t c_in;             /* in_features of the linear = C (+3 if use_absolute_xyz... see pillar_vfe.py:59-62) */
+    int32_t f_out;            /* out_features (64) */
+    int32_t use_absolute_xyz; /* USE_ABSLOTE_XYZ */
+    int32_t with_distance;    /* WITH_DISTANCE */
+    float offset[3];          /* voxel/2 + range_min per axis, computed in double by the caller (pillar_vfe.py:79-81) */
+    const float *weight;      /* [f_out, c_in] row-major = nn.Linear.weight */
+    const float *scale;       /* [f_out] */
+    const float *shift;       /* [f_out] */
+} pillars_pfn_t;
+
+/* what pillars_encode_bev / pillars_voxelize write; any pointer may be NULL to skip that output */
+typedef struct pillars_outputs {
+    int64_t pillar_capacity;  /* rows available in the per-pillar arrays below (>= sum of per-frame pillars) */
+    float *pillar_features;   /* [capacity, F]        batch_dict['pillar_features']                        */
+    int32_t *voxel_coords;    /* [capacity, 4] (b,z,y,x)  batch_dict['voxel_coords']                       */
+    int32_t *voxel_num_points;/* [capacity]           batch_dict['voxel_num_points'] (capped at P)         */
+    float *voxels;            /* [capacity, P, C] zero padded   batch_dict['voxels']                       */
+    int32_t *point_pillar;    /* [n_points] row of the pillar holding the point, -1 if rejected/dropped    */
+    int32_t *point_slot;      /* [n_points] slot inside the pillar, -1 if over the cap / rejected          */
+    int32_t *pillar_count;    /* [n_frames + 1] pillars per frame, total in the last entry                 */
+    float *bev;               /* [n_frames, F*nz, ny, nx]  batch_dict['spatial_features'] (encode_bev only) */
+} pillars_outputs_t;
+
+int pillars_abi_version(void);
+const char *pillars_last_error(void);
+
+/* 0 if device `device` (or the current one when < 0) can run this library (compute capability 10.x). */
+int pillars_device_ok(int device);
+
+/* Scratch bytes needed by pillars_voxelize / pillars_encode_bev for n_points total points in n_frames frames;
+ * by pillars_scatter_bev when n_points == 0 (then only the index map counts). */
+size_t pillars_workspace_bytes(int64_t n_points, int32_t n_frames, const pillars_grid_t *grid);
+
+/* points_b: collated batch_dict['points'] [n, row_stride] with the frame index in column 0, rows sorted by frame.
+ * Writes frame_offsets[0..n_frames] (frame b owns rows [offsets[b], offsets[b+1])). */
+int pillars_frame_offsets(const float *points_b, int64_t n, int32_t row_stride, int32_t n_frames,
+                          int32_t *frame_offsets, void *stream);
+
+/* Hard voxelisation of a batch: first-appearance pillar ids per frame, first-P points per pillar in point order,
+ * new pillars dropped once max_voxels exist.  points is [n, row_stride] fp32; x,y,z,... start at column `col0`
+ * (0 for packed frames, 1 for the collated PCDet layout); c_point channels are copied into `voxels`.
+ * Fills out->{voxel_coords, voxel_num_points, voxels, point_pillar, point_slot, pillar_count} (each optional). */
+int pillars_voxelize(const float *points, int64_t n, int32_t row_stride, int32_t col0, int32_t c_point,
+                     const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
+                     const pillars_outputs_t *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* PillarVFE.forward on already grouped voxels (the reference's own input format).
+ * voxels [m, P, C] fp32; num_points [m] and coords [m,4] (b,z,y,x) are int32, or fp32 when *_is_float != 0
+ * (models/__init__.py:36 casts everything to float).  out is [m, F]. */
+int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_points_is_float,
+                      const void *coords, int32_t coords_is_float, int64_t m, int32_t max_points,
+                      const pillars_pfn_t *pfn, const float voxel_size[3], float *out, void *stream);
+
+/* PointPillarScatter.forward: bev[b][f][y][x] = feats[m][f] for coords[m] = (b,z,y,x), zero elsewhere (nz == 1).
+ * m_dev, when not NULL, is a device int32 holding the live row count (<= m); rows beyond it are ignored.
+ * variant: 0 = default, 1 = plain vector stores, 2 = bulk async copies (1-D), 3 = TMA tensor stores (2-D). */
+int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
+                        const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, float *bev,
+                        void *workspace, size_t workspace_bytes, int32_t variant, void *stream);
+
+/* The fused path: raw points -> pillar features -> BEV.  Same grouping semantics as pillars_voxelize, same
+ * feature semantics as pillars_pfn_dense on its output, same canvas as pillars_scatter_bev. */
+int pillars_encode_bev(const float *points, int64_t n, int32_t row_stride, int32_t col0,
+                       const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
+                       const pillars_pfn_t *pfn, const pillars_outputs_t *out, void *workspace,
+                       size_t workspace_bytes, int32_t scatter_variant, void *stream);
+
+/* Number of kernel launches (incl. memsets) the last successful compute call on this thread enqueued. */
+int pillars_last_launch_count(void);
+
+/* Measurement hook (bench.py): four cudaEvent_t (as void*) that pillars_encode_bev / pillars_voxelize record on the
+ * call's stream at: [0] entry, [1] grouping done, [2] pillar features done, [3] scatter done.  NULL clears the hook.
+ * Thread-local; costs four cudaEventRecord per call while set. */
+int pillars_set_stage_events(void *const *events4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PILLARS_B200_H_ */

@@ -1,0 +1,9 @@
+"""B200-native (sm_100a) pillar LiDAR-encoder hot path of Advaith-Sajeev/LiDAR-Vision-VQA's src/lidar-encoder:
+point -> pillar grouping, per-pillar feature net (augment + Linear + BN + ReLU + max) and the dense BEV scatter,
+behind the reference's own module interface.  See DESIGN.md and include/pillars_b200.h."""
+from ._native import NativeLibraryError  # noqa: F401
+from .modules import (MAP_TO_BEV_REGISTRY, VFE_REGISTRY, PFNLayer, PillarVFE, PillarVFEFromPoints,  # noqa: F401
+                      PointPillarScatter, VFETemplate)
+from .ops import EncodeBuffers, GridSpec, PfnParams  # noqa: F401
+
+__version__ = "0.1.0"

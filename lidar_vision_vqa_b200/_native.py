@@ -1,0 +1,109 @@
+"""ctypes binding of libpillars_b200.so (include/pillars_b200.h).  There is no fallback: if the shared library is
+missing or the device is not an sm_100 part, the callers raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libpillars_b200.so")
+
+EXPORTED_SYMBOLS = (
+    "pillars_abi_version",
+    "pillars_last_error",
+    "pillars_device_ok",
+    "pillars_workspace_bytes",
+    "pillars_frame_offsets",
+    "pillars_voxelize",
+    "pillars_pfn_dense",
+    "pillars_scatter_bev",
+    "pillars_encode_bev",
+    "pillars_last_launch_count",
+    "pillars_set_stage_events",
+)
+
+
+class PillarsGrid(Structure):
+    _fields_ = [("range", c_float * 6), ("voxel", c_float * 3), ("grid", c_int32 * 3), ("max_points", c_int32),
+                ("max_voxels", c_int32)]
+
+
+class PillarsPfn(Structure):
+    _fields_ = [("c_point", c_int32), ("c_in", c_int32), ("f_out", c_int32), ("use_absolute_xyz", c_int32),
+                ("with_distance", c_int32), ("offset", c_float * 3), ("weight", c_void_p), ("scale", c_void_p),
+                ("shift", c_void_p)]
+
+
+class PillarsOutputs(Structure):
+    _fields_ = [("pillar_capacity", c_int64), ("pillar_features", c_void_p), ("voxel_coords", c_void_p),
+                ("voxel_num_points", c_void_p), ("voxels", c_void_p), ("point_pillar", c_void_p),
+                ("point_slot", c_void_p), ("pillar_count", c_void_p), ("bev", c_void_p)]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_LIB: Optional[ctypes.CDLL] = None
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Loads (building first if the .so is absent or stale and nvcc is available)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if build_if_missing:
+        from . import build as _build
+
+        if _build.needs_build():
+            _build.build()
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryError(f"{LIB_PATH} is missing: run `python -m lidar_vision_vqa_b200.build` "
+                                 "(there is no CPU/PyTorch fallback for the pillar path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.pillars_abi_version.restype = c_int
+    lib.pillars_last_error.restype = c_char_p
+    lib.pillars_last_launch_count.restype = c_int
+    lib.pillars_device_ok.restype = c_int
+    lib.pillars_device_ok.argtypes = [c_int]
+    lib.pillars_workspace_bytes.restype = c_size_t
+    lib.pillars_workspace_bytes.argtypes = [c_int64, c_int32, POINTER(PillarsGrid)]
+    lib.pillars_frame_offsets.restype = c_int
+    lib.pillars_frame_offsets.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
+    lib.pillars_voxelize.restype = c_int
+    lib.pillars_voxelize.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                     POINTER(PillarsGrid), POINTER(PillarsOutputs), c_void_p, c_size_t, c_void_p]
+    lib.pillars_pfn_dense.restype = c_int
+    lib.pillars_pfn_dense.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32,
+                                      POINTER(PillarsPfn), POINTER(c_float), c_void_p, c_void_p]
+    lib.pillars_scatter_bev.restype = c_int
+    lib.pillars_scatter_bev.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
+                                        c_int32, c_void_p, c_void_p, c_size_t, c_int32, c_void_p]
+    lib.pillars_encode_bev.restype = c_int
+    lib.pillars_encode_bev.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
+                                       POINTER(PillarsPfn), POINTER(PillarsOutputs), c_void_p, c_size_t, c_int32,
+                                       c_void_p]
+    lib.pillars_set_stage_events.restype = c_int
+    lib.pillars_set_stage_events.argtypes = [POINTER(c_void_p)]
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pillars_last_error().decode(errors="replace")
+        raise NativeLibraryError(f"{what} failed (code {rc}): {msg}")
+
+
+def make_grid(point_cloud_range, voxel_size, grid_size, max_points: int, max_voxels: int) -> PillarsGrid:
+    g = PillarsGrid()
+    for i in range(6):
+        g.range[i] = float(point_cloud_range[i])
+    for i in range(3):
+        g.voxel[i] = float(voxel_size[i])
+        g.grid[i] = int(grid_size[i])
+    g.max_points = int(max_points)
+    g.max_voxels = int(max_voxels)
+    return g

@@ -1,0 +1,279 @@
+// extern "C" surface of libpillars_b200.so (see include/pillars_b200.h for the contract and the reference lines each
+// entry point replaces).  Argument checking, workspace carving and kernel sequencing only -- no compute on the host.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pillars {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+static thread_local int g_launches_last = 0;
+static thread_local cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local bool g_stage_on = false;
+
+static void stage_mark(int i, cudaStream_t st)
+{
+    if (g_stage_on && g_stage_ev[i]) cudaEventRecord(g_stage_ev[i], st);
+}
+
+void note_launch(int n) { g_launches += n; }
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char *where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+static int check_grid(const pillars_grid_t *g, int nb)
+{
+    if (!g) return fail(PILLARS_E_BADARG, "grid is NULL");
+    for (int i = 0; i < 3; ++i) {
+        if (g->grid[i] < 1) return fail(PILLARS_E_BADARG, "grid[%d] = %d", i, g->grid[i]);
+        if (!(g->voxel[i] > 0.f)) return fail(PILLARS_E_BADARG, "voxel[%d] must be > 0", i);
+    }
+    if (g->max_points < 1) return fail(PILLARS_E_BADARG, "max_points = %d", g->max_points);
+    if (g->max_voxels < 0) return fail(PILLARS_E_BADARG, "max_voxels = %d", g->max_voxels);
+    if (nb < 0 || nb > kMaxFrames) return fail(PILLARS_E_UNSUPPORTED, "n_frames = %d (max %d)", nb, kMaxFrames);
+    const unsigned long long cells =
+        static_cast<unsigned long long>(g->grid[0]) * g->grid[1] * static_cast<unsigned long long>(g->grid[2]);
+    if (cells * static_cast<unsigned long long>(nb > 0 ? nb : 1) >= 0xFFFFFFFFull)
+        return fail(PILLARS_E_UNSUPPORTED, "n_frames * cells does not fit a 32-bit pillar key");
+    return 0;
+}
+
+static int check_points(const float *points, int64_t n, int stride, int col0, int c_point)
+{
+    if (n < 0 || n >= (1ll << 31) - kTile) return fail(PILLARS_E_UNSUPPORTED, "n_points = %lld", (long long)n);
+    if (n > 0 && !points) return fail(PILLARS_E_BADARG, "points is NULL");
+    if (stride < 3 || stride > 16) return fail(PILLARS_E_UNSUPPORTED, "row_stride = %d (3..16)", stride);
+    if (col0 < 0 || c_point < 3 || col0 + c_point > stride)
+        return fail(PILLARS_E_BADARG, "col0 = %d, c_point = %d do not fit row_stride = %d", col0, c_point, stride);
+    return 0;
+}
+
+static int idx_bits_for(int64_t n)
+{
+    int bits = 1;
+    while ((1ll << bits) < n) ++bits;
+    return bits;
+}
+
+static int check_pfn(const pillars_pfn_t *pfn)
+{
+    if (!pfn || !pfn->weight || !pfn->scale || !pfn->shift) return fail(PILLARS_E_BADARG, "pfn / weights NULL");
+    if (pfn->f_out != 64) return fail(PILLARS_E_UNSUPPORTED, "f_out = %d (only 64 is instantiated)", pfn->f_out);
+    if (pfn->c_point < 3 || pfn->c_point > 6)
+        return fail(PILLARS_E_UNSUPPORTED, "c_point = %d (3..6 are instantiated)", pfn->c_point);
+    const int want = (pfn->use_absolute_xyz ? pfn->c_point : pfn->c_point - 3) + 6 + (pfn->with_distance ? 1 : 0);
+    if (pfn->c_in != want) return fail(PILLARS_E_BADARG, "c_in = %d, expected %d", pfn->c_in, want);
+    return 0;
+}
+
+static PfnDev make_pfn_dev(const pillars_pfn_t &pfn, const float voxel[3])
+{
+    PfnDev d;
+    d.weight = pfn.weight;
+    d.scale = pfn.scale;
+    d.shift = pfn.shift;
+    for (int i = 0; i < 3; ++i) {
+        d.off[i] = pfn.offset[i];
+        d.vsz[i] = voxel[i];
+    }
+    return d;
+}
+
+}  // namespace pillars
+
+using namespace pillars;
+
+extern "C" {
+
+int pillars_abi_version(void) { return PILLARS_ABI_VERSION; }
+const char *pillars_last_error(void) { return g_err; }
+int pillars_last_launch_count(void) { return g_launches_last; }
+
+int pillars_set_stage_events(void *const *events4)
+{
+    g_stage_on = events4 != nullptr;
+    for (int i = 0; i < 4; ++i) g_stage_ev[i] = events4 ? static_cast<cudaEvent_t>(events4[i]) : nullptr;
+    return 0;
+}
+
+int pillars_device_ok(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(PILLARS_E_NODEVICE, "no CUDA device (%s)", cudaGetErrorName(e));
+    if (device < 0 && (e = cudaGetDevice(&device)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    int major = 0;
+    if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device)) != cudaSuccess)
+        return cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10) return fail(PILLARS_E_NODEVICE, "device %d has compute capability %d.x; this library is sm_100a only", device, major);
+    return 0;
+}
+
+size_t pillars_workspace_bytes(int64_t n_points, int32_t n_frames, const pillars_grid_t *grid)
+{
+    if (!grid || n_points < 0 || n_frames < 0) return 0;
+    const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
+    return carve_workspace(nullptr, n_points, n_frames, cells_xy).total_bytes;
+}
+
+int pillars_frame_offsets(const float *points_b, int64_t n, int32_t row_stride, int32_t n_frames,
+                          int32_t *frame_offsets, void *stream)
+{
+    g_launches = 0;
+    if (!frame_offsets || n < 0 || (n > 0 && !points_b) || row_stride < 1 || n_frames < 0)
+        return fail(PILLARS_E_BADARG, "pillars_frame_offsets: bad argument");
+    cudaError_t e = launch_frame_offsets(points_b, n, row_stride, n_frames, frame_offsets, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "pillars_frame_offsets");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+static int group_and_emit(const float *points, int64_t n, int32_t row_stride, int32_t col0, int32_t c_point,
+                          const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
+                          const pillars_pfn_t *pfn, const pillars_outputs_t *out, void *workspace, size_t workspace_bytes,
+                          bool want_bev, int scatter_variant, void *stream)
+{
+    g_launches = 0;
+    int rc;
+    if ((rc = check_grid(grid, n_frames))) return rc;
+    if ((rc = check_points(points, n, row_stride, col0, c_point))) return rc;
+    if (!frame_offsets || !out) return fail(PILLARS_E_BADARG, "frame_offsets / out is NULL");
+    if (pfn && (rc = check_pfn(pfn))) return rc;
+    if (pfn && pfn->c_point != c_point) return fail(PILLARS_E_BADARG, "pfn->c_point != c_point");
+    if (pfn && !out->pillar_features) return fail(PILLARS_E_BADARG, "pillar_features output is required");
+    if (want_bev && (!out->bev || !pfn)) return fail(PILLARS_E_BADARG, "bev output / pfn missing");
+    if (want_bev && grid->grid[2] != 1) return fail(PILLARS_E_UNSUPPORTED, "BEV scatter needs nz == 1");
+    if (out->pillar_capacity < 0) return fail(PILLARS_E_BADARG, "pillar_capacity < 0");
+    const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+        return fail(PILLARS_E_WORKSPACE, "workspace NULL or not 256-byte aligned");
+    const Workspace ws = carve_workspace(workspace, n, n_frames, cells_xy);
+    if (ws.total_bytes > workspace_bytes)
+        return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.total_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const GridDev gd = make_grid_dev(*grid);
+    cudaError_t e;
+    stage_mark(0, st);
+
+    if (out->point_pillar && n > 0) {
+        if ((e = cudaMemsetAsync(out->point_pillar, 0xFF, sizeof(int32_t) * n, st)) != cudaSuccess) return cuda_fail(e, "memset");
+        note_launch();
+    }
+    if (out->point_slot && n > 0) {
+        if ((e = cudaMemsetAsync(out->point_slot, 0xFF, sizeof(int32_t) * n, st)) != cudaSuccess) return cuda_fail(e, "memset");
+        note_launch();
+    }
+    if ((e = launch_group_points(points, n, row_stride, col0, frame_offsets, n_frames, gd, ws, out->pillar_count, st)) !=
+        cudaSuccess)
+        return cuda_fail(e, "group_points");
+    stage_mark(1, st);
+
+    FeatureJob job{};
+    job.points = points;
+    job.n = n;
+    job.stride = row_stride;
+    job.col0 = col0;
+    job.c_point = c_point;
+    job.nb = n_frames;
+    job.idx_bits = idx_bits_for(n > 1 ? n : 2);
+    job.do_features = pfn != nullptr;
+    if (pfn) {
+        job.use_abs = pfn->use_absolute_xyz != 0;
+        job.with_dist = pfn->with_distance != 0;
+        job.pfn = make_pfn_dev(*pfn, grid->voxel);
+        job.c_in = pfn->c_in;
+        job.f_out = pfn->f_out;
+    }
+    job.out = *out;
+    job.write_cell_row = want_bev;
+    if ((e = launch_pillar_features(job, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features");
+    stage_mark(2, st);
+
+    if (want_bev) {
+        if ((e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, pfn->f_out, grid->grid[0], grid->grid[1],
+                                out->bev, scatter_variant, st)) != cudaSuccess)
+            return cuda_fail(e, "scatter");
+    }
+    stage_mark(3, st);
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_voxelize(const float *points, int64_t n, int32_t row_stride, int32_t col0, int32_t c_point,
+                     const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
+                     const pillars_outputs_t *out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return group_and_emit(points, n, row_stride, col0, c_point, frame_offsets, n_frames, grid, nullptr, out, workspace,
+                          workspace_bytes, false, 0, stream);
+}
+
+int pillars_encode_bev(const float *points, int64_t n, int32_t row_stride, int32_t col0, const int32_t *frame_offsets,
+                       int32_t n_frames, const pillars_grid_t *grid, const pillars_pfn_t *pfn,
+                       const pillars_outputs_t *out, void *workspace, size_t workspace_bytes, int32_t scatter_variant,
+                       void *stream)
+{
+    if (!pfn) return fail(PILLARS_E_BADARG, "pfn is NULL");
+    return group_and_emit(points, n, row_stride, col0, pfn->c_point, frame_offsets, n_frames, grid, pfn, out, workspace,
+                          workspace_bytes, out && out->bev != nullptr, scatter_variant, stream);
+}
+
+int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_points_is_float, const void *coords,
+                      int32_t coords_is_float, int64_t m, int32_t max_points, const pillars_pfn_t *pfn,
+                      const float voxel_size[3], float *out, void *stream)
+{
+    g_launches = 0;
+    int rc;
+    if ((rc = check_pfn(pfn))) return rc;
+    if (m < 0 || max_points < 1 || !voxel_size) return fail(PILLARS_E_BADARG, "pillars_pfn_dense: bad size");
+    if (m > 0 && (!voxels || !num_points || !coords || !out)) return fail(PILLARS_E_BADARG, "pillars_pfn_dense: NULL pointer");
+    if (reinterpret_cast<uintptr_t>(coords) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0)
+        return fail(PILLARS_E_BADARG, "coords / out must be 16-byte aligned");
+    const PfnDev pd = make_pfn_dev(*pfn, voxel_size);
+    cudaError_t e = launch_pfn_dense(voxels, num_points, num_points_is_float != 0, coords, coords_is_float != 0, m,
+                                     max_points, pfn->c_point, pfn->c_in, pfn->f_out, pfn->use_absolute_xyz != 0,
+                                     pfn->with_distance != 0, pd, out, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "pillars_pfn_dense");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m, const int32_t *m_dev,
+                        int32_t n_frames, int32_t f, int32_t nx, int32_t ny, float *bev, void *workspace,
+                        size_t workspace_bytes, int32_t variant, void *stream)
+{
+    g_launches = 0;
+    if (m < 0 || n_frames < 0 || f < 1 || nx < 1 || ny < 1) return fail(PILLARS_E_BADARG, "pillars_scatter_bev: bad size");
+    if (n_frames > 0 && !bev) return fail(PILLARS_E_BADARG, "bev is NULL");
+    if (m > 0 && (!feats || !coords)) return fail(PILLARS_E_BADARG, "feats / coords NULL");
+    if (m > 0 && reinterpret_cast<uintptr_t>(coords) % 16 != 0) return fail(PILLARS_E_BADARG, "coords must be 16-byte aligned");
+    const size_t need = sizeof(int32_t) * static_cast<size_t>(n_frames) * nx * ny;
+    if (need > 0 && (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 16 != 0))
+        return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+    if (n_frames == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t *cell_row = static_cast<int32_t *>(workspace);
+    cudaError_t e;
+    if ((e = launch_build_cell_row(coords, coords_is_float != 0, m, m_dev, n_frames, nx, ny, cell_row, st)) != cudaSuccess)
+        return cuda_fail(e, "build_cell_row");
+    if ((e = launch_scatter(feats, cell_row, n_frames, f, nx, ny, bev, variant, st)) != cudaSuccess)
+        return cuda_fail(e, "scatter");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+}  // extern "C"

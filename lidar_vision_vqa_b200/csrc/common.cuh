@@ -1,0 +1,178 @@
+// Shared definitions for libpillars_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pillars_b200.h"
+
+namespace pillars {
+
+// ------------------------------------------------------------------------------------------------
+// Pillar hash table (open addressing, linear probing, HBM resident; 16 B entries so the three atomics of an insert hit
+// one 32 B sector).  Initialised by a single 0xFF memset:
+//   key   = 0xFFFFFFFF  -> empty
+//   first = 0xFFFFFFFF  -> atomicMin target: smallest point index that hit the cell
+//   cnt   = 0xFFFFFFFF  -> "count - 1": atomicAdd(cnt, k) returns old; old + 1 is the arrival rank base
+//   gid   = pillar id in first-appearance order over the whole batch (written by the scan kernel)
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) HashEntry {
+    uint32_t key;
+    uint32_t first;
+    uint32_t cnt;
+    uint32_t gid;
+};
+static constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+
+// small zero-initialised header at the start of the workspace
+struct Header {
+    uint32_t tile_counter;   // dynamic tile ids of the chained scan
+    uint32_t total_pillars;  // G: distinct occupied cells over the batch, before the max_voxels cap
+    uint32_t total_listed;   // points that fell into some cell (sum of all counts)
+    uint32_t pad[13];
+};
+
+static constexpr int kMaxFrames = 1024;  // frame_offsets are staged in shared memory
+static constexpr int kTile = 1024;       // points per CTA tile in the point-parallel kernels
+
+struct Workspace {
+    // zero-initialised region
+    Header *hdr;
+    unsigned long long *tile_desc;  // [n_tiles] chained-scan descriptors
+    uint32_t *frame_gstart;         // [B+1] first-appearance id at each frame start (uncapped, batch-global)
+    uint32_t *frame_rowbase;        // [B+1] output row at each frame start (after the max_voxels cap)
+    size_t zero_bytes;
+    // 0xFF-initialised region
+    HashEntry *table;               // [cap]
+    int32_t *cell_row;              // [B * ny * nx] dense BEV index map, -1 = empty
+    size_t ff_bytes;
+    // no init needed
+    int32_t *point_slot;            // [n] hash slot of each point, -1 = rejected
+    uint32_t *point_arrival;        // [n] arrival rank inside the cell (arbitrary order, only a bijection)
+    uint32_t *pillar_key;           // [n] cell key of pillar g
+    uint32_t *pillar_list;          // [n] start of pillar g's point list
+    uint32_t *pillar_cnt;           // [n] points that fell into pillar g (uncapped)
+    uint32_t *sorted_idx;           // [n] point indices grouped by pillar
+    uint32_t cap;                   // hash slots
+    uint32_t n_tiles;
+    size_t total_bytes;
+    char *zero_begin;
+    char *ff_begin;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+__host__ __device__ __forceinline__ T tmin(T a, T b)
+{
+    return a < b ? a : b;
+}
+
+// Carves `base` (may be nullptr to only size it).  n = total points, nb = frames, cells_xy = ny*nx.
+inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy)
+{
+    Workspace w{};
+    char *p = reinterpret_cast<char *>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *r = p ? p + off : nullptr;
+        off += align_up(bytes, 256);
+        return r;
+    };
+    w.n_tiles = static_cast<uint32_t>((n + kTile - 1) / kTile);
+    uint64_t cap = static_cast<uint64_t>(n) + static_cast<uint64_t>(n) / 2 + 64;  // load factor <= 2/3 worst case
+    w.cap = static_cast<uint32_t>(cap);
+    w.zero_begin = p ? p : nullptr;
+    w.hdr = reinterpret_cast<Header *>(take(sizeof(Header)));
+    w.tile_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
+    w.frame_gstart = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+    w.frame_rowbase = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+    w.zero_bytes = off;
+    w.ff_begin = p ? p + off : nullptr;
+    size_t ff0 = off;
+    w.table = reinterpret_cast<HashEntry *>(take(n > 0 ? sizeof(HashEntry) * cap : 0));
+    w.cell_row = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * static_cast<size_t>(nb) * cells_xy));
+    w.ff_bytes = off - ff0;
+    w.point_slot = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * n));
+    w.point_arrival = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
+    w.pillar_key = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
+    w.pillar_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
+    w.pillar_cnt = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
+    w.sorted_idx = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
+    w.total_bytes = off;
+    return w;
+}
+
+// Device-side copy of pillars_grid_t plus derived integers.
+struct GridDev {
+    float rmin[3];
+    float vsz[3];
+    int32_t g[3];       // nx ny nz
+    int32_t max_points;
+    int32_t max_voxels;
+    uint32_t cells;     // nx*ny*nz
+    uint32_t cells_xy;  // nx*ny
+};
+
+inline GridDev make_grid_dev(const pillars_grid_t &g)
+{
+    GridDev d;
+    for (int i = 0; i < 3; ++i) {
+        d.rmin[i] = g.range[i];
+        d.vsz[i] = g.voxel[i];
+        d.g[i] = g.grid[i];
+    }
+    d.max_points = g.max_points;
+    d.max_voxels = g.max_voxels;
+    d.cells_xy = static_cast<uint32_t>(g.grid[0]) * static_cast<uint32_t>(g.grid[1]);
+    d.cells = d.cells_xy * static_cast<uint32_t>(g.grid[2]);
+    return d;
+}
+
+struct PfnDev {
+    const float *weight;  // [F, C_in]
+    const float *scale;   // [F]
+    const float *shift;   // [F]
+    float off[3];
+    float vsz[3];
+};
+
+// launch bookkeeping (api.cu)
+void note_launch(int n = 1);
+
+// ---- launchers implemented in the kernel translation units ---------------------------------------
+cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, int nb, int32_t *offs, cudaStream_t st);
+
+cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, const int32_t *frame_offsets,
+                                int nb, const GridDev &gd, const Workspace &ws, int32_t *pillar_count,
+                                cudaStream_t st);
+
+struct FeatureJob {
+    const float *points;
+    int64_t n;
+    int stride;
+    int col0;
+    int c_point;
+    int nb;
+    int idx_bits;              // bits needed to hold a point index
+    bool use_abs;
+    bool with_dist;
+    bool do_features;          // run the PFN (needs pfn + pillar_features)
+    PfnDev pfn;
+    int c_in;
+    int f_out;
+    pillars_outputs_t out;     // by value; NULL members are skipped
+    bool write_cell_row;       // fill ws.cell_row for the BEV scatter
+};
+cudaError_t launch_pillar_features(const FeatureJob &job, const GridDev &gd, const Workspace &ws, cudaStream_t st);
+
+cudaError_t launch_pfn_dense(const float *voxels, const void *num_points, bool np_float, const void *coords,
+                             bool coords_float, int64_t m, int max_points, int c_point, int c_in, int f_out,
+                             bool use_abs, bool with_dist, const PfnDev &pfn, float *out, cudaStream_t st);
+
+cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t m, const int32_t *m_dev, int nb, int nx,
+                                  int ny, int32_t *cell_row, cudaStream_t st);
+cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, int f, int nx, int ny, float *bev,
+                           int variant, cudaStream_t st);
+
+}  // namespace pillars

@@ -1,0 +1,271 @@
+// Dense BEV canvas in "gather form" (replaces PointPillarScatter.forward,
+// src/lidar-encoder/pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37).
+//
+// The reference zero-fills a [F, ny*nx] canvas per frame, index-assigns F strided 4-byte columns per pillar and then
+// stacks the frames (a third full pass).  Here a dense index map cell -> pillar row (4 B per cell, written by the
+// feature kernel or by k_build_cell_row) turns the scatter inside out: every output element is written exactly once,
+// in NCHW order, with full-line stores, zero-fill included, no atomics.
+//
+// Three store paths over the same tiling (256 cells x F channels per tile), selectable for measurement:
+//   1 plain   : st.global.v4 from registers
+//   2 bulk1d  : the tile lives in shared memory ([F][256] floats, all zero except occupied cells); F threads each issue
+//               one cp.async.bulk.global.shared::cta row copy (UBLKCP).  An all-empty tile is stored straight from the
+//               resident zero tile without touching shared memory.
+//   3 tma2d   : same tile, one cp.async.bulk.tensor.2d store per tile through a CUtensorMap over the canvas viewed as
+//               [B*F rows, ny*nx cells] (UTMASTG).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pillars {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileCells = 256;
+
+__global__ void k_build_cell_row(const void *__restrict__ coords, int coords_float, int64_t m,
+                                 const int32_t *__restrict__ m_dev, int nb, int nx, int ny, int32_t *__restrict__ cell_row)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t live = m;
+    if (m_dev) live = tmin<int64_t>(m, static_cast<int64_t>(*m_dev));
+    if (i >= live) return;
+    int b, z, y, x;
+    if (coords_float) {
+        const float4 c = *reinterpret_cast<const float4 *>(static_cast<const float *>(coords) + i * 4);
+        b = static_cast<int>(c.x); z = static_cast<int>(c.y); y = static_cast<int>(c.z); x = static_cast<int>(c.w);
+    } else {
+        const int4 c = *reinterpret_cast<const int4 *>(static_cast<const int32_t *>(coords) + i * 4);
+        b = c.x; z = c.y; y = c.z; x = c.w;
+    }
+    // pointpillar_scatter.py:27  index = z + y*nx + x  (nz == 1, so z == 0)
+    const int64_t cell = static_cast<int64_t>(z) + static_cast<int64_t>(y) * nx + x;
+    if (b < 0 || b >= nb || cell < 0 || cell >= static_cast<int64_t>(nx) * ny) return;
+    atomicMax(cell_row + static_cast<int64_t>(b) * nx * ny + cell, static_cast<int32_t>(i));  // later row wins
+}
+
+// ---- variant 1 ----------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_plain(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
+                int tiles_per_plane, float *__restrict__ bev)
+{
+    constexpr int kPer = VEC ? 4 : 1;
+    const int b = blockIdx.x / tiles_per_plane;
+    const int64_t cell0 = static_cast<int64_t>(blockIdx.x % tiles_per_plane) * (kThreads * kPer) + threadIdx.x * kPer;
+    if (cell0 >= plane) return;
+    int32_t r[kPer];
+    if (VEC) {
+        const int4 v = *reinterpret_cast<const int4 *>(cell_row + b * plane + cell0);
+        r[0] = v.x; r[1 % kPer] = v.y; r[2 % kPer] = v.z; r[3 % kPer] = v.w;
+    } else {
+        r[0] = cell_row[b * plane + cell0];
+    }
+    float *dst = bev + (static_cast<int64_t>(b) * f) * plane + cell0;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) any |= r[k] >= 0;
+    if (!any) {
+        for (int c = 0; c < f; ++c) {
+            if (VEC) __stcs(reinterpret_cast<float4 *>(dst + c * plane), make_float4(0.f, 0.f, 0.f, 0.f));
+            else dst[c * plane] = 0.f;
+        }
+        return;
+    }
+    for (int c = 0; c < f; ++c) {
+        float v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) v[k] = r[k] >= 0 ? __ldg(feats + static_cast<int64_t>(r[k]) * f + c) : 0.f;
+        if (VEC) __stcs(reinterpret_cast<float4 *>(dst + c * plane), make_float4(v[0], v[1 % kPer], v[2 % kPer], v[3 % kPer]));
+        else dst[c * plane] = v[0];
+    }
+}
+
+// ---- async-proxy helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_1d(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void *ssrc, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(ssrc)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// ---- variants 2 and 3 ---------------------------------------------------------------------------
+// Shared-memory tile [f][256]; invariant between tiles: all zero.
+template <bool TMA2D>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
+                int tiles_per_plane, int64_t n_tiles, float *__restrict__ bev, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) float s_tile[];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < f * kTileCells; i += kThreads) s_tile[i] = 0.f;
+    fence_proxy_async();
+    __syncthreads();
+
+    const bool issuer = TMA2D ? (tid == 0) : (tid < f);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int b = static_cast<int>(t / tiles_per_plane);
+        const int64_t cell0 = (t % tiles_per_plane) * kTileCells;
+        const int ncell = static_cast<int>(tmin<int64_t>(kTileCells, plane - cell0));
+        const int32_t r = (tid < ncell) ? __ldg(cell_row + b * plane + cell0 + tid) : -1;
+        const int any = __syncthreads_or(r >= 0);
+        if (any) {
+            if (issuer) bulk_wait_read_all();  // earlier stores still read the zero tile
+            __syncthreads();
+            if (r >= 0) {
+                const float4 *src = reinterpret_cast<const float4 *>(feats + static_cast<int64_t>(r) * f);
+                for (int c = 0; c < f; c += 4) {
+                    const float4 v = __ldg(src + (c >> 2));
+                    s_tile[(c + 0) * kTileCells + tid] = v.x;
+                    s_tile[(c + 1) * kTileCells + tid] = v.y;
+                    s_tile[(c + 2) * kTileCells + tid] = v.z;
+                    s_tile[(c + 3) * kTileCells + tid] = v.w;
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
+        if (TMA2D) {
+            if (tid == 0) {
+                tma_store_2d(&tmap, s_tile, static_cast<int>(cell0), b * f);
+                bulk_commit();
+            }
+        } else if (tid < f) {
+            bulk_store_1d(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, s_tile + tid * kTileCells,
+                          static_cast<uint32_t>(ncell) * 4u);
+            bulk_commit();
+        }
+        if (any) {
+            if (issuer) bulk_wait_read_all();
+            __syncthreads();
+            if (r >= 0)
+                for (int c = 0; c < f; ++c) s_tile[c * kTileCells + tid] = 0.f;
+            fence_proxy_async();
+            // the next tile's __syncthreads_or orders these writes before any later store is issued
+        }
+    }
+    if (issuer) bulk_wait_all();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int sm_count()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace
+
+cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t m, const int32_t *m_dev, int nb, int nx,
+                                  int ny, int32_t *cell_row, cudaStream_t st)
+{
+    cudaError_t err = cudaMemsetAsync(cell_row, 0xFF, sizeof(int32_t) * static_cast<size_t>(nb) * nx * ny, st);
+    note_launch();
+    if (err != cudaSuccess || m == 0) return err;
+    const unsigned blocks = static_cast<unsigned>((m + kThreads - 1) / kThreads);
+    k_build_cell_row<<<blocks, kThreads, 0, st>>>(coords, coords_float ? 1 : 0, m, m_dev, nb, nx, ny, cell_row);
+    note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, int f, int nx, int ny, float *bev,
+                           int variant, cudaStream_t st)
+{
+    const int64_t plane = static_cast<int64_t>(nx) * ny;
+    if (nb == 0 || plane == 0 || f == 0) return cudaSuccess;
+    const bool vec_ok = (plane % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0) &&
+                        (reinterpret_cast<uintptr_t>(feats) % 16 == 0) && (f % 4 == 0);
+    const size_t smem = sizeof(float) * f * kTileCells;
+    const bool async_ok = vec_ok && f <= kThreads && smem <= 200 * 1024;
+    if (variant == 0) variant = async_ok ? 3 : 1;
+    if ((variant == 2 || variant == 3) && !async_ok) variant = 1;
+    if (variant == 3 && !get_encode_fn()) variant = 2;
+
+    if (variant == 1) {
+        if (vec_ok) {
+            const int tpp = static_cast<int>((plane + kThreads * 4 - 1) / (kThreads * 4));
+            k_scatter_plain<true><<<static_cast<unsigned>(nb) * tpp, kThreads, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+        } else {
+            const int tpp = static_cast<int>((plane + kThreads - 1) / kThreads);
+            k_scatter_plain<false><<<static_cast<unsigned>(nb) * tpp, kThreads, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+        }
+        note_launch();
+        return cudaGetLastError();
+    }
+
+    const int tpp = static_cast<int>((plane + kTileCells - 1) / kTileCells);
+    const int64_t n_tiles = static_cast<int64_t>(nb) * tpp;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (variant == 3) {
+        const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(plane), static_cast<cuuint64_t>(nb) * f};
+        const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(plane) * sizeof(float)};
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileCells), static_cast<cuuint32_t>(f)};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bev, gdim, gstride, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) variant = 2;
+    }
+    int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const int64_t grid = tmin<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * per_sm);
+    if (variant == 3) {
+        static bool attr3 = false;
+        if (!attr3) {
+            cudaFuncSetAttribute(k_scatter_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr3 = true;
+        }
+        k_scatter_async<true><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(feats, cell_row, f, plane, tpp, n_tiles,
+                                                                                  bev, tmap);
+    } else {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(k_scatter_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr2 = true;
+        }
+        k_scatter_async<false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(feats, cell_row, f, plane, tpp, n_tiles,
+                                                                                   bev, tmap);
+    }
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace pillars

@@ -1,0 +1,224 @@
+"""Drop-in modules for the pillar path, mirroring the reference's operator interface (names, constructor kwargs,
+``forward(batch_dict) -> batch_dict``, state-dict keys) so they can be registered in pcdet's registries unchanged:
+
+  reference (src/lidar-encoder/pcdet/...)                                  here
+  models/backbones_3d/vfe/vfe_template.py:4-22        VFETemplate            VFETemplate
+  models/backbones_3d/vfe/pillar_vfe.py:8-49          PFNLayer               PFNLayer (parameter container)
+  models/backbones_3d/vfe/pillar_vfe.py:52-123        PillarVFE              PillarVFE        ('voxels' input)
+  models/backbones_3d/vfe/dynamic_pillar_vfe.py:49-142 (point-input contract) PillarVFEFromPoints ('points' input,
+                                                                              hard-voxeliser semantics, fused grouping)
+  models/backbones_2d/map_to_bev/pointpillar_scatter.py:5-37  PointPillarScatter  PointPillarScatter
+
+Inference only: BatchNorm is folded from the running statistics, so ``forward`` raises in training mode.
+The compute is in libpillars_b200.so; a missing library or a non-sm_100 device raises (no eager fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._native import NativeLibraryError
+
+
+_MISSING = object()
+
+
+def _cfg_get(cfg, key, default=_MISSING):
+    """EasyDict-style attribute access, plain dicts and dict subclasses whose __getattr__ raises KeyError."""
+    try:
+        return getattr(cfg, key)
+    except (AttributeError, KeyError):
+        pass
+    if isinstance(cfg, dict) and key in cfg:
+        return cfg[key]
+    if default is _MISSING:
+        raise AttributeError(f"model_cfg has no {key}")
+    return default
+
+
+class VFETemplate(nn.Module):
+    def __init__(self, model_cfg, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+
+    def get_output_feature_dim(self):
+        raise NotImplementedError
+
+    def forward(self, **kwargs):
+        raise NotImplementedError
+
+
+class PFNLayer(nn.Module):
+    """Holds ``linear`` / ``norm`` exactly like pillar_vfe.py:9-27 so reference checkpoints load by key and shape.
+    It has no eager forward: the owning VFE folds it and calls the fused kernel."""
+
+    def __init__(self, in_channels, out_channels, use_norm=True, last_layer=False):
+        super().__init__()
+        self.last_vfe = last_layer
+        self.use_norm = use_norm
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        if self.use_norm:
+            self.linear = nn.Linear(in_channels, out_channels, bias=False)
+            self.norm = nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01)
+        else:
+            self.linear = nn.Linear(in_channels, out_channels, bias=True)
+
+    def forward(self, inputs):  # pragma: no cover
+        raise NativeLibraryError("PFNLayer has no eager path; call the owning VFE (libpillars_b200.so)")
+
+
+class _PillarVFEBase(VFETemplate):
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size=None, **kwargs):
+        super().__init__(model_cfg=model_cfg)
+        self.use_norm = _cfg_get(model_cfg, "USE_NORM")
+        self.with_distance = _cfg_get(model_cfg, "WITH_DISTANCE")
+        self.use_absolute_xyz = _cfg_get(model_cfg, "USE_ABSLOTE_XYZ")
+        self.num_raw_point_features = int(num_point_features)
+        num_point_features += 6 if self.use_absolute_xyz else 3
+        if self.with_distance:
+            num_point_features += 1
+        self.num_filters = list(_cfg_get(model_cfg, "NUM_FILTERS"))
+        assert len(self.num_filters) > 0
+        num_filters = [num_point_features] + list(self.num_filters)
+        layers = []
+        for i in range(len(num_filters) - 1):
+            layers.append(PFNLayer(num_filters[i], num_filters[i + 1], self.use_norm,
+                                   last_layer=(i >= len(num_filters) - 2)))
+        self.pfn_layers = nn.ModuleList(layers)
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in np.asarray(point_cloud_range).tolist()]
+        self.voxel_x, self.voxel_y, self.voxel_z = self.voxel_size
+        self.x_offset = self.voxel_x / 2 + self.point_cloud_range[0]
+        self.y_offset = self.voxel_y / 2 + self.point_cloud_range[1]
+        self.z_offset = self.voxel_z / 2 + self.point_cloud_range[2]
+        self.grid_size = None if grid_size is None else [int(v) for v in np.asarray(grid_size).tolist()]
+        self._folded = None
+        self._folded_key = None
+
+    def get_output_feature_dim(self):
+        return self.num_filters[-1]
+
+    def _params(self, device) -> ops.PfnParams:
+        if self.training:
+            raise RuntimeError("the B200 pillar path is inference-only (BatchNorm is folded from running statistics); "
+                               "call .eval()")
+        if len(self.pfn_layers) != 1:
+            raise NotImplementedError("multi-layer PFN (NUM_FILTERS with more than one entry) is not built yet")
+        layer = self.pfn_layers[0]
+        tensors = [layer.linear.weight] + ([layer.norm.weight, layer.norm.bias, layer.norm.running_mean,
+                                            layer.norm.running_var] if self.use_norm else [layer.linear.bias])
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._folded is None or key != self._folded_key:
+            bn = None
+            if self.use_norm:
+                bn = (layer.norm.weight, layer.norm.bias, layer.norm.running_mean, layer.norm.running_var,
+                      layer.norm.eps)
+            self._folded = ops.fold_pfn(layer.linear.weight, bn, None if self.use_norm else layer.linear.bias,
+                                        c_point=self.num_raw_point_features, use_absolute_xyz=self.use_absolute_xyz,
+                                        with_distance=self.with_distance, voxel_size=self.voxel_size,
+                                        point_cloud_range=self.point_cloud_range, device=device)
+            self._folded_key = key
+        return self._folded
+
+
+class PillarVFE(_PillarVFEBase):
+    """Reads ``voxels [M,P,C]``, ``voxel_num_points [M]``, ``voxel_coords [M,4] (b,z,y,x)`` (fp32 after
+    ``load_data_to_gpu``, models/__init__.py:36, or int32) and writes ``pillar_features`` -- pillar_vfe.py:94-123."""
+
+    def forward(self, batch_dict, **kwargs):
+        voxels = batch_dict["voxels"]
+        feats = ops.pfn_dense(voxels, batch_dict["voxel_num_points"], batch_dict["voxel_coords"],
+                              self._params(voxels.device), self.voxel_size)
+        batch_dict["pillar_features"] = feats.squeeze()  # pillar_vfe.py:121 (M == 1 collapses to [F] there too)
+        return batch_dict
+
+
+def _mode_value(v, training: bool):
+    if isinstance(v, dict) or hasattr(v, "keys"):
+        return int(v["train" if training else "test"])
+    return int(v)
+
+
+class PillarVFEFromPoints(_PillarVFEBase):
+    """Point-input variant: reads ``points [N, 1+C] (b,x,y,z,...)`` like DynamicPillarVFE (dynamic_pillar_vfe.py:90-91)
+    but groups with the HARD voxeliser's semantics (first-appearance ids, first ``MAX_POINTS_PER_VOXEL`` points, at most
+    ``MAX_NUMBER_OF_VOXELS`` pillars per frame), so its output equals ``transform_points_to_voxels`` + ``PillarVFE``.
+    Writes ``pillar_features``, ``voxel_features`` (alias), ``voxel_coords [M,4] int32``, ``voxel_num_points``; with
+    ``FUSE_SCATTER`` also ``spatial_features`` (the scatter then becomes a no-op).
+
+    Extra model_cfg keys (all optional): MAX_POINTS_PER_VOXEL (32), MAX_NUMBER_OF_VOXELS (40000, int or
+    {'train','test'}), FUSE_SCATTER (False), SCATTER_VARIANT ('auto')."""
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size, **kwargs):
+        super().__init__(model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size, **kwargs)
+        self.max_points = int(_cfg_get(model_cfg, "MAX_POINTS_PER_VOXEL", 32))
+        self.max_voxels = _mode_value(_cfg_get(model_cfg, "MAX_NUMBER_OF_VOXELS", 40000), training=False)
+        self.fuse_scatter = bool(_cfg_get(model_cfg, "FUSE_SCATTER", False))
+        self.scatter_variant = str(_cfg_get(model_cfg, "SCATTER_VARIANT", "auto"))
+        self.grid = ops.GridSpec(self.point_cloud_range, self.voxel_size, self.grid_size, self.max_points,
+                                 self.max_voxels)
+
+    def forward(self, batch_dict, **kwargs):
+        points = batch_dict["points"]
+        if not points.is_cuda:  # host batch (pinned or not): the H2D copy is part of the call
+            points = points.cuda(non_blocking=True)
+        points = points.contiguous()
+        batch_size = int(batch_dict["batch_size"])
+        offs = ops.frame_offsets_from_points(points, batch_size)
+        res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=1,
+                             with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
+        m = int(res["pillar_count"][-1].item())  # the one host sync: sizes the returned views (cf. pointpillar_scatter.py:17)
+        if m > res["pillar_features"].shape[0]:
+            raise RuntimeError("pillar capacity overflow")
+        batch_dict["voxel_features"] = batch_dict["pillar_features"] = res["pillar_features"][:m]
+        batch_dict["voxel_coords"] = res["voxel_coords"][:m]
+        batch_dict["voxel_num_points"] = res["voxel_num_points"][:m]
+        batch_dict["pillars_per_frame"] = res["pillar_count"][:-1]
+        if self.fuse_scatter:
+            batch_dict["spatial_features"] = res["bev"]
+            batch_dict["_b200_scatter_done"] = True
+        return batch_dict
+
+
+class PointPillarScatter(nn.Module):
+    """pointpillar_scatter.py:5-37.  ``batch_dict['batch_size']`` is used when present (the reference derives the
+    batch from ``coords[:,0].max()+1`` with a host sync, :17 -- identical unless trailing frames are empty)."""
+
+    def __init__(self, model_cfg, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.num_bev_features = _cfg_get(model_cfg, "NUM_BEV_FEATURES")
+        self.nx, self.ny, self.nz = (int(v) for v in np.asarray(grid_size).tolist())
+        assert self.nz == 1
+        self.variant = str(_cfg_get(model_cfg, "SCATTER_VARIANT", "auto"))
+
+    def forward(self, batch_dict, **kwargs):
+        if batch_dict.get("_b200_scatter_done", False) and "spatial_features" in batch_dict:
+            return batch_dict
+        feats, coords = batch_dict["pillar_features"], batch_dict["voxel_coords"]
+        if "batch_size" in batch_dict:
+            batch_size = int(batch_dict["batch_size"])
+        else:
+            batch_size = int(coords[:, 0].max().int().item()) + 1
+        if feats.shape[-1] != self.num_bev_features:
+            raise ValueError(f"pillar_features have {feats.shape[-1]} channels, NUM_BEV_FEATURES={self.num_bev_features}")
+        batch_dict["spatial_features"] = ops.scatter_bev(feats, coords, batch_size, self.nx, self.ny,
+                                                         variant=self.variant)
+        return batch_dict
+
+
+# name-keyed registries shaped like pcdet's (models/backbones_3d/vfe/__init__.py:9-18,
+# models/backbones_2d/map_to_bev/__init__.py:5-10); INTEGRATION.md shows the two-line merge into them.
+VFE_REGISTRY = {
+    "VFETemplate": VFETemplate,
+    "PillarVFE": PillarVFE,
+    "PillarVFEFromPoints": PillarVFEFromPoints,
+}
+MAP_TO_BEV_REGISTRY = {
+    "PointPillarScatter": PointPillarScatter,
+}

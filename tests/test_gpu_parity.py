@@ -1,0 +1,400 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against the CPU oracle
+on identical seeded inputs and against the golden vectors produced by the reference modules.
+
+Bars (BASELINE.json north_star): voxel coordinates, pillar ids and point->pillar membership BIT-EXACT;
+pillar features and BEV tokens within rtol 1e-3 (fp32).  ``FEAT_RTOL``/``FEAT_ATOL`` below are that tolerance; the
+observed error is ~1e-6, so the tests also assert a much tighter "expected" bound to catch regressions early.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, vfe_golden_names
+from lidar_vision_vqa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FEAT_RTOL = 1e-3   # the north_star tolerance
+FEAT_ATOL = 1e-5   # exact zeros in empty cells are compared exactly elsewhere
+TIGHT_RTOL, TIGHT_ATOL = 2e-5, 2e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lidar_vision_vqa_b200 as pkg
+    from lidar_vision_vqa_b200 import ops
+
+    pkg.ops = ops
+    return pkg
+
+
+def _sd_t(g):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in g["state_dict"].items()}
+
+
+def _trim(res):
+    m = int(res["pillar_count"][-1].item())
+    out = {}
+    for k, v in res.items():
+        if k in ("voxel_coords", "voxel_num_points", "voxels", "pillar_features"):
+            out[k] = v[:m].cpu().numpy()
+        elif k != "bev":
+            out[k] = v.cpu().numpy()
+    out["m"] = m
+    return out
+
+
+GROUP_CASES = {
+    # name: (frames, sweep model, C, range, voxel, P, max_voxels, points kept per frame)
+    "small_p32": (2, synth.NUSCENES_32, 5, (-12.8, -12.8, -5, 12.8, 12.8, 3), (0.4, 0.4, 8), 32, 4000, 3000),
+    "cap_binds_p4": (3, synth.NUSCENES_32, 5, (-12.8, -12.8, -5, 12.8, 12.8, 3), (0.4, 0.4, 8), 4, 4000, 4000),
+    "maxvox_binds": (3, synth.NUSCENES_32, 4, (-12.8, -12.8, -5, 12.8, 12.8, 3), (0.4, 0.4, 8), 8, 150, 4000),
+    "p1_maxvox1": (2, synth.NUSCENES_32, 5, (-12.8, -12.8, -5, 12.8, 12.8, 3), (0.4, 0.4, 8), 1, 1, 500),
+    "cfg1_full_sweep": (1, synth.NUSCENES_32, 5, (-51.2, -51.2, -5, 51.2, 51.2, 3), (0.2, 0.2, 8), 32, 30000, None),
+    "cfg1_p20": (2, synth.NUSCENES_32, 5, (-51.2, -51.2, -5, 51.2, 51.2, 3), (0.2, 0.2, 8), 20, 30000, None),
+    "tenSweep_maxvox30000_binds": (1, synth.NUSCENES_10SWEEP, 5, (-51.2, -51.2, -5, 51.2, 51.2, 3), (0.2, 0.2, 8), 32,
+                                   30000, None),
+    "waymo_0.1m": (1, synth.WAYMO_64, 5, (-51.2, -51.2, -2, 51.2, 51.2, 4), (0.1, 0.1, 6), 32, 200000, None),
+    "3d_voxels_nz8": (2, synth.NUSCENES_32, 5, (-12.8, -12.8, -5, 12.8, 12.8, 3), (0.4, 0.4, 1.0), 5, 4000, 3000),
+}
+
+
+def _make_case(name):
+    nb, model, c, rng, vs, p, mv, keep = GROUP_CASES[name]
+    frames = []
+    for b in range(nb):
+        f = synth.make_sweep(1000 + 17 * b + len(name), model, c)
+        if keep is not None:
+            f = f[np.hypot(f[:, 0], f[:, 1]) < 19.0][:keep]
+        frames.append(f)
+    offs = np.zeros(nb + 1, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    return np.concatenate(frames, 0), offs, rng, vs, p, mv
+
+
+@pytest.mark.parametrize("name", list(GROUP_CASES))
+def test_grouping_bit_exact(name, dev, L, oracle):
+    pts, offs, rng, vs, p, mv = _make_case(name)
+    grid = L.GridSpec.from_range(rng, vs, p, mv)
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    res = L.ops.voxelize(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid, want_voxels=True,
+                         want_membership=True)
+    got = _trim(res)
+    np.testing.assert_array_equal(got["pillar_count"][:-1], ref["pillars_per_frame"])
+    assert got["m"] == ref["coords"].shape[0]
+    np.testing.assert_array_equal(got["voxel_coords"], ref["coords"])
+    np.testing.assert_array_equal(got["voxel_num_points"], ref["num_points"])
+    np.testing.assert_array_equal(got["point_pillar"], ref["point_voxel"])
+    np.testing.assert_array_equal(got["point_slot"], ref["point_slot"])
+    np.testing.assert_array_equal(got["voxels"].view(np.uint32), ref["voxels"].view(np.uint32))
+
+
+def test_grouping_pcdet_layout_and_frame_offsets(dev, L, oracle):
+    """The collated [N, 1+C] layout with the frame index in column 0, including an empty middle frame."""
+    pts, offs, rng, vs, p, mv = _make_case("small_p32")
+    offs3 = np.array([offs[0], offs[1], offs[1], offs[2]], np.int32)  # frame 1 is empty
+    pb = np.empty((len(pts), 6), np.float32)
+    pb[:, 1:] = pts
+    pb[:offs[1], 0] = 0
+    pb[offs[1]:, 0] = 2
+    t = torch.from_numpy(pb).to(dev)
+    got_offs = L.ops.frame_offsets_from_points(t, 3)
+    np.testing.assert_array_equal(got_offs.cpu().numpy(), offs3)
+    grid = L.GridSpec.from_range(rng, vs, p, mv)
+    res = _trim(L.ops.voxelize(t, got_offs, grid, col0=1, want_voxels=True, want_membership=True))
+    ref = oracle.voxelize_batch(pts, offs3, rng, vs, p, mv)
+    np.testing.assert_array_equal(res["voxel_coords"], ref["coords"])
+    np.testing.assert_array_equal(res["point_slot"], ref["point_slot"])
+    np.testing.assert_array_equal(res["voxels"], ref["voxels"])
+    np.testing.assert_array_equal(res["pillar_count"][:-1], ref["pillars_per_frame"])
+
+
+def test_grouping_edge_cases(dev, L, oracle):
+    rng, vs = (0.0, 0.0, 0.0, 4.0, 4.0, 2.0), (1.0, 1.0, 2.0)
+    grid = L.GridSpec.from_range(rng, vs, 4, 10)
+    # boundaries, non-finite values, duplicates
+    pts = np.array([[0, 0, 0, 1, 0], [4.0, 1, 1, 2, 0], [3.9999998, 1, 1, 3, 0], [1, 1, 2.0, 4, 0],
+                    [-1e-7, 1, 1, 5, 0], [np.nan, 1, 1, 6, 0], [1, np.inf, 1, 7, 0], [0.5, 0.5, 0.5, 8, 0],
+                    [0.5, 0.5, 0.5, 8, 0]], np.float32)
+    offs = np.array([0, len(pts)], np.int32)
+    got = _trim(L.ops.voxelize(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid,
+                               want_membership=True))
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, 4, 10)
+    for k, rk in (("voxel_coords", "coords"), ("voxel_num_points", "num_points"), ("point_pillar", "point_voxel"),
+                  ("point_slot", "point_slot"), ("voxels", "voxels")):
+        np.testing.assert_array_equal(got[k], ref[rk], err_msg=k)
+    # no points at all / nothing in range / several empty frames
+    for arr, o in ((np.zeros((0, 5), np.float32), [0, 0, 0]), (np.full((7, 5), 100.0, np.float32), [0, 3, 7]),
+                   (pts, [0, 0, len(pts), len(pts)])):
+        o = np.asarray(o, np.int32)
+        got = _trim(L.ops.voxelize(torch.from_numpy(arr).to(dev), torch.from_numpy(o).to(dev), grid,
+                                   want_membership=True))
+        ref = oracle.voxelize_batch(arr, o, rng, vs, 4, 10)
+        assert got["m"] == ref["coords"].shape[0]
+        np.testing.assert_array_equal(got["pillar_count"][:-1], ref["pillars_per_frame"])
+        np.testing.assert_array_equal(got["voxel_coords"], ref["coords"])
+        np.testing.assert_array_equal(got["point_slot"], ref["point_slot"])
+
+
+def test_grouping_one_huge_pillar_and_many_frames(dev, L, oracle):
+    """20 000 points in one cell (cap 32 -> radix select over a long list) and 40 tiny frames (> one warp of frames)."""
+    rng, vs = (0.0, 0.0, 0.0, 8.0, 8.0, 2.0), (1.0, 1.0, 2.0)
+    r = np.random.default_rng(5)
+    big = np.concatenate([r.uniform(3.0, 4.0, (20000, 2)), r.uniform(0, 2, (20000, 1)), r.uniform(0, 1, (20000, 2))],
+                         1).astype(np.float32)
+    rest = np.concatenate([r.uniform(-1, 9, (6000, 2)), r.uniform(-0.5, 2.5, (6000, 1)), r.uniform(0, 1, (6000, 2))],
+                          1).astype(np.float32)
+    pts = np.concatenate([big, rest])[r.permutation(26000)]
+    cuts = np.sort(r.integers(0, 26000, 39))
+    offs = np.concatenate([[0], cuts, [26000]]).astype(np.int32)
+    grid = L.GridSpec.from_range(rng, vs, 32, 50)
+    got = _trim(L.ops.voxelize(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid,
+                               want_membership=True))
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, 32, 50)
+    np.testing.assert_array_equal(got["voxel_coords"], ref["coords"])
+    np.testing.assert_array_equal(got["voxel_num_points"], ref["num_points"])
+    np.testing.assert_array_equal(got["point_pillar"], ref["point_voxel"])
+    np.testing.assert_array_equal(got["point_slot"], ref["point_slot"])
+    np.testing.assert_array_equal(got["voxels"], ref["voxels"])
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors from the reference modules
+# ------------------------------------------------------------------------------------------------
+def _cfg(g):
+    from lidar_vision_vqa_b200.synth import GridConfig  # noqa: F401
+
+    class C(dict):
+        __getattr__ = dict.__getitem__
+
+    return C(USE_NORM=bool(g["use_norm"]), WITH_DISTANCE=bool(g["with_distance"]), USE_ABSLOTE_XYZ=bool(g["use_abs"]),
+             NUM_FILTERS=[int(v) for v in g["num_filters"]])
+
+
+SINGLE_LAYER = [n for n in vfe_golden_names() if "2layer" not in n]
+
+
+@pytest.mark.parametrize("name", SINGLE_LAYER)
+def test_pillar_vfe_module_vs_reference_golden(name, dev, L):
+    g = load_golden(name)
+    c = g["voxels"].shape[2]
+    vfe = L.PillarVFE(model_cfg=_cfg(g), num_point_features=c, voxel_size=list(g["voxel_size"]),
+                      point_cloud_range=g["range"], grid_size=g["grid_size"], depth_downsample_factor=None)
+    missing = vfe.load_state_dict(_sd_t(g), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    vfe.eval().to(dev)
+    bd = {"voxels": torch.from_numpy(g["voxels"]).to(dev),
+          "voxel_num_points": torch.from_numpy(g["voxel_num_points"]).to(dev),
+          "voxel_coords": torch.from_numpy(g["voxel_coords"]).to(dev), "batch_size": len(g["frame_offsets"]) - 1}
+    out = vfe(bd)["pillar_features"].cpu().numpy()
+    ref = g["out.pillar_features"]
+    assert out.shape == ref.shape  # includes the squeeze() of M == 1
+    np.testing.assert_allclose(out, ref, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+    np.testing.assert_allclose(out, ref, rtol=TIGHT_RTOL, atol=TIGHT_ATOL)
+
+
+@pytest.mark.parametrize("variant", ["plain", "bulk1d", "tma2d", "auto"])
+@pytest.mark.parametrize("name", [n for n in SINGLE_LAYER if n != "vfe_c5_m1"])
+def test_scatter_module_vs_reference_golden(name, variant, dev, L):
+    g = load_golden(name)
+
+    class C(dict):
+        __getattr__ = dict.__getitem__
+
+    sc = L.PointPillarScatter(model_cfg=C(NUM_BEV_FEATURES=64, SCATTER_VARIANT=variant), grid_size=g["grid_size"])
+    bd = {"pillar_features": torch.from_numpy(g["out.pillar_features"]).to(dev),
+          "voxel_coords": torch.from_numpy(g["voxel_coords"]).to(dev)}  # no batch_size: reference rule (coords max + 1)
+    bev = sc(bd)["spatial_features"].cpu().numpy()
+    ref = g["out.spatial_features"]
+    assert bev.shape == ref.shape
+    np.testing.assert_array_equal(bev.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", [n for n in SINGLE_LAYER if n != "vfe_c5_m1"])
+def test_fused_points_to_bev_vs_reference_golden(name, dev, L):
+    """points -> (grouping + PFN + scatter) in one call, against the reference modules' outputs."""
+    g = load_golden(name)
+    c = g["voxels"].shape[2]
+
+    class C(dict):
+        __getattr__ = dict.__getitem__
+
+    cfg = _cfg(g)
+    cfg.update(MAX_POINTS_PER_VOXEL=int(g["max_points"]), MAX_NUMBER_OF_VOXELS={"train": 1, "test": int(g["max_voxels"])},
+               FUSE_SCATTER=True)
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=c, voxel_size=list(g["voxel_size"]),
+                                point_cloud_range=g["range"], grid_size=g["grid_size"])
+    vfe.load_state_dict(_sd_t(g), strict=True)
+    vfe.eval().to(dev)
+    sc = L.PointPillarScatter(model_cfg=C(NUM_BEV_FEATURES=64), grid_size=g["grid_size"])
+    pb = synth.to_pcdet_points(g["points"], g["frame_offsets"])
+    bd = {"points": torch.from_numpy(pb).to(dev), "batch_size": len(g["frame_offsets"]) - 1}
+    bd = sc(vfe(bd))
+    np.testing.assert_array_equal(bd["voxel_coords"].cpu().numpy(), g["voxel_coords"].astype(np.int32))
+    np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), g["voxel_num_points"].astype(np.int32))
+    np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), g["out.pillar_features"], rtol=FEAT_RTOL,
+                               atol=FEAT_ATOL)
+    bev = bd["spatial_features"].cpu().numpy()
+    ref = g["out.spatial_features"]
+    # trailing empty frames: the reference sizes the batch from coords (pointpillar_scatter.py:17)
+    np.testing.assert_allclose(bev[:ref.shape[0]], ref, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+    assert (bev[ref.shape[0]:] == 0).all()
+    assert ((bev == 0) == (np.pad(ref, [(0, bev.shape[0] - ref.shape[0])] + [(0, 0)] * 3) == 0)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA path vs the oracle on fresh seeded inputs (sizes the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------------
+def _run_fused(L, dev, pts, offs, grid, sd, c, variant="auto", **kw):
+    pfn = L.ops.fold_pfn(sd["pfn_layers.0.linear.weight"],
+                         (sd["pfn_layers.0.norm.weight"], sd["pfn_layers.0.norm.bias"],
+                          sd["pfn_layers.0.norm.running_mean"], sd["pfn_layers.0.norm.running_var"], 1e-3), None,
+                         c_point=c, use_absolute_xyz=True, with_distance=False, voxel_size=grid.voxel_size,
+                         point_cloud_range=grid.point_cloud_range, device=dev)
+    return L.ops.encode_bev(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid, pfn,
+                            scatter_variant=variant, **kw)
+
+
+@pytest.mark.parametrize("name", ["cfg1_full_sweep", "cfg1_p20", "tenSweep_maxvox30000_binds", "waymo_0.1m",
+                                  "cap_binds_p4", "maxvox_binds"])
+def test_fused_path_vs_oracle(name, dev, L, oracle):
+    pts, offs, rng, vs, p, mv = _make_case(name)
+    c = pts.shape[1]
+    grid = L.GridSpec.from_range(rng, vs, p, mv)
+    sd = oracle.random_pfn_params(c + 6, [64], True, seed=3)
+    res = _run_fused(L, dev, pts, offs, grid, sd, c)
+    m = int(res["pillar_count"][-1].item())
+    ref_v = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    assert m == ref_v["coords"].shape[0]
+    np.testing.assert_array_equal(res["voxel_coords"][:m].cpu().numpy(), ref_v["coords"])
+    np.testing.assert_array_equal(res["voxel_num_points"][:m].cpu().numpy(), ref_v["num_points"])
+    ref_f = oracle.pillar_vfe(ref_v["voxels"], ref_v["num_points"], ref_v["coords"], sd, vs, rng).numpy()
+    got_f = res["pillar_features"][:m].cpu().numpy()
+    np.testing.assert_allclose(got_f, ref_f, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+    np.testing.assert_allclose(got_f, ref_f, rtol=1e-4, atol=1e-4)
+    nx, ny, _ = grid.grid_size
+    nb = len(offs) - 1
+    bev = res["bev"].cpu().numpy()
+    # the scatter itself moves bits: exact against the oracle scatter of OUR features ...
+    np.testing.assert_array_equal(bev, oracle.scatter_bev(got_f, ref_v["coords"], nx, ny, batch_size=nb))
+    # ... and within tolerance of the all-oracle canvas, with exactly the same empty cells
+    ref_bev = oracle.scatter_bev(ref_f, ref_v["coords"], nx, ny, batch_size=nb)
+    np.testing.assert_allclose(bev, ref_bev, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+
+
+def test_fused_path_c4_and_scatter_variants_agree(dev, L, oracle):
+    pts, offs, rng, vs, p, mv = _make_case("maxvox_binds")  # C = 4 (the product's nuScenes yaml)
+    grid = L.GridSpec.from_range(rng, vs, p, mv)
+    sd = oracle.random_pfn_params(10, [64], True, seed=4)
+    outs = {v: _run_fused(L, dev, pts, offs, grid, sd, 4, variant=v)["bev"].clone() for v in
+            ("plain", "bulk1d", "tma2d")}
+    assert torch.equal(outs["plain"], outs["bulk1d"])
+    assert torch.equal(outs["plain"], outs["tma2d"])
+    ref_v = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    ref_f = oracle.pillar_vfe(ref_v["voxels"], ref_v["num_points"], ref_v["coords"], sd, vs, rng).numpy()
+    ref_bev = oracle.scatter_bev(ref_f, ref_v["coords"], grid.grid_size[0], grid.grid_size[1], batch_size=len(offs) - 1)
+    np.testing.assert_allclose(outs["tma2d"].cpu().numpy(), ref_bev, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+
+
+def test_scatter_odd_shapes(dev, L, oracle):
+    """Grids that are not multiples of the 256-cell tile, of 4, and a channel count other than 64."""
+    r = np.random.default_rng(0)
+    for (nx, ny, f, nb) in ((432, 496, 64, 2), (100, 36, 32, 3), (37, 21, 64, 2), (64, 64, 128, 1)):
+        m = min(700, nx * ny // 3)
+        cells = np.stack([r.choice(nx * ny, m, replace=False) for _ in range(nb)])
+        coords = np.concatenate([np.stack([np.full(m, b), np.zeros(m, int), cells[b] // nx, cells[b] % nx], 1)
+                                 for b in range(nb)]).astype(np.int32)
+        feats = r.standard_normal((m * nb, f)).astype(np.float32)
+        ref = oracle.scatter_bev(feats, coords, nx, ny, batch_size=nb)
+        for variant in ("plain", "bulk1d", "tma2d", "auto"):
+            for cd in (coords, coords.astype(np.float32)):
+                bev = L.ops.scatter_bev(torch.from_numpy(feats).to(dev), torch.from_numpy(cd).to(dev), nb, nx, ny,
+                                        variant=variant)
+                np.testing.assert_array_equal(bev.cpu().numpy(), ref, err_msg=f"{nx}x{ny} f={f} {variant}")
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + full oracle comparison where it takes seconds
+# ------------------------------------------------------------------------------------------------
+def test_cfg2_full_size_properties_and_oracle(dev, L, oracle):
+    model, gc, nb = synth.WORKLOADS["cfg2_nuscenes32_b16_pillar0.2_bev512"]
+    pts, offs = synth.make_batch(nb, model, 5)
+    grid = L.GridSpec.from_range(gc.point_cloud_range, gc.voxel_size, gc.max_points_per_voxel, gc.max_voxels)
+    sd = oracle.random_pfn_params(11, [64], True, seed=0)
+    r1 = _run_fused(L, dev, pts, offs, grid, sd, 5, want_membership=True)
+    snap = {k: v.clone() for k, v in r1.items()}
+    r2 = _run_fused(L, dev, pts, offs, grid, sd, 5, want_membership=True)
+    for k in snap:  # idempotence / run-to-run determinism, bit for bit, although atomics land in any order
+        assert torch.equal(snap[k], r2[k]), k
+    m = int(snap["pillar_count"][-1].item())
+    counts = snap["pillar_count"][:-1].cpu().numpy()
+    coords = snap["voxel_coords"][:m].cpu().numpy()
+    npts = snap["voxel_num_points"][:m].cpu().numpy()
+    slot = snap["point_slot"].cpu().numpy()
+    pil = snap["point_pillar"].cpu().numpy()
+    # conservation: every stored point is counted once; slots inside a pillar are 0..n-1
+    assert (slot >= 0).sum() == npts.sum()
+    assert np.array_equal(np.bincount(pil[slot >= 0], minlength=m), npts)
+    assert (np.diff(coords[:, 0]) >= 0).all() and np.array_equal(np.bincount(coords[:, 0], minlength=nb), counts)
+    # one canvas cell per pillar, zero elsewhere; channel sums of the canvas equal the feature sums (linearity)
+    bev = snap["bev"]
+    assert int((bev != 0).any(dim=1).sum().item()) <= m
+    occ = torch.zeros((nb, 512, 512), dtype=torch.bool, device=dev)
+    ct = snap["voxel_coords"][:m].long()
+    occ[ct[:, 0], ct[:, 2], ct[:, 3]] = True
+    assert int(occ.sum().item()) == m
+    assert bool(((bev != 0).any(dim=1) <= occ).all())
+    fsum = torch.zeros((nb, 64), dtype=torch.float64, device=dev).index_add_(0, ct[:, 0], snap["pillar_features"][:m].double())
+    assert torch.allclose(bev.double().sum(dim=(2, 3)), fsum, rtol=1e-9, atol=1e-9)
+    # full oracle comparison (a few seconds of CPU)
+    ref_v = oracle.voxelize_batch(pts, offs, gc.point_cloud_range, gc.voxel_size, gc.max_points_per_voxel, gc.max_voxels)
+    np.testing.assert_array_equal(coords, ref_v["coords"])
+    np.testing.assert_array_equal(npts, ref_v["num_points"])
+    np.testing.assert_array_equal(slot, ref_v["point_slot"])
+    np.testing.assert_array_equal(pil, ref_v["point_voxel"])
+    ref_f = oracle.pillar_vfe(ref_v["voxels"], ref_v["num_points"], ref_v["coords"], sd, gc.voxel_size,
+                              gc.point_cloud_range).numpy()
+    np.testing.assert_allclose(snap["pillar_features"][:m].cpu().numpy(), ref_f, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+
+
+def test_hard_variant_equals_fused_variant(dev, L, oracle):
+    """PillarVFE('voxels' from the CPU voxeliser) and PillarVFEFromPoints('points') are two routes to the same answer."""
+    pts, offs, rng, vs, p, mv = _make_case("cfg1_p20")
+    grid = L.GridSpec.from_range(rng, vs, p, mv)
+    sd = oracle.random_pfn_params(11, [64], True, seed=9)
+    res = _run_fused(L, dev, pts, offs, grid, sd, 5)
+    m = int(res["pillar_count"][-1].item())
+    v = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+
+    class C(dict):
+        __getattr__ = dict.__getitem__
+
+    vfe = L.PillarVFE(model_cfg=C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64]),
+                      num_point_features=5, voxel_size=list(vs), point_cloud_range=np.asarray(rng, np.float32),
+                      grid_size=grid.grid_size)
+    vfe.load_state_dict(sd)
+    vfe.eval().to(dev)
+    voxels, npts, coords = oracle.collate_voxels(v)
+    out = vfe({"voxels": torch.from_numpy(voxels).to(dev), "voxel_num_points": torch.from_numpy(npts).to(dev),
+               "voxel_coords": torch.from_numpy(coords).to(dev)})["pillar_features"]
+    torch.testing.assert_close(out, res["pillar_features"][:m], rtol=1e-5, atol=1e-5)
+
+
+def test_cpu_tensors_and_training_mode_fail_loudly(dev, L):
+    class C(dict):
+        __getattr__ = dict.__getitem__
+
+    vfe = L.PillarVFE(model_cfg=C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64]),
+                      num_point_features=5, voxel_size=[0.2, 0.2, 8], point_cloud_range=[-1, -1, -1, 1, 1, 1])
+    bd = {"voxels": torch.zeros(3, 4, 5), "voxel_num_points": torch.ones(3), "voxel_coords": torch.zeros(3, 4)}
+    with pytest.raises(L.NativeLibraryError):
+        vfe.eval()(dict(bd))
+    with pytest.raises(RuntimeError):
+        vfe.train().to(dev)({k: v.to(dev) for k, v in bd.items()})
