@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Benchmark of the pillar LiDAR-encoder hot path (BASELINE.json metric: sweeps/s and points/s through the encoder, with
+the fraction of the HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path  (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (CPU oracle port)
+
+A "step" is one pass of the path (grouping -> pillar features -> BEV scatter) over one batch of synthetic sweeps per GPU.
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every definition used here.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+DEFAULT_WORKLOAD = "cfg2_nuscenes32_b16_pillar0.2_bev512"
+METRIC = "lidar_encoder_sweeps_per_sec"
+UNIT = "sweeps/s"
+F_OUT = 64
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "bulk1d", "tma2d"])
+    ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through the timed loop")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU arm (bounded sample)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json: hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clk, cmax = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                smax.append(cmax)
+                try:
+                    power.append(float(parts[2]))
+                except ValueError:
+                    pass
+                for nme, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+        if not sm:  # region shorter than one sample: take the nearest samples
+            vals = [float(l.split(",")[0]) for _, l in self.lines if l and l.split(",")[0].strip().replace(".", "").isdigit()]
+            return {"sm_mhz": (statistics.median(vals) if vals else None), "sm_max_mhz": None,
+                    "reasons": sorted(reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def make_frames(workload: str, n_frames: int, seed0: int):
+    from lidar_vision_vqa_b200 import synth
+
+    model, gc, _ = synth.WORKLOADS[workload]
+    frames = [synth.make_sweep(seed0 + i, model, 5) for i in range(n_frames)]
+    return frames, gc
+
+
+def pack(frames):
+    offs = np.zeros(len(frames) + 1, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    return np.concatenate(frames, 0), offs
+
+
+def algorithmic_bytes(n_raw, n_kept, m, c, f, nx, ny, nb):
+    """V (voxelise), P (fused PFN), S (scatter) bytes for one launch over the whole batch."""
+    v = 4 * c * n_raw + 4 * n_raw + 20 * m
+    p = 4 * c * n_kept + 4 * n_kept + 16 * m + 4 * f * m
+    s = 4 * f * m + 16 * m + 4 * f * nx * ny * nb
+    return {"V": v, "P": p, "S": s}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores (oracle port; the Python reference cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_arm(workload: str, frames_per_step: int, steps: int, warmup: int):
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import pillar_oracle as po
+
+    po.build_oracle_lib()
+    frames, gc = make_frames(workload, frames_per_step, seed0=0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = po.random_pfn_params(11, [F_OUT], True, seed=0)
+    nx, ny, _ = gc.grid_size
+    pool = ThreadPoolExecutor(max_workers=min(cores, frames_per_step))
+
+    def voxelise(fr):  # one frame per worker thread: the C call releases the GIL
+        return po.voxelize_hard(fr, gc.point_cloud_range, gc.voxel_size, gc.max_points_per_voxel, gc.max_voxels)
+
+    def one_step():
+        outs = list(pool.map(voxelise, frames))
+        coords = np.concatenate([np.concatenate([np.full((len(o["coords"]), 1), b, np.int32), o["coords"]], 1)
+                                 for b, o in enumerate(outs)], 0)
+        voxels = np.concatenate([o["voxels"] for o in outs], 0)
+        npts = np.concatenate([o["num_points"] for o in outs], 0)
+        with torch.inference_mode():
+            feats = po.pillar_vfe(voxels, npts.astype(np.float32), coords.astype(np.float32), sd, gc.voxel_size,
+                                  gc.point_cloud_range).numpy()
+        # dense canvas, one frame per worker thread
+        bounds = np.searchsorted(coords[:, 0], np.arange(len(frames) + 1))
+
+        def scat(b):
+            c = coords[bounds[b]:bounds[b + 1]].copy()
+            c[:, 0] = 0
+            return po.scatter_bev(feats[bounds[b]:bounds[b + 1]], c, nx, ny, batch_size=1)
+
+        bevs = list(pool.map(scat, range(len(frames))))
+        return len(coords), bevs[0].shape
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    n_pts = sum(len(f) for f in frames)
+    return {
+        "sweeps_per_s": frames_per_step * steps / dt,
+        "points_per_s": n_pts * steps / dt,
+        "ms_per_step": dt / steps * 1e3,
+        "cores": cores,
+        "sample": f"{frames_per_step} frames/step x {steps} steps of {workload} (C voxeliser one frame per thread, "
+                  f"torch-CPU PillarVFE with {cores} threads, C scatter one frame per thread)",
+    }
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    # bound the whole run to a couple of minutes: one CPU step of 4 frames is ~1 s on 8 threads
+    steps = min(steps, 20)
+    r = cpu_reference_arm(args.workload, args.cpu_frames, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["sweeps_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "points_per_sec": r["points_per_s"],
+        "config": {"workload": args.workload, "frames_per_step": args.cpu_frames, "device": "host CPU"},
+        "cpu_baseline": {"value": r["sweeps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["sweeps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import lidar_vision_vqa_b200 as L
+    from lidar_vision_vqa_b200 import _native, ops, synth
+    from oracle import pillar_oracle as po  # weights generator + cpu_baseline leg only
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+
+    model, gc, nb = synth.WORKLOADS[args.workload]
+    grid = L.GridSpec.from_range(gc.point_cloud_range, gc.voxel_size, gc.max_points_per_voxel, gc.max_voxels)
+    nx, ny, nz = grid.grid_size
+    sd = po.random_pfn_params(11, [F_OUT], True, seed=0)
+    pfn = ops.fold_pfn(sd["pfn_layers.0.linear.weight"],
+                       (sd["pfn_layers.0.norm.weight"], sd["pfn_layers.0.norm.bias"],
+                        sd["pfn_layers.0.norm.running_mean"], sd["pfn_layers.0.norm.running_var"], 1e-3), None,
+                       c_point=5, use_absolute_xyz=True, with_distance=False, voxel_size=grid.voxel_size,
+                       point_cloud_range=grid.point_cloud_range, device=dev)
+
+    # every rank owns its own frames (weak scaling: frames are independent units, no data-path collective)
+    rot = max(1, args.rotate)
+    host_batches = []
+    for r in range(rot):
+        frames, _ = make_frames(args.workload, nb, seed0=(rank * rot + r) * nb)
+        host_batches.append(pack(frames))
+    n_max = max(p.shape[0] for p, _ in host_batches)
+    dev_batches = [(torch.from_numpy(p).to(dev), torch.from_numpy(o).to(dev)) for p, o in host_batches]
+    bufs = ops.EncodeBuffers(n_max, nb, grid, F_OUT, dev)
+
+    def step(i):
+        p, o = dev_batches[i % rot]
+        return ops.encode_bev(p, o, grid, pfn, buffers=bufs, scatter_variant=args.scatter_variant)
+
+    for i in range(max(3, args.warmup)):
+        res = step(i)
+    torch.cuda.synchronize()
+    launches_per_step = ops.last_launch_count()
+    # workload statistics for the algorithmic byte counts (one sync, outside the timed region)
+    stats = []
+    for i in range(rot):
+        res = step(i)
+        m = int(res["pillar_count"][-1].item())
+        n_kept = int(res["voxel_num_points"][:m].sum().item())
+        stats.append((host_batches[i][0].shape[0], n_kept, m))
+    n_raw = statistics.mean(s[0] for s in stats)
+    n_kept = statistics.mean(s[1] for s in stats)
+    m_avg = statistics.mean(s[2] for s in stats)
+
+    K = args.steps
+    evs = []
+    for _ in range(K):
+        e4 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for e in e4:
+            e.record()
+        evs.append(e4)
+    torch.cuda.synchronize()
+    ev_arrays = [(ctypes.c_void_p * 4)(*[e.cuda_event for e in e4]) for e4 in evs]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    start.record()
+    for k in range(K):
+        lib.pillars_set_stage_events(ev_arrays[k])
+        step(k)
+    stop.record()
+    lib.pillars_set_stage_events(None)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    elapsed_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    stage_ms = np.array([[e4[i].elapsed_time(e4[i + 1]) for i in range(3)] for e4 in evs])  # group, features, scatter
+    stage_avg = stage_ms.mean(axis=0)
+    ms_per_step = elapsed_ms / K
+    sweeps_per_s = nb * world / (ms_per_step * 1e-3)
+    points_per_s = n_raw * world / (ms_per_step * 1e-3)
+
+    peak, peak_src = measured_peaks()
+    ab = algorithmic_bytes(n_raw, n_kept, m_avg, 5, F_OUT, nx, ny, nb)
+    scat_gbs = ab["S"] / (stage_avg[2] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_scatter_async (BEV scatter, dominant kernel of the step)",
+                "achieved": scat_gbs, "peak": peak, "unit": "GB/s", "frac": scat_gbs / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["S"],
+                "avg_launch_ms": float(stage_avg[2]), "share_of_step": float(stage_avg[2] / ms_per_step)}
+    stages = {
+        "group_ms": float(stage_avg[0]), "features_ms": float(stage_avg[1]), "scatter_ms": float(stage_avg[2]),
+        "group_gbs": ab["V"] / (stage_avg[0] * 1e-3) / 1e9, "features_gbs": ab["P"] / (stage_avg[1] * 1e-3) / 1e9,
+        "scatter_gbs": scat_gbs, "path_gbs": (ab["V"] + ab["P"] + ab["S"]) / (ms_per_step * 1e-3) / 1e9,
+        "features_frac_of_peak": ab["P"] / (stage_avg[1] * 1e-3) / 1e9 / peak,
+        "path_frac_of_peak": (ab["V"] + ab["P"] + ab["S"]) / (ms_per_step * 1e-3) / 1e9 / peak,
+        "algorithmic_bytes": ab, "points_raw": n_raw, "points_kept": n_kept, "pillars": m_avg,
+    }
+
+    # ---- end to end through the reference-facing modules, inputs in pinned host memory ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        cfg = Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[F_OUT],
+                  MAX_POINTS_PER_VOXEL=gc.max_points_per_voxel, MAX_NUMBER_OF_VOXELS=gc.max_voxels,
+                  FUSE_SCATTER=True, SCATTER_VARIANT=args.scatter_variant)
+        vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=list(gc.voxel_size),
+                                    point_cloud_range=np.asarray(gc.point_cloud_range, np.float32),
+                                    grid_size=np.asarray(grid.grid_size))
+        vfe.load_state_dict(sd)
+        vfe.eval().to(dev)
+        scatter = L.PointPillarScatter(model_cfg=Cfg(NUM_BEV_FEATURES=F_OUT), grid_size=np.asarray(grid.grid_size))
+        pinned = [torch.from_numpy(synth.to_pcdet_points(p, o)).pin_memory() for p, o in host_batches]
+
+        def e2e_step(i):
+            bd = {"points": pinned[i % rot], "batch_size": nb}
+            bd = scatter(vfe(bd))
+            return bd["pillars_per_frame"]  # host tensor: the D2H read of the step's result
+
+        for i in range(max(3, args.warmup)):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for k in range(K):
+            e2e_step(k)
+        e2.record()
+        torch.cuda.synchronize()
+        ms = s2.elapsed_time(e2)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        e2e = {"value": nb * world / (ms / K * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+               "h2d_bytes_per_step": int(statistics.mean(p.numel() * 4 for p in pinned)),
+               "d2h_bytes_per_step": (nb + 1) * 4,
+               "api": "PillarVFEFromPoints(FUSE_SCATTER).forward + PointPillarScatter.forward on a pinned host batch_dict"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_arm(args.workload, args.cpu_frames, steps=4, warmup=1)
+        cpu = {"value": r["sweeps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "points_per_sec": r["points_per_s"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": sweeps_per_s, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "points_per_sec": points_per_s,
+            "config": {"workload": args.workload, "frames_per_gpu": nb, "global_frames": nb * world,
+                       "points_per_frame": n_raw / nb, "pillars_per_frame": m_avg / nb, "grid": [nx, ny, nz],
+                       "max_points_per_voxel": gc.max_points_per_voxel, "max_voxels": gc.max_voxels,
+                       "scatter_variant": args.scatter_variant, "parallelism": f"dp{world} (frames sharded, no collective)",
+                       "l2": f"no explicit flush: each step writes {4 * F_OUT * nx * ny * nb / 2**20:.0f} MiB (>> 126 MB L2) "
+                             f"and cycles {rot} distinct input batches"},
+            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * K, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and rank == 0:
+        sys.stderr.write(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE\n")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -172,13 +172,16 @@ class PillarVFEFromPoints(_PillarVFEBase):
         offs = ops.frame_offsets_from_points(points, batch_size)
         res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=1,
                              with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
-        m = int(res["pillar_count"][-1].item())  # the one host sync: sizes the returned views (cf. pointpillar_scatter.py:17)
+        # the one host sync of the call: per-frame pillar counts (B+1 ints) size the returned views
+        # (the reference syncs at the same place for the batch size, pointpillar_scatter.py:17)
+        counts = res["pillar_count"].cpu()
+        m = int(counts[-1])
         if m > res["pillar_features"].shape[0]:
             raise RuntimeError("pillar capacity overflow")
         batch_dict["voxel_features"] = batch_dict["pillar_features"] = res["pillar_features"][:m]
         batch_dict["voxel_coords"] = res["voxel_coords"][:m]
         batch_dict["voxel_num_points"] = res["voxel_num_points"][:m]
-        batch_dict["pillars_per_frame"] = res["pillar_count"][:-1]
+        batch_dict["pillars_per_frame"] = counts[:-1]  # host tensor
         if self.fuse_scatter:
             batch_dict["spatial_features"] = res["bev"]
             batch_dict["_b200_scatter_done"] = True

@@ -29,6 +29,8 @@ class SweepModel:
     n_sweeps: int = 1
     ego_step: float = 0.45  # metres travelled between consecutive sweeps (multi-sweep clouds)
     sweep_dt: float = 0.05
+    ground_slope: float = 0.15  # amplitude of the slow ground undulation (m)
+    ground_rough: float = 0.06  # per-ray ground height noise (m)
 
 
 @dataclass(frozen=True)
@@ -70,9 +72,12 @@ def _one_revolution(rng: np.random.Generator, m: SweepModel) -> np.ndarray:
     az = (np.arange(m.az_steps, dtype=np.float64) + rng.uniform()) * (2.0 * np.pi / m.az_steps)
     el = np.deg2rad(np.linspace(m.elev_deg[0], m.elev_deg[1], m.beams))
     az_g, el_g = np.meshgrid(az, el, indexing="ij")  # firing order: all beams of one azimuth step
-    # ground return
-    with np.errstate(divide="ignore"):
-        r_ground = np.where(el_g < -1e-3, m.sensor_height / np.sin(-el_g), np.inf)
+    # ground return; a gently undulating, rough ground spreads the rings radially (flat ground would stack ~10
+    # points per near-field pillar and give 2.6 points/pillar overall instead of the ~2.1 of a real 32-beam sweep)
+    h = m.sensor_height + m.ground_slope * np.sin(3.0 * az_g + rng.uniform(0.0, 2.0 * np.pi)) \
+        + rng.normal(scale=m.ground_rough, size=az_g.shape)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r_ground = np.where(el_g < -1e-3, h / np.sin(-el_g), np.inf)
     # obstacles: a piecewise-constant range profile per azimuth sector gives object-like coherence,
     # plus a per-ray gamma draw for clutter
     n_sect = 96
@@ -84,6 +89,7 @@ def _one_revolution(rng: np.random.Generator, m: SweepModel) -> np.ndarray:
     hits_obj = (z_at_obj > -m.sensor_height) & (z_at_obj < sect_h[sect] - m.sensor_height)
     r_clutter = rng.gamma(shape=2.0, scale=14.0, size=az_g.shape) + 1.0
     use_clutter = rng.uniform(size=az_g.shape) < 0.12
+    use_clutter |= ~np.isfinite(r_ground) & ~hits_obj  # rays that meet neither ground nor object end on far structure
     r = np.where(hits_obj, np.minimum(r_obj, r_ground), r_ground)
     r = np.where(use_clutter, np.minimum(r, r_clutter), r)
     r = r + rng.normal(scale=0.02, size=r.shape)
