@@ -75,6 +75,11 @@ typedef struct pillars_pfn {
     const float *weight;      /* [f_out, c_in] row-major = nn.Linear.weight */
     const float *scale;       /* [f_out] */
     const float *shift;       /* [f_out] */
+    /* Optional HOST copies of the three arrays above (all three or none).  When present, pillars_encode_bev folds them
+     * into kernel parameters and runs the constant-bank fast kernel (USE_ABSLOTE_XYZ, no WITH_DISTANCE, C <= 5). */
+    const float *weight_host;
+    const float *scale_host;
+    const float *shift_host;
 } pillars_pfn_t;
 
 /* what pillars_encode_bev / pillars_voxelize write; any pointer may be NULL to skip that output */
@@ -141,6 +146,10 @@ int pillars_last_launch_count(void);
  * call's stream at: [0] entry, [1] grouping done, [2] pillar features done, [3] scatter done.  NULL clears the hook.
  * Thread-local; costs four cudaEventRecord per call while set. */
 int pillars_set_stage_events(void *const *events4);
+
+/* Test / measurement hook: non-zero makes pillars_encode_bev ignore the host weight copies and run the generic feature
+ * kernel (thread-local). */
+int pillars_force_generic_features(int on);
 
 #ifdef __cplusplus
 }

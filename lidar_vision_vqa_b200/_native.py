@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "pillars_encode_bev",
     "pillars_last_launch_count",
     "pillars_set_stage_events",
+    "pillars_force_generic_features",
 )
 
 
@@ -33,7 +34,7 @@ class PillarsGrid(Structure):
 class PillarsPfn(Structure):
     _fields_ = [("c_point", c_int32), ("c_in", c_int32), ("f_out", c_int32), ("use_absolute_xyz", c_int32),
                 ("with_distance", c_int32), ("offset", c_float * 3), ("weight", c_void_p), ("scale", c_void_p),
-                ("shift", c_void_p)]
+                ("shift", c_void_p), ("weight_host", c_void_p), ("scale_host", c_void_p), ("shift_host", c_void_p)]
 
 
 class PillarsOutputs(Structure):
@@ -85,6 +86,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_encode_bev.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
                                        POINTER(PillarsPfn), POINTER(PillarsOutputs), c_void_p, c_size_t, c_int32,
                                        c_void_p]
+    lib.pillars_force_generic_features.restype = c_int
+    lib.pillars_force_generic_features.argtypes = [c_int]
     lib.pillars_set_stage_events.restype = c_int
     lib.pillars_set_stage_events.argtypes = [POINTER(c_void_p)]
     _LIB = lib

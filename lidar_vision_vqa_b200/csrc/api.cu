@@ -81,6 +81,26 @@ static int check_pfn(const pillars_pfn_t *pfn)
     return 0;
 }
 
+static thread_local bool g_force_generic = false;
+
+// W.[p, p - mean, p - centre] regrouped around the pillar centre (see pfn_fast.cu); BatchNorm scale folded in, in double.
+static void fold_fast_weights(const pillars_pfn_t &pfn, FastWeights *fw)
+{
+    const int c = pfn.c_point, cin = pfn.c_in;  // feature order: p[0..c), cluster xyz, centre xyz
+    for (int o = 0; o < 64; ++o) {
+        const float *w = pfn.weight_host + static_cast<size_t>(o) * cin;
+        const double s = pfn.scale_host[o];
+        for (int a = 0; a < 3; ++a) {
+            fw->wp[a][o] = static_cast<float>(s * (static_cast<double>(w[a]) + w[c + a] + w[c + 3 + a]));
+            fw->wk[a][o] = static_cast<float>(s * w[a]);
+            fw->wk[3 + a][o] = static_cast<float>(s * w[c + a]);
+        }
+        fw->wp[3][o] = c > 3 ? static_cast<float>(s * w[3]) : 0.f;
+        fw->wp[4][o] = c > 4 ? static_cast<float>(s * w[4]) : 0.f;
+        fw->shift[o] = pfn.shift_host[o];
+    }
+}
+
 static PfnDev make_pfn_dev(const pillars_pfn_t &pfn, const float voxel[3])
 {
     PfnDev d;
@@ -108,6 +128,12 @@ int pillars_set_stage_events(void *const *events4)
 {
     g_stage_on = events4 != nullptr;
     for (int i = 0; i < 4; ++i) g_stage_ev[i] = events4 ? static_cast<cudaEvent_t>(events4[i]) : nullptr;
+    return 0;
+}
+
+int pillars_force_generic_features(int on)
+{
+    g_force_generic = on != 0;
     return 0;
 }
 
@@ -178,8 +204,13 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         if ((e = cudaMemsetAsync(out->point_slot, 0xFF, sizeof(int32_t) * n, st)) != cudaSuccess) return cuda_fail(e, "memset");
         note_launch();
     }
-    if ((e = launch_group_points(points, n, row_stride, col0, frame_offsets, n_frames, gd, ws, out->pillar_count, st)) !=
-        cudaSuccess)
+    // Feature kernel choice.  The constant-bank fast kernel covers the mainstream configuration when the caller also
+    // supplied host copies of the weights; everything else runs the generic 16-lanes-per-pillar kernel.
+    const bool membership = out->voxels || out->point_pillar || out->point_slot;
+    const bool fast = pfn && pfn->weight_host && pfn->scale_host && pfn->shift_host && pfn->use_absolute_xyz &&
+                      !pfn->with_distance && pfn->c_point <= 5 && pfn->f_out == 64 && !g_force_generic;
+    if ((e = launch_group_points(points, n, row_stride, col0, c_point, frame_offsets, n_frames, gd, ws, out->pillar_count,
+                                 /*want_index_lists=*/membership || !fast, /*want_records=*/fast, st)) != cudaSuccess)
         return cuda_fail(e, "group_points");
     stage_mark(1, st);
 
@@ -191,7 +222,7 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
     job.c_point = c_point;
     job.nb = n_frames;
     job.idx_bits = idx_bits_for(n > 1 ? n : 2);
-    job.do_features = pfn != nullptr;
+    job.do_features = pfn != nullptr && !fast;
     if (pfn) {
         job.use_abs = pfn->use_absolute_xyz != 0;
         job.with_dist = pfn->with_distance != 0;
@@ -200,8 +231,27 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         job.f_out = pfn->f_out;
     }
     job.out = *out;
-    job.write_cell_row = want_bev;
-    if ((e = launch_pillar_features(job, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features");
+    job.write_cell_row = want_bev && !fast;
+    if (!fast || membership) {
+        if ((e = launch_pillar_features(job, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features");
+    }
+    if (fast) {
+        FastWeights fw;
+        fold_fast_weights(*pfn, &fw);
+        FastJob fj{};
+        fj.n = n;
+        fj.idx_bits = job.idx_bits;
+        for (int i = 0; i < 3; ++i) {
+            fj.vsz[i] = grid->voxel[i];
+            fj.off[i] = pfn->offset[i];
+        }
+        fj.pillar_features = out->pillar_features;
+        fj.voxel_coords = out->voxel_coords;
+        fj.voxel_num_points = out->voxel_num_points;
+        fj.capacity = out->pillar_capacity;
+        fj.write_cell_row = want_bev;
+        if ((e = launch_pillar_features_fast(fj, fw, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features_fast");
+    }
     stage_mark(2, st);
 
     if (want_bev) {

@@ -32,13 +32,22 @@ struct Header {
     uint32_t pad[13];
 };
 
+// One point, moved next to the other points of its pillar (32 B = one DRAM sector).
+struct __align__(32) PointRecord {
+    float x, y, z, intensity, time;  // missing channels are 0
+    uint32_t idx;                    // index of the point in the input batch
+    uint32_t gid;                    // pillar id (first-appearance order, batch-global, uncapped)
+    uint32_t arrival;                // position inside the pillar's list; 0 marks the start of a list
+};
+
 static constexpr int kMaxFrames = 1024;  // frame_offsets are staged in shared memory
 static constexpr int kTile = 1024;       // points per CTA tile in the point-parallel kernels
 
 struct Workspace {
     // zero-initialised region
     Header *hdr;
-    unsigned long long *tile_desc;  // [n_tiles] chained-scan descriptors
+    unsigned long long *tile_desc;  // [n_tiles] scan: per-tile aggregates (valid bit | pillars | listed points)
+    unsigned long long *tile_prefix;// [n_tiles] scan: inclusive prefixes published by the last tile of each group
     uint32_t *frame_gstart;         // [B+1] first-appearance id at each frame start (uncapped, batch-global)
     uint32_t *frame_rowbase;        // [B+1] output row at each frame start (after the max_voxels cap)
     size_t zero_bytes;
@@ -53,6 +62,7 @@ struct Workspace {
     uint32_t *pillar_list;          // [n] start of pillar g's point list
     uint32_t *pillar_cnt;           // [n] points that fell into pillar g (uncapped)
     uint32_t *sorted_idx;           // [n] point indices grouped by pillar
+    PointRecord *records;           // [n] point records grouped by pillar
     uint32_t cap;                   // hash slots
     uint32_t n_tiles;
     size_t total_bytes;
@@ -85,6 +95,7 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     w.zero_begin = p ? p : nullptr;
     w.hdr = reinterpret_cast<Header *>(take(sizeof(Header)));
     w.tile_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
+    w.tile_prefix = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
     w.frame_gstart = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
     w.frame_rowbase = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
     w.zero_bytes = off;
@@ -99,6 +110,7 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     w.pillar_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.pillar_cnt = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.sorted_idx = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
+    w.records = reinterpret_cast<PointRecord *>(take(sizeof(PointRecord) * n));
     w.total_bytes = off;
     return w;
 }
@@ -143,9 +155,9 @@ void note_launch(int n = 1);
 // ---- launchers implemented in the kernel translation units ---------------------------------------
 cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, int nb, int32_t *offs, cudaStream_t st);
 
-cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, const int32_t *frame_offsets,
-                                int nb, const GridDev &gd, const Workspace &ws, int32_t *pillar_count,
-                                cudaStream_t st);
+cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, int c_point,
+                                const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
+                                int32_t *pillar_count, bool want_index_lists, bool want_records, cudaStream_t st);
 
 struct FeatureJob {
     const float *points;
@@ -165,6 +177,24 @@ struct FeatureJob {
     bool write_cell_row;       // fill ws.cell_row for the BEV scatter
 };
 cudaError_t launch_pillar_features(const FeatureJob &job, const GridDev &gd, const Workspace &ws, cudaStream_t st);
+
+// Host-folded weights of the fast feature kernel; passed by value as a kernel parameter (constant bank).
+struct FastWeights {
+    float wp[5][64];  // per point:  scale * (W_p + W_cluster + W_centre) for x,y,z;  scale * W for intensity, time
+    float wk[6][64];  // per pillar: scale * W_p (x,y,z) applied to the centre, scale * W_cluster applied to (mean - centre)
+    float shift[64];
+};
+struct FastJob {
+    int64_t n;  // upper bound of listed points (the input point count)
+    int idx_bits;
+    float vsz[3], off[3];
+    float *pillar_features;
+    int32_t *voxel_coords, *voxel_num_points;
+    int64_t capacity;
+    bool write_cell_row;
+};
+cudaError_t launch_pillar_features_fast(const FastJob &job, const FastWeights &w, const GridDev &gd, const Workspace &ws,
+                                        cudaStream_t st);
 
 cudaError_t launch_pfn_dense(const float *voxels, const void *num_points, bool np_float, const void *coords,
                              bool coords_float, int64_t m, int max_points, int c_point, int c_in, int f_out,

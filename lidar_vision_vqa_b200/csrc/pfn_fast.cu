@@ -1,0 +1,361 @@
+// Fast path of the per-pillar feature stage for the mainstream configuration (USE_ABSLOTE_XYZ, no WITH_DISTANCE,
+// C <= 5 point channels, one PFN layer, F = 64).  Same function as pfn.cu / pillar_vfe.py:29-49,94-123, reorganised so that
+// the FMA pipes do (almost) nothing but useful work:
+//
+//   * the points arrive as 32-byte records already grouped by pillar (k_place), so a CTA streams 256 consecutive list
+//     positions instead of gathering;
+//   * ONE THREAD PER POINT computes all 64 channels with the weights as constant-bank FFMA operands (they are a kernel
+//     parameter), i.e. no weight registers, no shared-memory weight traffic, no lanes idling on short pillars;
+//   * the linear layer is refactored around the pillar centre c:  with x' = x - c and m' = mean - c
+//         W.[p, p_xyz - mean, p_xyz - c] = (W_p + W_cl + W_ce).x' + W_it.(i,t)  +  [ W_p.c - W_cl.m' ]
+//     so a point costs 5 FMAs per channel and the bracket is one 6-FMA constant per (pillar, channel).  All per-point
+//     terms are small numbers (|x'| <= voxel/2): no cancellation is introduced.  BatchNorm's scale is folded into W on the
+//     host, and since "+ constant" and ReLU are monotone the max over the pillar's points is taken BEFORE them;
+//   * the per-point results go through shared memory ([32 ch][289] per half) and 8 threads per pillar take the max.
+//
+// A CTA owns the pillars whose list STARTS inside its 256 positions; the tail of its last pillar (usually 0-2 points in
+// the next chunk) is swept by warp 0.  Pillars over the cap (n > P) get their "first P by point index" threshold from a
+// warp-wide radix select.
+#include "common.cuh"
+
+namespace pillars {
+
+namespace {
+
+constexpr int kFT = 256;   // threads per CTA == list positions per chunk
+constexpr int kTailW = 32; // tail positions per sweep (one warp)
+constexpr int kLd = kFT + kTailW + 1;
+constexpr int kHalf = 32;  // channels per pass
+constexpr unsigned kFull = 0xffffffffu;
+
+struct FastParams {
+    const PointRecord *records;
+    const Header *hdr;
+    const uint32_t *pillar_key, *pillar_cnt, *frame_gstart, *frame_rowbase;
+    int32_t *cell_row;
+    float *pillar_features;
+    int32_t *voxel_coords, *voxel_num_points;
+    int64_t capacity;
+    GridDev gd;
+    float vsz[3], off[3];
+    int idx_bits;
+    FastWeights w;
+};
+
+__device__ __forceinline__ unsigned lanemask_le()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+template <int H>
+__device__ __forceinline__ void point_half(const FastParams &p, bool kept, float xp, float yp, float zp, float in, float tm,
+                                           float *__restrict__ col)
+{
+    if (kept) {
+#pragma unroll
+        for (int c = 0; c < kHalf; ++c) {
+            float a = xp * p.w.wp[0][H * kHalf + c];
+            a = fmaf(yp, p.w.wp[1][H * kHalf + c], a);
+            a = fmaf(zp, p.w.wp[2][H * kHalf + c], a);
+            a = fmaf(in, p.w.wp[3][H * kHalf + c], a);
+            a = fmaf(tm, p.w.wp[4][H * kHalf + c], a);
+            col[c * kLd] = a;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kHalf; ++c) col[c * kLd] = -INFINITY;
+    }
+}
+
+__global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_constant__ FastParams p)
+{
+    extern __shared__ __align__(16) float s_y[];  // [kHalf][kLd]
+    __shared__ float s_cx[kFT], s_cy[kFT], s_cz[kFT], s_mx[kFT], s_my[kFT], s_mz[kFT];
+    __shared__ int32_t s_row[kFT];
+    __shared__ uint32_t s_thr[kFT], s_pos0[kFT], s_cnt[kFT];
+    __shared__ int16_t s_start[kFT + 1];
+    __shared__ uint8_t s_pad[kFT];
+    __shared__ uint16_t s_big[kFT];
+    __shared__ int s_nbig, s_tail_len;
+    __shared__ int s_warp_cnt[kFT / 32];
+    __shared__ __align__(16) float s_wk[7][64];
+    __shared__ float s_acc_tail[kHalf];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t total = p.hdr->total_listed;
+    const uint32_t q0 = blockIdx.x * kFT;
+    if (q0 >= total) return;
+
+    for (int i = tid; i < 7 * 64; i += kFT) s_wk[i >> 6][i & 63] = (i < 6 * 64) ? p.w.wk[i >> 6][i & 63] : p.w.shift[i & 63];
+
+    const uint32_t pos = q0 + tid;
+    const bool in = pos < total;
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, __uint_as_float(1u));
+    if (in) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.records + pos);
+        ra = __ldg(src);
+        rb = __ldg(src + 1);
+    }
+    const uint32_t r_idx = __float_as_uint(rb.y), r_gid = __float_as_uint(rb.z);
+    const bool is_start = in && __float_as_uint(rb.w) == 0u;
+
+    // pillar-local index of every position: inclusive count of list starts, minus one
+    const unsigned bal = __ballot_sync(kFull, is_start);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    if (tid == 0) {
+        s_nbig = 0;
+        s_tail_len = 0;
+    }
+    __syncthreads();
+    int before = 0, n_pl = 0;
+#pragma unroll
+    for (int w = 0; w < kFT / 32; ++w) {
+        const int c = s_warp_cnt[w];
+        if (w < warp) before += c;
+        n_pl += c;
+    }
+    if (n_pl == 0) return;  // every position belongs to a pillar owned by an earlier CTA
+    const int pl = before + __popc(bal & lanemask_le()) - 1;
+    if (is_start) s_start[pl] = static_cast<int16_t>(tid);
+    if (tid == 0) s_start[n_pl] = kFT;
+
+    // ---- per-pillar constants, by the thread sitting on the list start ---------------------------------------------
+    const int P = p.gd.max_points;
+    if (is_start) {
+        const uint32_t key = __ldg(p.pillar_key + r_gid);
+        const uint32_t n = __ldg(p.pillar_cnt + r_gid);
+        const uint32_t b = key / p.gd.cells;
+        const uint32_t cell = key - b * p.gd.cells;
+        const uint32_t z = cell / p.gd.cells_xy;
+        const uint32_t rem = cell - z * p.gd.cells_xy;
+        const uint32_t y = rem / static_cast<uint32_t>(p.gd.g[0]);
+        const uint32_t x = rem - y * static_cast<uint32_t>(p.gd.g[0]);
+        const uint32_t local = r_gid - __ldg(p.frame_gstart + b);
+        const int64_t row = static_cast<int64_t>(__ldg(p.frame_rowbase + b)) + local;
+        const bool live = local < static_cast<uint32_t>(p.gd.max_voxels) && row < p.capacity;
+        // pillar centre: coord * voxel + offset, two roundings as in the reference (pillar_vfe.py:101-103)
+        const float cx = __fadd_rn(__fmul_rn(static_cast<float>(x), p.vsz[0]), p.off[0]);
+        const float cy = __fadd_rn(__fmul_rn(static_cast<float>(y), p.vsz[1]), p.off[1]);
+        const float cz = __fadd_rn(__fmul_rn(static_cast<float>(z), p.vsz[2]), p.off[2]);
+        s_cx[pl] = cx;
+        s_cy[pl] = cy;
+        s_cz[pl] = cz;
+        s_row[pl] = live ? static_cast<int32_t>(row) : -1;
+        s_cnt[pl] = n;
+        s_pos0[pl] = pos;
+        s_pad[pl] = n < static_cast<uint32_t>(P) ? 1 : 0;
+        s_thr[pl] = 0xFFFFFFFFu;
+        if (live) {
+            if (n > static_cast<uint32_t>(P)) {
+                s_big[atomicAdd(&s_nbig, 1)] = static_cast<uint16_t>(pl);
+            } else {
+                double sx = 0.0, sy = 0.0, sz = 0.0;  // double: the sum does not depend on the list order
+                for (uint32_t j = 0; j < n; ++j) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + pos + j));
+                    sx += static_cast<double>(q.x);
+                    sy += static_cast<double>(q.y);
+                    sz += static_cast<double>(q.z);
+                }
+                const float nf = static_cast<float>(n);
+                s_mx[pl] = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), cx);  // pillar_vfe.py:97, relative to the centre
+                s_my[pl] = __fsub_rn(__fdiv_rn(static_cast<float>(sy), nf), cy);
+                s_mz[pl] = __fsub_rn(__fdiv_rn(static_cast<float>(sz), nf), cz);
+            }
+            if (p.voxel_coords)
+                *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) =
+                    make_int4(static_cast<int>(b), static_cast<int>(z), static_cast<int>(y), static_cast<int>(x));
+            if (p.voxel_num_points) p.voxel_num_points[row] = static_cast<int32_t>(min(n, static_cast<uint32_t>(P)));
+            if (p.cell_row)
+                p.cell_row[static_cast<int64_t>(b) * p.gd.cells_xy + static_cast<int64_t>(y) * p.gd.g[0] + x] =
+                    static_cast<int32_t>(row);
+            if (pl == n_pl - 1) {
+                const int64_t over = static_cast<int64_t>(pos) + n - (static_cast<int64_t>(q0) + kFT);
+                s_tail_len = over > 0 ? static_cast<int>(over) : 0;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pillars over the cap: threshold = P-th smallest point index (radix select), mean over the kept ones ---------
+    for (int k = warp; k < s_nbig; k += kFT / 32) {
+        const int bp = s_big[k];
+        const uint32_t p0 = s_pos0[bp], n = s_cnt[bp];
+        uint32_t prefix = 0, kk = static_cast<uint32_t>(P);
+        for (int bit = p.idx_bits - 1; bit >= 0; --bit) {
+            const uint32_t himask = 0xFFFFFFFFu << (bit + 1);
+            uint32_t c0 = 0;
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint32_t v = __ldg(&p.records[p0 + j].idx);
+                c0 += ((v & himask) == prefix && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) c0 += __shfl_xor_sync(kFull, c0, s);
+            if (kk > c0) {
+                prefix |= 1u << bit;
+                kk -= c0;
+            }
+        }
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (uint32_t j = lane; j < n; j += 32) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + p0 + j));
+            if (__ldg(&p.records[p0 + j].idx) <= prefix) {
+                sx += static_cast<double>(q.x);
+                sy += static_cast<double>(q.y);
+                sz += static_cast<double>(q.z);
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            sx += __shfl_xor_sync(kFull, sx, s);
+            sy += __shfl_xor_sync(kFull, sy, s);
+            sz += __shfl_xor_sync(kFull, sz, s);
+        }
+        if (lane == 0) {
+            const float nf = static_cast<float>(P);
+            s_thr[bp] = prefix;
+            s_mx[bp] = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), s_cx[bp]);
+            s_my[bp] = __fsub_rn(__fdiv_rn(static_cast<float>(sy), nf), s_cy[bp]);
+            s_mz[bp] = __fsub_rn(__fdiv_rn(static_cast<float>(sz), nf), s_cz[bp]);
+        }
+    }
+    __syncthreads();
+
+    // ---- my point, relative to its pillar centre ---------------------------------------------------------------------
+    bool kept = false;
+    float xp = 0.f, yp = 0.f, zp = 0.f;
+    if (in && pl >= 0 && s_row[pl] >= 0 && r_idx <= s_thr[pl]) {
+        kept = true;
+        xp = __fsub_rn(ra.x, s_cx[pl]);
+        yp = __fsub_rn(ra.y, s_cy[pl]);
+        zp = __fsub_rn(ra.z, s_cz[pl]);
+    }
+    const int tail_len = s_tail_len;
+    const int last = n_pl - 1;
+    const int sub = tid & 7, slot = tid >> 3;  // max stage: 8 threads x 4 channels per pillar, 32 pillars per sweep
+
+#pragma unroll
+    for (int H = 0; H < 2; ++H) {
+        if (H == 0) point_half<0>(p, kept, xp, yp, zp, ra.w, rb.x, s_y + tid);
+        else point_half<1>(p, kept, xp, yp, zp, ra.w, rb.x, s_y + tid);
+        if (tid < kHalf) s_acc_tail[tid] = -INFINITY;
+        __syncthreads();
+
+        // tail of the last pillar that spills into the following chunk(s)
+        for (int t0 = 0; t0 < tail_len; t0 += kTailW) {
+            if (warp == 0) {
+                const bool tin = t0 + lane < tail_len;
+                bool tk = false;
+                float tx = 0.f, ty = 0.f, tz = 0.f, ti = 0.f, tt = 0.f;
+                if (tin) {
+                    const float4 *src = reinterpret_cast<const float4 *>(p.records + q0 + kFT + t0 + lane);
+                    const float4 a = __ldg(src), b = __ldg(src + 1);
+                    if (__float_as_uint(b.y) <= s_thr[last]) {
+                        tk = true;
+                        tx = __fsub_rn(a.x, s_cx[last]);
+                        ty = __fsub_rn(a.y, s_cy[last]);
+                        tz = __fsub_rn(a.z, s_cz[last]);
+                        ti = a.w;
+                        tt = b.x;
+                    }
+                }
+                if (H == 0) point_half<0>(p, tk, tx, ty, tz, ti, tt, s_y + kFT + lane);
+                else point_half<1>(p, tk, tx, ty, tz, ti, tt, s_y + kFT + lane);
+            }
+            __syncthreads();
+            if (tid < kHalf) {
+                float m = s_acc_tail[tid];
+#pragma unroll 8
+                for (int l = 0; l < kTailW; ++l) m = fmaxf(m, s_y[tid * kLd + kFT + l]);
+                s_acc_tail[tid] = m;
+            }
+            __syncthreads();
+        }
+
+        // max over each pillar's points, then the per-pillar constant, ReLU and the padded-slot term
+        for (int q = slot; q < n_pl; q += kFT / 8) {
+            const int row = s_row[q];
+            if (row < 0) continue;
+            const int a0 = s_start[q], a1 = s_start[q + 1];
+            float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            for (int j = a0; j < a1; ++j) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) m[o] = fmaxf(m[o], s_y[(4 * sub + o) * kLd + j]);
+            }
+            if (q == last && tail_len > 0) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) m[o] = fmaxf(m[o], s_acc_tail[4 * sub + o]);
+            }
+            const int ch = H * kHalf + 4 * sub;
+            const float cx = s_cx[q], cy = s_cy[q], cz = s_cz[q], mx = s_mx[q], my = s_my[q], mz = s_mz[q];
+            const float4 k0 = *reinterpret_cast<const float4 *>(&s_wk[0][ch]), k1 = *reinterpret_cast<const float4 *>(&s_wk[1][ch]),
+                         k2 = *reinterpret_cast<const float4 *>(&s_wk[2][ch]), k3 = *reinterpret_cast<const float4 *>(&s_wk[3][ch]),
+                         k4 = *reinterpret_cast<const float4 *>(&s_wk[4][ch]), k5 = *reinterpret_cast<const float4 *>(&s_wk[5][ch]),
+                         sh = *reinterpret_cast<const float4 *>(&s_wk[6][ch]);
+            const bool pad = s_pad[q] != 0;
+            float4 out;
+            {
+                float kc = fmaf(k0.x, cx, sh.x); kc = fmaf(k1.x, cy, kc); kc = fmaf(k2.x, cz, kc);
+                kc = fmaf(-k3.x, mx, kc); kc = fmaf(-k4.x, my, kc); kc = fmaf(-k5.x, mz, kc);
+                out.x = fmaxf(m[0] + kc, pad ? fmaxf(sh.x, 0.f) : 0.f);
+            }
+            {
+                float kc = fmaf(k0.y, cx, sh.y); kc = fmaf(k1.y, cy, kc); kc = fmaf(k2.y, cz, kc);
+                kc = fmaf(-k3.y, mx, kc); kc = fmaf(-k4.y, my, kc); kc = fmaf(-k5.y, mz, kc);
+                out.y = fmaxf(m[1] + kc, pad ? fmaxf(sh.y, 0.f) : 0.f);
+            }
+            {
+                float kc = fmaf(k0.z, cx, sh.z); kc = fmaf(k1.z, cy, kc); kc = fmaf(k2.z, cz, kc);
+                kc = fmaf(-k3.z, mx, kc); kc = fmaf(-k4.z, my, kc); kc = fmaf(-k5.z, mz, kc);
+                out.z = fmaxf(m[2] + kc, pad ? fmaxf(sh.z, 0.f) : 0.f);
+            }
+            {
+                float kc = fmaf(k0.w, cx, sh.w); kc = fmaf(k1.w, cy, kc); kc = fmaf(k2.w, cz, kc);
+                kc = fmaf(-k3.w, mx, kc); kc = fmaf(-k4.w, my, kc); kc = fmaf(-k5.w, mz, kc);
+                out.w = fmaxf(m[3] + kc, pad ? fmaxf(sh.w, 0.f) : 0.f);
+            }
+            *reinterpret_cast<float4 *>(p.pillar_features + static_cast<int64_t>(row) * 64 + ch) = out;
+        }
+        if (H == 0) __syncthreads();  // the second half overwrites s_y
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_pillar_features_fast(const FastJob &job, const FastWeights &w, const GridDev &gd, const Workspace &ws,
+                                        cudaStream_t st)
+{
+    if (job.n == 0) return cudaSuccess;
+    FastParams p{};
+    p.records = ws.records;
+    p.hdr = ws.hdr;
+    p.pillar_key = ws.pillar_key;
+    p.pillar_cnt = ws.pillar_cnt;
+    p.frame_gstart = ws.frame_gstart;
+    p.frame_rowbase = ws.frame_rowbase;
+    p.cell_row = job.write_cell_row ? ws.cell_row : nullptr;
+    p.pillar_features = job.pillar_features;
+    p.voxel_coords = job.voxel_coords;
+    p.voxel_num_points = job.voxel_num_points;
+    p.capacity = job.capacity;
+    p.gd = gd;
+    for (int i = 0; i < 3; ++i) {
+        p.vsz[i] = job.vsz[i];
+        p.off[i] = job.off[i];
+    }
+    p.idx_bits = job.idx_bits;
+    p.w = w;
+    const size_t smem = sizeof(float) * kHalf * kLd;
+    static bool attr_done = false;
+    if (!attr_done) {  // static + dynamic shared memory is just over the 48 KB default
+        cudaFuncSetAttribute(k_pillar_features_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_done = true;
+    }
+    const unsigned grid = static_cast<unsigned>((job.n + kFT - 1) / kFT);  // upper bound: listed points <= n
+    k_pillar_features_fast<<<grid, kFT, smem, st>>>(p);
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace pillars

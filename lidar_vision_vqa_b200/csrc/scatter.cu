@@ -22,7 +22,6 @@ namespace pillars {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTileCells = 256;
 
 __global__ void k_build_cell_row(const void *__restrict__ coords, int coords_float, int64_t m,
                                  const int32_t *__restrict__ m_dev, int nb, int nx, int ny, int32_t *__restrict__ cell_row)
@@ -102,58 +101,85 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void
 }
 
 // ---- variants 2 and 3 ---------------------------------------------------------------------------
-// Shared-memory tile [f][256]; invariant between tiles: all zero.
+// Persistent CTAs; two shared-memory tiles [f][kCells] per CTA, alternating.  Invariant: a tile that is not "dirty" is
+// all zero, so an empty stretch of the canvas is stored straight from it with no shared-memory write and no wait at all.
+// A tile that received pillar columns is restored lazily, the next time the buffer comes round (two tiles later), when the
+// store that read it has long finished (cp.async.bulk.wait_group.read 1).  The index-map entry of the next tile is
+// prefetched one iteration ahead so its latency hides behind the current tile.
+constexpr int kCells = 128;
+
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 template <bool TMA2D>
 __global__ void __launch_bounds__(kThreads)
 k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
                 int tiles_per_plane, int64_t n_tiles, float *__restrict__ bev, const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ __align__(128) float s_tile[];
+    extern __shared__ __align__(128) float s_tiles[];  // [2][f][kCells]
     const int tid = threadIdx.x;
-    for (int i = tid; i < f * kTileCells; i += kThreads) s_tile[i] = 0.f;
+    const int tile_floats = f * kCells;
+    for (int i = tid; i < 2 * tile_floats; i += kThreads) s_tiles[i] = 0.f;
     fence_proxy_async();
     __syncthreads();
 
+    constexpr int kParts = kThreads / kCells;  // threads per cell
+    const int cell = tid % kCells, part = tid / kCells;
+    const int c_lo = part * (f / kParts), c_hi = c_lo + f / kParts;
     const bool issuer = TMA2D ? (tid == 0) : (tid < f);
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+
+    bool dirty[2] = {false, false};       // CTA-uniform
+    int32_t r_prev[2] = {-1, -1};         // the row this thread copied into buffer k last time
+    int64_t t = blockIdx.x;
+    int32_t r_next = -1;
+    if (t < n_tiles) {
         const int b = static_cast<int>(t / tiles_per_plane);
-        const int64_t cell0 = (t % tiles_per_plane) * kTileCells;
-        const int ncell = static_cast<int>(tmin<int64_t>(kTileCells, plane - cell0));
-        const int32_t r = (tid < ncell) ? __ldg(cell_row + b * plane + cell0 + tid) : -1;
+        const int64_t cell0 = (t % tiles_per_plane) * kCells;
+        if (cell0 + cell < plane) r_next = __ldg(cell_row + b * plane + cell0 + cell);
+    }
+    for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        const int k = it & 1;
+        float *tile = s_tiles + k * tile_floats;
+        const int b = static_cast<int>(t / tiles_per_plane);
+        const int64_t cell0 = (t % tiles_per_plane) * kCells;
+        const int ncell = static_cast<int>(tmin<int64_t>(kCells, plane - cell0));
+        const int32_t r = r_next;
+        r_next = -1;
+        const int64_t tn = t + gridDim.x;
+        if (tn < n_tiles) {
+            const int bn = static_cast<int>(tn / tiles_per_plane);
+            const int64_t celln = (tn % tiles_per_plane) * kCells;
+            if (celln + cell < plane) r_next = __ldg(cell_row + bn * plane + celln + cell);
+        }
         const int any = __syncthreads_or(r >= 0);
-        if (any) {
-            if (issuer) bulk_wait_read_all();  // earlier stores still read the zero tile
+        if (any || dirty[k]) {
+            if (issuer) bulk_wait_read_1();  // the store issued from this buffer two tiles ago has released it
             __syncthreads();
+            if (dirty[k] && r_prev[k] >= 0)
+                for (int c = c_lo; c < c_hi; ++c) tile[c * kCells + cell] = 0.f;
             if (r >= 0) {
-                const float4 *src = reinterpret_cast<const float4 *>(feats + static_cast<int64_t>(r) * f);
-                for (int c = 0; c < f; c += 4) {
-                    const float4 v = __ldg(src + (c >> 2));
-                    s_tile[(c + 0) * kTileCells + tid] = v.x;
-                    s_tile[(c + 1) * kTileCells + tid] = v.y;
-                    s_tile[(c + 2) * kTileCells + tid] = v.z;
-                    s_tile[(c + 3) * kTileCells + tid] = v.w;
+                const float4 *src = reinterpret_cast<const float4 *>(feats + static_cast<int64_t>(r) * f + c_lo);
+                for (int c = c_lo; c < c_hi; c += 4) {
+                    const float4 v = __ldg(src++);
+                    tile[(c + 0) * kCells + cell] = v.x;
+                    tile[(c + 1) * kCells + cell] = v.y;
+                    tile[(c + 2) * kCells + cell] = v.z;
+                    tile[(c + 3) * kCells + cell] = v.w;
                 }
             }
             fence_proxy_async();
             __syncthreads();
+            dirty[k] = any != 0;
+            r_prev[k] = r;
         }
         if (TMA2D) {
             if (tid == 0) {
-                tma_store_2d(&tmap, s_tile, static_cast<int>(cell0), b * f);
+                tma_store_2d(&tmap, tile, static_cast<int>(cell0), b * f);
                 bulk_commit();
             }
         } else if (tid < f) {
-            bulk_store_1d(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, s_tile + tid * kTileCells,
+            bulk_store_1d(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, tile + tid * kCells,
                           static_cast<uint32_t>(ncell) * 4u);
             bulk_commit();
-        }
-        if (any) {
-            if (issuer) bulk_wait_read_all();
-            __syncthreads();
-            if (r >= 0)
-                for (int c = 0; c < f; ++c) s_tile[c * kTileCells + tid] = 0.f;
-            fence_proxy_async();
-            // the next tile's __syncthreads_or orders these writes before any later store is issued
         }
     }
     if (issuer) bulk_wait_all();
@@ -211,8 +237,8 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
     if (nb == 0 || plane == 0 || f == 0) return cudaSuccess;
     const bool vec_ok = (plane % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0) &&
                         (reinterpret_cast<uintptr_t>(feats) % 16 == 0) && (f % 4 == 0);
-    const size_t smem = sizeof(float) * f * kTileCells;
-    const bool async_ok = vec_ok && f <= kThreads && smem <= 200 * 1024;
+    const size_t smem = sizeof(float) * 2 * f * kCells;
+    const bool async_ok = vec_ok && f <= kThreads && f % 8 == 0 && smem <= 200 * 1024;
     if (variant == 0) variant = async_ok ? 3 : 1;
     if ((variant == 2 || variant == 3) && !async_ok) variant = 1;
     if (variant == 3 && !get_encode_fn()) variant = 2;
@@ -229,14 +255,14 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
         return cudaGetLastError();
     }
 
-    const int tpp = static_cast<int>((plane + kTileCells - 1) / kTileCells);
+    const int tpp = static_cast<int>((plane + kCells - 1) / kCells);
     const int64_t n_tiles = static_cast<int64_t>(nb) * tpp;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (variant == 3) {
         const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(plane), static_cast<cuuint64_t>(nb) * f};
         const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(plane) * sizeof(float)};
-        const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileCells), static_cast<cuuint32_t>(f)};
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(kCells), static_cast<cuuint32_t>(f)};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bev, gdim, gstride, box, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -245,7 +271,7 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
     }
     int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     const int64_t grid = tmin<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * per_sm);
     if (variant == 3) {
         static bool attr3 = false;

@@ -2,13 +2,17 @@
 // (replaces the spconv CPU call behind src/lidar-encoder/pcdet/datasets/processor/data_processor.py:16-61,133-180):
 //
 //   k_quantize_insert   coalesced float4 tile loads -> fp32 sub/div/floor -> cell key -> open-addressing hash insert
-//                       (atomicCAS), atomicMin(first point index), atomicAdd(count).  __match_any_sync merges the
-//                       lanes of a warp that hit the same cell so one lane talks to HBM for the whole group.
-//   k_scan_assign       single-pass chained scan (decoupled look-back) over points in index order of
-//                       [point is the first of its cell] and of the cell counts: gives every pillar its id in
-//                       first-appearance order and the start of its point list, with no sort.
-//   k_place             writes each point index into its pillar's list; block 0 also turns the per-frame
-//                       first-appearance counts into output rows under the max_voxels cap.
+//                       (atomicCAS straight on the slot, no probing load), then atomicMin(first point index) and
+//                       atomicAdd(count) issued back to back.  __match_any_sync merges the lanes of a warp that hit
+//                       the same cell so one lane talks to HBM for the whole group.  One point per thread: the kernel
+//                       is a chain of L2 round trips, so it wants as many warps in flight as the SMs hold.
+//   k_scan_assign       single-pass scan over points in index order of [point is the first of its cell] and of the
+//                       cell counts: gives every pillar its id in first-appearance order and the start of its point
+//                       list, with no sort.  Tiles publish their aggregate at once; a tile sums the aggregates of the
+//                       tiles of its 256-tile group in ONE parallel read plus the published prefix of the previous
+//                       group, so the dependency chain is n_tiles/256 long instead of n_tiles.
+//   k_place             moves each point into its pillar's list (index list and/or 32-byte point records); block 0
+//                       also turns the per-frame first-appearance counts into output rows under the max_voxels cap.
 //
 // The per-pillar "first P points in index order" rule is applied by the consumers (pfn.cu) with a radix select over
 // the list, so nothing here depends on the order in which atomics land.
@@ -19,7 +23,8 @@ namespace pillars {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPerThread = kTile / kThreads;  // 4
+constexpr int kPerThread = kTile / kThreads;  // 4 (scan kernel)
+constexpr int kGroup = 256;                   // tiles per look-back group
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k)
 {
@@ -64,124 +69,125 @@ __global__ void k_frame_offsets(const float *__restrict__ pts, int64_t n, int st
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1
+// K1: one point per thread, 256 points per CTA
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int col0,
                   const int32_t *__restrict__ frame_offsets, int nb, GridDev gd, HashEntry *__restrict__ table,
                   uint32_t cap, int32_t *__restrict__ point_slot, uint32_t *__restrict__ point_arrival, int vec_ok)
 {
-    extern __shared__ __align__(16) float s_pts[];  // [kTile * stride]
-    __shared__ int32_t s_off[kMaxFrames + 1];
+    extern __shared__ __align__(16) float s_pts[];  // [kThreads * stride]
+    __shared__ int s_b0, s_b1;
 
     const int tid = threadIdx.x;
-    const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kTile;
-    const int count = static_cast<int>(tmin<int64_t>(kTile, n - tile_start));
+    const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kThreads;
+    const int count = static_cast<int>(tmin<int64_t>(kThreads, n - tile_start));
 
-    for (int i = tid; i <= nb; i += kThreads) s_off[i] = frame_offsets[i];
-
-    // one contiguous, fully coalesced read of the tile (rows are 16..32 B, so per-row vector loads would not be)
+    // one contiguous, fully coalesced read of the tile (rows are 12..64 B, so per-row vector loads would not be)
     const float *src = points + tile_start * stride;
     const int nfl = count * stride;
     if (vec_ok) {
         const float4 *src4 = reinterpret_cast<const float4 *>(src);
         float4 *dst4 = reinterpret_cast<float4 *>(s_pts);
         const int n4 = nfl >> 2;
-#pragma unroll 4
         for (int i = tid; i < n4; i += kThreads) dst4[i] = __ldg(src4 + i);
         for (int i = (n4 << 2) + tid; i < nfl; i += kThreads) s_pts[i] = __ldg(src + i);
     } else {
         for (int i = tid; i < nfl; i += kThreads) s_pts[i] = __ldg(src + i);
     }
+    // frames touched by this tile: [b0, b1]; two binary searches per CTA instead of one per point
+    if (tid < 2) {
+        const int64_t i = tid == 0 ? tile_start : tile_start + count - 1;
+        int lo = 0, hi = nb;  // invariant: offsets[lo] <= i < offsets[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(frame_offsets + mid) <= i) lo = mid; else hi = mid;
+        }
+        if (tid == 0) s_b0 = lo; else s_b1 = lo;
+    }
     __syncthreads();
 
-    const unsigned lane_lt = lanemask_lt();
-    const int lane = tid & 31;
-
-#pragma unroll
-    for (int k = 0; k < kPerThread; ++k) {
-        const int local = k * kThreads + tid;  // a warp covers 32 consecutive points: lane order == index order
-        const int64_t i = tile_start + local;
-        bool valid = false;
-        uint32_t key = 0;
-        if (local < count) {
-            const float *p = s_pts + local * stride + col0;
-            // IEEE fp32, true division, no contraction: bit-identical to the CPU voxeliser
-            const float fx = floorf(__fdiv_rn(__fsub_rn(p[0], gd.rmin[0]), gd.vsz[0]));
-            const float fy = floorf(__fdiv_rn(__fsub_rn(p[1], gd.rmin[1]), gd.vsz[1]));
-            const float fz = floorf(__fdiv_rn(__fsub_rn(p[2], gd.rmin[2]), gd.vsz[2]));
-            valid = (fx >= 0.f) && (fx < static_cast<float>(gd.g[0])) && (fy >= 0.f) &&
-                    (fy < static_cast<float>(gd.g[1])) && (fz >= 0.f) && (fz < static_cast<float>(gd.g[2]));
-            if (valid) {
-                // frame = last b with s_off[b] <= i
-                int lo = 0, hi = nb;  // invariant: s_off[lo] <= i < s_off[hi]
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= i) lo = mid; else hi = mid;
-                }
-                const uint32_t cx = static_cast<uint32_t>(fx), cy = static_cast<uint32_t>(fy),
-                               cz = static_cast<uint32_t>(fz);
-                key = static_cast<uint32_t>(lo) * gd.cells + (cz * gd.g[1] + cy) * gd.g[0] + cx;
-            }
-        }
-        const unsigned active = __ballot_sync(0xffffffffu, valid);
-        int32_t slot_out = -1;
-        uint32_t arrival = 0;
+    const int64_t i = tile_start + tid;
+    bool valid = false;
+    uint32_t key = 0;
+    if (tid < count) {
+        const float *p = s_pts + tid * stride + col0;
+        // IEEE fp32, true division, no contraction: bit-identical to the CPU voxeliser
+        const float fx = floorf(__fdiv_rn(__fsub_rn(p[0], gd.rmin[0]), gd.vsz[0]));
+        const float fy = floorf(__fdiv_rn(__fsub_rn(p[1], gd.rmin[1]), gd.vsz[1]));
+        const float fz = floorf(__fdiv_rn(__fsub_rn(p[2], gd.rmin[2]), gd.vsz[2]));
+        valid = (fx >= 0.f) && (fx < static_cast<float>(gd.g[0])) && (fy >= 0.f) && (fy < static_cast<float>(gd.g[1])) &&
+                (fz >= 0.f) && (fz < static_cast<float>(gd.g[2]));
         if (valid) {
-            const unsigned peers = __match_any_sync(active, key);
-            const int leader = __ffs(peers) - 1;  // lowest lane == smallest point index of the group
-            uint32_t slot = 0, base = 0;
-            if (lane == leader) {
-                slot = static_cast<uint32_t>((static_cast<uint64_t>(hash_key(key)) * cap) >> 32);
-                while (true) {
-                    uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&table[slot].key);
-                    if (cur == kEmptyKey) cur = atomicCAS(&table[slot].key, kEmptyKey, key);
-                    if (cur == kEmptyKey || cur == key) break;
-                    slot = (slot + 1 == cap) ? 0u : slot + 1;
-                }
-                atomicMin(&table[slot].first, static_cast<uint32_t>(i));
-                base = atomicAdd(&table[slot].cnt, static_cast<uint32_t>(__popc(peers))) + 1u;
+            int b = s_b0;  // almost always the only frame of the tile
+            const int b1 = s_b1;
+            while (b < b1 && __ldg(frame_offsets + b + 1) <= i) ++b;
+            const uint32_t cx = static_cast<uint32_t>(fx), cy = static_cast<uint32_t>(fy), cz = static_cast<uint32_t>(fz);
+            key = static_cast<uint32_t>(b) * gd.cells + (cz * gd.g[1] + cy) * gd.g[0] + cx;
+        }
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    int32_t slot_out = -1;
+    uint32_t arrival = 0;
+    if (valid) {
+        const int lane = tid & 31;
+        const unsigned peers = __match_any_sync(active, key);
+        const int leader = __ffs(peers) - 1;  // lowest lane == smallest point index of the group
+        uint32_t slot = 0, base = 0;
+        if (lane == leader) {
+            slot = static_cast<uint32_t>((static_cast<uint64_t>(hash_key(key)) * cap) >> 32);
+            while (true) {
+                const uint32_t cur = atomicCAS(&table[slot].key, kEmptyKey, key);
+                if (cur == kEmptyKey || cur == key) break;
+                slot = (slot + 1 == cap) ? 0u : slot + 1;
             }
-            slot = __shfl_sync(peers, slot, leader);
-            base = __shfl_sync(peers, base, leader);
-            slot_out = static_cast<int32_t>(slot);
-            arrival = base + static_cast<uint32_t>(__popc(peers & lane_lt));
+            atomicMin(&table[slot].first, static_cast<uint32_t>(i));  // independent of the add below: both in flight
+            base = atomicAdd(&table[slot].cnt, static_cast<uint32_t>(__popc(peers))) + 1u;
         }
-        if (local < count) {
-            point_slot[i] = slot_out;
-            point_arrival[i] = arrival;
-        }
+        slot = __shfl_sync(peers, slot, leader);
+        base = __shfl_sync(peers, base, leader);
+        slot_out = static_cast<int32_t>(slot);
+        arrival = base + static_cast<uint32_t>(__popc(peers & lanemask_lt()));
+    }
+    if (tid < count) {
+        point_slot[i] = slot_out;
+        point_arrival[i] = arrival;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: chained scan.  Descriptor = status(2) | pillars(31) | listed points(31)
+// K2: scan.  Descriptor = valid(1) | pillars(31) | listed points(31); running sums travel as (pillars << 32 | listed)
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned long long kStatusAgg = 1ull << 62;
-constexpr unsigned long long kStatusPrefix = 2ull << 62;
-constexpr unsigned long long kValMask = (1ull << 62) - 1;
+constexpr unsigned long long kValid = 1ull << 63;
 
-// running sums travel as (pillars << 32 | listed); descriptors pack them into 31+31 bits
 __device__ __forceinline__ unsigned long long pack_desc(unsigned long long v)
 {
-    return ((v >> 32) << 31) | (v & 0x7FFFFFFFull);
+    return kValid | ((v >> 32) << 31) | (v & 0x7FFFFFFFull);
 }
 __device__ __forceinline__ unsigned long long unpack_desc(unsigned long long d)
 {
-    d &= kValMask;
+    d &= ~kValid;
     return ((d >> 31) << 32) | (d & 0x7FFFFFFFull);
+}
+__device__ __forceinline__ unsigned long long wait_desc(const unsigned long long *p)
+{
+    unsigned long long d;
+    do {
+        d = ld_relaxed_u64(p);
+    } while (!(d & kValid));
+    return unpack_desc(d);
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slot, HashEntry *__restrict__ table,
-              Header *__restrict__ hdr, unsigned long long *__restrict__ tile_desc,
+              Header *__restrict__ hdr, unsigned long long *__restrict__ tile_agg, unsigned long long *__restrict__ tile_prefix,
               uint32_t *__restrict__ pillar_key, uint32_t *__restrict__ pillar_list,
               uint32_t *__restrict__ pillar_cnt, const int32_t *__restrict__ frame_offsets, int nb,
               uint32_t *__restrict__ frame_gstart)
 {
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
-    __shared__ unsigned long long s_tile_excl;
+    __shared__ unsigned long long s_look[kThreads / 32];
     __shared__ uint32_t s_thr_excl[kThreads];
     __shared__ uint8_t s_thr_flags[kThreads];
 
@@ -200,21 +206,19 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
 #pragma unroll
         for (int k = 0; k < kPerThread; ++k) slot[k] = (i0 + k < n) ? point_slot[i0 + k] : -1;
     }
+    uint4 ent[kPerThread];
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k)  // all gathers in flight before the first use
+        ent[k] = slot[k] >= 0 ? *reinterpret_cast<const uint4 *>(&table[slot[k]]) : make_uint4(0, 0xFFFFFFFFu, 0, 0);
     unsigned long long val[kPerThread];
-    uint32_t ekey[kPerThread];
     unsigned flags = 0;
     unsigned long long tsum = 0;
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
         val[k] = 0;
-        ekey[k] = 0;
-        if (slot[k] >= 0) {
-            const uint4 e = *reinterpret_cast<const uint4 *>(&table[slot[k]]);
-            if (e.y == static_cast<uint32_t>(i0 + k)) {  // this point opened the pillar
-                val[k] = (1ull << 32) | static_cast<unsigned long long>(e.z + 1u);
-                ekey[k] = e.x;
-                flags |= 1u << k;
-            }
+        if (slot[k] >= 0 && ent[k].y == static_cast<uint32_t>(i0 + k)) {  // this point opened the pillar
+            val[k] = (1ull << 32) | static_cast<unsigned long long>(ent[k].z + 1u);
+            flags |= 1u << k;
         }
         tsum += val[k];
     }
@@ -227,51 +231,31 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    unsigned long long warp_excl = 0, tile_agg = 0;
+    unsigned long long warp_excl = 0, tile_sum = 0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) {
         const unsigned long long s = s_warp[w];
         if (w < warp) warp_excl += s;
-        tile_agg += s;
+        tile_sum += s;
     }
     const unsigned long long thr_excl = warp_excl + incl - tsum;
+    if (tid == 0) st_relaxed_u64(&tile_agg[tile], pack_desc(tile_sum));  // visible to the successors at once
 
-    // decoupled look-back, warp 0
-    if (warp == 0) {
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(&tile_desc[0], kStatusPrefix | pack_desc(tile_agg));
-        } else {
-            if (lane == 0) st_relaxed_u64(&tile_desc[tile], kStatusAgg | pack_desc(tile_agg));
-            int64_t j = static_cast<int64_t>(tile) - 1;
-            while (true) {
-                const int64_t idx = j - lane;
-                unsigned long long d = kStatusPrefix;  // virtual tile before 0: prefix 0
-                if (idx >= 0) {
-                    do {
-                        d = ld_relaxed_u64(&tile_desc[idx]);
-                    } while ((d >> 62) == 0);
-                }
-                const unsigned pmask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                unsigned long long contrib = unpack_desc(d);
-                if (pmask) {
-                    const int firstp = __ffs(pmask) - 1;
-                    if (lane > firstp) contrib = 0;
-                }
+    // look-back: aggregates of the tiles of my group that precede me (one parallel read) + prefix of the previous group
+    const uint32_t group_first = tile & ~static_cast<uint32_t>(kGroup - 1);
+    unsigned long long look = 0;
+    if (group_first + tid < tile) look = wait_desc(&tile_agg[group_first + tid]);
+    if (tid == kThreads - 1 && group_first > 0) look += wait_desc(&tile_prefix[group_first - 1]);
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, s);
-                excl += contrib;
-                if (pmask) break;
-                j -= 32;
-            }
-            if (lane == 0) st_relaxed_u64(&tile_desc[tile], kStatusPrefix | pack_desc(excl + tile_agg));
-        }
-        if (lane == 0) s_tile_excl = excl;
-    }
+    for (int s = 16; s > 0; s >>= 1) look += __shfl_xor_sync(0xffffffffu, look, s);
+    if (lane == 0) s_look[warp] = look;
     s_thr_excl[tid] = static_cast<uint32_t>(thr_excl >> 32);
     s_thr_flags[tid] = static_cast<uint8_t>(flags);
     __syncthreads();
-    const unsigned long long tile_excl = s_tile_excl;
+    unsigned long long tile_excl = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) tile_excl += s_look[w];
+    if (tid == 0 && (tile & (kGroup - 1)) == kGroup - 1) st_relaxed_u64(&tile_prefix[tile], pack_desc(tile_excl + tile_sum));
 
     unsigned long long run = tile_excl + thr_excl;
 #pragma unroll
@@ -279,7 +263,7 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
         if (flags & (1u << k)) {
             const uint32_t g = static_cast<uint32_t>(run >> 32);
             table[slot[k]].gid = g;
-            pillar_key[g] = ekey[k];
+            pillar_key[g] = ent[k].x;
             pillar_list[g] = static_cast<uint32_t>(run & 0xFFFFFFFFull);
             pillar_cnt[g] = static_cast<uint32_t>(val[k] & 0xFFFFFFFFull);
             run += val[k];
@@ -288,7 +272,7 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
 
     // first-appearance id at every frame start that falls into this tile
     const bool last_tile = (tile == n_tiles - 1);
-    const uint32_t tile_total = static_cast<uint32_t>((tile_excl + tile_agg) >> 32);
+    const uint32_t tile_total = static_cast<uint32_t>((tile_excl + tile_sum) >> 32);
     for (int f = tid; f <= nb; f += kThreads) {
         const int64_t pos = frame_offsets[f];
         if (pos >= tile_start && pos < tile_start + kTile && pos < n) {
@@ -302,7 +286,7 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
     }
     if (last_tile && tid == 0) {
         hdr->total_pillars = tile_total;
-        hdr->total_listed = static_cast<uint32_t>((tile_excl + tile_agg) & 0xFFFFFFFFull);
+        hdr->total_listed = static_cast<uint32_t>((tile_excl + tile_sum) & 0xFFFFFFFFull);
     }
 }
 
@@ -310,9 +294,10 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
 // K3: lists + output rows per frame
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_place(int64_t n, const int32_t *__restrict__ point_slot, const uint32_t *__restrict__ point_arrival,
+k_place(const float *__restrict__ points, int64_t n, int stride, int col0, int c_point,
+        const int32_t *__restrict__ point_slot, const uint32_t *__restrict__ point_arrival,
         const HashEntry *__restrict__ table, const uint32_t *__restrict__ pillar_list,
-        uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ frame_gstart,
+        uint32_t *__restrict__ sorted_idx, PointRecord *__restrict__ records, const uint32_t *__restrict__ frame_gstart,
         uint32_t *__restrict__ frame_rowbase, int nb, int max_voxels, int32_t *__restrict__ pillar_count)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
@@ -320,7 +305,23 @@ k_place(int64_t n, const int32_t *__restrict__ point_slot, const uint32_t *__res
         const int32_t s = point_slot[i];
         if (s >= 0) {
             const uint32_t g = table[s].gid;
-            sorted_idx[pillar_list[g] + point_arrival[i]] = static_cast<uint32_t>(i);
+            const uint32_t arrival = point_arrival[i];
+            const uint32_t pos = pillar_list[g] + arrival;
+            if (sorted_idx) sorted_idx[pos] = static_cast<uint32_t>(i);
+            if (records) {
+                // one full 32-byte sector per point: the feature kernel then streams its input instead of gathering
+                const float *p = points + i * stride + col0;
+                float4 a, b;
+                a.x = __ldg(p); a.y = __ldg(p + 1); a.z = __ldg(p + 2);
+                a.w = c_point > 3 ? __ldg(p + 3) : 0.f;
+                b.x = c_point > 4 ? __ldg(p + 4) : 0.f;
+                b.y = __uint_as_float(static_cast<uint32_t>(i));
+                b.z = __uint_as_float(g);
+                b.w = __uint_as_float(arrival);
+                float4 *dst = reinterpret_cast<float4 *>(records + pos);
+                dst[0] = a;
+                dst[1] = b;
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -360,9 +361,9 @@ cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, const int32_t *frame_offsets,
-                                int nb, const GridDev &gd, const Workspace &ws, int32_t *pillar_count,
-                                cudaStream_t st)
+cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, int c_point,
+                                const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
+                                int32_t *pillar_count, bool want_index_lists, bool want_records, cudaStream_t st)
 {
     cudaError_t err;
     if ((err = cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st)) != cudaSuccess) return err;
@@ -375,21 +376,18 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
         }
         return cudaSuccess;
     }
-    const size_t smem = sizeof(float) * kTile * stride;
-    const int vec_ok = (reinterpret_cast<uintptr_t>(points) % 16 == 0) ? 1 : 0;  // tile starts are 1024 rows apart
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_quantize_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
-    }
-    k_quantize_insert<<<ws.n_tiles, kThreads, smem, st>>>(points, n, stride, col0, frame_offsets, nb, gd, ws.table, ws.cap,
-                                                          ws.point_slot, ws.point_arrival, vec_ok);
-    k_scan_assign<<<ws.n_tiles, kThreads, 0, st>>>(n, ws.n_tiles, ws.point_slot, ws.table, ws.hdr, ws.tile_desc,
-                                                   ws.pillar_key, ws.pillar_list, ws.pillar_cnt, frame_offsets, nb,
-                                                   ws.frame_gstart);
+    const size_t smem = sizeof(float) * kThreads * stride;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(points) % 16 == 0) ? 1 : 0;  // tile starts are 256 rows apart
     const unsigned pb = static_cast<unsigned>((n + kThreads - 1) / kThreads);
-    k_place<<<pb, kThreads, 0, st>>>(n, ws.point_slot, ws.point_arrival, ws.table, ws.pillar_list, ws.sorted_idx,
-                                     ws.frame_gstart, ws.frame_rowbase, nb, gd.max_voxels, pillar_count);
+    k_quantize_insert<<<pb, kThreads, smem, st>>>(points, n, stride, col0, frame_offsets, nb, gd, ws.table, ws.cap,
+                                                  ws.point_slot, ws.point_arrival, vec_ok);
+    k_scan_assign<<<ws.n_tiles, kThreads, 0, st>>>(n, ws.n_tiles, ws.point_slot, ws.table, ws.hdr, ws.tile_desc,
+                                                   ws.tile_prefix, ws.pillar_key, ws.pillar_list, ws.pillar_cnt,
+                                                   frame_offsets, nb, ws.frame_gstart);
+    k_place<<<pb, kThreads, 0, st>>>(points, n, stride, col0, c_point, ws.point_slot, ws.point_arrival, ws.table,
+                                     ws.pillar_list, want_index_lists ? ws.sorted_idx : nullptr,
+                                     want_records ? ws.records : nullptr, ws.frame_gstart, ws.frame_rowbase, nb,
+                                     gd.max_voxels, pillar_count);
     note_launch(3);
     return cudaGetLastError();
 }

@@ -78,6 +78,10 @@ class PfnParams:
     use_absolute_xyz: bool
     with_distance: bool
     offset: Tuple[float, float, float]
+    # host copies (numpy float32): the fast kernel takes its weights as kernel parameters
+    weight_host: Optional[np.ndarray] = None
+    scale_host: Optional[np.ndarray] = None
+    shift_host: Optional[np.ndarray] = None
 
     def native(self) -> PillarsPfn:
         p = PillarsPfn()
@@ -91,6 +95,10 @@ class PfnParams:
         p.weight = self.weight.data_ptr()
         p.scale = self.scale.data_ptr()
         p.shift = self.shift.data_ptr()
+        if self.weight_host is not None and self.scale_host is not None and self.shift_host is not None:
+            p.weight_host = self.weight_host.ctypes.data
+            p.scale_host = self.scale_host.ctypes.data
+            p.shift_host = self.shift_host.ctypes.data
         return p
 
 
@@ -110,9 +118,10 @@ def fold_pfn(weight: torch.Tensor, bn: Optional[Tuple[torch.Tensor, torch.Tensor
         sh = bias.detach().double() if bias is not None else torch.zeros(f, dtype=torch.float64)
     # pillar_vfe.py:79-81: python floats (double), later promoted into fp32 tensor arithmetic
     off = tuple(float(voxel_size[i]) / 2 + float(point_cloud_range[i]) for i in range(3))
-    return PfnParams(w, sc.to(device=device, dtype=torch.float32).contiguous(),
-                     sh.to(device=device, dtype=torch.float32).contiguous(), int(c_point), bool(use_absolute_xyz),
-                     bool(with_distance), off)
+    sc32, sh32 = sc.to(torch.float32).contiguous(), sh.to(torch.float32).contiguous()
+    return PfnParams(w, sc32.to(device), sh32.to(device), int(c_point), bool(use_absolute_xyz), bool(with_distance), off,
+                     weight_host=np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32),
+                     scale_host=np.ascontiguousarray(sc32.cpu().numpy()), shift_host=np.ascontiguousarray(sh32.cpu().numpy()))
 
 
 def frame_offsets_from_points(points_b: torch.Tensor, batch_size: int) -> torch.Tensor:
@@ -292,6 +301,11 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
                                  ctypes.byref(nat), ctypes.byref(out), buffers.ws.data_ptr(), buffers.ws.numel(),
                                  SCATTER_VARIANTS[scatter_variant], _stream_ptr()), "pillars_encode_bev")
     return res
+
+
+def force_generic_features(on: bool) -> None:
+    """Test / measurement hook: run the generic feature kernel even when the fast one is eligible."""
+    _native.load().pillars_force_generic_features(int(bool(on)))
 
 
 def last_launch_count() -> int:

@@ -262,9 +262,17 @@ def _run_fused(L, dev, pts, offs, grid, sd, c, variant="auto", **kw):
                             scatter_variant=variant, **kw)
 
 
+@pytest.fixture(params=["fast", "generic"])
+def feature_kernel(request, L):
+    """Both feature kernels: the constant-bank fast one (default when eligible) and the generic 16-lane one."""
+    L.ops.force_generic_features(request.param == "generic")
+    yield request.param
+    L.ops.force_generic_features(False)
+
+
 @pytest.mark.parametrize("name", ["cfg1_full_sweep", "cfg1_p20", "tenSweep_maxvox30000_binds", "waymo_0.1m",
-                                  "cap_binds_p4", "maxvox_binds"])
-def test_fused_path_vs_oracle(name, dev, L, oracle):
+                                  "cap_binds_p4", "maxvox_binds", "p1_maxvox1"])
+def test_fused_path_vs_oracle(name, feature_kernel, dev, L, oracle):
     pts, offs, rng, vs, p, mv = _make_case(name)
     c = pts.shape[1]
     grid = L.GridSpec.from_range(rng, vs, p, mv)
@@ -287,6 +295,29 @@ def test_fused_path_vs_oracle(name, dev, L, oracle):
     # ... and within tolerance of the all-oracle canvas, with exactly the same empty cells
     ref_bev = oracle.scatter_bev(ref_f, ref_v["coords"], nx, ny, batch_size=nb)
     np.testing.assert_allclose(bev, ref_bev, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+
+
+def test_fused_huge_pillar_spanning_chunks(feature_kernel, dev, L, oracle):
+    """One cell holding 20 000 points (its list spans ~80 chunks of the fast kernel) next to ordinary pillars."""
+    rng, vs = (0.0, 0.0, 0.0, 8.0, 8.0, 2.0), (1.0, 1.0, 2.0)
+    r = np.random.default_rng(11)
+    big = np.concatenate([r.uniform(3.0, 4.0, (20000, 2)), r.uniform(0, 2, (20000, 1)), r.uniform(0, 255, (20000, 1)),
+                          r.uniform(0, 0.5, (20000, 1))], 1).astype(np.float32)
+    rest = np.concatenate([r.uniform(-1, 9, (6000, 2)), r.uniform(-0.5, 2.5, (6000, 1)), r.uniform(0, 255, (6000, 1)),
+                           r.uniform(0, 0.5, (6000, 1))], 1).astype(np.float32)
+    pts = np.concatenate([big, rest])[r.permutation(26000)]
+    offs = np.array([0, 9000, 9000, 26000], np.int32)
+    for p_max in (32, 5):
+        grid = L.GridSpec.from_range(rng, vs, p_max, 60)
+        sd = oracle.random_pfn_params(11, [64], True, seed=13)
+        res = _run_fused(L, dev, pts, offs, grid, sd, 5)
+        m = int(res["pillar_count"][-1].item())
+        ref_v = oracle.voxelize_batch(pts, offs, rng, vs, p_max, 60)
+        assert m == ref_v["coords"].shape[0]
+        np.testing.assert_array_equal(res["voxel_coords"][:m].cpu().numpy(), ref_v["coords"])
+        np.testing.assert_array_equal(res["voxel_num_points"][:m].cpu().numpy(), ref_v["num_points"])
+        ref_f = oracle.pillar_vfe(ref_v["voxels"], ref_v["num_points"], ref_v["coords"], sd, vs, rng).numpy()
+        np.testing.assert_allclose(res["pillar_features"][:m].cpu().numpy(), ref_f, rtol=FEAT_RTOL, atol=FEAT_ATOL)
 
 
 def test_fused_path_c4_and_scatter_variants_agree(dev, L, oracle):
@@ -323,7 +354,7 @@ def test_scatter_odd_shapes(dev, L, oracle):
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties + full oracle comparison where it takes seconds
 # ------------------------------------------------------------------------------------------------
-def test_cfg2_full_size_properties_and_oracle(dev, L, oracle):
+def test_cfg2_full_size_properties_and_oracle(feature_kernel, dev, L, oracle):
     model, gc, nb = synth.WORKLOADS["cfg2_nuscenes32_b16_pillar0.2_bev512"]
     pts, offs = synth.make_batch(nb, model, 5)
     grid = L.GridSpec.from_range(gc.point_cloud_range, gc.voxel_size, gc.max_points_per_voxel, gc.max_voxels)
