@@ -72,11 +72,10 @@ __device__ __forceinline__ void point_half(const FastParams &p, bool kept, float
 __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_constant__ FastParams p)
 {
     extern __shared__ __align__(16) float s_y[];  // [kHalf][kLd]
-    __shared__ float s_cx[kFT], s_cy[kFT], s_cz[kFT], s_mx[kFT], s_my[kFT], s_mz[kFT];
-    __shared__ int32_t s_row[kFT];
+    __shared__ float4 s_c4[kFT];  // pillar centre x,y,z ; w = 1.0 when the pillar has empty (padded) slots
+    __shared__ float4 s_m4[kFT];  // mean - centre x,y,z ; w = output row as int bits (-1: pillar not emitted)
     __shared__ uint32_t s_thr[kFT], s_pos0[kFT], s_cnt[kFT];
     __shared__ int16_t s_start[kFT + 1];
-    __shared__ uint8_t s_pad[kFT];
     __shared__ uint16_t s_big[kFT];
     __shared__ int s_nbig, s_tail_len;
     __shared__ int s_warp_cnt[kFT / 32];
@@ -139,13 +138,10 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
         const float cx = __fadd_rn(__fmul_rn(static_cast<float>(x), p.vsz[0]), p.off[0]);
         const float cy = __fadd_rn(__fmul_rn(static_cast<float>(y), p.vsz[1]), p.off[1]);
         const float cz = __fadd_rn(__fmul_rn(static_cast<float>(z), p.vsz[2]), p.off[2]);
-        s_cx[pl] = cx;
-        s_cy[pl] = cy;
-        s_cz[pl] = cz;
-        s_row[pl] = live ? static_cast<int32_t>(row) : -1;
+        s_c4[pl] = make_float4(cx, cy, cz, n < static_cast<uint32_t>(P) ? 1.f : 0.f);
+        float4 m4 = make_float4(0.f, 0.f, 0.f, __int_as_float(live ? static_cast<int32_t>(row) : -1));
         s_cnt[pl] = n;
         s_pos0[pl] = pos;
-        s_pad[pl] = n < static_cast<uint32_t>(P) ? 1 : 0;
         s_thr[pl] = 0xFFFFFFFFu;
         if (live) {
             if (n > static_cast<uint32_t>(P)) {
@@ -159,9 +155,9 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
                     sz += static_cast<double>(q.z);
                 }
                 const float nf = static_cast<float>(n);
-                s_mx[pl] = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), cx);  // pillar_vfe.py:97, relative to the centre
-                s_my[pl] = __fsub_rn(__fdiv_rn(static_cast<float>(sy), nf), cy);
-                s_mz[pl] = __fsub_rn(__fdiv_rn(static_cast<float>(sz), nf), cz);
+                m4.x = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), cx);  // pillar_vfe.py:97, relative to the centre
+                m4.y = __fsub_rn(__fdiv_rn(static_cast<float>(sy), nf), cy);
+                m4.z = __fsub_rn(__fdiv_rn(static_cast<float>(sz), nf), cz);
             }
             if (p.voxel_coords)
                 *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) =
@@ -175,6 +171,7 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
                 s_tail_len = over > 0 ? static_cast<int>(over) : 0;
             }
         }
+        s_m4[pl] = m4;
     }
     __syncthreads();
 
@@ -214,10 +211,11 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
         }
         if (lane == 0) {
             const float nf = static_cast<float>(P);
+            const float4 c4 = s_c4[bp];
             s_thr[bp] = prefix;
-            s_mx[bp] = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), s_cx[bp]);
-            s_my[bp] = __fsub_rn(__fdiv_rn(static_cast<float>(sy), nf), s_cy[bp]);
-            s_mz[bp] = __fsub_rn(__fdiv_rn(static_cast<float>(sz), nf), s_cz[bp]);
+            s_m4[bp].x = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), c4.x);
+            s_m4[bp].y = __fsub_rn(__fdiv_rn(static_cast<float>(sy), nf), c4.y);
+            s_m4[bp].z = __fsub_rn(__fdiv_rn(static_cast<float>(sz), nf), c4.z);
         }
     }
     __syncthreads();
@@ -225,11 +223,12 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
     // ---- my point, relative to its pillar centre ---------------------------------------------------------------------
     bool kept = false;
     float xp = 0.f, yp = 0.f, zp = 0.f;
-    if (in && pl >= 0 && s_row[pl] >= 0 && r_idx <= s_thr[pl]) {
+    if (in && pl >= 0 && __float_as_int(s_m4[pl].w) >= 0 && r_idx <= s_thr[pl]) {
         kept = true;
-        xp = __fsub_rn(ra.x, s_cx[pl]);
-        yp = __fsub_rn(ra.y, s_cy[pl]);
-        zp = __fsub_rn(ra.z, s_cz[pl]);
+        const float4 c4 = s_c4[pl];
+        xp = __fsub_rn(ra.x, c4.x);
+        yp = __fsub_rn(ra.y, c4.y);
+        zp = __fsub_rn(ra.z, c4.z);
     }
     const int tail_len = s_tail_len;
     const int last = n_pl - 1;
@@ -252,10 +251,11 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
                     const float4 *src = reinterpret_cast<const float4 *>(p.records + q0 + kFT + t0 + lane);
                     const float4 a = __ldg(src), b = __ldg(src + 1);
                     if (__float_as_uint(b.y) <= s_thr[last]) {
+                        const float4 c4 = s_c4[last];
                         tk = true;
-                        tx = __fsub_rn(a.x, s_cx[last]);
-                        ty = __fsub_rn(a.y, s_cy[last]);
-                        tz = __fsub_rn(a.z, s_cz[last]);
+                        tx = __fsub_rn(a.x, c4.x);
+                        ty = __fsub_rn(a.y, c4.y);
+                        tz = __fsub_rn(a.z, c4.z);
                         ti = a.w;
                         tt = b.x;
                     }
@@ -274,48 +274,57 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
         }
 
         // max over each pillar's points, then the per-pillar constant, ReLU and the padded-slot term
-        for (int q = slot; q < n_pl; q += kFT / 8) {
-            const int row = s_row[q];
-            if (row < 0) continue;
-            const int a0 = s_start[q], a1 = s_start[q + 1];
-            float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            for (int j = a0; j < a1; ++j) {
-#pragma unroll
-                for (int o = 0; o < 4; ++o) m[o] = fmaxf(m[o], s_y[(4 * sub + o) * kLd + j]);
-            }
-            if (q == last && tail_len > 0) {
-#pragma unroll
-                for (int o = 0; o < 4; ++o) m[o] = fmaxf(m[o], s_acc_tail[4 * sub + o]);
-            }
+        {
             const int ch = H * kHalf + 4 * sub;
-            const float cx = s_cx[q], cy = s_cy[q], cz = s_cz[q], mx = s_mx[q], my = s_my[q], mz = s_mz[q];
             const float4 k0 = *reinterpret_cast<const float4 *>(&s_wk[0][ch]), k1 = *reinterpret_cast<const float4 *>(&s_wk[1][ch]),
                          k2 = *reinterpret_cast<const float4 *>(&s_wk[2][ch]), k3 = *reinterpret_cast<const float4 *>(&s_wk[3][ch]),
                          k4 = *reinterpret_cast<const float4 *>(&s_wk[4][ch]), k5 = *reinterpret_cast<const float4 *>(&s_wk[5][ch]),
                          sh = *reinterpret_cast<const float4 *>(&s_wk[6][ch]);
-            const bool pad = s_pad[q] != 0;
-            float4 out;
-            {
-                float kc = fmaf(k0.x, cx, sh.x); kc = fmaf(k1.x, cy, kc); kc = fmaf(k2.x, cz, kc);
-                kc = fmaf(-k3.x, mx, kc); kc = fmaf(-k4.x, my, kc); kc = fmaf(-k5.x, mz, kc);
-                out.x = fmaxf(m[0] + kc, pad ? fmaxf(sh.x, 0.f) : 0.f);
+            const float4 relu_sh = make_float4(fmaxf(sh.x, 0.f), fmaxf(sh.y, 0.f), fmaxf(sh.z, 0.f), fmaxf(sh.w, 0.f));
+            const float *ycol = s_y + (4 * sub) * kLd;
+            for (int q = slot; q < n_pl; q += kFT / 8) {
+                const float4 m4 = s_m4[q];
+                const int row = __float_as_int(m4.w);
+                if (row < 0) continue;
+                const float4 c4 = s_c4[q];
+                const int a0 = s_start[q], a1 = s_start[q + 1];
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                for (int j = a0; j < a1; ++j) {
+                    m0 = fmaxf(m0, ycol[j]);
+                    m1 = fmaxf(m1, ycol[kLd + j]);
+                    m2 = fmaxf(m2, ycol[2 * kLd + j]);
+                    m3 = fmaxf(m3, ycol[3 * kLd + j]);
+                }
+                if (q == last && tail_len > 0) {
+                    m0 = fmaxf(m0, s_acc_tail[4 * sub + 0]);
+                    m1 = fmaxf(m1, s_acc_tail[4 * sub + 1]);
+                    m2 = fmaxf(m2, s_acc_tail[4 * sub + 2]);
+                    m3 = fmaxf(m3, s_acc_tail[4 * sub + 3]);
+                }
+                const bool pad = c4.w != 0.f;
+                float4 out;
+                {
+                    float kc = fmaf(k0.x, c4.x, sh.x); kc = fmaf(k1.x, c4.y, kc); kc = fmaf(k2.x, c4.z, kc);
+                    kc = fmaf(-k3.x, m4.x, kc); kc = fmaf(-k4.x, m4.y, kc); kc = fmaf(-k5.x, m4.z, kc);
+                    out.x = fmaxf(m0 + kc, pad ? relu_sh.x : 0.f);
+                }
+                {
+                    float kc = fmaf(k0.y, c4.x, sh.y); kc = fmaf(k1.y, c4.y, kc); kc = fmaf(k2.y, c4.z, kc);
+                    kc = fmaf(-k3.y, m4.x, kc); kc = fmaf(-k4.y, m4.y, kc); kc = fmaf(-k5.y, m4.z, kc);
+                    out.y = fmaxf(m1 + kc, pad ? relu_sh.y : 0.f);
+                }
+                {
+                    float kc = fmaf(k0.z, c4.x, sh.z); kc = fmaf(k1.z, c4.y, kc); kc = fmaf(k2.z, c4.z, kc);
+                    kc = fmaf(-k3.z, m4.x, kc); kc = fmaf(-k4.z, m4.y, kc); kc = fmaf(-k5.z, m4.z, kc);
+                    out.z = fmaxf(m2 + kc, pad ? relu_sh.z : 0.f);
+                }
+                {
+                    float kc = fmaf(k0.w, c4.x, sh.w); kc = fmaf(k1.w, c4.y, kc); kc = fmaf(k2.w, c4.z, kc);
+                    kc = fmaf(-k3.w, m4.x, kc); kc = fmaf(-k4.w, m4.y, kc); kc = fmaf(-k5.w, m4.z, kc);
+                    out.w = fmaxf(m3 + kc, pad ? relu_sh.w : 0.f);
+                }
+                *reinterpret_cast<float4 *>(p.pillar_features + static_cast<int64_t>(row) * 64 + ch) = out;
             }
-            {
-                float kc = fmaf(k0.y, cx, sh.y); kc = fmaf(k1.y, cy, kc); kc = fmaf(k2.y, cz, kc);
-                kc = fmaf(-k3.y, mx, kc); kc = fmaf(-k4.y, my, kc); kc = fmaf(-k5.y, mz, kc);
-                out.y = fmaxf(m[1] + kc, pad ? fmaxf(sh.y, 0.f) : 0.f);
-            }
-            {
-                float kc = fmaf(k0.z, cx, sh.z); kc = fmaf(k1.z, cy, kc); kc = fmaf(k2.z, cz, kc);
-                kc = fmaf(-k3.z, mx, kc); kc = fmaf(-k4.z, my, kc); kc = fmaf(-k5.z, mz, kc);
-                out.z = fmaxf(m[2] + kc, pad ? fmaxf(sh.z, 0.f) : 0.f);
-            }
-            {
-                float kc = fmaf(k0.w, cx, sh.w); kc = fmaf(k1.w, cy, kc); kc = fmaf(k2.w, cz, kc);
-                kc = fmaf(-k3.w, mx, kc); kc = fmaf(-k4.w, my, kc); kc = fmaf(-k5.w, mz, kc);
-                out.w = fmaxf(m[3] + kc, pad ? fmaxf(sh.w, 0.f) : 0.f);
-            }
-            *reinterpret_cast<float4 *>(p.pillar_features + static_cast<int64_t>(row) * 64 + ch) = out;
         }
         if (H == 0) __syncthreads();  // the second half overwrites s_y
     }

@@ -87,16 +87,25 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store_1d(void *gdst, const void *ssrc, uint32_t bytes)
+// The canvas is written once and not read by this path: mark its lines evict-first so the 1 GiB stream does not push the
+// index map and the pillar features (both re-read by this very kernel) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_first()
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_store_1d(void *gdst, const void *ssrc, uint32_t bytes, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
                  : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void *ssrc, int c0, int c1)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void *ssrc, int c0, int c1, uint64_t pol)
 {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                      reinterpret_cast<uint64_t>(tmap)),
-                 "r"(smem_u32(ssrc)), "r"(c0), "r"(c1)
+                 "r"(smem_u32(ssrc)), "r"(c0), "r"(c1), "l"(pol)
                  : "memory");
 }
 
@@ -126,6 +135,7 @@ k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cel
     const int cell = tid % kCells, part = tid / kCells;
     const int c_lo = part * (f / kParts), c_hi = c_lo + f / kParts;
     const bool issuer = TMA2D ? (tid == 0) : (tid < f);
+    const uint64_t pol = policy_evict_first();
 
     bool dirty[2] = {false, false};       // CTA-uniform
     int32_t r_prev[2] = {-1, -1};         // the row this thread copied into buffer k last time
@@ -173,12 +183,12 @@ k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cel
         }
         if (TMA2D) {
             if (tid == 0) {
-                tma_store_2d(&tmap, tile, static_cast<int>(cell0), b * f);
+                tma_store_2d(&tmap, tile, static_cast<int>(cell0), b * f, pol);
                 bulk_commit();
             }
         } else if (tid < f) {
             bulk_store_1d(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, tile + tid * kCells,
-                          static_cast<uint32_t>(ncell) * 4u);
+                          static_cast<uint32_t>(ncell) * 4u, pol);
             bulk_commit();
         }
     }
