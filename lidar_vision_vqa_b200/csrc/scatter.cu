@@ -15,6 +15,8 @@
 //               [B*F rows, ny*nx cells] (UTMASTG).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pillars {
@@ -45,6 +47,11 @@ __global__ void k_build_cell_row(const void *__restrict__ coords, int coords_flo
 }
 
 // ---- variant 1 ----------------------------------------------------------------------------------
+// Warp-autonomous direct stores: a warp owns 128 consecutive cells (4 per lane) x all channels = 32 KB of the canvas and
+// never waits for another warp.  A warp whose 128 cells are empty streams zeros; otherwise each lane fetches, 8 channels
+// at a time, the feature rows of its occupied cells with two 16-byte loads per row and composes one float4 per channel.
+// Eight passes of one L2 round trip each per 32 KB keep the SM far above its share of HBM write bandwidth with a handful
+// of resident warps, so the kernel runs at the speed of the write stream.
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads)
 k_scatter_plain(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
@@ -53,31 +60,54 @@ k_scatter_plain(const float *__restrict__ feats, const int32_t *__restrict__ cel
     constexpr int kPer = VEC ? 4 : 1;
     const int b = blockIdx.x / tiles_per_plane;
     const int64_t cell0 = static_cast<int64_t>(blockIdx.x % tiles_per_plane) * (kThreads * kPer) + threadIdx.x * kPer;
-    if (cell0 >= plane) return;
+    const bool inb = cell0 < plane;
     int32_t r[kPer];
-    if (VEC) {
-        const int4 v = *reinterpret_cast<const int4 *>(cell_row + b * plane + cell0);
-        r[0] = v.x; r[1 % kPer] = v.y; r[2 % kPer] = v.z; r[3 % kPer] = v.w;
-    } else {
-        r[0] = cell_row[b * plane + cell0];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) r[k] = -1;
+    if (inb) {
+        if (VEC) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(cell_row + b * plane + cell0));
+            r[0] = v.x; r[1 % kPer] = v.y; r[2 % kPer] = v.z; r[3 % kPer] = v.w;
+        } else {
+            r[0] = __ldg(cell_row + b * plane + cell0);
+        }
     }
-    float *dst = bev + (static_cast<int64_t>(b) * f) * plane + cell0;
     bool any = false;
 #pragma unroll
     for (int k = 0; k < kPer; ++k) any |= r[k] >= 0;
-    if (!any) {
-        for (int c = 0; c < f; ++c) {
-            if (VEC) __stcs(reinterpret_cast<float4 *>(dst + c * plane), make_float4(0.f, 0.f, 0.f, 0.f));
-            else dst[c * plane] = 0.f;
+    float *dst = bev + (static_cast<int64_t>(b) * f) * plane + cell0;
+    if (!__any_sync(0xffffffffu, any)) {
+        if (inb) {
+            if (VEC) {
+#pragma unroll 8
+                for (int c = 0; c < f; ++c) __stcs(reinterpret_cast<float4 *>(dst + c * plane), make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+                for (int c = 0; c < f; ++c) __stcs(dst + c * plane, 0.f);
+            }
         }
         return;
     }
-    for (int c = 0; c < f; ++c) {
-        float v[kPer];
+    if (!inb) return;
+    if (VEC) {
+        for (int c0 = 0; c0 < f; c0 += 8) {
+            float v[4][8];
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) v[k] = r[k] >= 0 ? __ldg(feats + static_cast<int64_t>(r[k]) * f + c) : 0.f;
-        if (VEC) __stcs(reinterpret_cast<float4 *>(dst + c * plane), make_float4(v[0], v[1 % kPer], v[2 % kPer], v[3 % kPer]));
-        else dst[c * plane] = v[0];
+            for (int k = 0; k < 4; ++k) {
+                float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                if (r[k % kPer] >= 0) {
+                    const float4 *row = reinterpret_cast<const float4 *>(feats + static_cast<int64_t>(r[k % kPer]) * f + c0);
+                    lo = __ldg(row);
+                    hi = __ldg(row + 1);
+                }
+                v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w;
+                v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                __stcs(reinterpret_cast<float4 *>(dst + (c0 + j) * plane), make_float4(v[0][j], v[1][j], v[2][j], v[3][j]));
+        }
+    } else {
+        for (int c = 0; c < f; ++c) __stcs(dst + c * plane, r[0] >= 0 ? __ldg(feats + static_cast<int64_t>(r[0]) * f + c) : 0.f);
     }
 }
 
@@ -109,17 +139,28 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, const void
                  : "memory");
 }
 
+__device__ __forceinline__ void bulk_store_1d_nohint(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_nohint(const CUtensorMap *tmap, const void *ssrc, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(ssrc)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 // ---- variants 2 and 3 ---------------------------------------------------------------------------
 // Persistent CTAs; two shared-memory tiles [f][kCells] per CTA, alternating.  Invariant: a tile that is not "dirty" is
 // all zero, so an empty stretch of the canvas is stored straight from it with no shared-memory write and no wait at all.
 // A tile that received pillar columns is restored lazily, the next time the buffer comes round (two tiles later), when the
 // store that read it has long finished (cp.async.bulk.wait_group.read 1).  The index-map entry of the next tile is
 // prefetched one iteration ahead so its latency hides behind the current tile.
-constexpr int kCells = 128;
-
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-template <bool TMA2D>
+template <bool TMA2D, int kCells, bool kHint>
 __global__ void __launch_bounds__(kThreads)
 k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
                 int tiles_per_plane, int64_t n_tiles, float *__restrict__ bev, const __grid_constant__ CUtensorMap tmap)
@@ -135,7 +176,7 @@ k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cel
     const int cell = tid % kCells, part = tid / kCells;
     const int c_lo = part * (f / kParts), c_hi = c_lo + f / kParts;
     const bool issuer = TMA2D ? (tid == 0) : (tid < f);
-    const uint64_t pol = policy_evict_first();
+    const uint64_t pol = kHint ? policy_evict_first() : 0ull;
 
     bool dirty[2] = {false, false};       // CTA-uniform
     int32_t r_prev[2] = {-1, -1};         // the row this thread copied into buffer k last time
@@ -183,12 +224,17 @@ k_scatter_async(const float *__restrict__ feats, const int32_t *__restrict__ cel
         }
         if (TMA2D) {
             if (tid == 0) {
-                tma_store_2d(&tmap, tile, static_cast<int>(cell0), b * f, pol);
+                if (kHint) tma_store_2d(&tmap, tile, static_cast<int>(cell0), b * f, pol);
+                else tma_store_2d_nohint(&tmap, tile, static_cast<int>(cell0), b * f);
                 bulk_commit();
             }
         } else if (tid < f) {
-            bulk_store_1d(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, tile + tid * kCells,
-                          static_cast<uint32_t>(ncell) * 4u, pol);
+            if (kHint)
+                bulk_store_1d(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, tile + tid * kCells,
+                              static_cast<uint32_t>(ncell) * 4u, pol);
+            else
+                bulk_store_1d_nohint(bev + (static_cast<int64_t>(b) * f + tid) * plane + cell0, tile + tid * kCells,
+                                     static_cast<uint32_t>(ncell) * 4u);
             bulk_commit();
         }
     }
@@ -246,10 +292,10 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
     const int64_t plane = static_cast<int64_t>(nx) * ny;
     if (nb == 0 || plane == 0 || f == 0) return cudaSuccess;
     const bool vec_ok = (plane % 4 == 0) && (reinterpret_cast<uintptr_t>(bev) % 16 == 0) &&
-                        (reinterpret_cast<uintptr_t>(feats) % 16 == 0) && (f % 4 == 0);
-    const size_t smem = sizeof(float) * 2 * f * kCells;
+                        (reinterpret_cast<uintptr_t>(feats) % 16 == 0) && (f % 8 == 0);
+    const size_t smem = sizeof(float) * 2 * f * 128;
     const bool async_ok = vec_ok && f <= kThreads && f % 8 == 0 && smem <= 200 * 1024;
-    if (variant == 0) variant = async_ok ? 3 : 1;
+    if (variant == 0) variant = 1;  // measured on B200: direct stores 205 us, TMA tile stores 268 us (profiles/r01_scatter_variants.md)
     if ((variant == 2 || variant == 3) && !async_ok) variant = 1;
     if (variant == 3 && !get_encode_fn()) variant = 2;
 
@@ -265,40 +311,53 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
         return cudaGetLastError();
     }
 
-    const int tpp = static_cast<int>((plane + kCells - 1) / kCells);
+    // tuning knobs (measurement only): tile width, CTAs per SM, L2 hint
+    static int env_cells = -1, env_ctas = -1, env_nohint = -1;
+    if (env_cells < 0) {
+        const char *e1 = getenv("PILLARS_SCATTER_CELLS"), *e2 = getenv("PILLARS_SCATTER_CTAS"), *e3 = getenv("PILLARS_SCATTER_NOHINT");
+        env_cells = e1 ? atoi(e1) : 0;
+        env_ctas = e2 ? atoi(e2) : 0;
+        env_nohint = e3 ? atoi(e3) : 0;
+    }
+    const int cells = (env_cells == 256 || env_cells == 64) ? env_cells : 128;
+    const size_t smem_bytes = sizeof(float) * 2 * f * cells;
+    const int tpp = static_cast<int>((plane + cells - 1) / cells);
     const int64_t n_tiles = static_cast<int64_t>(nb) * tpp;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (variant == 3) {
         const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(plane), static_cast<cuuint64_t>(nb) * f};
         const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(plane) * sizeof(float)};
-        const cuuint32_t box[2] = {static_cast<cuuint32_t>(kCells), static_cast<cuuint32_t>(f)};
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(cells), static_cast<cuuint32_t>(f)};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bev, gdim, gstride, box, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) variant = 2;
     }
-    int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+    int per_sm = static_cast<int>((220 * 1024) / (smem_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 6) per_sm = 6;
-    const int64_t grid = tmin<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * per_sm);
+    if (per_sm > 8) per_sm = 8;
+    if (env_ctas > 0 && env_ctas < per_sm) per_sm = env_ctas;
+    const unsigned grid = static_cast<unsigned>(tmin<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * per_sm));
+#define PILLARS_LAUNCH_SCATTER(T2D, CELLS, HINT)                                                                          \
+    do {                                                                                                                  \
+        cudaFuncSetAttribute(k_scatter_async<T2D, CELLS, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+        k_scatter_async<T2D, CELLS, HINT><<<grid, kThreads, smem_bytes, st>>>(feats, cell_row, f, plane, tpp, n_tiles, bev, \
+                                                                              tmap);                                      \
+    } while (0)
+#define PILLARS_LAUNCH_SCATTER_C(T2D, HINT)                      \
+    do {                                                         \
+        if (cells == 64) PILLARS_LAUNCH_SCATTER(T2D, 64, HINT);  \
+        else if (cells == 256) PILLARS_LAUNCH_SCATTER(T2D, 256, HINT); \
+        else PILLARS_LAUNCH_SCATTER(T2D, 128, HINT);             \
+    } while (0)
     if (variant == 3) {
-        static bool attr3 = false;
-        if (!attr3) {
-            cudaFuncSetAttribute(k_scatter_async<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr3 = true;
-        }
-        k_scatter_async<true><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(feats, cell_row, f, plane, tpp, n_tiles,
-                                                                                  bev, tmap);
+        if (env_nohint) PILLARS_LAUNCH_SCATTER_C(true, false);
+        else PILLARS_LAUNCH_SCATTER_C(true, true);
     } else {
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaFuncSetAttribute(k_scatter_async<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr2 = true;
-        }
-        k_scatter_async<false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(feats, cell_row, f, plane, tpp, n_tiles,
-                                                                                   bev, tmap);
+        if (env_nohint) PILLARS_LAUNCH_SCATTER_C(false, false);
+        else PILLARS_LAUNCH_SCATTER_C(false, true);
     }
     note_launch();
     return cudaGetLastError();
