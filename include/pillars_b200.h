@@ -147,6 +147,12 @@ int pillars_last_launch_count(void);
  * Thread-local; costs four cudaEventRecord per call while set. */
 int pillars_set_stage_events(void *const *events4);
 
+/* Pipelining hook (thread-local).  With enable != 0 the BEV scatter of subsequent pillars_encode_bev calls is enqueued on
+ * `stream` instead of the call's stream, ordered after the feature kernel by an event.  The small latency-bound kernels of
+ * the next batch (on a higher-priority stream) then run alongside the bandwidth-bound canvas write of this one.  The
+ * caller owns the hazards: the next call that reuses the same outputs / workspace must first wait for `stream`. */
+int pillars_set_scatter_stream(void *stream, int enable);
+
 /* Test / measurement hook: non-zero makes pillars_encode_bev ignore the host weight copies and run the generic feature
  * kernel (thread-local). */
 int pillars_force_generic_features(int on);

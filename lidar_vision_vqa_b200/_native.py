@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "pillars_last_launch_count",
     "pillars_set_stage_events",
     "pillars_force_generic_features",
+    "pillars_set_scatter_stream",
 )
 
 
@@ -86,6 +87,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_encode_bev.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
                                        POINTER(PillarsPfn), POINTER(PillarsOutputs), c_void_p, c_size_t, c_int32,
                                        c_void_p]
+    lib.pillars_set_scatter_stream.restype = c_int
+    lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
     lib.pillars_force_generic_features.restype = c_int
     lib.pillars_force_generic_features.argtypes = [c_int]
     lib.pillars_set_stage_events.restype = c_int

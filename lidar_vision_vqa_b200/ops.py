@@ -258,9 +258,11 @@ class EncodeBuffers:
 
 def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, pfn: PfnParams, *, col0: int = 0,
                buffers: Optional[EncodeBuffers] = None, with_bev: bool = True, scatter_variant: str = "auto",
-               want_membership: bool = False, want_voxels: bool = False) -> Dict[str, torch.Tensor]:
+               want_membership: bool = False, want_voxels: bool = False,
+               scatter_stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
     """The fused path: raw points -> pillar_features / voxel_coords / voxel_num_points / pillar_count / bev.
-    Everything is enqueued on the current stream; nothing synchronises."""
+    Everything is enqueued on the current stream; nothing synchronises.  With ``scatter_stream`` the canvas write goes to
+    that stream (ordered after the feature kernel); the caller then waits on it before reusing ``buffers``."""
     _check_points(points, frame_offsets)
     lib = _native.load()
     n, stride = points.shape
@@ -297,9 +299,15 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
         res["voxels"] = torch.empty((buffers.capacity, grid.max_points, pfn.c_point), dtype=torch.float32, device=dev)
         out.voxels = res["voxels"].data_ptr()
     nat = pfn.native()
-    check(lib.pillars_encode_bev(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
-                                 ctypes.byref(nat), ctypes.byref(out), buffers.ws.data_ptr(), buffers.ws.numel(),
-                                 SCATTER_VARIANTS[scatter_variant], _stream_ptr()), "pillars_encode_bev")
+    if scatter_stream is not None:
+        lib.pillars_set_scatter_stream(int(scatter_stream.cuda_stream), 1)
+    try:
+        check(lib.pillars_encode_bev(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
+                                     ctypes.byref(nat), ctypes.byref(out), buffers.ws.data_ptr(), buffers.ws.numel(),
+                                     SCATTER_VARIANTS[scatter_variant], _stream_ptr()), "pillars_encode_bev")
+    finally:
+        if scatter_stream is not None:
+            lib.pillars_set_scatter_stream(None, 0)
     return res
 
 
