@@ -42,9 +42,9 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "bulk1d", "tma2d"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through the timed loop")
-    ap.add_argument("--streams", type=int, default=3,
+    ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the timed steps are pipelined over (independent batches overlap)")
-    ap.add_argument("--no-split", action="store_true", help="keep the scatter on the step's own stream")
+XX
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU arm (bounded sample)")
@@ -316,7 +316,7 @@ def run_b200(args, rank, world, local_rank):
     serial_ms = s1.elapsed_time(e1)
 
     # ---- timed region 2 (the headline): the same K steps pipelined over n_streams streams ----------------------------
-    split = n_streams > 1 and not args.no_split
+    split = n_streams > 1 and args.split
     for w in range(max(3, args.warmup)):  # warm the other streams' buffers
         with torch.cuda.stream(streams[w % n_streams]):
             step(w, w % n_streams)

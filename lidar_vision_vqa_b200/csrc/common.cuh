@@ -13,7 +13,8 @@ namespace pillars {
 // one 32 B sector).  Initialised by a single 0xFF memset:
 //   key   = 0xFFFFFFFF  -> empty
 //   first = 0xFFFFFFFF  -> atomicMin target: smallest point index that hit the cell
-//   cnt   = 0xFFFFFFFF  -> "count - 1": atomicAdd(cnt, k) returns old; old + 1 is the arrival rank base
+//   cnt   = 0xFFFFFFFF  -> "count - 1": atomicAdd(cnt, k) returns old; old + 1 is the arrival rank base;
+//                          the scan kernel later replaces it by the start of the pillar's point list
 //   gid   = pillar id in first-appearance order over the whole batch (written by the scan kernel)
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) HashEntry {
@@ -41,7 +42,7 @@ struct __align__(32) PointRecord {
 };
 
 static constexpr int kMaxFrames = 1024;  // frame_offsets are staged in shared memory
-static constexpr int kTile = 1024;       // points per CTA tile in the point-parallel kernels
+static constexpr int kTile = 2048;       // points per CTA tile of the scan kernel
 
 struct Workspace {
     // zero-initialised region

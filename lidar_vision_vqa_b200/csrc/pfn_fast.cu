@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
     __shared__ float4 s_c4[kFT];  // pillar centre x,y,z ; w = 1.0 when the pillar has empty (padded) slots
     __shared__ float4 s_m4[kFT];  // mean - centre x,y,z ; w = output row as int bits (-1: pillar not emitted)
     __shared__ uint32_t s_thr[kFT], s_pos0[kFT], s_cnt[kFT];
+    __shared__ float s_px[kFT], s_py[kFT], s_pz[kFT];  // the chunk's coordinates, for the per-pillar mean
     __shared__ int16_t s_start[kFT + 1];
     __shared__ uint16_t s_big[kFT];
     __shared__ int s_nbig, s_tail_len;
@@ -99,6 +100,9 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
     }
     const uint32_t r_idx = __float_as_uint(rb.y), r_gid = __float_as_uint(rb.z);
     const bool is_start = in && __float_as_uint(rb.w) == 0u;
+    s_px[tid] = ra.x;
+    s_py[tid] = ra.y;
+    s_pz[tid] = ra.z;
 
     // pillar-local index of every position: inclusive count of list starts, minus one
     const unsigned bal = __ballot_sync(kFull, is_start);
@@ -149,10 +153,17 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
             } else {
                 double sx = 0.0, sy = 0.0, sz = 0.0;  // double: the sum does not depend on the list order
                 for (uint32_t j = 0; j < n; ++j) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + pos + j));
-                    sx += static_cast<double>(q.x);
-                    sy += static_cast<double>(q.y);
-                    sz += static_cast<double>(q.z);
+                    const uint32_t t = tid + j;
+                    if (t < kFT) {  // staged by the owner of that position before the first barrier
+                        sx += static_cast<double>(s_px[t]);
+                        sy += static_cast<double>(s_py[t]);
+                        sz += static_cast<double>(s_pz[t]);
+                    } else {  // the pillar continues in the next chunk
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + pos + j));
+                        sx += static_cast<double>(q.x);
+                        sy += static_cast<double>(q.y);
+                        sz += static_cast<double>(q.z);
+                    }
                 }
                 const float nf = static_cast<float>(n);
                 m4.x = __fsub_rn(__fdiv_rn(static_cast<float>(sx), nf), cx);  // pillar_vfe.py:97, relative to the centre
@@ -288,8 +299,15 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
                 if (row < 0) continue;
                 const float4 c4 = s_c4[q];
                 const int a0 = s_start[q], a1 = s_start[q + 1];
-                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-                for (int j = a0; j < a1; ++j) {
+                // almost every pillar has <= 4 points in the chunk: four clamped, branch-free reads (re-reading the last
+                // element is harmless for a max), then a loop only for the rare longer run
+                const int l = a1 - 1;
+                const int j1 = min(a0 + 1, l), j2 = min(a0 + 2, l), j3 = min(a0 + 3, l);
+                float m0 = fmaxf(fmaxf(ycol[a0], ycol[j1]), fmaxf(ycol[j2], ycol[j3]));
+                float m1 = fmaxf(fmaxf(ycol[kLd + a0], ycol[kLd + j1]), fmaxf(ycol[kLd + j2], ycol[kLd + j3]));
+                float m2 = fmaxf(fmaxf(ycol[2 * kLd + a0], ycol[2 * kLd + j1]), fmaxf(ycol[2 * kLd + j2], ycol[2 * kLd + j3]));
+                float m3 = fmaxf(fmaxf(ycol[3 * kLd + a0], ycol[3 * kLd + j1]), fmaxf(ycol[3 * kLd + j2], ycol[3 * kLd + j3]));
+                for (int j = a0 + 4; j < a1; ++j) {
                     m0 = fmaxf(m0, ycol[j]);
                     m1 = fmaxf(m1, ycol[kLd + j]);
                     m2 = fmaxf(m2, ycol[2 * kLd + j]);

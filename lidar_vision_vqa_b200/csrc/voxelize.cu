@@ -23,7 +23,7 @@ namespace pillars {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPerThread = kTile / kThreads;  // 4 (scan kernel)
+constexpr int kPerThread = kTile / kThreads;  // 8 (scan kernel)
 constexpr int kGroup = 256;                   // tiles per look-back group
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k)
@@ -183,7 +183,7 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
               Header *__restrict__ hdr, unsigned long long *__restrict__ tile_agg, unsigned long long *__restrict__ tile_prefix,
               uint32_t *__restrict__ pillar_key, uint32_t *__restrict__ pillar_list,
               uint32_t *__restrict__ pillar_cnt, const int32_t *__restrict__ frame_offsets, int nb,
-              uint32_t *__restrict__ frame_gstart)
+              uint32_t *__restrict__ frame_gstart, int dynamic_ids)
 {
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
@@ -192,16 +192,23 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
     __shared__ uint8_t s_thr_flags[kThreads];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&hdr->tile_counter, 1u);  // ids in scheduling order: predecessors are resident
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    // A tile spins on its predecessors, so they must be running: guaranteed when the whole grid is co-resident
+    // (blockIdx is then the tile id), otherwise ids are handed out in scheduling order.
+    if (dynamic_ids) {
+        if (tid == 0) s_tile = atomicAdd(&hdr->tile_counter, 1u);
+        __syncthreads();
+    }
+    const uint32_t tile = dynamic_ids ? s_tile : blockIdx.x;
     const int64_t tile_start = static_cast<int64_t>(tile) * kTile;
     const int64_t i0 = tile_start + tid * kPerThread;
 
     int32_t slot[kPerThread];
     if (i0 + kPerThread <= n) {
-        const int4 v = *reinterpret_cast<const int4 *>(point_slot + i0);
-        slot[0] = v.x; slot[1] = v.y; slot[2] = v.z; slot[3] = v.w;
+#pragma unroll
+        for (int k = 0; k < kPerThread; k += 4) {
+            const int4 v = *reinterpret_cast<const int4 *>(point_slot + i0 + k);
+            slot[k] = v.x; slot[k + 1] = v.y; slot[k + 2] = v.z; slot[k + 3] = v.w;
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < kPerThread; ++k) slot[k] = (i0 + k < n) ? point_slot[i0 + k] : -1;
@@ -262,7 +269,9 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
     for (int k = 0; k < kPerThread; ++k) {
         if (flags & (1u << k)) {
             const uint32_t g = static_cast<uint32_t>(run >> 32);
-            table[slot[k]].gid = g;
+            // cnt was only needed by this (owning) thread: the entry now carries the list base and the pillar id, so
+            // k_place resolves a point with one 16-byte load
+            *reinterpret_cast<uint2 *>(&table[slot[k]].cnt) = make_uint2(static_cast<uint32_t>(run & 0xFFFFFFFFull), g);
             pillar_key[g] = ent[k].x;
             pillar_list[g] = static_cast<uint32_t>(run & 0xFFFFFFFFull);
             pillar_cnt[g] = static_cast<uint32_t>(val[k] & 0xFFFFFFFFull);
@@ -304,9 +313,10 @@ k_place(const float *__restrict__ points, int64_t n, int stride, int col0, int c
     if (i < n) {
         const int32_t s = point_slot[i];
         if (s >= 0) {
-            const uint32_t g = table[s].gid;
+            const uint4 e = *reinterpret_cast<const uint4 *>(&table[s]);  // {key, first, list base, pillar id}
+            const uint32_t g = e.w;
             const uint32_t arrival = point_arrival[i];
-            const uint32_t pos = pillar_list[g] + arrival;
+            const uint32_t pos = e.z + arrival;
             if (sorted_idx) sorted_idx[pos] = static_cast<uint32_t>(i);
             if (records) {
                 // one full 32-byte sector per point: the feature kernel then streams its input instead of gathering
@@ -381,9 +391,12 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
     const unsigned pb = static_cast<unsigned>((n + kThreads - 1) / kThreads);
     k_quantize_insert<<<pb, kThreads, smem, st>>>(points, n, stride, col0, frame_offsets, nb, gd, ws.table, ws.cap,
                                                   ws.point_slot, ws.point_arrival, vec_ok);
+    // Tile ids are always handed out in scheduling order (one atomic per CTA): with other streams sharing the GPU nothing
+    // guarantees that blockIdx order is dispatch order, and a tile spins on its predecessors.
+    const int dynamic_ids = 1;
     k_scan_assign<<<ws.n_tiles, kThreads, 0, st>>>(n, ws.n_tiles, ws.point_slot, ws.table, ws.hdr, ws.tile_desc,
                                                    ws.tile_prefix, ws.pillar_key, ws.pillar_list, ws.pillar_cnt,
-                                                   frame_offsets, nb, ws.frame_gstart);
+                                                   frame_offsets, nb, ws.frame_gstart, dynamic_ids);
     k_place<<<pb, kThreads, 0, st>>>(points, n, stride, col0, c_point, ws.point_slot, ws.point_arrival, ws.table,
                                      ws.pillar_list, want_index_lists ? ws.sorted_idx : nullptr,
                                      want_records ? ws.records : nullptr, ws.frame_gstart, ws.frame_rowbase, nb,
