@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through the timed loop")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the timed steps are pipelined over (independent batches overlap)")
-XX
+    ap.add_argument("--split", action="store_true",
+                    help="put the scatter on a separate low-priority stream (measured: no gain, see DESIGN.md)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU arm (bounded sample)")
