@@ -410,10 +410,48 @@ def run_b200(args, rank, world, local_rank):
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        module_ms = ms
+        # the throughput-oriented public API: PillarEncoderPipeline keeps `depth` host batches in flight, so the H2D copy
+        # of batch k+1 overlaps the kernels of batch k.  Every step still copies its points from pinned host memory and
+        # reads its per-frame pillar counts back.
+        from lidar_vision_vqa_b200.pipeline import PillarEncoderPipeline
+
+        depth = 3
+        pipe = PillarEncoderPipeline(vfe, n_frames=nb, max_points=max(p.shape[0] for p in pinned), depth=depth,
+                                     scatter_variant=args.scatter_variant)
+        for i in range(max(3, args.warmup)):
+            pipe.result(pipe.submit(pinned[i % rot]))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_e0 = time.perf_counter()
+        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s3.record()
+        tickets = []
+        checksum = 0
+        for k in range(K):
+            tickets.append(pipe.submit(pinned[k % rot]))
+            if len(tickets) == depth:
+                checksum += int(pipe.result(tickets.pop(0))["pillars_per_frame"].sum())
+        while tickets:
+            checksum += int(pipe.result(tickets.pop(0))["pillars_per_frame"].sum())
+        torch.cuda.synchronize()
+        e3.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t_e0) * 1e3
+        ms = max(s3.elapsed_time(e3), wall_ms)  # the host is part of this loop: take the slower clock
+        if world > 1:
+            t = torch.tensor([ms, module_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, module_ms = float(t[0].item()), float(t[1].item())
         e2e = {"value": nb * world / (ms / K * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
                "h2d_bytes_per_step": int(statistics.mean(p.numel() * 4 for p in pinned)),
                "d2h_bytes_per_step": (nb + 1) * 4,
-               "api": "PillarVFEFromPoints(FUSE_SCATTER).forward + PointPillarScatter.forward on a pinned host batch_dict"}
+               "api": f"PillarEncoderPipeline.submit/result (depth {depth}) on pinned host batch_dict['points']",
+               "pillars_checksum": checksum,
+               "module_forward": {"value": nb * world / (module_ms / K * 1e-3), "ms_per_step": module_ms / K,
+                                  "api": "PillarVFEFromPoints(FUSE_SCATTER).forward + PointPillarScatter.forward, one "
+                                         "blocking call per batch"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -16,15 +16,15 @@
 // A CTA owns the pillars whose list STARTS inside its 256 positions; the tail of its last pillar (usually 0-2 points in
 // the next chunk) is swept by warp 0.  Pillars over the cap (n > P) get their "first P by point index" threshold from a
 // warp-wide radix select.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pillars {
 
 namespace {
 
-constexpr int kFT = 256;   // threads per CTA == list positions per chunk
 constexpr int kTailW = 32; // tail positions per sweep (one warp)
-constexpr int kLd = kFT + kTailW + 1;
 constexpr int kHalf = 32;  // channels per pass
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -49,7 +49,7 @@ __device__ __forceinline__ unsigned lanemask_le()
     return m;
 }
 
-template <int H>
+template <int H, int kLd>
 __device__ __forceinline__ void point_half(const FastParams &p, bool kept, float xp, float yp, float zp, float in, float tm,
                                            float *__restrict__ col)
 {
@@ -69,8 +69,11 @@ __device__ __forceinline__ void point_half(const FastParams &p, bool kept, float
     }
 }
 
-__global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_constant__ FastParams p)
+// kFT = threads per CTA == list positions per chunk
+template <int kFT>
+__global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_fast(const __grid_constant__ FastParams p)
 {
+    constexpr int kLd = kFT + kTailW + 1;
     extern __shared__ __align__(16) float s_y[];  // [kHalf][kLd]
     __shared__ float4 s_c4[kFT];  // pillar centre x,y,z ; w = 1.0 when the pillar has empty (padded) slots
     __shared__ float4 s_m4[kFT];  // mean - centre x,y,z ; w = output row as int bits (-1: pillar not emitted)
@@ -247,8 +250,8 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
 
 #pragma unroll
     for (int H = 0; H < 2; ++H) {
-        if (H == 0) point_half<0>(p, kept, xp, yp, zp, ra.w, rb.x, s_y + tid);
-        else point_half<1>(p, kept, xp, yp, zp, ra.w, rb.x, s_y + tid);
+        if (H == 0) point_half<0, kLd>(p, kept, xp, yp, zp, ra.w, rb.x, s_y + tid);
+        else point_half<1, kLd>(p, kept, xp, yp, zp, ra.w, rb.x, s_y + tid);
         if (tid < kHalf) s_acc_tail[tid] = -INFINITY;
         __syncthreads();
 
@@ -271,8 +274,8 @@ __global__ void __launch_bounds__(kFT, 4) k_pillar_features_fast(const __grid_co
                         tt = b.x;
                     }
                 }
-                if (H == 0) point_half<0>(p, tk, tx, ty, tz, ti, tt, s_y + kFT + lane);
-                else point_half<1>(p, tk, tx, ty, tz, ti, tt, s_y + kFT + lane);
+                if (H == 0) point_half<0, kLd>(p, tk, tx, ty, tz, ti, tt, s_y + kFT + lane);
+                else point_half<1, kLd>(p, tk, tx, ty, tz, ti, tt, s_y + kFT + lane);
             }
             __syncthreads();
             if (tid < kHalf) {
@@ -373,14 +376,23 @@ cudaError_t launch_pillar_features_fast(const FastJob &job, const FastWeights &w
     }
     p.idx_bits = job.idx_bits;
     p.w = w;
-    const size_t smem = sizeof(float) * kHalf * kLd;
-    static bool attr_done = false;
-    if (!attr_done) {  // static + dynamic shared memory is just over the 48 KB default
-        cudaFuncSetAttribute(k_pillar_features_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_done = true;
+    static int ft = 0;
+    if (!ft) {
+        const char *e = getenv("PILLARS_FEAT_THREADS");
+        ft = e ? atoi(e) : 256;
+        if (ft != 64 && ft != 128 && ft != 256) ft = 256;
     }
-    const unsigned grid = static_cast<unsigned>((job.n + kFT - 1) / kFT);  // upper bound: listed points <= n
-    k_pillar_features_fast<<<grid, kFT, smem, st>>>(p);
+    const size_t smem = sizeof(float) * kHalf * (ft + kTailW + 1);
+    const unsigned grid = static_cast<unsigned>((job.n + ft - 1) / ft);  // upper bound: listed points <= n
+    // static + dynamic shared memory is just over the 48 KB default at 256 threads
+    if (ft == 256) {
+        cudaFuncSetAttribute(k_pillar_features_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        k_pillar_features_fast<256><<<grid, 256, smem, st>>>(p);
+    } else if (ft == 128) {
+        k_pillar_features_fast<128><<<grid, 128, smem, st>>>(p);
+    } else {
+        k_pillar_features_fast<64><<<grid, 64, smem, st>>>(p);
+    }
     note_launch();
     return cudaGetLastError();
 }

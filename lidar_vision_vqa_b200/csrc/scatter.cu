@@ -52,14 +52,14 @@ __global__ void k_build_cell_row(const void *__restrict__ coords, int coords_flo
 // at a time, the feature rows of its occupied cells with two 16-byte loads per row and composes one float4 per channel.
 // Eight passes of one L2 round trip each per 32 KB keep the SM far above its share of HBM write bandwidth with a handful
 // of resident warps, so the kernel runs at the speed of the write stream.
-template <bool VEC>
+template <bool VEC, int CPP, bool PIPE>
 __global__ void __launch_bounds__(kThreads)
 k_scatter_plain(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
                 int tiles_per_plane, float *__restrict__ bev)
 {
     constexpr int kPer = VEC ? 4 : 1;
     const int b = blockIdx.x / tiles_per_plane;
-    const int64_t cell0 = static_cast<int64_t>(blockIdx.x % tiles_per_plane) * (kThreads * kPer) + threadIdx.x * kPer;
+    const int64_t cell0 = static_cast<int64_t>(blockIdx.x % tiles_per_plane) * (blockDim.x * kPer) + threadIdx.x * kPer;
     const bool inb = cell0 < plane;
     int32_t r[kPer];
 #pragma unroll
@@ -89,22 +89,40 @@ k_scatter_plain(const float *__restrict__ feats, const int32_t *__restrict__ cel
     }
     if (!inb) return;
     if (VEC) {
-        for (int c0 = 0; c0 < f; c0 += 8) {
-            float v[4][8];
+        constexpr int kV = CPP / 4;  // 16-byte loads per row and pass
+        float4 cur[4][kV], nxt[4][kV];
+        auto fetch = [&](float4 (&dstv)[4][kV], int c0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+#pragma unroll
+                for (int q = 0; q < kV; ++q) dstv[k][q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r[k % kPer] >= 0) {
                     const float4 *row = reinterpret_cast<const float4 *>(feats + static_cast<int64_t>(r[k % kPer]) * f + c0);
-                    lo = __ldg(row);
-                    hi = __ldg(row + 1);
-                }
-                v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w;
-                v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
-            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                __stcs(reinterpret_cast<float4 *>(dst + (c0 + j) * plane), make_float4(v[0][j], v[1][j], v[2][j], v[3][j]));
+                    for (int q = 0; q < kV; ++q) dstv[k][q] = __ldg(row + q);
+                }
+            }
+        };
+        fetch(cur, 0);
+        for (int c0 = 0; c0 < f; c0 += CPP) {
+            if (PIPE && c0 + CPP < f) fetch(nxt, c0 + CPP);  // next pass in flight while this one is stored
+#pragma unroll
+            for (int q = 0; q < kV; ++q) {
+                __stcs(reinterpret_cast<float4 *>(dst + (c0 + 4 * q + 0) * plane), make_float4(cur[0][q].x, cur[1][q].x, cur[2][q].x, cur[3][q].x));
+                __stcs(reinterpret_cast<float4 *>(dst + (c0 + 4 * q + 1) * plane), make_float4(cur[0][q].y, cur[1][q].y, cur[2][q].y, cur[3][q].y));
+                __stcs(reinterpret_cast<float4 *>(dst + (c0 + 4 * q + 2) * plane), make_float4(cur[0][q].z, cur[1][q].z, cur[2][q].z, cur[3][q].z));
+                __stcs(reinterpret_cast<float4 *>(dst + (c0 + 4 * q + 3) * plane), make_float4(cur[0][q].w, cur[1][q].w, cur[2][q].w, cur[3][q].w));
+            }
+            if (c0 + CPP < f) {
+                if (PIPE) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int q = 0; q < kV; ++q) cur[k][q] = nxt[k][q];
+                } else {
+                    fetch(cur, c0 + CPP);
+                }
+            }
         }
     } else {
         for (int c = 0; c < f; ++c) __stcs(dst + c * plane, r[0] >= 0 ? __ldg(feats + static_cast<int64_t>(r[0]) * f + c) : 0.f);
@@ -300,12 +318,23 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
     if (variant == 3 && !get_encode_fn()) variant = 2;
 
     if (variant == 1) {
+        static int mode = -1, bs = 0;
+        if (mode < 0) {
+            const char *e1 = getenv("PILLARS_SCATTER_PLAIN_MODE"), *e2 = getenv("PILLARS_SCATTER_PLAIN_BLOCK");
+            mode = e1 ? atoi(e1) : 0;
+            bs = e2 ? atoi(e2) : kThreads;
+            if (bs != 64 && bs != 128 && bs != 256) bs = kThreads;
+        }
         if (vec_ok) {
-            const int tpp = static_cast<int>((plane + kThreads * 4 - 1) / (kThreads * 4));
-            k_scatter_plain<true><<<static_cast<unsigned>(nb) * tpp, kThreads, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+            const int tpp = static_cast<int>((plane + bs * 4 - 1) / (bs * 4));
+            const unsigned grid = static_cast<unsigned>(nb) * tpp;
+            if (mode == 1) k_scatter_plain<true, 4, false><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+            else if (mode == 2) k_scatter_plain<true, 8, true><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+            else if (mode == 3) k_scatter_plain<true, 4, true><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+            else k_scatter_plain<true, 8, false><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
         } else {
             const int tpp = static_cast<int>((plane + kThreads - 1) / kThreads);
-            k_scatter_plain<false><<<static_cast<unsigned>(nb) * tpp, kThreads, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+            k_scatter_plain<false, 8, false><<<static_cast<unsigned>(nb) * tpp, kThreads, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
         }
         note_launch();
         return cudaGetLastError();
