@@ -453,6 +453,34 @@ def run_b200(args, rank, world, local_rank):
                                   "api": "PillarVFEFromPoints(FUSE_SCATTER).forward + PointPillarScatter.forward, one "
                                          "blocking call per batch"}}
 
+    # ---- the one exchange step of the multi-GPU layout: compact BEV tokens gathered to the fusion rank (rank 0) --------
+    gather = None
+    if world > 1:
+        from lidar_vision_vqa_b200 import sharding
+
+        res = step(0)
+        torch.cuda.synchronize()
+        m_loc = int(res["pillar_count"][-1].item())
+        feats_loc, coords_loc = res["pillar_features"][:m_loc], res["voxel_coords"][:m_loc]
+        for _ in range(3):
+            sharding.gather_bev_tokens(feats_loc, coords_loc, rank * nb, nb * world, dst=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            tok = sharding.gather_bev_tokens(feats_loc, coords_loc, rank * nb, nb * world, dst=0)
+        if rank == 0:
+            canvas = sharding.densify(tok, nx, ny)
+        g1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather = {"ms_per_gather": float(t.item()), "payload_bytes_per_rank": int(m_loc * (F_OUT + 4) * 4),
+                  "what": "sharding.gather_bev_tokens (counts all-gather + padded NCCL gather of [M,64] features and "
+                          "[M,4] coords to rank 0); one densify of the whole batch on rank 0 included in the last "
+                          "iteration; NOT part of `value` (frames never need to meet on this path)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_arm(args.workload, args.cpu_frames, steps=4, warmup=1)
@@ -471,7 +499,7 @@ def run_b200(args, rank, world, local_rank):
                        "pipeline_streams": n_streams, "scatter_on_low_priority_stream": bool(split),
                        "l2": f"no explicit flush: each step writes {4 * F_OUT * nx * ny * nb / 2**20:.0f} MiB (>> 126 MB L2) "
                              f"and cycles {rot} distinct input batches"},
-            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gather_to_fusion_rank": gather,
             "gpu_launches": launches_per_step * K * 2, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

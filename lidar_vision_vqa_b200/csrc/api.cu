@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -215,6 +216,39 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         if ((e = cudaMemsetAsync(out->point_slot, 0xFF, sizeof(int32_t) * n, st)) != cudaSuccess) return cuda_fail(e, "memset");
         note_launch();
     }
+    // Optional (PILLARS_L2_PERSIST=1): ask L2 to keep the pillar features written by the feature kernel resident until the
+    // scatter has read them back (access-policy window on this stream, persisting set-aside sized once per process).
+    static int l2_mode = -1;
+    static size_t l2_setaside = 0, l2_max_window = 0;
+    if (l2_mode < 0) {
+        const char *ev = getenv("PILLARS_L2_PERSIST");
+        l2_mode = ev ? atoi(ev) : 0;
+        if (l2_mode) {
+            int dev = 0, max_persist = 0, max_win = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            l2_setaside = static_cast<size_t>(max_persist);
+            l2_max_window = static_cast<size_t>(max_win);
+            if (l2_setaside == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_setaside) != cudaSuccess) l2_mode = 0;
+            fprintf(stderr, "[pillars] L2 persisting set-aside %zu MB, max window %zu MB, mode %d\n", l2_setaside >> 20,
+                    l2_max_window >> 20, l2_mode);
+        }
+    }
+    const bool l2_window = l2_mode && want_bev && out->pillar_features && out->pillar_capacity > 0;
+    if (l2_window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        size_t bytes = static_cast<size_t>(out->pillar_capacity) * 64 * sizeof(float);
+        if (bytes > l2_max_window) bytes = l2_max_window;
+        av.accessPolicyWindow.base_ptr = out->pillar_features;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = bytes <= l2_setaside ? 1.0f : static_cast<float>(l2_setaside) / static_cast<float>(bytes);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
+
     // Feature kernel choice.  The constant-bank fast kernel covers the mainstream configuration when the caller also
     // supplied host copies of the weights; everything else runs the generic 16-lanes-per-pillar kernel.
     const bool membership = out->voxels || out->point_pillar || out->point_slot;
@@ -279,6 +313,11 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
             return cuda_fail(e, "scatter");
     }
     stage_mark(3, st);
+    if (l2_window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
     g_launches_last = g_launches;
     return 0;
 }

@@ -9,17 +9,19 @@
 namespace pillars {
 
 // ------------------------------------------------------------------------------------------------
-// Pillar hash table (open addressing, linear probing, HBM resident; 16 B entries so the three atomics of an insert hit
-// one 32 B sector).  Initialised by a single 0xFF memset:
-//   key   = 0xFFFFFFFF  -> empty
-//   first = 0xFFFFFFFF  -> atomicMin target: smallest point index that hit the cell
+// Pillar hash table (open addressing, linear probing, HBM resident; 16 B entries = half a sector).  Initialised by a single
+// 0xFF memset.  The first eight bytes are ONE 64-bit word (key << 32 | first): a point claims an empty slot and records
+// itself as the pillar's first point with a single 64-bit atomicCAS; later points of the same cell only issue a 64-bit
+// atomicMin when their index is smaller than the one the CAS returned (rare: blocks run roughly in index order).
+//   first = 0xFFFFFFFF  -> smallest point index that hit the cell          (low half of the word)
+//   key   = 0xFFFFFFFF  -> empty                                           (high half of the word)
 //   cnt   = 0xFFFFFFFF  -> "count - 1": atomicAdd(cnt, k) returns old; old + 1 is the arrival rank base;
 //                          the scan kernel later replaces it by the start of the pillar's point list
 //   gid   = pillar id in first-appearance order over the whole batch (written by the scan kernel)
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) HashEntry {
-    uint32_t key;
     uint32_t first;
+    uint32_t key;
     uint32_t cnt;
     uint32_t gid;
 };

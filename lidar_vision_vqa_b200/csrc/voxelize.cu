@@ -2,8 +2,9 @@
 // (replaces the spconv CPU call behind src/lidar-encoder/pcdet/datasets/processor/data_processor.py:16-61,133-180):
 //
 //   k_quantize_insert   coalesced float4 tile loads -> fp32 sub/div/floor -> cell key -> open-addressing hash insert
-//                       (atomicCAS straight on the slot, no probing load), then atomicMin(first point index) and
-//                       atomicAdd(count) issued back to back.  __match_any_sync merges the lanes of a warp that hit
+//                       (one 64-bit atomicCAS on {key, first index}: claims the slot and records the first point at
+//                       once; an atomicMin follows only if a later-arriving point has a smaller index) and
+//                       atomicAdd(count).  __match_any_sync merges the lanes of a warp that hit
 //                       the same cell so one lane talks to HBM for the whole group.  One point per thread: the kernel
 //                       is a chain of L2 round trips, so it wants as many warps in flight as the SMs hold.
 //   k_scan_assign       single-pass scan over points in index order of [point is the first of its cell] and of the
@@ -136,12 +137,17 @@ k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int c
         uint32_t slot = 0, base = 0;
         if (lane == leader) {
             slot = static_cast<uint32_t>((static_cast<uint64_t>(hash_key(key)) * cap) >> 32);
+            const unsigned long long mine = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(i);
             while (true) {
-                const uint32_t cur = atomicCAS(&table[slot].key, kEmptyKey, key);
-                if (cur == kEmptyKey || cur == key) break;
+                unsigned long long *word = reinterpret_cast<unsigned long long *>(&table[slot]);
+                const unsigned long long cur = atomicCAS(word, 0xFFFFFFFFFFFFFFFFull, mine);
+                if (cur == 0xFFFFFFFFFFFFFFFFull) break;  // claimed: key and first index set by the same atomic
+                if (static_cast<uint32_t>(cur >> 32) == key) {
+                    if (mine < cur) atomicMin(word, mine);  // same key in the high half: orders by point index
+                    break;
+                }
                 slot = (slot + 1 == cap) ? 0u : slot + 1;
             }
-            atomicMin(&table[slot].first, static_cast<uint32_t>(i));  // independent of the add below: both in flight
             base = atomicAdd(&table[slot].cnt, static_cast<uint32_t>(__popc(peers))) + 1u;
         }
         slot = __shfl_sync(peers, slot, leader);
@@ -216,14 +222,14 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
     uint4 ent[kPerThread];
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k)  // all gathers in flight before the first use
-        ent[k] = slot[k] >= 0 ? *reinterpret_cast<const uint4 *>(&table[slot[k]]) : make_uint4(0, 0xFFFFFFFFu, 0, 0);
+        ent[k] = slot[k] >= 0 ? *reinterpret_cast<const uint4 *>(&table[slot[k]]) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
     unsigned long long val[kPerThread];
     unsigned flags = 0;
     unsigned long long tsum = 0;
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
         val[k] = 0;
-        if (slot[k] >= 0 && ent[k].y == static_cast<uint32_t>(i0 + k)) {  // this point opened the pillar
+        if (slot[k] >= 0 && ent[k].x == static_cast<uint32_t>(i0 + k)) {  // this point opened the pillar
             val[k] = (1ull << 32) | static_cast<unsigned long long>(ent[k].z + 1u);
             flags |= 1u << k;
         }
@@ -272,7 +278,7 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
             // cnt was only needed by this (owning) thread: the entry now carries the list base and the pillar id, so
             // k_place resolves a point with one 16-byte load
             *reinterpret_cast<uint2 *>(&table[slot[k]].cnt) = make_uint2(static_cast<uint32_t>(run & 0xFFFFFFFFull), g);
-            pillar_key[g] = ent[k].x;
+            pillar_key[g] = ent[k].y;
             pillar_list[g] = static_cast<uint32_t>(run & 0xFFFFFFFFull);
             pillar_cnt[g] = static_cast<uint32_t>(val[k] & 0xFFFFFFFFull);
             run += val[k];
@@ -313,7 +319,7 @@ k_place(const float *__restrict__ points, int64_t n, int stride, int col0, int c
     if (i < n) {
         const int32_t s = point_slot[i];
         if (s >= 0) {
-            const uint4 e = *reinterpret_cast<const uint4 *>(&table[s]);  // {key, first, list base, pillar id}
+            const uint4 e = *reinterpret_cast<const uint4 *>(&table[s]);  // {first, key, list base, pillar id}
             const uint32_t g = e.w;
             const uint32_t arrival = point_arrival[i];
             const uint32_t pos = e.z + arrival;

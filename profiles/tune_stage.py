@@ -27,6 +27,10 @@ pfn = ops.fold_pfn(sd["pfn_layers.0.linear.weight"], (sd["pfn_layers.0.norm.weig
                    point_cloud_range=grid.point_cloud_range, device=dev)
 p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
 bufs = ops.EncodeBuffers(len(pts), nb, grid, 64, dev)
+if "--tightcap" in sys.argv:  # size the per-pillar outputs by the pillar count actually seen (+5 %)
+    r0 = ops.encode_bev(p, o, grid, pfn, buffers=bufs, scatter_variant=variant)
+    m0 = int(r0["pillar_count"][-1].item())
+    bufs = ops.EncodeBuffers(len(pts), nb, grid, 64, dev, capacity=int(m0 * 1.05) + 16)
 lib = _native.load()
 K = 30
 evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
