@@ -125,11 +125,13 @@ int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_p
                       const void *coords, int32_t coords_is_float, int64_t m, int32_t max_points,
                       const pillars_pfn_t *pfn, const float voxel_size[3], float *out, void *stream);
 
-/* PointPillarScatter.forward: bev[b][f][y][x] = feats[m][f] for coords[m] = (b,z,y,x), zero elsewhere (nz == 1).
+/* PointPillarScatter.forward: bev[b][f][y][x] = feats[m][f] for coords[m] = (b,z,y,x), zero elsewhere (nz == 1), and
+ * PointPillarScatter3d.forward (pointpillar_scatter.py:40-73) for nz > 1: bev[b][f][z*ny*nx + y*nx + x], which viewed as
+ * [B, f*nz, ny, nx] is exactly the reference's output.
  * m_dev, when not NULL, is a device int32 holding the live row count (<= m); rows beyond it are ignored.
  * variant: 0 = default, 1 = plain vector stores, 2 = bulk async copies (1-D), 3 = TMA tensor stores (2-D). */
 int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
-                        const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, float *bev,
+                        const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz, float *bev,
                         void *workspace, size_t workspace_bytes, int32_t variant, void *stream);
 
 /* The fused path: raw points -> pillar features -> BEV.  Same grouping semantics as pillars_voxelize, same

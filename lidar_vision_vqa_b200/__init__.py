@@ -3,7 +3,7 @@ point -> pillar grouping, per-pillar feature net (augment + Linear + BN + ReLU +
 behind the reference's own module interface.  See DESIGN.md and include/pillars_b200.h."""
 from ._native import NativeLibraryError  # noqa: F401
 from .modules import (MAP_TO_BEV_REGISTRY, VFE_REGISTRY, PFNLayer, PillarVFE, PillarVFEFromPoints,  # noqa: F401
-                      PointPillarScatter, VFETemplate)
+                      PointPillarScatter, PointPillarScatter3d, VFETemplate)
 from .ops import EncodeBuffers, GridSpec, PfnParams  # noqa: F401
 
 __version__ = "0.1.0"

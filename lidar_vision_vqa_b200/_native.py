@@ -82,7 +82,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                       POINTER(PillarsPfn), POINTER(c_float), c_void_p, c_void_p]
     lib.pillars_scatter_bev.restype = c_int
     lib.pillars_scatter_bev.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
-                                        c_int32, c_void_p, c_void_p, c_size_t, c_int32, c_void_p]
+                                        c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_int32, c_void_p]
     lib.pillars_encode_bev.restype = c_int
     lib.pillars_encode_bev.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
                                        POINTER(PillarsPfn), POINTER(PillarsOutputs), c_void_p, c_size_t, c_int32,

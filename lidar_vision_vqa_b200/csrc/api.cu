@@ -216,39 +216,6 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         if ((e = cudaMemsetAsync(out->point_slot, 0xFF, sizeof(int32_t) * n, st)) != cudaSuccess) return cuda_fail(e, "memset");
         note_launch();
     }
-    // Optional (PILLARS_L2_PERSIST=1): ask L2 to keep the pillar features written by the feature kernel resident until the
-    // scatter has read them back (access-policy window on this stream, persisting set-aside sized once per process).
-    static int l2_mode = -1;
-    static size_t l2_setaside = 0, l2_max_window = 0;
-    if (l2_mode < 0) {
-        const char *ev = getenv("PILLARS_L2_PERSIST");
-        l2_mode = ev ? atoi(ev) : 0;
-        if (l2_mode) {
-            int dev = 0, max_persist = 0, max_win = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-            l2_setaside = static_cast<size_t>(max_persist);
-            l2_max_window = static_cast<size_t>(max_win);
-            if (l2_setaside == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_setaside) != cudaSuccess) l2_mode = 0;
-            fprintf(stderr, "[pillars] L2 persisting set-aside %zu MB, max window %zu MB, mode %d\n", l2_setaside >> 20,
-                    l2_max_window >> 20, l2_mode);
-        }
-    }
-    const bool l2_window = l2_mode && want_bev && out->pillar_features && out->pillar_capacity > 0;
-    if (l2_window) {
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof(av));
-        size_t bytes = static_cast<size_t>(out->pillar_capacity) * 64 * sizeof(float);
-        if (bytes > l2_max_window) bytes = l2_max_window;
-        av.accessPolicyWindow.base_ptr = out->pillar_features;
-        av.accessPolicyWindow.num_bytes = bytes;
-        av.accessPolicyWindow.hitRatio = bytes <= l2_setaside ? 1.0f : static_cast<float>(l2_setaside) / static_cast<float>(bytes);
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
-
     // Feature kernel choice.  The constant-bank fast kernel covers the mainstream configuration when the caller also
     // supplied host copies of the weights; everything else runs the generic 16-lanes-per-pillar kernel.
     const bool membership = out->voxels || out->point_pillar || out->point_slot;
@@ -313,11 +280,6 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
             return cuda_fail(e, "scatter");
     }
     stage_mark(3, st);
-    if (l2_window) {
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof(av));
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
     g_launches_last = g_launches;
     return 0;
 }
@@ -361,24 +323,25 @@ int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_p
 }
 
 int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m, const int32_t *m_dev,
-                        int32_t n_frames, int32_t f, int32_t nx, int32_t ny, float *bev, void *workspace,
+                        int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz, float *bev, void *workspace,
                         size_t workspace_bytes, int32_t variant, void *stream)
 {
     g_launches = 0;
-    if (m < 0 || n_frames < 0 || f < 1 || nx < 1 || ny < 1) return fail(PILLARS_E_BADARG, "pillars_scatter_bev: bad size");
+    if (m < 0 || n_frames < 0 || f < 1 || nx < 1 || ny < 1 || nz < 1) return fail(PILLARS_E_BADARG, "pillars_scatter_bev: bad size");
     if (n_frames > 0 && !bev) return fail(PILLARS_E_BADARG, "bev is NULL");
     if (m > 0 && (!feats || !coords)) return fail(PILLARS_E_BADARG, "feats / coords NULL");
     if (m > 0 && reinterpret_cast<uintptr_t>(coords) % 16 != 0) return fail(PILLARS_E_BADARG, "coords must be 16-byte aligned");
-    const size_t need = sizeof(int32_t) * static_cast<size_t>(n_frames) * nx * ny;
+    const size_t need = sizeof(int32_t) * static_cast<size_t>(n_frames) * nx * ny * nz;
     if (need > 0 && (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 16 != 0))
         return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
     if (n_frames == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int32_t *cell_row = static_cast<int32_t *>(workspace);
     cudaError_t e;
-    if ((e = launch_build_cell_row(coords, coords_is_float != 0, m, m_dev, n_frames, nx, ny, cell_row, st)) != cudaSuccess)
+    if ((e = launch_build_cell_row(coords, coords_is_float != 0, m, m_dev, n_frames, nx, ny, nz, cell_row, st)) != cudaSuccess)
         return cuda_fail(e, "build_cell_row");
-    if ((e = launch_scatter(feats, cell_row, n_frames, f, nx, ny, bev, variant, st)) != cudaSuccess)
+    // the canvas of the 3-D variant is the 2-D one with nz*ny rows per channel
+    if ((e = launch_scatter(feats, cell_row, n_frames, f, nx, ny * nz, bev, variant, st)) != cudaSuccess)
         return cuda_fail(e, "scatter");
     g_launches_last = g_launches;
     return 0;

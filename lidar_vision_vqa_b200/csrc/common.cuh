@@ -204,7 +204,7 @@ cudaError_t launch_pfn_dense(const float *voxels, const void *num_points, bool n
                              bool use_abs, bool with_dist, const PfnDev &pfn, float *out, cudaStream_t st);
 
 cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t m, const int32_t *m_dev, int nb, int nx,
-                                  int ny, int32_t *cell_row, cudaStream_t st);
+                                  int ny, int nz, int32_t *cell_row, cudaStream_t st);
 cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, int f, int nx, int ny, float *bev,
                            int variant, cudaStream_t st);
 

@@ -26,7 +26,8 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void k_build_cell_row(const void *__restrict__ coords, int coords_float, int64_t m,
-                                 const int32_t *__restrict__ m_dev, int nb, int nx, int ny, int32_t *__restrict__ cell_row)
+                                 const int32_t *__restrict__ m_dev, int nb, int nx, int ny, int nz,
+                                 int32_t *__restrict__ cell_row)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     int64_t live = m;
@@ -40,10 +41,11 @@ __global__ void k_build_cell_row(const void *__restrict__ coords, int coords_flo
         const int4 c = *reinterpret_cast<const int4 *>(static_cast<const int32_t *>(coords) + i * 4);
         b = c.x; z = c.y; y = c.z; x = c.w;
     }
-    // pointpillar_scatter.py:27  index = z + y*nx + x  (nz == 1, so z == 0)
-    const int64_t cell = static_cast<int64_t>(z) + static_cast<int64_t>(y) * nx + x;
-    if (b < 0 || b >= nb || cell < 0 || cell >= static_cast<int64_t>(nx) * ny) return;
-    atomicMax(cell_row + static_cast<int64_t>(b) * nx * ny + cell, static_cast<int32_t>(i));  // later row wins
+    // pointpillar_scatter.py:27  index = z + y*nx + x (nz == 1, so z == 0);  :63  index = z*ny*nx + y*nx + x (3-D variant)
+    const int64_t plane = static_cast<int64_t>(nx) * ny * nz;
+    const int64_t cell = nz > 1 ? (static_cast<int64_t>(z) * ny + y) * nx + x : static_cast<int64_t>(z) + static_cast<int64_t>(y) * nx + x;
+    if (b < 0 || b >= nb || cell < 0 || cell >= plane || x < 0 || x >= nx) return;
+    atomicMax(cell_row + static_cast<int64_t>(b) * plane + cell, static_cast<int32_t>(i));  // later row wins
 }
 
 // ---- variant 1 ----------------------------------------------------------------------------------
@@ -293,13 +295,13 @@ int sm_count()
 }  // namespace
 
 cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t m, const int32_t *m_dev, int nb, int nx,
-                                  int ny, int32_t *cell_row, cudaStream_t st)
+                                  int ny, int nz, int32_t *cell_row, cudaStream_t st)
 {
-    cudaError_t err = cudaMemsetAsync(cell_row, 0xFF, sizeof(int32_t) * static_cast<size_t>(nb) * nx * ny, st);
+    cudaError_t err = cudaMemsetAsync(cell_row, 0xFF, sizeof(int32_t) * static_cast<size_t>(nb) * nx * ny * nz, st);
     note_launch();
     if (err != cudaSuccess || m == 0) return err;
     const unsigned blocks = static_cast<unsigned>((m + kThreads - 1) / kThreads);
-    k_build_cell_row<<<blocks, kThreads, 0, st>>>(coords, coords_float ? 1 : 0, m, m_dev, nb, nx, ny, cell_row);
+    k_build_cell_row<<<blocks, kThreads, 0, st>>>(coords, coords_float ? 1 : 0, m, m_dev, nb, nx, ny, nz, cell_row);
     note_launch();
     return cudaGetLastError();
 }

@@ -215,6 +215,31 @@ class PointPillarScatter(nn.Module):
         return batch_dict
 
 
+class PointPillarScatter3d(nn.Module):
+    """pointpillar_scatter.py:40-73: grid from ``INPUT_SHAPE``, ``NUM_BEV_FEATURES // nz`` channels per pillar, canvas
+    index ``z*ny*nx + y*nx + x``, output ``[B, NUM_BEV_FEATURES, ny, nx]``."""
+
+    def __init__(self, model_cfg, grid_size=None, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.nx, self.ny, self.nz = (int(v) for v in _cfg_get(model_cfg, "INPUT_SHAPE"))
+        self.num_bev_features = _cfg_get(model_cfg, "NUM_BEV_FEATURES")
+        self.num_bev_features_before_compression = self.num_bev_features // self.nz
+        self.variant = str(_cfg_get(model_cfg, "SCATTER_VARIANT", "auto"))
+
+    def forward(self, batch_dict, **kwargs):
+        feats, coords = batch_dict["pillar_features"], batch_dict["voxel_coords"]
+        if "batch_size" in batch_dict:
+            batch_size = int(batch_dict["batch_size"])
+        else:
+            batch_size = int(coords[:, 0].max().int().item()) + 1
+        if feats.shape[-1] != self.num_bev_features_before_compression:
+            raise ValueError("pillar_features channels != NUM_BEV_FEATURES // nz")
+        batch_dict["spatial_features"] = ops.scatter_bev(feats, coords, batch_size, self.nx, self.ny, self.nz,
+                                                         variant=self.variant)
+        return batch_dict
+
+
 # name-keyed registries shaped like pcdet's (models/backbones_3d/vfe/__init__.py:9-18,
 # models/backbones_2d/map_to_bev/__init__.py:5-10); INTEGRATION.md shows the two-line merge into them.
 VFE_REGISTRY = {
@@ -224,4 +249,5 @@ VFE_REGISTRY = {
 }
 MAP_TO_BEV_REGISTRY = {
     "PointPillarScatter": PointPillarScatter,
+    "PointPillarScatter3d": PointPillarScatter3d,
 }

@@ -213,10 +213,11 @@ def pfn_dense(voxels: torch.Tensor, num_points: torch.Tensor, coords: torch.Tens
     return out
 
 
-def scatter_bev(pillar_features: torch.Tensor, coords: torch.Tensor, batch_size: int, nx: int, ny: int, *,
+def scatter_bev(pillar_features: torch.Tensor, coords: torch.Tensor, batch_size: int, nx: int, ny: int, nz: int = 1, *,
                 m_dev: Optional[torch.Tensor] = None, variant: str = "auto", ws_slot: int = 0,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """PointPillarScatter.forward: ``[B, F, ny, nx]`` float32, zero where no pillar."""
+    """PointPillarScatter.forward: ``[B, F, ny, nx]`` float32, zero where no pillar; with ``nz > 1`` the 3-D variant
+    (PointPillarScatter3d, pointpillar_scatter.py:40-73): ``[B, F*nz, ny, nx]``."""
     _require_device(pillar_features)
     feats = pillar_features.reshape(-1, pillar_features.shape[-1]).contiguous()
     if feats.dtype != torch.float32:
@@ -227,11 +228,11 @@ def scatter_bev(pillar_features: torch.Tensor, coords: torch.Tensor, batch_size:
     else:
         crd, crd_f = coords.to(torch.int32).contiguous(), 0
     dev = feats.device
-    bev = out if out is not None else torch.empty((batch_size, f, ny, nx), dtype=torch.float32, device=dev)
-    need = 4 * batch_size * nx * ny
+    bev = out if out is not None else torch.empty((batch_size, f * nz, ny, nx), dtype=torch.float32, device=dev)
+    need = 4 * batch_size * nx * ny * nz
     ws = workspace(need, dev, ws_slot)
     check(_native.load().pillars_scatter_bev(feats.data_ptr(), crd.data_ptr(), crd_f, m, _ptr(m_dev), batch_size, f, nx,
-                                             ny, bev.data_ptr(), ws.data_ptr(), ws.numel(), SCATTER_VARIANTS[variant],
+                                             ny, nz, bev.data_ptr(), ws.data_ptr(), ws.numel(), SCATTER_VARIANTS[variant],
                                              _stream_ptr()), "pillars_scatter_bev")
     return bev
 

@@ -87,4 +87,4 @@ def densify(tokens: GatheredTokens, nx: int, ny: int, variant: str = "auto") -> 
     single-GPU path)."""
     from . import ops
 
-    return ops.scatter_bev(tokens.pillar_features, tokens.voxel_coords, tokens.n_frames, nx, ny, variant=variant)
+    return ops.scatter_bev(tokens.pillar_features, tokens.voxel_coords, tokens.n_frames, nx, ny, 1, variant=variant)

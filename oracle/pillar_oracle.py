@@ -51,7 +51,7 @@ def _lib():
                                              ctypes.c_int, fp, ip, ip, ip, ip]
         lib.oracle_scatter_bev.restype = ctypes.c_int
         lib.oracle_scatter_bev.argtypes = [fp, ip, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_int, fp]
+                                           ctypes.c_int, ctypes.c_int, fp]
         _LIB = lib
     return _LIB
 
@@ -266,14 +266,14 @@ def collate_voxels(v: dict, as_float: bool = True):
 # --------------------------------------------------------------------------------------------------
 # BEV scatter
 # --------------------------------------------------------------------------------------------------
-def scatter_bev(pillar_features, coords, nx: int, ny: int, batch_size: Optional[int] = None) -> np.ndarray:
-    """pointpillar_scatter.py:14-37 (nz == 1).  ``batch_size`` None reproduces the reference's
-    ``coords[:,0].max()+1`` (:17).  Runs the C restatement."""
+def scatter_bev(pillar_features, coords, nx: int, ny: int, batch_size: Optional[int] = None, nz: int = 1) -> np.ndarray:
+    """pointpillar_scatter.py:14-37 (nz == 1) and :40-73 (PointPillarScatter3d, nz > 1 -> ``[B, F*nz, ny, nx]``).
+    ``batch_size`` None reproduces the reference's ``coords[:,0].max()+1`` (:17).  Runs the C restatement."""
     f = np.ascontiguousarray(np.asarray(pillar_features, dtype=np.float32))
     c = np.ascontiguousarray(np.asarray(coords).astype(np.int32))
     nb = int(c[:, 0].max()) + 1 if batch_size is None else int(batch_size)
-    bev = np.empty((nb, f.shape[1], ny, nx), dtype=np.float32)
-    rc = _lib().oracle_scatter_bev(_fptr(f), _iptr(c), f.shape[0], nb, f.shape[1], nx, ny, _fptr(bev))
+    bev = np.empty((nb, f.shape[1] * nz, ny, nx), dtype=np.float32)
+    rc = _lib().oracle_scatter_bev(_fptr(f), _iptr(c), f.shape[0], nb, f.shape[1], nx, ny, nz, _fptr(bev))
     if rc != 0:
         raise RuntimeError(f"oracle_scatter_bev failed: {rc}")
     return bev

@@ -120,24 +120,27 @@ int oracle_voxelize_hard(const float *points, int64_t n, int c, const float *ran
     return num_voxels;
 }
 
-/* The reference's dense BEV scatter, restated for one batch (nz == 1):
- *   src/lidar-encoder/pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37
- *   canvas[b][f][y*nx + x] = feats[m][f]   for every pillar m with coords (b, z, y, x); zero elsewhere.
- * coords is [m,4] int32 (b,z,y,x); bev is [B, F, ny, nx] and is zero-filled here.  Later rows overwrite
+/* The reference's dense BEV scatter, restated for one batch:
+ *   src/lidar-encoder/pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37  (nz == 1)
+ *   canvas[b][f][z + y*nx + x] = feats[m][f]   for every pillar m with coords (b, z, y, x); zero elsewhere;
+ *   pointpillar_scatter.py:40-73 (PointPillarScatter3d, nz > 1): canvas[b][f][z*ny*nx + y*nx + x], the canvas
+ *   [F, nz*ny*nx] then viewed as [F*nz, ny, nx].
+ * coords is [m,4] int32 (b,z,y,x); bev is [B, F*nz, ny, nx] and is zero-filled here.  Later rows overwrite
  * earlier ones on a duplicate cell (the voxeliser never produces duplicates).
  */
-int oracle_scatter_bev(const float *feats, const int32_t *coords, int64_t m, int nb, int f, int nx, int ny,
+int oracle_scatter_bev(const float *feats, const int32_t *coords, int64_t m, int nb, int f, int nx, int ny, int nz,
                        float *bev)
 {
-    if (!feats || !coords || !bev)
+    if (!feats || !coords || !bev || nz < 1)
         return -1;
-    const size_t plane = (size_t)nx * ny;
+    const size_t plane = (size_t)nx * ny * nz;
     memset(bev, 0, (size_t)nb * f * plane * sizeof(float));
     for (int64_t i = 0; i < m; ++i) {
         const int32_t b = coords[4 * i], z = coords[4 * i + 1], y = coords[4 * i + 2], x = coords[4 * i + 3];
-        if (b < 0 || b >= nb || y < 0 || y >= ny || x < 0 || x >= nx)
+        if (b < 0 || b >= nb || y < 0 || y >= ny || x < 0 || x >= nx || z < 0 || z >= nz)
             return -2;
-        const size_t cell = (size_t)z + (size_t)y * nx + x; /* pointpillar_scatter.py:27 */
+        const size_t cell = nz > 1 ? ((size_t)z * ny + y) * nx + x           /* pointpillar_scatter.py:63 */
+                                   : (size_t)z + (size_t)y * nx + x;         /* pointpillar_scatter.py:27 */
         float *dst = bev + (size_t)b * f * plane + cell;
         const float *src = feats + (size_t)i * f;
         for (int k = 0; k < f; ++k)

@@ -116,6 +116,27 @@ def run_dynamic(name, *, batch, c, n_keep, seed, num_filters=(64,)):
     print(f"{name}: N={len(pb)} M={save['out.voxel_coords'].shape[0]} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def run_scatter3d(name, *, batch, nx, ny, nz, c_before, m_per_frame, seed):
+    """PointPillarScatter3d on random unique cells (the DSVT-pillar configs use it with nz > 1)."""
+    ref = ref_loader.load_reference()
+    rng = np.random.default_rng(seed)
+    coords, feats = [], []
+    for b in range(batch):
+        cells = rng.choice(nx * ny * nz, m_per_frame, replace=False)
+        z, rem = cells // (nx * ny), cells % (nx * ny)
+        coords.append(np.stack([np.full(m_per_frame, b), z, rem // nx, rem % nx], 1))
+        feats.append(rng.standard_normal((m_per_frame, c_before)).astype(np.float32))
+    coords = np.concatenate(coords).astype(np.float32)  # fp32 like load_data_to_gpu
+    feats = np.concatenate(feats)
+    sc = ref.PointPillarScatter3d(ref.AttrDict(INPUT_SHAPE=[nx, ny, nz], NUM_BEV_FEATURES=c_before * nz), grid_size=None)
+    with torch.inference_mode():
+        out = sc({"pillar_features": torch.from_numpy(feats), "voxel_coords": torch.from_numpy(coords)})
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, pillar_features=feats, voxel_coords=coords, input_shape=np.array([nx, ny, nz]),
+                        num_bev_features=np.int32(c_before * nz), **{"out.spatial_features": out["spatial_features"].numpy()})
+    print(f"{name}: out {tuple(out['spatial_features'].shape)} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -129,3 +150,4 @@ if __name__ == "__main__":
     run_case("vfe_c5_m1", batch=1, c=5, p_max=8, max_voxels=1, n_keep=200, seed=50, scatter=False)
     run_case("vfe_c5_2layer", batch=1, c=5, p_max=12, max_voxels=1000, n_keep=1200, seed=60, num_filters=(64, 64))
     run_dynamic("dyn_c5", batch=2, c=5, n_keep=2000, seed=70)
+    run_scatter3d("scatter3d_nz2", batch=2, nx=40, ny=36, nz=2, c_before=32, m_per_frame=300, seed=80)

@@ -53,7 +53,7 @@ def test_workspace_query_and_argument_errors(lib):
     assert 0 < a < b < c
     assert lib.pillars_workspace_bytes(0, 4, ctypes.byref(g)) >= 4 * 4 * 512 * 512
     # bad arguments are reported through the return code + pillars_last_error, never a crash
-    rc = lib.pillars_scatter_bev(None, None, 0, 5, None, 1, 64, 8, 8, None, None, 0, 0, None)
+    rc = lib.pillars_scatter_bev(None, None, 0, 5, None, 1, 64, 8, 8, 1, None, None, 0, 0, None)
     assert rc != 0 and lib.pillars_last_error()
     out = _native.PillarsOutputs()
     rc = lib.pillars_voxelize(None, 10, 5, 0, 5, None, 1, ctypes.byref(g), ctypes.byref(out), None, 0, None)

@@ -334,6 +334,26 @@ def test_fused_path_c4_and_scatter_variants_agree(dev, L, oracle):
     np.testing.assert_allclose(outs["tma2d"].cpu().numpy(), ref_bev, rtol=FEAT_RTOL, atol=FEAT_ATOL)
 
 
+@pytest.mark.parametrize("variant", ["plain", "bulk1d", "tma2d", "auto"])
+def test_scatter3d_module_vs_reference_golden(variant, dev, L):
+    """PointPillarScatter3d (pointpillar_scatter.py:40-73): nz = 2, 32 channels per pillar -> [B, 64, ny, nx]."""
+    g = load_golden("scatter3d_nz2")
+
+    class C(dict):
+        __getattr__ = dict.__getitem__
+
+    sc = L.PointPillarScatter3d(model_cfg=C(INPUT_SHAPE=[int(v) for v in g["input_shape"]],
+                                            NUM_BEV_FEATURES=int(g["num_bev_features"]), SCATTER_VARIANT=variant),
+                                grid_size=None)
+    for coords in (g["voxel_coords"], g["voxel_coords"].astype(np.int32)):
+        bd = {"pillar_features": torch.from_numpy(g["pillar_features"]).to(dev),
+              "voxel_coords": torch.from_numpy(coords).to(dev)}
+        bev = sc(bd)["spatial_features"].cpu().numpy()
+        ref = g["out.spatial_features"]
+        assert bev.shape == ref.shape
+        np.testing.assert_array_equal(bev.view(np.uint32), ref.view(np.uint32))
+
+
 def test_scatter_odd_shapes(dev, L, oracle):
     """Grids that are not multiples of the 256-cell tile, of 4, and a channel count other than 64."""
     r = np.random.default_rng(0)

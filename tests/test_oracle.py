@@ -34,6 +34,15 @@ def test_scatter_restatement_matches_reference_golden(oracle, name):
     np.testing.assert_array_equal(bev, g["out.spatial_features"])
 
 
+def test_scatter3d_restatement_matches_reference_golden(oracle):
+    """PointPillarScatter3d (pointpillar_scatter.py:40-73), nz = 2, fp32 coords as after load_data_to_gpu."""
+    g = load_golden("scatter3d_nz2")
+    nx, ny, nz = (int(v) for v in g["input_shape"])
+    bev = oracle.scatter_bev(g["pillar_features"], g["voxel_coords"], nx, ny, nz=nz)
+    assert bev.shape == g["out.spatial_features"].shape == (2, int(g["num_bev_features"]), ny, nx)
+    np.testing.assert_array_equal(bev, g["out.spatial_features"])
+
+
 @pytest.mark.parametrize("name", vfe_golden_names())
 def test_golden_voxel_inputs_are_reproducible(oracle, name):
     """The voxel tensors fed to the reference came from the C voxeliser; regenerate them from the stored points."""
