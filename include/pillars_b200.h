@@ -75,12 +75,13 @@ typedef struct pillars_pfn {
     const float *weight;      /* [f_out, c_in] row-major = nn.Linear.weight */
     const float *scale;       /* [f_out] */
     const float *shift;       /* [f_out] */
-    /* Optional HOST copies of the three arrays above (all three or none).  When present, pillars_encode_bev folds them
-     * into kernel parameters and runs the constant-bank fast kernel (USE_ABSLOTE_XYZ, no WITH_DISTANCE, C <= 5). */
-    const float *weight_host;
-    const float *scale_host;
-    const float *shift_host;
+    /* Optional: the layer regrouped around the pillar centre, PILLARS_FOLDED_FLOATS floats on the device, written once
+     * per model by pillars_fold_pfn().  NULL: pillars_encode_bev folds into its workspace on every call (one extra
+     * single-block launch).  Used by the streaming feature kernel (USE_ABSLOTE_XYZ, no WITH_DISTANCE, C <= 5). */
+    const float *folded;
 } pillars_pfn_t;
+
+#define PILLARS_FOLDED_FLOATS (13 * 64)
 
 /* what pillars_encode_bev / pillars_voxelize write; any pointer may be NULL to skip that output */
 typedef struct pillars_outputs {
@@ -117,6 +118,10 @@ int pillars_frame_offsets(const float *points_b, int64_t n, int32_t row_stride, 
 int pillars_voxelize(const float *points, int64_t n, int32_t row_stride, int32_t col0, int32_t c_point,
                      const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
                      const pillars_outputs_t *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Prepares pfn->folded: `folded` (device, PILLARS_FOLDED_FLOATS floats) from pfn->weight/scale/shift.  Fails with
+ * PILLARS_E_UNSUPPORTED when the layer is not one the streaming kernel covers (then leave pfn->folded NULL). */
+int pillars_fold_pfn(const pillars_pfn_t *pfn, float *folded, void *stream);
 
 /* PillarVFE.forward on already grouped voxels (the reference's own input format).
  * voxels [m, P, C] fp32; num_points [m] and coords [m,4] (b,z,y,x) are int32, or fp32 when *_is_float != 0

@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = (
     "pillars_workspace_bytes",
     "pillars_frame_offsets",
     "pillars_voxelize",
+    "pillars_fold_pfn",
     "pillars_pfn_dense",
     "pillars_scatter_bev",
     "pillars_encode_bev",
@@ -35,7 +36,7 @@ class PillarsGrid(Structure):
 class PillarsPfn(Structure):
     _fields_ = [("c_point", c_int32), ("c_in", c_int32), ("f_out", c_int32), ("use_absolute_xyz", c_int32),
                 ("with_distance", c_int32), ("offset", c_float * 3), ("weight", c_void_p), ("scale", c_void_p),
-                ("shift", c_void_p), ("weight_host", c_void_p), ("scale_host", c_void_p), ("shift_host", c_void_p)]
+                ("shift", c_void_p), ("folded", c_void_p)]
 
 
 class PillarsOutputs(Structure):
@@ -77,6 +78,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_voxelize.restype = c_int
     lib.pillars_voxelize.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                      POINTER(PillarsGrid), POINTER(PillarsOutputs), c_void_p, c_size_t, c_void_p]
+    lib.pillars_fold_pfn.restype = c_int
+    lib.pillars_fold_pfn.argtypes = [POINTER(PillarsPfn), c_void_p, c_void_p]
     lib.pillars_pfn_dense.restype = c_int
     lib.pillars_pfn_dense.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32,
                                       POINTER(PillarsPfn), POINTER(c_float), c_void_p, c_void_p]

@@ -88,22 +88,10 @@ static int check_pfn(const pillars_pfn_t *pfn)
 
 static thread_local bool g_force_generic = false;
 
-// W.[p, p - mean, p - centre] regrouped around the pillar centre (see pfn_fast.cu); BatchNorm scale folded in, in double.
-static void fold_fast_weights(const pillars_pfn_t &pfn, FastWeights *fw)
+// what pfn_stream.cu is written for: absolute xyz + cluster + centre features of a <= 5-channel point, 64 outputs
+static bool stream_kernel_covers(const pillars_pfn_t &pfn)
 {
-    const int c = pfn.c_point, cin = pfn.c_in;  // feature order: p[0..c), cluster xyz, centre xyz
-    for (int o = 0; o < 64; ++o) {
-        const float *w = pfn.weight_host + static_cast<size_t>(o) * cin;
-        const double s = pfn.scale_host[o];
-        for (int a = 0; a < 3; ++a) {
-            fw->wp[a][o] = static_cast<float>(s * (static_cast<double>(w[a]) + w[c + a] + w[c + 3 + a]));
-            fw->wk[a][o] = static_cast<float>(s * w[a]);
-            fw->wk[3 + a][o] = static_cast<float>(s * w[c + a]);
-        }
-        fw->wp[3][o] = c > 3 ? static_cast<float>(s * w[3]) : 0.f;
-        fw->wp[4][o] = c > 4 ? static_cast<float>(s * w[4]) : 0.f;
-        fw->shift[o] = pfn.shift_host[o];
-    }
+    return pfn.use_absolute_xyz && !pfn.with_distance && pfn.c_point <= 5 && pfn.f_out == 64;
 }
 
 static PfnDev make_pfn_dev(const pillars_pfn_t &pfn, const float voxel[3])
@@ -216,13 +204,24 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         if ((e = cudaMemsetAsync(out->point_slot, 0xFF, sizeof(int32_t) * n, st)) != cudaSuccess) return cuda_fail(e, "memset");
         note_launch();
     }
-    // Feature kernel choice.  The constant-bank fast kernel covers the mainstream configuration when the caller also
-    // supplied host copies of the weights; everything else runs the generic 16-lanes-per-pillar kernel.
+    // Feature kernel choice.  The streaming kernel covers the mainstream configuration; everything else runs the generic
+    // 16-lanes-per-pillar kernel.
     const bool membership = out->voxels || out->point_pillar || out->point_slot;
-    const bool fast = pfn && pfn->weight_host && pfn->scale_host && pfn->shift_host && pfn->use_absolute_xyz &&
-                      !pfn->with_distance && pfn->c_point <= 5 && pfn->f_out == 64 && !g_force_generic;
+    const bool fast = pfn && stream_kernel_covers(*pfn) && !g_force_generic;
+    PlaceExtras px{};
+    px.records = fast;
+    if (fast) {
+        for (int i = 0; i < 3; ++i) {
+            px.vsz[i] = grid->voxel[i];
+            px.off[i] = pfn->offset[i];
+        }
+        px.voxel_coords = out->voxel_coords;
+        px.voxel_num_points = out->voxel_num_points;
+        px.write_cell_row = want_bev;
+        px.capacity = out->pillar_capacity;
+    }
     if ((e = launch_group_points(points, n, row_stride, col0, c_point, frame_offsets, n_frames, gd, ws, out->pillar_count,
-                                 /*want_index_lists=*/membership || !fast, /*want_records=*/fast, st)) != cudaSuccess)
+                                 /*want_index_lists=*/membership || !fast, px, st)) != cudaSuccess)
         return cuda_fail(e, "group_points");
     stage_mark(1, st);
 
@@ -248,21 +247,18 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         if ((e = launch_pillar_features(job, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features");
     }
     if (fast) {
-        FastWeights fw;
-        fold_fast_weights(*pfn, &fw);
+        const float *folded = pfn->folded;
+        if (!folded) {  // the caller did not prepare the table: fold into the workspace (one more single-block launch)
+            if ((e = launch_fold_pfn(job.pfn, pfn->c_point, pfn->c_in, ws.folded, st)) != cudaSuccess)
+                return cuda_fail(e, "fold_pfn");
+            folded = ws.folded;
+        }
         FastJob fj{};
         fj.n = n;
         fj.idx_bits = job.idx_bits;
-        for (int i = 0; i < 3; ++i) {
-            fj.vsz[i] = grid->voxel[i];
-            fj.off[i] = pfn->offset[i];
-        }
         fj.pillar_features = out->pillar_features;
-        fj.voxel_coords = out->voxel_coords;
-        fj.voxel_num_points = out->voxel_num_points;
-        fj.capacity = out->pillar_capacity;
-        fj.write_cell_row = want_bev;
-        if ((e = launch_pillar_features_fast(fj, fw, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features_fast");
+        if ((e = launch_pillar_features_stream(fj, folded, gd, ws, st)) != cudaSuccess)
+            return cuda_fail(e, "pillar_features_stream");
     }
     stage_mark(2, st);
 
@@ -280,6 +276,20 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
             return cuda_fail(e, "scatter");
     }
     stage_mark(3, st);
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_fold_pfn(const pillars_pfn_t *pfn, float *folded, void *stream)
+{
+    g_launches = 0;
+    int rc;
+    if ((rc = check_pfn(pfn))) return rc;
+    if (!folded) return fail(PILLARS_E_BADARG, "folded is NULL");
+    if (!stream_kernel_covers(*pfn)) return fail(PILLARS_E_UNSUPPORTED, "layer is outside what the streaming feature kernel covers");
+    const float unit[3] = {1.f, 1.f, 1.f};
+    cudaError_t e = launch_fold_pfn(make_pfn_dev(*pfn, unit), pfn->c_point, pfn->c_in, folded, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "fold_pfn");
     g_launches_last = g_launches;
     return 0;
 }

@@ -32,12 +32,13 @@ struct Header {
     uint32_t tile_counter;   // dynamic tile ids of the chained scan
     uint32_t total_pillars;  // G: distinct occupied cells over the batch, before the max_voxels cap
     uint32_t total_listed;   // points that fell into some cell (sum of all counts)
-    uint32_t pad[13];
+    uint32_t tiles_done;     // scan tiles that have finished (the last one turns frame starts into output rows)
+    uint32_t pad[12];
 };
 
 // One point, moved next to the other points of its pillar (32 B = one DRAM sector).
 struct __align__(32) PointRecord {
-    float x, y, z, intensity, time;  // missing channels are 0
+    float x, y, z, intensity, time;  // x,y,z RELATIVE TO THE PILLAR CENTRE (pillar_vfe.py:100-103); missing channels are 0
     uint32_t idx;                    // index of the point in the input batch
     uint32_t gid;                    // pillar id (first-appearance order, batch-global, uncapped)
     uint32_t arrival;                // position inside the pillar's list; 0 marks the start of a list
@@ -66,6 +67,8 @@ struct Workspace {
     uint32_t *pillar_cnt;           // [n] points that fell into pillar g (uncapped)
     uint32_t *sorted_idx;           // [n] point indices grouped by pillar
     PointRecord *records;           // [n] point records grouped by pillar
+    float4 *pillar_meta;            // [2n] per pillar g: {centre x,y,z, 1.0 if n < P} {row (int bits, -1: dropped), n (uint bits), -, -}
+    float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
     uint32_t cap;                   // hash slots
     uint32_t n_tiles;
     size_t total_bytes;
@@ -114,6 +117,8 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     w.pillar_cnt = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.sorted_idx = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.records = reinterpret_cast<PointRecord *>(take(sizeof(PointRecord) * n));
+    w.pillar_meta = reinterpret_cast<float4 *>(take(sizeof(float4) * 2 * n));
+    w.folded = reinterpret_cast<float *>(take(sizeof(float) * PILLARS_FOLDED_FLOATS));
     w.total_bytes = off;
     return w;
 }
@@ -158,9 +163,19 @@ void note_launch(int n = 1);
 // ---- launchers implemented in the kernel translation units ---------------------------------------
 cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, int nb, int32_t *offs, cudaStream_t st);
 
+// What k_place additionally emits for the streaming feature kernel (records == true): point records relative to the pillar
+// centre, the per-pillar constants, and the per-pillar outputs that need no feature arithmetic.
+struct PlaceExtras {
+    bool records;
+    float vsz[3], off[3];      // pillar centre = coord * vsz + off (pillar_vfe.py:79-81,101-103)
+    int32_t *voxel_coords;     // [capacity,4] or NULL
+    int32_t *voxel_num_points; // [capacity] or NULL
+    bool write_cell_row;       // fill ws.cell_row for the BEV scatter
+    int64_t capacity;
+};
 cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, int c_point,
                                 const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
-                                int32_t *pillar_count, bool want_index_lists, bool want_records, cudaStream_t st);
+                                int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras, cudaStream_t st);
 
 struct FeatureJob {
     const float *points;
@@ -181,23 +196,18 @@ struct FeatureJob {
 };
 cudaError_t launch_pillar_features(const FeatureJob &job, const GridDev &gd, const Workspace &ws, cudaStream_t st);
 
-// Host-folded weights of the fast feature kernel; passed by value as a kernel parameter (constant bank).
-struct FastWeights {
-    float wp[5][64];  // per point:  scale * (W_p + W_cluster + W_centre) for x,y,z;  scale * W for intensity, time
-    float wk[6][64];  // per pillar: scale * W_p (x,y,z) applied to the centre, scale * W_cluster applied to (mean - centre)
-    float shift[64];
-};
 struct FastJob {
     int64_t n;  // upper bound of listed points (the input point count)
     int idx_bits;
-    float vsz[3], off[3];
     float *pillar_features;
-    int32_t *voxel_coords, *voxel_num_points;
-    int64_t capacity;
-    bool write_cell_row;
 };
-cudaError_t launch_pillar_features_fast(const FastJob &job, const FastWeights &w, const GridDev &gd, const Workspace &ws,
-                                        cudaStream_t st);
+// The streaming feature kernel (pfn_stream.cu) and the folding of one PFN layer into its table:
+//   rows 0-4   per point   scale * (W_p + W_cluster + W_centre) for x,y,z;  scale * W for intensity, time
+//   rows 5-10  per pillar  scale * W_p (x,y,z) applied to the centre;  -scale * W_cluster applied to (mean - centre)
+//   row  11    shift       row 12  relu(shift)
+cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st);
+cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folded, const GridDev &gd, const Workspace &ws,
+                                          cudaStream_t st);
 
 cudaError_t launch_pfn_dense(const float *voxels, const void *num_points, bool np_float, const void *coords,
                              bool coords_float, int64_t m, int max_points, int c_point, int c_in, int f_out,

@@ -189,7 +189,8 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
               Header *__restrict__ hdr, unsigned long long *__restrict__ tile_agg, unsigned long long *__restrict__ tile_prefix,
               uint32_t *__restrict__ pillar_key, uint32_t *__restrict__ pillar_list,
               uint32_t *__restrict__ pillar_cnt, const int32_t *__restrict__ frame_offsets, int nb,
-              uint32_t *__restrict__ frame_gstart, int dynamic_ids)
+              uint32_t *__restrict__ frame_gstart, int dynamic_ids, int max_voxels, uint32_t *__restrict__ frame_rowbase,
+              int32_t *__restrict__ pillar_count)
 {
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
@@ -303,50 +304,20 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
         hdr->total_pillars = tile_total;
         hdr->total_listed = static_cast<uint32_t>((tile_excl + tile_sum) & 0xFFFFFFFFull);
     }
-}
 
-// ---------------------------------------------------------------------------------------------
-// K3: lists + output rows per frame
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_place(const float *__restrict__ points, int64_t n, int stride, int col0, int c_point,
-        const int32_t *__restrict__ point_slot, const uint32_t *__restrict__ point_arrival,
-        const HashEntry *__restrict__ table, const uint32_t *__restrict__ pillar_list,
-        uint32_t *__restrict__ sorted_idx, PointRecord *__restrict__ records, const uint32_t *__restrict__ frame_gstart,
-        uint32_t *__restrict__ frame_rowbase, int nb, int max_voxels, int32_t *__restrict__ pillar_count)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (i < n) {
-        const int32_t s = point_slot[i];
-        if (s >= 0) {
-            const uint4 e = *reinterpret_cast<const uint4 *>(&table[s]);  // {first, key, list base, pillar id}
-            const uint32_t g = e.w;
-            const uint32_t arrival = point_arrival[i];
-            const uint32_t pos = e.z + arrival;
-            if (sorted_idx) sorted_idx[pos] = static_cast<uint32_t>(i);
-            if (records) {
-                // one full 32-byte sector per point: the feature kernel then streams its input instead of gathering
-                const float *p = points + i * stride + col0;
-                float4 a, b;
-                a.x = __ldg(p); a.y = __ldg(p + 1); a.z = __ldg(p + 2);
-                a.w = c_point > 3 ? __ldg(p + 3) : 0.f;
-                b.x = c_point > 4 ? __ldg(p + 4) : 0.f;
-                b.y = __uint_as_float(static_cast<uint32_t>(i));
-                b.z = __uint_as_float(g);
-                b.w = __uint_as_float(arrival);
-                float4 *dst = reinterpret_cast<float4 *>(records + pos);
-                dst[0] = a;
-                dst[1] = b;
-            }
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        const int lane = threadIdx.x;
+    // The tile that finishes last turns the per-frame first-appearance counts into output rows under the max_voxels cap
+    // (every frame start has been published by then).
+    __shared__ uint32_t s_done;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_done = atomicAdd(&hdr->tiles_done, 1u);
+    __syncthreads();
+    if (s_done == n_tiles - 1 && warp == 0) {
         uint32_t carry = 0;
         for (int f0 = 0; f0 < nb; f0 += 32) {
             const int f = f0 + lane;
             uint32_t m = 0;
-            if (f < nb) m = min(frame_gstart[f + 1] - frame_gstart[f], static_cast<uint32_t>(max_voxels));
+            if (f < nb) m = min(__ldcg(frame_gstart + f + 1) - __ldcg(frame_gstart + f), static_cast<uint32_t>(max_voxels));
             uint32_t incl = m;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -366,6 +337,101 @@ k_place(const float *__restrict__ points, int64_t n, int stride, int col0, int c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3: lists.  For the streaming feature kernel it also resolves everything about a pillar that needs no feature
+// arithmetic: the point's coordinates relative to the pillar centre go into its record, and the thread of the point that
+// opened the pillar writes the pillar's constants (centre, row, count) plus voxel_coords / voxel_num_points / the BEV index
+// map.  This kernel waits on L2 round trips, so the extra integer work is free; in the feature kernel it was not.
+// ---------------------------------------------------------------------------------------------
+struct PlaceParams {
+    const float *points;
+    int64_t n;
+    int stride, col0, c_point;
+    const int32_t *point_slot;
+    const uint32_t *point_arrival;
+    const HashEntry *table;
+    uint32_t *sorted_idx;    // or NULL
+    PointRecord *records;    // or NULL
+    float4 *pillar_meta;
+    const uint32_t *pillar_cnt, *frame_gstart, *frame_rowbase;
+    GridDev gd;
+    int sh_cells, sh_cells_xy, sh_nx;  // log2 of the divisor when it is a power of two, else -1
+    float vsz[3], off[3];
+    int32_t *voxel_coords, *voxel_num_points, *cell_row;
+    int64_t capacity;
+};
+
+__device__ __forceinline__ uint32_t div_by(uint32_t v, uint32_t d, int sh) { return sh >= 0 ? v >> sh : v / d; }
+
+__global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ PlaceParams p)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (i >= p.n) return;
+    const int32_t s = p.point_slot[i];
+    if (s < 0) return;
+    const uint4 e = *reinterpret_cast<const uint4 *>(&p.table[s]);  // {first, key, list base, pillar id}
+    const uint32_t g = e.w;
+    const uint32_t arrival = p.point_arrival[i];
+    const uint32_t pos = e.z + arrival;
+    if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i);
+    if (!p.records) return;
+
+    const uint32_t key = e.y;
+    const uint32_t b = div_by(key, p.gd.cells, p.sh_cells);
+    const uint32_t cell = key - b * p.gd.cells;
+    const uint32_t z = div_by(cell, p.gd.cells_xy, p.sh_cells_xy);
+    const uint32_t rem = cell - z * p.gd.cells_xy;
+    const uint32_t y = div_by(rem, static_cast<uint32_t>(p.gd.g[0]), p.sh_nx);
+    const uint32_t x = rem - y * static_cast<uint32_t>(p.gd.g[0]);
+    // pillar centre: coord * voxel + offset, two roundings as in the reference (pillar_vfe.py:101-103)
+    const float cx = __fadd_rn(__fmul_rn(static_cast<float>(x), p.vsz[0]), p.off[0]);
+    const float cy = __fadd_rn(__fmul_rn(static_cast<float>(y), p.vsz[1]), p.off[1]);
+    const float cz = __fadd_rn(__fmul_rn(static_cast<float>(z), p.vsz[2]), p.off[2]);
+
+    // one full 32-byte sector per point: the feature kernel then streams its input instead of gathering
+    const float *q = p.points + i * p.stride + p.col0;
+    float4 a, c;
+    a.x = __fsub_rn(__ldg(q), cx);  // f_center (pillar_vfe.py:100-103)
+    a.y = __fsub_rn(__ldg(q + 1), cy);
+    a.z = __fsub_rn(__ldg(q + 2), cz);
+    a.w = p.c_point > 3 ? __ldg(q + 3) : 0.f;
+    c.x = p.c_point > 4 ? __ldg(q + 4) : 0.f;
+    c.y = __uint_as_float(static_cast<uint32_t>(i));
+    c.z = __uint_as_float(g);
+    c.w = __uint_as_float(arrival);
+    float4 *dst = reinterpret_cast<float4 *>(p.records + pos);
+    dst[0] = a;
+    dst[1] = c;
+
+    if (e.x == static_cast<uint32_t>(i)) {  // this point opened the pillar
+        const uint32_t n = p.pillar_cnt[g];
+        const uint32_t local = g - p.frame_gstart[b];
+        const int64_t row = static_cast<int64_t>(p.frame_rowbase[b]) + local;
+        const bool live = local < static_cast<uint32_t>(p.gd.max_voxels) && row < p.capacity;
+        const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
+        p.pillar_meta[2 * static_cast<size_t>(g)] = make_float4(cx, cy, cz, n < P ? 1.f : 0.f);
+        p.pillar_meta[2 * static_cast<size_t>(g) + 1] =
+            make_float4(__int_as_float(live ? static_cast<int32_t>(row) : -1), __uint_as_float(n), 0.f, 0.f);
+        if (live) {
+            if (p.voxel_coords)
+                *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) =
+                    make_int4(static_cast<int>(b), static_cast<int>(z), static_cast<int>(y), static_cast<int>(x));
+            if (p.voxel_num_points) p.voxel_num_points[row] = static_cast<int32_t>(min(n, P));
+            if (p.cell_row)
+                p.cell_row[static_cast<int64_t>(b) * p.gd.cells_xy + static_cast<int64_t>(y) * p.gd.g[0] + x] =
+                    static_cast<int32_t>(row);
+        }
+    }
+}
+
+int log2_exact(uint32_t v)
+{
+    if (v == 0 || (v & (v - 1)) != 0) return -1;
+    int s = 0;
+    while ((1u << s) != v) ++s;
+    return s;
+}
+
 }  // namespace
 
 cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, int nb, int32_t *offs, cudaStream_t st)
@@ -379,7 +445,7 @@ cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, i
 
 cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, int c_point,
                                 const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
-                                int32_t *pillar_count, bool want_index_lists, bool want_records, cudaStream_t st)
+                                int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras, cudaStream_t st)
 {
     cudaError_t err;
     if ((err = cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st)) != cudaSuccess) return err;
@@ -402,12 +468,40 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
     const int dynamic_ids = 1;
     k_scan_assign<<<ws.n_tiles, kThreads, 0, st>>>(n, ws.n_tiles, ws.point_slot, ws.table, ws.hdr, ws.tile_desc,
                                                    ws.tile_prefix, ws.pillar_key, ws.pillar_list, ws.pillar_cnt,
-                                                   frame_offsets, nb, ws.frame_gstart, dynamic_ids);
-    k_place<<<pb, kThreads, 0, st>>>(points, n, stride, col0, c_point, ws.point_slot, ws.point_arrival, ws.table,
-                                     ws.pillar_list, want_index_lists ? ws.sorted_idx : nullptr,
-                                     want_records ? ws.records : nullptr, ws.frame_gstart, ws.frame_rowbase, nb,
-                                     gd.max_voxels, pillar_count);
-    note_launch(3);
+                                                   frame_offsets, nb, ws.frame_gstart, dynamic_ids, gd.max_voxels,
+                                                   ws.frame_rowbase, pillar_count);
+    note_launch(2);
+    if (want_index_lists || extras.records) {
+        PlaceParams pp{};
+        pp.points = points;
+        pp.n = n;
+        pp.stride = stride;
+        pp.col0 = col0;
+        pp.c_point = c_point;
+        pp.point_slot = ws.point_slot;
+        pp.point_arrival = ws.point_arrival;
+        pp.table = ws.table;
+        pp.sorted_idx = want_index_lists ? ws.sorted_idx : nullptr;
+        pp.records = extras.records ? ws.records : nullptr;
+        pp.pillar_meta = ws.pillar_meta;
+        pp.pillar_cnt = ws.pillar_cnt;
+        pp.frame_gstart = ws.frame_gstart;
+        pp.frame_rowbase = ws.frame_rowbase;
+        pp.gd = gd;
+        pp.sh_cells = log2_exact(gd.cells);
+        pp.sh_cells_xy = log2_exact(gd.cells_xy);
+        pp.sh_nx = log2_exact(static_cast<uint32_t>(gd.g[0]));
+        for (int k = 0; k < 3; ++k) {
+            pp.vsz[k] = extras.vsz[k];
+            pp.off[k] = extras.off[k];
+        }
+        pp.voxel_coords = extras.records ? extras.voxel_coords : nullptr;
+        pp.voxel_num_points = extras.records ? extras.voxel_num_points : nullptr;
+        pp.cell_row = extras.records && extras.write_cell_row ? ws.cell_row : nullptr;
+        pp.capacity = extras.capacity;
+        k_place<<<pb, kThreads, 0, st>>>(pp);
+        note_launch();
+    }
     return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@ import torch
 from . import _native
 from ._native import NativeLibraryError, PillarsOutputs, PillarsPfn, check, make_grid
 
+FOLDED_FLOATS = 13 * 64  # PILLARS_FOLDED_FLOATS
 SCATTER_VARIANTS = {"auto": 0, "plain": 1, "bulk1d": 2, "tma2d": 3}
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -78,10 +79,9 @@ class PfnParams:
     use_absolute_xyz: bool
     with_distance: bool
     offset: Tuple[float, float, float]
-    # host copies (numpy float32): the fast kernel takes its weights as kernel parameters
-    weight_host: Optional[np.ndarray] = None
-    scale_host: Optional[np.ndarray] = None
-    shift_host: Optional[np.ndarray] = None
+    # the layer regrouped around the pillar centre for the streaming feature kernel (pillars_fold_pfn), or None when
+    # the configuration is outside what that kernel covers
+    folded: Optional[torch.Tensor] = None
 
     def native(self) -> PillarsPfn:
         p = PillarsPfn()
@@ -95,11 +95,19 @@ class PfnParams:
         p.weight = self.weight.data_ptr()
         p.scale = self.scale.data_ptr()
         p.shift = self.shift.data_ptr()
-        if self.weight_host is not None and self.scale_host is not None and self.shift_host is not None:
-            p.weight_host = self.weight_host.ctypes.data
-            p.scale_host = self.scale_host.ctypes.data
-            p.shift_host = self.shift_host.ctypes.data
+        p.folded = _ptr(self.folded)
         return p
+
+    def prepare(self) -> "PfnParams":
+        """Folds the table of the streaming feature kernel once (device side); a no-op without a device."""
+        if self.folded is None and self.weight.is_cuda and self.use_absolute_xyz and not self.with_distance \
+                and self.c_point <= 5 and self.weight.shape[0] == 64:
+            _require_device(self.weight)
+            folded = torch.empty(FOLDED_FLOATS, dtype=torch.float32, device=self.weight.device)
+            nat = self.native()
+            check(_native.load().pillars_fold_pfn(ctypes.byref(nat), folded.data_ptr(), _stream_ptr()), "pillars_fold_pfn")
+            self.folded = folded
+        return self
 
 
 def fold_pfn(weight: torch.Tensor, bn: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, float]],
@@ -119,9 +127,8 @@ def fold_pfn(weight: torch.Tensor, bn: Optional[Tuple[torch.Tensor, torch.Tensor
     # pillar_vfe.py:79-81: python floats (double), later promoted into fp32 tensor arithmetic
     off = tuple(float(voxel_size[i]) / 2 + float(point_cloud_range[i]) for i in range(3))
     sc32, sh32 = sc.to(torch.float32).contiguous(), sh.to(torch.float32).contiguous()
-    return PfnParams(w, sc32.to(device), sh32.to(device), int(c_point), bool(use_absolute_xyz), bool(with_distance), off,
-                     weight_host=np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32),
-                     scale_host=np.ascontiguousarray(sc32.cpu().numpy()), shift_host=np.ascontiguousarray(sh32.cpu().numpy()))
+    return PfnParams(w, sc32.to(device), sh32.to(device), int(c_point), bool(use_absolute_xyz), bool(with_distance),
+                     off).prepare()
 
 
 def frame_offsets_from_points(points_b: torch.Tensor, batch_size: int) -> torch.Tensor:

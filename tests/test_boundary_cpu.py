@@ -39,7 +39,7 @@ def test_struct_layouts_match_header_sizes():
     from lidar_vision_vqa_b200 import _native
 
     assert ctypes.sizeof(_native.PillarsGrid) == 6 * 4 + 3 * 4 + 3 * 4 + 4 + 4
-    assert ctypes.sizeof(_native.PillarsPfn) == 5 * 4 + 3 * 4 + 6 * 8
+    assert ctypes.sizeof(_native.PillarsPfn) == 5 * 4 + 3 * 4 + 4 * 8
     assert ctypes.sizeof(_native.PillarsOutputs) == 9 * 8
 
 
