@@ -39,8 +39,8 @@ struct Header {
 // One point, moved next to the other points of its pillar (32 B = one DRAM sector).
 struct __align__(32) PointRecord {
     float x, y, z, intensity, time;  // x,y,z RELATIVE TO THE PILLAR CENTRE (pillar_vfe.py:100-103); missing channels are 0
+    uint32_t flags;                  // 0; walk control in the feature kernel's staged copy
     uint32_t idx;                    // index of the point in the input batch
-    uint32_t gid;                    // pillar id (first-appearance order, batch-global, uncapped)
     uint32_t arrival;                // position inside the pillar's list; 0 marks the start of a list
 };
 
@@ -67,7 +67,7 @@ struct Workspace {
     uint32_t *pillar_cnt;           // [n] points that fell into pillar g (uncapped)
     uint32_t *sorted_idx;           // [n] point indices grouped by pillar
     PointRecord *records;           // [n] point records grouped by pillar
-    float4 *pillar_meta;            // [2n] per pillar g: {centre x,y,z, 1.0 if n < P} {row (int bits, -1: dropped), n (uint bits), -, -}
+    float4 *pillar_meta;            // [2n] per pillar, at its list start position: {centre x,y,z, 1.0 if n < P} {row (int bits, -1: dropped), n (uint bits), -, -}
     float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
     uint32_t cap;                   // hash slots
     uint32_t n_tiles;

@@ -113,132 +113,125 @@ __device__ __forceinline__ void point_step(const LaneWeights &w, const float4 a,
     acc.y = fmaxf(acc.y, y.y);
 }
 
-template <int kFT>
-__global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_stream(const __grid_constant__ StreamParams p)
+// One warp = 32 consecutive list positions (+ a 32-position look-ahead), nothing shared between warps: no CTA barrier, a
+// warp that is done leaves.  kWarps warps per CTA only share the launch.
+template <int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, 2048 / (32 * kWarps) > 32 ? 32 : 2048 / (32 * kWarps) / 2)
+k_pillar_features_stream(const __grid_constant__ StreamParams p)
 {
-    constexpr int kStage = kFT + kLook;
-    // One 32-byte slot per staged list position, holding the point ("pt" half) and, when the position is a list start, the
-    // constants of the pillar that starts there ("pl" half, kPl float4 further on): the walking warp addresses both from
-    // one running shared-memory address.
+    constexpr int kOwn = 32;
+    constexpr int kStage = kOwn + kLook;
+    // Per warp, one 32-byte slot per staged list position for the point ("pt") and one per own position for the pillar that
+    // starts there ("pl"); the walk addresses both from one running shared-memory address.
     //   pt[2j]   = x, y, z (relative to the pillar centre), intensity ;  x = NaN: point beyond the first-P cap
-    //   pt[2j+1] = time, flags (int bits), -, -
+    //   pt[2j+1] = time, flags (int bits), point index, position inside the pillar's list
     //   pl[2j]   = centre x,y,z ; w = 1.0 when the pillar has empty (padded) slots
     //   pl[2j+1] = mean - centre x,y,z ; w = output row as int bits (-1: pillar not emitted)
-    constexpr int kPl = 2 * (kStage + 1);
-    __shared__ float4 s_slot[kPl + 2 * kFT];
-    float4 *const s_pt = s_slot;
-    float4 *const s_pl = s_slot + kPl;
-    __shared__ uint32_t s_thr[kFT];  // largest kept point index (0xFFFFFFFF: keep all)
-    __shared__ uint32_t s_cnt[kFT];
-    __shared__ uint16_t s_big[kFT];
-    __shared__ int s_nbig, s_more;
+    constexpr int kPl = 2 * (kStage + 1);       // float4 offset of the pl half
+    constexpr int kSlot = kPl + 2 * kOwn;       // float4 per warp
+    __shared__ float4 s_all[kWarps * kSlot];
+    __shared__ uint32_t s_thr_all[kWarps * kOwn];  // largest kept point index of the pillar starting there
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t total = p.hdr->total_listed;
-    const uint32_t q0 = blockIdx.x * kFT;
+    const uint32_t q0 = (blockIdx.x * kWarps + warp) * kOwn;
     if (q0 >= total) return;
+    float4 *const s_pt = s_all + warp * kSlot;
+    float4 *const s_pl = s_pt + kPl;
+    uint32_t *const s_thr = s_thr_all + warp * kOwn;
     const float qnan = __int_as_float(0x7fc00000);
 
-    // ---- phase 1a: stage the chunk (+ look-ahead) -------------------------------------------------------------------------
-    const uint32_t pos = q0 + tid;
-    const bool in = pos < total;
+    // ---- phase 1a: stage 64 records ---------------------------------------------------------------------------------------
+    const uint32_t pos = q0 + lane;
     float4 ra = make_float4(qnan, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, __uint_as_float(1u));
-    if (in) {
+    float4 ta = ra, tb = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
+    if (pos < total) {
         const float4 *src = reinterpret_cast<const float4 *>(p.records + pos);
         ra = __ldg(src);
         rb = __ldg(src + 1);
     }
-    const uint32_t r_idx = __float_as_uint(rb.y), r_gid = __float_as_uint(rb.z), r_arr = __float_as_uint(rb.w);
-    const bool is_start = in && r_arr == 0u;
+    if (pos + kOwn < total) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.records + pos + kOwn);
+        ta = __ldg(src);
+        tb = __ldg(src + 1);
+    }
+    const uint32_t r_arr = __float_as_uint(rb.w);
+    const bool is_start = r_arr == 0u;  // positions beyond the list carry arrival 1
+    const unsigned bal = __ballot_sync(kFull, is_start);
+    if (bal == 0u) return;  // every position belongs to a pillar that started in an earlier chunk
     float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
-    if (is_start) {  // in flight across the barrier
-        m0 = __ldg(p.pillar_meta + 2 * static_cast<size_t>(r_gid));
-        m1 = __ldg(p.pillar_meta + 2 * static_cast<size_t>(r_gid) + 1);
+    if (is_start) {
+        m0 = __ldg(p.pillar_meta + 2 * static_cast<size_t>(pos));
+        m1 = __ldg(p.pillar_meta + 2 * static_cast<size_t>(pos) + 1);
     }
-    uint32_t t_idx = 0, t_arr = 0xFFFFFFFFu;
-    if (tid < kLook) {
-        const uint32_t tpos = q0 + kFT + tid;
-        float4 ta = make_float4(qnan, 0.f, 0.f, 0.f), tb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tpos < total) {
-            const float4 *src = reinterpret_cast<const float4 *>(p.records + tpos);
-            ta = __ldg(src);
-            tb = __ldg(src + 1);
-            t_idx = __float_as_uint(tb.y);
-            t_arr = __float_as_uint(tb.w);
-        }
-        s_pt[2 * (kFT + tid)] = ta;
-        s_pt[2 * (kFT + tid) + 1] = make_float4(tb.x, 0.f, 0.f, 0.f);
-    }
-    s_pt[2 * tid] = ra;
-    s_pt[2 * tid + 1] = make_float4(rb.x, 0.f, 0.f, 0.f);
-    if (tid == 0) {
-        s_nbig = 0;
-        s_more = 0;
+    s_pt[2 * lane] = ra;
+    s_pt[2 * lane + 1] = rb;
+    s_pt[2 * (kOwn + lane)] = ta;
+    s_pt[2 * (kOwn + lane) + 1] = tb;
+    if (lane == 0) {
         s_pt[2 * kStage] = make_float4(qnan, 0.f, 0.f, 0.f);
         s_pt[2 * kStage + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const unsigned bal = __ballot_sync(kFull, is_start);
-    if (!__syncthreads_or(is_start ? 1 : 0)) return;  // every position belongs to a pillar owned by an earlier CTA
+    __syncwarp();
 
-    // ---- phase 1b: the thread sitting on a list start publishes the pillar's constants and marks its final point ----------
+    // ---- phase 1b: the lane sitting on a list start publishes the pillar's constants and marks its final point -------------
     const uint32_t P = static_cast<uint32_t>(p.max_points);
+    const uint32_t n = __float_as_uint(m1.y);
+    const bool live = is_start && __float_as_int(m1.x) >= 0;
+    const bool big = live && n > P;
+    int more = 0;  // points of the warp's last pillar beyond the staged positions
     if (is_start) {
-        const uint32_t n = __float_as_uint(m1.y);
-        const bool live = __float_as_int(m1.x) >= 0;
         float4 m4 = make_float4(0.f, 0.f, 0.f, m1.x);
-        s_thr[tid] = 0xFFFFFFFFu;
-        if (live) {
-            if (n > P) {
-                s_cnt[tid] = n;
-                s_big[atomicAdd(&s_nbig, 1)] = static_cast<uint16_t>(tid);
-            } else {
-                // mean of the pillar's points (pillar_vfe.py:97); double: the sum does not depend on the list order
-                double sx = 0.0, sy = 0.0, sz = 0.0;
-                const uint32_t n_in = min(n, static_cast<uint32_t>(kStage - tid));
-                for (uint32_t j = 0; j < n_in; ++j) {
-                    const float4 q = s_pt[2 * (tid + j)];
-                    sx += static_cast<double>(q.x);
-                    sy += static_cast<double>(q.y);
-                    sz += static_cast<double>(q.z);
-                }
-                for (uint32_t j = n_in; j < n; ++j) {  // P > 32 only
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + pos + j));
-                    sx += static_cast<double>(q.x);
-                    sy += static_cast<double>(q.y);
-                    sz += static_cast<double>(q.z);
-                }
-                // the reference rounds the ABSOLUTE mean to fp32 before subtracting it; reproduce that rounding step
-                const float rn = __frcp_rn(static_cast<float>(n));
-                m4.x = __fsub_rn(__fadd_rn(m0.x, static_cast<float>(sx) * rn), m0.x);
-                m4.y = __fsub_rn(__fadd_rn(m0.y, static_cast<float>(sy) * rn), m0.y);
-                m4.z = __fsub_rn(__fadd_rn(m0.z, static_cast<float>(sz) * rn), m0.z);
+        s_thr[lane] = 0xFFFFFFFFu;
+        if (live && !big) {
+            // mean of the pillar's points (pillar_vfe.py:97); double: the sum does not depend on the list order
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            const uint32_t n_in = min(n, static_cast<uint32_t>(kStage - lane));
+            for (uint32_t j = 0; j < n_in; ++j) {
+                const float4 q = s_pt[2 * (lane + j)];
+                sx += static_cast<double>(q.x);
+                sy += static_cast<double>(q.y);
+                sz += static_cast<double>(q.z);
             }
+            for (uint32_t j = n_in; j < n; ++j) {  // P > 32 only
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + pos + j));
+                sx += static_cast<double>(q.x);
+                sy += static_cast<double>(q.y);
+                sz += static_cast<double>(q.z);
+            }
+            // the reference rounds the ABSOLUTE mean to fp32 before subtracting it; reproduce that rounding step
+            const float rn = __frcp_rn(static_cast<float>(n));
+            m4.x = __fsub_rn(__fadd_rn(m0.x, static_cast<float>(sx) * rn), m0.x);
+            m4.y = __fsub_rn(__fadd_rn(m0.y, static_cast<float>(sy) * rn), m0.y);
+            m4.z = __fsub_rn(__fadd_rn(m0.z, static_cast<float>(sz) * rn), m0.z);
         }
-        s_pl[2 * tid] = m0;
-        s_pl[2 * tid + 1] = m4;
+        s_pl[2 * lane] = m0;
+        s_pl[2 * lane + 1] = m4;
         // walk control: flag the pillar's final point (dropped pillars are walked too, their row is -1)
-        const uint32_t endp = static_cast<uint32_t>(tid) + n - 1u;
+        const uint32_t endp = static_cast<uint32_t>(lane) + n - 1u;
         const bool last_of_warp = (31 - __clz(bal)) == lane;
         if (endp < static_cast<uint32_t>(kStage)) {
             s_pt[2 * endp + 1].y = __int_as_float(last_of_warp ? kFlagStop : kFlagLast);
-        } else {  // only the CTA's last pillar can run past the look-ahead
+        } else {  // only the warp's last pillar can run past the look-ahead
             s_pt[2 * (kStage - 1) + 1].y = __int_as_float(kFlagStop | kFlagMore);
-            s_more = static_cast<int>(endp + 1u - kStage);
+            more = static_cast<int>(endp + 1u - kStage);
         }
     }
-    __syncthreads();
+    more = __shfl_sync(kFull, more, 31 - __clz(bal));
+    __syncwarp();
 
     // ---- pillars over the cap: threshold = P-th smallest point index (radix select), mean over the kept ones ---------
-    const int nbig = s_nbig;
-    if (nbig) {
-        for (int k = warp; k < nbig; k += kFT / 32) {
-            const int bp = s_big[k];
-            const uint32_t p0 = q0 + bp, n = s_cnt[bp];
+    unsigned bigmask = __ballot_sync(kFull, big);
+    if (bigmask) {
+        while (bigmask) {
+            const int bp = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const uint32_t p0 = q0 + bp, nb = __shfl_sync(kFull, n, bp);
             uint32_t prefix = 0, kk = P;
             for (int bit = p.idx_bits - 1; bit >= 0; --bit) {
                 const uint32_t himask = 0xFFFFFFFFu << (bit + 1);
                 uint32_t c0 = 0;
-                for (uint32_t j = lane; j < n; j += 32) {
+                for (uint32_t j = lane; j < nb; j += 32) {
                     const uint32_t v = __ldg(&p.records[p0 + j].idx);
                     c0 += ((v & himask) == prefix && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
                 }
@@ -250,7 +243,7 @@ __global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_stream(cons
                 }
             }
             double sx = 0.0, sy = 0.0, sz = 0.0;
-            for (uint32_t j = lane; j < n; j += 32) {
+            for (uint32_t j = lane; j < nb; j += 32) {
                 const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + p0 + j));
                 if (__ldg(&p.records[p0 + j].idx) <= prefix) {
                     sx += static_cast<double>(q.x);
@@ -273,17 +266,18 @@ __global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_stream(cons
                 s_pl[2 * bp + 1].z = __fsub_rn(__fadd_rn(c4.z, static_cast<float>(sz) * rn), c4.z);
             }
         }
-        __syncthreads();
+        __syncwarp();
         // points beyond the cap become NaN: fmaxf ignores them, so the walk needs no branch
-        if (in && r_arr <= static_cast<uint32_t>(tid) && r_idx > s_thr[tid - static_cast<int>(r_arr)]) s_pt[2 * tid].x = qnan;
-        if (tid < kLook) {
-            const int j = kFT + tid;
+        if (r_arr <= static_cast<uint32_t>(lane) && __float_as_uint(rb.z) > s_thr[lane - static_cast<int>(r_arr)])
+            s_pt[2 * lane].x = qnan;
+        {
+            const uint32_t t_arr = __float_as_uint(tb.w);
+            const int j = kOwn + lane;
             const int ps = j - static_cast<int>(t_arr);
-            if (t_arr <= static_cast<uint32_t>(j) && ps < kFT && t_idx > s_thr[ps]) s_pt[2 * j].x = qnan;
+            if (t_arr <= static_cast<uint32_t>(j) && ps < kOwn && __float_as_uint(tb.z) > s_thr[ps]) s_pt[2 * j].x = qnan;
         }
-        __syncthreads();
+        __syncwarp();
     }
-    if (bal == 0u) return;  // no list starts among this warp's positions
 
     // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair -------------------------
     LaneWeights w;
@@ -299,8 +293,8 @@ __global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_stream(cons
     unsigned long long out_lane = static_cast<unsigned long long>(__cvta_generic_to_global(p.pillar_features + 2 * lane));
     asm volatile("" : "+l"(out_lane));
     constexpr uint32_t kPlBytes = kPl * sizeof(float4);
-    const int j0 = warp * 32 + __ffs(bal) - 1;
-    uint32_t sp = static_cast<uint32_t>(__cvta_generic_to_shared(s_pt)) + 32u * j0;  // the point being accumulated
+    const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pt));
+    uint32_t sp = s_base + 32u * (__ffs(bal) - 1);  // the point being accumulated
     uint32_t ss = sp;  // first point of the pillar being accumulated; its constants sit kPlBytes further on
     float2 acc = make_float2(-INFINITY, -INFINITY);
 
@@ -311,10 +305,10 @@ __global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_stream(cons
         float2 kc = fma2s(w.k0, c4.x, w.sh);
         kc = fma2s(w.k1, c4.y, kc);
         kc = fma2s(w.k2, c4.z, kc);
-        kc = fma2s(w.k3, m4.x, kc);
-        kc = fma2s(w.k4, m4.y, kc);
-        kc = fma2s(w.k5, m4.z, kc);
-        const float2 v = add2(acc, kc);
+        float2 kd = mul2s(w.k3, m4.x);
+        kd = fma2s(w.k4, m4.y, kd);
+        kd = fma2s(w.k5, m4.z, kd);
+        const float2 v = add2(add2(acc, kc), kd);
         const float2 fl2 = mul2s(w.rsh, c4.w);  // relu(shift) when the pillar has padded slots, else 0
         if (row >= 0)
             asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
@@ -350,19 +344,17 @@ __global__ void __launch_bounds__(kFT, 1024 / kFT) k_pillar_features_stream(cons
     }
     if (fl & kFlagMore) {
         // rest of a long list, straight from global memory: 32 records per sweep, broadcast by shuffles
-        const int js = static_cast<int>((ss - static_cast<uint32_t>(__cvta_generic_to_shared(s_pt))) >> 5);
-        const int rem = s_more;
         const uint32_t base = q0 + kStage;
-        const uint32_t thr = s_thr[js];
-        for (int k0 = 0; k0 < rem; k0 += 32) {
-            const int cnt = min(32, rem - k0);
+        const uint32_t thr = s_thr[(ss - s_base) >> 5];
+        for (int k0 = 0; k0 < more; k0 += 32) {
+            const int cnt = min(32, more - k0);
             float4 qa = make_float4(qnan, 0.f, 0.f, 0.f);
             float qt = 0.f;
             if (lane < cnt) {
                 const float4 *src = reinterpret_cast<const float4 *>(p.records + base + k0 + lane);
                 const float4 u = __ldg(src), v = __ldg(src + 1);
                 qa = u;
-                if (__float_as_uint(v.y) > thr) qa.x = qnan;
+                if (__float_as_uint(v.z) > thr) qa.x = qnan;
                 qt = v.x;
             }
             for (int l = 0; l < cnt; ++l) {
@@ -421,13 +413,14 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     static int ft = 0;
     if (!ft) {
         const char *e = getenv("PILLARS_FEAT_THREADS");
-        ft = e ? atoi(e) : 256;
-        if (ft != 64 && ft != 128 && ft != 256) ft = 256;
+        ft = e ? atoi(e) : 128;
+        if (ft != 64 && ft != 128 && ft != 256) ft = 128;
     }
-    const unsigned grid = static_cast<unsigned>((job.n + ft - 1) / ft);  // upper bound: listed points <= n
-    if (ft == 256) k_pillar_features_stream<256><<<grid, 256, 0, st>>>(p);
-    else if (ft == 128) k_pillar_features_stream<128><<<grid, 128, 0, st>>>(p);
-    else k_pillar_features_stream<64><<<grid, 64, 0, st>>>(p);
+    const int64_t chunks = (job.n + 31) / 32;  // upper bound: listed points <= n
+    const unsigned grid = static_cast<unsigned>((chunks * 32 + ft - 1) / ft);
+    if (ft == 256) k_pillar_features_stream<8><<<grid, 256, 0, st>>>(p);
+    else if (ft == 128) k_pillar_features_stream<4><<<grid, 128, 0, st>>>(p);
+    else k_pillar_features_stream<2><<<grid, 64, 0, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }

@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ Plac
     a.z = __fsub_rn(__ldg(q + 2), cz);
     a.w = p.c_point > 3 ? __ldg(q + 3) : 0.f;
     c.x = p.c_point > 4 ? __ldg(q + 4) : 0.f;
-    c.y = __uint_as_float(static_cast<uint32_t>(i));
-    c.z = __uint_as_float(g);
+    c.y = 0.f;  // walk-control flags, set by the feature kernel in its staged copy
+    c.z = __uint_as_float(static_cast<uint32_t>(i));
     c.w = __uint_as_float(arrival);
     float4 *dst = reinterpret_cast<float4 *>(p.records + pos);
     dst[0] = a;
@@ -409,8 +409,9 @@ __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ Plac
         const int64_t row = static_cast<int64_t>(p.frame_rowbase[b]) + local;
         const bool live = local < static_cast<uint32_t>(p.gd.max_voxels) && row < p.capacity;
         const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
-        p.pillar_meta[2 * static_cast<size_t>(g)] = make_float4(cx, cy, cz, n < P ? 1.f : 0.f);
-        p.pillar_meta[2 * static_cast<size_t>(g) + 1] =
+        // indexed by the list START POSITION, so the consumer needs nothing but its own position to find it
+        p.pillar_meta[2 * static_cast<size_t>(e.z)] = make_float4(cx, cy, cz, n < P ? 1.f : 0.f);
+        p.pillar_meta[2 * static_cast<size_t>(e.z) + 1] =
             make_float4(__int_as_float(live ? static_cast<int32_t>(row) : -1), __uint_as_float(n), 0.f, 0.f);
         if (live) {
             if (p.voxel_coords)
