@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "bulk1d", "tma2d"])
+    ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "bulk1d", "tma2d", "wide", "persist", "patch"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through the timed loop")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the timed steps are pipelined over (independent batches overlap)")
@@ -360,7 +360,7 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     ab = algorithmic_bytes(n_raw, n_kept, m_avg, 5, F_OUT, nx, ny, nb)
     scat_gbs = ab["S"] / (stage_avg[2] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "BEV scatter kernel (k_scatter_plain; dominant kernel of the step)",
+    roofline = {"bound": "hbm", "kernel": "BEV scatter kernel (k_scatter_wide; dominant kernel of the step)",
                 "achieved": scat_gbs, "peak": peak, "unit": "GB/s", "frac": scat_gbs / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["S"],
                 "avg_launch_ms": float(stage_avg[2]), "share_of_step": float(stage_avg[2] / serial_ms_per_step),

@@ -131,6 +131,218 @@ k_scatter_plain(const float *__restrict__ feats, const int32_t *__restrict__ cel
     }
 }
 
+// ---- variant 4 ----------------------------------------------------------------------------------
+// Same warp-autonomous scheme with 256-bit accesses (sm_100: LDG.256 / STG.256): a lane owns 8 consecutive cells, a warp
+// 256 cells x all channels = 64 KB of the canvas, and every store instruction of the warp writes 1 KB contiguous.  Half the
+// LSU instructions of variant 1 for the same bytes.
+__device__ __forceinline__ void stg256(float *p, float a, float b, float c, float d, float e, float f, float g, float h)
+{
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+                 "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
+__device__ __forceinline__ void stg256_cs(float *p, float a, float b, float c, float d, float e, float f, float g, float h)
+{
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d),
+                 "f"(e), "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
+
+// Work split: a CTA owns blockDim.x * 8 consecutive cells x `chan_per_cta` channels (a multiple of 8).  With 8 channels per
+// CTA the canvas is written as few long sequential streams (measured with profiles/micro/fill_patterns.cu on B200: 64
+// channel-strided streams per thread 164 us for the 1 GiB canvas, 8 channels x 8 KB runs per CTA 149 us, linear fill 146 us);
+// the CTAs of one cell tile then each read one 32-byte sector of every pillar row, so no feature byte is fetched twice.
+// tile_major != 0: consecutive CTAs are the channel groups of one cell tile (index map and feature rows are shared by CTAs
+// that run together); 0: consecutive CTAs walk the plane for one channel group.
+template <bool CS, int CPP>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_wide(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
+               int tiles_per_plane, int chan_per_cta, int tile_major, float *__restrict__ bev)
+{
+    const int groups = f / chan_per_cta;
+    int b, tile, cg;
+    if (tile_major) {
+        cg = blockIdx.x % groups;
+        tile = (blockIdx.x / groups) % tiles_per_plane;
+        b = blockIdx.x / (groups * tiles_per_plane);
+    } else {
+        tile = blockIdx.x % tiles_per_plane;
+        cg = (blockIdx.x / tiles_per_plane) % groups;
+        b = blockIdx.x / (groups * tiles_per_plane);
+    }
+    const int64_t cell0 = static_cast<int64_t>(tile) * (blockDim.x * 8) + threadIdx.x * 8;
+    const bool inb = cell0 < plane;  // plane % 8 == 0: a lane is entirely inside or outside
+    int32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = -1;
+    if (inb) {
+        const int4 *src = reinterpret_cast<const int4 *>(cell_row + b * plane + cell0);
+        const int4 v = __ldg(src), w = __ldg(src + 1);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        r[4] = w.x; r[5] = w.y; r[6] = w.z; r[7] = w.w;
+    }
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) any |= r[k] >= 0;
+    const int c_begin = cg * chan_per_cta, c_end = c_begin + chan_per_cta;
+    float *dst = bev + (static_cast<int64_t>(b) * f) * plane + cell0;
+    auto store = [&](float *p, float a, float b2, float c, float d, float e, float f2, float g, float h) {
+        if (CS) stg256_cs(p, a, b2, c, d, e, f2, g, h);
+        else stg256(p, a, b2, c, d, e, f2, g, h);
+    };
+    if (!__any_sync(0xffffffffu, any)) {
+        if (inb) {
+#pragma unroll 8
+            for (int c = c_begin; c < c_end; ++c) store(dst + c * plane, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    if (!inb) return;
+    constexpr int kV = CPP / 4;  // 16-byte loads per row and pass
+    for (int c0 = c_begin; c0 < c_end; c0 += CPP) {
+        float4 v[8][kV];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int q = 0; q < kV; ++q) v[k][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r[k] >= 0) {
+                const float4 *row = reinterpret_cast<const float4 *>(feats + static_cast<int64_t>(r[k]) * f + c0);
+#pragma unroll
+                for (int q = 0; q < kV; ++q) v[k][q] = __ldg(row + q);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kV; ++q) {
+            float *d = dst + (c0 + 4 * q) * plane;
+            store(d, v[0][q].x, v[1][q].x, v[2][q].x, v[3][q].x, v[4][q].x, v[5][q].x, v[6][q].x, v[7][q].x);
+            store(d + plane, v[0][q].y, v[1][q].y, v[2][q].y, v[3][q].y, v[4][q].y, v[5][q].y, v[6][q].y, v[7][q].y);
+            store(d + 2 * plane, v[0][q].z, v[1][q].z, v[2][q].z, v[3][q].z, v[4][q].z, v[5][q].z, v[6][q].z, v[7][q].z);
+            store(d + 3 * plane, v[0][q].w, v[1][q].w, v[2][q].w, v[3][q].w, v[4][q].w, v[5][q].w, v[6][q].w, v[7][q].w);
+        }
+    }
+}
+
+// ---- variant 5 ----------------------------------------------------------------------------------
+// Persistent warps over (frame, channel group of 8, 256-cell tile) items, tile fastest.  Per item a warp writes 8 channels x
+// 1 KB; the warps of one sweep over the item list cover consecutive tiles, so HBM sees a few long sequential write streams.
+// Two latencies are taken off the store path:
+//   * the index-map entry of the warp's NEXT item is loaded before the current item is stored;
+//   * lanes whose 8 cells are all empty (two thirds of them even in populated areas) store their zeros at once, without
+//     waiting for the feature rows the other lanes of the warp gather.
+__device__ __forceinline__ void ldg256_stream(const float *p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+template <bool CS>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_persist(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
+                  int tiles_per_plane, int64_t n_items, float *__restrict__ bev)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int groups = f >> 3;
+    const int per_frame = groups * tiles_per_plane;
+
+    auto load_index = [&](int64_t it, int4 &lo, int4 &hi) {
+        lo = hi = make_int4(-1, -1, -1, -1);
+        if (it < n_items) {
+            const int b = static_cast<int>(it / per_frame);
+            const int tile = static_cast<int>(it % tiles_per_plane);
+            const int64_t cell0 = static_cast<int64_t>(tile) * 256 + lane * 8;
+            if (cell0 < plane) {
+                const int4 *src = reinterpret_cast<const int4 *>(cell_row + b * plane + cell0);
+                lo = __ldg(src);
+                hi = __ldg(src + 1);
+            }
+        }
+    };
+    auto store = [&](float *p, float a, float b2, float c, float d, float e, float f2, float g, float h) {
+        if (CS) stg256_cs(p, a, b2, c, d, e, f2, g, h);
+        else stg256(p, a, b2, c, d, e, f2, g, h);
+    };
+
+    int4 lo, hi;
+    load_index(item, lo, hi);
+    while (item < n_items) {
+        int4 nlo, nhi;
+        load_index(item + n_warps, nlo, nhi);
+
+        const int b = static_cast<int>(item / per_frame);
+        const int rem = static_cast<int>(item - static_cast<int64_t>(b) * per_frame);
+        const int cg = rem / tiles_per_plane;
+        const int tile = rem - cg * tiles_per_plane;
+        const int64_t cell0 = static_cast<int64_t>(tile) * 256 + lane * 8;
+        const int c0 = cg * 8;
+        float *dst = bev + (static_cast<int64_t>(b) * f + c0) * plane + cell0;
+        if (cell0 < plane) {
+            const int32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            bool occ = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) occ |= r[k] >= 0;
+            if (!occ) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) store(dst + c * plane, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+            } else {
+                float v[8][8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[k][c] = 0.f;
+                    if (r[k] >= 0) ldg256_stream(feats + static_cast<int64_t>(r[k]) * f + c0, v[k]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    store(dst + c * plane, v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]);
+            }
+        }
+        lo = nlo;
+        hi = nhi;
+        item += n_warps;
+    }
+}
+
+// ---- variant 6 ----------------------------------------------------------------------------------
+// Zero stream first, patch second.  Same work split as variant 4 (CTA = blockDim.x * 8 cells x 8 channels, plane-major), but a
+// lane stores its 8 x 32 bytes of zeros as soon as its index-map entry has arrived and only then fetches the 32-byte
+// feature sector of each occupied cell (5 % of the cells) and overwrites those elements with 4-byte stores, which merge
+// into the lines the lane has just written while they are still dirty in L2.  The bulk write stream therefore never waits
+// for the gather, and since no canvas data is held in registers the SM keeps three times as many warps in flight.
+template <bool CS>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_patch(const float *__restrict__ feats, const int32_t *__restrict__ cell_row, int f, int64_t plane,
+                int tiles_per_plane, float *__restrict__ bev)
+{
+    const int groups = f >> 3;
+    const int tile = blockIdx.x % tiles_per_plane;
+    const int cg = (blockIdx.x / tiles_per_plane) % groups;
+    const int b = blockIdx.x / (groups * tiles_per_plane);
+    const int64_t cell0 = static_cast<int64_t>(tile) * (blockDim.x * 8) + threadIdx.x * 8;
+    if (cell0 >= plane) return;
+    const int4 *src = reinterpret_cast<const int4 *>(cell_row + b * plane + cell0);
+    const int4 lo = __ldg(src), hi = __ldg(src + 1);
+    const int c0 = cg * 8;
+    float *dst = bev + (static_cast<int64_t>(b) * f + c0) * plane + cell0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (CS) stg256_cs(dst + c * plane, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+        else stg256(dst + c * plane, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+    }
+    const int32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (r[k] >= 0) {
+            float v[8];
+            ldg256_stream(feats + static_cast<int64_t>(r[k]) * f + c0, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c * plane + k] = v[c];
+        }
+    }
+}
+
 // ---- async-proxy helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -315,9 +527,77 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
                         (reinterpret_cast<uintptr_t>(feats) % 16 == 0) && (f % 8 == 0);
     const size_t smem = sizeof(float) * 2 * f * 128;
     const bool async_ok = vec_ok && f <= kThreads && f % 8 == 0 && smem <= 200 * 1024;
-    if (variant == 0) variant = 1;  // measured on B200: direct stores 205 us, TMA tile stores 268 us (profiles/r01_scatter_variants.md)
+    const bool wide_ok = vec_ok && (plane % 8 == 0) && (reinterpret_cast<uintptr_t>(bev) % 32 == 0);
+    // measured on B200, cfg2 (profiles/r01_scatter_variants.md): channel-group 256-bit stores 172 us, direct stores with all
+    // channels per warp 203 us, TMA tile stores 268 us
+    if (variant == 0) variant = wide_ok ? 4 : 1;
     if ((variant == 2 || variant == 3) && !async_ok) variant = 1;
     if (variant == 3 && !get_encode_fn()) variant = 2;
+    if (variant == 4 && !wide_ok) variant = 1;
+
+    if (variant == 5 && !(wide_ok && f % 8 == 0)) variant = 1;
+    if (variant == 5) {
+        static int cs = -1, bs = 0, per_sm = 0;
+        if (cs < 0) {
+            const char *e1 = getenv("PILLARS_SCATTER_PERSIST_CS"), *e2 = getenv("PILLARS_SCATTER_PERSIST_BLOCK"),
+                       *e3 = getenv("PILLARS_SCATTER_PERSIST_CTAS");
+            cs = e1 ? atoi(e1) : 0;
+            bs = e2 ? atoi(e2) : 128;
+            per_sm = e3 ? atoi(e3) : 4;
+            if (bs != 32 && bs != 64 && bs != 128 && bs != 256) bs = 128;
+            if (per_sm < 1 || per_sm > 32) per_sm = 4;
+        }
+        const int tpp = static_cast<int>((plane + 255) / 256);
+        const int64_t n_items = static_cast<int64_t>(nb) * (f / 8) * tpp;
+        const int64_t ctas_needed = (n_items * 32 + bs - 1) / bs;
+        const unsigned grid = static_cast<unsigned>(tmin<int64_t>(ctas_needed, static_cast<int64_t>(sm_count()) * per_sm));
+        if (cs) k_scatter_persist<true><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, n_items, bev);
+        else k_scatter_persist<false><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, n_items, bev);
+        note_launch();
+        return cudaGetLastError();
+    }
+    if (variant == 6 && !(wide_ok && f % 8 == 0)) variant = 1;
+    if (variant == 6) {
+        static int cs = -1, bs = 0;
+        if (cs < 0) {
+            const char *e1 = getenv("PILLARS_SCATTER_PATCH_CS"), *e2 = getenv("PILLARS_SCATTER_PATCH_BLOCK");
+            cs = e1 ? atoi(e1) : 0;
+            bs = e2 ? atoi(e2) : 128;
+            if (bs != 32 && bs != 64 && bs != 128 && bs != 256) bs = 128;
+        }
+        const int tpp = static_cast<int>((plane + bs * 8 - 1) / (bs * 8));
+        const unsigned grid = static_cast<unsigned>(nb) * tpp * (f / 8);
+        if (cs) k_scatter_patch<true><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+        else k_scatter_patch<false><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, bev);
+        note_launch();
+        return cudaGetLastError();
+    }
+    if (variant == 4) {
+        static int cs = -1, bs = 0, cpc = 0, tile_major = 0;
+        if (cs < 0) {
+            const char *e1 = getenv("PILLARS_SCATTER_WIDE_CS"), *e2 = getenv("PILLARS_SCATTER_WIDE_BLOCK"),
+                       *e3 = getenv("PILLARS_SCATTER_WIDE_CHAN"), *e4 = getenv("PILLARS_SCATTER_WIDE_TILEMAJOR");
+            cs = e1 ? atoi(e1) : 0;
+            bs = e2 ? atoi(e2) : 128;
+            cpc = e3 ? atoi(e3) : 8;
+            tile_major = e4 ? atoi(e4) : 0;
+            if (bs != 32 && bs != 64 && bs != 128 && bs != 256) bs = 128;
+        }
+        int chan = (cpc >= 8 && cpc % 8 == 0 && f % cpc == 0) ? cpc : f;
+        const int tpp = static_cast<int>((plane + bs * 8 - 1) / (bs * 8));
+        const unsigned grid = static_cast<unsigned>(nb) * tpp * (f / chan);
+        static int cpp = 0;
+        if (!cpp) {
+            const char *e5 = getenv("PILLARS_SCATTER_WIDE_CPP");
+            cpp = (e5 && atoi(e5) == 4) ? 4 : 8;
+        }
+        if (cs && cpp == 8) k_scatter_wide<true, 8><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, chan, tile_major, bev);
+        else if (cs) k_scatter_wide<true, 4><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, chan, tile_major, bev);
+        else if (cpp == 8) k_scatter_wide<false, 8><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, chan, tile_major, bev);
+        else k_scatter_wide<false, 4><<<grid, bs, 0, st>>>(feats, cell_row, f, plane, tpp, chan, tile_major, bev);
+        note_launch();
+        return cudaGetLastError();
+    }
 
     if (variant == 1) {
         static int mode = -1, bs = 0;

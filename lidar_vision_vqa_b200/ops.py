@@ -14,7 +14,7 @@ from . import _native
 from ._native import NativeLibraryError, PillarsOutputs, PillarsPfn, check, make_grid
 
 FOLDED_FLOATS = 13 * 64  # PILLARS_FOLDED_FLOATS
-SCATTER_VARIANTS = {"auto": 0, "plain": 1, "bulk1d": 2, "tma2d": 3}
+SCATTER_VARIANTS = {"auto": 0, "plain": 1, "bulk1d": 2, "tma2d": 3, "wide": 4, "persist": 5, "patch": 6}
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
 _DEVICE_OK: Dict[int, bool] = {}

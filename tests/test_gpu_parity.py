@@ -200,7 +200,7 @@ def test_pillar_vfe_module_vs_reference_golden(name, dev, L):
     np.testing.assert_allclose(out, ref, rtol=TIGHT_RTOL, atol=TIGHT_ATOL)
 
 
-@pytest.mark.parametrize("variant", ["plain", "bulk1d", "tma2d", "auto"])
+@pytest.mark.parametrize("variant", ["plain", "bulk1d", "tma2d", "wide", "persist", "patch", "auto"])
 @pytest.mark.parametrize("name", [n for n in SINGLE_LAYER if n != "vfe_c5_m1"])
 def test_scatter_module_vs_reference_golden(name, variant, dev, L):
     g = load_golden(name)
@@ -334,7 +334,7 @@ def test_fused_path_c4_and_scatter_variants_agree(dev, L, oracle):
     np.testing.assert_allclose(outs["tma2d"].cpu().numpy(), ref_bev, rtol=FEAT_RTOL, atol=FEAT_ATOL)
 
 
-@pytest.mark.parametrize("variant", ["plain", "bulk1d", "tma2d", "auto"])
+@pytest.mark.parametrize("variant", ["plain", "bulk1d", "tma2d", "wide", "persist", "patch", "auto"])
 def test_scatter3d_module_vs_reference_golden(variant, dev, L):
     """PointPillarScatter3d (pointpillar_scatter.py:40-73): nz = 2, 32 channels per pillar -> [B, 64, ny, nx]."""
     g = load_golden("scatter3d_nz2")
@@ -364,7 +364,7 @@ def test_scatter_odd_shapes(dev, L, oracle):
                                  for b in range(nb)]).astype(np.int32)
         feats = r.standard_normal((m * nb, f)).astype(np.float32)
         ref = oracle.scatter_bev(feats, coords, nx, ny, batch_size=nb)
-        for variant in ("plain", "bulk1d", "tma2d", "auto"):
+        for variant in ("plain", "bulk1d", "tma2d", "wide", "persist", "patch", "auto"):
             for cd in (coords, coords.astype(np.float32)):
                 bev = L.ops.scatter_bev(torch.from_numpy(feats).to(dev), torch.from_numpy(cd).to(dev), nb, nx, ny,
                                         variant=variant)
