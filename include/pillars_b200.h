@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PILLARS_ABI_VERSION 1
+#define PILLARS_ABI_VERSION 2
 
 /* error codes (negative; positive values are cudaError_t) */
 #define PILLARS_E_BADARG (-1)      /* NULL pointer, bad size, unsupported combination */
@@ -146,6 +146,48 @@ int pillars_encode_bev(const float *points, int64_t n, int32_t row_stride, int32
                        const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
                        const pillars_pfn_t *pfn, const pillars_outputs_t *out, void *workspace,
                        size_t workspace_bytes, int32_t scatter_variant, void *stream);
+
+/* ---- general feature stacks: two-layer PFN, DynamicPillarVFE, DynamicPillarVFESimple2D ---------------------------------
+ * replaces (paths under src/lidar-encoder/pcdet/models/backbones_3d/vfe/):
+ *   pillars_pfn_dense_stack   pillar_vfe.py:94-123 with a ModuleList of two PFNLayers (:18-19,44-49,119-120)
+ *   pillars_encode_stack      mode HARD:    data_processor.py voxelisation + the same stack (any NUM_FILTERS of 1-2 entries)
+ *                             mode DYNAMIC: dynamic_pillar_vfe.py:90-142 (DynamicPillarVFE.forward, PFNLayerV2 :35-46) and
+ *                                           :193-240 (DynamicPillarVFESimple2D.forward) with layout SIMPLE2D            */
+#define PILLARS_LAYOUT_PILLAR_VFE 0 /* features = [point channels, f_cluster, f_center (, distance)]  pillar_vfe.py:105-113 */
+#define PILLARS_LAYOUT_SIMPLE2D 1   /* features = [f_center, point channels (, distance)]   dynamic_pillar_vfe.py:209-224 */
+#define PILLARS_MODE_HARD 0         /* first-appearance rows, MAX_POINTS_PER_VOXEL / MAX_NUMBER_OF_VOXELS caps, padded-slot row */
+#define PILLARS_MODE_DYNAMIC 1      /* rows by sorted key b*nx*ny + ix*ny + iy, no caps, x/y range check only */
+
+typedef struct pillars_pfn_stack {
+    int32_t n_layers;         /* 1 or 2 */
+    int32_t c_point;          /* channels of a raw point incl. xyz */
+    int32_t out_features[2];  /* out_features of each layer's linear (layer 0 of two: NUM_FILTERS[0] / 2, at most 32) */
+    int32_t use_absolute_xyz;
+    int32_t with_distance;
+    int32_t layout;           /* PILLARS_LAYOUT_* */
+    float offset[3];          /* voxel/2 + range_min per axis */
+    const float *weight[2];   /* [out, in] row-major; in of layer 1 = 2 * out_features[0] */
+    const float *scale[2];    /* folded BatchNorm (or 1) */
+    const float *shift[2];    /* folded BatchNorm (or the linear's bias) */
+} pillars_pfn_stack_t;
+
+/* in_features of layer 0 for this stack (C + 6, C + 3, ... see the layouts above), or a negative error code. */
+int pillars_pfn_stack_in_features(const pillars_pfn_stack_t *stack);
+
+/* PillarVFE.forward on padded voxels with a one- or two-layer stack; out is [m, out_features[n_layers-1]]. */
+int pillars_pfn_dense_stack(const float *voxels, const void *num_points, int32_t num_points_is_float,
+                            const void *coords, int32_t coords_is_float, int64_t m, int32_t max_points,
+                            const pillars_pfn_stack_t *stack, const float voxel_size[3], float *out, void *stream);
+
+/* Raw points -> pillar features (+ BEV in mode HARD when out->bev is set) through a feature stack.
+ * coords_cols: 4 writes out->voxel_coords as (b,z,y,x) -- (b,0,y,x) in mode DYNAMIC, dynamic_pillar_vfe.py:132-138;
+ *              3 writes (b,y,x), the `pillar_coords` of DynamicPillarVFESimple2D (:232-238).
+ * In mode DYNAMIC grid->max_points / max_voxels are ignored and out->voxel_num_points receives the uncapped counts. */
+int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int32_t col0,
+                         const int32_t *frame_offsets, int32_t n_frames, const pillars_grid_t *grid,
+                         const pillars_pfn_stack_t *stack, int32_t mode, int32_t coords_cols,
+                         const pillars_outputs_t *out, void *workspace, size_t workspace_bytes,
+                         int32_t scatter_variant, void *stream);
 
 /* Number of kernel launches (incl. memsets) the last successful compute call on this thread enqueued. */
 int pillars_last_launch_count(void);

@@ -25,7 +25,14 @@ EXPORTED_SYMBOLS = (
     "pillars_set_stage_events",
     "pillars_force_generic_features",
     "pillars_set_scatter_stream",
+    "pillars_pfn_stack_in_features",
+    "pillars_pfn_dense_stack",
+    "pillars_encode_stack",
 )
+
+ABI_VERSION = 2
+LAYOUT_PILLAR_VFE, LAYOUT_SIMPLE2D = 0, 1
+MODE_HARD, MODE_DYNAMIC = 0, 1
 
 
 class PillarsGrid(Structure):
@@ -37,6 +44,12 @@ class PillarsPfn(Structure):
     _fields_ = [("c_point", c_int32), ("c_in", c_int32), ("f_out", c_int32), ("use_absolute_xyz", c_int32),
                 ("with_distance", c_int32), ("offset", c_float * 3), ("weight", c_void_p), ("scale", c_void_p),
                 ("shift", c_void_p), ("folded", c_void_p)]
+
+
+class PillarsPfnStack(Structure):
+    _fields_ = [("n_layers", c_int32), ("c_point", c_int32), ("out_features", c_int32 * 2),
+                ("use_absolute_xyz", c_int32), ("with_distance", c_int32), ("layout", c_int32), ("offset", c_float * 3),
+                ("weight", c_void_p * 2), ("scale", c_void_p * 2), ("shift", c_void_p * 2)]
 
 
 class PillarsOutputs(Structure):
@@ -90,6 +103,15 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_encode_bev.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
                                        POINTER(PillarsPfn), POINTER(PillarsOutputs), c_void_p, c_size_t, c_int32,
                                        c_void_p]
+    lib.pillars_pfn_stack_in_features.restype = c_int
+    lib.pillars_pfn_stack_in_features.argtypes = [POINTER(PillarsPfnStack)]
+    lib.pillars_pfn_dense_stack.restype = c_int
+    lib.pillars_pfn_dense_stack.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32,
+                                            POINTER(PillarsPfnStack), POINTER(c_float), c_void_p, c_void_p]
+    lib.pillars_encode_stack.restype = c_int
+    lib.pillars_encode_stack.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
+                                         POINTER(PillarsPfnStack), c_int32, c_int32, POINTER(PillarsOutputs), c_void_p,
+                                         c_size_t, c_int32, c_void_p]
     lib.pillars_set_scatter_stream.restype = c_int
     lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
     lib.pillars_force_generic_features.restype = c_int

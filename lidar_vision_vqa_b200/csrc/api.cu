@@ -332,6 +332,135 @@ int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_p
     return 0;
 }
 
+static int check_stack(const pillars_pfn_stack_t *sk, StackDev *sd, const float voxel[3])
+{
+    if (!sk) return fail(PILLARS_E_BADARG, "stack is NULL");
+    if (sk->n_layers < 1 || sk->n_layers > 2)
+        return fail(PILLARS_E_UNSUPPORTED, "n_layers = %d (1 or 2 are built)", sk->n_layers);
+    if (sk->c_point < 3 || sk->c_point > 8) return fail(PILLARS_E_UNSUPPORTED, "c_point = %d (3..8)", sk->c_point);
+    if (sk->layout != PILLARS_LAYOUT_PILLAR_VFE && sk->layout != PILLARS_LAYOUT_SIMPLE2D)
+        return fail(PILLARS_E_BADARG, "layout = %d", sk->layout);
+    sd->n_layers = sk->n_layers;
+    sd->use_abs = sk->use_absolute_xyz != 0;
+    sd->with_dist = sk->with_distance != 0;
+    sd->layout = sk->layout;
+    for (int l = 0; l < 2; ++l) {
+        sd->out[l] = l < sk->n_layers ? sk->out_features[l] : 0;
+        sd->weight[l] = l < sk->n_layers ? sk->weight[l] : nullptr;
+        sd->scale[l] = l < sk->n_layers ? sk->scale[l] : nullptr;
+        sd->shift[l] = l < sk->n_layers ? sk->shift[l] : nullptr;
+        if (l < sk->n_layers && (!sk->weight[l] || !sk->scale[l] || !sk->shift[l]))
+            return fail(PILLARS_E_BADARG, "stack layer %d: weight / scale / shift NULL", l);
+    }
+    for (int i = 0; i < 3; ++i) {
+        sd->off[i] = sk->offset[i];
+        sd->vsz[i] = voxel ? voxel[i] : 1.f;
+    }
+    if (!stack_supported(*sd, sk->c_point))
+        return fail(PILLARS_E_UNSUPPORTED, "feature stack outside the built shapes (layer 0 in <= 16, out <= 64; two layers: "
+                                           "out[0] <= 32)");
+    return 0;
+}
+
+int pillars_pfn_stack_in_features(const pillars_pfn_stack_t *stack)
+{
+    if (!stack) return fail(PILLARS_E_BADARG, "stack is NULL");
+    StackDev sd{};
+    sd.use_abs = stack->use_absolute_xyz != 0;
+    sd.with_dist = stack->with_distance != 0;
+    sd.layout = stack->layout;
+    return stack_c_in(sd, stack->c_point);
+}
+
+int pillars_pfn_dense_stack(const float *voxels, const void *num_points, int32_t num_points_is_float, const void *coords,
+                            int32_t coords_is_float, int64_t m, int32_t max_points, const pillars_pfn_stack_t *stack,
+                            const float voxel_size[3], float *out, void *stream)
+{
+    g_launches = 0;
+    StackDev sd{};
+    int rc;
+    if (!voxel_size) return fail(PILLARS_E_BADARG, "voxel_size is NULL");
+    if ((rc = check_stack(stack, &sd, voxel_size))) return rc;
+    if (stack->layout != PILLARS_LAYOUT_PILLAR_VFE) return fail(PILLARS_E_BADARG, "padded voxels only exist for PillarVFE");
+    if (m < 0 || max_points < 1) return fail(PILLARS_E_BADARG, "pillars_pfn_dense_stack: bad size");
+    if (m > 0 && (!voxels || !num_points || !coords || !out)) return fail(PILLARS_E_BADARG, "pillars_pfn_dense_stack: NULL pointer");
+    if (reinterpret_cast<uintptr_t>(coords) % 16 != 0) return fail(PILLARS_E_BADARG, "coords must be 16-byte aligned");
+    cudaError_t e = launch_pfn_multi_dense(voxels, num_points, num_points_is_float != 0, coords, coords_is_float != 0, m,
+                                           max_points, stack->c_point, sd, out, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "pillars_pfn_dense_stack");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int32_t col0, const int32_t *frame_offsets,
+                         int32_t n_frames, const pillars_grid_t *grid, const pillars_pfn_stack_t *stack, int32_t mode,
+                         int32_t coords_cols, const pillars_outputs_t *out, void *workspace, size_t workspace_bytes,
+                         int32_t scatter_variant, void *stream)
+{
+    g_launches = 0;
+    int rc;
+    if ((rc = check_grid(grid, n_frames))) return rc;
+    StackDev sd{};
+    if ((rc = check_stack(stack, &sd, grid->voxel))) return rc;
+    if ((rc = check_points(points, n, row_stride, col0, stack->c_point))) return rc;
+    if (mode != PILLARS_MODE_HARD && mode != PILLARS_MODE_DYNAMIC) return fail(PILLARS_E_BADARG, "mode = %d", mode);
+    if (coords_cols != 3 && coords_cols != 4) return fail(PILLARS_E_BADARG, "coords_cols = %d", coords_cols);
+    if (!frame_offsets || !out || !out->pillar_features) return fail(PILLARS_E_BADARG, "frame_offsets / out / pillar_features NULL");
+    if (out->voxels || out->point_pillar || out->point_slot)
+        return fail(PILLARS_E_UNSUPPORTED, "membership outputs come from pillars_voxelize");
+    const bool dynamic = mode == PILLARS_MODE_DYNAMIC;
+    const bool want_bev = out->bev != nullptr;
+    if (want_bev && (dynamic || grid->grid[2] != 1 || coords_cols != 4))
+        return fail(PILLARS_E_UNSUPPORTED, "the fused BEV canvas needs mode HARD, nz == 1 and 4-column coords");
+    if (out->pillar_capacity < 0) return fail(PILLARS_E_BADARG, "pillar_capacity < 0");
+    const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+        return fail(PILLARS_E_WORKSPACE, "workspace NULL or not 256-byte aligned");
+    const Workspace ws = carve_workspace(workspace, n, n_frames, cells_xy);
+    if (ws.total_bytes > workspace_bytes)
+        return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.total_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GridDev gd = make_grid_dev(*grid);
+    if (dynamic) {
+        gd.ignore_z = 1;
+        gd.max_points = 0x7FFFFFFF;
+        gd.max_voxels = 0x7FFFFFFF;
+    }
+    cudaError_t e;
+    stage_mark(0, st);
+    PlaceExtras px{};
+    if ((e = launch_group_points(points, n, row_stride, col0, stack->c_point, frame_offsets, n_frames, gd, ws,
+                                 out->pillar_count, /*want_index_lists=*/true, px, st)) != cudaSuccess)
+        return cuda_fail(e, "group_points");
+    stage_mark(1, st);
+    MultiJob job{};
+    job.points = points;
+    job.n = n;
+    job.stride = row_stride;
+    job.col0 = col0;
+    job.c_point = stack->c_point;
+    job.nb = n_frames;
+    job.idx_bits = idx_bits_for(n > 1 ? n : 2);
+    job.dynamic = dynamic;
+    job.write_cell_row = want_bev;
+    job.pillar_features = out->pillar_features;
+    job.voxel_coords = out->voxel_coords;
+    job.voxel_num_points = out->voxel_num_points;
+    job.coords_cols = coords_cols;
+    job.capacity = out->pillar_capacity;
+    if ((e = launch_pfn_multi_lists(job, sd, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pfn_multi");
+    stage_mark(2, st);
+    if (want_bev) {
+        const int f_last = sd.out[sd.n_layers - 1];
+        if ((e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, f_last, grid->grid[0], grid->grid[1], out->bev,
+                                scatter_variant, st)) != cudaSuccess)
+            return cuda_fail(e, "scatter");
+    }
+    stage_mark(3, st);
+    g_launches_last = g_launches;
+    return 0;
+}
+
 int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m, const int32_t *m_dev,
                         int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz, float *bev, void *workspace,
                         size_t workspace_bytes, int32_t variant, void *stream)

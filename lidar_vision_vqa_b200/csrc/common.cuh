@@ -69,6 +69,7 @@ struct Workspace {
     PointRecord *records;           // [n] point records grouped by pillar
     float4 *pillar_meta;            // [2n] per pillar, at its list start position: {centre x,y,z, 1.0 if n < P} {row (int bits, -1: dropped), n (uint bits), -, -}
     float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
+    uint32_t *scan_scratch;         // [B * ny * nx / 2048 + 2] block sums of the cell-rank scan (dynamic variant)
     uint32_t cap;                   // hash slots
     uint32_t n_tiles;
     size_t total_bytes;
@@ -119,6 +120,7 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     w.records = reinterpret_cast<PointRecord *>(take(sizeof(PointRecord) * n));
     w.pillar_meta = reinterpret_cast<float4 *>(take(sizeof(float4) * 2 * n));
     w.folded = reinterpret_cast<float *>(take(sizeof(float) * PILLARS_FOLDED_FLOATS));
+    w.scan_scratch = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (static_cast<size_t>(nb) * cells_xy / 2048 + 2)));
     w.total_bytes = off;
     return w;
 }
@@ -132,6 +134,7 @@ struct GridDev {
     int32_t max_voxels;
     uint32_t cells;     // nx*ny*nz
     uint32_t cells_xy;  // nx*ny
+    int32_t ignore_z;   // dynamic pillar variant: z is neither range checked nor part of the key (dynamic_pillar_vfe.py:93-96)
 };
 
 inline GridDev make_grid_dev(const pillars_grid_t &g)
@@ -146,6 +149,7 @@ inline GridDev make_grid_dev(const pillars_grid_t &g)
     d.max_voxels = g.max_voxels;
     d.cells_xy = static_cast<uint32_t>(g.grid[0]) * static_cast<uint32_t>(g.grid[1]);
     d.cells = d.cells_xy * static_cast<uint32_t>(g.grid[2]);
+    d.ignore_z = 0;
     return d;
 }
 
@@ -212,6 +216,34 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
 cudaError_t launch_pfn_dense(const float *voxels, const void *num_points, bool np_float, const void *coords,
                              bool coords_float, int64_t m, int max_points, int c_point, int c_in, int f_out,
                              bool use_abs, bool with_dist, const PfnDev &pfn, float *out, cudaStream_t st);
+
+// ---- general feature stack (pfn_multi.cu) -----------------------------------------------------
+struct StackDev {
+    int n_layers;          // 1 or 2
+    int out[2];            // outputs of each layer's linear
+    int use_abs, with_dist;
+    int layout;            // 0: [point, cluster, centre(, dist)]   1: [centre, point(, dist)] (DynamicPillarVFESimple2D)
+    const float *weight[2], *scale[2], *shift[2];
+    float off[3], vsz[3];
+};
+struct MultiJob {
+    const float *points;
+    int64_t n;
+    int stride, col0, c_point, nb, idx_bits;
+    bool dynamic;          // DynamicPillarVFE semantics (rows by sorted key, no caps)
+    bool write_cell_row;
+    float *pillar_features;
+    int32_t *voxel_coords, *voxel_num_points;
+    int coords_cols;
+    int64_t capacity;
+};
+int stack_c_in(const StackDev &sd, int c_point);
+bool stack_supported(const StackDev &sd, int c_point);
+cudaError_t launch_pfn_multi_lists(const MultiJob &job, const StackDev &sd, const GridDev &gd, const Workspace &ws,
+                                   cudaStream_t st);
+cudaError_t launch_pfn_multi_dense(const float *voxels, const void *num_points, bool np_float, const void *coords,
+                                   bool coords_float, int64_t m, int max_points, int c_point, const StackDev &sd,
+                                   float *out, cudaStream_t st);
 
 cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t m, const int32_t *m_dev, int nb, int nx,
                                   int ny, int nz, int32_t *cell_row, cudaStream_t st);

@@ -116,7 +116,7 @@ k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int c
         // IEEE fp32, true division, no contraction: bit-identical to the CPU voxeliser
         const float fx = floorf(__fdiv_rn(__fsub_rn(p[0], gd.rmin[0]), gd.vsz[0]));
         const float fy = floorf(__fdiv_rn(__fsub_rn(p[1], gd.rmin[1]), gd.vsz[1]));
-        const float fz = floorf(__fdiv_rn(__fsub_rn(p[2], gd.rmin[2]), gd.vsz[2]));
+        const float fz = gd.ignore_z ? 0.f : floorf(__fdiv_rn(__fsub_rn(p[2], gd.rmin[2]), gd.vsz[2]));
         valid = (fx >= 0.f) && (fx < static_cast<float>(gd.g[0])) && (fy >= 0.f) && (fy < static_cast<float>(gd.g[1])) &&
                 (fz >= 0.f) && (fz < static_cast<float>(gd.g[2]));
         if (valid) {

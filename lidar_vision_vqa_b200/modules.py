@@ -40,6 +40,15 @@ def _cfg_get(cfg, key, default=_MISSING):
     return default
 
 
+def _points_on_device(points: torch.Tensor) -> torch.Tensor:
+    """A host batch (pinned or not) is copied as part of the call; without a GPU the call fails loudly."""
+    if not points.is_cuda:
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("the pillar path runs on a B200 only: no CUDA device (no CPU fallback)")
+        points = points.cuda(non_blocking=True)
+    return points.contiguous()
+
+
 class VFETemplate(nn.Module):
     def __init__(self, model_cfg, **kwargs):
         super().__init__()
@@ -99,20 +108,34 @@ class _PillarVFEBase(VFETemplate):
         self.grid_size = None if grid_size is None else [int(v) for v in np.asarray(grid_size).tolist()]
         self._folded = None
         self._folded_key = None
+        self._stack_folded = None
+        self._stack_key = None
 
     def get_output_feature_dim(self):
         return self.num_filters[-1]
 
-    def _params(self, device) -> ops.PfnParams:
+    LAYOUT = 0  # ops / _native LAYOUT_PILLAR_VFE
+
+    def _layer_tensors(self):
+        out = []
+        for layer in self.pfn_layers:
+            out += [layer.linear.weight] + ([layer.norm.weight, layer.norm.bias, layer.norm.running_mean,
+                                             layer.norm.running_var] if self.use_norm else [layer.linear.bias])
+        return out
+
+    def _check_eval(self):
         if self.training:
             raise RuntimeError("the B200 pillar path is inference-only (BatchNorm is folded from running statistics); "
                                "call .eval()")
-        if len(self.pfn_layers) != 1:
-            raise NotImplementedError("multi-layer PFN (NUM_FILTERS with more than one entry) is not built yet")
+
+    def _single_layer(self) -> bool:
+        return len(self.pfn_layers) == 1 and self.LAYOUT == 0
+
+    def _params(self, device) -> ops.PfnParams:
+        """The single-layer form consumed by the streaming / dense kernels."""
+        self._check_eval()
         layer = self.pfn_layers[0]
-        tensors = [layer.linear.weight] + ([layer.norm.weight, layer.norm.bias, layer.norm.running_mean,
-                                            layer.norm.running_var] if self.use_norm else [layer.linear.bias])
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in self._layer_tensors())
         if self._folded is None or key != self._folded_key:
             bn = None
             if self.use_norm:
@@ -125,6 +148,28 @@ class _PillarVFEBase(VFETemplate):
             self._folded_key = key
         return self._folded
 
+    def _stack(self, device) -> ops.PfnStackParams:
+        """Any one- or two-layer configuration, for the general feature kernel (csrc/pfn_multi.cu)."""
+        self._check_eval()
+        if len(self.pfn_layers) > 2:
+            raise NotImplementedError("PFN stacks of more than two layers are not built (no reference config uses one)")
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in self._layer_tensors())
+        if self._stack_folded is None or key != self._stack_key:
+            layers = []
+            for layer in self.pfn_layers:
+                bn = None
+                if self.use_norm:
+                    bn = (layer.norm.weight, layer.norm.bias, layer.norm.running_mean, layer.norm.running_var,
+                          layer.norm.eps)
+                layers.append((layer.linear.weight, bn, None if self.use_norm else layer.linear.bias))
+            self._stack_folded = ops.fold_pfn_stack(layers, c_point=self.num_raw_point_features,
+                                                    use_absolute_xyz=self.use_absolute_xyz,
+                                                    with_distance=self.with_distance, voxel_size=self.voxel_size,
+                                                    point_cloud_range=self.point_cloud_range, device=device,
+                                                    layout=self.LAYOUT)
+            self._stack_key = key
+        return self._stack_folded
+
 
 class PillarVFE(_PillarVFEBase):
     """Reads ``voxels [M,P,C]``, ``voxel_num_points [M]``, ``voxel_coords [M,4] (b,z,y,x)`` (fp32 after
@@ -132,8 +177,13 @@ class PillarVFE(_PillarVFEBase):
 
     def forward(self, batch_dict, **kwargs):
         voxels = batch_dict["voxels"]
-        feats = ops.pfn_dense(voxels, batch_dict["voxel_num_points"], batch_dict["voxel_coords"],
-                              self._params(voxels.device), self.voxel_size)
+        if self._single_layer():
+            feats = ops.pfn_dense(voxels, batch_dict["voxel_num_points"], batch_dict["voxel_coords"],
+                                  self._params(voxels.device), self.voxel_size)
+        else:  # NUM_FILTERS with two entries: pillar_vfe.py:44-49,119-120
+            ops._require_device(voxels)
+            feats = ops.pfn_dense_stack(voxels, batch_dict["voxel_num_points"], batch_dict["voxel_coords"],
+                                        self._stack(voxels.device), self.voxel_size)
         batch_dict["pillar_features"] = feats.squeeze()  # pillar_vfe.py:121 (M == 1 collapses to [F] there too)
         return batch_dict
 
@@ -164,14 +214,15 @@ class PillarVFEFromPoints(_PillarVFEBase):
                                  self.max_voxels)
 
     def forward(self, batch_dict, **kwargs):
-        points = batch_dict["points"]
-        if not points.is_cuda:  # host batch (pinned or not): the H2D copy is part of the call
-            points = points.cuda(non_blocking=True)
-        points = points.contiguous()
+        points = _points_on_device(batch_dict["points"])
         batch_size = int(batch_dict["batch_size"])
         offs = ops.frame_offsets_from_points(points, batch_size)
-        res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=1,
-                             with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
+        if self._single_layer():
+            res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=1,
+                                 with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
+        else:
+            res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=1,
+                                   with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
         # the one host sync of the call: per-frame pillar counts (B+1 ints) size the returned views
         # (the reference syncs at the same place for the batch size, pointpillar_scatter.py:17)
         counts = res["pillar_count"].cpu()
@@ -186,6 +237,78 @@ class PillarVFEFromPoints(_PillarVFEBase):
             batch_dict["spatial_features"] = res["bev"]
             batch_dict["_b200_scatter_done"] = True
         return batch_dict
+
+
+class DynamicPillarVFE(_PillarVFEBase):
+    """dynamic_pillar_vfe.py:49-142 (registry name ``DynPillarVFE``): reads ``points [N, 1+C] (b,x,y,z,...)``; quantises x,y
+    on the device (z is not range checked), groups with NO per-pillar cap, ``scatter_mean`` / ``PFNLayerV2`` /
+    ``scatter_max``; rows come out in the order of the merged key ``b*nx*ny + ix*ny + iy`` (``torch.unique``, :99-103) and
+    ``voxel_coords`` is ``(b, 0, iy, ix)`` int32 (:132-138).  Writes ``pillar_features``, ``voxel_features``,
+    ``voxel_coords`` (and ``voxel_num_points``, the uncapped counts, which the reference does not emit)."""
+
+    COORDS_COLS = 4
+    COORDS_KEY = "voxel_coords"
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, **kwargs):
+        super().__init__(model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size, **kwargs)
+        nx, ny, _ = self.grid_size
+        # nz = 1 for the key: the dynamic variants collapse z (the reference builds its key from ix, iy only)
+        self.grid = ops.GridSpec(self.point_cloud_range, self.voxel_size, (nx, ny, 1), 2 ** 31 - 1, 2 ** 31 - 1)
+
+    def forward(self, batch_dict, **kwargs):
+        points = _points_on_device(batch_dict["points"])
+        if "batch_size" in batch_dict:
+            batch_size = int(batch_dict["batch_size"])
+        else:
+            batch_size = int(points[:, 0].max().item()) + 1 if points.shape[0] else 0
+        offs = ops.frame_offsets_from_points(points, batch_size)
+        res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=1, dynamic=True,
+                               coords_cols=self.COORDS_COLS)
+        m = int(res["pillar_count"][-1].item())  # the reference syncs here too (torch.unique returns a sized tensor)
+        feats = res["pillar_features"][:m]
+        batch_dict["pillar_features"] = feats
+        if self.COORDS_KEY == "voxel_coords":
+            batch_dict["voxel_features"] = feats
+        batch_dict[self.COORDS_KEY] = res["voxel_coords"][:m]
+        batch_dict["voxel_num_points"] = res["voxel_num_points"][:m]
+        return batch_dict
+
+
+class DynamicPillarVFESimple2D(DynamicPillarVFE):
+    """dynamic_pillar_vfe.py:145-240: features ``[f_center, point channels (, distance)]`` (no cluster offset), so the
+    first linear has ``C + 3`` inputs (:151-157); writes ``pillar_features`` and ``pillar_coords [M,3] (b, iy, ix)``."""
+
+    LAYOUT = 1
+    COORDS_COLS = 3
+    COORDS_KEY = "pillar_coords"
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, **kwargs):
+        nn.Module.__init__(self)
+        self.model_cfg = model_cfg
+        self.use_norm = _cfg_get(model_cfg, "USE_NORM")
+        self.with_distance = _cfg_get(model_cfg, "WITH_DISTANCE")
+        self.use_absolute_xyz = _cfg_get(model_cfg, "USE_ABSLOTE_XYZ")
+        self.num_raw_point_features = int(num_point_features)
+        c_in = int(num_point_features)
+        if self.use_absolute_xyz:
+            c_in += 3
+        if self.with_distance:
+            c_in += 1
+        self.num_filters = list(_cfg_get(model_cfg, "NUM_FILTERS"))
+        assert len(self.num_filters) > 0
+        dims = [c_in] + list(self.num_filters)
+        self.pfn_layers = nn.ModuleList([PFNLayer(dims[i], dims[i + 1], self.use_norm, last_layer=(i >= len(dims) - 2))
+                                         for i in range(len(dims) - 1)])
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in np.asarray(point_cloud_range).tolist()]
+        self.voxel_x, self.voxel_y, self.voxel_z = self.voxel_size
+        self.x_offset = self.voxel_x / 2 + self.point_cloud_range[0]
+        self.y_offset = self.voxel_y / 2 + self.point_cloud_range[1]
+        self.z_offset = self.voxel_z / 2 + self.point_cloud_range[2]
+        self.grid_size = [int(v) for v in np.asarray(grid_size).tolist()]
+        self._folded = self._folded_key = self._stack_folded = self._stack_key = None
+        nx, ny = self.grid_size[0], self.grid_size[1]
+        self.grid = ops.GridSpec(self.point_cloud_range, self.voxel_size, (nx, ny, 1), 2 ** 31 - 1, 2 ** 31 - 1)
 
 
 class PointPillarScatter(nn.Module):
@@ -246,6 +369,8 @@ VFE_REGISTRY = {
     "VFETemplate": VFETemplate,
     "PillarVFE": PillarVFE,
     "PillarVFEFromPoints": PillarVFEFromPoints,
+    "DynPillarVFE": DynamicPillarVFE,
+    "DynamicPillarVFESimple2D": DynamicPillarVFESimple2D,
 }
 MAP_TO_BEV_REGISTRY = {
     "PointPillarScatter": PointPillarScatter,

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import NativeLibraryError, PillarsOutputs, PillarsPfn, check, make_grid
+from ._native import NativeLibraryError, PillarsOutputs, PillarsPfn, PillarsPfnStack, check, make_grid
 
 FOLDED_FLOATS = 13 * 64  # PILLARS_FOLDED_FLOATS
 SCATTER_VARIANTS = {"auto": 0, "plain": 1, "bulk1d": 2, "tma2d": 3, "wide": 4, "persist": 5, "patch": 6}
@@ -131,6 +131,64 @@ def fold_pfn(weight: torch.Tensor, bn: Optional[Tuple[torch.Tensor, torch.Tensor
                      off).prepare()
 
 
+@dataclass
+class PfnStackParams:
+    """A one- or two-layer PFN stack with BatchNorm folded (eval mode), resident on the device: what the general
+    feature kernel (csrc/pfn_multi.cu) consumes."""
+
+    layers: Sequence[PfnParams]  # folded layers in order; only weight / scale / shift of each are used
+    c_point: int
+    use_absolute_xyz: bool
+    with_distance: bool
+    offset: Tuple[float, float, float]
+    layout: int = _native.LAYOUT_PILLAR_VFE
+
+    @property
+    def f_out(self) -> int:
+        return int(self.layers[-1].weight.shape[0])
+
+    def native(self) -> PillarsPfnStack:
+        s = PillarsPfnStack()
+        s.n_layers = len(self.layers)
+        s.c_point = self.c_point
+        s.use_absolute_xyz = int(self.use_absolute_xyz)
+        s.with_distance = int(self.with_distance)
+        s.layout = int(self.layout)
+        for i in range(3):
+            s.offset[i] = float(self.offset[i])
+        for i, layer in enumerate(self.layers):
+            s.out_features[i] = int(layer.weight.shape[0])
+            s.weight[i] = layer.weight.data_ptr()
+            s.scale[i] = layer.scale.data_ptr()
+            s.shift[i] = layer.shift.data_ptr()
+        return s
+
+
+def fold_layer(weight: torch.Tensor, bn, bias, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(weight fp32, scale, shift) of one layer on `device`; BatchNorm1d(eval) folded in float64."""
+    w = weight.detach().to(device=device, dtype=torch.float32).contiguous()
+    f = w.shape[0]
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        sc = gamma.detach().double().cpu() / torch.sqrt(var.detach().double().cpu() + eps)
+        sh = beta.detach().double().cpu() - mean.detach().double().cpu() * sc
+    else:
+        sc = torch.ones(f, dtype=torch.float64)
+        sh = bias.detach().double().cpu() if bias is not None else torch.zeros(f, dtype=torch.float64)
+    return w, sc.to(torch.float32).contiguous().to(device), sh.to(torch.float32).contiguous().to(device)
+
+
+def fold_pfn_stack(layers, *, c_point: int, use_absolute_xyz: bool, with_distance: bool, voxel_size, point_cloud_range,
+                   device, layout: int = _native.LAYOUT_PILLAR_VFE) -> PfnStackParams:
+    """``layers``: sequence of ``(linear_weight, bn_tuple_or_None, bias_or_None)`` in order."""
+    off = tuple(float(voxel_size[i]) / 2 + float(point_cloud_range[i]) for i in range(3))
+    folded = []
+    for (w, bn, bias) in layers:
+        wf, sc, sh = fold_layer(w, bn, bias, device)
+        folded.append(PfnParams(wf, sc, sh, int(c_point), bool(use_absolute_xyz), bool(with_distance), off))
+    return PfnStackParams(folded, int(c_point), bool(use_absolute_xyz), bool(with_distance), off, int(layout))
+
+
 def frame_offsets_from_points(points_b: torch.Tensor, batch_size: int) -> torch.Tensor:
     """``batch_dict['points']`` ``[N, 1+C]`` (frame index in column 0, datasets/dataset.py:237-244) -> ``[B+1]`` int32."""
     _require_device(points_b)
@@ -218,6 +276,78 @@ def pfn_dense(voxels: torch.Tensor, num_points: torch.Tensor, coords: torch.Tens
     check(_native.load().pillars_pfn_dense(voxels.data_ptr(), npts.data_ptr(), np_f, crd.data_ptr(), crd_f, m, p,
                                            ctypes.byref(nat), vs, out.data_ptr(), _stream_ptr()), "pillars_pfn_dense")
     return out
+
+
+def pfn_dense_stack(voxels: torch.Tensor, num_points: torch.Tensor, coords: torch.Tensor, stack: PfnStackParams,
+                    voxel_size) -> torch.Tensor:
+    """PillarVFE.forward on padded voxels through a one- or two-layer stack (pillar_vfe.py:94-123 with :44-49)."""
+    _require_device(voxels)
+    if voxels.dtype != torch.float32 or voxels.dim() != 3:
+        raise ValueError("voxels must be float32 [M,P,C]")
+    voxels = voxels.contiguous()
+    m, p, c = voxels.shape
+    if c != stack.c_point:
+        raise ValueError(f"voxels have {c} channels, the PFN was built for {stack.c_point}")
+
+    def norm(t):
+        if t.dtype in (torch.float32, torch.int32):
+            return t.contiguous(), int(t.dtype == torch.float32)
+        if t.dtype.is_floating_point:
+            return t.to(torch.float32).contiguous(), 1
+        return t.to(torch.int32).contiguous(), 0
+
+    npts, np_f = norm(num_points)
+    crd, crd_f = norm(coords)
+    out = torch.empty((m, stack.f_out), dtype=torch.float32, device=voxels.device)
+    vs = (ctypes.c_float * 3)(*[float(v) for v in voxel_size])
+    nat = stack.native()
+    check(_native.load().pillars_pfn_dense_stack(voxels.data_ptr(), npts.data_ptr(), np_f, crd.data_ptr(), crd_f, m, p,
+                                                 ctypes.byref(nat), vs, out.data_ptr(), _stream_ptr()),
+          "pillars_pfn_dense_stack")
+    return out
+
+
+def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, stack: PfnStackParams, *,
+                 col0: int = 0, dynamic: bool = False, coords_cols: int = 4, with_bev: bool = False,
+                 capacity: Optional[int] = None, scatter_variant: str = "auto", ws_slot: int = 0) -> Dict[str, torch.Tensor]:
+    """Raw points -> pillar features through the general feature kernel.  ``dynamic=False``: hard-voxeliser semantics
+    (the fused equivalent of ``transform_points_to_voxels`` + a multi-layer ``PillarVFE``); ``dynamic=True``:
+    DynamicPillarVFE / DynamicPillarVFESimple2D semantics (dynamic_pillar_vfe.py:90-142, :193-240)."""
+    _check_points(points, frame_offsets)
+    lib = _native.load()
+    n, stride = points.shape
+    nb = frame_offsets.numel() - 1
+    if stride - col0 < stack.c_point:
+        raise ValueError("points have fewer channels than the PFN expects")
+    dev = points.device
+    cap = capacity
+    if cap is None:
+        cap = n if dynamic else min(n, nb * grid.max_voxels)
+    nx, ny, nz = grid.grid_size
+    res = {
+        "pillar_features": torch.empty((cap, stack.f_out), dtype=torch.float32, device=dev),
+        "voxel_coords": torch.empty((cap, coords_cols), dtype=torch.int32, device=dev),
+        "voxel_num_points": torch.empty((cap,), dtype=torch.int32, device=dev),
+        "pillar_count": torch.empty((nb + 1,), dtype=torch.int32, device=dev),
+    }
+    out = PillarsOutputs()
+    out.pillar_capacity = cap
+    out.pillar_features = res["pillar_features"].data_ptr()
+    out.voxel_coords = res["voxel_coords"].data_ptr()
+    out.voxel_num_points = res["voxel_num_points"].data_ptr()
+    out.pillar_count = res["pillar_count"].data_ptr()
+    if with_bev:
+        res["bev"] = torch.empty((nb, stack.f_out * nz, ny, nx), dtype=torch.float32, device=dev)
+        out.bev = res["bev"].data_ptr()
+    g = grid.native()
+    need = lib.pillars_workspace_bytes(n, nb, ctypes.byref(g))
+    ws = workspace(need, dev, ws_slot)
+    nat = stack.native()
+    check(lib.pillars_encode_stack(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
+                                   ctypes.byref(nat), _native.MODE_DYNAMIC if dynamic else _native.MODE_HARD, coords_cols,
+                                   ctypes.byref(out), ws.data_ptr(), ws.numel(), SCATTER_VARIANTS[scatter_variant],
+                                   _stream_ptr()), "pillars_encode_stack")
+    return res
 
 
 def scatter_bev(pillar_features: torch.Tensor, coords: torch.Tensor, batch_size: int, nx: int, ny: int, nz: int = 1, *,

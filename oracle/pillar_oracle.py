@@ -14,6 +14,9 @@ Pieces (each cites the reference lines it restates; paths relative to ``src/lida
   (PillarVFE.forward), fp32 torch on CPU.  *Pinned*: checked against the reference module itself
   (``tests/golden/*.npz`` made by ``tests/golden/make_golden.py`` in the build container).
 * :func:`scatter_bev` -- ``models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-37``.  *Pinned* likewise.
+* :func:`dynamic_pillar_vfe` -- ``models/backbones_3d/vfe/dynamic_pillar_vfe.py:35-46,90-142`` (DynamicPillarVFE +
+  PFNLayerV2) and ``:193-240`` (DynamicPillarVFESimple2D) restated with plain torch index ops.  *Pinned* against the
+  reference modules' goldens (``dyn_*.npz``).
 * :func:`dynamic_pillar_sets` -- the on-device quantisation of
   ``models/backbones_3d/vfe/dynamic_pillar_vfe.py:93-103`` (set of pillars + counts), used as a second opinion
   for the voxeliser's quantisation.  *Pinned* against the reference DynamicPillarVFE golden.
@@ -299,3 +302,67 @@ def dynamic_pillar_sets(points_b: np.ndarray, point_cloud_range, voxel_size):
     uq = uq.int()
     coords = torch.stack([uq // sxy, torch.zeros_like(uq), uq % sy, (uq % sxy) // sy], dim=1)
     return coords.numpy().astype(np.int32), cnt.numpy()
+
+
+def _pfn_layer_v2(x: torch.Tensor, inv: torch.Tensor, m: int, sd: dict, i: int, use_norm: bool, last: bool) -> torch.Tensor:
+    """dynamic_pillar_vfe.py:35-46 (PFNLayerV2.forward): x is [N, Cin], inv [N] the pillar of each point."""
+    y = x @ sd[f"pfn_layers.{i}.linear.weight"].float().t()
+    if use_norm:
+        gamma = sd[f"pfn_layers.{i}.norm.weight"].float()
+        beta = sd[f"pfn_layers.{i}.norm.bias"].float()
+        mu = sd[f"pfn_layers.{i}.norm.running_mean"].float()
+        var = sd[f"pfn_layers.{i}.norm.running_var"].float()
+        y = (y - mu) / torch.sqrt(var + 1e-3) * gamma + beta
+    else:
+        y = y + sd[f"pfn_layers.{i}.linear.bias"].float()
+    y = torch.relu(y)
+    y_max = torch.full((m, y.shape[1]), float("-inf"), dtype=y.dtype)
+    y_max = y_max.scatter_reduce(0, inv.view(-1, 1).expand_as(y), y, reduce="amax", include_self=True)  # scatter_max :40
+    if last:
+        return y_max
+    return torch.cat([y, y_max[inv]], dim=1)  # :44-45
+
+
+def dynamic_pillar_vfe(points_b, state_dict: dict, voxel_size, point_cloud_range, use_norm: bool = True,
+                       with_distance: bool = False, use_absolute_xyz: bool = True, simple2d: bool = False):
+    """DynamicPillarVFE.forward (dynamic_pillar_vfe.py:90-142) or, with ``simple2d``, DynamicPillarVFESimple2D.forward
+    (:193-240) on CPU in fp32.  Returns ``(pillar_features [M,F], coords)`` with coords ``[M,4] (b,0,iy,ix)`` or, for
+    simple2d, ``[M,3] (b,iy,ix)``; rows sorted by the merged key."""
+    p = torch.as_tensor(points_b, dtype=torch.float32)
+    rng = torch.tensor(np.asarray(point_cloud_range, dtype=np.float32))
+    vs = torch.tensor(np.asarray(voxel_size, dtype=np.float32))
+    grid = torch.tensor(grid_size_of(point_cloud_range, voxel_size))
+    vx, vy, vz = (float(v) for v in voxel_size)
+    x_off = vx / 2 + float(point_cloud_range[0])
+    y_off = vy / 2 + float(point_cloud_range[1])
+    z_off = vz / 2 + float(point_cloud_range[2])
+    ij = torch.floor((p[:, [1, 2]] - rng[[0, 1]]) / vs[[0, 1]]).int()  # :93
+    ok = ((ij >= 0) & (ij < grid[[0, 1]])).all(dim=1)  # :94
+    p, ij = p[ok], ij[ok]
+    xyz = p[:, [1, 2, 3]].contiguous()
+    sxy, sy = int(grid[0] * grid[1]), int(grid[1])
+    key = p[:, 0].int() * sxy + ij[:, 0] * sy + ij[:, 1]  # :99-101
+    uq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)  # :103
+    m = uq.shape[0]
+    f_center = torch.zeros_like(xyz)
+    f_center[:, 0] = xyz[:, 0] - (ij[:, 0].to(xyz.dtype) * vx + x_off)  # :109
+    f_center[:, 1] = xyz[:, 1] - (ij[:, 1].to(xyz.dtype) * vy + y_off)  # :110
+    f_center[:, 2] = xyz[:, 2] - z_off  # :111
+    if simple2d:
+        feats = [f_center, p[:, 1:] if use_absolute_xyz else p[:, 4:]]  # :209-213
+    else:
+        mean = torch.zeros((m, 3), dtype=xyz.dtype).index_add_(0, inv, xyz) / cnt.to(xyz.dtype).view(-1, 1)  # :105
+        f_cluster = xyz - mean[inv]  # :106
+        feats = [p[:, 1:] if use_absolute_xyz else p[:, 4:], f_cluster, f_center]  # :113-116
+    if with_distance:
+        feats.append(torch.linalg.vector_norm(p[:, 1:4], ord=2, dim=1, keepdim=True))
+    x = torch.cat(feats, dim=-1)
+    n_layers = len([k for k in state_dict if k.endswith("linear.weight")])
+    for i in range(n_layers):
+        x = _pfn_layer_v2(x, inv, m, state_dict, i, use_norm, last=(i == n_layers - 1))
+    uq = uq.int()
+    if simple2d:
+        coords = torch.stack([uq // sxy, uq % sy, (uq % sxy) // sy], dim=1)  # :232-237 then [:, [0, 2, 1]]
+    else:
+        coords = torch.stack([uq // sxy, torch.zeros_like(uq), uq % sy, (uq % sxy) // sy], dim=1)  # :132-138
+    return x, coords.numpy().astype(np.int32), cnt.numpy()

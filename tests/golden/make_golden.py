@@ -88,27 +88,36 @@ def run_case(name, *, batch, c, p_max, max_voxels, n_keep, seed, use_norm=True, 
           f"-> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
-def run_dynamic(name, *, batch, c, n_keep, seed, num_filters=(64,)):
+def run_dynamic(name, *, batch, c, n_keep, seed, num_filters=(64,), keep_z_outliers=False, simple2d=False,
+                with_distance=False, use_abs=True):
     ref = ref_loader.load_reference()
-    pts, offs = small_batch(batch, c, n_keep, seed)
-    # DynamicPillarVFE never checks z; keep z inside the range so its pillar set is comparable with the hard voxeliser
-    pts = pts[(pts[:, 2] >= RANGE[2]) & (pts[:, 2] < RANGE[5])]
-    # recompute offsets after the z filter
     pb_full = synth.to_pcdet_points(*small_batch(batch, c, n_keep, seed))
-    pb = pb_full[(pb_full[:, 3] >= RANGE[2]) & (pb_full[:, 3] < RANGE[5])]
+    if keep_z_outliers:
+        # DynamicPillarVFE never range-checks z (dynamic_pillar_vfe.py:93-96): push some points outside [zmin, zmax)
+        pb = pb_full.copy()
+        pb[::7, 3] += 9.0
+        pb[::11, 3] -= 9.0
+    else:
+        # keep z inside the range so the pillar set is comparable with the hard voxeliser
+        pb = pb_full[(pb_full[:, 3] >= RANGE[2]) & (pb_full[:, 3] < RANGE[5])]
     grid = po.grid_size_of(RANGE, VOXEL)
-    cfg = ref.AttrDict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=list(num_filters))
+    cfg = ref.AttrDict(USE_NORM=True, WITH_DISTANCE=with_distance, USE_ABSLOTE_XYZ=use_abs, NUM_FILTERS=list(num_filters))
+    cls = ref.DynamicPillarVFESimple2D if simple2d else ref.DynamicPillarVFE
     with ref_loader.cuda_is_identity():
-        vfe = ref.DynamicPillarVFE(model_cfg=cfg, num_point_features=c, voxel_size=list(VOXEL), grid_size=grid,
-                                   point_cloud_range=np.asarray(RANGE, np.float32))
+        vfe = cls(model_cfg=cfg, num_point_features=c, voxel_size=list(VOXEL), grid_size=grid,
+                  point_cloud_range=np.asarray(RANGE, np.float32))
     sd = po.random_pfn_params(vfe.pfn_layers[0].linear.in_features, num_filters, True, seed=seed + 100)
     vfe.load_state_dict(sd, strict=True)
     vfe.eval()
     with torch.inference_mode():
         bd = vfe({"points": torch.from_numpy(pb), "batch_size": batch})
+    ckey = "pillar_coords" if simple2d else "voxel_coords"
     save = {"points_b": pb, "range": np.asarray(RANGE, np.float32), "voxel_size": np.asarray(VOXEL, np.float32),
-            "grid_size": grid, "out.voxel_coords": bd["voxel_coords"].numpy(),
-            "out.pillar_features": bd["pillar_features"].numpy()}
+            "grid_size": grid, "out.voxel_coords": bd[ckey].numpy(),
+            "out.pillar_features": bd["pillar_features"].numpy(),
+            "num_filters": np.asarray(num_filters, np.int32), "simple2d": np.bool_(simple2d),
+            "with_distance": np.bool_(with_distance), "use_abs": np.bool_(use_abs), "batch": np.int32(batch),
+            "c": np.int32(c)}
     for k, v in sd.items():
         save["sd." + k] = v.numpy()
     path = os.path.join(OUT, name + ".npz")
@@ -150,4 +159,9 @@ if __name__ == "__main__":
     run_case("vfe_c5_m1", batch=1, c=5, p_max=8, max_voxels=1, n_keep=200, seed=50, scatter=False)
     run_case("vfe_c5_2layer", batch=1, c=5, p_max=12, max_voxels=1000, n_keep=1200, seed=60, num_filters=(64, 64))
     run_dynamic("dyn_c5", batch=2, c=5, n_keep=2000, seed=70)
+    run_dynamic("dyn_c5_2layer_zout", batch=2, c=5, n_keep=1500, seed=71, num_filters=(64, 64), keep_z_outliers=True)
+    run_dynamic("dyn2d_c5_f32", batch=2, c=5, n_keep=1500, seed=72, num_filters=(32,), simple2d=True,
+                keep_z_outliers=True)
+    run_dynamic("dyn_c4_dist_noabs", batch=1, c=4, n_keep=1200, seed=73, num_filters=(64,), with_distance=True,
+                use_abs=False)
     run_scatter3d("scatter3d_nz2", batch=2, nx=40, ny=36, nz=2, c_before=32, m_per_frame=300, seed=80)

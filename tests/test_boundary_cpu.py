@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_native.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pillars_abi_version() == 1
+    assert lib.pillars_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():
@@ -120,3 +120,25 @@ def test_grid_size_rule_and_bn_fold():
     bn.eval()
     torch.testing.assert_close((x @ w.t()) * p.scale + p.shift, bn(x @ w.t()), rtol=1e-5, atol=1e-5)
     assert p.offset == (0.2 / 2 + -51.2, 0.2 / 2 + -51.2, 8.0 / 2 + -5)
+
+
+@pytest.mark.parametrize("name", ["dyn_c5", "dyn_c5_2layer_zout", "dyn2d_c5_f32", "dyn_c4_dist_noabs"])
+def test_dynamic_vfe_state_dict_contract(name):
+    """DynPillarVFE / DynamicPillarVFESimple2D: constructor kwargs of dynamic_pillar_vfe.py:50,146, registry names of
+    backbones_3d/vfe/__init__.py:9-18, reference state-dict keys load strictly, get_output_feature_dim."""
+    import lidar_vision_vqa_b200 as L
+
+    g = load_golden(name)
+    reg = "DynamicPillarVFESimple2D" if bool(g["simple2d"]) else "DynPillarVFE"
+    cls = L.VFE_REGISTRY[reg]
+    cfg = Cfg(USE_NORM=True, WITH_DISTANCE=bool(g["with_distance"]), USE_ABSLOTE_XYZ=bool(g["use_abs"]),
+              NUM_FILTERS=[int(v) for v in g["num_filters"]])
+    vfe = cls(model_cfg=cfg, num_point_features=int(g["c"]), voxel_size=[float(v) for v in g["voxel_size"]],
+              grid_size=g["grid_size"], point_cloud_range=g["range"], depth_downsample_factor=None)
+    sd = {k: torch.from_numpy(v) for k, v in g["state_dict"].items()}
+    vfe.load_state_dict(sd, strict=True)
+    assert vfe.get_output_feature_dim() == int(g["num_filters"][-1])
+    assert set(vfe.state_dict().keys()) == set(sd.keys())
+    if not torch.cuda.is_available():
+        with pytest.raises(L.NativeLibraryError):
+            vfe.eval()({"points": torch.from_numpy(g["points_b"]), "batch_size": int(g["batch"])})

@@ -14,6 +14,10 @@ from lidar_vision_vqa_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
+
+class C(dict):
+    __getattr__ = dict.__getitem__
+
 FEAT_RTOL = 1e-3   # the north_star tolerance
 FEAT_ATOL = 1e-5   # exact zeros in empty cells are compared exactly elsewhere
 TIGHT_RTOL, TIGHT_ATOL = 2e-5, 2e-5
@@ -450,3 +454,121 @@ def test_cpu_tensors_and_training_mode_fail_loudly(dev, L):
         vfe.eval()(dict(bd))
     with pytest.raises(RuntimeError):
         vfe.train().to(dev)({k: v.to(dev) for k, v in bd.items()})
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# general feature stack (csrc/pfn_multi.cu): two-layer PFN, DynamicPillarVFE, DynamicPillarVFESimple2D
+# ---------------------------------------------------------------------------------------------------------------------
+DYN_GOLDENS = ["dyn_c5", "dyn_c5_2layer_zout", "dyn2d_c5_f32", "dyn_c4_dist_noabs"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DYN_GOLDENS)
+def test_dynamic_vfe_modules_vs_reference_golden(name, dev, L):
+    """DynPillarVFE / DynamicPillarVFESimple2D drop-ins on the reference's own inputs: voxel_coords / pillar_coords and the
+    row order bit-exact, pillar_features within rtol 1e-3 (fp32)."""
+    g = load_golden(name)
+    simple = bool(g["simple2d"])
+    cls = L.DynamicPillarVFESimple2D if simple else L.DynamicPillarVFE
+    cfg = C(USE_NORM=True, WITH_DISTANCE=bool(g["with_distance"]), USE_ABSLOTE_XYZ=bool(g["use_abs"]),
+            NUM_FILTERS=[int(v) for v in g["num_filters"]])
+    vfe = cls(model_cfg=cfg, num_point_features=int(g["c"]), voxel_size=[float(v) for v in g["voxel_size"]],
+              grid_size=g["grid_size"], point_cloud_range=g["range"])
+    vfe.load_state_dict(_sd_t(g), strict=True)
+    vfe.eval().to(dev)
+    bd = vfe({"points": torch.from_numpy(g["points_b"]).to(dev), "batch_size": int(g["batch"])})
+    key = "pillar_coords" if simple else "voxel_coords"
+    got_c = bd[key].cpu().numpy()
+    np.testing.assert_array_equal(got_c, g["out.voxel_coords"])
+    assert bd[key].dtype == torch.int32
+    np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), g["out.pillar_features"], rtol=1e-3, atol=1e-5)
+    if not simple:
+        assert bd["voxel_features"] is bd["pillar_features"]
+    # the batch size can also be derived from the points (the reference never reads batch_size here)
+    bd2 = vfe({"points": torch.from_numpy(g["points_b"]).to(dev)})
+    np.testing.assert_array_equal(bd2[key].cpu().numpy(), g["out.voxel_coords"])
+
+
+@pytest.mark.gpu
+def test_dynamic_vfe_counts_and_scatter_roundtrip(dev, L, oracle):
+    """Uncapped per-pillar counts equal torch.unique's, and the dynamic coords feed PointPillarScatter unchanged."""
+    g = load_golden("dyn_c5")
+    cfg = C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64])
+    vfe = L.DynamicPillarVFE(model_cfg=cfg, num_point_features=5, voxel_size=[float(v) for v in g["voxel_size"]],
+                             grid_size=g["grid_size"], point_cloud_range=g["range"])
+    vfe.load_state_dict(_sd_t(g), strict=True)
+    vfe.eval().to(dev)
+    bd = vfe({"points": torch.from_numpy(g["points_b"]).to(dev), "batch_size": 2})
+    _, cnt = oracle.dynamic_pillar_sets(g["points_b"], g["range"], g["voxel_size"])
+    np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), cnt)
+    sc = L.PointPillarScatter(model_cfg=C(NUM_BEV_FEATURES=64), grid_size=g["grid_size"])
+    bd = sc(bd)
+    ref = oracle.scatter_bev(bd["pillar_features"].cpu().numpy(), bd["voxel_coords"].cpu().numpy(),
+                             int(g["grid_size"][0]), int(g["grid_size"][1]), batch_size=2)
+    np.testing.assert_array_equal(bd["spatial_features"].cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_two_layer_pillar_vfe_vs_reference_golden(dev, L):
+    """NUM_FILTERS [64, 64] (waymo_models/pointpillar_1x.yaml:34) on the reference's padded voxels: the padded-slot row is
+    NOT re-masked between the layers (pillar_vfe.py:44-49,119-120)."""
+    g = load_golden("vfe_c5_2layer")
+    vfe = L.PillarVFE(model_cfg=_cfg(g), num_point_features=5, voxel_size=[float(v) for v in g["voxel_size"]],
+                      point_cloud_range=g["range"], grid_size=g["grid_size"])
+    vfe.load_state_dict(_sd_t(g), strict=True)
+    vfe.eval().to(dev)
+    for as_int in (False, True):
+        npts = torch.from_numpy(g["voxel_num_points"]).to(dev)
+        crd = torch.from_numpy(g["voxel_coords"]).to(dev)
+        if as_int:
+            npts, crd = npts.int(), crd.int()
+        bd = vfe({"voxels": torch.from_numpy(g["voxels"]).to(dev), "voxel_num_points": npts, "voxel_coords": crd})
+        np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), g["out.pillar_features"], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_two_layer_fused_points_to_bev_vs_reference_golden(dev, L):
+    """points -> grouping -> two-layer stack -> BEV in one call equals the reference's PillarVFE + PointPillarScatter on the
+    voxels the hard voxeliser makes of the same points."""
+    g = load_golden("vfe_c5_2layer")
+    cfg = _cfg(g)
+    cfg["MAX_POINTS_PER_VOXEL"] = int(g["max_points"])
+    cfg["MAX_NUMBER_OF_VOXELS"] = int(g["max_voxels"])
+    cfg["FUSE_SCATTER"] = True
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=[float(v) for v in g["voxel_size"]],
+                                point_cloud_range=g["range"], grid_size=g["grid_size"])
+    vfe.load_state_dict(_sd_t(g), strict=True)
+    vfe.eval().to(dev)
+    offs = g["frame_offsets"]
+    from lidar_vision_vqa_b200 import synth
+
+    pb = torch.from_numpy(synth.to_pcdet_points(g["points"], offs)).to(dev)
+    bd = vfe({"points": pb, "batch_size": len(offs) - 1})
+    np.testing.assert_array_equal(bd["voxel_coords"].cpu().numpy(), g["voxel_coords"].astype(np.int32))
+    np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), g["voxel_num_points"].astype(np.int32))
+    np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), g["out.pillar_features"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(bd["spatial_features"].cpu().numpy(), g["out.spatial_features"], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["vfe_c5_p32_f32coords", "vfe_c5_p8_capbinds_maxvox200", "vfe_c5_dist_noabs"])
+def test_general_kernel_agrees_with_single_layer_goldens(name, dev, L):
+    """The general kernel run on single-layer configurations (hard semantics, caps binding) against the reference."""
+    from lidar_vision_vqa_b200 import ops, synth
+
+    g = load_golden(name)
+    sd = _sd_t(g)
+    grid = L.GridSpec(tuple(float(v) for v in g["range"]), tuple(float(v) for v in g["voxel_size"]),
+                      tuple(int(v) for v in g["grid_size"]), int(g["max_points"]), int(g["max_voxels"]))
+    bn = (sd["pfn_layers.0.norm.weight"], sd["pfn_layers.0.norm.bias"], sd["pfn_layers.0.norm.running_mean"],
+          sd["pfn_layers.0.norm.running_var"], 1e-3)
+    stack = ops.fold_pfn_stack([(sd["pfn_layers.0.linear.weight"], bn, None)], c_point=g["points"].shape[1],
+                               use_absolute_xyz=bool(g["use_abs"]), with_distance=bool(g["with_distance"]),
+                               voxel_size=grid.voxel_size, point_cloud_range=grid.point_cloud_range, device=dev)
+    res = ops.encode_stack(torch.from_numpy(g["points"]).to(dev), torch.from_numpy(g["frame_offsets"]).to(dev), grid,
+                           stack, with_bev=True)
+    m = int(res["pillar_count"][-1].item())
+    assert m == g["voxel_coords"].shape[0]
+    np.testing.assert_array_equal(res["voxel_coords"][:m].cpu().numpy(), g["voxel_coords"].astype(np.int32))
+    np.testing.assert_allclose(res["pillar_features"][:m].cpu().numpy(), g["out.pillar_features"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(res["bev"].cpu().numpy(), g["out.spatial_features"], rtol=1e-3, atol=1e-5)

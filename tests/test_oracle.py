@@ -115,6 +115,25 @@ def test_pillar_set_matches_reference_dynamic_vfe_golden(oracle):
     np.testing.assert_array_equal(v["num_points"][order], dcnt)
 
 
+DYN_GOLDENS = ["dyn_c5", "dyn_c5_2layer_zout", "dyn2d_c5_f32", "dyn_c4_dist_noabs"]
+
+
+@pytest.mark.parametrize("name", DYN_GOLDENS)
+def test_dynamic_vfe_restatement_matches_reference_golden(name, oracle):
+    """oracle.dynamic_pillar_vfe vs the reference's DynamicPillarVFE / DynamicPillarVFESimple2D outputs: coordinates and
+    row order bit-exact (z outliers included: the dynamic variants never range-check z), features to 1e-5."""
+    import torch
+
+    g = load_golden(name)
+    sd = {k: torch.from_numpy(v) for k, v in g["state_dict"].items()}
+    feats, coords, _ = oracle.dynamic_pillar_vfe(g["points_b"], sd, g["voxel_size"], g["range"],
+                                                 with_distance=bool(g["with_distance"]),
+                                                 use_absolute_xyz=bool(g["use_abs"]), simple2d=bool(g["simple2d"]))
+    np.testing.assert_array_equal(coords, g["out.voxel_coords"])
+    assert feats.shape == g["out.pillar_features"].shape
+    np.testing.assert_allclose(feats.numpy(), g["out.pillar_features"], rtol=1e-5, atol=1e-5)
+
+
 def test_live_reference_if_present(oracle):
     """In the build container re-run the reference module itself on a fresh random case (not a stored golden)."""
     from oracle import ref_loader
