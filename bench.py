@@ -122,6 +122,20 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def ncu_traffic(kernel_prefix: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/r01_traffic.json, taken on the default workload).  None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if workload != DEFAULT_WORKLOAD or not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        kernels = json.load(f).get("kernels", {})
+    for name, v in kernels.items():
+        if name.startswith(kernel_prefix):
+            return float(v["dram_bytes_read"]) + float(v["dram_bytes_write"])
+    return None
+
+
 def make_frames(workload: str, n_frames: int, seed0: int):
     from lidar_vision_vqa_b200 import synth
 
@@ -316,6 +330,25 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
     serial_ms = s1.elapsed_time(e1)
 
+    stage_ms = np.array([[e4[i].elapsed_time(e4[i + 1]) for i in range(3)] for e4 in evs])  # group, features, scatter
+
+    # ---- side measurement (not part of `value`): the same path with the canvas written as float16, the dtype the product's
+    #      extractor stores (src/get-data/precompute_bev_features.py:394); CUDA events around the scatter stage ---------------
+    half_ms = None
+    if (nx * ny) % 8 == 0:
+        buf16 = ops.EncodeBuffers(n_max, nb, grid, F_OUT, dev, bev_dtype=torch.float16)
+        for i in range(3):
+            ops.encode_bev(*dev_batches[i % rot], grid, pfn, buffers=buf16)
+        torch.cuda.synchronize()
+        n16 = min(K, 20)
+        for k in range(n16):
+            lib.pillars_set_stage_events(ev_arrays[k])
+            ops.encode_bev(*dev_batches[k % rot], grid, pfn, buffers=buf16)
+        lib.pillars_set_stage_events(None)
+        torch.cuda.synchronize()
+        half_ms = float(np.mean([evs[k][2].elapsed_time(evs[k][3]) for k in range(n16)]))
+        del buf16
+
     # ---- timed region 2 (the headline): the same K steps pipelined over n_streams streams ----------------------------
     split = n_streams > 1 and args.split
     for w in range(max(3, args.warmup)):  # warm the other streams' buffers
@@ -350,7 +383,6 @@ def run_b200(args, rank, world, local_rank):
         elapsed_ms, serial_ms = float(t[0].item()), float(t[1].item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
-    stage_ms = np.array([[e4[i].elapsed_time(e4[i + 1]) for i in range(3)] for e4 in evs])  # group, features, scatter
     stage_avg = stage_ms.mean(axis=0)
     ms_per_step = elapsed_ms / K
     serial_ms_per_step = serial_ms / K
@@ -361,7 +393,9 @@ def run_b200(args, rank, world, local_rank):
     ab = algorithmic_bytes(n_raw, n_kept, m_avg, 5, F_OUT, nx, ny, nb)
     scat_gbs = ab["S"] / (stage_avg[2] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "BEV scatter kernel (k_scatter_wide; dominant kernel of the step)",
-                "achieved": scat_gbs, "peak": peak, "unit": "GB/s", "frac": scat_gbs / peak, "traffic": None,
+                "achieved": scat_gbs, "peak": peak, "unit": "GB/s", "frac": scat_gbs / peak,
+                "traffic": ncu_traffic("k_scatter_wide", args.workload) if args.scatter_variant in ("auto", "wide") else None,
+                "traffic_source": "profiles/r01_traffic.json (ncu --set full, one launch, dram read + write bytes)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["S"],
                 "avg_launch_ms": float(stage_avg[2]), "share_of_step": float(stage_avg[2] / serial_ms_per_step),
                 "timed_in": "single-stream pass of the same K steps (kernels do not overlap there)"}
@@ -373,6 +407,7 @@ def run_b200(args, rank, world, local_rank):
         "features_frac_of_peak": ab["P"] / (stage_avg[1] * 1e-3) / 1e9 / peak,
         "path_frac_of_peak": (ab["V"] + ab["P"] + ab["S"]) / (ms_per_step * 1e-3) / 1e9 / peak,
         "algorithmic_bytes": ab, "points_raw": n_raw, "points_kept": n_kept, "pillars": m_avg,
+        "scatter_float16_canvas_ms": half_ms,
     }
 
     # ---- end to end through the reference-facing modules, inputs in pinned host memory ---------------------------

@@ -94,6 +94,8 @@ typedef struct pillars_outputs {
     int32_t *point_slot;      /* [n_points] slot inside the pillar, -1 if over the cap / rejected          */
     int32_t *pillar_count;    /* [n_frames + 1] pillars per frame, total in the last entry                 */
     float *bev;               /* [n_frames, F*nz, ny, nx]  batch_dict['spatial_features'] (encode_bev only) */
+    void *bev_half;           /* same canvas as IEEE float16 (round to nearest even), the dtype the product stores:
+                                 src/get-data/precompute_bev_features.py:394; may be given instead of or beside bev */
 } pillars_outputs_t;
 
 int pillars_abi_version(void);
@@ -139,6 +141,12 @@ int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_p
 int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
                         const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz, float *bev,
                         void *workspace, size_t workspace_bytes, int32_t variant, void *stream);
+
+/* PointPillarScatter.forward followed by the extractor's `.astype(np.float16)` (precompute_bev_features.py:394) in one
+ * pass: bev_half is [n_frames, f*nz, ny, nx] float16.  Needs nx*ny*nz % 8 == 0 and f % 8 == 0. */
+int pillars_scatter_bev_half(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
+                             const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz,
+                             void *bev_half, void *workspace, size_t workspace_bytes, void *stream);
 
 /* The fused path: raw points -> pillar features -> BEV.  Same grouping semantics as pillars_voxelize, same
  * feature semantics as pillars_pfn_dense on its output, same canvas as pillars_scatter_bev. */

@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "pillars_pfn_stack_in_features",
     "pillars_pfn_dense_stack",
     "pillars_encode_stack",
+    "pillars_scatter_bev_half",
 )
 
 ABI_VERSION = 2
@@ -55,7 +56,7 @@ class PillarsPfnStack(Structure):
 class PillarsOutputs(Structure):
     _fields_ = [("pillar_capacity", c_int64), ("pillar_features", c_void_p), ("voxel_coords", c_void_p),
                 ("voxel_num_points", c_void_p), ("voxels", c_void_p), ("point_pillar", c_void_p),
-                ("point_slot", c_void_p), ("pillar_count", c_void_p), ("bev", c_void_p)]
+                ("point_slot", c_void_p), ("pillar_count", c_void_p), ("bev", c_void_p), ("bev_half", c_void_p)]
 
 
 class NativeLibraryError(RuntimeError):
@@ -99,6 +100,9 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_scatter_bev.restype = c_int
     lib.pillars_scatter_bev.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
                                         c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_int32, c_void_p]
+    lib.pillars_scatter_bev_half.restype = c_int
+    lib.pillars_scatter_bev_half.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
+                                             c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.pillars_encode_bev.restype = c_int
     lib.pillars_encode_bev.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
                                        POINTER(PillarsPfn), POINTER(PillarsOutputs), c_void_p, c_size_t, c_int32,

@@ -182,7 +182,7 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
     if (pfn && (rc = check_pfn(pfn))) return rc;
     if (pfn && pfn->c_point != c_point) return fail(PILLARS_E_BADARG, "pfn->c_point != c_point");
     if (pfn && !out->pillar_features) return fail(PILLARS_E_BADARG, "pillar_features output is required");
-    if (want_bev && (!out->bev || !pfn)) return fail(PILLARS_E_BADARG, "bev output / pfn missing");
+    if (want_bev && ((!out->bev && !out->bev_half) || !pfn)) return fail(PILLARS_E_BADARG, "bev output / pfn missing");
     if (want_bev && grid->grid[2] != 1) return fail(PILLARS_E_UNSUPPORTED, "BEV scatter needs nz == 1");
     if (out->pillar_capacity < 0) return fail(PILLARS_E_BADARG, "pillar_capacity < 0");
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
@@ -271,9 +271,14 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
             if ((e = cudaEventRecord(g_scatter_event, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
             if ((e = cudaStreamWaitEvent(sst, g_scatter_event, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
         }
-        if ((e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, pfn->f_out, grid->grid[0], grid->grid[1],
+        if (out->bev &&
+            (e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, pfn->f_out, grid->grid[0], grid->grid[1],
                                 out->bev, scatter_variant, sst)) != cudaSuccess)
             return cuda_fail(e, "scatter");
+        if (out->bev_half &&
+            (e = launch_scatter_half(out->pillar_features, ws.cell_row, n_frames, pfn->f_out, grid->grid[0],
+                                     grid->grid[1], out->bev_half, sst)) != cudaSuccess)
+            return cuda_fail(e, "scatter (float16 canvas: needs nx*ny % 8 == 0, f % 8 == 0)");
     }
     stage_mark(3, st);
     g_launches_last = g_launches;
@@ -309,7 +314,7 @@ int pillars_encode_bev(const float *points, int64_t n, int32_t row_stride, int32
 {
     if (!pfn) return fail(PILLARS_E_BADARG, "pfn is NULL");
     return group_and_emit(points, n, row_stride, col0, pfn->c_point, frame_offsets, n_frames, grid, pfn, out, workspace,
-                          workspace_bytes, out && out->bev != nullptr, scatter_variant, stream);
+                          workspace_bytes, out && (out->bev != nullptr || out->bev_half != nullptr), scatter_variant, stream);
 }
 
 int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_points_is_float, const void *coords,
@@ -409,7 +414,7 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     if (out->voxels || out->point_pillar || out->point_slot)
         return fail(PILLARS_E_UNSUPPORTED, "membership outputs come from pillars_voxelize");
     const bool dynamic = mode == PILLARS_MODE_DYNAMIC;
-    const bool want_bev = out->bev != nullptr;
+    const bool want_bev = out->bev != nullptr || out->bev_half != nullptr;
     if (want_bev && (dynamic || grid->grid[2] != 1 || coords_cols != 4))
         return fail(PILLARS_E_UNSUPPORTED, "the fused BEV canvas needs mode HARD, nz == 1 and 4-column coords");
     if (out->pillar_capacity < 0) return fail(PILLARS_E_BADARG, "pillar_capacity < 0");
@@ -452,9 +457,12 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     stage_mark(2, st);
     if (want_bev) {
         const int f_last = sd.out[sd.n_layers - 1];
-        if ((e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, f_last, grid->grid[0], grid->grid[1], out->bev,
-                                scatter_variant, st)) != cudaSuccess)
+        if (out->bev && (e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, f_last, grid->grid[0],
+                                            grid->grid[1], out->bev, scatter_variant, st)) != cudaSuccess)
             return cuda_fail(e, "scatter");
+        if (out->bev_half && (e = launch_scatter_half(out->pillar_features, ws.cell_row, n_frames, f_last, grid->grid[0],
+                                                      grid->grid[1], out->bev_half, st)) != cudaSuccess)
+            return cuda_fail(e, "scatter (float16 canvas)");
     }
     stage_mark(3, st);
     g_launches_last = g_launches;
@@ -482,6 +490,32 @@ int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_i
     // the canvas of the 3-D variant is the 2-D one with nz*ny rows per channel
     if ((e = launch_scatter(feats, cell_row, n_frames, f, nx, ny * nz, bev, variant, st)) != cudaSuccess)
         return cuda_fail(e, "scatter");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_scatter_bev_half(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
+                             const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz,
+                             void *bev_half, void *workspace, size_t workspace_bytes, void *stream)
+{
+    g_launches = 0;
+    if (m < 0 || n_frames < 0 || f < 1 || nx < 1 || ny < 1 || nz < 1) return fail(PILLARS_E_BADARG, "pillars_scatter_bev_half: bad size");
+    if (n_frames > 0 && !bev_half) return fail(PILLARS_E_BADARG, "bev_half is NULL");
+    if (m > 0 && (!feats || !coords)) return fail(PILLARS_E_BADARG, "feats / coords NULL");
+    if (m > 0 && reinterpret_cast<uintptr_t>(coords) % 16 != 0) return fail(PILLARS_E_BADARG, "coords must be 16-byte aligned");
+    if ((static_cast<int64_t>(nx) * ny * nz) % 8 != 0 || f % 8 != 0)
+        return fail(PILLARS_E_UNSUPPORTED, "float16 canvas needs nx*ny*nz %% 8 == 0 and f %% 8 == 0");
+    const size_t need = sizeof(int32_t) * static_cast<size_t>(n_frames) * nx * ny * nz;
+    if (need > 0 && (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 16 != 0))
+        return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+    if (n_frames == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t *cell_row = static_cast<int32_t *>(workspace);
+    cudaError_t e;
+    if ((e = launch_build_cell_row(coords, coords_is_float != 0, m, m_dev, n_frames, nx, ny, nz, cell_row, st)) != cudaSuccess)
+        return cuda_fail(e, "build_cell_row");
+    if ((e = launch_scatter_half(feats, cell_row, n_frames, f, nx, ny * nz, bev_half, st)) != cudaSuccess)
+        return cuda_fail(e, "scatter (float16 canvas)");
     g_launches_last = g_launches;
     return 0;
 }

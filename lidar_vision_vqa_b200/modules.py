@@ -40,6 +40,16 @@ def _cfg_get(cfg, key, default=_MISSING):
     return default
 
 
+def _dtype_of(name) -> torch.dtype:
+    if isinstance(name, torch.dtype):
+        return name
+    table = {"float32": torch.float32, "fp32": torch.float32, "float16": torch.float16, "fp16": torch.float16,
+             "half": torch.float16}
+    if str(name) not in table:
+        raise ValueError(f"OUT_DTYPE {name!r}: float32 or float16")
+    return table[str(name)]
+
+
 def _points_on_device(points: torch.Tensor) -> torch.Tensor:
     """A host batch (pinned or not) is copied as part of the call; without a GPU the call fails loudly."""
     if not points.is_cuda:
@@ -322,6 +332,9 @@ class PointPillarScatter(nn.Module):
         self.nx, self.ny, self.nz = (int(v) for v in np.asarray(grid_size).tolist())
         assert self.nz == 1
         self.variant = str(_cfg_get(model_cfg, "SCATTER_VARIANT", "auto"))
+        # optional: 'float16' writes the canvas in the dtype the product's extractor stores
+        # (src/get-data/precompute_bev_features.py:394); the default float32 is the reference module's output
+        self.out_dtype = _dtype_of(_cfg_get(model_cfg, "OUT_DTYPE", "float32"))
 
     def forward(self, batch_dict, **kwargs):
         if batch_dict.get("_b200_scatter_done", False) and "spatial_features" in batch_dict:
@@ -334,7 +347,7 @@ class PointPillarScatter(nn.Module):
         if feats.shape[-1] != self.num_bev_features:
             raise ValueError(f"pillar_features have {feats.shape[-1]} channels, NUM_BEV_FEATURES={self.num_bev_features}")
         batch_dict["spatial_features"] = ops.scatter_bev(feats, coords, batch_size, self.nx, self.ny,
-                                                         variant=self.variant)
+                                                         variant=self.variant, out_dtype=self.out_dtype)
         return batch_dict
 
 

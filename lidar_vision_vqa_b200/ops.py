@@ -352,9 +352,10 @@ def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSp
 
 def scatter_bev(pillar_features: torch.Tensor, coords: torch.Tensor, batch_size: int, nx: int, ny: int, nz: int = 1, *,
                 m_dev: Optional[torch.Tensor] = None, variant: str = "auto", ws_slot: int = 0,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """PointPillarScatter.forward: ``[B, F, ny, nx]`` float32, zero where no pillar; with ``nz > 1`` the 3-D variant
-    (PointPillarScatter3d, pointpillar_scatter.py:40-73): ``[B, F*nz, ny, nx]``."""
+    (PointPillarScatter3d, pointpillar_scatter.py:40-73): ``[B, F*nz, ny, nx]``.  ``out_dtype=torch.float16`` fuses the
+    extractor's ``astype(np.float16)`` (src/get-data/precompute_bev_features.py:394) into the same pass."""
     _require_device(pillar_features)
     feats = pillar_features.reshape(-1, pillar_features.shape[-1]).contiguous()
     if feats.dtype != torch.float32:
@@ -365,9 +366,18 @@ def scatter_bev(pillar_features: torch.Tensor, coords: torch.Tensor, batch_size:
     else:
         crd, crd_f = coords.to(torch.int32).contiguous(), 0
     dev = feats.device
-    bev = out if out is not None else torch.empty((batch_size, f * nz, ny, nx), dtype=torch.float32, device=dev)
+    if out_dtype not in (torch.float32, torch.float16):
+        raise ValueError("out_dtype must be float32 or float16")
+    bev = out if out is not None else torch.empty((batch_size, f * nz, ny, nx), dtype=out_dtype, device=dev)
+    if bev.dtype != out_dtype:
+        raise ValueError("out has the wrong dtype")
     need = 4 * batch_size * nx * ny * nz
     ws = workspace(need, dev, ws_slot)
+    if out_dtype == torch.float16:
+        check(_native.load().pillars_scatter_bev_half(feats.data_ptr(), crd.data_ptr(), crd_f, m, _ptr(m_dev), batch_size,
+                                                      f, nx, ny, nz, bev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                      _stream_ptr()), "pillars_scatter_bev_half")
+        return bev
     check(_native.load().pillars_scatter_bev(feats.data_ptr(), crd.data_ptr(), crd_f, m, _ptr(m_dev), batch_size, f, nx,
                                              ny, nz, bev.data_ptr(), ws.data_ptr(), ws.numel(), SCATTER_VARIANTS[variant],
                                              _stream_ptr()), "pillars_scatter_bev")
@@ -379,7 +389,7 @@ class EncodeBuffers:
     traffic inside a timed loop)."""
 
     def __init__(self, n_points: int, n_frames: int, grid: GridSpec, f_out: int, device, *, with_bev: bool = True,
-                 capacity: Optional[int] = None, ws_slot: int = 0):
+                 capacity: Optional[int] = None, ws_slot: int = 0, bev_dtype: torch.dtype = torch.float32):
         cap = min(n_points, n_frames * grid.max_voxels) if capacity is None else capacity
         nx, ny, nz = grid.grid_size
         self.capacity = cap
@@ -387,7 +397,7 @@ class EncodeBuffers:
         self.voxel_coords = torch.empty((cap, 4), dtype=torch.int32, device=device)
         self.voxel_num_points = torch.empty((cap,), dtype=torch.int32, device=device)
         self.pillar_count = torch.empty((n_frames + 1,), dtype=torch.int32, device=device)
-        self.bev = torch.empty((n_frames, f_out * nz, ny, nx), dtype=torch.float32, device=device) if with_bev else None
+        self.bev = torch.empty((n_frames, f_out * nz, ny, nx), dtype=bev_dtype, device=device) if with_bev else None
         g = grid.native()
         need = _native.load().pillars_workspace_bytes(n_points, n_frames, ctypes.byref(g))
         self.ws = torch.empty(need, dtype=torch.uint8, device=device)
@@ -426,7 +436,10 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
     if with_bev:
         if buffers.bev is None:
             raise ValueError("buffers were created without a BEV canvas")
-        out.bev = buffers.bev.data_ptr()
+        if buffers.bev.dtype == torch.float16:
+            out.bev_half = buffers.bev.data_ptr()
+        else:
+            out.bev = buffers.bev.data_ptr()
         res["bev"] = buffers.bev
     if want_membership:
         res["point_pillar"] = torch.empty((n,), dtype=torch.int32, device=dev)

@@ -23,10 +23,12 @@ from .modules import PillarVFEFromPoints
 
 
 class _Slot:
-    def __init__(self, n_frames: int, max_points: int, row: int, grid: ops.GridSpec, f_out: int, device, capacity):
+    def __init__(self, n_frames: int, max_points: int, row: int, grid: ops.GridSpec, f_out: int, device, capacity,
+                 bev_dtype=torch.float32):
         self.stream = torch.cuda.Stream(device=device)
         self.points = torch.empty((max_points, row), dtype=torch.float32, device=device)
-        self.buffers = ops.EncodeBuffers(max_points, n_frames, grid, f_out, device, capacity=capacity)
+        self.buffers = ops.EncodeBuffers(max_points, n_frames, grid, f_out, device, capacity=capacity,
+                                         bev_dtype=bev_dtype)
         self.counts_host = torch.empty((n_frames + 1,), dtype=torch.int32).pin_memory()
         self.done = torch.cuda.Event()
         self.n = 0
@@ -38,7 +40,8 @@ class PillarEncoderPipeline:
     """``depth`` batches in flight, each on its own stream with its own device buffers."""
 
     def __init__(self, vfe: PillarVFEFromPoints, n_frames: int, max_points: int, depth: int = 2,
-                 pillar_capacity: Optional[int] = None, scatter_variant: str = "auto"):
+                 pillar_capacity: Optional[int] = None, scatter_variant: str = "auto",
+                 bev_dtype: torch.dtype = torch.float32):
         dev = next(vfe.parameters()).device
         if dev.type != "cuda":
             raise ops.NativeLibraryError("PillarEncoderPipeline needs the module on a CUDA device")
@@ -50,8 +53,8 @@ class PillarEncoderPipeline:
         self.pfn = vfe._params(dev)
         self.scatter_variant = scatter_variant
         f_out = int(self.pfn.weight.shape[0])
-        self.slots: List[_Slot] = [_Slot(self.n_frames, max_points, self.row, self.grid, f_out, dev, pillar_capacity)
-                                   for _ in range(max(1, depth))]
+        self.slots: List[_Slot] = [_Slot(self.n_frames, max_points, self.row, self.grid, f_out, dev, pillar_capacity,
+                                         bev_dtype) for _ in range(max(1, depth))]
         self._next = 0
 
     def submit(self, points_host: torch.Tensor) -> int:

@@ -572,3 +572,83 @@ def test_general_kernel_agrees_with_single_layer_goldens(name, dev, L):
     np.testing.assert_array_equal(res["voxel_coords"][:m].cpu().numpy(), g["voxel_coords"].astype(np.int32))
     np.testing.assert_allclose(res["pillar_features"][:m].cpu().numpy(), g["out.pillar_features"], rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(res["bev"].cpu().numpy(), g["out.spatial_features"], rtol=1e-3, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# float16 canvas + the bulk extractor (src/get-data/precompute_bev_features.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["vfe_c5_p32_f32coords", "vfe_c4_p20_i32coords"])
+def test_half_canvas_equals_reference_astype_float16(name, dev, L):
+    """PointPillarScatter(OUT_DTYPE float16) on the reference's own pillar features == the reference canvas cast the way
+    the extractor casts it (precompute_bev_features.py:394 astype(np.float16)): bit-exact."""
+    g = load_golden(name)
+    sc = L.PointPillarScatter(model_cfg=C(NUM_BEV_FEATURES=64, OUT_DTYPE="float16"), grid_size=g["grid_size"])
+    bd = sc({"pillar_features": torch.from_numpy(g["out.pillar_features"]).to(dev),
+             "voxel_coords": torch.from_numpy(g["voxel_coords"]).to(dev), "batch_size": len(g["frame_offsets"]) - 1})
+    got = bd["spatial_features"]
+    assert got.dtype == torch.float16
+    want = g["out.spatial_features"].astype(np.float16)
+    np.testing.assert_array_equal(got.cpu().numpy().view(np.uint16), want.view(np.uint16))
+
+
+@pytest.mark.gpu
+def test_bev_extractor_matches_oracle_and_reference_file_format(dev, L, oracle, tmp_path):
+    """BevExtractor over 5 frames in batches of 2 (ragged last batch): per-token float16 [C,H,W] .npy files whose content
+    equals voxelise -> PillarVFE -> PointPillarScatter -> astype(float16) of the CPU oracle (fp16 of values within 1e-3)."""
+    from lidar_vision_vqa_b200 import synth
+    from lidar_vision_vqa_b200.extract import BevExtractor
+
+    rng, vs, p, mv = (-25.6, -25.6, -5.0, 25.6, 25.6, 3.0), (0.4, 0.4, 8.0), 16, 5000
+    frames = [synth.make_sweep(300 + i, synth.NUSCENES_32, 5)[:6000 + 500 * i] for i in range(5)]
+    sd = oracle.random_pfn_params(11, [64], True, seed=9)
+    cfg = C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64], MAX_POINTS_PER_VOXEL=p,
+            MAX_NUMBER_OF_VOXELS=mv)
+    grid_size = oracle.grid_size_of(rng, vs)
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=list(vs),
+                                point_cloud_range=np.asarray(rng, np.float32), grid_size=grid_size)
+    vfe.load_state_dict(sd)
+    vfe.eval().to(dev)
+    ex = BevExtractor(vfe, batch_size=2, max_points_per_frame=9000, depth=2)
+    items = [(f"tok{i:02d}", f) for i, f in enumerate(frames)]
+    n = ex.run_to_dir(items, str(tmp_path))
+    assert n == 5
+    nx, ny = int(grid_size[0]), int(grid_size[1])
+    for tok, f in items:
+        got = np.load(tmp_path / f"{tok}.npy")
+        assert got.dtype == np.float16 and got.shape == (64, ny, nx)
+        v = oracle.voxelize_hard(f, rng, vs, p, mv)
+        c4 = np.concatenate([np.zeros((len(v["coords"]), 1), np.int32), v["coords"]], 1)
+        feats = oracle.pillar_vfe(v["voxels"], v["num_points"], c4, sd, vs, rng).numpy()
+        ref = oracle.scatter_bev(feats, c4, nx, ny, batch_size=1)[0]
+        # occupancy pattern exact, values fp16(within 1e-3 of the reference)
+        np.testing.assert_array_equal(got != 0, ref.astype(np.float16) != 0)
+        np.testing.assert_allclose(got.astype(np.float32), ref, rtol=2e-3, atol=1e-3)
+    # generator form returns the same arrays in input order
+    toks = [t for t, _ in ex.run(items)]
+    assert toks == [t for t, _ in items]
+
+
+@pytest.mark.gpu
+def test_fused_half_canvas_is_the_cast_of_the_float_canvas(dev, L, oracle):
+    """encode_bev with a float16 canvas == float32 canvas of the same call cast with round-to-nearest-even."""
+    from lidar_vision_vqa_b200 import ops, synth
+
+    rng, vs = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), (0.2, 0.2, 8.0)
+    pts, offs = synth.make_batch(2, synth.NUSCENES_32, 5, seed0=21)
+    grid = L.GridSpec.from_range(rng, vs, 32, 30000)
+    sd = oracle.random_pfn_params(11, [64], True, seed=2)
+    pfn = ops.fold_pfn(sd["pfn_layers.0.linear.weight"],
+                       (sd["pfn_layers.0.norm.weight"], sd["pfn_layers.0.norm.bias"],
+                        sd["pfn_layers.0.norm.running_mean"], sd["pfn_layers.0.norm.running_var"], 1e-3), None,
+                       c_point=5, use_absolute_xyz=True, with_distance=False, voxel_size=vs, point_cloud_range=rng,
+                       device=dev)
+    p_d, o_d = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
+    b32 = ops.EncodeBuffers(len(pts), 2, grid, 64, dev)
+    b16 = ops.EncodeBuffers(len(pts), 2, grid, 64, dev, bev_dtype=torch.float16)
+    r32 = ops.encode_bev(p_d, o_d, grid, pfn, buffers=b32)
+    r16 = ops.encode_bev(p_d, o_d, grid, pfn, buffers=b16)
+    torch.cuda.synchronize()
+    assert r16["bev"].dtype == torch.float16
+    np.testing.assert_array_equal(r16["bev"].cpu().numpy().view(np.uint16),
+                                  r32["bev"].cpu().numpy().astype(np.float16).view(np.uint16))
