@@ -139,7 +139,8 @@ class _PillarVFEBase(VFETemplate):
                                "call .eval()")
 
     def _single_layer(self) -> bool:
-        return len(self.pfn_layers) == 1 and self.LAYOUT == 0
+        """What the streaming / single-layer kernels are instantiated for; everything else runs the general kernel."""
+        return len(self.pfn_layers) == 1 and self.LAYOUT == 0 and int(self.num_filters[-1]) == 64
 
     def _params(self, device) -> ops.PfnParams:
         """The single-layer form consumed by the streaming / dense kernels."""

@@ -323,6 +323,7 @@ def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSp
     cap = capacity
     if cap is None:
         cap = n if dynamic else min(n, nb * grid.max_voxels)
+    cap = max(int(cap), 1)  # an empty batch still needs non-NULL output pointers
     nx, ny, nz = grid.grid_size
     res = {
         "pillar_features": torch.empty((cap, stack.f_out), dtype=torch.float32, device=dev),

@@ -652,3 +652,87 @@ def test_fused_half_canvas_is_the_cast_of_the_float_canvas(dev, L, oracle):
     assert r16["bev"].dtype == torch.float16
     np.testing.assert_array_equal(r16["bev"].cpu().numpy().view(np.uint16),
                                   r32["bev"].cpu().numpy().astype(np.float16).view(np.uint16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("filters", [[64, 64], [32], [48, 40]])
+def test_general_kernel_vs_oracle_caps_binding(filters, dev, L, oracle):
+    """Two-layer / narrow stacks through the fused hard path where BOTH caps bind (P = 4 points per pillar, 150 pillars
+    per frame) and pillars far longer than the cap exist: grouping bit-exact, features rtol 1e-3 vs the CPU oracle
+    (pillar_vfe.py:44-49: the padded row is not re-masked between layers)."""
+    from lidar_vision_vqa_b200 import synth
+
+    rng, vs, p, mv = (-12.8, -12.8, -5.0, 12.8, 12.8, 3.0), (0.8, 0.8, 8.0), 4, 150
+    frames = [synth.make_sweep(500 + i, synth.NUSCENES_32, 5)[:5000] for i in range(3)]
+    frames[1] = frames[1][:0]  # an empty frame in the middle
+    offs = np.zeros(4, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    pts = np.concatenate(frames, 0)
+    sd = oracle.random_pfn_params(11, filters, True, seed=3)
+    cfg = C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=filters, MAX_POINTS_PER_VOXEL=p,
+            MAX_NUMBER_OF_VOXELS=mv, FUSE_SCATTER=True)
+    grid_size = oracle.grid_size_of(rng, vs)
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=list(vs),
+                                point_cloud_range=np.asarray(rng, np.float32), grid_size=grid_size)
+    vfe.load_state_dict(sd)
+    vfe.eval().to(dev)
+    bd = vfe({"points": torch.from_numpy(synth.to_pcdet_points(pts, offs)).to(dev), "batch_size": 3})
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    assert ref["num_points"].max() == p and (ref["pillars_per_frame"] == [mv, 0, mv]).all()
+    np.testing.assert_array_equal(bd["voxel_coords"].cpu().numpy(), ref["coords"])
+    np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), ref["num_points"])
+    ref_f = oracle.pillar_vfe(ref["voxels"], ref["num_points"], ref["coords"], sd, vs, rng).numpy()
+    np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), ref_f, rtol=1e-3, atol=1e-5)
+    ref_bev = oracle.scatter_bev(bd["pillar_features"].cpu().numpy(), ref["coords"], int(grid_size[0]), int(grid_size[1]),
+                                 batch_size=3)
+    np.testing.assert_array_equal(bd["spatial_features"].cpu().numpy(), ref_bev)
+    # the same stack on the reference's padded voxels (hard module) gives the same rows
+    hard = L.PillarVFE(model_cfg=C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=filters),
+                       num_point_features=5, voxel_size=list(vs), point_cloud_range=np.asarray(rng, np.float32),
+                       grid_size=grid_size)
+    hard.load_state_dict(sd)
+    hard.eval().to(dev)
+    bd2 = hard({"voxels": torch.from_numpy(ref["voxels"]).to(dev),
+                "voxel_num_points": torch.from_numpy(ref["num_points"]).to(dev).float(),
+                "voxel_coords": torch.from_numpy(ref["coords"]).to(dev).float()})
+    np.testing.assert_allclose(bd2["pillar_features"].cpu().numpy(), ref_f, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("simple", [False, True])
+def test_dynamic_vfe_vs_oracle_edge_cases(simple, dev, L, oracle):
+    """Dynamic variants against the CPU restatement on a fresh case: an empty frame, a frame whose points all lie outside
+    x/y, one pillar holding thousands of points (no cap), points far outside z, and an empty batch."""
+    from lidar_vision_vqa_b200 import synth
+
+    rng, vs = (-20.0, -20.0, -5.0, 20.0, 20.0, 3.0), (0.5, 0.5, 8.0)
+    r = np.random.default_rng(11)
+    f0 = synth.make_sweep(700, synth.NUSCENES_32, 5)[:4000]
+    f0[::5, 2] += 30.0
+    f1 = f0[:0]
+    f2 = f0[:300].copy()
+    f2[:, :2] += 500.0  # nothing in range
+    f3 = np.concatenate([np.tile(np.array([[1.23, -4.56, 0.1, 7.0, 0.0]], np.float32), (3000, 1)) +
+                         r.normal(0, 0.01, (3000, 5)).astype(np.float32), f0[:500]], 0)
+    frames = [f0, f1, f2, f3]
+    offs = np.zeros(5, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    pb = synth.to_pcdet_points(np.concatenate(frames, 0), offs)
+    filters = [32] if simple else [64, 64]
+    c_in = 8 if simple else 11
+    sd = oracle.random_pfn_params(c_in, filters, True, seed=5)
+    cls = L.DynamicPillarVFESimple2D if simple else L.DynamicPillarVFE
+    vfe = cls(model_cfg=C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=filters),
+              num_point_features=5, voxel_size=list(vs), grid_size=oracle.grid_size_of(rng, vs),
+              point_cloud_range=np.asarray(rng, np.float32))
+    vfe.load_state_dict(sd)
+    vfe.eval().to(dev)
+    bd = vfe({"points": torch.from_numpy(pb).to(dev), "batch_size": 4})
+    ref_f, ref_c, ref_n = oracle.dynamic_pillar_vfe(pb, sd, vs, rng, simple2d=simple)
+    key = "pillar_coords" if simple else "voxel_coords"
+    np.testing.assert_array_equal(bd[key].cpu().numpy(), ref_c)
+    np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), ref_n)
+    assert ref_n.max() >= 3000
+    np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), ref_f.numpy(), rtol=1e-3, atol=1e-5)
+    empty = vfe({"points": torch.zeros((0, 6), device=dev), "batch_size": 2})
+    assert empty["pillar_features"].shape == (0, filters[-1]) and empty[key].shape[0] == 0
