@@ -20,6 +20,8 @@
 // the max of layer 0, then layer 1 on [x, max]) and layer 0 is recomputed instead of stored, so pillars of any length
 // (the dynamic variant has no cap) need no scratch.  Not the headline kernel: it exists for coverage and is bound by
 // shared-memory traffic; the mainstream single-layer configuration runs pfn_stream.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pillars {
@@ -91,46 +93,35 @@ __device__ __forceinline__ float warp_sum_f32(float v)
     return v;
 }
 
-__global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ MultiParams p)
+struct PillarCtx {
+    Pillar pi;
+    const float *vox;   // dense source: the pillar's padded rows
+    bool compact;       // kept point indices were compacted into the warp's shared list
+    uint32_t n_iter;    // list entries (or rows) to visit
+    float mx, my, mz;   // mean of the kept points
+    float cx, cy, cz;   // pillar centre
+};
+
+// t-th list entry of the pillar -> pointer to the point's channels, or NULL when the entry is beyond the first-P cap
+__device__ __forceinline__ const float *pillar_point(const MultiParams &p, const PillarCtx &c, const uint32_t *keep, uint32_t t)
 {
-    __shared__ float s_w0[kMaxIn0][kMaxOut];
-    __shared__ float s_w1[kMaxIn1][kMaxOut];
-    __shared__ float s_sc[2][kMaxOut], s_sh[2][kMaxOut];
-    __shared__ float s_f[kWarps][kMaxOut];          // feature / activation exchange of a warp
-    __shared__ uint32_t s_keep[kWarps][kKeepMax];   // kept point indices of a long capped pillar
+    if (p.dense) return c.vox + static_cast<int64_t>(t) * p.c_point;
+    const uint32_t idx = c.compact ? keep[t] : p.sorted_idx[c.pi.list + t];
+    if (idx > c.pi.thr) return nullptr;
+    return p.points + static_cast<int64_t>(idx) * p.stride + p.col0;
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int in1 = 2 * p.out0;
-    for (int i = tid; i < kMaxIn0 * kMaxOut; i += kThreads) {
-        const int k = i / kMaxOut, o = i % kMaxOut;
-        s_w0[k][o] = (k < p.c_in && o < p.out0) ? p.w0[o * p.c_in + k] : 0.f;
-    }
-    for (int i = tid; i < kMaxIn1 * kMaxOut; i += kThreads) {
-        const int k = i / kMaxOut, o = i % kMaxOut;
-        s_w1[k][o] = (p.n_layers > 1 && k < in1 && o < p.out1) ? p.w1[o * in1 + k] : 0.f;
-    }
-    for (int o = tid; o < kMaxOut; o += kThreads) {
-        s_sc[0][o] = o < p.out0 ? p.s0[o] : 0.f;
-        s_sh[0][o] = o < p.out0 ? p.h0[o] : 0.f;
-        s_sc[1][o] = (p.n_layers > 1 && o < p.out1) ? p.s1[o] : 0.f;
-        s_sh[1][o] = (p.n_layers > 1 && o < p.out1) ? p.h1[o] : 0.f;
-    }
-    __syncthreads();
-
-    const int f_last = p.n_layers > 1 ? p.out1 : p.out0;
-    const int my_kind = lane < p.c_in ? p.kind[lane < kMaxIn0 ? lane : 0] : -1;
-    const int my_arg = lane < p.c_in ? p.arg[lane < kMaxIn0 ? lane : 0] : 0;
-    float *const fbuf = s_f[warp];
-    uint32_t *const keep = s_keep[warp];
-    const int64_t total = p.dense ? p.m : static_cast<int64_t>(p.hdr->total_pillars);
-    const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kWarps;
+// Everything about pillar g that does not depend on the feature stack (warp-uniform): row, coordinates, the kept subset
+// under the first-P rule, mean, centre.  Returns false for a pillar that produces no output.  All 32 lanes must call.
+__device__ __forceinline__ bool prepare_pillar(const MultiParams &p, int64_t g, int lane, uint32_t *keep, PillarCtx &c)
+{
     const uint32_t P = static_cast<uint32_t>(p.max_points);
-
-    for (int64_t g = static_cast<int64_t>(blockIdx.x) * kWarps + warp; g < total; g += warp_stride) {
+    {
         // ---- resolve the pillar (warp-uniform) -----------------------------------------------------------------------
-        Pillar pi{};
+        Pillar &pi = c.pi;
+        pi = Pillar{};
         pi.thr = 0xFFFFFFFFu;
-        const float *vox = nullptr;
+        c.vox = nullptr;
         if (p.dense) {
             int n;
             if (p.np_float) {
@@ -153,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ 
             pi.n_all = pi.n_keep;
             pi.row = g;
             pi.live = true;
-            vox = p.voxels + g * static_cast<int64_t>(P) * p.c_point;
+            c.vox = p.voxels + g * static_cast<int64_t>(P) * p.c_point;
         } else {
             const uint32_t key = p.pillar_key[g];
             pi.list = p.pillar_list[g];
@@ -196,10 +187,10 @@ __global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ 
             }
             pi.nf = static_cast<float>(pi.n_keep);
         }
-        if (!pi.live) continue;
+        if (!pi.live) return false;
 
         // a capped pillar much longer than the cap: compact the kept indices once instead of filtering in every pass
-        bool compact = false;
+        c.compact = false;
         if (!p.dense && !p.dynamic && pi.n_all > P && pi.n_all > 64 && P <= static_cast<uint32_t>(kKeepMax)) {
             uint32_t base = 0;
             for (uint32_t j0 = 0; j0 < pi.n_all; j0 += 32) {
@@ -212,18 +203,16 @@ __global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ 
                 base += __popc(bal);
             }
             __syncwarp();
-            compact = true;
+            c.compact = true;
         }
-        const uint32_t n_iter = p.dense ? pi.n_keep : (compact ? pi.n_keep : pi.n_all);
-        auto point_at = [&](uint32_t t) -> const float * {
-            if (p.dense) return vox + static_cast<int64_t>(t) * p.c_point;
-            const uint32_t idx = compact ? keep[t] : p.sorted_idx[pi.list + t];
-            if (idx > pi.thr) return nullptr;
-            return p.points + static_cast<int64_t>(idx) * p.stride + p.col0;
-        };
+        c.n_iter = p.dense ? pi.n_keep : (c.compact ? pi.n_keep : pi.n_all);
+        const uint32_t n_iter = c.n_iter;
+        const float *vox = c.vox;
+        auto point_at = [&](uint32_t t) -> const float * { return pillar_point(p, c, keep, t); };
 
         // ---- mean of the pillar (pillar_vfe.py:97 / scatter_mean, dynamic_pillar_vfe.py:105) --------------------------
-        float mx = 0.f, my = 0.f, mz = 0.f;
+        float &mx = c.mx, &my = c.my, &mz = c.mz;
+        mx = my = mz = 0.f;
         {
             if (p.dense) {  // the reference sums ALL P slots in fp32, whatever the padding holds
                 float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -250,9 +239,56 @@ __global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ 
             }
         }
         // pillar centre: coord * voxel + offset, two roundings (pillar_vfe.py:100-103; dynamic_pillar_vfe.py:109-111)
-        const float cx = __fadd_rn(__fmul_rn(static_cast<float>(pi.x), p.vsz[0]), p.off[0]);
-        const float cy = __fadd_rn(__fmul_rn(static_cast<float>(pi.y), p.vsz[1]), p.off[1]);
-        const float cz = p.dynamic ? p.off[2] : __fadd_rn(__fmul_rn(static_cast<float>(pi.z), p.vsz[2]), p.off[2]);
+        c.cx = __fadd_rn(__fmul_rn(static_cast<float>(pi.x), p.vsz[0]), p.off[0]);
+        c.cy = __fadd_rn(__fmul_rn(static_cast<float>(pi.y), p.vsz[1]), p.off[1]);
+        c.cz = p.dynamic ? p.off[2] : __fadd_rn(__fmul_rn(static_cast<float>(pi.z), p.vsz[2]), p.off[2]);
+
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ MultiParams p)
+{
+    __shared__ float s_w0[kMaxIn0][kMaxOut];
+    __shared__ float s_w1[kMaxIn1][kMaxOut];
+    __shared__ float s_sc[2][kMaxOut], s_sh[2][kMaxOut];
+    __shared__ float s_f[kWarps][kMaxOut];          // feature / activation exchange of a warp
+    __shared__ uint32_t s_keep[kWarps][kKeepMax];   // kept point indices of a long capped pillar
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int in1 = 2 * p.out0;
+    for (int i = tid; i < kMaxIn0 * kMaxOut; i += kThreads) {
+        const int k = i / kMaxOut, o = i % kMaxOut;
+        s_w0[k][o] = (k < p.c_in && o < p.out0) ? p.w0[o * p.c_in + k] : 0.f;
+    }
+    for (int i = tid; i < kMaxIn1 * kMaxOut; i += kThreads) {
+        const int k = i / kMaxOut, o = i % kMaxOut;
+        s_w1[k][o] = (p.n_layers > 1 && k < in1 && o < p.out1) ? p.w1[o * in1 + k] : 0.f;
+    }
+    for (int o = tid; o < kMaxOut; o += kThreads) {
+        s_sc[0][o] = o < p.out0 ? p.s0[o] : 0.f;
+        s_sh[0][o] = o < p.out0 ? p.h0[o] : 0.f;
+        s_sc[1][o] = (p.n_layers > 1 && o < p.out1) ? p.s1[o] : 0.f;
+        s_sh[1][o] = (p.n_layers > 1 && o < p.out1) ? p.h1[o] : 0.f;
+    }
+    __syncthreads();
+
+    const int f_last = p.n_layers > 1 ? p.out1 : p.out0;
+    const int my_kind = lane < p.c_in ? p.kind[lane < kMaxIn0 ? lane : 0] : -1;
+    const int my_arg = lane < p.c_in ? p.arg[lane < kMaxIn0 ? lane : 0] : 0;
+    float *const fbuf = s_f[warp];
+    uint32_t *const keep = s_keep[warp];
+    const int64_t total = p.dense ? p.m : static_cast<int64_t>(p.hdr->total_pillars);
+    const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kWarps;
+    const uint32_t P = static_cast<uint32_t>(p.max_points);
+
+    for (int64_t g = static_cast<int64_t>(blockIdx.x) * kWarps + warp; g < total; g += warp_stride) {
+        PillarCtx ctx;
+        if (!prepare_pillar(p, g, lane, keep, ctx)) continue;
+        const Pillar &pi = ctx.pi;
+        const uint32_t n_iter = ctx.n_iter;
+        const float mx = ctx.mx, my = ctx.my, mz = ctx.mz, cx = ctx.cx, cy = ctx.cy, cz = ctx.cz;
+        auto point_at = [&](uint32_t t) -> const float * { return pillar_point(p, ctx, keep, t); };
 
         // the first C_in lanes build one augmented feature each; every lane then reads all of them
         auto features_to_buf = [&](const float *q) {
@@ -384,6 +420,232 @@ __global__ void __launch_bounds__(kThreads) k_pfn_multi(const __grid_constant__ 
                     static_cast<int32_t>(pi.row);
         }
     }
+}
+
+// ---- the common shapes, register resident -------------------------------------------------------------------------------
+// USE_ABSLOTE_XYZ, no WITH_DISTANCE, C point channels known at compile time: every lane builds the whole augmented feature
+// vector itself from one broadcast load of the point (no exchange), layer 0's weights for the lane's channels sit in
+// registers, and so do layer 1's (32 inputs x the channel pair {lane, lane + 32} = 64 registers, consumed by packed
+// FFMA2).  Layer 0's outputs travel to layer 1 through a 128-byte per-warp buffer read back as eight 16-byte broadcasts.
+//   LAYOUT 0: [point, point_xyz - mean, point_xyz - centre]     LAYOUT 1 (Simple2D): [point_xyz - centre, point]
+__device__ __forceinline__ unsigned long long pk2(float a, float b)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void ffma2_bcast(unsigned long long &acc, unsigned long long w, float x)
+{
+    unsigned long long rx;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rx) : "f"(x));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(rx));
+}
+
+template <int C, int LAYOUT, bool TWO>
+__global__ void __launch_bounds__(kThreads, 2) k_pfn_multi_reg(const __grid_constant__ MultiParams p)
+{
+    constexpr int kCin = LAYOUT == 1 ? C + 3 : C + 6;
+    __shared__ float s_w1k[32][kMaxOut];             // layer 1, inputs out0..2*out0-1 (the pillar-max half), [k][channel]
+    __shared__ __align__(16) float s_x[kWarps][32];  // layer 0 outputs of the current point
+    __shared__ uint32_t s_keep[kWarps][kKeepMax];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int out0 = p.out0, out1 = p.out1;
+    if (TWO) {
+        for (int i = tid; i < 32 * kMaxOut; i += kThreads) {
+            const int k = i / kMaxOut, o = i % kMaxOut;
+            s_w1k[k][o] = (k < out0 && o < out1) ? p.w1[o * (2 * out0) + out0 + k] : 0.f;
+        }
+    }
+    // layer 0: channels lane (a) and lane + 32 (b; only single-layer stacks are wider than 32)
+    float w0a[kCin], w0b[kCin];
+#pragma unroll
+    for (int k = 0; k < kCin; ++k) {
+        w0a[k] = lane < out0 ? __ldg(p.w0 + lane * kCin + k) : 0.f;
+        w0b[k] = (!TWO && lane + 32 < out0) ? __ldg(p.w0 + (lane + 32) * kCin + k) : 0.f;
+    }
+    const float s0a = lane < out0 ? __ldg(p.s0 + lane) : 0.f, h0a = lane < out0 ? __ldg(p.h0 + lane) : 0.f;
+    const float s0b = (!TWO && lane + 32 < out0) ? __ldg(p.s0 + lane + 32) : 0.f;
+    const float h0b = (!TWO && lane + 32 < out0) ? __ldg(p.h0 + lane + 32) : 0.f;
+    // layer 1: inputs 0..out0-1 (the per-point half) for the channel pair {lane, lane + 32}
+    unsigned long long w1[TWO ? 32 : 1];
+    float s1a = 0.f, h1a = 0.f, s1b = 0.f, h1b = 0.f;
+    if (TWO) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float a = (k < out0 && lane < out1) ? __ldg(p.w1 + lane * (2 * out0) + k) : 0.f;
+            const float b = (k < out0 && lane + 32 < out1) ? __ldg(p.w1 + (lane + 32) * (2 * out0) + k) : 0.f;
+            w1[k] = pk2(a, b);
+        }
+        if (lane < out1) { s1a = __ldg(p.s1 + lane); h1a = __ldg(p.h1 + lane); }
+        if (lane + 32 < out1) { s1b = __ldg(p.s1 + lane + 32); h1b = __ldg(p.h1 + lane + 32); }
+    }
+    __syncthreads();
+
+    const int f_last = TWO ? out1 : out0;
+    float *const xbuf = s_x[warp];
+    uint32_t *const keep = s_keep[warp];
+    const int64_t total = p.dense ? p.m : static_cast<int64_t>(p.hdr->total_pillars);
+    const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kWarps;
+    const uint32_t P = static_cast<uint32_t>(p.max_points);
+
+    for (int64_t g = static_cast<int64_t>(blockIdx.x) * kWarps + warp; g < total; g += warp_stride) {
+        PillarCtx ctx;
+        if (!prepare_pillar(p, g, lane, keep, ctx)) continue;
+        const Pillar &pi = ctx.pi;
+        const uint32_t n_iter = ctx.n_iter;
+        const bool pad_row = !p.dynamic && pi.n_keep < P;  // one all-zero row stands for every padded slot
+
+        // layer 0 of one point for the lane's channels (pre-activation sums)
+        auto layer0 = [&](const float *q, float &ya, float &yb) {
+            float pt[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) pt[c] = __ldg(q + c);
+            float f[kCin];
+            if (LAYOUT == 1) {
+                f[0] = __fsub_rn(pt[0], ctx.cx); f[1] = __fsub_rn(pt[1], ctx.cy); f[2] = __fsub_rn(pt[2], ctx.cz);
+#pragma unroll
+                for (int c = 0; c < C; ++c) f[3 + c] = pt[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) f[c] = pt[c];
+                f[C + 0] = __fsub_rn(pt[0], ctx.mx); f[C + 1] = __fsub_rn(pt[1], ctx.my); f[C + 2] = __fsub_rn(pt[2], ctx.mz);
+                f[C + 3] = __fsub_rn(pt[0], ctx.cx); f[C + 4] = __fsub_rn(pt[1], ctx.cy); f[C + 5] = __fsub_rn(pt[2], ctx.cz);
+            }
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < kCin; ++k) {
+                a = fmaf(f[k], w0a[k], a);
+                if (!TWO) b = fmaf(f[k], w0b[k], b);
+            }
+            ya = fmaxf(fmaf(a, s0a, h0a), 0.f);
+            yb = fmaxf(fmaf(b, s0b, h0b), 0.f);
+        };
+
+        float out_a, out_b;
+        if (!TWO) {
+            float best_a = -INFINITY, best_b = -INFINITY;
+            for (uint32_t t = 0; t < n_iter; ++t) {
+                const float *q = pillar_point(p, ctx, keep, t);
+                if (!q) continue;
+                float ya, yb;
+                layer0(q, ya, yb);
+                best_a = fmaxf(best_a, ya);
+                best_b = fmaxf(best_b, yb);
+            }
+            if (pad_row) {
+                best_a = fmaxf(best_a, fmaxf(h0a, 0.f));
+                best_b = fmaxf(best_b, fmaxf(h0b, 0.f));
+            }
+            out_a = best_a;
+            out_b = best_b;
+        } else {
+            // pass A: pillar-wise max of layer 0
+            float xmax = -INFINITY;
+            for (uint32_t t = 0; t < n_iter; ++t) {
+                const float *q = pillar_point(p, ctx, keep, t);
+                if (!q) continue;
+                float ya, yb;
+                layer0(q, ya, yb);
+                xmax = fmaxf(xmax, ya);
+            }
+            const float xpad = fmaxf(h0a, 0.f);
+            if (pad_row) xmax = fmaxf(xmax, xpad);
+            // constant half of layer 1's input: W1[:, out0:] . xmax
+            xbuf[lane] = lane < out0 ? xmax : 0.f;
+            __syncwarp();
+            float ka = 0.f, kb = 0.f;
+            for (int k = 0; k < out0; ++k) {
+                const float f = xbuf[k];
+                ka = fmaf(f, s_w1k[k][lane], ka);
+                kb = fmaf(f, s_w1k[k][lane + 32], kb);
+            }
+            __syncwarp();
+            const unsigned long long kacc = pk2(ka, kb);
+            auto layer1 = [&](float x, float &ya, float &yb) {
+                xbuf[lane] = x;  // lanes >= out0 carry 0 (zero weights, zero scale and shift)
+                __syncwarp();
+                unsigned long long acc = kacc;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(xbuf + 4 * k4);
+                    ffma2_bcast(acc, w1[4 * k4 + 0], xv.x);
+                    ffma2_bcast(acc, w1[4 * k4 + 1], xv.y);
+                    ffma2_bcast(acc, w1[4 * k4 + 2], xv.z);
+                    ffma2_bcast(acc, w1[4 * k4 + 3], xv.w);
+                }
+                float a, b;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(acc));
+                ya = fmaxf(fmaf(a, s1a, h1a), 0.f);
+                yb = fmaxf(fmaf(b, s1b, h1b), 0.f);
+                __syncwarp();
+            };
+            // pass B: layer 0 again, then layer 1 on [x, xmax]
+            float best_a = -INFINITY, best_b = -INFINITY;
+            for (uint32_t t = 0; t < n_iter; ++t) {
+                const float *q = pillar_point(p, ctx, keep, t);
+                if (!q) continue;
+                float xa, xb, ya, yb;
+                layer0(q, xa, xb);
+                layer1(xa, ya, yb);
+                best_a = fmaxf(best_a, ya);
+                best_b = fmaxf(best_b, yb);
+            }
+            if (pad_row) {
+                float ya, yb;
+                layer1(xpad, ya, yb);
+                best_a = fmaxf(best_a, ya);
+                best_b = fmaxf(best_b, yb);
+            }
+            out_a = best_a;
+            out_b = best_b;
+        }
+
+        float *dst = p.pillar_features + pi.row * f_last;
+        if (lane < f_last) dst[lane] = out_a;
+        if (lane + 32 < f_last) dst[lane + 32] = out_b;
+        if (lane == 0 && !p.dense) {
+            if (p.voxel_coords) {
+                if (p.coords_cols == 3) {
+                    int32_t *c = p.voxel_coords + pi.row * 3;
+                    c[0] = pi.b; c[1] = pi.y; c[2] = pi.x;
+                } else {
+                    *reinterpret_cast<int4 *>(p.voxel_coords + pi.row * 4) = make_int4(pi.b, p.dynamic ? 0 : pi.z, pi.y, pi.x);
+                }
+            }
+            if (p.voxel_num_points) p.voxel_num_points[pi.row] = static_cast<int32_t>(pi.n_keep);
+            if (p.cell_row)
+                p.cell_row[static_cast<int64_t>(pi.b) * p.gd.cells_xy + static_cast<int64_t>(pi.y) * p.gd.g[0] + pi.x] =
+                    static_cast<int32_t>(pi.row);
+        }
+    }
+}
+
+// picks the register-resident kernel when the configuration is one of its instantiations, else the general one
+bool launch_reg_variant(const MultiParams &p, const StackDev &sd, unsigned blocks, cudaStream_t st)
+{
+    static int off = -1;
+    if (off < 0) {
+        const char *e = getenv("PILLARS_MULTI_GENERIC");
+        off = e ? atoi(e) : 0;
+    }
+    if (off || !sd.use_abs || sd.with_dist) return false;
+    if (reinterpret_cast<uintptr_t>(p.points) % 4 != 0) return false;
+    const bool two = sd.n_layers == 2;
+    if (two && (sd.out[0] > 32 || sd.out[1] > 64)) return false;
+    if (!two && sd.out[0] > 64) return false;
+#define PILLARS_REG_CASE(CC, LL)                                                              \
+    if (p.c_point == CC && sd.layout == LL) {                                                 \
+        if (two) k_pfn_multi_reg<CC, LL, true><<<blocks, kThreads, 0, st>>>(p);               \
+        else k_pfn_multi_reg<CC, LL, false><<<blocks, kThreads, 0, st>>>(p);                  \
+        return true;                                                                          \
+    }
+    PILLARS_REG_CASE(4, 0)
+    PILLARS_REG_CASE(5, 0)
+    PILLARS_REG_CASE(4, 1)
+    PILLARS_REG_CASE(5, 1)
+#undef PILLARS_REG_CASE
+    return false;
 }
 
 // ---- rows of the dynamic variant: rank of every occupied cell in (b, ix, iy) order -----------------------------------------
@@ -591,7 +853,8 @@ cudaError_t launch_pfn_multi_lists(const MultiJob &job, const StackDev &sd, cons
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k_pfn_multi<<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
+    if (!launch_reg_variant(p, sd, static_cast<unsigned>(blocks), st))
+        k_pfn_multi<<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
@@ -618,7 +881,8 @@ cudaError_t launch_pfn_multi_dense(const float *voxels, const void *num_points, 
     int64_t blocks = (m + kWarps - 1) / kWarps;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    k_pfn_multi<<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
+    if (!launch_reg_variant(p, sd, static_cast<unsigned>(blocks), st))
+        k_pfn_multi<<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
