@@ -75,8 +75,16 @@ __global__ void k_frame_offsets(const float *__restrict__ pts, int64_t n, int st
 __global__ void __launch_bounds__(kThreads)
 k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int col0,
                   const int32_t *__restrict__ frame_offsets, int nb, GridDev gd, HashEntry *__restrict__ table,
-                  uint32_t cap, int32_t *__restrict__ point_slot, uint32_t *__restrict__ point_arrival, int vec_ok)
+                  uint32_t cap, int32_t *__restrict__ point_slot, uint32_t *__restrict__ point_arrival, int vec_ok,
+                  uint4 *__restrict__ zero_region, uint32_t zero_vecs, uint4 *__restrict__ ff_region, uint32_t ff_vecs)
 {
+    // Scratch that only the LATER kernels of the call read is initialised here, in the shadow of this kernel's atomic round
+    // trips, instead of by separate memsets: the scan's header / tile descriptors (zero) and the BEV index map (-1).
+    {
+        const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsz = gridDim.x * kThreads;
+        if (gtid < zero_vecs) zero_region[gtid] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t v = gtid; v < ff_vecs; v += gsz) ff_region[v] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
     extern __shared__ __align__(16) float s_pts[];  // [kThreads * stride]
     __shared__ int s_b0, s_b1;
 
@@ -449,9 +457,18 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
                                 int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras, cudaStream_t st)
 {
     cudaError_t err;
-    if ((err = cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st)) != cudaSuccess) return err;
-    if ((err = cudaMemsetAsync(ws.ff_begin, 0xFF, ws.ff_bytes, st)) != cudaSuccess) return err;
-    note_launch(2);
+    // One memset per call: the hash table must be empty before the first insert.  The rest of the scratch (scan header and
+    // tile descriptors: zero; BEV index map: -1) is initialised by the insert kernel itself, unless there is no point at all.
+    const size_t table_bytes = reinterpret_cast<char *>(ws.cell_row) - ws.ff_begin;
+    const size_t map_bytes = ws.ff_bytes - table_bytes;
+    const bool in_kernel_init = n > 0 && static_cast<int64_t>(ws.zero_bytes / 16) <= n && ws.zero_bytes % 16 == 0 &&
+                                map_bytes % 16 == 0;
+    if (!in_kernel_init) {
+        if ((err = cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, st)) != cudaSuccess) return err;
+        note_launch();
+    }
+    if ((err = cudaMemsetAsync(ws.ff_begin, 0xFF, in_kernel_init ? table_bytes : ws.ff_bytes, st)) != cudaSuccess) return err;
+    note_launch();
     if (n == 0) {
         if (pillar_count) {
             if ((err = cudaMemsetAsync(pillar_count, 0, sizeof(int32_t) * (nb + 1), st)) != cudaSuccess) return err;
@@ -463,7 +480,11 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
     const int vec_ok = (reinterpret_cast<uintptr_t>(points) % 16 == 0) ? 1 : 0;  // tile starts are 256 rows apart
     const unsigned pb = static_cast<unsigned>((n + kThreads - 1) / kThreads);
     k_quantize_insert<<<pb, kThreads, smem, st>>>(points, n, stride, col0, frame_offsets, nb, gd, ws.table, ws.cap,
-                                                  ws.point_slot, ws.point_arrival, vec_ok);
+                                                  ws.point_slot, ws.point_arrival, vec_ok,
+                                                  reinterpret_cast<uint4 *>(ws.zero_begin),
+                                                  in_kernel_init ? static_cast<uint32_t>(ws.zero_bytes / 16) : 0u,
+                                                  reinterpret_cast<uint4 *>(ws.cell_row),
+                                                  in_kernel_init ? static_cast<uint32_t>(map_bytes / 16) : 0u);
     // Tile ids are always handed out in scheduling order (one atomic per CTA): with other streams sharing the GPU nothing
     // guarantees that blockIdx order is dispatch order, and a tile spins on its predecessors.
     const int dynamic_ids = 1;
