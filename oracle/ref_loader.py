@@ -132,3 +132,50 @@ def cuda_is_identity():
         yield
     finally:
         torch.Tensor.cuda = orig
+
+
+# ---- src/encoder-decoder: VATLiDAR (the first consumer of the BEV canvas) ------------------------------
+_ED_MODELS = os.path.join(REFERENCE_ROOT, "src", "encoder-decoder", "training", "models")
+
+
+def vat_lidar_available() -> bool:
+    return os.path.isfile(os.path.join(_ED_MODELS, "vat_lidar.py"))
+
+
+def load_vat_lidar():
+    """The unmodified ``VATLiDAR`` class (src/encoder-decoder/training/models/vat_lidar.py:42) loaded by path under a
+    stub package; its optional ``..utils.debug`` import fails softly there (vat_lidar.py:32-36)."""
+    if "vat" in _CACHE:
+        return _CACHE["vat"]
+    if not vat_lidar_available():
+        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+    for name in ("_ref_ed", "_ref_ed.models"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = []
+        sys.modules[name] = pkg
+    for modname, fname in (("_ref_ed.models.vat_blocks", "vat_blocks.py"), ("_ref_ed.models.vat_lidar", "vat_lidar.py")):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(_ED_MODELS, fname))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+    _CACHE["vat"] = sys.modules["_ref_ed.models.vat_lidar"].VATLiDAR
+    return _CACHE["vat"]
+
+
+def vat_lidar_kv_tokens(model, bev):
+    """BEV tokens exactly as ``VATLiDAR.forward`` hands them to its first block (vat_lidar.py:206-253, ``blk(q, x)`` at
+    :285): captured with a forward pre-hook, so the reference's own forward computes them."""
+    import torch
+
+    got = {}
+
+    def hook(_mod, args):
+        got["kv"] = args[1].detach().clone()
+
+    h = model.blocks[0].register_forward_pre_hook(hook)
+    try:
+        with torch.inference_mode():
+            model(bev)
+    finally:
+        h.remove()
+    return got["kv"]
