@@ -32,6 +32,9 @@
  *                                      spatial_features, i.e. module_list[vfe, map_to_bev] of
  *                                      models/detectors/pointpillar.py:9-11 fed by `points` the way
  *                                      models/backbones_3d/vfe/dynamic_pillar_vfe.py:90-142 is
+ *   pillars_tokens_prepare,            src/encoder-decoder/training/models/vat_lidar.py:206-253: the BEV tokeniser at the
+ *   pillars_bev_tokens[_map|_dense]    head of VATLiDAR.forward (refine -> proj -> norm_tokens -> + geo PE -> + view embed),
+ *                                      the first consumer of spatial_features; geometry tables per :123-185
  */
 #ifndef PILLARS_B200_H_
 #define PILLARS_B200_H_
@@ -43,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PILLARS_ABI_VERSION 2
+#define PILLARS_ABI_VERSION 3
 
 /* error codes (negative; positive values are cudaError_t) */
 #define PILLARS_E_BADARG (-1)      /* NULL pointer, bad size, unsupported combination */
@@ -196,6 +199,56 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
                          const pillars_pfn_stack_t *stack, int32_t mode, int32_t coords_cols,
                          const pillars_outputs_t *out, void *workspace, size_t workspace_bytes,
                          int32_t scatter_variant, void *stream);
+
+/* ---- BEV tokeniser: VATLiDAR.forward up to the tokens its blocks attend over --------------------------------------------
+ * replaces src/encoder-decoder/training/models/vat_lidar.py:206-253 (eval mode):
+ *   x = GELU(conv3x3_depthwise(bev) + b)  :82-85,211   y = LayerNorm(conv1x1(x))  :88-89,222-225
+ *   tokens = y + geo_mlp(geom) + view_embed[sector]     :229-245        -> [n_frames, h*w, d_model]
+ * Supported shapes: c_in % 4 == 0, c_in <= 512; d_model % 128 == 0, d_model <= 1024.  All pointers 16-byte aligned. */
+typedef struct pillars_tokenizer {
+    int32_t c_in;               /* channels of the canvas = refine / proj in_channels */
+    int32_t d_model;
+    const float *dw_weight;     /* [c_in, 9]      refine.0.weight [c_in,1,3,3]                        */
+    const float *dw_bias;       /* [c_in]         refine.0.bias                                       */
+    const float *proj_weight_t; /* [c_in, d_model] proj.weight [d_model,c_in,1,1] TRANSPOSED by the caller */
+    const float *proj_bias;     /* [d_model]      proj.bias                                           */
+    const float *ln_weight;     /* [d_model]      norm_tokens.weight                                  */
+    const float *ln_bias;       /* [d_model]      norm_tokens.bias                                    */
+    float ln_eps;               /* norm_tokens.eps (1e-5)                                             */
+    const float *pe;            /* [h*w, d_model] written by pillars_tokens_prepare                   */
+    const float *background;    /* [d_model]      written by pillars_tokens_prepare                   */
+} pillars_tokenizer_t;
+
+/* Once per (weights, h, w): pe_out[cell] = geo_mlp.2(GELU(geo_mlp.0(geom[cell]))) + view_embed[sector[cell]] and
+ * background_out = LayerNorm(proj(GELU(refine bias))), the token (before PE) of a cell whose 3x3 window is all zero.
+ * geom [h*w,5] / sector [h*w] are the tables of VATLiDAR._grid (:123-185), computed by the caller;
+ * geo_w1 [d,5] = geo_mlp.0.weight, geo_w2_t [d,d] = geo_mlp.2.weight TRANSPOSED, view_embed [6,d].
+ * Reads tk->{c_in,d_model,dw_bias,proj_weight_t,proj_bias,ln_*}; tk->pe / tk->background are not read. */
+int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
+                           const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
+                           const float *view_embed, float *pe_out, float *background_out, void *stream);
+
+/* Scratch bytes: index map only (dense == 0, for pillars_bev_tokens) or index map + compacted rows (dense != 0). */
+size_t pillars_tokens_workspace_bytes(int32_t n_frames, int32_t c_in, int32_t h, int32_t w, int32_t dense);
+
+/* Tokens straight from pillar rows, no dense canvas: feats [m, c_in] and coords [m,4] (b,z,y,x) exactly as
+ * pillars_scatter_bev takes them (h = ny, w = nx, nz == 1).  tokens is [n_frames, h*w, d_model]. */
+int pillars_bev_tokens(const float *feats, const void *coords, int32_t coords_is_float, int64_t m, const int32_t *m_dev,
+                       int32_t n_frames, int32_t h, int32_t w, const pillars_tokenizer_t *tk, float *tokens,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same with an index map that already exists: cell_row [n_frames, h, w] int32, row of the pillar in the cell or -1. */
+int pillars_bev_tokens_map(const float *feats, const int32_t *cell_row, int32_t n_frames, int32_t h, int32_t w,
+                           const pillars_tokenizer_t *tk, float *tokens, void *stream);
+
+/* VATLiDAR's own input: a dense canvas bev [n_frames, c_in, h, w].  Cells with a non-zero channel are compacted into rows
+ * (workspace), then the same kernel runs; on a canvas without zeros every cell takes the arithmetic path. */
+int pillars_bev_tokens_dense(const float *bev, int32_t n_frames, int32_t h, int32_t w, const pillars_tokenizer_t *tk,
+                             float *tokens, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Byte offset, inside a workspace of pillars_encode_bev for the same (n_points, n_frames, grid), of the BEV index map
+ * [n_frames, ny, nx] that call leaves behind when it wrote a canvas -- the cell_row argument of pillars_bev_tokens_map. */
+size_t pillars_workspace_cell_row_offset(int64_t n_points, int32_t n_frames, const pillars_grid_t *grid);
 
 /* Number of kernel launches (incl. memsets) the last successful compute call on this thread enqueued. */
 int pillars_last_launch_count(void);

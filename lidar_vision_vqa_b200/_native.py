@@ -29,9 +29,15 @@ EXPORTED_SYMBOLS = (
     "pillars_pfn_dense_stack",
     "pillars_encode_stack",
     "pillars_scatter_bev_half",
+    "pillars_tokens_prepare",
+    "pillars_tokens_workspace_bytes",
+    "pillars_bev_tokens",
+    "pillars_bev_tokens_map",
+    "pillars_bev_tokens_dense",
+    "pillars_workspace_cell_row_offset",
 )
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LAYOUT_PILLAR_VFE, LAYOUT_SIMPLE2D = 0, 1
 MODE_HARD, MODE_DYNAMIC = 0, 1
 
@@ -57,6 +63,12 @@ class PillarsOutputs(Structure):
     _fields_ = [("pillar_capacity", c_int64), ("pillar_features", c_void_p), ("voxel_coords", c_void_p),
                 ("voxel_num_points", c_void_p), ("voxels", c_void_p), ("point_pillar", c_void_p),
                 ("point_slot", c_void_p), ("pillar_count", c_void_p), ("bev", c_void_p), ("bev_half", c_void_p)]
+
+
+class PillarsTokenizer(Structure):
+    _fields_ = [("c_in", c_int32), ("d_model", c_int32), ("dw_weight", c_void_p), ("dw_bias", c_void_p),
+                ("proj_weight_t", c_void_p), ("proj_bias", c_void_p), ("ln_weight", c_void_p), ("ln_bias", c_void_p),
+                ("ln_eps", c_float), ("pe", c_void_p), ("background", c_void_p)]
 
 
 class NativeLibraryError(RuntimeError):
@@ -116,6 +128,22 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_encode_stack.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, POINTER(PillarsGrid),
                                          POINTER(PillarsPfnStack), c_int32, c_int32, POINTER(PillarsOutputs), c_void_p,
                                          c_size_t, c_int32, c_void_p]
+    lib.pillars_tokens_prepare.restype = c_int
+    lib.pillars_tokens_prepare.argtypes = [POINTER(PillarsTokenizer), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pillars_tokens_workspace_bytes.restype = c_size_t
+    lib.pillars_tokens_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
+    lib.pillars_bev_tokens.restype = c_int
+    lib.pillars_bev_tokens.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
+                                       POINTER(PillarsTokenizer), c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.pillars_bev_tokens_map.restype = c_int
+    lib.pillars_bev_tokens_map.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(PillarsTokenizer), c_void_p,
+                                           c_void_p]
+    lib.pillars_bev_tokens_dense.restype = c_int
+    lib.pillars_bev_tokens_dense.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(PillarsTokenizer), c_void_p,
+                                             c_void_p, c_size_t, c_void_p]
+    lib.pillars_workspace_cell_row_offset.restype = c_size_t
+    lib.pillars_workspace_cell_row_offset.argtypes = [c_int64, c_int32, POINTER(PillarsGrid)]
     lib.pillars_set_scatter_stream.restype = c_int
     lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
     lib.pillars_force_generic_features.restype = c_int

@@ -520,4 +520,138 @@ int pillars_scatter_bev_half(const float *feats, const void *coords, int32_t coo
     return 0;
 }
 
+// ---- BEV tokeniser ------------------------------------------------------------------------------------------------------
+static int check_tokenizer(const pillars_tokenizer_t *tk, bool need_tables, TokenizerDev *td)
+{
+    if (!tk) return fail(PILLARS_E_BADARG, "tokenizer is NULL");
+    if (!tokens_shape_supported(tk->c_in, tk->d_model))
+        return fail(PILLARS_E_UNSUPPORTED, "tokeniser needs c_in %% 4 == 0 (<= 512) and d_model %% 128 == 0 (<= 1024), got %d / %d",
+                    tk->c_in, tk->d_model);
+    const void *ptrs[] = {tk->dw_weight, tk->dw_bias, tk->proj_weight_t, tk->proj_bias, tk->ln_weight, tk->ln_bias,
+                          need_tables ? tk->pe : tk->dw_bias, need_tables ? tk->background : tk->dw_bias};
+    for (const void *q : ptrs)
+        if (!q || reinterpret_cast<uintptr_t>(q) % 16 != 0) return fail(PILLARS_E_BADARG, "tokenizer pointer NULL or not 16-byte aligned");
+    td->c = tk->c_in; td->d = tk->d_model;
+    td->dw_w = tk->dw_weight; td->dw_b = tk->dw_bias; td->wt = tk->proj_weight_t; td->pb = tk->proj_bias;
+    td->gamma = tk->ln_weight; td->beta = tk->ln_bias; td->eps = tk->ln_eps; td->pe = tk->pe; td->bg = tk->background;
+    return 0;
+}
+
+int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
+                           const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
+                           const float *view_embed, float *pe_out, float *background_out, void *stream)
+{
+    g_launches = 0;
+    TokenizerDev td{};
+    int rc;
+    if ((rc = check_tokenizer(tk, false, &td))) return rc;
+    if (h < 0 || w < 0) return fail(PILLARS_E_BADARG, "pillars_tokens_prepare: bad size");
+    if (!background_out || !geo_w1 || !geo_b1 || !geo_w2_t || !geo_b2 || !view_embed)
+        return fail(PILLARS_E_BADARG, "pillars_tokens_prepare: NULL pointer");
+    if (static_cast<int64_t>(h) * w > 0 && (!geom || !sector || !pe_out))
+        return fail(PILLARS_E_BADARG, "pillars_tokens_prepare: geom / sector / pe_out NULL");
+    cudaError_t e = launch_tokens_prepare(td, geom, sector, h, w, geo_w1, geo_b1, geo_w2_t, geo_b2, view_embed, pe_out,
+                                          background_out, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "tokens_prepare");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+static size_t tokens_map_bytes(int32_t n_frames, int32_t h, int32_t w)
+{
+    return align_up(sizeof(int32_t) * static_cast<size_t>(n_frames) * h * w, 256);
+}
+
+size_t pillars_tokens_workspace_bytes(int32_t n_frames, int32_t c_in, int32_t h, int32_t w, int32_t dense)
+{
+    if (n_frames < 0 || c_in < 0 || h < 0 || w < 0) return 0;
+    size_t b = tokens_map_bytes(n_frames, h, w);
+    if (dense) b += 256 + align_up(sizeof(float) * static_cast<size_t>(n_frames) * h * w * c_in, 256);
+    return b;
+}
+
+static int check_tokens_call(const pillars_tokenizer_t *tk, int32_t n_frames, int32_t h, int32_t w, const float *tokens,
+                             TokenizerDev *td)
+{
+    int rc;
+    if ((rc = check_tokenizer(tk, true, td))) return rc;
+    if (n_frames < 0 || h < 0 || w < 0) return fail(PILLARS_E_BADARG, "tokens: bad size");
+    if (static_cast<int64_t>(n_frames) * h * w > 0 && (!tokens || reinterpret_cast<uintptr_t>(tokens) % 16 != 0))
+        return fail(PILLARS_E_BADARG, "tokens output NULL or not 16-byte aligned");
+    return 0;
+}
+
+int pillars_bev_tokens_map(const float *feats, const int32_t *cell_row, int32_t n_frames, int32_t h, int32_t w,
+                           const pillars_tokenizer_t *tk, float *tokens, void *stream)
+{
+    g_launches = 0;
+    TokenizerDev td{};
+    int rc;
+    if ((rc = check_tokens_call(tk, n_frames, h, w, tokens, &td))) return rc;
+    if (static_cast<int64_t>(n_frames) * h * w == 0) return 0;
+    if (!cell_row) return fail(PILLARS_E_BADARG, "cell_row is NULL");
+    cudaError_t e = launch_bev_tokens(td, feats, cell_row, n_frames, h, w, tokens, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "bev_tokens");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_bev_tokens(const float *feats, const void *coords, int32_t coords_is_float, int64_t m, const int32_t *m_dev,
+                       int32_t n_frames, int32_t h, int32_t w, const pillars_tokenizer_t *tk, float *tokens,
+                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    g_launches = 0;
+    TokenizerDev td{};
+    int rc;
+    if ((rc = check_tokens_call(tk, n_frames, h, w, tokens, &td))) return rc;
+    if (m < 0 || (m > 0 && (!feats || !coords))) return fail(PILLARS_E_BADARG, "feats / coords NULL");
+    if (m > 0 && reinterpret_cast<uintptr_t>(coords) % 16 != 0) return fail(PILLARS_E_BADARG, "coords must be 16-byte aligned");
+    if (static_cast<int64_t>(n_frames) * h * w == 0) return 0;
+    const size_t need = tokens_map_bytes(n_frames, h, w);
+    if (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 16 != 0)
+        return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t *cell_row = static_cast<int32_t *>(workspace);
+    cudaError_t e;
+    if ((e = launch_build_cell_row(coords, coords_is_float != 0, m, m_dev, n_frames, w, h, 1, cell_row, st)) != cudaSuccess)
+        return cuda_fail(e, "build_cell_row");
+    if ((e = launch_bev_tokens(td, feats, cell_row, n_frames, h, w, tokens, st)) != cudaSuccess) return cuda_fail(e, "bev_tokens");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_bev_tokens_dense(const float *bev, int32_t n_frames, int32_t h, int32_t w, const pillars_tokenizer_t *tk,
+                             float *tokens, void *workspace, size_t workspace_bytes, void *stream)
+{
+    g_launches = 0;
+    TokenizerDev td{};
+    int rc;
+    if ((rc = check_tokens_call(tk, n_frames, h, w, tokens, &td))) return rc;
+    if (static_cast<int64_t>(n_frames) * h * w == 0) return 0;
+    if (!bev) return fail(PILLARS_E_BADARG, "bev is NULL");
+    const size_t need = pillars_tokens_workspace_bytes(n_frames, tk->c_in, h, w, 1);
+    if (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+        return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes (256-byte aligned), %zu needed", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *base = static_cast<char *>(workspace);
+    int32_t *cell_row = reinterpret_cast<int32_t *>(base);
+    uint32_t *counter = reinterpret_cast<uint32_t *>(base + tokens_map_bytes(n_frames, h, w));
+    float *rows = reinterpret_cast<float *>(base + tokens_map_bytes(n_frames, h, w) + 256);
+    cudaError_t e;
+    if ((e = launch_canvas_to_rows(bev, n_frames, tk->c_in, h, w, cell_row, rows, counter, st)) != cudaSuccess)
+        return cuda_fail(e, "canvas_to_rows");
+    if ((e = launch_bev_tokens(td, rows, cell_row, n_frames, h, w, tokens, st)) != cudaSuccess) return cuda_fail(e, "bev_tokens");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+size_t pillars_workspace_cell_row_offset(int64_t n_points, int32_t n_frames, const pillars_grid_t *grid)
+{
+    if (!grid || n_points < 0 || n_frames < 0) return 0;
+    const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
+    char *base = reinterpret_cast<char *>(static_cast<uintptr_t>(4096));  // any non-null base: only the offset is wanted
+    const Workspace ws = carve_workspace(base, n_points, n_frames, cells_xy);
+    return static_cast<size_t>(reinterpret_cast<char *>(ws.cell_row) - base);
+}
+
 }  // extern "C"

@@ -253,4 +253,22 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
 cudaError_t launch_scatter_half(const float *feats, const int32_t *cell_row, int nb, int f, int nx, int ny, void *bev,
                                 cudaStream_t st);
 
+// ---- BEV tokeniser (tokens.cu): head of VATLiDAR.forward, src/encoder-decoder/training/models/vat_lidar.py:206-253 ----
+struct TokenizerDev {
+    int c, d;
+    const float *dw_w, *dw_b;  // [c, 9], [c]
+    const float *wt, *pb;      // [c, d] (transposed projection), [d]
+    const float *gamma, *beta; // LayerNorm
+    float eps;
+    const float *pe, *bg;      // [h*w, d], [d]
+};
+bool tokens_shape_supported(int c, int d);
+cudaError_t launch_tokens_prepare(const TokenizerDev &tk, const float *geom, const int32_t *sid, int h, int w, const float *w1,
+                                  const float *b1, const float *w2t, const float *b2, const float *view, float *pe, float *bg,
+                                  cudaStream_t st);
+cudaError_t launch_canvas_to_rows(const float *bev, int nb, int c, int h, int w, int32_t *cell_row, float *rows,
+                                  uint32_t *counter, cudaStream_t st);
+cudaError_t launch_bev_tokens(const TokenizerDev &tk, const float *feats, const int32_t *cell_row, int nb, int h, int w,
+                              float *out, cudaStream_t st);
+
 }  // namespace pillars

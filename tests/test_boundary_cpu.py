@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_native.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pillars_abi_version() == _native.ABI_VERSION == 2
+    assert lib.pillars_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header_sizes():
@@ -41,6 +41,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_native.PillarsGrid) == 6 * 4 + 3 * 4 + 3 * 4 + 4 + 4
     assert ctypes.sizeof(_native.PillarsPfn) == 5 * 4 + 3 * 4 + 4 * 8
     assert ctypes.sizeof(_native.PillarsOutputs) == 10 * 8
+    assert ctypes.sizeof(_native.PillarsTokenizer) == 2 * 4 + 6 * 8 + 8 + 2 * 8  # eps padded to 8
 
 
 def test_workspace_query_and_argument_errors(lib):
@@ -142,3 +143,50 @@ def test_dynamic_vfe_state_dict_contract(name):
     if not torch.cuda.is_available():
         with pytest.raises(L.NativeLibraryError):
             vfe.eval()({"points": torch.from_numpy(g["points_b"]), "batch_size": int(g["batch"])})
+
+
+# ---- BEV tokeniser (VATLiDAR head, vat_lidar.py:63-121,206-253) -------------------------------------------------------------
+def test_tokenizer_state_dict_contract_and_host_tables():
+    """Parameter names/shapes are the reference's (so its checkpoints load), geometry tables equal the oracle's."""
+    from lidar_vision_vqa_b200 import tokens as T
+    from oracle import tokens_oracle as to
+
+    tk = T.VATLiDARTokenizer(c_in=64, d_model=256)
+    sd = to.random_token_params(64, 256, seed=0)
+    assert {k: tuple(v.shape) for k, v in tk.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    res = tk.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert tk.norm_tokens.eps == to.LN_EPS
+    for h, w in [(13, 9), (50, 50), (96, 64), (1, 7)]:
+        geom, sid = T.grid_tables(h, w)
+        g2, s2 = to.grid_geometry(h, w)
+        np.testing.assert_array_equal(sid.numpy(), s2)
+        np.testing.assert_allclose(geom.numpy(), g2, rtol=0, atol=1e-6)
+
+
+def test_tokenizer_argument_errors(lib):
+    from lidar_vision_vqa_b200 import _native
+
+    t = _native.PillarsTokenizer()
+    t.c_in, t.d_model = 64, 100  # d_model must be a multiple of 128
+    assert lib.pillars_bev_tokens_map(None, None, 1, 8, 8, ctypes.byref(t), None, None) == -3
+    assert b"d_model" in lib.pillars_last_error()
+    assert lib.pillars_bev_tokens_map(None, None, 1, 8, 8, None, None, None) == -1
+    a = lib.pillars_tokens_workspace_bytes(2, 64, 16, 16, 0)
+    b = lib.pillars_tokens_workspace_bytes(2, 64, 16, 16, 1)
+    assert 2 * 16 * 16 * 4 <= a < b and b >= a + 2 * 16 * 16 * 64 * 4
+    g = _native.make_grid((-51.2, -51.2, -5, 51.2, 51.2, 3), (0.2, 0.2, 8), (512, 512, 1), 32, 30000)
+    off = lib.pillars_workspace_cell_row_offset(100_000, 4, ctypes.byref(g))
+    assert 0 < off and off + 4 * 4 * 512 * 512 <= lib.pillars_workspace_bytes(100_000, 4, ctypes.byref(g))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_tokenizer_without_gpu_fails_loudly():
+    import lidar_vision_vqa_b200 as L
+    from lidar_vision_vqa_b200 import tokens as T
+
+    tk = T.VATLiDARTokenizer(c_in=8, d_model=128).eval()
+    with pytest.raises(L.NativeLibraryError):
+        tk(torch.zeros(1, 8, 4, 4))
+    with pytest.raises(L.NativeLibraryError):
+        tk.forward_pillars(torch.zeros(2, 8), torch.zeros(2, 4), 1, (4, 4))
