@@ -61,15 +61,16 @@ struct TokParams {
 // -------------------------------------------------------------------------------------------------------------------
 // main kernel.  NQ = d / 128: a lane owns channels 4*(lane + 32*q) .. +3, q < NQ (512 contiguous bytes per warp and q).
 // G = cells whose projection runs together in one warp.
-// dynamic shared memory: s_dw [10][c] (depthwise weights transposed + bias) | s_a [warps][G][c] (refined activations)
+// dynamic shared memory: s_dw [10][c] (depthwise weights transposed + bias) | s_a [warps][c/4][G] float4 (refined activations)
 // -------------------------------------------------------------------------------------------------------------------
 template <int NQ, int G>
 __global__ void __launch_bounds__(kTokThreads, 2) k_bev_tokens(const __grid_constant__ TokParams p)
 {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ int32_t s_map[kFrameChunk][3][kTileX + 2];
-    __shared__ uint32_t s_act[kFrameChunk];                       // bit t: cell t of the tile has a non-empty window
-    __shared__ uint16_t s_list[kTokWarps][kCellsPerWarp * kFrameChunk];
+    __shared__ uint32_t s_act[kFrameChunk];                  // bit t: cell t of the tile has a non-empty window
+    __shared__ uint16_t s_list[kTileX * kFrameChunk];        // (cell of the tile) * kFrameChunk + frame, CTA-wide
+    __shared__ uint32_t s_count;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = p.c, d = p.d, w = p.w, h = p.h;
@@ -83,9 +84,16 @@ __global__ void __launch_bounds__(kTokThreads, 2) k_bev_tokens(const __grid_cons
     }
     for (int i = tid; i < c; i += kTokThreads) s_dw[9 * c + i] = __ldg(p.dw_b + i);
 
+    // refine: lane = (cell g of the group, channel quad): consecutive lanes hold consecutive cells, so the activation tile
+    // [quad][G] is written without bank conflicts and read back by the projection with one running pointer
+    const int quads = c >> 2;
+    const int rg = lane % G, rq = lane / G;
+    constexpr int kQuadStep = 32 / G;
+
     for (int b0 = 0; b0 < p.nb; b0 += kFrameChunk) {
         const int nbb = min(kFrameChunk, p.nb - b0);
         __syncthreads();  // the previous chunk's readers are done
+        if (tid == 0) s_count = 0;
         for (int i = tid; i < nbb * 3 * (kTileX + 2); i += kTokThreads) {
             const int bb = i / (3 * (kTileX + 2)), r = i - bb * 3 * (kTileX + 2);
             const int dy = r / (kTileX + 2), dx = r - dy * (kTileX + 2);
@@ -108,12 +116,20 @@ __global__ void __launch_bounds__(kTokThreads, 2) k_bev_tokens(const __grid_cons
         }
         __syncthreads();
 
-        // ---- pass A: stream the input-independent tokens, collect the cells that need arithmetic ---------------------------
-        int n_list = 0;
+        // ---- pass A: stream the input-independent tokens, collect the (cell, frame) pairs that need arithmetic --------------
         for (int tt = 0; tt < kCellsPerWarp; ++tt) {
             const int t = warp * kCellsPerWarp + tt, x = x0 + t;
             if (x >= w) break;
             const size_t cell = static_cast<size_t>(y) * w + x;
+            const unsigned amask = __ballot_sync(kFull, lane < nbb && ((s_act[lane & (kFrameChunk - 1)] >> t) & 1u));
+            if (amask) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_count, static_cast<uint32_t>(__popc(amask)));
+                base = __shfl_sync(kFull, base, 0);
+                if ((amask >> lane) & 1u)
+                    s_list[base + __popc(amask & ((1u << lane) - 1u))] = static_cast<uint16_t>(t * kFrameChunk + lane);
+            }
+            if (__popc(amask) == nbb) continue;
             float4 v[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -121,57 +137,72 @@ __global__ void __launch_bounds__(kTokThreads, 2) k_bev_tokens(const __grid_cons
                 const float4 e = __ldg(reinterpret_cast<const float4 *>(p.pe + cell * d) + lane + 32 * q);
                 v[q] = make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
             }
-            for (int bb = 0; bb < nbb; ++bb) {
-                if ((s_act[bb] >> t) & 1u) {
-                    if (lane == 0) s_list[warp][n_list] = static_cast<uint16_t>(tt * kFrameChunk + bb);
-                    ++n_list;
-                } else {
-                    float4 *dst = reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(b0 + bb) * h * w + cell) * d);
+            float4 *dst = reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(b0) * h * w + cell) * d) + lane;
+            const size_t frame_step = static_cast<size_t>(h) * w * (d >> 2);
+            for (int bb = 0; bb < nbb; ++bb, dst += frame_step) {
+                if ((amask >> bb) & 1u) continue;
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) __stcs(dst + lane + 32 * q, v[q]);
-                }
+                for (int q = 0; q < NQ; ++q) __stcs(dst + 32 * q, v[q]);
             }
         }
-        __syncwarp();
+        __syncthreads();
+        const int n_list = static_cast<int>(s_count);
 
-        // ---- pass B: G cells at a time -------------------------------------------------------------------------------------
-        for (int i0 = 0; i0 < n_list; i0 += G) {
+        // ---- pass B: G pairs at a time per warp, groups dealt round-robin over the CTA's warps ------------------------------
+        for (int i0 = warp * G; i0 < n_list; i0 += kTokWarps * G) {
             const int cnt = min(G, n_list - i0);
             // refine: depthwise 3x3 over the window's pillar rows, + bias, GELU (vat_lidar.py:82-85)
-            for (int g = 0; g < cnt; ++g) {
-                const int e = s_list[warp][i0 + g];
-                const int tt = e / kFrameChunk, bb = e - tt * kFrameChunk, t = warp * kCellsPerWarp + tt;
-                int32_t rows[9];
+            if (rg < cnt) {
+                const int e = s_list[i0 + rg];
+                const int t = e / kFrameChunk, bb = e - t * kFrameChunk;
+                const float4 *rowp[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) rows[k] = s_map[bb][k / 3][t + k % 3];
-                for (int ch = lane; ch < c; ch += 32) {
-                    float acc = s_dw[9 * c + ch];
+                for (int k = 0; k < 9; ++k) {
+                    const int32_t r = s_map[bb][k / 3][t + k % 3];
+                    rowp[k] = r >= 0 ? reinterpret_cast<const float4 *>(p.feats + static_cast<size_t>(r) * c) : nullptr;
+                }
+                for (int qd = rq; qd < quads; qd += kQuadStep) {
+                    float4 f[9];
 #pragma unroll
-                    for (int k = 0; k < 9; ++k)
-                        if (rows[k] >= 0) acc = fmaf(s_dw[k * c + ch], __ldg(p.feats + static_cast<size_t>(rows[k]) * c + ch), acc);
-                    s_a[g * c + ch] = gelu_erf(acc);
+                    for (int k = 0; k < 9; ++k) f[k] = rowp[k] ? __ldg(rowp[k] + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 acc = *reinterpret_cast<const float4 *>(s_dw + 9 * c + 4 * qd);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const float4 wk = *reinterpret_cast<const float4 *>(s_dw + k * c + 4 * qd);
+                        acc.x = fmaf(wk.x, f[k].x, acc.x);
+                        acc.y = fmaf(wk.y, f[k].y, acc.y);
+                        acc.z = fmaf(wk.z, f[k].z, acc.z);
+                        acc.w = fmaf(wk.w, f[k].w, acc.w);
+                    }
+                    reinterpret_cast<float4 *>(s_a)[qd * G + rg] =
+                        make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
                 }
             }
             __syncwarp();
             // projection (vat_lidar.py:88,222): acc[g][q] += a[g][ch] * Wp^T[ch][lane's channels]
             float acc[G][NQ][4];
 #pragma unroll
-            for (int g = 0; g < G; ++g)
+            for (int q = 0; q < NQ; ++q) {
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(p.pb) + lane + 32 * q);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const float4 bq = __ldg(reinterpret_cast<const float4 *>(p.pb) + lane + 32 * q);
+                for (int g = 0; g < G; ++g) {
                     acc[g][q][0] = bq.x; acc[g][q][1] = bq.y; acc[g][q][2] = bq.z; acc[g][q][3] = bq.w;
                 }
-            for (int c4 = 0; c4 < c; c4 += 4) {
+            }
+            const float4 *wp = reinterpret_cast<const float4 *>(p.wt) + lane;
+            const int d4 = d >> 2;
+            const float4 *ap = reinterpret_cast<const float4 *>(s_a);          // [quad][G]: one running pointer, immediate offsets
+            const float4 *const ap_end = ap + static_cast<size_t>(quads) * G;
+            for (; ap != ap_end; ap += G) {
                 float4 av[G];
 #pragma unroll
-                for (int g = 0; g < G; ++g) av[g] = *reinterpret_cast<const float4 *>(s_a + g * c + c4);
+                for (int g = 0; g < G; ++g) av[g] = ap[g];
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     float4 wv[NQ];
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-                        wv[q] = __ldg(reinterpret_cast<const float4 *>(p.wt + static_cast<size_t>(c4 + cc) * d) + lane + 32 * q);
+                    for (int q = 0; q < NQ; ++q) wv[q] = __ldg(wp + 32 * q);
+                    wp += d4;
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const float a = cc == 0 ? av[g].x : cc == 1 ? av[g].y : cc == 2 ? av[g].z : av[g].w;
@@ -204,21 +235,22 @@ __global__ void __launch_bounds__(kTokThreads, 2) k_bev_tokens(const __grid_cons
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
                     const float rstd = 1.f / sqrtf(ss / static_cast<float>(d) + p.eps);
-                    const int e = s_list[warp][i0 + g];
-                    const int tt = e / kFrameChunk, bb = e - tt * kFrameChunk;
-                    const size_t cell = static_cast<size_t>(y) * w + x0 + warp * kCellsPerWarp + tt;
-                    float4 *dst = reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(b0 + bb) * h * w + cell) * d);
+                    const int e = s_list[i0 + g];
+                    const int t = e / kFrameChunk, bb = e - t * kFrameChunk;
+                    const size_t cell = static_cast<size_t>(y) * w + x0 + t;
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(b0 + bb) * h * w + cell) * d) + lane;
+                    const float4 *pe4 = reinterpret_cast<const float4 *>(p.pe + cell * d) + lane;
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         const float4 ga = __ldg(reinterpret_cast<const float4 *>(p.gamma) + lane + 32 * q);
                         const float4 be = __ldg(reinterpret_cast<const float4 *>(p.beta) + lane + 32 * q);
-                        const float4 pe = __ldg(reinterpret_cast<const float4 *>(p.pe + cell * d) + lane + 32 * q);
+                        const float4 pe = __ldg(pe4 + 32 * q);
                         float4 o4;
                         o4.x = fmaf((acc[g][q][0] - mean) * rstd, ga.x, be.x) + pe.x;
                         o4.y = fmaf((acc[g][q][1] - mean) * rstd, ga.y, be.y) + pe.y;
                         o4.z = fmaf((acc[g][q][2] - mean) * rstd, ga.z, be.z) + pe.z;
                         o4.w = fmaf((acc[g][q][3] - mean) * rstd, ga.w, be.w) + pe.w;
-                        __stcs(dst + lane + 32 * q, o4);
+                        __stcs(dst + 32 * q, o4);
                     }
                 }
             }
