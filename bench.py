@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--split", action="store_true",
                     help="put the scatter on a separate low-priority stream (measured: no gain, see DESIGN.md)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tokens", action="store_true", help="skip the BEV tokeniser side measurement")
+    ap.add_argument("--tokens-d-model", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU arm (bounded sample)")
     return ap.parse_args()
@@ -349,6 +351,38 @@ def run_b200(args, rank, world, local_rank):
         half_ms = float(np.mean([evs[k][2].elapsed_time(evs[k][3]) for k in range(n16)]))
         del buf16
 
+    # ---- side measurement (not part of `value`): the first consumer of the canvas, the BEV tokeniser of VATLiDAR
+    #      (src/encoder-decoder/training/models/vat_lidar.py:206-253), fed from the pillar rows + index map of the last step ----
+    tokens_stage = None
+    if not args.no_tokens and nz == 1:
+        from lidar_vision_vqa_b200 import tokens as T
+        from oracle import tokens_oracle as tor  # random weights only
+
+        d_tok = args.tokens_d_model
+        tk = T.VATLiDARTokenizer(F_OUT, d_tok)
+        tk.load_state_dict({k: torch.from_numpy(v) for k, v in tor.random_token_params(F_OUT, d_tok, seed=11).items()})
+        tk = tk.eval().to(dev)
+        tk.tables(ny, nx)
+        tok_out = torch.empty((nb, ny * nx, d_tok), dtype=torch.float32, device=dev)
+        res_t = ops.encode_bev(*dev_batches[0], grid, pfn, buffers=bufs[0], want_index_map=True)
+        cmap = res_t["cell_row"]
+        for _ in range(3):
+            tk.forward_index_map(res_t["pillar_features"], cmap, out=tok_out)
+        ts_, te_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_tok = min(K, 10)
+        torch.cuda.synchronize()
+        ts_.record()
+        for _ in range(n_tok):
+            tk.forward_index_map(res_t["pillar_features"], cmap, out=tok_out)
+        te_.record()
+        torch.cuda.synchronize()
+        tok_ms = ts_.elapsed_time(te_) / n_tok
+        tok_bytes = tok_out.numel() * 4 + ny * nx * d_tok * 4  # tokens written + PE table read once
+        tokens_stage = {"kernel": "k_bev_tokens (sparse-aware VATLiDAR tokeniser, rows + index map -> [B, H*W, d])",
+                        "d_model": d_tok, "ms": tok_ms, "algorithmic_bytes": tok_bytes,
+                        "gbs": tok_bytes / (tok_ms * 1e-3) / 1e9, "tokens_per_s": nb * ny * nx / (tok_ms * 1e-3)}
+        del tok_out, tk
+
     # ---- timed region 2 (the headline): the same K steps pipelined over n_streams streams ----------------------------
     split = n_streams > 1 and args.split
     for w in range(max(3, args.warmup)):  # warm the other streams' buffers
@@ -408,7 +442,10 @@ def run_b200(args, rank, world, local_rank):
         "path_frac_of_peak": (ab["V"] + ab["P"] + ab["S"]) / (ms_per_step * 1e-3) / 1e9 / peak,
         "algorithmic_bytes": ab, "points_raw": n_raw, "points_kept": n_kept, "pillars": m_avg,
         "scatter_float16_canvas_ms": half_ms,
+        "tokens": tokens_stage,
     }
+    if tokens_stage:
+        tokens_stage["frac_of_peak"] = tokens_stage["gbs"] / peak
 
     # ---- end to end through the reference-facing modules, inputs in pinned host memory ---------------------------
     e2e = None

@@ -60,11 +60,13 @@ struct TokParams {
 
 // -------------------------------------------------------------------------------------------------------------------
 // main kernel.  NQ = d / 128: a lane owns channels 4*(lane + 32*q) .. +3, q < NQ (512 contiguous bytes per warp and q).
-// G = cells whose projection runs together in one warp.
+// G = cells whose projection runs together in one warp: a projection column loaded once feeds G cells, but the G x NQ x 4
+// accumulators set the register count and with it the warps in flight -- measured on B200 (16 x 512^2, d = 256): G = 8 at
+// 2 CTAs/SM 1586 us, G = 4 at 3 CTAs/SM 1425 us; d = 512: G = 4 1475 us, G = 2 1645 us.
 // dynamic shared memory: s_dw [10][c] (depthwise weights transposed + bias) | s_a [warps][c/4][G] float4 (refined activations)
 // -------------------------------------------------------------------------------------------------------------------
 template <int NQ, int G>
-__global__ void __launch_bounds__(kTokThreads, 2) k_bev_tokens(const __grid_constant__ TokParams p)
+__global__ void __launch_bounds__(kTokThreads, (NQ * G <= 8) ? 3 : 2) k_bev_tokens(const __grid_constant__ TokParams p)
 {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ int32_t s_map[kFrameChunk][3][kTileX + 2];
@@ -459,7 +461,7 @@ cudaError_t launch_bev_tokens(const TokenizerDev &tk, const float *feats, const 
     p.pe = tk.pe; p.bg = tk.bg; p.out = out;
     switch (tk.d / 128) {
         case 1: return launch_tokens_t<1, 8>(p, st);
-        case 2: return launch_tokens_t<2, 8>(p, st);
+        case 2: return launch_tokens_t<2, 4>(p, st);
         case 3: return launch_tokens_t<3, 4>(p, st);
         case 4: return launch_tokens_t<4, 4>(p, st);
         case 5: return launch_tokens_t<5, 2>(p, st);

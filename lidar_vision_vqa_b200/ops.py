@@ -407,9 +407,11 @@ class EncodeBuffers:
 
 def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, pfn: PfnParams, *, col0: int = 0,
                buffers: Optional[EncodeBuffers] = None, with_bev: bool = True, scatter_variant: str = "auto",
-               want_membership: bool = False, want_voxels: bool = False,
+               want_membership: bool = False, want_voxels: bool = False, want_index_map: bool = False,
                scatter_stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
     """The fused path: raw points -> pillar_features / voxel_coords / voxel_num_points / pillar_count / bev.
+    ``want_index_map`` adds ``cell_row`` [n_frames, ny, nx] int32 (row of the pillar in each cell, -1 = empty): a view of
+    the workspace, valid until ``buffers`` is reused -- the input of the BEV tokeniser (tokens.py).
     Everything is enqueued on the current stream; nothing synchronises.  With ``scatter_stream`` the canvas write goes to
     that stream (ordered after the feature kernel); the caller then waits on it before reusing ``buffers``."""
     _check_points(points, frame_offsets)
@@ -450,6 +452,13 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
     if want_voxels:
         res["voxels"] = torch.empty((buffers.capacity, grid.max_points, pfn.c_point), dtype=torch.float32, device=dev)
         out.voxels = res["voxels"].data_ptr()
+    if want_index_map:
+        if not with_bev:
+            raise ValueError("the index map is only written together with a canvas")
+        # the workspace layout depends on the point count of THIS call
+        off = lib.pillars_workspace_cell_row_offset(n, nb, ctypes.byref(g))
+        nx, ny, _ = grid.grid_size
+        res["cell_row"] = buffers.ws[off:off + 4 * nb * ny * nx].view(torch.int32).view(nb, ny, nx)
     nat = pfn.native()
     if scatter_stream is not None:
         lib.pillars_set_scatter_stream(int(scatter_stream.cuda_stream), 1)

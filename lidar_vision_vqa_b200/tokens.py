@@ -197,8 +197,9 @@ class VATLiDARTokenizer(nn.Module):
 
 
 def encode_index_map(buffers: "ops.EncodeBuffers", n_points: int, n_frames: int, grid: "ops.GridSpec") -> torch.Tensor:
-    """View of the BEV index map [n_frames, ny, nx] that ``ops.encode_bev(..., buffers=buffers)`` left in its workspace
-    (valid until the next call that reuses ``buffers``)."""
+    """View of the BEV index map [n_frames, ny, nx] that ``ops.encode_bev(points, ..., buffers=buffers)`` left in its
+    workspace (valid until ``buffers`` is reused).  ``n_points`` must be the row count of the ``points`` of THAT call: the
+    workspace is carved by it.  ``ops.encode_bev(..., want_index_map=True)`` returns the same view without that pitfall."""
     g = grid.native()
     off = _native.load().pillars_workspace_cell_row_offset(n_points, n_frames, ctypes.byref(g))
     nx, ny, _ = grid.grid_size

@@ -165,10 +165,11 @@ def test_cfg2_canvas_tokens_from_the_fused_encoder(dev):
                        point_cloud_range=grid.point_cloud_range, device=dev)
     p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
     bufs = ops.EncodeBuffers(len(pts), nb, grid, 64, dev)
-    res = ops.encode_bev(p, o, grid, pfn, buffers=bufs)
+    res = ops.encode_bev(p, o, grid, pfn, buffers=bufs, want_index_map=True)
     sd = to.random_token_params(64, 128, seed=11)
     tk = make_tokenizer(sd, dev)
-    cell_row = T.encode_index_map(bufs, len(pts), nb, grid)
+    cell_row = res["cell_row"]
+    assert torch.equal(cell_row, T.encode_index_map(bufs, len(pts), nb, grid))
     m = int(res["pillar_count"][-1].item())
     assert int((cell_row >= 0).sum().item()) == m
     tok_map = tk.forward_index_map(res["pillar_features"], cell_row)
