@@ -253,7 +253,11 @@ def run_b200(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_cpus = None
     if world > 1:
+        from lidar_vision_vqa_b200 import sharding
+
+        numa_cpus = sharding.bind_to_gpu_numa_node(local_rank)  # pinned e2e buffers land next to this rank's GPU
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
 
@@ -521,6 +525,7 @@ def run_b200(args, rank, world, local_rank):
                "d2h_bytes_per_step": (nb + 1) * 4,
                "api": f"PillarEncoderPipeline.submit/result (depth {depth}) on pinned host batch_dict['points']",
                "pillars_checksum": checksum,
+               "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None,
                "module_forward": {"value": nb * world / (module_ms / K * 1e-3), "ms_per_step": module_ms / K,
                                   "api": "PillarVFEFromPoints(FUSE_SCATTER).forward + PointPillarScatter.forward, one "
                                          "blocking call per batch"}}

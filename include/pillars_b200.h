@@ -217,16 +217,21 @@ typedef struct pillars_tokenizer {
     float ln_eps;               /* norm_tokens.eps (1e-5)                                             */
     const float *pe;            /* [h*w, d_model] written by pillars_tokens_prepare                   */
     const float *background;    /* [d_model]      written by pillars_tokens_prepare                   */
+    const float *proj_frag;     /* [2*c_in*d_model] optional: the projection in tensor-core fragment order, written by
+                                   pillars_tokens_prepare.  When set (and c_in % 8 == 0, d_model 128 or 256) the 1x1
+                                   projection runs on the tensor cores as a 3-term TF32 split (fp32-accurate); NULL: FMA pipes */
 } pillars_tokenizer_t;
 
 /* Once per (weights, h, w): pe_out[cell] = geo_mlp.2(GELU(geo_mlp.0(geom[cell]))) + view_embed[sector[cell]] and
  * background_out = LayerNorm(proj(GELU(refine bias))), the token (before PE) of a cell whose 3x3 window is all zero.
  * geom [h*w,5] / sector [h*w] are the tables of VATLiDAR._grid (:123-185), computed by the caller;
  * geo_w1 [d,5] = geo_mlp.0.weight, geo_w2_t [d,d] = geo_mlp.2.weight TRANSPOSED, view_embed [6,d].
- * Reads tk->{c_in,d_model,dw_bias,proj_weight_t,proj_bias,ln_*}; tk->pe / tk->background are not read. */
+ * proj_frag_out (2*c_in*d_model floats, may be NULL) receives the table for tk->proj_frag.
+ * Reads tk->{c_in,d_model,dw_bias,proj_weight_t,proj_bias,ln_*}; tk->pe / background / proj_frag are not read. */
 int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
                            const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
-                           const float *view_embed, float *pe_out, float *background_out, void *stream);
+                           const float *view_embed, float *pe_out, float *background_out, float *proj_frag_out,
+                           void *stream);
 
 /* Scratch bytes: index map only (dense == 0, for pillars_bev_tokens) or index map + compacted rows (dense != 0). */
 size_t pillars_tokens_workspace_bytes(int32_t n_frames, int32_t c_in, int32_t h, int32_t w, int32_t dense);

@@ -261,11 +261,13 @@ struct TokenizerDev {
     const float *gamma, *beta; // LayerNorm
     float eps;
     const float *pe, *bg;      // [h*w, d], [d]
+    const float *wfrag;        // [2 * c * d] projection in tensor-core fragment order, or NULL (FMA projection)
 };
 bool tokens_shape_supported(int c, int d);
+bool tokens_mma_supported(int c, int d);
 cudaError_t launch_tokens_prepare(const TokenizerDev &tk, const float *geom, const int32_t *sid, int h, int w, const float *w1,
                                   const float *b1, const float *w2t, const float *b2, const float *view, float *pe, float *bg,
-                                  cudaStream_t st);
+                                  float *wfrag, cudaStream_t st);
 cudaError_t launch_canvas_to_rows(const float *bev, int nb, int c, int h, int w, int32_t *cell_row, float *rows,
                                   uint32_t *counter, cudaStream_t st);
 cudaError_t launch_bev_tokens(const TokenizerDev &tk, const float *feats, const int32_t *cell_row, int nb, int h, int w,

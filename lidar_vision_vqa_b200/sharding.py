@@ -88,3 +88,28 @@ def densify(tokens: GatheredTokens, nx: int, ny: int, variant: str = "auto") -> 
     from . import ops
 
     return ops.scatter_bev(tokens.pillar_features, tokens.voxel_coords, tokens.n_frames, nx, ny, 1, variant=variant)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Restricts this process to the CPUs NVML reports as local to GPU ``device_index`` (one process per GPU, so pinned
+    host buffers allocated afterwards are first-touched on that GPU's NUMA node and the host->device copies of the ranks do
+    not all cross the same socket link).  Returns the CPU list, or None when NVML / affinity is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 - best effort: no NVML, no permission, exotic topology
+        return None

@@ -49,8 +49,14 @@ def grid_tables(h: int, w: int) -> Tuple[torch.Tensor, torch.Tensor]:
 class VATLiDARTokenizer(nn.Module):
     """Drop-in for the tokenising part of ``VATLiDAR`` (same constructor arguments for that part, same parameter names)."""
 
-    def __init__(self, c_in: int, d_model: int):
+    def __init__(self, c_in: int, d_model: int, tensor_cores: bool = False):
+        """``tensor_cores``: run the 1x1 projection as a 3-term TF32 split (``mma.sync``, fp32-accurate) where the kernel
+        has that variant (c_in % 8 == 0, d_model 128 or 256) instead of fp32 FFMA2.  Off by default: measured slower on
+        B200 (1.80 vs 1.42 ms on 16 x 512^2 at d = 256) because register-fragment operands saturate the L1/LSU data pipe --
+        see DESIGN.md 4b."""
         super().__init__()
+        self.tensor_cores = bool(tensor_cores)
+        self._frag: Optional[torch.Tensor] = None
         self.c_in, self.d_model = int(c_in), int(d_model)
         self.refine = nn.Sequential(nn.Conv2d(c_in, c_in, kernel_size=3, padding=1, groups=c_in), nn.GELU())
         self.proj = nn.Conv2d(c_in, d_model, kernel_size=1, bias=True)
@@ -62,11 +68,11 @@ class VATLiDARTokenizer(nn.Module):
 
     # ---- parameters in the layout the kernels read, rebuilt when the module moves or loads a checkpoint ---------------
     def _apply(self, fn, *a, **k):
-        self._packed, self._tables = None, {}
+        self._packed, self._tables, self._frag = None, {}, None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed, self._tables = None, {}
+        self._packed, self._tables, self._frag = None, {}, None
         return super().load_state_dict(*a, **k)
 
     def _pack(self, dev) -> Dict[str, torch.Tensor]:
@@ -96,6 +102,7 @@ class VATLiDARTokenizer(nn.Module):
         t.ln_weight, t.ln_bias, t.ln_eps = pk["gamma"].data_ptr(), pk["beta"].data_ptr(), float(self.norm_tokens.eps)
         t.pe = None if pe is None else pe.data_ptr()
         t.background = None if bg is None else bg.data_ptr()
+        t.proj_frag = self._frag.data_ptr() if (self._frag is not None and pe is not None) else None
         return t
 
     def _device(self) -> torch.device:
@@ -119,10 +126,16 @@ class VATLiDARTokenizer(nn.Module):
             pe = torch.empty((h * w, self.d_model), dtype=torch.float32, device=dev)
             bg = torch.empty((self.d_model,), dtype=torch.float32, device=dev)
             nat = self._native_struct(pk)
+            frag = None
+            if self.tensor_cores and self._frag is None and self.c_in % 8 == 0 and self.d_model in (128, 256):
+                frag = torch.empty((2 * self.c_in * self.d_model,), dtype=torch.float32, device=dev)
             check(_native.load().pillars_tokens_prepare(ctypes.byref(nat), geom.data_ptr(), sid.data_ptr(), h, w,
                                                         pk["w1"].data_ptr(), pk["b1"].data_ptr(), pk["w2t"].data_ptr(),
                                                         pk["b2"].data_ptr(), pk["view"].data_ptr(), pe.data_ptr(),
-                                                        bg.data_ptr(), ops._stream_ptr()), "pillars_tokens_prepare")
+                                                        bg.data_ptr(), None if frag is None else frag.data_ptr(),
+                                                        ops._stream_ptr()), "pillars_tokens_prepare")
+            if frag is not None:
+                self._frag = frag
             self._tables[key] = (pe, bg)
         return self._tables[key]
 
