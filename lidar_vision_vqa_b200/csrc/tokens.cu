@@ -511,6 +511,103 @@ __global__ void __launch_bounds__(32 * kRowsWarps) k_canvas_to_rows(const float 
     }
 }
 
+// Vectorised variant (plane % 4 == 0, 16-byte aligned canvas): a lane scans 4 consecutive cells with 16-byte loads, a warp
+// 128 cells, eight channel planes in flight per lane.  Occupied cells of a sparse group are then fetched one by one (a cell's
+// channels are 4-byte gathers from planes that were just read, i.e. L2 hits, written as one coalesced row); a group with
+// more than a quarter of its cells occupied goes through the shared-memory transpose in 32-cell sub-groups instead.
+__global__ void __launch_bounds__(32 * kRowsWarps) k_canvas_to_rows_v4(const float *__restrict__ bev, int nb, int c, int64_t plane,
+                                                                      int32_t *__restrict__ cell_row, float *__restrict__ rows,
+                                                                      uint32_t *__restrict__ counter)
+{
+    __shared__ float s_t[kRowsWarps][32][65];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t groups_per_frame = (plane + 127) / 128;
+    const int64_t grp = static_cast<int64_t>(blockIdx.x) * kRowsWarps + warp;
+    if (grp >= groups_per_frame * nb) return;
+    const int b = static_cast<int>(grp / groups_per_frame);
+    const int64_t cell0 = (grp - b * groups_per_frame) * 128, cell = cell0 + 4 * lane;
+    const bool in = cell < plane;  // plane % 4 == 0: a lane's four cells are inside or outside together
+    const float *fbase = bev + static_cast<size_t>(b) * c * plane;
+    uint32_t bx = 0, by = 0, bz = 0, bw = 0;  // OR of the value bits without the sign: non-zero <=> some channel != +-0
+    if (in) {
+        const float4 *src = reinterpret_cast<const float4 *>(fbase + cell);
+        const size_t step = static_cast<size_t>(plane >> 2);
+        int ch = 0;
+        for (; ch + 8 <= c; ch += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (ch + k) * step);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                bx |= __float_as_uint(v[k].x); by |= __float_as_uint(v[k].y);
+                bz |= __float_as_uint(v[k].z); bw |= __float_as_uint(v[k].w);
+            }
+        }
+        for (; ch < c; ++ch) {
+            const float4 v = __ldg(src + ch * step);
+            bx |= __float_as_uint(v.x); by |= __float_as_uint(v.y); bz |= __float_as_uint(v.z); bw |= __float_as_uint(v.w);
+        }
+    }
+    const bool any[4] = {(bx & 0x7fffffffu) != 0u, (by & 0x7fffffffu) != 0u, (bz & 0x7fffffffu) != 0u, (bw & 0x7fffffffu) != 0u};
+    unsigned m[4];
+    int total = 0, before[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        m[j] = __ballot_sync(kFull, any[j]);
+        before[j] = total;
+        total += __popc(m[j]);
+    }
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(counter, static_cast<uint32_t>(total));
+    base = __shfl_sync(kFull, base, 0);
+    int32_t row[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        row[j] = any[j] ? static_cast<int32_t>(base + before[j] + __popc(m[j] & ((1u << lane) - 1u))) : -1;
+    if (in) *reinterpret_cast<int4 *>(cell_row + static_cast<size_t>(b) * plane + cell) = make_int4(row[0], row[1], row[2], row[3]);
+    if (!total) return;
+    if (total <= 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned mm = m[j];
+            while (mm) {
+                const int l = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const int32_t r = __shfl_sync(kFull, row[j], l);
+                const float *cp = fbase + cell0 + 4 * l + j;
+                for (int k = lane; k < c; k += 32) rows[static_cast<size_t>(r) * c + k] = __ldg(cp + static_cast<size_t>(k) * plane);
+            }
+        }
+        return;
+    }
+    // dense group: 32-cell sub-groups through the transpose tile; sub-group s holds cells cell0 + 32 s + lane', owned by
+    // lane (8 s + lane' / 4), component lane' % 4
+    for (int sgrp = 0; sgrp < 4; ++sgrp) {
+        const int owner = 8 * sgrp + (lane >> 2), comp = lane & 3;
+        int32_t my_row = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int32_t rj = __shfl_sync(kFull, row[j], owner);
+            if (comp == j) my_row = rj;
+        }
+        const unsigned sm = __ballot_sync(kFull, my_row >= 0);
+        if (!sm) continue;
+        const int64_t scell = cell0 + 32 * sgrp + lane;
+        const bool sin = scell < plane;
+        for (int ch0 = 0; ch0 < c; ch0 += 64) {
+            const int nch = min(64, c - ch0);
+            __syncwarp();
+            for (int k = 0; k < nch; ++k) s_t[warp][lane][k] = sin ? __ldg(fbase + static_cast<size_t>(ch0 + k) * plane + scell) : 0.f;
+            __syncwarp();
+            for (int l = 0; l < 32; ++l) {
+                if (!((sm >> l) & 1u)) continue;
+                const int32_t r = __shfl_sync(kFull, my_row, l);
+                for (int k = lane; k < nch; k += 32) rows[static_cast<size_t>(r) * c + ch0 + k] = s_t[warp][l][k];
+            }
+        }
+    }
+}
+
 // Projection matrix in mma.m16n8k8 A-fragment order, split into tf32 hi / lo: for k-step ks (8 input channels), channel tile
 // m (16 outputs) and lane l = 4 gq + tq:  {a0,a1,a2,a3} = Wp[16m + gq (+8)][8ks + tq (+4)]  as 4 hi words then 4 lo words.
 __global__ void k_tok_wfrag(const float *__restrict__ wt, int c, int d, uint32_t *__restrict__ frag)
@@ -578,6 +675,14 @@ cudaError_t launch_canvas_to_rows(const float *bev, int nb, int c, int h, int w,
     note_launch();
     if (e != cudaSuccess) return e;
     const int64_t plane = static_cast<int64_t>(h) * w;
+    if (plane % 4 == 0 && reinterpret_cast<uintptr_t>(bev) % 16 == 0 && reinterpret_cast<uintptr_t>(cell_row) % 16 == 0) {
+        const int64_t groups4 = (plane + 127) / 128 * nb;
+        if (groups4 == 0) return cudaSuccess;
+        k_canvas_to_rows_v4<<<static_cast<unsigned>((groups4 + kRowsWarps - 1) / kRowsWarps), 32 * kRowsWarps, 0, st>>>(
+            bev, nb, c, plane, cell_row, rows, counter);
+        note_launch();
+        return cudaGetLastError();
+    }
     const int64_t groups = (plane + 31) / 32 * nb;
     if (groups == 0) return cudaSuccess;
     k_canvas_to_rows<<<static_cast<unsigned>((groups + kRowsWarps - 1) / kRowsWarps), 32 * kRowsWarps, 0, st>>>(
