@@ -72,7 +72,7 @@ __global__ void k_frame_offsets(const float *__restrict__ pts, int64_t n, int st
 // ---------------------------------------------------------------------------------------------
 // K1: one point per thread, 256 points per CTA
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)
 k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int col0,
                   const int32_t *__restrict__ frame_offsets, int nb, GridDev gd, HashEntry *__restrict__ table,
                   uint32_t cap, int32_t *__restrict__ point_slot, uint32_t *__restrict__ point_arrival, int vec_ok,
