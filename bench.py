@@ -435,6 +435,8 @@ def run_b200(args, rank, world, local_rank):
                 "traffic": ncu_traffic("k_scatter_wide", args.workload) if args.scatter_variant in ("auto", "wide") else None,
                 "traffic_source": "profiles/r01_traffic.json (ncu --set full, one launch, dram read + write bytes)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["S"],
+                "note": "the peak is a COPY measurement (read + write); a pure write stream can exceed it slightly, so frac may "
+                        "land a fraction of a percent above 1",
                 "avg_launch_ms": float(stage_avg[2]), "share_of_step": float(stage_avg[2] / serial_ms_per_step),
                 "timed_in": "single-stream pass of the same K steps (kernels do not overlap there)"}
     stages = {
