@@ -220,20 +220,24 @@ typedef struct pillars_tokenizer {
     const float *proj_frag;     /* [2*c_in*d_model] optional: the projection in tensor-core fragment order, written by
                                    pillars_tokens_prepare.  When set (and c_in % 8 == 0, d_model 128 or 256) the 1x1
                                    projection runs on the tensor cores as a 3-term TF32 split (fp32-accurate); NULL: FMA pipes */
+    const float *proj_umma;     /* [2*c_in*d_model] optional: the projection as the shared-memory image of the tcgen05 variant
+                                   (tf32 hi | lo halves, K-major, 128-byte swizzle), written by pillars_tokens_prepare.  When set
+                                   (c_in 32 or 64, d_model 128 or 256) and a workspace is given, the active cells of the batch are
+                                   compacted into 128-row tiles and projected with tcgen05.mma.kind::tf32 (accumulator in TMEM) */
 } pillars_tokenizer_t;
 
 /* Once per (weights, h, w): pe_out[cell] = geo_mlp.2(GELU(geo_mlp.0(geom[cell]))) + view_embed[sector[cell]] and
  * background_out = LayerNorm(proj(GELU(refine bias))), the token (before PE) of a cell whose 3x3 window is all zero.
  * geom [h*w,5] / sector [h*w] are the tables of VATLiDAR._grid (:123-185), computed by the caller;
  * geo_w1 [d,5] = geo_mlp.0.weight, geo_w2_t [d,d] = geo_mlp.2.weight TRANSPOSED, view_embed [6,d].
- * proj_frag_out (2*c_in*d_model floats, may be NULL) receives the table for tk->proj_frag.
+ * proj_frag_out / proj_umma_out (2*c_in*d_model floats each, may be NULL) receive the tables for tk->proj_frag / proj_umma.
  * Reads tk->{c_in,d_model,dw_bias,proj_weight_t,proj_bias,ln_*}; tk->pe / background / proj_frag are not read. */
 int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
                            const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
                            const float *view_embed, float *pe_out, float *background_out, float *proj_frag_out,
-                           void *stream);
+                           float *proj_umma_out, void *stream);
 
-/* Scratch bytes: index map only (dense == 0, for pillars_bev_tokens) or index map + compacted rows (dense != 0). */
+/* Scratch bytes: index map + pair list (dense == 0, for pillars_bev_tokens / _map) or those + compacted rows (dense != 0). */
 size_t pillars_tokens_workspace_bytes(int32_t n_frames, int32_t c_in, int32_t h, int32_t w, int32_t dense);
 
 /* Tokens straight from pillar rows, no dense canvas: feats [m, c_in] and coords [m,4] (b,z,y,x) exactly as
@@ -242,9 +246,12 @@ int pillars_bev_tokens(const float *feats, const void *coords, int32_t coords_is
                        int32_t n_frames, int32_t h, int32_t w, const pillars_tokenizer_t *tk, float *tokens,
                        void *workspace, size_t workspace_bytes, void *stream);
 
-/* Same with an index map that already exists: cell_row [n_frames, h, w] int32, row of the pillar in the cell or -1. */
+/* Same with an index map that already exists: cell_row [n_frames, h, w] int32, row of the pillar in the cell or -1.
+ * workspace (pillars_tokens_workspace_bytes(..., 0) bytes) is only needed by the tcgen05 variant (tk->proj_umma); with
+ * workspace == NULL that variant is not used. */
 int pillars_bev_tokens_map(const float *feats, const int32_t *cell_row, int32_t n_frames, int32_t h, int32_t w,
-                           const pillars_tokenizer_t *tk, float *tokens, void *stream);
+                           const pillars_tokenizer_t *tk, float *tokens, void *workspace, size_t workspace_bytes,
+                           void *stream);
 
 /* VATLiDAR's own input: a dense canvas bev [n_frames, c_in, h, w].  Cells with a non-zero channel are compacted into rows
  * (workspace), then the same kernel runs; on a canvas without zeros every cell takes the arithmetic path. */

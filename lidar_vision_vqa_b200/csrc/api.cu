@@ -535,6 +535,8 @@ static int check_tokenizer(const pillars_tokenizer_t *tk, bool need_tables, Toke
     td->dw_w = tk->dw_weight; td->dw_b = tk->dw_bias; td->wt = tk->proj_weight_t; td->pb = tk->proj_bias;
     td->gamma = tk->ln_weight; td->beta = tk->ln_bias; td->eps = tk->ln_eps; td->pe = tk->pe; td->bg = tk->background;
     td->wfrag = need_tables ? tk->proj_frag : nullptr;
+    td->wimg = need_tables ? tk->proj_umma : nullptr;
+    if (td->wimg && reinterpret_cast<uintptr_t>(td->wimg) % 16 != 0) return fail(PILLARS_E_BADARG, "proj_umma not 16-byte aligned");
     if (td->wfrag && reinterpret_cast<uintptr_t>(td->wfrag) % 16 != 0) return fail(PILLARS_E_BADARG, "proj_frag not 16-byte aligned");
     return 0;
 }
@@ -542,7 +544,7 @@ static int check_tokenizer(const pillars_tokenizer_t *tk, bool need_tables, Toke
 int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
                            const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
                            const float *view_embed, float *pe_out, float *background_out, float *proj_frag_out,
-                           void *stream)
+                           float *proj_umma_out, void *stream)
 {
     g_launches = 0;
     TokenizerDev td{};
@@ -556,6 +558,9 @@ int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, con
     cudaError_t e = launch_tokens_prepare(td, geom, sector, h, w, geo_w1, geo_b1, geo_w2_t, geo_b2, view_embed, pe_out,
                                           background_out, proj_frag_out, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "tokens_prepare");
+    if (proj_umma_out && tokens_umma_supported(td.c, td.d) &&
+        (e = launch_tokens_wimg(td.wt, td.c, td.d, proj_umma_out, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+        return cuda_fail(e, "tokens_wimg");
     g_launches_last = g_launches;
     return 0;
 }
@@ -565,10 +570,26 @@ static size_t tokens_map_bytes(int32_t n_frames, int32_t h, int32_t w)
     return align_up(sizeof(int32_t) * static_cast<size_t>(n_frames) * h * w, 256);
 }
 
+// pair list of the tcgen05 variant: a counter (256 B) + one 32-bit entry per (frame, cell)
+static size_t tokens_list_bytes(int32_t n_frames, int32_t h, int32_t w) { return 256 + tokens_map_bytes(n_frames, h, w); }
+
+// runs the tokeniser on rows + index map; `scratch` (tokens_list_bytes, 256-byte aligned) enables the tcgen05 variant
+static cudaError_t run_tokens(const TokenizerDev &td, const float *feats, const int32_t *cell_row, int32_t n_frames, int32_t h,
+                              int32_t w, float *tokens, void *scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (td.wimg && tokens_umma_supported(td.c, td.d) && scratch && reinterpret_cast<uintptr_t>(scratch) % 256 == 0 &&
+        scratch_bytes >= tokens_list_bytes(n_frames, h, w)) {
+        uint32_t *count = static_cast<uint32_t *>(scratch);
+        uint32_t *list = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) + 256);
+        return launch_bev_tokens_umma(td, feats, cell_row, n_frames, h, w, tokens, list, count, st);
+    }
+    return launch_bev_tokens(td, feats, cell_row, n_frames, h, w, tokens, st);
+}
+
 size_t pillars_tokens_workspace_bytes(int32_t n_frames, int32_t c_in, int32_t h, int32_t w, int32_t dense)
 {
     if (n_frames < 0 || c_in < 0 || h < 0 || w < 0) return 0;
-    size_t b = tokens_map_bytes(n_frames, h, w);
+    size_t b = tokens_map_bytes(n_frames, h, w) + tokens_list_bytes(n_frames, h, w);
     if (dense) b += 256 + align_up(sizeof(float) * static_cast<size_t>(n_frames) * h * w * c_in, 256);
     return b;
 }
@@ -585,7 +606,7 @@ static int check_tokens_call(const pillars_tokenizer_t *tk, int32_t n_frames, in
 }
 
 int pillars_bev_tokens_map(const float *feats, const int32_t *cell_row, int32_t n_frames, int32_t h, int32_t w,
-                           const pillars_tokenizer_t *tk, float *tokens, void *stream)
+                           const pillars_tokenizer_t *tk, float *tokens, void *workspace, size_t workspace_bytes, void *stream)
 {
     g_launches = 0;
     TokenizerDev td{};
@@ -593,7 +614,10 @@ int pillars_bev_tokens_map(const float *feats, const int32_t *cell_row, int32_t 
     if ((rc = check_tokens_call(tk, n_frames, h, w, tokens, &td))) return rc;
     if (static_cast<int64_t>(n_frames) * h * w == 0) return 0;
     if (!cell_row) return fail(PILLARS_E_BADARG, "cell_row is NULL");
-    cudaError_t e = launch_bev_tokens(td, feats, cell_row, n_frames, h, w, tokens, static_cast<cudaStream_t>(stream));
+    // the pair list sits behind the (unused here) index-map part of a pillars_tokens_workspace_bytes(..., 0) workspace
+    char *scratch = workspace ? static_cast<char *>(workspace) + tokens_map_bytes(n_frames, h, w) : nullptr;
+    const size_t scratch_bytes = workspace && workspace_bytes > tokens_map_bytes(n_frames, h, w) ? workspace_bytes - tokens_map_bytes(n_frames, h, w) : 0;
+    cudaError_t e = run_tokens(td, feats, cell_row, n_frames, h, w, tokens, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "bev_tokens");
     g_launches_last = g_launches;
     return 0;
@@ -618,7 +642,9 @@ int pillars_bev_tokens(const float *feats, const void *coords, int32_t coords_is
     cudaError_t e;
     if ((e = launch_build_cell_row(coords, coords_is_float != 0, m, m_dev, n_frames, w, h, 1, cell_row, st)) != cudaSuccess)
         return cuda_fail(e, "build_cell_row");
-    if ((e = launch_bev_tokens(td, feats, cell_row, n_frames, h, w, tokens, st)) != cudaSuccess) return cuda_fail(e, "bev_tokens");
+    char *scratch = static_cast<char *>(workspace) + need;
+    if ((e = run_tokens(td, feats, cell_row, n_frames, h, w, tokens, scratch, workspace_bytes - need, st)) != cudaSuccess)
+        return cuda_fail(e, "bev_tokens");
     g_launches_last = g_launches;
     return 0;
 }
@@ -638,12 +664,15 @@ int pillars_bev_tokens_dense(const float *bev, int32_t n_frames, int32_t h, int3
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char *base = static_cast<char *>(workspace);
     int32_t *cell_row = reinterpret_cast<int32_t *>(base);
-    uint32_t *counter = reinterpret_cast<uint32_t *>(base + tokens_map_bytes(n_frames, h, w));
-    float *rows = reinterpret_cast<float *>(base + tokens_map_bytes(n_frames, h, w) + 256);
+    char *scratch = base + tokens_map_bytes(n_frames, h, w);
+    const size_t scratch_bytes = tokens_list_bytes(n_frames, h, w);
+    uint32_t *counter = reinterpret_cast<uint32_t *>(scratch + scratch_bytes);
+    float *rows = reinterpret_cast<float *>(scratch + scratch_bytes + 256);
     cudaError_t e;
     if ((e = launch_canvas_to_rows(bev, n_frames, tk->c_in, h, w, cell_row, rows, counter, st)) != cudaSuccess)
         return cuda_fail(e, "canvas_to_rows");
-    if ((e = launch_bev_tokens(td, rows, cell_row, n_frames, h, w, tokens, st)) != cudaSuccess) return cuda_fail(e, "bev_tokens");
+    if ((e = run_tokens(td, rows, cell_row, n_frames, h, w, tokens, scratch, scratch_bytes, st)) != cudaSuccess)
+        return cuda_fail(e, "bev_tokens");
     g_launches_last = g_launches;
     return 0;
 }

@@ -49,13 +49,20 @@ def grid_tables(h: int, w: int) -> Tuple[torch.Tensor, torch.Tensor]:
 class VATLiDARTokenizer(nn.Module):
     """Drop-in for the tokenising part of ``VATLiDAR`` (same constructor arguments for that part, same parameter names)."""
 
-    def __init__(self, c_in: int, d_model: int, tensor_cores: bool = False):
-        """``tensor_cores``: run the 1x1 projection as a 3-term TF32 split (``mma.sync``, fp32-accurate) where the kernel
-        has that variant (c_in % 8 == 0, d_model 128 or 256) instead of fp32 FFMA2.  Off by default: measured slower on
-        B200 (1.80 vs 1.42 ms on 16 x 512^2 at d = 256) because register-fragment operands saturate the L1/LSU data pipe --
-        see DESIGN.md 4b."""
+    def __init__(self, c_in: int, d_model: int, projection: str = "auto"):
+        """``projection`` selects how the 1x1 projection runs (all variants are fp32-accurate and parity-tested):
+        ``"fma"``   fp32 FFMA2 on the FMA pipes, any supported shape;
+        ``"umma"``  tcgen05.mma.kind::tf32 as a 3-term hi/lo split, accumulator in tensor memory, the active cells of the
+                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256);
+        ``"mma"``   the same split with legacy ``mma.sync`` (c_in % 8 == 0, d_model 128 or 256) -- measured slower than
+                    ``"fma"``, kept as evidence (DESIGN.md 4b);
+        ``"auto"``  ``"umma"`` where it exists, else ``"fma"``."""
         super().__init__()
-        self.tensor_cores = bool(tensor_cores)
+        if projection not in ("auto", "fma", "mma", "umma"):
+            raise ValueError("projection must be one of auto / fma / mma / umma")
+        umma_ok = c_in in (32, 64) and d_model in (128, 256)
+        self.projection = ("umma" if umma_ok else "fma") if projection == "auto" else projection
+        self._umma: Optional[torch.Tensor] = None
         self._frag: Optional[torch.Tensor] = None
         self.c_in, self.d_model = int(c_in), int(d_model)
         self.refine = nn.Sequential(nn.Conv2d(c_in, c_in, kernel_size=3, padding=1, groups=c_in), nn.GELU())
@@ -68,11 +75,11 @@ class VATLiDARTokenizer(nn.Module):
 
     # ---- parameters in the layout the kernels read, rebuilt when the module moves or loads a checkpoint ---------------
     def _apply(self, fn, *a, **k):
-        self._packed, self._tables, self._frag = None, {}, None
+        self._packed, self._tables, self._frag, self._umma = None, {}, None, None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed, self._tables, self._frag = None, {}, None
+        self._packed, self._tables, self._frag, self._umma = None, {}, None, None
         return super().load_state_dict(*a, **k)
 
     def _pack(self, dev) -> Dict[str, torch.Tensor]:
@@ -103,6 +110,7 @@ class VATLiDARTokenizer(nn.Module):
         t.pe = None if pe is None else pe.data_ptr()
         t.background = None if bg is None else bg.data_ptr()
         t.proj_frag = self._frag.data_ptr() if (self._frag is not None and pe is not None) else None
+        t.proj_umma = self._umma.data_ptr() if (self._umma is not None and pe is not None) else None
         return t
 
     def _device(self) -> torch.device:
@@ -126,16 +134,21 @@ class VATLiDARTokenizer(nn.Module):
             pe = torch.empty((h * w, self.d_model), dtype=torch.float32, device=dev)
             bg = torch.empty((self.d_model,), dtype=torch.float32, device=dev)
             nat = self._native_struct(pk)
-            frag = None
-            if self.tensor_cores and self._frag is None and self.c_in % 8 == 0 and self.d_model in (128, 256):
+            frag = umma = None
+            if self.projection == "mma" and self._frag is None and self.c_in % 8 == 0 and self.d_model in (128, 256):
                 frag = torch.empty((2 * self.c_in * self.d_model,), dtype=torch.float32, device=dev)
+            if self.projection == "umma" and self._umma is None and self.c_in in (32, 64) and self.d_model in (128, 256):
+                umma = torch.empty((2 * self.c_in * self.d_model,), dtype=torch.float32, device=dev)
             check(_native.load().pillars_tokens_prepare(ctypes.byref(nat), geom.data_ptr(), sid.data_ptr(), h, w,
                                                         pk["w1"].data_ptr(), pk["b1"].data_ptr(), pk["w2t"].data_ptr(),
                                                         pk["b2"].data_ptr(), pk["view"].data_ptr(), pe.data_ptr(),
                                                         bg.data_ptr(), None if frag is None else frag.data_ptr(),
+                                                        None if umma is None else umma.data_ptr(),
                                                         ops._stream_ptr()), "pillars_tokens_prepare")
             if frag is not None:
                 self._frag = frag
+            if umma is not None:
+                self._umma = umma
             self._tables[key] = (pe, bg)
         return self._tables[key]
 
@@ -204,8 +217,13 @@ class VATLiDARTokenizer(nn.Module):
         feats = pillar_features.contiguous()
         tokens = self._out(out, b, h, w, dev)
         nat = self._native_struct(self._pack(dev), pe, bg)
-        check(_native.load().pillars_bev_tokens_map(feats.data_ptr(), cell_row.data_ptr(), b, h, w, ctypes.byref(nat),
-                                                    tokens.data_ptr(), ops._stream_ptr()), "pillars_bev_tokens_map")
+        lib = _native.load()
+        ws_ptr, ws_len = None, 0
+        if self._umma is not None:  # the tcgen05 variant keeps its (frame, cell) pair list in a workspace
+            ws = ops.workspace(lib.pillars_tokens_workspace_bytes(b, self.c_in, h, w, 0), dev, slot=7)
+            ws_ptr, ws_len = ws.data_ptr(), ws.numel()
+        check(lib.pillars_bev_tokens_map(feats.data_ptr(), cell_row.data_ptr(), b, h, w, ctypes.byref(nat), tokens.data_ptr(),
+                                         ws_ptr, ws_len, ops._stream_ptr()), "pillars_bev_tokens_map")
         return tokens
 
 

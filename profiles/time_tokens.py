@@ -1,5 +1,5 @@
 """Timing of the BEV tokeniser (csrc/tokens.cu) on the cfg2 canvas: pillars_encode_bev -> tokens from the encoder's index
-map.  Usage: python profiles/time_tokens.py [frames] [d_model] [--dense] [--mma]"""
+map.  Usage: python profiles/time_tokens.py [frames] [d_model] [--dense] [--fma|--mma]"""
 import os
 import sys
 
@@ -28,7 +28,8 @@ p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
 bufs = ops.EncodeBuffers(len(pts), nb, grid, 64, dev)
 res = ops.encode_bev(p, o, grid, pfn, buffers=bufs)
 sd = to.random_token_params(64, d, seed=11)
-tk = T.VATLiDARTokenizer(64, d, tensor_cores="--mma" in sys.argv)
+proj = "mma" if "--mma" in sys.argv else "fma" if "--fma" in sys.argv else "umma"
+tk = T.VATLiDARTokenizer(64, d, projection=proj)
 tk.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
 tk = tk.eval().to(dev)
 cell_row = T.encode_index_map(bufs, len(pts), nb, grid)
@@ -49,6 +50,6 @@ for _ in range(10):
 ms = float(np.median(ts))
 gb = out.numel() * 4 / 1e9
 pe_gb = 512 * 512 * d * 4 / 1e9
-print(f"tokens nb={nb} d={d} {'dense' if dense else 'rows'} {'mma' if '--mma' in sys.argv else 'fma'}: {ms * 1e3:.0f} us, write {gb / ms * 1e3:.0f} GB/s "
+print(f"tokens nb={nb} d={d} {'dense' if dense else 'rows'} {proj}: {ms * 1e3:.0f} us, write {gb / ms * 1e3:.0f} GB/s "
       f"(+PE read {pe_gb:.2f} GB), cells with a non-empty window {100 * active:.1f} %, tables prepared in {t_prep:.1f} ms",
       flush=True)

@@ -41,7 +41,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_native.PillarsGrid) == 6 * 4 + 3 * 4 + 3 * 4 + 4 + 4
     assert ctypes.sizeof(_native.PillarsPfn) == 5 * 4 + 3 * 4 + 4 * 8
     assert ctypes.sizeof(_native.PillarsOutputs) == 10 * 8
-    assert ctypes.sizeof(_native.PillarsTokenizer) == 2 * 4 + 6 * 8 + 8 + 3 * 8  # eps padded to 8
+    assert ctypes.sizeof(_native.PillarsTokenizer) == 2 * 4 + 6 * 8 + 8 + 4 * 8  # eps padded to 8
 
 
 def test_workspace_query_and_argument_errors(lib):
@@ -169,12 +169,12 @@ def test_tokenizer_argument_errors(lib):
 
     t = _native.PillarsTokenizer()
     t.c_in, t.d_model = 64, 100  # d_model must be a multiple of 128
-    assert lib.pillars_bev_tokens_map(None, None, 1, 8, 8, ctypes.byref(t), None, None) == -3
+    assert lib.pillars_bev_tokens_map(None, None, 1, 8, 8, ctypes.byref(t), None, None, 0, None) == -3
     assert b"d_model" in lib.pillars_last_error()
-    assert lib.pillars_bev_tokens_map(None, None, 1, 8, 8, None, None, None) == -1
+    assert lib.pillars_bev_tokens_map(None, None, 1, 8, 8, None, None, None, 0, None) == -1
     a = lib.pillars_tokens_workspace_bytes(2, 64, 16, 16, 0)
     b = lib.pillars_tokens_workspace_bytes(2, 64, 16, 16, 1)
-    assert 2 * 16 * 16 * 4 <= a < b and b >= a + 2 * 16 * 16 * 64 * 4
+    assert 2 * 2 * 16 * 16 * 4 <= a < b and b >= a + 2 * 16 * 16 * 64 * 4
     g = _native.make_grid((-51.2, -51.2, -5, 51.2, 51.2, 3), (0.2, 0.2, 8), (512, 512, 1), 32, 30000)
     off = lib.pillars_workspace_cell_row_offset(100_000, 4, ctypes.byref(g))
     assert 0 < off and off + 4 * 4 * 512 * 512 <= lib.pillars_workspace_bytes(100_000, 4, ctypes.byref(g))

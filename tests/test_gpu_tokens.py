@@ -31,11 +31,11 @@ def dev():
     return torch.device("cuda:0")
 
 
-def make_tokenizer(sd, dev, tensor_cores=False):
+def make_tokenizer(sd, dev, projection="auto"):
     from lidar_vision_vqa_b200 import tokens as T
 
     c, d = sd["refine.0.bias"].shape[0], sd["proj.bias"].shape[0]
-    tk = T.VATLiDARTokenizer(c_in=c, d_model=d, tensor_cores=tensor_cores)
+    tk = T.VATLiDARTokenizer(c_in=c, d_model=d, projection=projection)
     tk.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
     return tk.eval().to(dev)
 
@@ -50,12 +50,12 @@ def rows_of(bev):
     return feats, coords
 
 
-@pytest.mark.parametrize("tensor_cores", [True, False])
+@pytest.mark.parametrize("projection", ["umma", "fma", "mma"])
 @pytest.mark.parametrize("name", token_golden_names())
-def test_dense_forward_matches_reference_golden(dev, name, tensor_cores):
+def test_dense_forward_matches_reference_golden(dev, name, projection):
     """Both projection variants: 3-term TF32 split on the tensor cores (where instantiated) and fp32 on the FMA pipes."""
     g = load_golden(name)
-    tk = make_tokenizer(g["state_dict"], dev, tensor_cores)
+    tk = make_tokenizer(g["state_dict"], dev, projection)
     out = tk(torch.from_numpy(g["bev"]).to(dev)).cpu().numpy()
     assert out.shape == g["out.tokens"].shape
     np.testing.assert_allclose(out, g["out.tokens"], rtol=TOK_RTOL, atol=TOK_ATOL)
@@ -175,8 +175,9 @@ def test_cfg2_canvas_tokens_from_the_fused_encoder(dev):
     m = int(res["pillar_count"][-1].item())
     assert int((cell_row >= 0).sum().item()) == m
     tok_map = tk.forward_index_map(res["pillar_features"], cell_row)
-    tok_mma = make_tokenizer(sd, dev, tensor_cores=True).forward_index_map(res["pillar_features"], cell_row)
-    assert float((tok_map - tok_mma).abs().max()) < 2e-5  # tensor-core 3xTF32 split vs fp32 FMA projection
+    for other in ("fma", "mma"):  # tcgen05 split (default here) vs fp32 FFMA2 vs mma.sync split
+        tok_o = make_tokenizer(sd, dev, projection=other).forward_index_map(res["pillar_features"], cell_row)
+        assert float((tok_map - tok_o).abs().max()) < 3e-5, other
     tok_dense = tk(res["bev"])
     tok_rows = tk.forward_pillars(res["pillar_features"], res["voxel_coords"], nb, (512, 512), pillar_count=res["pillar_count"])
     assert torch.equal(tok_map, tok_dense) and torch.equal(tok_map, tok_rows)
