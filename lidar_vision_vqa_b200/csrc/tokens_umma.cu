@@ -26,7 +26,9 @@ namespace pillars {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kUT = 256;        // threads of both kernels
+constexpr int kUT = 256;        // threads of the streaming kernel
+constexpr int kUmmaT = 512;     // threads of the tcgen05 kernel: 4 TMEM lane quarters x kParts column parts
+constexpr int kParts = kUmmaT / 128;
 constexpr int kUW = kUT / 32;
 constexpr int kTileM = 128;     // pairs per GEMM tile = TMEM lanes
 constexpr int kTileX = 32;
@@ -48,7 +50,8 @@ struct StreamListParams {
 // -------------------------------------------------------------------------------------------------------------------
 // pass over the index map: stream the input-independent tokens, list the rest.  NQ = d / 128.
 // -------------------------------------------------------------------------------------------------------------------
-template <int NQ>
+// kMode 0: both duties in one pass; 1: list only (cheap, runs first); 2: stream only (runs beside the tcgen05 kernel)
+template <int NQ, int kMode>
 __global__ void __launch_bounds__(kUT) k_tok_stream_list(const __grid_constant__ StreamListParams p)
 {
     __shared__ int32_t s_map[kFrameChunk][3][kTileX + 2];
@@ -89,14 +92,14 @@ __global__ void __launch_bounds__(kUT) k_tok_stream_list(const __grid_constant__
             if (x >= w) break;
             const size_t cell = static_cast<size_t>(y) * w + x;
             const unsigned amask = __ballot_sync(kFull, lane < nbb && ((s_act[lane & (kFrameChunk - 1)] >> t) & 1u));
-            if (amask) {
+            if (kMode != 2 && amask) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&s_count, static_cast<uint32_t>(__popc(amask)));
                 base = __shfl_sync(kFull, base, 0);
                 if ((amask >> lane) & 1u)
                     s_list[base + __popc(amask & ((1u << lane) - 1u))] = static_cast<uint32_t>((b0 + lane) * plane + cell);
             }
-            if (__popc(amask) == nbb) continue;
+            if (kMode == 1 || __popc(amask) == nbb) continue;
             float4 v[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(kUT) k_tok_stream_list(const __grid_constant__
             }
         }
         __syncthreads();
-        const uint32_t n = s_count;
+        const uint32_t n = kMode == 2 ? 0u : s_count;
         if (n) {
             if (tid == 0) s_base = atomicAdd(p.count, n);
             __syncthreads();
@@ -202,7 +205,7 @@ __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo)
     hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
 }
 
-__global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ UmmaParams p)
+__global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ UmmaParams p)
 {
     extern __shared__ __align__(1024) uint8_t s_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -215,10 +218,10 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
     uint8_t *const s_a = s_al + 2 * w_half;           // A_hi | A_lo
     float *const s_dw = reinterpret_cast<float *>(s_a + 2 * a_half);  // [10][c]
     float *const s_vec = s_dw + 10 * c;                                // pb | gamma | beta, [3][d]
-    int32_t *const s_nb = reinterpret_cast<int32_t *>(s_vec + 3 * d);  // [128][9]
-    uint32_t *const s_ent = reinterpret_cast<uint32_t *>(s_nb + kTileM * 9);  // [128]
-    float *const s_stat = reinterpret_cast<float *>(s_ent + kTileM);          // [2][128]
-    uint64_t *const s_mbar = reinterpret_cast<uint64_t *>(s_stat + 2 * kTileM);
+    int32_t *const s_nb_all = reinterpret_cast<int32_t *>(s_vec + 3 * d);            // [2][128][9] (double buffered per tile)
+    uint32_t *const s_ent_all = reinterpret_cast<uint32_t *>(s_nb_all + 2 * kTileM * 9);  // [2][128]
+    float *const s_stat = reinterpret_cast<float *>(s_ent_all + 2 * kTileM);          // [kParts][128]
+    uint64_t *const s_mbar = reinterpret_cast<uint64_t *>(s_stat + kParts * kTileM);
     uint32_t *const s_tmem = reinterpret_cast<uint32_t *>(s_mbar + 1);
 
     // ---- one-time setup: TMEM columns, mbarrier, W image, small vectors ----------------------------------------------------
@@ -233,14 +236,14 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
     {
         const uint4 *src = p.wimg;
         uint4 *dst = reinterpret_cast<uint4 *>(s_w);
-        for (uint32_t i = tid; i < (2 * w_half) >> 4; i += kUT) dst[i] = __ldg(src + i);
+        for (uint32_t i = tid; i < (2 * w_half) >> 4; i += kUmmaT) dst[i] = __ldg(src + i);
     }
-    for (int i = tid; i < 9 * c; i += kUT) {
+    for (int i = tid; i < 9 * c; i += kUmmaT) {
         const int ch = i / 9, k = i - ch * 9;
         s_dw[k * c + ch] = __ldg(p.dw_w + i);
     }
-    for (int i = tid; i < c; i += kUT) s_dw[9 * c + i] = __ldg(p.dw_b + i);
-    for (int i = tid; i < d; i += kUT) {
+    for (int i = tid; i < c; i += kUmmaT) s_dw[9 * c + i] = __ldg(p.dw_b + i);
+    for (int i = tid; i < d; i += kUmmaT) {
         s_vec[i] = __ldg(p.pb + i);
         s_vec[d + i] = __ldg(p.gamma + i);
         s_vec[2 * d + i] = __ldg(p.beta + i);
@@ -256,27 +259,42 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
     const size_t plane = static_cast<size_t>(h) * w;
     uint32_t parity = 0;
 
-    for (uint32_t tile = blockIdx.x; static_cast<uint64_t>(tile) * kTileM < n_total; tile += gridDim.x) {
-        // ---- the tile's pairs and the pillar rows of their 3x3 windows -------------------------------------------------------
+    // A tile's pairs and the pillar rows of their 3x3 windows (threads 0..127), one tile AHEAD of the arithmetic: the index
+    // lookups run under the previous tile's MMA, and the rows / PE lines the tile will touch are requested into L2 right away.
+    auto load_meta = [&](uint32_t tile, int buf) {
         if (tid < kTileM) {
             const uint32_t idx = tile * kTileM + tid;
-            const uint32_t e = idx < n_total ? __ldg(p.list + idx) : kNoEntry;
-            s_ent[tid] = e;
+            const uint32_t e = (static_cast<uint64_t>(tile) * kTileM < n_total && idx < n_total) ? __ldg(p.list + idx) : kNoEntry;
+            s_ent_all[buf * kTileM + tid] = e;
             if (e != kNoEntry) {
                 const uint32_t b = e / static_cast<uint32_t>(plane), cell = e - b * static_cast<uint32_t>(plane);
                 const int yy0 = static_cast<int>(cell / w), xx0 = static_cast<int>(cell - static_cast<uint32_t>(yy0) * w);
+                int32_t *nb = s_nb_all + (buf * kTileM + tid) * 9;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     const int yy = yy0 + k / 3 - 1, xx = xx0 + k % 3 - 1;
                     int32_t r = -1;
                     if (yy >= 0 && yy < h && xx >= 0 && xx < w) r = __ldg(p.cell_row + (static_cast<size_t>(b) * h + yy) * w + xx);
-                    s_nb[tid * 9 + k] = r;
+                    nb[k] = r;
+                    if (r >= 0) {
+                        const char *row = reinterpret_cast<const char *>(p.feats + static_cast<size_t>(r) * c);
+                        for (int o = 0; o < c * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                    }
                 }
+                const char *pe = reinterpret_cast<const char *>(p.pe + static_cast<size_t>(cell) * d);
+                for (int o = 0; o < d * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + o));
             }
         }
-        __syncthreads();
+    };
+    load_meta(blockIdx.x, 0);
+    __syncthreads();
+    int cur = 0;
+
+    for (uint32_t tile = blockIdx.x; static_cast<uint64_t>(tile) * kTileM < n_total; tile += gridDim.x, cur ^= 1) {
+        const int32_t *const s_nb = s_nb_all + cur * kTileM * 9;
+        const uint32_t *const s_ent = s_ent_all + cur * kTileM;
         // ---- refine: A[row][channel] = GELU(depthwise 3x3 + bias), split into tf32 hi / lo, written in the swizzled layout --------
-        for (int item = tid; item < kTileM * quads; item += kUT) {
+        for (int item = tid; item < kTileM * quads; item += kUmmaT) {
             const int row = item / quads, qd = item - row * quads;
             float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s_ent[row] != kNoEntry) {
@@ -327,6 +345,7 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
             }
             __syncwarp();
         }
+        load_meta(tile + gridDim.x, cur ^ 1);  // next tile's lookups overlap this tile's MMAs
         if (!mbar_wait(smem_u32(s_mbar), parity)) {  // never observed; reported through the pair counter's spare words
             if (tid == 0) atomicExch(const_cast<uint32_t *>(p.count) + 1, 0xDEAD0000u | (tile & 0xFFFFu));
             break;
@@ -334,9 +353,9 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
         parity ^= 1u;
         tc_fence_after();
         if (p.dbg_stage == 3) { __syncthreads(); continue; }
-        // ---- epilogue: thread = (cell = TMEM lane 32 (warp % 4) + lane, column half warp / 4) -------------------------------------
+        // ---- epilogue: thread = (cell = TMEM lane 32 (warp % 4) + lane, column part warp / 4) -------------------------------------
         const int row = 32 * (warp & 3) + lane, hf = warp >> 2;
-        const int half_cols = d >> 1, col0 = hf * half_cols;
+        const int half_cols = d / kParts, col0 = hf * half_cols;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(col0);
         float v[32];
         float s = 0.f;
@@ -347,7 +366,10 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
         }
         s_stat[hf * kTileM + row] = s;
         __syncthreads();
-        const float mean = (s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d);
+        float tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
+        const float mean = tot / static_cast<float>(d);
         __syncthreads();
         float q = 0.f;
         for (int ch = 0; ch < half_cols; ch += 32) {
@@ -360,7 +382,10 @@ __global__ void __launch_bounds__(kUT, 1) k_tok_umma(const __grid_constant__ Umm
         }
         s_stat[hf * kTileM + row] = q;
         __syncthreads();
-        const float rstd = 1.f / sqrtf((s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d) + p.eps);
+        tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
+        const float rstd = 1.f / sqrtf(tot / static_cast<float>(d) + p.eps);
         const uint32_t e = s_ent[row];
         const bool live = e != kNoEntry;  // tcgen05.ld is warp-collective: every lane loads, only live rows store
         const uint32_t b = live ? e / static_cast<uint32_t>(plane) : 0u, cell = live ? e - b * static_cast<uint32_t>(plane) : 0u;
@@ -417,7 +442,7 @@ size_t umma_smem_bytes(int c, int d)
 {
     const size_t kb_n = static_cast<size_t>(c) >> 5;
     return 2 * kb_n * d * 128 + 2 * kb_n * kTileM * 128 + sizeof(float) * (10 * static_cast<size_t>(c) + 3 * static_cast<size_t>(d)) +
-           sizeof(int32_t) * kTileM * 9 + sizeof(uint32_t) * kTileM + sizeof(float) * 2 * kTileM + 16;
+           2 * (sizeof(int32_t) * kTileM * 9 + sizeof(uint32_t) * kTileM) + sizeof(float) * kParts * kTileM + 16;
 }
 
 }  // namespace
@@ -444,9 +469,32 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
     sp.cell_row = cell_row; sp.nb = nb; sp.h = h; sp.w = w; sp.d = tk.d; sp.pe = tk.pe; sp.bg = tk.bg; sp.out = out;
     sp.list = list; sp.count = count;
     const dim3 grid(static_cast<unsigned>((w + kTileX - 1) / kTileX), static_cast<unsigned>(h));
-    if (tk.d == 128) k_tok_stream_list<1><<<grid, kUT, 0, st>>>(sp);
-    else k_tok_stream_list<2><<<grid, kUT, 0, st>>>(sp);
-    note_launch();
+    // The streaming kernel is HBM-bound, the tcgen05 kernel latency/issue-bound: they run side by side.  The pair list comes
+    // first (cheap pass over the index map), then the call forks: streaming on a helper stream, arithmetic on `st`, joined
+    // again before the call returns, so for the caller everything is still ordered on `st`.
+    static thread_local cudaStream_t aux = nullptr;
+    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    static const bool serial = getenv("PILLARS_UMMA_SERIAL") != nullptr;
+    if (!serial && !aux) {
+        if ((e = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if (serial) {
+        if (tk.d == 128) k_tok_stream_list<1, 0><<<grid, kUT, 0, st>>>(sp);
+        else k_tok_stream_list<2, 0><<<grid, kUT, 0, st>>>(sp);
+        note_launch();
+    } else {
+        if (tk.d == 128) k_tok_stream_list<1, 1><<<grid, kUT, 0, st>>>(sp);
+        else k_tok_stream_list<2, 1><<<grid, kUT, 0, st>>>(sp);
+        note_launch();
+        if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
+        if (tk.d == 128) k_tok_stream_list<1, 2><<<grid, kUT, 0, aux>>>(sp);
+        else k_tok_stream_list<2, 2><<<grid, kUT, 0, aux>>>(sp);
+        note_launch();
+        if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     UmmaParams up{};
@@ -465,8 +513,9 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if ((e = cudaFuncSetAttribute(k_tok_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     }
-    k_tok_umma<<<sms, kUT, smem, st>>>(up);
+    k_tok_umma<<<sms, kUmmaT, smem, st>>>(up);
     note_launch();
+    if (!serial && (e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
