@@ -28,7 +28,7 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kUT = 256;        // threads of the streaming kernel
 constexpr int kUmmaT = 512;     // threads of the tcgen05 kernel: 4 TMEM lane quarters x kParts column parts
-constexpr int kParts = kUmmaT / 128;
+constexpr int kParts = 2;       // column halves of the epilogue group
 constexpr int kUW = kUT / 32;
 constexpr int kTileM = 128;     // pairs per GEMM tile = TMEM lanes
 constexpr int kTileX = 32;
@@ -152,12 +152,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
-// bounded wait (non-blocking test_wait): a mistake in the MMA set-up must end in an error code, not in a hung GPU
+// bounded wait: try_wait parks the warp in hardware (no issue slots burnt while the other group works) and returns after a
+// system-defined time limit at the latest; a bounded number of retries turns a set-up mistake into an error code, not a hang
 __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity)
 {
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
         uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok)
                      : "r"(mbar), "r"(parity)
                      : "memory");
@@ -205,6 +206,15 @@ __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo)
     hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
 }
 
+__device__ __forceinline__ void bar_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+
+// Warp-specialised, two tiles in flight per CTA:
+//   warps 0-7  (group R, 256 threads)  metadata + refine of tile i+1 into the A buffers; thread 0 issues the MMAs
+//   warps 8-15 (group E, 256 threads)  LayerNorm + PE + stores of tile i out of tensor memory
+// The accumulator is double buffered in TMEM (2 x d columns), so MMA(i+1) may run while E still reads tile i; the A buffers
+// are single: refine(i+1) starts when the commit of MMA(i) has arrived (a_free).  mbarriers: a_free (1 arrival: commit),
+// acc_ready[2] (1: commit), acc_free[2] (256: every E thread after its last TMEM read of the tile).
 __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ UmmaParams p)
 {
     extern __shared__ __align__(1024) uint8_t s_raw[];
@@ -218,19 +228,27 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
     uint8_t *const s_a = s_al + 2 * w_half;           // A_hi | A_lo
     float *const s_dw = reinterpret_cast<float *>(s_a + 2 * a_half);  // [10][c]
     float *const s_vec = s_dw + 10 * c;                                // pb | gamma | beta, [3][d]
-    int32_t *const s_nb_all = reinterpret_cast<int32_t *>(s_vec + 3 * d);            // [2][128][9] (double buffered per tile)
+    int32_t *const s_nb_all = reinterpret_cast<int32_t *>(s_vec + 3 * d);                 // [2][128][9]
     uint32_t *const s_ent_all = reinterpret_cast<uint32_t *>(s_nb_all + 2 * kTileM * 9);  // [2][128]
-    float *const s_stat = reinterpret_cast<float *>(s_ent_all + 2 * kTileM);          // [kParts][128]
-    uint64_t *const s_mbar = reinterpret_cast<uint64_t *>(s_stat + kParts * kTileM);
-    uint32_t *const s_tmem = reinterpret_cast<uint32_t *>(s_mbar + 1);
+    float *const s_stat = reinterpret_cast<float *>(s_ent_all + 2 * kTileM);              // [2][128] (E group, column halves)
+    uint64_t *const s_mbar = reinterpret_cast<uint64_t *>(s_stat + kParts * kTileM);      // a_free, acc_ready[2], acc_free[2]
+    uint32_t *const s_tmem = reinterpret_cast<uint32_t *>(s_mbar + 5);
+    volatile uint32_t *const s_abort = s_tmem + 1;
+    const uint32_t mb_a_free = smem_u32(s_mbar), mb_ready0 = smem_u32(s_mbar + 1), mb_free0 = smem_u32(s_mbar + 3);
+    const uint32_t tmem_cols = 2u * static_cast<uint32_t>(d);
 
-    // ---- one-time setup: TMEM columns, mbarrier, W image, small vectors ----------------------------------------------------
+    // ---- one-time setup ------------------------------------------------------------------------------------------------------
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(static_cast<uint32_t>(d)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        mbar_init(smem_u32(s_mbar), 1);
+        mbar_init(mb_a_free, 1);
+        mbar_init(mb_ready0, 1);
+        mbar_init(mb_ready0 + 8, 1);
+        mbar_init(mb_free0, kUmmaT / 2);
+        mbar_init(mb_free0 + 8, kUmmaT / 2);
+        *s_abort = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -257,166 +275,187 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
     if (p.dbg_stage == 1) n_total = 0;
     const uint32_t idesc = umma_idesc_tf32(d);
     const size_t plane = static_cast<size_t>(h) * w;
-    uint32_t parity = 0;
-
-    // A tile's pairs and the pillar rows of their 3x3 windows (threads 0..127), one tile AHEAD of the arithmetic: the index
-    // lookups run under the previous tile's MMA, and the rows / PE lines the tile will touch are requested into L2 right away.
-    auto load_meta = [&](uint32_t tile, int buf) {
-        if (tid < kTileM) {
-            const uint32_t idx = tile * kTileM + tid;
-            const uint32_t e = (static_cast<uint64_t>(tile) * kTileM < n_total && idx < n_total) ? __ldg(p.list + idx) : kNoEntry;
-            s_ent_all[buf * kTileM + tid] = e;
-            if (e != kNoEntry) {
-                const uint32_t b = e / static_cast<uint32_t>(plane), cell = e - b * static_cast<uint32_t>(plane);
-                const int yy0 = static_cast<int>(cell / w), xx0 = static_cast<int>(cell - static_cast<uint32_t>(yy0) * w);
-                int32_t *nb = s_nb_all + (buf * kTileM + tid) * 9;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const int yy = yy0 + k / 3 - 1, xx = xx0 + k % 3 - 1;
-                    int32_t r = -1;
-                    if (yy >= 0 && yy < h && xx >= 0 && xx < w) r = __ldg(p.cell_row + (static_cast<size_t>(b) * h + yy) * w + xx);
-                    nb[k] = r;
-                    if (r >= 0) {
-                        const char *row = reinterpret_cast<const char *>(p.feats + static_cast<size_t>(r) * c);
-                        for (int o = 0; o < c * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
-                    }
-                }
-                const char *pe = reinterpret_cast<const char *>(p.pe + static_cast<size_t>(cell) * d);
-                for (int o = 0; o < d * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + o));
-            }
-        }
+    const uint32_t n_tiles = (n_total + kTileM - 1) / kTileM;
+    const auto report = [&](uint32_t code) {  // bounded waits never expire in a correct run; leave a trace if one does
+        *s_abort = 1u;
+        atomicExch(const_cast<uint32_t *>(p.count) + 1, 0xDEAD0000u | code);
     };
-    load_meta(blockIdx.x, 0);
-    __syncthreads();
-    int cur = 0;
 
-    for (uint32_t tile = blockIdx.x; static_cast<uint64_t>(tile) * kTileM < n_total; tile += gridDim.x, cur ^= 1) {
-        const int32_t *const s_nb = s_nb_all + cur * kTileM * 9;
-        const uint32_t *const s_ent = s_ent_all + cur * kTileM;
-        // ---- refine: A[row][channel] = GELU(depthwise 3x3 + bias), split into tf32 hi / lo, written in the swizzled layout --------
-        for (int item = tid; item < kTileM * quads; item += kUmmaT) {
-            const int row = item / quads, qd = item - row * quads;
-            float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s_ent[row] != kNoEntry) {
-                float4 acc = *reinterpret_cast<const float4 *>(s_dw + 9 * c + 4 * qd);
+    if (warp < kUmmaT / 64) {
+        // ================================ group R: metadata, refine, MMA issue ===================================================
+        const int rt = tid;  // 0..255
+        auto load_meta = [&](uint32_t tile, int buf) {
+            if (rt < kTileM) {
+                const uint32_t idx = tile * kTileM + rt;
+                const uint32_t e = (tile < n_tiles && idx < n_total) ? __ldg(p.list + idx) : kNoEntry;
+                s_ent_all[buf * kTileM + rt] = e;
+                if (e != kNoEntry) {
+                    const uint32_t b = e / static_cast<uint32_t>(plane), cell = e - b * static_cast<uint32_t>(plane);
+                    const int yy0 = static_cast<int>(cell / w), xx0 = static_cast<int>(cell - static_cast<uint32_t>(yy0) * w);
+                    int32_t *nb = s_nb_all + (buf * kTileM + rt) * 9;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const int32_t r = s_nb[row * 9 + k];
-                    if (r >= 0) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(p.feats + static_cast<size_t>(r) * c) + qd);
-                        const float4 wk = *reinterpret_cast<const float4 *>(s_dw + k * c + 4 * qd);
-                        acc.x = fmaf(wk.x, f.x, acc.x);
-                        acc.y = fmaf(wk.y, f.y, acc.y);
-                        acc.z = fmaf(wk.z, f.z, acc.z);
-                        acc.w = fmaf(wk.w, f.w, acc.w);
+                    for (int k = 0; k < 9; ++k) {
+                        const int yy = yy0 + k / 3 - 1, xx = xx0 + k % 3 - 1;
+                        int32_t r = -1;
+                        if (yy >= 0 && yy < h && xx >= 0 && xx < w) r = __ldg(p.cell_row + (static_cast<size_t>(b) * h + yy) * w + xx);
+                        nb[k] = r;
+                        if (r >= 0) {
+                            const char *row = reinterpret_cast<const char *>(p.feats + static_cast<size_t>(r) * c);
+                            for (int o = 0; o < c * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                        }
                     }
                 }
-                act = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
             }
-            float4 hi, lo;
-            split4(act, hi, lo);
-            const uint32_t off = static_cast<uint32_t>(qd >> 3) * (kTileM * 128u) + static_cast<uint32_t>(row) * 128u +
-                                 ((static_cast<uint32_t>(qd & 7) ^ static_cast<uint32_t>(row & 7)) << 4);
-            *reinterpret_cast<float4 *>(s_a + off) = hi;
-            *reinterpret_cast<float4 *>(s_a + a_half + off) = lo;
-        }
-        fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-        tc_fence_before();
-        __syncthreads();
-        if (p.dbg_stage == 2) continue;
-        // ---- projection: one thread issues 3 x c/8 MMAs, the commit arrives on the mbarrier when they have all finished ----------
-        if (warp == 0) {
-            tc_fence_after();
-            if (lane == 0) {
+        };
+        load_meta(blockIdx.x, 0);
+        bar_named(1, kUmmaT / 2);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int cur = it & 1;
+            const int32_t *const s_nb = s_nb_all + cur * kTileM * 9;
+            const uint32_t *const s_ent = s_ent_all + cur * kTileM;
+            // the A buffers are free once the previous tile's MMAs have completed
+            if (it > 0 && !mbar_wait(mb_a_free, (it - 1) & 1u)) { report(1); break; }
+#pragma unroll 2
+            for (int item = rt; item < kTileM * quads; item += kUmmaT / 2) {
+                const int row = item / quads, qd = item - row * quads;
+                float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s_ent[row] != kNoEntry) {
+                    // all nine row gathers are requested before the first one is consumed
+                    float4 f[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const int32_t r = s_nb[row * 9 + k];
+                        f[k] = r >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.feats + static_cast<size_t>(r) * c) + qd)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    float4 acc = *reinterpret_cast<const float4 *>(s_dw + 9 * c + 4 * qd);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const float4 wk = *reinterpret_cast<const float4 *>(s_dw + k * c + 4 * qd);
+                        acc.x = fmaf(wk.x, f[k].x, acc.x);
+                        acc.y = fmaf(wk.y, f[k].y, acc.y);
+                        acc.z = fmaf(wk.z, f[k].z, acc.z);
+                        acc.w = fmaf(wk.w, f[k].w, acc.w);
+                    }
+                    act = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
+                }
+                float4 hi, lo;
+                split4(act, hi, lo);
+                const uint32_t off = static_cast<uint32_t>(qd >> 3) * (kTileM * 128u) + static_cast<uint32_t>(row) * 128u +
+                                     ((static_cast<uint32_t>(qd & 7) ^ static_cast<uint32_t>(row & 7)) << 4);
+                *reinterpret_cast<float4 *>(s_a + off) = hi;
+                *reinterpret_cast<float4 *>(s_a + a_half + off) = lo;
+            }
+            fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+            tc_fence_before();
+            bar_named(1, kUmmaT / 2);
+            if (p.dbg_stage == 2) continue;
+            if (rt == 0) {
+                // the accumulator stage must have been drained by the epilogue of tile it - 2
+                bool ok = true;
+                if (it >= 2) ok = mbar_wait(mb_free0 + 8u * cur, ((it >> 1) - 1) & 1u);
+                if (!ok) report(2);
+                tc_fence_after();
                 const uint32_t a_hi = smem_u32(s_a), a_lo = a_hi + a_half, w_hi = smem_u32(s_w), w_lo = w_hi + w_half;
+                const uint32_t tacc = tmem_base + static_cast<uint32_t>(cur) * static_cast<uint32_t>(d);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < kb_n; ++kb) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t ao = static_cast<uint32_t>(kb) * (kTileM * 128u) + k * 32u;
                         const uint32_t bo = static_cast<uint32_t>(kb) * (static_cast<uint32_t>(d) * 128u) + k * 32u;
-                        umma_tf32(tmem_base, umma_desc_sw128(a_lo + ao), umma_desc_sw128(w_hi + bo), idesc, accumulate);
-                        umma_tf32(tmem_base, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_lo + bo), idesc, 1u);
-                        umma_tf32(tmem_base, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_hi + bo), idesc, 1u);
+                        umma_tf32(tacc, umma_desc_sw128(a_lo + ao), umma_desc_sw128(w_hi + bo), idesc, accumulate);
+                        umma_tf32(tacc, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_lo + bo), idesc, 1u);
+                        umma_tf32(tacc, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_hi + bo), idesc, 1u);
                         accumulate = 1u;
                     }
                 }
-                umma_commit(smem_u32(s_mbar));
+                umma_commit(mb_a_free);
+                umma_commit(mb_ready0 + 8u * cur);
             }
-            __syncwarp();
+            load_meta(tile + gridDim.x, cur ^ 1);  // next tile's lookups run under this tile's MMAs
+            bar_named(1, kUmmaT / 2);
         }
-        load_meta(tile + gridDim.x, cur ^ 1);  // next tile's lookups overlap this tile's MMAs
-        if (!mbar_wait(smem_u32(s_mbar), parity)) {  // never observed; reported through the pair counter's spare words
-            if (tid == 0) atomicExch(const_cast<uint32_t *>(p.count) + 1, 0xDEAD0000u | (tile & 0xFFFFu));
-            break;
-        }
-        parity ^= 1u;
-        tc_fence_after();
-        if (p.dbg_stage == 3) { __syncthreads(); continue; }
-        // ---- epilogue: thread = (cell = TMEM lane 32 (warp % 4) + lane, column part warp / 4) -------------------------------------
-        const int row = 32 * (warp & 3) + lane, hf = warp >> 2;
-        const int half_cols = d / kParts, col0 = hf * half_cols;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(col0);
-        float v[32];
-        float s = 0.f;
-        for (int ch = 0; ch < half_cols; ch += 32) {
-            tmem_ld32(taddr + ch, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s += v[j] + s_vec[col0 + ch + j];
-        }
-        s_stat[hf * kTileM + row] = s;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
-        const float mean = tot / static_cast<float>(d);
-        __syncthreads();
-        float q = 0.f;
-        for (int ch = 0; ch < half_cols; ch += 32) {
-            tmem_ld32(taddr + ch, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float x = v[j] + s_vec[col0 + ch + j] - mean;
-                q = fmaf(x, x, q);
-            }
-        }
-        s_stat[hf * kTileM + row] = q;
-        __syncthreads();
-        tot = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
-        const float rstd = 1.f / sqrtf(tot / static_cast<float>(d) + p.eps);
-        const uint32_t e = s_ent[row];
-        const bool live = e != kNoEntry;  // tcgen05.ld is warp-collective: every lane loads, only live rows store
-        const uint32_t b = live ? e / static_cast<uint32_t>(plane) : 0u, cell = live ? e - b * static_cast<uint32_t>(plane) : 0u;
-        const float4 *pe4 = reinterpret_cast<const float4 *>(p.pe + static_cast<size_t>(cell) * d + col0);
-        float4 *dst = reinterpret_cast<float4 *>(p.out + static_cast<size_t>(live ? e : 0u) * d + col0);
-        for (int ch = 0; ch < half_cols; ch += 32) {
-            tmem_ld32(taddr + ch, v);
-            if (live) {
+    } else {
+        // ================================ group E: LayerNorm + PE + stores out of tensor memory ===================================
+        const int et = tid - kUmmaT / 2;          // 0..255
+        const int ew = et >> 5;                   // 0..7; TMEM lane quarter = warp % 4 (8 % 4 == 0, so ew % 4 too)
+        const int row = 32 * (ew & 3) + lane, hf = ew >> 2;
+        const int half_cols = d >> 1, col0 = hf * half_cols;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if (p.dbg_stage == 2) continue;
+            const int cur = it & 1;
+            const uint32_t idx = tile * kTileM + row;
+            const uint32_t e = idx < n_total ? __ldg(p.list + idx) : kNoEntry;
+            const bool live = e != kNoEntry;  // tcgen05.ld is warp-collective: every lane loads, only live rows store
+            const uint32_t b = live ? e / static_cast<uint32_t>(plane) : 0u, cell = live ? e - b * static_cast<uint32_t>(plane) : 0u;
+            const float4 *pe4 = reinterpret_cast<const float4 *>(p.pe + static_cast<size_t>(cell) * d + col0);
+            float4 *dst = reinterpret_cast<float4 *>(p.out + static_cast<size_t>(live ? e : 0u) * d + col0);
+            if (live)
+                for (int o = 0; o < half_cols * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(pe4) + o));
+            if (!mbar_wait(mb_ready0 + 8u * cur, (it >> 1) & 1u)) { report(3); break; }
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (ew & 3)) << 16) + static_cast<uint32_t>(cur * d + col0);
+            float v[32];
+            float s = 0.f;
+            for (int ch = 0; ch < half_cols; ch += 32) {
+                tmem_ld32(taddr + ch, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const int col = col0 + ch + j;
-                    const float4 pb = *reinterpret_cast<const float4 *>(s_vec + col);
-                    const float4 ga = *reinterpret_cast<const float4 *>(s_vec + d + col);
-                    const float4 be = *reinterpret_cast<const float4 *>(s_vec + 2 * d + col);
-                    const float4 pe = __ldg(pe4 + ((ch + j) >> 2));
-                    float4 o;
-                    o.x = fmaf((v[j] + pb.x - mean) * rstd, ga.x, be.x) + pe.x;
-                    o.y = fmaf((v[j + 1] + pb.y - mean) * rstd, ga.y, be.y) + pe.y;
-                    o.z = fmaf((v[j + 2] + pb.z - mean) * rstd, ga.z, be.z) + pe.z;
-                    o.w = fmaf((v[j + 3] + pb.w - mean) * rstd, ga.w, be.w) + pe.w;
-                    __stcs(dst + ((ch + j) >> 2), o);
+                    const float4 pb = *reinterpret_cast<const float4 *>(s_vec + col0 + ch + j);
+                    s += (v[j] + pb.x) + (v[j + 1] + pb.y) + (v[j + 2] + pb.z) + (v[j + 3] + pb.w);
+                }
+            }
+            s_stat[hf * kTileM + row] = s;
+            bar_named(2, kUmmaT / 2);
+            const float mean = (s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d);
+            bar_named(2, kUmmaT / 2);
+            float q = 0.f;
+            for (int ch = 0; ch < half_cols; ch += 32) {
+                tmem_ld32(taddr + ch, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 pb = *reinterpret_cast<const float4 *>(s_vec + col0 + ch + j);
+                    const float x0 = v[j] + pb.x - mean, x1 = v[j + 1] + pb.y - mean, x2 = v[j + 2] + pb.z - mean, x3 = v[j + 3] + pb.w - mean;
+                    q = fmaf(x0, x0, q); q = fmaf(x1, x1, q); q = fmaf(x2, x2, q); q = fmaf(x3, x3, q);
+                }
+            }
+            s_stat[hf * kTileM + row] = q;
+            bar_named(2, kUmmaT / 2);
+            const float rstd = 1.f / sqrtf((s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d) + p.eps);
+            bar_named(2, kUmmaT / 2);
+            for (int ch = 0; ch < half_cols; ch += 32) {
+                tmem_ld32(taddr + ch, v);
+                if (ch + 32 >= half_cols) {  // last read of this accumulator stage: hand it back to the MMA issuer
+                    tc_fence_before();
+                    mbar_arrive(mb_free0 + 8u * cur);
+                }
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = col0 + ch + j;
+                        const float4 pb = *reinterpret_cast<const float4 *>(s_vec + col);
+                        const float4 ga = *reinterpret_cast<const float4 *>(s_vec + d + col);
+                        const float4 be = *reinterpret_cast<const float4 *>(s_vec + 2 * d + col);
+                        const float4 pe = __ldg(pe4 + ((ch + j) >> 2));
+                        float4 o;
+                        o.x = fmaf((v[j] + pb.x - mean) * rstd, ga.x, be.x) + pe.x;
+                        o.y = fmaf((v[j + 1] + pb.y - mean) * rstd, ga.y, be.y) + pe.y;
+                        o.z = fmaf((v[j + 2] + pb.z - mean) * rstd, ga.z, be.z) + pe.z;
+                        o.w = fmaf((v[j + 3] + pb.w - mean) * rstd, ga.w, be.w) + pe.w;
+                        __stcs(dst + ((ch + j) >> 2), o);
+                    }
                 }
             }
         }
-        tc_fence_before();  // the accumulator reads above are ordered before the next tile's MMAs
-        __syncthreads();
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(static_cast<uint32_t>(d)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
 // W image: element (n, k) of Wp = wt[k][n], half hf (0 hi, 1 lo), at [(hf * kb_n + k / 32) * d + n] * 128 B + 16-byte chunk
@@ -442,7 +481,7 @@ size_t umma_smem_bytes(int c, int d)
 {
     const size_t kb_n = static_cast<size_t>(c) >> 5;
     return 2 * kb_n * d * 128 + 2 * kb_n * kTileM * 128 + sizeof(float) * (10 * static_cast<size_t>(c) + 3 * static_cast<size_t>(d)) +
-           2 * (sizeof(int32_t) * kTileM * 9 + sizeof(uint32_t) * kTileM) + sizeof(float) * kParts * kTileM + 16;
+           2 * (sizeof(int32_t) * kTileM * 9 + sizeof(uint32_t) * kTileM) + sizeof(float) * kParts * kTileM + 5 * 8 + 16;
 }
 
 }  // namespace
