@@ -17,8 +17,6 @@
 //                       per-thread loop plus one shared-memory exchange between the two column halves; + PE; store.
 //
 // Shapes: C in {32, 64}, d in {128, 256} (W_hi + W_lo + A_hi + A_lo <= 192 KB of shared memory, N <= 256 per MMA).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace pillars {
@@ -50,8 +48,7 @@ struct StreamListParams {
 // -------------------------------------------------------------------------------------------------------------------
 // pass over the index map: stream the input-independent tokens, list the rest.  NQ = d / 128.
 // -------------------------------------------------------------------------------------------------------------------
-// kMode 0: both duties in one pass; 1: list only (cheap, runs first); 2: stream only (runs beside the tcgen05 kernel)
-template <int NQ, int kMode>
+template <int NQ>
 __global__ void __launch_bounds__(kUT) k_tok_stream_list(const __grid_constant__ StreamListParams p)
 {
     __shared__ int32_t s_map[kFrameChunk][3][kTileX + 2];
@@ -92,14 +89,14 @@ __global__ void __launch_bounds__(kUT) k_tok_stream_list(const __grid_constant__
             if (x >= w) break;
             const size_t cell = static_cast<size_t>(y) * w + x;
             const unsigned amask = __ballot_sync(kFull, lane < nbb && ((s_act[lane & (kFrameChunk - 1)] >> t) & 1u));
-            if (kMode != 2 && amask) {
+            if (amask) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&s_count, static_cast<uint32_t>(__popc(amask)));
                 base = __shfl_sync(kFull, base, 0);
                 if ((amask >> lane) & 1u)
                     s_list[base + __popc(amask & ((1u << lane) - 1u))] = static_cast<uint32_t>((b0 + lane) * plane + cell);
             }
-            if (kMode == 1 || __popc(amask) == nbb) continue;
+            if (__popc(amask) == nbb) continue;
             float4 v[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -116,7 +113,7 @@ __global__ void __launch_bounds__(kUT) k_tok_stream_list(const __grid_constant__
             }
         }
         __syncthreads();
-        const uint32_t n = kMode == 2 ? 0u : s_count;
+        const uint32_t n = s_count;
         if (n) {
             if (tid == 0) s_base = atomicAdd(p.count, n);
             __syncthreads();
@@ -194,7 +191,6 @@ struct UmmaParams {
     const uint4 *wimg;        // [2 (hi, lo)][c / 32][d][128 B], swizzled: the exact shared-memory image
     const uint32_t *list, *count;
     float *out;
-    int dbg_stage;  // bring-up knob (PILLARS_UMMA_STAGE): 0 = full kernel
 };
 
 // tf32 split of a float4: hi keeps sign, exponent and 10 mantissa bits (what the tensor core reads), lo = x - hi (exact)
@@ -272,7 +268,6 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     uint32_t n_total = __ldg(p.count);
-    if (p.dbg_stage == 1) n_total = 0;
     const uint32_t idesc = umma_idesc_tf32(d);
     const size_t plane = static_cast<size_t>(h) * w;
     const uint32_t n_tiles = (n_total + kTileM - 1) / kTileM;
@@ -350,7 +345,6 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
             tc_fence_before();
             bar_named(1, kUmmaT / 2);
-            if (p.dbg_stage == 2) continue;
             if (rt == 0) {
                 // the accumulator stage must have been drained by the epilogue of tile it - 2
                 bool ok = true;
@@ -385,7 +379,6 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
         const int half_cols = d >> 1, col0 = hf * half_cols;
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            if (p.dbg_stage == 2) continue;
             const int cur = it & 1;
             const uint32_t idx = tile * kTileM + row;
             const uint32_t e = idx < n_total ? __ldg(p.list + idx) : kNoEntry;
@@ -508,42 +501,18 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
     sp.cell_row = cell_row; sp.nb = nb; sp.h = h; sp.w = w; sp.d = tk.d; sp.pe = tk.pe; sp.bg = tk.bg; sp.out = out;
     sp.list = list; sp.count = count;
     const dim3 grid(static_cast<unsigned>((w + kTileX - 1) / kTileX), static_cast<unsigned>(h));
-    // The streaming kernel is HBM-bound, the tcgen05 kernel latency/issue-bound: they run side by side.  The pair list comes
-    // first (cheap pass over the index map), then the call forks: streaming on a helper stream, arithmetic on `st`, joined
-    // again before the call returns, so for the caller everything is still ordered on `st`.
-    static thread_local cudaStream_t aux = nullptr;
-    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    static const bool serial = getenv("PILLARS_UMMA_SERIAL") != nullptr;
-    if (!serial && !aux) {
-        if ((e = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-        if ((e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
-    }
-    if (serial) {
-        if (tk.d == 128) k_tok_stream_list<1, 0><<<grid, kUT, 0, st>>>(sp);
-        else k_tok_stream_list<2, 0><<<grid, kUT, 0, st>>>(sp);
-        note_launch();
-    } else {
-        if (tk.d == 128) k_tok_stream_list<1, 1><<<grid, kUT, 0, st>>>(sp);
-        else k_tok_stream_list<2, 1><<<grid, kUT, 0, st>>>(sp);
-        note_launch();
-        if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
-        if (tk.d == 128) k_tok_stream_list<1, 2><<<grid, kUT, 0, aux>>>(sp);
-        else k_tok_stream_list<2, 2><<<grid, kUT, 0, aux>>>(sp);
-        note_launch();
-        if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
-    }
+    // Measured: running the streaming pass beside the tcgen05 kernel (helper stream, shared-memory-free streaming CTAs sized to
+    // what one tcgen05 CTA leaves of an SM) is slower (1.59 ms) than one after the other (1.42 ms): the streaming pass needs
+    // the whole SM's warps to saturate HBM.
+    if (tk.d == 128) k_tok_stream_list<1><<<grid, kUT, 0, st>>>(sp);
+    else k_tok_stream_list<2><<<grid, kUT, 0, st>>>(sp);
+    note_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     UmmaParams up{};
     up.feats = feats; up.cell_row = cell_row; up.nb = nb; up.h = h; up.w = w; up.c = tk.c; up.d = tk.d;
     up.dw_w = tk.dw_w; up.dw_b = tk.dw_b; up.pb = tk.pb; up.gamma = tk.gamma; up.beta = tk.beta; up.eps = tk.eps; up.pe = tk.pe;
     up.wimg = reinterpret_cast<const uint4 *>(tk.wimg); up.list = list; up.count = count; up.out = out;
-    {
-        const char *e_st = getenv("PILLARS_UMMA_STAGE");
-        up.dbg_stage = e_st ? atoi(e_st) : 0;
-    }
     const size_t smem = umma_smem_bytes(tk.c, tk.d) + 1024;  // slack for the 1024-byte alignment of the tiles
     static int sms = 0;
     if (!sms) {
@@ -554,7 +523,6 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
     }
     k_tok_umma<<<sms, kUmmaT, smem, st>>>(up);
     note_launch();
-    if (!serial && (e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

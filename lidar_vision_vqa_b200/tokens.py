@@ -51,17 +51,17 @@ class VATLiDARTokenizer(nn.Module):
 
     def __init__(self, c_in: int, d_model: int, projection: str = "auto"):
         """``projection`` selects how the 1x1 projection runs (all variants are fp32-accurate and parity-tested):
-        ``"fma"``   fp32 FFMA2 on the FMA pipes, any supported shape;
+        ``"fma"``   fp32 FFMA2 on the FMA pipes inside one fused kernel, any supported shape;
         ``"umma"``  tcgen05.mma.kind::tf32 as a 3-term hi/lo split, accumulator in tensor memory, the active cells of the
-                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256);
-        ``"mma"``   the same split with legacy ``mma.sync`` (c_in % 8 == 0, d_model 128 or 256) -- measured slower than
-                    ``"fma"``, kept as evidence (DESIGN.md 4b);
-        ``"auto"``  ``"umma"`` where it exists, else ``"fma"``."""
+                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256); same speed as ``"fma"`` on B200
+                    today (1.43 vs 1.42 ms on 16 x 512^2, d = 256): the GEMM itself becomes free, the row gathers and the
+                    LayerNorm epilogue around it set the time (DESIGN.md 4b);
+        ``"mma"``   the same split with legacy ``mma.sync`` (c_in % 8 == 0, d_model 128 or 256) -- slower, kept as evidence;
+        ``"auto"``  ``"fma"``."""
         super().__init__()
         if projection not in ("auto", "fma", "mma", "umma"):
             raise ValueError("projection must be one of auto / fma / mma / umma")
-        umma_ok = c_in in (32, 64) and d_model in (128, 256)
-        self.projection = ("umma" if umma_ok else "fma") if projection == "auto" else projection
+        self.projection = "fma" if projection == "auto" else projection
         self._umma: Optional[torch.Tensor] = None
         self._frag: Optional[torch.Tensor] = None
         self.c_in, self.d_model = int(c_in), int(d_model)
