@@ -363,28 +363,36 @@ def run_b200(args, rank, world, local_rank):
         from oracle import tokens_oracle as tor  # random weights only
 
         d_tok = args.tokens_d_model
-        tk = T.VATLiDARTokenizer(F_OUT, d_tok)
-        tk.load_state_dict({k: torch.from_numpy(v) for k, v in tor.random_token_params(F_OUT, d_tok, seed=11).items()})
-        tk = tk.eval().to(dev)
-        tk.tables(ny, nx)
         tok_out = torch.empty((nb, ny * nx, d_tok), dtype=torch.float32, device=dev)
         res_t = ops.encode_bev(*dev_batches[0], grid, pfn, buffers=bufs[0], want_index_map=True)
         cmap = res_t["cell_row"]
-        for _ in range(3):
-            tk.forward_index_map(res_t["pillar_features"], cmap, out=tok_out)
-        ts_, te_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_tok = min(K, 10)
-        torch.cuda.synchronize()
-        ts_.record()
-        for _ in range(n_tok):
-            tk.forward_index_map(res_t["pillar_features"], cmap, out=tok_out)
-        te_.record()
-        torch.cuda.synchronize()
-        tok_ms = ts_.elapsed_time(te_) / n_tok
         tok_bytes = tok_out.numel() * 4 + ny * nx * d_tok * 4  # tokens written + PE table read once
+        variants = {}
+        for proj in ("fma", "umma"):  # fused FFMA2 kernel (default) and the tcgen05 projection, same inputs and outputs
+            if proj == "umma" and not (F_OUT in (32, 64) and d_tok in (128, 256)):
+                continue
+            tk = T.VATLiDARTokenizer(F_OUT, d_tok, projection=proj)
+            tk.load_state_dict({k: torch.from_numpy(v) for k, v in tor.random_token_params(F_OUT, d_tok, seed=11).items()})
+            tk = tk.eval().to(dev)
+            tk.tables(ny, nx)
+            for _ in range(3):
+                tk.forward_index_map(res_t["pillar_features"], cmap, out=tok_out)
+            ts_, te_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_tok = min(K, 10)
+            torch.cuda.synchronize()
+            ts_.record()
+            for _ in range(n_tok):
+                tk.forward_index_map(res_t["pillar_features"], cmap, out=tok_out)
+            te_.record()
+            torch.cuda.synchronize()
+            variants[proj] = ts_.elapsed_time(te_) / n_tok
+        tok_ms = variants["fma"]
         tokens_stage = {"kernel": "k_bev_tokens (sparse-aware VATLiDAR tokeniser, rows + index map -> [B, H*W, d])",
                         "d_model": d_tok, "ms": tok_ms, "algorithmic_bytes": tok_bytes,
-                        "gbs": tok_bytes / (tok_ms * 1e-3) / 1e9, "tokens_per_s": nb * ny * nx / (tok_ms * 1e-3)}
+                        "gbs": tok_bytes / (tok_ms * 1e-3) / 1e9, "tokens_per_s": nb * ny * nx / (tok_ms * 1e-3),
+                        "ms_by_projection": variants,
+                        "projections": "fma = fused FFMA2 kernel (default); umma = k_tok_stream_list + k_tok_umma "
+                                       "(tcgen05.mma.kind::tf32 3-term split, accumulator in TMEM)"}
         del tok_out, tk
 
     # ---- timed region 2 (the headline): the same K steps pipelined over n_streams streams ----------------------------
