@@ -45,7 +45,7 @@ struct __align__(32) PointRecord {
 };
 
 static constexpr int kMaxFrames = 1024;  // frame_offsets are staged in shared memory
-static constexpr int kTile = 2048;       // points per CTA tile of the scan kernel
+static constexpr int kTile = 1024;       // points per CTA tile of the scan kernel
 
 struct Workspace {
     // zero-initialised region

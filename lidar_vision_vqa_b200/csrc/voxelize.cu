@@ -24,7 +24,7 @@ namespace pillars {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPerThread = kTile / kThreads;  // 8 (scan kernel)
+constexpr int kPerThread = kTile / kThreads;  // 4 (scan kernel); must stay a multiple of 4 (int4 slot loads)
 constexpr int kGroup = 256;                   // tiles per look-back group
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k)
