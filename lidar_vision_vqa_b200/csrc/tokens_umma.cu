@@ -25,7 +25,9 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kUT = 256;        // threads of the streaming kernel
-constexpr int kUmmaT = 512;     // threads of the tcgen05 kernel: 4 TMEM lane quarters x kParts column parts
+constexpr int kUmmaR = 768;     // refine group of the tcgen05 kernel (latency-bound row gathers: it gets most of the warps)
+constexpr int kUmmaE = 256;     // epilogue group: 4 TMEM lane quarters x kParts column parts
+constexpr int kUmmaT = kUmmaR + kUmmaE;
 constexpr int kParts = 2;       // column halves of the epilogue group
 constexpr int kUW = kUT / 32;
 constexpr int kTileM = 128;     // pairs per GEMM tile = TMEM lanes
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
         mbar_init(mb_a_free, 1);
         mbar_init(mb_ready0, 1);
         mbar_init(mb_ready0 + 8, 1);
-        mbar_init(mb_free0, kUmmaT / 2);
-        mbar_init(mb_free0 + 8, kUmmaT / 2);
+        mbar_init(mb_free0, kUmmaE);
+        mbar_init(mb_free0 + 8, kUmmaE);
         *s_abort = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
         atomicExch(const_cast<uint32_t *>(p.count) + 1, 0xDEAD0000u | code);
     };
 
-    if (warp < kUmmaT / 64) {
+    if (warp < kUmmaR / 32) {
         // ================================ group R: metadata, refine, MMA issue ===================================================
         const int rt = tid;  // 0..255
         auto load_meta = [&](uint32_t tile, int buf) {
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             }
         };
         load_meta(blockIdx.x, 0);
-        bar_named(1, kUmmaT / 2);
+        bar_named(1, kUmmaR);
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int cur = it & 1;
@@ -311,8 +313,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             const uint32_t *const s_ent = s_ent_all + cur * kTileM;
             // the A buffers are free once the previous tile's MMAs have completed
             if (it > 0 && !mbar_wait(mb_a_free, (it - 1) & 1u)) { report(1); break; }
-#pragma unroll 2
-            for (int item = rt; item < kTileM * quads; item += kUmmaT / 2) {
+            for (int item = rt; item < kTileM * quads; item += kUmmaR) {
                 const int row = item / quads, qd = item - row * quads;
                 float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (s_ent[row] != kNoEntry) {
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             }
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
             tc_fence_before();
-            bar_named(1, kUmmaT / 2);
+            bar_named(1, kUmmaR);
             if (rt == 0) {
                 // the accumulator stage must have been drained by the epilogue of tile it - 2
                 bool ok = true;
@@ -369,11 +370,11 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
                 umma_commit(mb_ready0 + 8u * cur);
             }
             load_meta(tile + gridDim.x, cur ^ 1);  // next tile's lookups run under this tile's MMAs
-            bar_named(1, kUmmaT / 2);
+            bar_named(1, kUmmaR);
         }
     } else {
         // ================================ group E: LayerNorm + PE + stores out of tensor memory ===================================
-        const int et = tid - kUmmaT / 2;          // 0..255
+        const int et = tid - kUmmaR;              // 0..255 (kUmmaR is a multiple of 128: the lane quarter is still warp % 4)
         const int ew = et >> 5;                   // 0..7; TMEM lane quarter = warp % 4 (8 % 4 == 0, so ew % 4 too)
         const int row = 32 * (ew & 3) + lane, hf = ew >> 2;
         const int half_cols = d >> 1, col0 = hf * half_cols;
@@ -402,9 +403,9 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
                 }
             }
             s_stat[hf * kTileM + row] = s;
-            bar_named(2, kUmmaT / 2);
+            bar_named(2, kUmmaE);
             const float mean = (s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d);
-            bar_named(2, kUmmaT / 2);
+            bar_named(2, kUmmaE);
             float q = 0.f;
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
@@ -416,9 +417,9 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
                 }
             }
             s_stat[hf * kTileM + row] = q;
-            bar_named(2, kUmmaT / 2);
+            bar_named(2, kUmmaE);
             const float rstd = 1.f / sqrtf((s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d) + p.eps);
-            bar_named(2, kUmmaT / 2);
+            bar_named(2, kUmmaE);
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
                 if (ch + 32 >= half_cols) {  // last read of this accumulator stage: hand it back to the MMA issuer
