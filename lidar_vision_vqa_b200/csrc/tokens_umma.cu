@@ -25,10 +25,11 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kUT = 256;        // threads of the streaming kernel
-constexpr int kUmmaR = 768;     // refine group of the tcgen05 kernel (latency-bound row gathers: it gets most of the warps)
+constexpr int kUmmaR = 768;     // refine group of the tcgen05 kernel: latency-bound row gathers, so it gets most of the warps
+                                // (measured on 16 x 512^2, d = 256: R/E = 512/512 1473 us, 768/256 1365 us, 896/128 1372 us)
 constexpr int kUmmaE = 256;     // epilogue group: 4 TMEM lane quarters x kParts column parts
 constexpr int kUmmaT = kUmmaR + kUmmaE;
-constexpr int kParts = 2;       // column halves of the epilogue group
+constexpr int kParts = kUmmaE / 128;  // column parts of the epilogue group
 constexpr int kUW = kUT / 32;
 constexpr int kTileM = 128;     // pairs per GEMM tile = TMEM lanes
 constexpr int kTileX = 32;
@@ -207,12 +208,12 @@ __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo)
 __device__ __forceinline__ void bar_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
 
-// Warp-specialised, two tiles in flight per CTA:
-//   warps 0-7  (group R, 256 threads)  metadata + refine of tile i+1 into the A buffers; thread 0 issues the MMAs
-//   warps 8-15 (group E, 256 threads)  LayerNorm + PE + stores of tile i out of tensor memory
+// Warp-specialised, two tiles in flight per CTA (1024 threads at 64 registers):
+//   warps 0-23  (group R, 768 threads)  metadata + refine of tile i+1 into the A buffers; thread 0 issues the MMAs
+//   warps 24-31 (group E, 256 threads)  LayerNorm + PE + stores of tile i out of tensor memory
 // The accumulator is double buffered in TMEM (2 x d columns), so MMA(i+1) may run while E still reads tile i; the A buffers
 // are single: refine(i+1) starts when the commit of MMA(i) has arrived (a_free).  mbarriers: a_free (1 arrival: commit),
-// acc_ready[2] (1: commit), acc_free[2] (256: every E thread after its last TMEM read of the tile).
+// acc_ready[2] (1: commit), acc_free[2] (kUmmaE: every E thread after its last TMEM read of the tile).
 __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ UmmaParams p)
 {
     extern __shared__ __align__(1024) uint8_t s_raw[];
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
         const int et = tid - kUmmaR;              // 0..255 (kUmmaR is a multiple of 128: the lane quarter is still warp % 4)
         const int ew = et >> 5;                   // 0..7; TMEM lane quarter = warp % 4 (8 % 4 == 0, so ew % 4 too)
         const int row = 32 * (ew & 3) + lane, hf = ew >> 2;
-        const int half_cols = d >> 1, col0 = hf * half_cols;
+        const int half_cols = d / kParts, col0 = hf * half_cols;
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int cur = it & 1;
@@ -404,7 +405,10 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             }
             s_stat[hf * kTileM + row] = s;
             bar_named(2, kUmmaE);
-            const float mean = (s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d);
+            float tot = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
+            const float mean = tot / static_cast<float>(d);
             bar_named(2, kUmmaE);
             float q = 0.f;
             for (int ch = 0; ch < half_cols; ch += 32) {
@@ -418,7 +422,10 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             }
             s_stat[hf * kTileM + row] = q;
             bar_named(2, kUmmaE);
-            const float rstd = 1.f / sqrtf((s_stat[row] + s_stat[kTileM + row]) / static_cast<float>(d) + p.eps);
+            tot = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
+            const float rstd = 1.f / sqrtf(tot / static_cast<float>(d) + p.eps);
             bar_named(2, kUmmaE);
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);

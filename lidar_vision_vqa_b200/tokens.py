@@ -53,15 +53,15 @@ class VATLiDARTokenizer(nn.Module):
         """``projection`` selects how the 1x1 projection runs (all variants are fp32-accurate and parity-tested):
         ``"fma"``   fp32 FFMA2 on the FMA pipes inside one fused kernel, any supported shape;
         ``"umma"``  tcgen05.mma.kind::tf32 as a 3-term hi/lo split, accumulator in tensor memory, the active cells of the
-                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256); same speed as ``"fma"`` on B200
-                    today (1.43 vs 1.42 ms on 16 x 512^2, d = 256): the GEMM itself becomes free, the row gathers and the
-                    LayerNorm epilogue around it set the time (DESIGN.md 4b);
+                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256): 1.37 ms against 1.42 ms of
+                    ``"fma"`` on 16 x 512^2 at d = 256, 0.87 against 0.96 ms at d = 128 (DESIGN.md 4b);
         ``"mma"``   the same split with legacy ``mma.sync`` (c_in % 8 == 0, d_model 128 or 256) -- slower, kept as evidence;
-        ``"auto"``  ``"fma"``."""
+        ``"auto"``  ``"umma"`` where it exists, else ``"fma"``."""
         super().__init__()
         if projection not in ("auto", "fma", "mma", "umma"):
             raise ValueError("projection must be one of auto / fma / mma / umma")
-        self.projection = "fma" if projection == "auto" else projection
+        umma_ok = c_in in (32, 64) and d_model in (128, 256)
+        self.projection = ("umma" if umma_ok else "fma") if projection == "auto" else projection
         self._umma: Optional[torch.Tensor] = None
         self._frag: Optional[torch.Tensor] = None
         self.c_in, self.d_model = int(c_in), int(d_model)

@@ -1,5 +1,5 @@
 """Timing of the BEV tokeniser (csrc/tokens.cu) on the cfg2 canvas: pillars_encode_bev -> tokens from the encoder's index
-map.  Usage: python profiles/time_tokens.py [frames] [d_model] [--dense] [--umma|--mma]"""
+map.  Usage: python profiles/time_tokens.py [frames] [d_model] [--dense] [--fma|--mma]"""
 import os
 import sys
 
@@ -28,7 +28,7 @@ p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
 bufs = ops.EncodeBuffers(len(pts), nb, grid, 64, dev)
 res = ops.encode_bev(p, o, grid, pfn, buffers=bufs)
 sd = to.random_token_params(64, d, seed=11)
-proj = "mma" if "--mma" in sys.argv else "umma" if "--umma" in sys.argv else "fma"
+proj = "mma" if "--mma" in sys.argv else "fma" if "--fma" in sys.argv else "umma"
 tk = T.VATLiDARTokenizer(64, d, projection=proj)
 tk.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
 tk = tk.eval().to(dev)

@@ -175,7 +175,7 @@ def test_cfg2_canvas_tokens_from_the_fused_encoder(dev):
     m = int(res["pillar_count"][-1].item())
     assert int((cell_row >= 0).sum().item()) == m
     tok_map = tk.forward_index_map(res["pillar_features"], cell_row)
-    for other in ("umma", "mma"):  # fp32 FFMA2 (default) vs tcgen05 split vs mma.sync split
+    for other in ("fma", "mma"):  # tcgen05 split (default for this shape) vs fp32 FFMA2 vs mma.sync split
         tok_o = make_tokenizer(sd, dev, projection=other).forward_index_map(res["pillar_features"], cell_row)
         assert float((tok_map - tok_o).abs().max()) < 3e-5, other
     tok_dense = tk(res["bev"])
