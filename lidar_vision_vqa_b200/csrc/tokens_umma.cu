@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t s_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = p.c, d = p.d, w = p.w, h = p.h;
-    const int kb_n = c >> 5, quads = c >> 2;
+    const int kb_n = c >> 5, quads = c >> 2, qshift = quads == 16 ? 4 : 3;
     const uint32_t w_half = static_cast<uint32_t>(kb_n) * d * 128u;       // bytes of W_hi (= W_lo)
     const uint32_t a_half = static_cast<uint32_t>(kb_n) * kTileM * 128u;  // bytes of A_hi (= A_lo)
     uint8_t *const s_al = s_raw + ((1024u - (smem_u32(s_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
                         const int yy = yy0 + k / 3 - 1, xx = xx0 + k % 3 - 1;
                         int32_t r = -1;
                         if (yy >= 0 && yy < h && xx >= 0 && xx < w) r = __ldg(p.cell_row + (static_cast<size_t>(b) * h + yy) * w + xx);
-                        nb[k] = r;
+                        nb[k] = r >= 0 ? r * quads : -1;  // float4 index of the row start: the refine adds the quad
                         if (r >= 0) {
                             const char *row = reinterpret_cast<const char *>(p.feats + static_cast<size_t>(r) * c);
                             for (int o = 0; o < c * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             // the A buffers are free once the previous tile's MMAs have completed
             if (it > 0 && !mbar_wait(mb_a_free, (it - 1) & 1u)) { report(1); break; }
             for (int item = rt; item < kTileM * quads; item += kUmmaR) {
-                const int row = item / quads, qd = item - row * quads;
+                const int row = item >> qshift, qd = item & (quads - 1);  // quads is 8 or 16
                 float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (s_ent[row] != kNoEntry) {
                     // all nine row gathers are requested before the first one is consumed
@@ -323,8 +323,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 9; ++k) {
                         const int32_t r = s_nb[row * 9 + k];
-                        f[k] = r >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.feats + static_cast<size_t>(r) * c) + qd)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[k] = r >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.feats) + (r + qd)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     float4 acc = *reinterpret_cast<const float4 *>(s_dw + 9 * c + 4 * qd);
 #pragma unroll
