@@ -135,6 +135,34 @@ def test_shapes_of_the_reference_test_matrix(dev, c, d, h, w):
     np.testing.assert_allclose(out, to.bev_tokens(bev, sd), rtol=TIGHT_RTOL, atol=1e-4)
 
 
+@pytest.mark.parametrize("projection", ["umma", "fma"])
+def test_frame_chunks_empty_and_full_canvases_on_both_projections(dev, projection):
+    """Edge cases of the tile machinery: more than 16 frames (index-map windows are staged 16 frames at a time), a pair count
+    that is not a multiple of the 128-row tile, no active pair at all, every pair active; c_in = 32 is a shape the tcgen05
+    variant is instantiated for."""
+    sd = to.random_token_params(32, 128, seed=9)
+    tk = make_tokenizer(sd, dev, projection)
+    assert tk.projection == projection
+    rng = np.random.default_rng(4)
+    h, w, b = 12, 44, 19
+    occ = rng.random((b, 1, h, w)) < 0.1
+    bev = np.where(occ, np.maximum(rng.standard_normal((b, 32, h, w)), 0), 0).astype(np.float32)
+    ref = to.bev_tokens(bev, sd)
+    out = tk(torch.from_numpy(bev).to(dev))
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=TIGHT_RTOL, atol=TIGHT_ATOL)
+    feats, coords = rows_of(bev)
+    rows = tk.forward_pillars(torch.from_numpy(feats).to(dev), torch.from_numpy(coords).to(dev), b, (h, w))
+    assert torch.equal(out, rows)
+    # nothing active: only the streamed background
+    expect = to.background_token(sd)[None] + to.positional_table(sd, h, w)
+    out0 = tk(torch.zeros(2, 32, h, w, device=dev)).cpu().numpy()
+    np.testing.assert_allclose(out0[1], expect, rtol=TIGHT_RTOL, atol=TIGHT_ATOL)
+    # everything active: 2 * 12 * 44 = 1056 pairs = 8 full tiles + 32 rows
+    dense = (rng.standard_normal((2, 32, h, w)) + 2.5).astype(np.float32)
+    np.testing.assert_allclose(tk(torch.from_numpy(dense).to(dev)).cpu().numpy(), to.bev_tokens(dense, sd),
+                               rtol=TIGHT_RTOL, atol=TIGHT_ATOL)
+
+
 def test_unsupported_shapes_fail_loudly(dev):
     from lidar_vision_vqa_b200 import NativeLibraryError
     from lidar_vision_vqa_b200 import tokens as T
