@@ -214,12 +214,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarr
 // The accumulator is double buffered in TMEM (2 x d columns), so MMA(i+1) may run while E still reads tile i; the A buffers
 // are single: refine(i+1) starts when the commit of MMA(i) has arrived (a_free).  mbarriers: a_free (1 arrival: commit),
 // acc_ready[2] (1: commit), acc_free[2] (kUmmaE: every E thread after its last TMEM read of the tile).
+template <int C, int D>
 __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ UmmaParams p)
 {
+    // channel counts are compile-time: shared-memory addressing of the weights and of the swizzled tiles folds into immediates
     extern __shared__ __align__(1024) uint8_t s_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = p.c, d = p.d, w = p.w, h = p.h;
-    const int kb_n = c >> 5, quads = c >> 2, qshift = quads == 16 ? 4 : 3;
+    constexpr int c = C, d = D;
+    const int w = p.w, h = p.h;
+    constexpr int kb_n = C >> 5, quads = C >> 2, qshift = quads == 16 ? 4 : 3;
     const uint32_t w_half = static_cast<uint32_t>(kb_n) * d * 128u;       // bytes of W_hi (= W_lo)
     const uint32_t a_half = static_cast<uint32_t>(kb_n) * kTileM * 128u;  // bytes of A_hi (= A_lo)
     uint8_t *const s_al = s_raw + ((1024u - (smem_u32(s_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
@@ -526,9 +529,15 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if ((e = cudaFuncSetAttribute(k_tok_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_tok_umma<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_tok_umma<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_tok_umma<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_tok_umma<32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     }
-    k_tok_umma<<<sms, kUmmaT, smem, st>>>(up);
+    if (tk.c == 64 && tk.d == 256) k_tok_umma<64, 256><<<sms, kUmmaT, smem, st>>>(up);
+    else if (tk.c == 64) k_tok_umma<64, 128><<<sms, kUmmaT, smem, st>>>(up);
+    else if (tk.d == 256) k_tok_umma<32, 256><<<sms, kUmmaT, smem, st>>>(up);
+    else k_tok_umma<32, 128><<<sms, kUmmaT, smem, st>>>(up);
     note_launch();
     return cudaGetLastError();
 }
