@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (ew & 3)) << 16) + static_cast<uint32_t>(cur * d + col0);
             float v[32];
             float s = 0.f;
+#pragma unroll 1
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
 #pragma unroll
@@ -413,6 +414,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             const float mean = tot / static_cast<float>(d);
             bar_named(2, kUmmaE);
             float q = 0.f;
+#pragma unroll 1
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
 #pragma unroll
@@ -429,6 +431,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
             const float rstd = 1.f / sqrtf(tot / static_cast<float>(d) + p.eps);
             bar_named(2, kUmmaE);
+#pragma unroll 1
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
                 if (ch + 32 >= half_cols) {  // last read of this accumulator stage: hand it back to the MMA issuer
