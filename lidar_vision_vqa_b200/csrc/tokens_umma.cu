@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
     int32_t *const s_nb_all = reinterpret_cast<int32_t *>(s_vec + 3 * d);                 // [2][128][9]
     uint32_t *const s_ent_all = reinterpret_cast<uint32_t *>(s_nb_all + 2 * kTileM * 9);  // [2][128]
     float *const s_stat = reinterpret_cast<float *>(s_ent_all + 2 * kTileM);              // [2][128] (E group, column halves)
-    uint64_t *const s_mbar = reinterpret_cast<uint64_t *>(s_stat + kParts * kTileM);      // a_free, acc_ready[2], acc_free[2]
+    uint64_t *const s_mbar = reinterpret_cast<uint64_t *>(s_stat + 2 * kParts * kTileM);      // a_free, acc_ready[2], acc_free[2]
     uint32_t *const s_tmem = reinterpret_cast<uint32_t *>(s_mbar + 5);
     volatile uint32_t *const s_abort = s_tmem + 1;
     const uint32_t mb_a_free = smem_u32(s_mbar), mb_ready0 = smem_u32(s_mbar + 1), mb_free0 = smem_u32(s_mbar + 3);
@@ -396,41 +396,44 @@ __global__ void __launch_bounds__(kUmmaT, 1) k_tok_umma(const __grid_constant__ 
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (ew & 3)) << 16) + static_cast<uint32_t>(cur * d + col0);
             float v[32];
-            float s = 0.f;
+            // LayerNorm statistics in ONE pass over the accumulator: sums of (x - c) and (x - c)^2 around the pivot c = the
+            // thread's first value (the shifted-data form: no cancellation as long as c lies inside the data), then the
+            // column parts are merged with the pairwise mean / M2 update.
+            float s1 = 0.f, s2 = 0.f, piv = 0.f;
 #pragma unroll 1
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
+                if (ch == 0) piv = v[0] + s_vec[col0];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 pb = *reinterpret_cast<const float4 *>(s_vec + col0 + ch + j);
-                    s += (v[j] + pb.x) + (v[j + 1] + pb.y) + (v[j + 2] + pb.z) + (v[j + 3] + pb.w);
+                    const float x0 = v[j] + pb.x - piv, x1 = v[j + 1] + pb.y - piv, x2 = v[j + 2] + pb.z - piv, x3 = v[j + 3] + pb.w - piv;
+                    s1 += (x0 + x1) + (x2 + x3);
+                    s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
                 }
             }
-            s_stat[hf * kTileM + row] = s;
-            bar_named(2, kUmmaE);
-            float tot = 0.f;
+            const float n_part = static_cast<float>(half_cols);
+            float mean = piv + s1 / n_part;          // mean of this thread's columns
+            float m2 = s2 - s1 * s1 / n_part;        // sum of squared deviations from it
+            if constexpr (kParts > 1) {
+                s_stat[hf * kTileM + row] = mean;
+                s_stat[(kParts + hf) * kTileM + row] = m2;
+                bar_named(2, kUmmaE);
+                float msum = 0.f;
 #pragma unroll
-            for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
-            const float mean = tot / static_cast<float>(d);
-            bar_named(2, kUmmaE);
-            float q = 0.f;
-#pragma unroll 1
-            for (int ch = 0; ch < half_cols; ch += 32) {
-                tmem_ld32(taddr + ch, v);
+                for (int pp = 0; pp < kParts; ++pp) msum += s_stat[pp * kTileM + row];
+                const float mall = msum / static_cast<float>(kParts);
+                float m2all = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 pb = *reinterpret_cast<const float4 *>(s_vec + col0 + ch + j);
-                    const float x0 = v[j] + pb.x - mean, x1 = v[j + 1] + pb.y - mean, x2 = v[j + 2] + pb.z - mean, x3 = v[j + 3] + pb.w - mean;
-                    q = fmaf(x0, x0, q); q = fmaf(x1, x1, q); q = fmaf(x2, x2, q); q = fmaf(x3, x3, q);
+                for (int pp = 0; pp < kParts; ++pp) {
+                    const float dm = s_stat[pp * kTileM + row] - mall;
+                    m2all += s_stat[(kParts + pp) * kTileM + row] + n_part * dm * dm;
                 }
+                bar_named(2, kUmmaE);
+                mean = mall;
+                m2 = m2all;
             }
-            s_stat[hf * kTileM + row] = q;
-            bar_named(2, kUmmaE);
-            tot = 0.f;
-#pragma unroll
-            for (int pp = 0; pp < kParts; ++pp) tot += s_stat[pp * kTileM + row];
-            const float rstd = 1.f / sqrtf(tot / static_cast<float>(d) + p.eps);
-            bar_named(2, kUmmaE);
+            const float rstd = 1.f / sqrtf(fmaxf(m2, 0.f) / static_cast<float>(d) + p.eps);
 #pragma unroll 1
             for (int ch = 0; ch < half_cols; ch += 32) {
                 tmem_ld32(taddr + ch, v);
@@ -487,7 +490,7 @@ size_t umma_smem_bytes(int c, int d)
 {
     const size_t kb_n = static_cast<size_t>(c) >> 5;
     return 2 * kb_n * d * 128 + 2 * kb_n * kTileM * 128 + sizeof(float) * (10 * static_cast<size_t>(c) + 3 * static_cast<size_t>(d)) +
-           2 * (sizeof(int32_t) * kTileM * 9 + sizeof(uint32_t) * kTileM) + sizeof(float) * kParts * kTileM + 5 * 8 + 16;
+           2 * (sizeof(int32_t) * kTileM * 9 + sizeof(uint32_t) * kTileM) + sizeof(float) * 2 * kParts * kTileM + 5 * 8 + 16;
 }
 
 }  // namespace
