@@ -53,8 +53,8 @@ class VATLiDARTokenizer(nn.Module):
         """``projection`` selects how the 1x1 projection runs (all variants are fp32-accurate and parity-tested):
         ``"fma"``   fp32 FFMA2 on the FMA pipes inside one fused kernel, any supported shape;
         ``"umma"``  tcgen05.mma.kind::tf32 as a 3-term hi/lo split, accumulator in tensor memory, the active cells of the
-                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256): 1.33 ms against 1.42 ms of
-                    ``"fma"`` on 16 x 512^2 at d = 256, 0.80 against 0.96 ms at d = 128 (DESIGN.md 4b);
+                    batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256): 1.31 ms against 1.42 ms of
+                    ``"fma"`` on 16 x 512^2 at d = 256, 0.79 against 0.96 ms at d = 128 (DESIGN.md 4b);
         ``"mma"``   the same split with legacy ``mma.sync`` (c_in % 8 == 0, d_model 128 or 256) -- slower, kept as evidence;
         ``"auto"``  ``"umma"`` where it exists, else ``"fma"``."""
         super().__init__()
