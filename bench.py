@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "bulk1d", "tma2d", "wide", "persist", "patch"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through the timed loop")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the timed steps are pipelined over (independent batches overlap)")
     ap.add_argument("--split", action="store_true",
                     help="put the scatter on a separate low-priority stream (measured: no gain, see DESIGN.md)")
