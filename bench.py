@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--link-warmup-ms", type=float, default=200.0,
                     help="untimed pinned host->device copies before each end-to-end region (wakes the PCIe link); 0 disables")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="host batches in flight in the end-to-end pipeline")
     ap.add_argument("--no-tokens", action="store_true", help="skip the BEV tokeniser side measurement")
     ap.add_argument("--tokens-d-model", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -521,7 +522,7 @@ def run_b200(args, rank, world, local_rank):
         # reads its per-frame pillar counts back.
         from lidar_vision_vqa_b200.pipeline import PillarEncoderPipeline
 
-        depth = 3
+        depth = args.e2e_depth
         pipe = PillarEncoderPipeline(vfe, n_frames=nb, max_points=max(p.shape[0] for p in pinned), depth=depth,
                                      scatter_variant=args.scatter_variant)
         wake_host_link()
