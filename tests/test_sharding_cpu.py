@@ -85,3 +85,17 @@ def test_gather_without_process_group_is_identity():
     coords = torch.zeros(5, 4, dtype=torch.int32)
     tok = sharding.gather_bev_tokens(feats, coords, frame_base=3, n_frames_total=4)
     assert torch.equal(tok.pillar_features, feats) and int(tok.voxel_coords[0, 0]) == 3
+
+
+def test_numa_binding_is_best_effort():
+    """No NVML / no GPU here: the helper must report None (or a CPU list) and never raise or change the affinity to nothing."""
+    import os
+
+    from lidar_vision_vqa_b200 import sharding
+
+    before = os.sched_getaffinity(0)
+    got = sharding.bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    assert got is None or (len(got) > 0 and set(got) <= before)
+    assert len(after) > 0
+    os.sched_setaffinity(0, before)
