@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PILLARS_ABI_VERSION 3
+#define PILLARS_ABI_VERSION 4
 
 /* error codes (negative; positive values are cudaError_t) */
 #define PILLARS_E_BADARG (-1)      /* NULL pointer, bad size, unsupported combination */
@@ -275,6 +275,14 @@ int pillars_set_stage_events(void *const *events4);
  * the next batch (on a higher-priority stream) then run alongside the bandwidth-bound canvas write of this one.  The
  * caller owns the hazards: the next call that reuses the same outputs / workspace must first wait for `stream`. */
 int pillars_set_scatter_stream(void *stream, int enable);
+
+/* Grouping implementation used by pillars_voxelize / pillars_encode_bev / pillars_encode_stack (thread-local):
+ *   0  automatic: the direct-mapped cell table when n_frames * cells <= 16 * n_points + 2^22 (every pillar grid of the
+ *      reference's configs), else the open-addressing hash table;
+ *   1  always the hash table;   2  the direct-mapped table whenever n_frames * cells < 2^31.
+ * Both produce bit-identical outputs (tests run every grouping case through both).  pillars_workspace_bytes() covers
+ * either choice. */
+int pillars_set_grouping(int mode);
 
 /* Test / measurement hook: non-zero makes pillars_encode_bev ignore the host weight copies and run the generic feature
  * kernel (thread-local). */

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "pillars_last_launch_count",
     "pillars_set_stage_events",
     "pillars_force_generic_features",
+    "pillars_set_grouping",
     "pillars_set_scatter_stream",
     "pillars_pfn_stack_in_features",
     "pillars_pfn_dense_stack",
@@ -37,7 +38,7 @@ EXPORTED_SYMBOLS = (
     "pillars_workspace_cell_row_offset",
 )
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LAYOUT_PILLAR_VFE, LAYOUT_SIMPLE2D = 0, 1
 MODE_HARD, MODE_DYNAMIC = 0, 1
 
@@ -146,6 +147,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_workspace_cell_row_offset.argtypes = [c_int64, c_int32, POINTER(PillarsGrid)]
     lib.pillars_set_scatter_stream.restype = c_int
     lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
+    lib.pillars_set_grouping.restype = c_int
+    lib.pillars_set_grouping.argtypes = [c_int]
     lib.pillars_force_generic_features.restype = c_int
     lib.pillars_force_generic_features.argtypes = [c_int]
     lib.pillars_set_stage_events.restype = c_int

@@ -26,6 +26,28 @@ static void stage_mark(int i, cudaStream_t st)
 
 void note_launch(int n) { g_launches += n; }
 
+int current_sm_count()
+{
+    static thread_local int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = sms;
+    return sms;
+}
+
+// grouping implementation: 0 = automatic, 1 = hash table, 2 = direct-mapped table whenever it is possible
+static thread_local int g_grouping = 0;
+
+static int resolve_group_mode(bool allow_dense, int64_t n, int nb, int64_t cells)
+{
+    if (!allow_dense || g_grouping == 1) return kGroupHash;
+    if (g_grouping == 2) return dense_possible(n, nb, cells) ? kGroupDense : kGroupHash;
+    return dense_preferred(n, nb, cells) ? kGroupDense : kGroupHash;
+}
+
 static int fail(int code, const char *fmt, ...)
 {
     va_list ap;
@@ -131,6 +153,13 @@ int pillars_set_scatter_stream(void *stream, int enable)
     return 0;
 }
 
+int pillars_set_grouping(int mode)
+{
+    if (mode < 0 || mode > 2) return fail(PILLARS_E_BADARG, "grouping mode = %d (0 auto, 1 hash, 2 dense)", mode);
+    g_grouping = mode;
+    return 0;
+}
+
 int pillars_force_generic_features(int on)
 {
     g_force_generic = on != 0;
@@ -154,7 +183,7 @@ size_t pillars_workspace_bytes(int64_t n_points, int32_t n_frames, const pillars
 {
     if (!grid || n_points < 0 || n_frames < 0) return 0;
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
-    return carve_workspace(nullptr, n_points, n_frames, cells_xy).total_bytes;
+    return workspace_bytes_any(n_points, n_frames, cells_xy, cells_xy * grid->grid[2]);
 }
 
 int pillars_frame_offsets(const float *points_b, int64_t n, int32_t row_stride, int32_t n_frames,
@@ -179,6 +208,7 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
     if ((rc = check_grid(grid, n_frames))) return rc;
     if ((rc = check_points(points, n, row_stride, col0, c_point))) return rc;
     if (!frame_offsets || !out) return fail(PILLARS_E_BADARG, "frame_offsets / out is NULL");
+    if (n > 0 && n_frames == 0) return fail(PILLARS_E_BADARG, "n_points = %lld with n_frames = 0", (long long)n);
     if (pfn && (rc = check_pfn(pfn))) return rc;
     if (pfn && pfn->c_point != c_point) return fail(PILLARS_E_BADARG, "pfn->c_point != c_point");
     if (pfn && !out->pillar_features) return fail(PILLARS_E_BADARG, "pillar_features output is required");
@@ -188,7 +218,9 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
     if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
         return fail(PILLARS_E_WORKSPACE, "workspace NULL or not 256-byte aligned");
-    const Workspace ws = carve_workspace(workspace, n, n_frames, cells_xy);
+    const int64_t cells = cells_xy * grid->grid[2];
+    const Workspace ws = carve_workspace(workspace, n, n_frames, cells_xy, cells,
+                                         resolve_group_mode(true, n, n_frames, cells));
     if (ws.total_bytes > workspace_bytes)
         return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.total_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -218,8 +250,8 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         px.voxel_coords = out->voxel_coords;
         px.voxel_num_points = out->voxel_num_points;
         px.write_cell_row = want_bev;
-        px.capacity = out->pillar_capacity;
     }
+    px.capacity = out->pillar_capacity;
     if ((e = launch_group_points(points, n, row_stride, col0, c_point, frame_offsets, n_frames, gd, ws, out->pillar_count,
                                  /*want_index_lists=*/membership || !fast, px, st)) != cudaSuccess)
         return cuda_fail(e, "group_points");
@@ -257,6 +289,10 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         fj.n = n;
         fj.idx_bits = job.idx_bits;
         fj.pillar_features = out->pillar_features;
+        for (int i = 0; i < 3; ++i) {
+            fj.vsz[i] = grid->voxel[i];
+            fj.off[i] = pfn->offset[i];
+        }
         if ((e = launch_pillar_features_stream(fj, folded, gd, ws, st)) != cudaSuccess)
             return cuda_fail(e, "pillar_features_stream");
     }
@@ -421,7 +457,11 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
     if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
         return fail(PILLARS_E_WORKSPACE, "workspace NULL or not 256-byte aligned");
-    const Workspace ws = carve_workspace(workspace, n, n_frames, cells_xy);
+    if (n > 0 && n_frames == 0) return fail(PILLARS_E_BADARG, "n_points = %lld with n_frames = 0", (long long)n);
+    const int64_t cells = cells_xy * grid->grid[2];
+    // the dynamic variant ranks the cells of the dense index-map region itself: it keeps the hash table
+    const Workspace ws = carve_workspace(workspace, n, n_frames, cells_xy, cells,
+                                         resolve_group_mode(!dynamic, n, n_frames, cells));
     if (ws.total_bytes > workspace_bytes)
         return fail(PILLARS_E_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, ws.total_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -434,6 +474,7 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     cudaError_t e;
     stage_mark(0, st);
     PlaceExtras px{};
+    px.capacity = out->pillar_capacity;
     if ((e = launch_group_points(points, n, row_stride, col0, stack->c_point, frame_offsets, n_frames, gd, ws,
                                  out->pillar_count, /*want_index_lists=*/true, px, st)) != cudaSuccess)
         return cuda_fail(e, "group_points");
@@ -682,7 +723,9 @@ size_t pillars_workspace_cell_row_offset(int64_t n_points, int32_t n_frames, con
     if (!grid || n_points < 0 || n_frames < 0) return 0;
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
     char *base = reinterpret_cast<char *>(static_cast<uintptr_t>(4096));  // any non-null base: only the offset is wanted
-    const Workspace ws = carve_workspace(base, n_points, n_frames, cells_xy);
+    const int64_t cells = cells_xy * grid->grid[2];
+    const Workspace ws = carve_workspace(base, n_points, n_frames, cells_xy, cells,
+                                         resolve_group_mode(true, n_points, n_frames, cells));
     return static_cast<size_t>(reinterpret_cast<char *>(ws.cell_row) - base);
 }
 

@@ -47,8 +47,16 @@ struct __align__(32) PointRecord {
 static constexpr int kMaxFrames = 1024;  // frame_offsets are staged in shared memory
 static constexpr int kTile = 1024;       // points per CTA tile of the scan kernel
 
+// Two grouping implementations fill the same workspace products:
+//   kGroupHash   open-addressing hash table keyed by the 32-bit cell key (any grid, voxelize.cu)
+//   kGroupDense  direct-mapped table with one entry per (frame, cell) (group_dense.cu); chosen when n_frames * cells is of
+//                the order of the point count, which is the case for every pillar grid of the reference's configs
+enum GroupMode { kGroupHash = 0, kGroupDense = 1 };
+
 struct Workspace {
-    // zero-initialised region
+    int mode;
+    // hash: zero-initialised region.  dense: hdr / frame tables need no initialisation, the tile descriptors live in the
+    // 0xFF region (a descriptor is ready when bit 63 is clear)
     Header *hdr;
     unsigned long long *tile_desc;  // [n_tiles] scan: per-tile aggregates (valid bit | pillars | listed points)
     unsigned long long *tile_prefix;// [n_tiles] scan: inclusive prefixes published by the last tile of each group
@@ -56,18 +64,22 @@ struct Workspace {
     uint32_t *frame_rowbase;        // [B+1] output row at each frame start (after the max_voxels cap)
     size_t zero_bytes;
     // 0xFF-initialised region
-    HashEntry *table;               // [cap]
-    int32_t *cell_row;              // [B * ny * nx] dense BEV index map, -1 = empty
+    HashEntry *table;               // hash: [cap]
+    uint32_t *tile_counter;         // dense: dynamic tile ids, counts up from 0xFFFFFFFF
+    uint32_t *frame_new;            // dense: [B] pillars opened in each frame, minus one
+    uint32_t *cell_first;           // dense: [B * cells] smallest point index of the cell; after the scan 0x80000000 | list base
+    int32_t *cell_row;              // BEV index map, -1 = empty.  hash: [B * ny * nx].  dense: [B * cells], holds
+                                    // "points in the cell - 1" between the insert and the scan kernel
     size_t ff_bytes;
     // no init needed
-    int32_t *point_slot;            // [n] hash slot of each point, -1 = rejected
+    int32_t *point_slot;            // [n] hash: slot of each point; dense: its key b * cells + cell; -1 = rejected
     uint32_t *point_arrival;        // [n] arrival rank inside the cell (arbitrary order, only a bijection)
     uint32_t *pillar_key;           // [n] cell key of pillar g
     uint32_t *pillar_list;          // [n] start of pillar g's point list
     uint32_t *pillar_cnt;           // [n] points that fell into pillar g (uncapped)
     uint32_t *sorted_idx;           // [n] point indices grouped by pillar
     PointRecord *records;           // [n] point records grouped by pillar
-    float4 *pillar_meta;            // [2n] per pillar, at its list start position: {centre x,y,z, 1.0 if n < P} {row (int bits, -1: dropped), n (uint bits), -, -}
+    uint4 *pillar_meta;             // [n] per pillar, at its list start position: {cell key, row (-1: dropped), n, -}
     float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
     uint32_t *scan_scratch;         // [B * ny * nx / 2048 + 2] block sums of the cell-rank scan (dynamic variant)
     uint32_t cap;                   // hash slots
@@ -85,10 +97,23 @@ __host__ __device__ __forceinline__ T tmin(T a, T b)
     return a < b ? a : b;
 }
 
-// Carves `base` (may be nullptr to only size it).  n = total points, nb = frames, cells_xy = ny*nx.
-inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy)
+// The dense table needs n_frames * cells entries: worth it while that stays within a small multiple of the point count
+// (16 x 512^2 cells for 0.5 M points at cfg2) and below 2^31 (the base tag bit).
+inline bool dense_possible(int64_t n, int nb, int64_t cells)
+{
+    const int64_t total = static_cast<int64_t>(nb) * cells;
+    return n > 0 && total > 0 && total < (1ll << 31);
+}
+inline bool dense_preferred(int64_t n, int nb, int64_t cells)
+{
+    return dense_possible(n, nb, cells) && static_cast<int64_t>(nb) * cells <= 16 * n + (1ll << 22);
+}
+
+// Carves `base` (may be nullptr to only size it).  n = total points, nb = frames, cells_xy = ny*nx, cells = nz*ny*nx.
+inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy, int64_t cells, int mode)
 {
     Workspace w{};
+    w.mode = mode;
     char *p = reinterpret_cast<char *>(base);
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -100,29 +125,55 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     uint64_t cap = static_cast<uint64_t>(n) + static_cast<uint64_t>(n) / 2 + 64;  // load factor <= 2/3 worst case
     w.cap = static_cast<uint32_t>(cap);
     w.zero_begin = p ? p : nullptr;
-    w.hdr = reinterpret_cast<Header *>(take(sizeof(Header)));
-    w.tile_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
-    w.tile_prefix = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
-    w.frame_gstart = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
-    w.frame_rowbase = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
-    w.zero_bytes = off;
-    w.ff_begin = p ? p + off : nullptr;
-    size_t ff0 = off;
-    w.table = reinterpret_cast<HashEntry *>(take(n > 0 ? sizeof(HashEntry) * cap : 0));
-    w.cell_row = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * static_cast<size_t>(nb) * cells_xy));
-    w.ff_bytes = off - ff0;
+    if (mode == kGroupHash) {
+        w.hdr = reinterpret_cast<Header *>(take(sizeof(Header)));
+        w.tile_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
+        w.tile_prefix = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
+        w.frame_gstart = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+        w.frame_rowbase = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+        w.zero_bytes = off;
+        w.ff_begin = p ? p + off : nullptr;
+        const size_t ff0 = off;
+        w.table = reinterpret_cast<HashEntry *>(take(n > 0 ? sizeof(HashEntry) * cap : 0));
+        w.cell_row = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * static_cast<size_t>(nb) * cells_xy));
+        w.ff_bytes = off - ff0;
+    } else {
+        w.zero_bytes = 0;
+        w.ff_begin = p ? p : nullptr;
+        w.tile_counter = reinterpret_cast<uint32_t *>(take(64));
+        w.frame_new = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+        w.tile_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
+        w.tile_prefix = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
+        w.cell_first = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * static_cast<size_t>(nb) * cells));
+        w.cell_row = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * static_cast<size_t>(nb) * cells));
+        w.ff_bytes = off;
+        w.hdr = reinterpret_cast<Header *>(take(sizeof(Header)));
+        w.frame_gstart = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+        w.frame_rowbase = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
+    }
     w.point_slot = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * n));
     w.point_arrival = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.pillar_key = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.pillar_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.pillar_cnt = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.sorted_idx = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
-    w.records = reinterpret_cast<PointRecord *>(take(sizeof(PointRecord) * n));
-    w.pillar_meta = reinterpret_cast<float4 *>(take(sizeof(float4) * 2 * n));
+    w.records = reinterpret_cast<PointRecord *>(take(sizeof(PointRecord) * (n + 64)));  // + a look-ahead chunk of slack
+    w.pillar_meta = reinterpret_cast<uint4 *>(take(sizeof(uint4) * (n + 64)));
     w.folded = reinterpret_cast<float *>(take(sizeof(float) * PILLARS_FOLDED_FLOATS));
     w.scan_scratch = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (static_cast<size_t>(nb) * cells_xy / 2048 + 2)));
     w.total_bytes = off;
     return w;
+}
+
+// bytes that fit either layout (what pillars_workspace_bytes reports)
+inline size_t workspace_bytes_any(int64_t n, int nb, int64_t cells_xy, int64_t cells)
+{
+    size_t b = carve_workspace(nullptr, n, nb, cells_xy, cells, kGroupHash).total_bytes;
+    if (dense_possible(n, nb, cells)) {
+        const size_t d = carve_workspace(nullptr, n, nb, cells_xy, cells, kGroupDense).total_bytes;
+        if (d > b) b = d;
+    }
+    return b;
 }
 
 // Device-side copy of pillars_grid_t plus derived integers.
@@ -163,6 +214,8 @@ struct PfnDev {
 
 // launch bookkeeping (api.cu)
 void note_launch(int n = 1);
+// SM count of the calling thread's current device (cached per device)
+int current_sm_count();
 
 // ---- launchers implemented in the kernel translation units ---------------------------------------
 cudaError_t launch_frame_offsets(const float *points_b, int64_t n, int stride, int nb, int32_t *offs, cudaStream_t st);
@@ -180,6 +233,12 @@ struct PlaceExtras {
 cudaError_t launch_group_points(const float *points, int64_t n, int stride, int col0, int c_point,
                                 const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
                                 int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras, cudaStream_t st);
+
+// the direct-mapped implementation (group_dense.cu); same products as launch_group_points, chosen by ws.mode
+cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride, int col0, int c_point,
+                                      const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
+                                      int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras,
+                                      cudaStream_t st);
 
 struct FeatureJob {
     const float *points;
@@ -204,6 +263,7 @@ struct FastJob {
     int64_t n;  // upper bound of listed points (the input point count)
     int idx_bits;
     float *pillar_features;
+    float vsz[3], off[3];  // pillar centre = coord * vsz + off (pillar_vfe.py:79-81,101-103)
 };
 // The streaming feature kernel (pfn_stream.cu) and the folding of one PFN layer into its table:
 //   rows 0-4   per point   scale * (W_p + W_cluster + W_centre) for x,y,z;  scale * W for intensity, time

@@ -1,0 +1,389 @@
+// Point -> pillar grouping with a DIRECT-MAPPED cell table (same semantics and same workspace products as voxelize.cu;
+// replaces the spconv CPU call behind src/lidar-encoder/pcdet/datasets/processor/data_processor.py:16-61,133-180).
+//
+// Every pillar grid of the reference's configs has n_frames * cells within a small multiple of the point count (16 x 512^2
+// cells for 0.5 M points), so the "hash table" can be the identity: one 8-byte entry per (frame, cell), split into two
+// 4-byte planes that a single 0xFF memset initialises and that stay L2 resident.
+//
+//   k_insert_dense   coalesced tile loads -> fp32 sub/div/floor -> key = frame * cells + cell.  __match_any_sync merges the
+//                    lanes of a warp that hit the same cell; the leader issues ONE atomicAdd on the count plane (returns
+//                    the arrival rank of the group) and one fire-and-forget atomicMin on the first-index plane.  No
+//                    probing, no CAS loop, no key compare: one dependent L2 round trip per point instead of two or more.
+//                    The claim of an empty cell also counts the frame's pillars (one atomic per CTA), so the scan kernel
+//                    knows every frame's row base before it starts.
+//   k_scan_dense     single-pass chained scan over points in index order of [point is the first of its cell] and of the
+//                    cell counts => pillar id in first-appearance order + start of its point list (no sort).  The thread
+//                    that owns a pillar's first point writes everything per-pillar that needs no feature arithmetic:
+//                    voxel_coords, voxel_num_points, the pillar's {key, row, n} record for the feature kernel, the BEV
+//                    index-map entry (the count plane BECOMES the index map: empty cells already hold -1), and the
+//                    list base into the first-index plane (tagged with bit 31 so that it can never be mistaken for a
+//                    point index by a tile that is still testing "am I the first").
+//   k_place_dense    point -> its pillar's list (index list and/or 32-byte records): key -> base -> position.
+#include "group_common.cuh"
+
+namespace pillars {
+
+namespace {
+
+constexpr int kScanThreads = 512;
+constexpr int kScanPer = kTile / kScanThreads;  // 2
+constexpr uint32_t kBaseTag = 0x80000000u;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__global__ void __launch_bounds__(kGroupThreads, 8)
+k_insert_dense(const float *__restrict__ points, int64_t n, int stride, int col0, const int32_t *__restrict__ frame_offsets,
+               int nb, GridDev gd, uint32_t *__restrict__ cell_first, uint32_t *__restrict__ cell_cnt,
+               int32_t *__restrict__ point_key, uint32_t *__restrict__ point_arrival, uint32_t *__restrict__ frame_new,
+               int vec_ok)
+{
+    extern __shared__ __align__(16) float s_pts[];  // [kGroupThreads * stride]
+    __shared__ int s_b0, s_b1;
+    __shared__ uint32_t s_claims;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kGroupThreads;
+    const int count = static_cast<int>(tmin<int64_t>(kGroupThreads, n - tile_start));
+    load_point_tile(points + tile_start * stride, count, stride, vec_ok, s_pts, tid, kGroupThreads);
+    if (tid < 2) {  // frames touched by this tile: [b0, b1]
+        const int lo = find_frame(frame_offsets, nb, tid == 0 ? tile_start : tile_start + count - 1);
+        if (tid == 0) s_b0 = lo; else s_b1 = lo;
+    }
+    if (tid == 2) s_claims = 0u;
+    __syncthreads();
+
+    const int64_t i = tile_start + tid;
+    bool valid = false;
+    uint32_t key = 0;
+    int b = s_b0;
+    if (tid < count) {
+        uint32_t cell = 0;
+        valid = quantize_point(s_pts + tid * stride + col0, gd, cell);
+        if (valid) {
+            const int b1 = s_b1;
+            while (b < b1 && __ldg(frame_offsets + b + 1) <= i) ++b;
+            key = static_cast<uint32_t>(b) * gd.cells + cell;
+        }
+    }
+    const unsigned active = __ballot_sync(kFullMask, valid);
+    int32_t key_out = -1;
+    uint32_t arrival = 0;
+    bool claimed = false;
+    if (valid) {
+        const unsigned peers = __match_any_sync(active, key);
+        const int leader = __ffs(peers) - 1;  // lowest lane == smallest point index of the group
+        uint32_t base = 0;
+        if (lane == leader) {
+            // count plane holds "points - 1" (0xFFFFFFFF = empty): the returned value + 1 is the group's arrival rank
+            const uint32_t old = atomicAdd(&cell_cnt[key], static_cast<uint32_t>(__popc(peers)));
+            atomicMin(&cell_first[key], static_cast<uint32_t>(i));
+            claimed = old == 0xFFFFFFFFu;
+            base = old + 1u;
+        }
+        base = __shfl_sync(peers, base, leader);
+        arrival = base + static_cast<uint32_t>(__popc(peers & lanemask_lt()));
+        key_out = static_cast<int32_t>(key);
+    }
+    // pillars opened per frame: one atomic per CTA when the tile lies inside one frame (the rule), else one per claim
+    const bool one_frame = s_b0 == s_b1;
+    const unsigned cl = __ballot_sync(kFullMask, claimed);
+    if (one_frame) {
+        if (lane == 0 && cl) atomicAdd(&s_claims, static_cast<uint32_t>(__popc(cl)));
+    } else if (claimed) {
+        atomicAdd(&frame_new[b], 1u);
+    }
+    if (tid < count) {
+        point_key[i] = key_out;
+        point_arrival[i] = arrival;
+    }
+    __syncthreads();
+    if (one_frame && tid == 0 && s_claims) atomicAdd(&frame_new[s_b0], s_claims);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan.  Descriptor = pillars(31) << 31 | listed points(31), bit 63 CLEAR when ready (the region is 0xFF-initialised);
+// running sums travel as (pillars << 32 | listed)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_desc(unsigned long long v)
+{
+    return ((v >> 32) << 31) | (v & 0x7FFFFFFFull);
+}
+__device__ __forceinline__ unsigned long long wait_desc(const unsigned long long *p)
+{
+    unsigned long long d;
+    do {
+        d = ld_relaxed_u64(p);
+    } while (d >> 63);
+    return ((d >> 31) << 32) | (d & 0x7FFFFFFFull);
+}
+
+template <int kWarps>
+__device__ __forceinline__ unsigned long long block_scan_excl(unsigned long long v, unsigned long long *s_warp, int lane,
+                                                              int warp, unsigned long long &total)
+{
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long wex = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const unsigned long long s = s_warp[w];
+        if (w < warp) wex += s;
+        total += s;
+    }
+    __syncthreads();
+    return wex + incl - v;
+}
+
+struct ScanDenseParams {
+    int64_t n;
+    uint32_t n_tiles;
+    const int32_t *point_key;
+    uint32_t *cell_first;
+    int32_t *cell_row;  // count plane on entry, BEV index map on exit
+    uint32_t *tile_counter;
+    unsigned long long *tile_agg, *tile_prefix;
+    const uint32_t *frame_new;
+    int nb;
+    Header *hdr;
+    uint32_t *frame_gstart, *frame_rowbase;
+    int32_t *pillar_count;
+    uint32_t *pillar_key, *pillar_list, *pillar_cnt;  // when write_lists
+    uint4 *pillar_meta;                               // when write_meta
+    int32_t *voxel_coords, *voxel_num_points;         // when write_meta (may be NULL)
+    GridDev gd;
+    int sh_cells, sh_cells_xy, sh_nx;
+    int64_t capacity;
+    int write_lists, write_meta;
+};
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_constant__ ScanDenseParams p)
+{
+    constexpr int kWarps = kScanThreads / 32;
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_warp[kWarps];
+    __shared__ unsigned long long s_look[kWarps];
+    __shared__ uint32_t s_gstart[kMaxFrames + 1], s_rowbase[kMaxFrames + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // A tile spins on its predecessors, so they must be running: ids are handed out in scheduling order.
+    if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1u) + 1u;
+
+    // ---- per-frame tables from the insert kernel's pillar counts: first-appearance id and output row at each frame start
+    const uint32_t mv = static_cast<uint32_t>(p.gd.max_voxels);
+    {
+        const int f0 = 2 * tid;
+        uint32_t g0 = 0, g1 = 0;
+        if (f0 < p.nb) g0 = __ldcg(p.frame_new + f0) + 1u;
+        if (f0 + 1 < p.nb) g1 = __ldcg(p.frame_new + f0 + 1) + 1u;
+        const uint32_t r0 = min(g0, mv), r1 = min(g1, mv);
+        unsigned long long total;
+        const unsigned long long ex = block_scan_excl<kWarps>(
+            (static_cast<unsigned long long>(g0 + g1) << 32) | static_cast<unsigned long long>(r0 + r1), s_warp, lane, warp,
+            total);  // (also orders the s_tile store before its use)
+        const uint32_t eg = static_cast<uint32_t>(ex >> 32), er = static_cast<uint32_t>(ex & 0xFFFFFFFFull);
+        if (f0 < p.nb) {
+            s_gstart[f0] = eg;
+            s_rowbase[f0] = er;
+        }
+        if (f0 + 1 < p.nb) {
+            s_gstart[f0 + 1] = eg + g0;
+            s_rowbase[f0 + 1] = er + r0;
+        }
+        if (tid == 0) {
+            s_gstart[p.nb] = static_cast<uint32_t>(total >> 32);
+            s_rowbase[p.nb] = static_cast<uint32_t>(total & 0xFFFFFFFFull);
+        }
+        if (s_tile == 0) {  // tile 0 publishes the tables for the later stages
+            if (f0 < p.nb) {
+                p.frame_gstart[f0] = eg;
+                p.frame_rowbase[f0] = er;
+                if (p.pillar_count) p.pillar_count[f0] = static_cast<int32_t>(r0);
+            }
+            if (f0 + 1 < p.nb) {
+                p.frame_gstart[f0 + 1] = eg + g0;
+                p.frame_rowbase[f0 + 1] = er + r0;
+                if (p.pillar_count) p.pillar_count[f0 + 1] = static_cast<int32_t>(r1);
+            }
+            if (tid == 0) {
+                p.frame_gstart[p.nb] = static_cast<uint32_t>(total >> 32);
+                p.frame_rowbase[p.nb] = static_cast<uint32_t>(total & 0xFFFFFFFFull);
+                if (p.pillar_count) p.pillar_count[p.nb] = static_cast<int32_t>(total & 0xFFFFFFFFull);
+                p.hdr->total_pillars = static_cast<uint32_t>(total >> 32);
+            }
+        }
+    }
+
+    const uint32_t tile = s_tile;
+    const int64_t tile_start = static_cast<int64_t>(tile) * kTile;
+    const int64_t i0 = tile_start + tid * kScanPer;
+
+    int32_t key[kScanPer];
+    if (i0 + kScanPer <= p.n) {
+        const int2 v = *reinterpret_cast<const int2 *>(p.point_key + i0);
+        key[0] = v.x;
+        key[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) key[k] = (i0 + k < p.n) ? p.point_key[i0 + k] : -1;
+    }
+    uint32_t first[kScanPer], cntm1[kScanPer];
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {  // all gathers in flight before the first use
+        first[k] = key[k] >= 0 ? __ldcg(p.cell_first + key[k]) : 0xFFFFFFFFu;
+        cntm1[k] = key[k] >= 0 ? static_cast<uint32_t>(__ldcg(p.cell_row + key[k])) : 0u;
+    }
+    unsigned long long val[kScanPer];
+    unsigned flags = 0;
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        val[k] = 0;
+        // a tagged entry (list base already written by the pillar's owner) never equals a point index
+        if (key[k] >= 0 && first[k] == static_cast<uint32_t>(i0 + k)) {
+            val[k] = (1ull << 32) | static_cast<unsigned long long>(cntm1[k] + 1u);
+            flags |= 1u << k;
+        }
+        tsum += val[k];
+    }
+    unsigned long long tile_sum;
+    const unsigned long long thr_excl = block_scan_excl<kWarps>(tsum, s_warp, lane, warp, tile_sum);
+    if (tid == 0) st_relaxed_u64(&p.tile_agg[tile], pack_desc(tile_sum));  // visible to the successors at once
+
+    // look-back: aggregates of the tiles of my group that precede me (one parallel read) + prefix of the previous group
+    const uint32_t group_first = tile & ~static_cast<uint32_t>(kLookGroup - 1);
+    unsigned long long look = 0;
+    if (tid < kLookGroup && group_first + tid < tile) look = wait_desc(&p.tile_agg[group_first + tid]);
+    if (tid == kScanThreads - 1 && group_first > 0) look += wait_desc(&p.tile_prefix[group_first - 1]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) look += __shfl_xor_sync(kFullMask, look, s);
+    if (lane == 0) s_look[warp] = look;
+    __syncthreads();
+    unsigned long long tile_excl = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) tile_excl += s_look[w];
+    if (tid == 0 && (tile & (kLookGroup - 1)) == kLookGroup - 1)
+        st_relaxed_u64(&p.tile_prefix[tile], pack_desc(tile_excl + tile_sum));
+
+    unsigned long long run = tile_excl + thr_excl;
+    const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        if (flags & (1u << k)) {
+            const uint32_t g = static_cast<uint32_t>(run >> 32);
+            const uint32_t base = static_cast<uint32_t>(run & 0xFFFFFFFFull);
+            const uint32_t n = static_cast<uint32_t>(val[k] & 0xFFFFFFFFull);
+            const uint32_t ukey = static_cast<uint32_t>(key[k]);
+            const CellCoord c = decode_key(p, ukey);
+            const uint32_t local = g - s_gstart[c.b];
+            const int64_t row = static_cast<int64_t>(s_rowbase[c.b]) + local;
+            const bool live = local < mv && row < p.capacity;
+            p.cell_row[ukey] = live ? static_cast<int32_t>(row) : -1;
+            p.cell_first[ukey] = kBaseTag | base;
+            if (p.write_lists) {
+                p.pillar_key[g] = ukey;
+                p.pillar_list[g] = base;
+                p.pillar_cnt[g] = n;
+            }
+            if (p.write_meta) {
+                // indexed by the list START POSITION, so the feature kernel needs nothing but its own position to find it
+                p.pillar_meta[base] = make_uint4(ukey, live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, 0u);
+                if (live) {
+                    if (p.voxel_coords)
+                        *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) = make_int4(
+                            static_cast<int>(c.b), static_cast<int>(c.z), static_cast<int>(c.y), static_cast<int>(c.x));
+                    if (p.voxel_num_points) p.voxel_num_points[row] = static_cast<int32_t>(min(n, P));
+                }
+            }
+            run += val[k];
+        }
+    }
+    if (tile == p.n_tiles - 1 && tid == 0)
+        p.hdr->total_listed = static_cast<uint32_t>((tile_excl + tile_sum) & 0xFFFFFFFFull);
+}
+
+__global__ void __launch_bounds__(kGroupThreads) k_place_dense(const __grid_constant__ PlaceParams p)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kGroupThreads + threadIdx.x;
+    if (i >= p.n) return;
+    const int32_t key = p.point_slot[i];
+    if (key < 0) return;
+    const uint32_t arrival = p.point_arrival[i];
+    const uint32_t base = __ldg(p.cell_first + key) & ~kBaseTag;
+    const uint32_t pos = base + arrival;
+    if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i);
+    if (!p.records) return;
+    write_record(p, i, decode_key(p, static_cast<uint32_t>(key)), pos, arrival);
+}
+
+}  // namespace
+
+cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride, int col0, int c_point,
+                                      const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
+                                      int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras,
+                                      cudaStream_t st)
+{
+    cudaError_t err;
+    // ONE memset per call: tile counter, per-frame pillar counters, scan descriptors and both planes of the cell table all
+    // start from 0xFF bytes (counters count up from -1, a descriptor is ready once bit 63 is clear).
+    if ((err = cudaMemsetAsync(ws.ff_begin, 0xFF, ws.ff_bytes, st)) != cudaSuccess) return err;
+    note_launch();
+    if (n == 0) {
+        if (pillar_count) {
+            if ((err = cudaMemsetAsync(pillar_count, 0, sizeof(int32_t) * (nb + 1), st)) != cudaSuccess) return err;
+            note_launch();
+        }
+        return cudaSuccess;
+    }
+    const size_t smem = sizeof(float) * kGroupThreads * stride;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(points) % 16 == 0) ? 1 : 0;  // tile starts are 256 rows apart
+    const unsigned pb = static_cast<unsigned>((n + kGroupThreads - 1) / kGroupThreads);
+    k_insert_dense<<<pb, kGroupThreads, smem, st>>>(points, n, stride, col0, frame_offsets, nb, gd, ws.cell_first,
+                                                    reinterpret_cast<uint32_t *>(ws.cell_row), ws.point_slot,
+                                                    ws.point_arrival, ws.frame_new, vec_ok);
+    note_launch();
+
+    const PlaceParams pp = make_place_params(points, n, stride, col0, c_point, gd, ws, want_index_lists, extras);
+    ScanDenseParams sp{};
+    sp.n = n;
+    sp.n_tiles = ws.n_tiles;
+    sp.point_key = ws.point_slot;
+    sp.cell_first = ws.cell_first;
+    sp.cell_row = ws.cell_row;
+    sp.tile_counter = ws.tile_counter;
+    sp.tile_agg = ws.tile_desc;
+    sp.tile_prefix = ws.tile_prefix;
+    sp.frame_new = ws.frame_new;
+    sp.nb = nb;
+    sp.hdr = ws.hdr;
+    sp.frame_gstart = ws.frame_gstart;
+    sp.frame_rowbase = ws.frame_rowbase;
+    sp.pillar_count = pillar_count;
+    sp.pillar_key = ws.pillar_key;
+    sp.pillar_list = ws.pillar_list;
+    sp.pillar_cnt = ws.pillar_cnt;
+    sp.pillar_meta = ws.pillar_meta;
+    sp.voxel_coords = pp.voxel_coords;
+    sp.voxel_num_points = pp.voxel_num_points;
+    sp.gd = gd;
+    sp.sh_cells = pp.sh_cells;
+    sp.sh_cells_xy = pp.sh_cells_xy;
+    sp.sh_nx = pp.sh_nx;
+    sp.capacity = extras.records ? extras.capacity : (1ll << 62);
+    sp.write_lists = want_index_lists ? 1 : 0;
+    sp.write_meta = extras.records ? 1 : 0;
+    k_scan_dense<<<ws.n_tiles, kScanThreads, 0, st>>>(sp);
+    note_launch();
+    if (want_index_lists || extras.records) {
+        k_place_dense<<<pb, kGroupThreads, 0, st>>>(pp);
+        note_launch();
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace pillars

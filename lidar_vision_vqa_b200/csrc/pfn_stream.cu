@@ -1,48 +1,68 @@
 // Per-pillar feature stage for the mainstream configuration (USE_ABSLOTE_XYZ, no WITH_DISTANCE, C <= 5 point channels,
 // one PFN layer, F = 64): pillar_vfe.py:94-123 (augment) + :29-49 (Linear + BatchNorm(eval) + ReLU + max over the pillar).
 //
-// Shape of the work.  The points arrive as 32-byte records grouped by pillar (k_place), ~2 points per pillar.  The layer is
+// Shape of the work.  The points arrive as 32-byte records grouped by pillar (place kernel), ~2 points per pillar, and one
+// 16-byte {cell key, row, n} record per pillar at the pillar's list start position (scan / place kernel).  The layer is
 // regrouped around the pillar centre c (x' = x - c, m' = mean - c):
 //       W.[p, p_xyz - mean, p_xyz - c] = (W_p + W_cl + W_ce).x' + W_it.(i,t)  +  [ W_p.c - W_cl.m' ]
 // i.e. 5 FMAs per (point, channel) plus one 6-FMA constant per (pillar, channel); every per-point term is a small number, so
 // nothing cancels.  BatchNorm's scale is folded into W, and since "+ constant" and ReLU are monotone the max over the
 // pillar's points is taken before them.
 //
-// Mapping.  The kernel is bound by instruction issue, not by HBM, so the layout minimises issued instructions per point:
-//   * phase 1, one thread per list position (CTA = kFT positions + a 32-position look-ahead): stage the records in shared
-//     memory; the thread sitting on a list start derives the pillar's row, centre, mean and writes voxel_coords /
-//     voxel_num_points / the BEV index map; every thread then rewrites its point relative to the centre (NaN when the point
-//     is beyond the first-P cap: fmaxf ignores NaN, so dropped points need no branch later);
-//   * phase 2, one warp per run of pillars, ONE LANE PER CHANNEL PAIR: the warp walks its points in list order, each point
-//     is two broadcast shared-memory loads + 5 packed FFMA2 (fma.rn.f32x2: two channels per instruction, the point value
-//     as the scalar-broadcast operand) + 2 FMNMX with the running max in registers; at a pillar end (a flag stored with
-//     the point) the lanes add the per-pillar constant (6 FFMA2), apply ReLU / the padded-slot term and store the 256-byte
-//     output row with one coalesced 8-byte store per lane.  No shared-memory transpose, no divergence, no idle lanes on
-//     short pillars.
-// A CTA owns the pillars whose list STARTS inside its kFT positions; a list that runs past the look-ahead (only possible
-// for n > 32) is finished from global memory by the owning warp.  Pillars over the cap (n > P) get their "first P by point
-// index" threshold from a warp-wide radix select.
+// Mapping.  The kernel is bound by instruction issue, not by HBM, so everything is arranged to issue few instructions and
+// to never wait for memory:
+//   * persistent warps: a warp owns a CONTIGUOUS range of 32-position chunks of the record list and slides a shared-memory
+//     window over it.  Records and pillar entries are brought in by cp.async (LDGSTS, no registers) two chunks / one chunk
+//     AHEAD of the chunk being processed, so a chunk's loads are in flight during the previous chunk's arithmetic; every
+//     record is fetched once (the look-ahead half of a window is the next chunk's own half);
+//   * phase 1, one lane per list position, no loops: the per-pillar sums for the mean are accumulated with shared-memory
+//     integer atomics on fixed-point coordinates relative to the pillar centre (order independent => bit-reproducible,
+//     resolution 2^-29 of a metre at 0.2 m pillars, far below the fp32 rounding of the reference's own absolute-coordinate
+//     sum); points beyond the first-P cap are found by rank counting inside the window and become NaN (fmaxf ignores
+//     NaN, so the walk needs no branch); the lane on a list start turns the sums into the pillar's constants and flags
+//     the pillar's final point;
+//   * phase 2, ONE LANE PER CHANNEL PAIR: the warp walks its points in list order, each point is two broadcast
+//     shared-memory loads + 5 packed FFMA2 (fma.rn.f32x2: two channels per instruction) + 2 FMNMX with the running max in
+//     registers; at a pillar end the lanes add the per-pillar constant (6 FFMA2), apply ReLU / the padded-slot term and
+//     store the 256-byte output row with one coalesced 8-byte store per lane.
+// A warp owns the pillars whose list STARTS inside its chunks.  A pillar of more than 32 points cannot fit the window; it
+// is necessarily the last pillar starting in its chunk and is handled after the walk by a warp-cooperative path that reads
+// its records from global memory (radix select of the P-th smallest point index when n > P).
+#include <cmath>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "group_common.cuh"
 
 namespace pillars {
 
 namespace {
 
-constexpr int kLook = 32;  // list positions staged beyond the CTA's own chunk
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kFlagLast = 1;  // final point of its pillar
-constexpr int kFlagStop = 2;  // ... and that pillar is the last one owned by the walking warp
-constexpr int kFlagMore = 4;  // the pillar continues beyond the staged positions
+constexpr int kFlagStop = 2;  // ... and the walk of this chunk ends here
 
-struct StreamParams {
-    const PointRecord *records;   // grouped by pillar, x,y,z relative to the pillar centre (k_place)
+// per-warp shared memory (bytes)
+constexpr uint32_t kRecSlot = 32 * 32;             // one chunk of records
+constexpr uint32_t kRecRing = 4 * kRecSlot;        // slots 0..2 = chunk % 3, slot 3 mirrors slot 0 (a window never wraps)
+constexpr uint32_t kMetaSlot = 32 * 16;            // one chunk of pillar entries
+constexpr uint32_t kMetaRing = 2 * kMetaSlot;
+constexpr uint32_t kPlBytes = 32 * 32;             // pillar constants of the chunk being walked
+constexpr uint32_t kSumBytes = 3 * 32 * 4;
+constexpr uint32_t kOffMeta = kRecRing;
+constexpr uint32_t kOffPl = kOffMeta + kMetaRing;
+constexpr uint32_t kOffSum = kOffPl + kPlBytes;
+constexpr uint32_t kWarpSmem = kOffSum + kSumBytes;  // 6528
+
+struct WalkParams {
+    const PointRecord *records;   // grouped by pillar, x,y,z relative to the pillar centre (place kernel)
     const Header *hdr;
-    const float4 *pillar_meta;    // [2 * pillars] by pillar id, see Workspace
+    const uint4 *pillar_meta;     // by list start position: {cell key, row, n, -}
     const float *folded;          // [PILLARS_FOLDED_FLOATS], see launch_fold_pfn
     float *pillar_features;
-    int max_points;
+    GridDev gd;
+    int sh_cells, sh_cells_xy, sh_nx;
+    float vsz[3], off[3];
+    float fx_scale[3], fx_inv[3];  // fixed-point scale of the mean sums per axis (a power of two) and its inverse
     int idx_bits;
 };
 
@@ -81,12 +101,17 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b)
     return unpack2(rd);
 }
 
-// shared-memory accesses of the walk: 32-bit addresses, so that the loop carries one address register and no generic-pointer
-// arithmetic
+// shared-memory accesses by 32-bit address: the walk carries one address register and no generic-pointer arithmetic
 __device__ __forceinline__ float4 lds4(uint32_t addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds4u(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ float2 lds2(uint32_t addr)
@@ -95,6 +120,31 @@ __device__ __forceinline__ float2 lds2(uint32_t addr)
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds1u(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts1(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void atoms_add(uint32_t addr, int v)
+{
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// 16 bytes global -> shared without registers; src_bytes = 0 writes zeros
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct LaneWeights {
     float2 w0, w1, w2, w3, w4;        // per point: x', y', z', intensity, time
@@ -113,173 +163,140 @@ __device__ __forceinline__ void point_step(const LaneWeights &w, const float4 a,
     acc.y = fmaxf(acc.y, y.y);
 }
 
-// One warp = 32 consecutive list positions (+ a 32-position look-ahead), nothing shared between warps: no CTA barrier, a
-// warp that is done leaves.  kWarps warps per CTA only share the launch.
-template <int kWarps>
-__global__ void __launch_bounds__(32 * kWarps, 2048 / (32 * kWarps) > 32 ? 32 : 2048 / (32 * kWarps) / 2)
-k_pillar_features_stream(const __grid_constant__ StreamParams p)
+// per-pillar constant, ReLU, padded-slot term, one 256-byte row.  c4 = centre xyz + (1.0 when the pillar has empty slots),
+// m4 = mean - centre xyz + row as int bits (-1: pillar not emitted)
+__device__ __forceinline__ void pillar_finish(const LaneWeights &w, const float4 c4, const float4 m4, const float2 acc,
+                                              unsigned long long out_lane)
 {
-    constexpr int kOwn = 32;
-    constexpr int kStage = kOwn + kLook;
-    // Per warp, one 32-byte slot per staged list position for the point ("pt") and one per own position for the pillar that
-    // starts there ("pl"); the walk addresses both from one running shared-memory address.
-    //   pt[2j]   = x, y, z (relative to the pillar centre), intensity ;  x = NaN: point beyond the first-P cap
-    //   pt[2j+1] = time, flags (int bits), point index, position inside the pillar's list
-    //   pl[2j]   = centre x,y,z ; w = 1.0 when the pillar has empty (padded) slots
-    //   pl[2j+1] = mean - centre x,y,z ; w = output row as int bits (-1: pillar not emitted)
-    constexpr int kPl = 2 * (kStage + 1);       // float4 offset of the pl half
-    constexpr int kSlot = kPl + 2 * kOwn;       // float4 per warp
-    __shared__ float4 s_all[kWarps * kSlot];
-    __shared__ uint32_t s_thr_all[kWarps * kOwn];  // largest kept point index of the pillar starting there
+    float2 kc = fma2s(w.k0, c4.x, w.sh);
+    kc = fma2s(w.k1, c4.y, kc);
+    kc = fma2s(w.k2, c4.z, kc);
+    kc = fma2s(w.k3, m4.x, kc);
+    kc = fma2s(w.k4, m4.y, kc);
+    kc = fma2s(w.k5, m4.z, kc);
+    const float2 v = add2(acc, kc);
+    const float2 fl2 = mul2s(w.rsh, c4.w);  // relu(shift) when the pillar has padded slots, else 0
+    const int row = __float_as_int(m4.w);
+    if (row >= 0)
+        asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
+                     "f"(fmaxf(v.x, fl2.x)), "f"(fmaxf(v.y, fl2.y))
+                     : "memory");
+}
+
+// mean - centre with the reference's rounding of the ABSOLUTE mean to fp32 (pillar_vfe.py:97-98)
+__device__ __forceinline__ float rel_mean(float c, float s_rel_mean) { return __fsub_rn(__fadd_rn(c, s_rel_mean), c); }
+
+// A pillar of more than 32 points: straight from global memory, the whole warp on one pillar.
+__device__ __noinline__ void long_pillar(const WalkParams &p, const LaneWeights &w, uint32_t p0, uint32_t n, int row, float cx,
+                                         float cy, float cz, unsigned long long out_lane, int lane)
+{
+    const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
+    const float qnan = __int_as_float(0x7fc00000);
+    uint32_t thr = 0xFFFFFFFFu;
+    if (n > P) {  // threshold = P-th smallest point index (radix select): the first P points in index order are kept
+        uint32_t prefix = 0, kk = P;
+        for (int bit = p.idx_bits - 1; bit >= 0; --bit) {
+            const uint32_t himask = bit >= 31 ? 0u : 0xFFFFFFFFu << (bit + 1);
+            uint32_t c0 = 0;
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint32_t v = __ldg(&p.records[p0 + j].idx);
+                c0 += ((v & himask) == prefix && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) c0 += __shfl_xor_sync(kFull, c0, s);
+            if (kk > c0) {
+                prefix |= 1u << bit;
+                kk -= c0;
+            }
+        }
+        thr = prefix;
+    }
+    // mean of the kept points; double: the sum does not depend on the list order
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (uint32_t j = lane; j < n; j += 32) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + p0 + j));
+        if (__ldg(&p.records[p0 + j].idx) <= thr) {
+            sx += static_cast<double>(q.x);
+            sy += static_cast<double>(q.y);
+            sz += static_cast<double>(q.z);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        sx += __shfl_xor_sync(kFull, sx, s);
+        sy += __shfl_xor_sync(kFull, sy, s);
+        sz += __shfl_xor_sync(kFull, sz, s);
+    }
+    const float rn = __frcp_rn(static_cast<float>(min(n, P)));
+    const float4 c4 = make_float4(cx, cy, cz, n < P ? 1.f : 0.f);
+    const float4 m4 = make_float4(rel_mean(cx, static_cast<float>(sx) * rn), rel_mean(cy, static_cast<float>(sy) * rn),
+                                  rel_mean(cz, static_cast<float>(sz) * rn), __int_as_float(row));
+    float2 acc = make_float2(-INFINITY, -INFINITY);
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+        const int cnt = static_cast<int>(min(32u, n - k0));
+        float4 qa = make_float4(qnan, 0.f, 0.f, 0.f);
+        float qt = 0.f;
+        if (lane < cnt) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + k0 + lane);
+            const float4 u = __ldg(src), v = __ldg(src + 1);
+            qa = u;
+            if (__float_as_uint(v.z) > thr) qa.x = qnan;
+            qt = v.x;
+        }
+        for (int l = 0; l < cnt; ++l) {
+            const float4 v = make_float4(__shfl_sync(kFull, qa.x, l), __shfl_sync(kFull, qa.y, l),
+                                         __shfl_sync(kFull, qa.z, l), __shfl_sync(kFull, qa.w, l));
+            point_step(w, v, __shfl_sync(kFull, qt, l), acc);
+        }
+    }
+    pillar_finish(w, c4, m4, acc, out_lane);
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, 1024 / (32 * kWarps))
+k_pillar_walk(const __grid_constant__ WalkParams p)
+{
+    __shared__ __align__(16) unsigned char s_all[kWarps * kWarpSmem];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t total = p.hdr->total_listed;
-    const uint32_t q0 = (blockIdx.x * kWarps + warp) * kOwn;
-    if (q0 >= total) return;
-    float4 *const s_pt = s_all + warp * kSlot;
-    float4 *const s_pl = s_pt + kPl;
-    uint32_t *const s_thr = s_thr_all + warp * kOwn;
+    const uint32_t total = __ldcg(&p.hdr->total_listed);
+    const uint32_t n_chunks = (total + 31u) >> 5;
+    const uint32_t gw = blockIdx.x * kWarps + warp, n_warps = gridDim.x * kWarps;
+    uint32_t c = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * gw / n_warps);
+    const uint32_t c_end = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * (gw + 1) / n_warps);
+    if (c >= c_end) return;
+
+    const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * kWarpSmem;
+    const uint32_t s_meta = s_warp + kOffMeta, s_pl = s_warp + kOffPl, s_sum = s_warp + kOffSum;
     const float qnan = __int_as_float(0x7fc00000);
+    const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
 
-    // ---- phase 1a: stage 64 records ---------------------------------------------------------------------------------------
-    const uint32_t pos = q0 + lane;
-    float4 ra = make_float4(qnan, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, __uint_as_float(1u));
-    float4 ta = ra, tb = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
-    if (pos < total) {
-        const float4 *src = reinterpret_cast<const float4 *>(p.records + pos);
-        ra = __ldg(src);
-        rb = __ldg(src + 1);
-    }
-    if (pos + kOwn < total) {
-        const float4 *src = reinterpret_cast<const float4 *>(p.records + pos + kOwn);
-        ta = __ldg(src);
-        tb = __ldg(src + 1);
-    }
-    const uint32_t r_arr = __float_as_uint(rb.w);
-    const bool is_start = r_arr == 0u;  // positions beyond the list carry arrival 1
-    const unsigned bal = __ballot_sync(kFull, is_start);
-    if (bal == 0u) return;  // every position belongs to a pillar that started in an earlier chunk
-    float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
-    if (is_start) {
-        m0 = __ldg(p.pillar_meta + 2 * static_cast<size_t>(pos));
-        m1 = __ldg(p.pillar_meta + 2 * static_cast<size_t>(pos) + 1);
-    }
-    s_pt[2 * lane] = ra;
-    s_pt[2 * lane + 1] = rb;
-    s_pt[2 * (kOwn + lane)] = ta;
-    s_pt[2 * (kOwn + lane) + 1] = tb;
-    if (lane == 0) {
-        s_pt[2 * kStage] = make_float4(qnan, 0.f, 0.f, 0.f);
-        s_pt[2 * kStage + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();
+    // chunk k -> record slot k % 3 (+ the mirror slot 3 when k % 3 == 0), pillar entries -> slot k % 2
+    auto fetch_records = [&](uint32_t k, uint32_t k3) {
+        const uint32_t pos = (k << 5) + lane;
+        const bool ok = pos < total;
+        const float4 *src = reinterpret_cast<const float4 *>(p.records + (ok ? pos : 0u));
+        const int nbytes = ok ? 16 : 0;
+        const uint32_t dst = s_warp + k3 * kRecSlot + lane * 32u;
+        cp_async16(dst, src, nbytes);
+        cp_async16(dst + 16, src + 1, nbytes);
+        if (k3 == 0) {
+            cp_async16(dst + 3 * kRecSlot, src, nbytes);
+            cp_async16(dst + 3 * kRecSlot + 16, src + 1, nbytes);
+        }
+    };
+    auto fetch_meta = [&](uint32_t k) {
+        const uint32_t pos = (k << 5) + lane;
+        const bool ok = pos < total;
+        cp_async16(s_meta + (k & 1u) * kMetaSlot + lane * 16u, p.pillar_meta + (ok ? pos : 0u), ok ? 16 : 0);
+    };
 
-    // ---- phase 1b: the lane sitting on a list start publishes the pillar's constants and marks its final point -------------
-    const uint32_t P = static_cast<uint32_t>(p.max_points);
-    const uint32_t n = __float_as_uint(m1.y);
-    const bool live = is_start && __float_as_int(m1.x) >= 0;
-    const bool big = live && n > P;
-    int more = 0;  // points of the warp's last pillar beyond the staged positions
-    if (is_start) {
-        float4 m4 = make_float4(0.f, 0.f, 0.f, m1.x);
-        s_thr[lane] = 0xFFFFFFFFu;
-        if (live && !big) {
-            // mean of the pillar's points (pillar_vfe.py:97); double: the sum does not depend on the list order
-            double sx = 0.0, sy = 0.0, sz = 0.0;
-            const uint32_t n_in = min(n, static_cast<uint32_t>(kStage - lane));
-            for (uint32_t j = 0; j < n_in; ++j) {
-                const float4 q = s_pt[2 * (lane + j)];
-                sx += static_cast<double>(q.x);
-                sy += static_cast<double>(q.y);
-                sz += static_cast<double>(q.z);
-            }
-            for (uint32_t j = n_in; j < n; ++j) {  // P > 32 only
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + pos + j));
-                sx += static_cast<double>(q.x);
-                sy += static_cast<double>(q.y);
-                sz += static_cast<double>(q.z);
-            }
-            // the reference rounds the ABSOLUTE mean to fp32 before subtracting it; reproduce that rounding step
-            const float rn = __frcp_rn(static_cast<float>(n));
-            m4.x = __fsub_rn(__fadd_rn(m0.x, static_cast<float>(sx) * rn), m0.x);
-            m4.y = __fsub_rn(__fadd_rn(m0.y, static_cast<float>(sy) * rn), m0.y);
-            m4.z = __fsub_rn(__fadd_rn(m0.z, static_cast<float>(sz) * rn), m0.z);
-        }
-        s_pl[2 * lane] = m0;
-        s_pl[2 * lane + 1] = m4;
-        // walk control: flag the pillar's final point (dropped pillars are walked too, their row is -1)
-        const uint32_t endp = static_cast<uint32_t>(lane) + n - 1u;
-        const bool last_of_warp = (31 - __clz(bal)) == lane;
-        if (endp < static_cast<uint32_t>(kStage)) {
-            s_pt[2 * endp + 1].y = __int_as_float(last_of_warp ? kFlagStop : kFlagLast);
-        } else {  // only the warp's last pillar can run past the look-ahead
-            s_pt[2 * (kStage - 1) + 1].y = __int_as_float(kFlagStop | kFlagMore);
-            more = static_cast<int>(endp + 1u - kStage);
-        }
-    }
-    more = __shfl_sync(kFull, more, 31 - __clz(bal));
-    __syncwarp();
+    uint32_t c3 = c % 3u;  // slot of chunk c
+    fetch_records(c, c3);
+    fetch_records(c + 1, c3 == 2 ? 0u : c3 + 1);
+    fetch_meta(c);
+    cp_async_commit();
 
-    // ---- pillars over the cap: threshold = P-th smallest point index (radix select), mean over the kept ones ---------
-    unsigned bigmask = __ballot_sync(kFull, big);
-    if (bigmask) {
-        while (bigmask) {
-            const int bp = __ffs(bigmask) - 1;
-            bigmask &= bigmask - 1;
-            const uint32_t p0 = q0 + bp, nb = __shfl_sync(kFull, n, bp);
-            uint32_t prefix = 0, kk = P;
-            for (int bit = p.idx_bits - 1; bit >= 0; --bit) {
-                const uint32_t himask = 0xFFFFFFFFu << (bit + 1);
-                uint32_t c0 = 0;
-                for (uint32_t j = lane; j < nb; j += 32) {
-                    const uint32_t v = __ldg(&p.records[p0 + j].idx);
-                    c0 += ((v & himask) == prefix && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
-                }
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) c0 += __shfl_xor_sync(kFull, c0, s);
-                if (kk > c0) {
-                    prefix |= 1u << bit;
-                    kk -= c0;
-                }
-            }
-            double sx = 0.0, sy = 0.0, sz = 0.0;
-            for (uint32_t j = lane; j < nb; j += 32) {
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + p0 + j));
-                if (__ldg(&p.records[p0 + j].idx) <= prefix) {
-                    sx += static_cast<double>(q.x);
-                    sy += static_cast<double>(q.y);
-                    sz += static_cast<double>(q.z);
-                }
-            }
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                sx += __shfl_xor_sync(kFull, sx, s);
-                sy += __shfl_xor_sync(kFull, sy, s);
-                sz += __shfl_xor_sync(kFull, sz, s);
-            }
-            if (lane == 0) {
-                const float rn = __frcp_rn(static_cast<float>(P));
-                const float4 c4 = s_pl[2 * bp];
-                s_thr[bp] = prefix;
-                s_pl[2 * bp + 1].x = __fsub_rn(__fadd_rn(c4.x, static_cast<float>(sx) * rn), c4.x);
-                s_pl[2 * bp + 1].y = __fsub_rn(__fadd_rn(c4.y, static_cast<float>(sy) * rn), c4.y);
-                s_pl[2 * bp + 1].z = __fsub_rn(__fadd_rn(c4.z, static_cast<float>(sz) * rn), c4.z);
-            }
-        }
-        __syncwarp();
-        // points beyond the cap become NaN: fmaxf ignores them, so the walk needs no branch
-        if (r_arr <= static_cast<uint32_t>(lane) && __float_as_uint(rb.z) > s_thr[lane - static_cast<int>(r_arr)])
-            s_pt[2 * lane].x = qnan;
-        {
-            const uint32_t t_arr = __float_as_uint(tb.w);
-            const int j = kOwn + lane;
-            const int ps = j - static_cast<int>(t_arr);
-            if (t_arr <= static_cast<uint32_t>(j) && ps < kOwn && __float_as_uint(tb.z) > s_thr[ps]) s_pt[2 * j].x = qnan;
-        }
-        __syncwarp();
-    }
-
-    // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair -------------------------
     LaneWeights w;
     {
         const float2 *fw = reinterpret_cast<const float2 *>(p.folded) + lane;
@@ -292,83 +309,137 @@ k_pillar_features_stream(const __grid_constant__ StreamParams p)
     // the lane's output base as a global-space address kept in registers (not recomputed per pillar)
     unsigned long long out_lane = static_cast<unsigned long long>(__cvta_generic_to_global(p.pillar_features + 2 * lane));
     asm volatile("" : "+l"(out_lane));
-    constexpr uint32_t kPlBytes = kPl * sizeof(float4);
-    const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pt));
-    uint32_t sp = s_base + 32u * (__ffs(bal) - 1);  // the point being accumulated
-    uint32_t ss = sp;  // first point of the pillar being accumulated; its constants sit kPlBytes further on
-    float2 acc = make_float2(-INFINITY, -INFINITY);
+    cp_async_wait_all();
+    __syncwarp();
 
-    // pillar end: per-pillar constant, ReLU, padded-slot term, one 256-byte row
-    auto pillar_end = [&]() {
-        const float4 c4 = lds4(ss + kPlBytes), m4 = lds4(ss + kPlBytes + 16);
-        const int row = __float_as_int(m4.w);
-        float2 kc = fma2s(w.k0, c4.x, w.sh);
-        kc = fma2s(w.k1, c4.y, kc);
-        kc = fma2s(w.k2, c4.z, kc);
-        float2 kd = mul2s(w.k3, m4.x);
-        kd = fma2s(w.k4, m4.y, kd);
-        kd = fma2s(w.k5, m4.z, kd);
-        const float2 v = add2(add2(acc, kc), kd);
-        const float2 fl2 = mul2s(w.rsh, c4.w);  // relu(shift) when the pillar has padded slots, else 0
-        if (row >= 0)
-            asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
-                         "f"(fmaxf(v.x, fl2.x)), "f"(fmaxf(v.y, fl2.y))
-                         : "memory");
-        acc = make_float2(-INFINITY, -INFINITY);
-    };
+    for (; c < c_end; ++c) {
+        // loads for the chunks ahead fly during this chunk's arithmetic
+        {
+            const uint32_t k3 = c3 == 0 ? 2u : c3 - 1;  // (c + 2) % 3
+            fetch_records(c + 2, k3);
+            fetch_meta(c + 1);
+            cp_async_commit();
+        }
+        const uint32_t rs = s_warp + c3 * kRecSlot;  // window: 64 consecutive positions starting at chunk c
+        const uint32_t pos = (c << 5) + lane;
 
-    // two points per trip, registers ping-ponged so that the next point is always in flight and nothing is copied
-    float4 a0 = lds4(sp);
-    float2 b0 = lds2(sp + 16);
-    int fl;
-    while (true) {
-        const float4 a1 = lds4(sp + 32);
-        const float2 b1 = lds2(sp + 48);
-        point_step(w, a0, b0.x, acc);
-        fl = __float_as_int(b0.y);
-        if (fl != 0) {
-            if (fl & kFlagStop) break;
-            pillar_end();
-            ss = sp + 32;
-        }
-        a0 = lds4(sp + 64);
-        b0 = lds2(sp + 80);
-        point_step(w, a1, b1.x, acc);
-        fl = __float_as_int(b1.y);
-        if (fl != 0) {
-            if (fl & kFlagStop) break;
-            pillar_end();
-            ss = sp + 64;
-        }
-        sp += 64;
-    }
-    if (fl & kFlagMore) {
-        // rest of a long list, straight from global memory: 32 records per sweep, broadcast by shuffles
-        const uint32_t base = q0 + kStage;
-        const uint32_t thr = s_thr[(ss - s_base) >> 5];
-        for (int k0 = 0; k0 < more; k0 += 32) {
-            const int cnt = min(32, more - k0);
-            float4 qa = make_float4(qnan, 0.f, 0.f, 0.f);
-            float qt = 0.f;
-            if (lane < cnt) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.records + base + k0 + lane);
-                const float4 u = __ldg(src), v = __ldg(src + 1);
-                qa = u;
-                if (__float_as_uint(v.z) > thr) qa.x = qnan;
-                qt = v.x;
+        // ---- phase 1 -----------------------------------------------------------------------------------------------------
+        const uint4 rb = lds4u(rs + lane * 32u + 16);          // {time, flags, idx, arrival} of my own position
+        const uint4 tb = lds4u(rs + (32u + lane) * 32u + 16);  // ... and of my look-ahead position
+        const bool own_ok = pos < total, la_ok = pos + 32u < total;
+        const bool is_start = own_ok && rb.w == 0u;
+        const unsigned bal = __ballot_sync(kFull, is_start);
+        if (bal != 0u) {
+            const uint4 me = lds4u(s_meta + (c & 1u) * kMetaSlot + lane * 16u);  // {key, row, n, -}: valid on start lanes
+            sts1(s_sum + lane * 4u, 0u);
+            sts1(s_sum + 128u + lane * 4u, 0u);
+            sts1(s_sum + 256u + lane * 4u, 0u);
+            __syncwarp();
+            // every position adds itself to the sums of its pillar (when that pillar starts in this chunk and fits the
+            // window); positions beyond the first-P cap are found by rank counting and become NaN
+            auto contribute = [&](uint32_t j, uint32_t arrival, uint32_t idx) {
+                if (arrival > j) return;  // the pillar started in an earlier chunk
+                const uint32_t slot = j - arrival;
+                if (slot >= 32u) return;  // starts in the next chunk
+                const uint32_t np = lds1u(s_meta + (c & 1u) * kMetaSlot + slot * 16u + 8u);
+                if (np > 32u) return;     // long pillar: handled after the walk
+                bool keep = true;
+                if (np > P) {
+                    uint32_t rank = 0;
+                    for (uint32_t k = 0; k < np; ++k) rank += lds1u(rs + (slot + k) * 32u + 24u) < idx ? 1u : 0u;
+                    keep = rank < P;
+                }
+                if (keep) {
+                    const float4 q = lds4(rs + j * 32u);
+                    atoms_add(s_sum + slot * 4u, __float2int_rn(q.x * p.fx_scale[0]));
+                    atoms_add(s_sum + 128u + slot * 4u, __float2int_rn(q.y * p.fx_scale[1]));
+                    atoms_add(s_sum + 256u + slot * 4u, __float2int_rn(q.z * p.fx_scale[2]));
+                } else {
+                    sts1(rs + j * 32u, __float_as_uint(qnan));
+                }
+            };
+            if (own_ok) contribute(lane, rb.w, rb.z);
+            if (la_ok) contribute(32u + lane, tb.w, tb.z);
+            __syncwarp();
+
+            const uint32_t n = me.z;
+            const bool is_long = is_start && n > 32u;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            if (is_start) {
+                const CellCoord cc = decode_key(p, me.x);
+                cx = __fadd_rn(__fmul_rn(static_cast<float>(cc.x), p.vsz[0]), p.off[0]);
+                cy = __fadd_rn(__fmul_rn(static_cast<float>(cc.y), p.vsz[1]), p.off[1]);
+                cz = __fadd_rn(__fmul_rn(static_cast<float>(cc.z), p.vsz[2]), p.off[2]);
+                if (!is_long) {
+                    const float rn = __frcp_rn(static_cast<float>(min(n, P)));
+                    const float mx = static_cast<float>(static_cast<int>(lds1u(s_sum + lane * 4u))) * p.fx_inv[0] * rn;
+                    const float my = static_cast<float>(static_cast<int>(lds1u(s_sum + 128u + lane * 4u))) * p.fx_inv[1] * rn;
+                    const float mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
+                    sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, n < P ? 1.f : 0.f));
+                    sts4(s_pl + lane * 32u + 16, make_float4(rel_mean(cx, mx), rel_mean(cy, my), rel_mean(cz, mz),
+                                                             __uint_as_float(me.y)));
+                    sts1(rs + (lane + n - 1u) * 32u + 20u, kFlagLast);  // walk control: the pillar's final point
+                }
             }
-            for (int l = 0; l < cnt; ++l) {
-                const float4 v = make_float4(__shfl_sync(kFull, qa.x, l), __shfl_sync(kFull, qa.y, l),
-                                             __shfl_sync(kFull, qa.z, l), __shfl_sync(kFull, qa.w, l));
-                point_step(w, v, __shfl_sync(kFull, qt, l), acc);
+            __syncwarp();
+            // the walk stops at the end of the last pillar that fits the window; a long pillar can only be the last start
+            const int first_start = __ffs(bal) - 1, last_start = 31 - __clz(bal);
+            const bool long_last = __shfl_sync(kFull, is_long ? 1 : 0, last_start) != 0;
+            if (lane == last_start) {
+                if (!long_last) sts1(rs + (lane + n - 1u) * 32u + 20u, kFlagLast | kFlagStop);
+                else if (last_start > first_start) sts1(rs + (lane - 1u) * 32u + 20u, kFlagLast | kFlagStop);
+            }
+            __syncwarp();
+
+            // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair -------------------
+            if (!(long_last && last_start == first_start)) {
+                const uint32_t pl_delta = s_pl - rs;
+                uint32_t sp = rs + 32u * first_start;  // the point being accumulated
+                uint32_t ss = sp;                      // first point of the pillar being accumulated
+                float2 acc = make_float2(-INFINITY, -INFINITY);
+                // two points per trip, registers ping-ponged so that the next point is always in flight
+                float4 a0 = lds4(sp);
+                float2 b0 = lds2(sp + 16);
+                int fl;
+                while (true) {
+                    const float4 a1 = lds4(sp + 32);
+                    const float2 b1 = lds2(sp + 48);
+                    point_step(w, a0, b0.x, acc);
+                    fl = __float_as_int(b0.y);
+                    if (fl != 0) {
+                        if (fl & kFlagStop) break;
+                        pillar_finish(w, lds4(ss + pl_delta), lds4(ss + pl_delta + 16), acc, out_lane);
+                        acc = make_float2(-INFINITY, -INFINITY);
+                        ss = sp + 32;
+                    }
+                    a0 = lds4(sp + 64);
+                    b0 = lds2(sp + 80);
+                    point_step(w, a1, b1.x, acc);
+                    fl = __float_as_int(b1.y);
+                    if (fl != 0) {
+                        if (fl & kFlagStop) break;
+                        pillar_finish(w, lds4(ss + pl_delta), lds4(ss + pl_delta + 16), acc, out_lane);
+                        acc = make_float2(-INFINITY, -INFINITY);
+                        ss = sp + 64;
+                    }
+                    sp += 64;
+                }
+                pillar_finish(w, lds4(ss + pl_delta), lds4(ss + pl_delta + 16), acc, out_lane);
+            }
+            if (long_last) {
+                const uint32_t ln = __shfl_sync(kFull, n, last_start);
+                const int lrow = static_cast<int>(__shfl_sync(kFull, me.y, last_start));
+                long_pillar(p, w, (c << 5) + last_start, ln, lrow, __shfl_sync(kFull, cx, last_start),
+                            __shfl_sync(kFull, cy, last_start), __shfl_sync(kFull, cz, last_start), out_lane, lane);
             }
         }
+        cp_async_wait_all();
+        __syncwarp();
+        c3 = c3 == 2 ? 0u : c3 + 1;
     }
-    pillar_end();
 }
 
-// ---- folding of the layer's weights (device side, once per call inside k_place's idle lanes would also do; kept as its
-//      own tiny kernel so that callers can prepare the table once per model) ------------------------------------------
+// ---- folding of the layer's weights (once per model: pillars_fold_pfn) ------------------------------------------------
 __global__ void k_fold_pfn(const float *__restrict__ weight, const float *__restrict__ scale,
                            const float *__restrict__ shift, int c_point, int c_in, float *__restrict__ folded)
 {
@@ -389,6 +460,12 @@ __global__ void k_fold_pfn(const float *__restrict__ weight, const float *__rest
     folded[12 * 64 + o] = fmaxf(sh, 0.f);
 }
 
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 }  // namespace
 
 cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st)
@@ -402,25 +479,41 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
                                           cudaStream_t st)
 {
     if (job.n == 0) return cudaSuccess;
-    StreamParams p{};
+    WalkParams p{};
     p.records = ws.records;
     p.hdr = ws.hdr;
     p.pillar_meta = ws.pillar_meta;
     p.folded = folded;
     p.pillar_features = job.pillar_features;
-    p.max_points = gd.max_points;
+    p.gd = gd;
+    p.sh_cells = log2_exact(gd.cells);
+    p.sh_cells_xy = log2_exact(gd.cells_xy);
+    p.sh_nx = log2_exact(static_cast<uint32_t>(gd.g[0]));
     p.idx_bits = job.idx_bits;
-    static int ft = 0;
-    if (!ft) {
-        const char *e = getenv("PILLARS_FEAT_THREADS");
-        ft = e ? atoi(e) : 128;
-        if (ft != 64 && ft != 128 && ft != 256) ft = 128;
+    const int window = gd.max_points < 32 ? gd.max_points : 32;  // points that can enter one sum
+    for (int k = 0; k < 3; ++k) {
+        p.vsz[k] = job.vsz[k];
+        p.off[k] = job.off[k];
+        // |x'| <= voxel / 2 (+ rounding); the sum of `window` fixed-point values must stay below 2^31
+        const double extent = 0.5 * static_cast<double>(gd.vsz[k]) * 1.01 + 1e-6;
+        int s = static_cast<int>(std::floor(std::log2(2147483647.0 / (window * extent))));
+        s = s < -60 ? -60 : (s > 60 ? 60 : s);
+        p.fx_scale[k] = static_cast<float>(std::ldexp(1.0, s));
+        p.fx_inv[k] = static_cast<float>(std::ldexp(1.0, -s));
     }
+    // Persistent warps: about `cpw` chunks of 32 list positions per warp, at most one full wave of warps.
+    const int sms = current_sm_count();
+    static const int cpw = [] {
+        const int v = env_int("PILLARS_WALK_CPW", 3);
+        return v < 1 ? 1 : v;
+    }();
+    constexpr int kWarps = 4;
     const int64_t chunks = (job.n + 31) / 32;  // upper bound: listed points <= n
-    const unsigned grid = static_cast<unsigned>((chunks * 32 + ft - 1) / ft);
-    if (ft == 256) k_pillar_features_stream<8><<<grid, 256, 0, st>>>(p);
-    else if (ft == 128) k_pillar_features_stream<4><<<grid, 128, 0, st>>>(p);
-    else k_pillar_features_stream<2><<<grid, 64, 0, st>>>(p);
+    int64_t warps = (chunks + cpw - 1) / cpw;
+    const int64_t wave = static_cast<int64_t>(sms) * 32;
+    if (warps > wave) warps = wave;
+    const unsigned grid = static_cast<unsigned>((warps + kWarps - 1) / kWarps);
+    k_pillar_walk<kWarps><<<grid, 32 * kWarps, 0, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }

@@ -17,7 +17,7 @@
 //
 // The per-pillar "first P points in index order" rule is applied by the consumers (pfn.cu) with a radix select over
 // the list, so nothing here depends on the order in which atomics land.
-#include "common.cuh"
+#include "group_common.cuh"
 
 namespace pillars {
 
@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kPerThread = kTile / kThreads;  // 4 (scan kernel); must stay a multiple of 4 (int4 slot loads)
-constexpr int kGroup = 256;                   // tiles per look-back group
+constexpr int kGroup = kLookGroup;            // tiles per look-back group
 
 __device__ __forceinline__ uint32_t hash_key(uint32_t k)
 {
@@ -34,24 +34,6 @@ __device__ __forceinline__ uint32_t hash_key(uint32_t k)
     k *= 0x85EBCA77u;
     k ^= k >> 13;
     return k;
-}
-
-__device__ __forceinline__ unsigned lanemask_lt()
-{
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
-}
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,26 +74,11 @@ k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int c
     const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kThreads;
     const int count = static_cast<int>(tmin<int64_t>(kThreads, n - tile_start));
 
-    // one contiguous, fully coalesced read of the tile (rows are 12..64 B, so per-row vector loads would not be)
-    const float *src = points + tile_start * stride;
-    const int nfl = count * stride;
-    if (vec_ok) {
-        const float4 *src4 = reinterpret_cast<const float4 *>(src);
-        float4 *dst4 = reinterpret_cast<float4 *>(s_pts);
-        const int n4 = nfl >> 2;
-        for (int i = tid; i < n4; i += kThreads) dst4[i] = __ldg(src4 + i);
-        for (int i = (n4 << 2) + tid; i < nfl; i += kThreads) s_pts[i] = __ldg(src + i);
-    } else {
-        for (int i = tid; i < nfl; i += kThreads) s_pts[i] = __ldg(src + i);
-    }
+    load_point_tile(points + tile_start * stride, count, stride, vec_ok, s_pts, tid, kThreads);
     // frames touched by this tile: [b0, b1]; two binary searches per CTA instead of one per point
     if (tid < 2) {
         const int64_t i = tid == 0 ? tile_start : tile_start + count - 1;
-        int lo = 0, hi = nb;  // invariant: offsets[lo] <= i < offsets[hi]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(frame_offsets + mid) <= i) lo = mid; else hi = mid;
-        }
+        const int lo = find_frame(frame_offsets, nb, i);
         if (tid == 0) s_b0 = lo; else s_b1 = lo;
     }
     __syncthreads();
@@ -120,19 +87,13 @@ k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int c
     bool valid = false;
     uint32_t key = 0;
     if (tid < count) {
-        const float *p = s_pts + tid * stride + col0;
-        // IEEE fp32, true division, no contraction: bit-identical to the CPU voxeliser
-        const float fx = floorf(__fdiv_rn(__fsub_rn(p[0], gd.rmin[0]), gd.vsz[0]));
-        const float fy = floorf(__fdiv_rn(__fsub_rn(p[1], gd.rmin[1]), gd.vsz[1]));
-        const float fz = gd.ignore_z ? 0.f : floorf(__fdiv_rn(__fsub_rn(p[2], gd.rmin[2]), gd.vsz[2]));
-        valid = (fx >= 0.f) && (fx < static_cast<float>(gd.g[0])) && (fy >= 0.f) && (fy < static_cast<float>(gd.g[1])) &&
-                (fz >= 0.f) && (fz < static_cast<float>(gd.g[2]));
+        uint32_t cell = 0;
+        valid = quantize_point(s_pts + tid * stride + col0, gd, cell);
         if (valid) {
             int b = s_b0;  // almost always the only frame of the tile
             const int b1 = s_b1;
             while (b < b1 && __ldg(frame_offsets + b + 1) <= i) ++b;
-            const uint32_t cx = static_cast<uint32_t>(fx), cy = static_cast<uint32_t>(fy), cz = static_cast<uint32_t>(fz);
-            key = static_cast<uint32_t>(b) * gd.cells + (cz * gd.g[1] + cy) * gd.g[0] + cx;
+            key = static_cast<uint32_t>(b) * gd.cells + cell;
         }
     }
     const unsigned active = __ballot_sync(0xffffffffu, valid);
@@ -351,26 +312,6 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
 // opened the pillar writes the pillar's constants (centre, row, count) plus voxel_coords / voxel_num_points / the BEV index
 // map.  This kernel waits on L2 round trips, so the extra integer work is free; in the feature kernel it was not.
 // ---------------------------------------------------------------------------------------------
-struct PlaceParams {
-    const float *points;
-    int64_t n;
-    int stride, col0, c_point;
-    const int32_t *point_slot;
-    const uint32_t *point_arrival;
-    const HashEntry *table;
-    uint32_t *sorted_idx;    // or NULL
-    PointRecord *records;    // or NULL
-    float4 *pillar_meta;
-    const uint32_t *pillar_cnt, *frame_gstart, *frame_rowbase;
-    GridDev gd;
-    int sh_cells, sh_cells_xy, sh_nx;  // log2 of the divisor when it is a power of two, else -1
-    float vsz[3], off[3];
-    int32_t *voxel_coords, *voxel_num_points, *cell_row;
-    int64_t capacity;
-};
-
-__device__ __forceinline__ uint32_t div_by(uint32_t v, uint32_t d, int sh) { return sh >= 0 ? v >> sh : v / d; }
-
 __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ PlaceParams p)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
@@ -384,61 +325,27 @@ __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ Plac
     if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i);
     if (!p.records) return;
 
-    const uint32_t key = e.y;
-    const uint32_t b = div_by(key, p.gd.cells, p.sh_cells);
-    const uint32_t cell = key - b * p.gd.cells;
-    const uint32_t z = div_by(cell, p.gd.cells_xy, p.sh_cells_xy);
-    const uint32_t rem = cell - z * p.gd.cells_xy;
-    const uint32_t y = div_by(rem, static_cast<uint32_t>(p.gd.g[0]), p.sh_nx);
-    const uint32_t x = rem - y * static_cast<uint32_t>(p.gd.g[0]);
-    // pillar centre: coord * voxel + offset, two roundings as in the reference (pillar_vfe.py:101-103)
-    const float cx = __fadd_rn(__fmul_rn(static_cast<float>(x), p.vsz[0]), p.off[0]);
-    const float cy = __fadd_rn(__fmul_rn(static_cast<float>(y), p.vsz[1]), p.off[1]);
-    const float cz = __fadd_rn(__fmul_rn(static_cast<float>(z), p.vsz[2]), p.off[2]);
-
-    // one full 32-byte sector per point: the feature kernel then streams its input instead of gathering
-    const float *q = p.points + i * p.stride + p.col0;
-    float4 a, c;
-    a.x = __fsub_rn(__ldg(q), cx);  // f_center (pillar_vfe.py:100-103)
-    a.y = __fsub_rn(__ldg(q + 1), cy);
-    a.z = __fsub_rn(__ldg(q + 2), cz);
-    a.w = p.c_point > 3 ? __ldg(q + 3) : 0.f;
-    c.x = p.c_point > 4 ? __ldg(q + 4) : 0.f;
-    c.y = 0.f;  // walk-control flags, set by the feature kernel in its staged copy
-    c.z = __uint_as_float(static_cast<uint32_t>(i));
-    c.w = __uint_as_float(arrival);
-    float4 *dst = reinterpret_cast<float4 *>(p.records + pos);
-    dst[0] = a;
-    dst[1] = c;
+    const CellCoord c = decode_key(p, e.y);
+    write_record(p, i, c, pos, arrival);
 
     if (e.x == static_cast<uint32_t>(i)) {  // this point opened the pillar
         const uint32_t n = p.pillar_cnt[g];
-        const uint32_t local = g - p.frame_gstart[b];
-        const int64_t row = static_cast<int64_t>(p.frame_rowbase[b]) + local;
+        const uint32_t local = g - p.frame_gstart[c.b];
+        const int64_t row = static_cast<int64_t>(p.frame_rowbase[c.b]) + local;
         const bool live = local < static_cast<uint32_t>(p.gd.max_voxels) && row < p.capacity;
         const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
         // indexed by the list START POSITION, so the consumer needs nothing but its own position to find it
-        p.pillar_meta[2 * static_cast<size_t>(e.z)] = make_float4(cx, cy, cz, n < P ? 1.f : 0.f);
-        p.pillar_meta[2 * static_cast<size_t>(e.z) + 1] =
-            make_float4(__int_as_float(live ? static_cast<int32_t>(row) : -1), __uint_as_float(n), 0.f, 0.f);
+        p.pillar_meta[e.z] = make_uint4(e.y, live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, 0u);
         if (live) {
             if (p.voxel_coords)
                 *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) =
-                    make_int4(static_cast<int>(b), static_cast<int>(z), static_cast<int>(y), static_cast<int>(x));
+                    make_int4(static_cast<int>(c.b), static_cast<int>(c.z), static_cast<int>(c.y), static_cast<int>(c.x));
             if (p.voxel_num_points) p.voxel_num_points[row] = static_cast<int32_t>(min(n, P));
             if (p.cell_row)
-                p.cell_row[static_cast<int64_t>(b) * p.gd.cells_xy + static_cast<int64_t>(y) * p.gd.g[0] + x] =
+                p.cell_row[static_cast<int64_t>(c.b) * p.gd.cells_xy + static_cast<int64_t>(c.y) * p.gd.g[0] + c.x] =
                     static_cast<int32_t>(row);
         }
     }
-}
-
-int log2_exact(uint32_t v)
-{
-    if (v == 0 || (v & (v - 1)) != 0) return -1;
-    int s = 0;
-    while ((1u << s) != v) ++s;
-    return s;
 }
 
 }  // namespace
@@ -456,6 +363,9 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
                                 const int32_t *frame_offsets, int nb, const GridDev &gd, const Workspace &ws,
                                 int32_t *pillar_count, bool want_index_lists, const PlaceExtras &extras, cudaStream_t st)
 {
+    if (ws.mode == kGroupDense)
+        return launch_group_points_dense(points, n, stride, col0, c_point, frame_offsets, nb, gd, ws, pillar_count,
+                                         want_index_lists, extras, st);
     cudaError_t err;
     // One memset per call: the hash table must be empty before the first insert.  The rest of the scratch (scan header and
     // tile descriptors: zero; BEV index map: -1) is initialised by the insert kernel itself, unless there is no point at all.
@@ -494,33 +404,7 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
                                                    ws.frame_rowbase, pillar_count);
     note_launch(2);
     if (want_index_lists || extras.records) {
-        PlaceParams pp{};
-        pp.points = points;
-        pp.n = n;
-        pp.stride = stride;
-        pp.col0 = col0;
-        pp.c_point = c_point;
-        pp.point_slot = ws.point_slot;
-        pp.point_arrival = ws.point_arrival;
-        pp.table = ws.table;
-        pp.sorted_idx = want_index_lists ? ws.sorted_idx : nullptr;
-        pp.records = extras.records ? ws.records : nullptr;
-        pp.pillar_meta = ws.pillar_meta;
-        pp.pillar_cnt = ws.pillar_cnt;
-        pp.frame_gstart = ws.frame_gstart;
-        pp.frame_rowbase = ws.frame_rowbase;
-        pp.gd = gd;
-        pp.sh_cells = log2_exact(gd.cells);
-        pp.sh_cells_xy = log2_exact(gd.cells_xy);
-        pp.sh_nx = log2_exact(static_cast<uint32_t>(gd.g[0]));
-        for (int k = 0; k < 3; ++k) {
-            pp.vsz[k] = extras.vsz[k];
-            pp.off[k] = extras.off[k];
-        }
-        pp.voxel_coords = extras.records ? extras.voxel_coords : nullptr;
-        pp.voxel_num_points = extras.records ? extras.voxel_num_points : nullptr;
-        pp.cell_row = extras.records && extras.write_cell_row ? ws.cell_row : nullptr;
-        pp.capacity = extras.capacity;
+        const PlaceParams pp = make_place_params(points, n, stride, col0, c_point, gd, ws, want_index_lists, extras);
         k_place<<<pb, kThreads, 0, st>>>(pp);
         note_launch();
     }

@@ -472,6 +472,15 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
     return res
 
 
+GROUPING_MODES = {"auto": 0, "hash": 1, "dense": 2}
+
+
+def set_grouping(mode: str) -> None:
+    """Grouping implementation (thread-local): 'auto', 'hash' (open-addressing table) or 'dense' (direct-mapped cell
+    table whenever n_frames * cells < 2^31).  Outputs are bit-identical."""
+    check(_native.load().pillars_set_grouping(GROUPING_MODES[mode]), "pillars_set_grouping")
+
+
 def force_generic_features(on: bool) -> None:
     """Test / measurement hook: run the generic feature kernel even when the fast one is eligible."""
     _native.load().pillars_force_generic_features(int(bool(on)))

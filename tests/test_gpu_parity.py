@@ -83,8 +83,16 @@ def _make_case(name):
     return np.concatenate(frames, 0), offs, rng, vs, p, mv
 
 
+@pytest.fixture(params=["hash", "dense"])
+def grouping(request, L):
+    """Both grouping implementations: the open-addressing hash table and the direct-mapped cell table."""
+    L.ops.set_grouping(request.param)
+    yield request.param
+    L.ops.set_grouping("auto")
+
+
 @pytest.mark.parametrize("name", list(GROUP_CASES))
-def test_grouping_bit_exact(name, dev, L, oracle):
+def test_grouping_bit_exact(name, grouping, dev, L, oracle):
     pts, offs, rng, vs, p, mv = _make_case(name)
     grid = L.GridSpec.from_range(rng, vs, p, mv)
     ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
@@ -100,7 +108,7 @@ def test_grouping_bit_exact(name, dev, L, oracle):
     np.testing.assert_array_equal(got["voxels"].view(np.uint32), ref["voxels"].view(np.uint32))
 
 
-def test_grouping_pcdet_layout_and_frame_offsets(dev, L, oracle):
+def test_grouping_pcdet_layout_and_frame_offsets(grouping, dev, L, oracle):
     """The collated [N, 1+C] layout with the frame index in column 0, including an empty middle frame."""
     pts, offs, rng, vs, p, mv = _make_case("small_p32")
     offs3 = np.array([offs[0], offs[1], offs[1], offs[2]], np.int32)  # frame 1 is empty
@@ -120,7 +128,7 @@ def test_grouping_pcdet_layout_and_frame_offsets(dev, L, oracle):
     np.testing.assert_array_equal(res["pillar_count"][:-1], ref["pillars_per_frame"])
 
 
-def test_grouping_edge_cases(dev, L, oracle):
+def test_grouping_edge_cases(grouping, dev, L, oracle):
     rng, vs = (0.0, 0.0, 0.0, 4.0, 4.0, 2.0), (1.0, 1.0, 2.0)
     grid = L.GridSpec.from_range(rng, vs, 4, 10)
     # boundaries, non-finite values, duplicates
@@ -147,7 +155,7 @@ def test_grouping_edge_cases(dev, L, oracle):
         np.testing.assert_array_equal(got["point_slot"], ref["point_slot"])
 
 
-def test_grouping_one_huge_pillar_and_many_frames(dev, L, oracle):
+def test_grouping_one_huge_pillar_and_many_frames(grouping, dev, L, oracle):
     """20 000 points in one cell (cap 32 -> radix select over a long list) and 40 tiny frames (> one warp of frames)."""
     rng, vs = (0.0, 0.0, 0.0, 8.0, 8.0, 2.0), (1.0, 1.0, 2.0)
     r = np.random.default_rng(5)
@@ -276,7 +284,7 @@ def feature_kernel(request, L):
 
 @pytest.mark.parametrize("name", ["cfg1_full_sweep", "cfg1_p20", "tenSweep_maxvox30000_binds", "waymo_0.1m",
                                   "cap_binds_p4", "maxvox_binds", "p1_maxvox1"])
-def test_fused_path_vs_oracle(name, feature_kernel, dev, L, oracle):
+def test_fused_path_vs_oracle(name, feature_kernel, grouping, dev, L, oracle):
     pts, offs, rng, vs, p, mv = _make_case(name)
     c = pts.shape[1]
     grid = L.GridSpec.from_range(rng, vs, p, mv)
@@ -301,7 +309,7 @@ def test_fused_path_vs_oracle(name, feature_kernel, dev, L, oracle):
     np.testing.assert_allclose(bev, ref_bev, rtol=FEAT_RTOL, atol=FEAT_ATOL)
 
 
-def test_fused_huge_pillar_spanning_chunks(feature_kernel, dev, L, oracle):
+def test_fused_huge_pillar_spanning_chunks(feature_kernel, grouping, dev, L, oracle):
     """One cell holding 20 000 points (its list spans ~80 chunks of the fast kernel) next to ordinary pillars."""
     rng, vs = (0.0, 0.0, 0.0, 8.0, 8.0, 2.0), (1.0, 1.0, 2.0)
     r = np.random.default_rng(11)
