@@ -239,7 +239,8 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
     // Feature kernel choice.  The streaming kernel covers the mainstream configuration; everything else runs the generic
     // 16-lanes-per-pillar kernel.
     const bool membership = out->voxels || out->point_pillar || out->point_slot;
-    const bool fast = pfn && stream_kernel_covers(*pfn) && !g_force_generic;
+    // (the streaming kernel's per-pillar record packs x and y into 16 bits each)
+    const bool fast = pfn && stream_kernel_covers(*pfn) && !g_force_generic && grid->grid[0] <= 0xFFFF && grid->grid[1] <= 0xFFFF;
     PlaceExtras px{};
     px.records = fast;
     if (fast) {

@@ -79,7 +79,7 @@ struct Workspace {
     uint32_t *pillar_cnt;           // [n] points that fell into pillar g (uncapped)
     uint32_t *sorted_idx;           // [n] point indices grouped by pillar
     PointRecord *records;           // [n] point records grouped by pillar
-    uint4 *pillar_meta;             // [n] per pillar, at its list start position: {cell key, row (-1: dropped), n, -}
+    uint4 *pillar_meta;             // [n] per pillar, at its list start position: {x | y << 16, row (-1: dropped), n, z}
     float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
     uint32_t *scan_scratch;         // [B * ny * nx / 2048 + 2] block sums of the cell-rank scan (dynamic variant)
     uint32_t cap;                   // hash slots

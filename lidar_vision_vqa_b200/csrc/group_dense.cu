@@ -14,7 +14,7 @@
 //   k_scan_dense     single-pass chained scan over points in index order of [point is the first of its cell] and of the
 //                    cell counts => pillar id in first-appearance order + start of its point list (no sort).  The thread
 //                    that owns a pillar's first point writes everything per-pillar that needs no feature arithmetic:
-//                    voxel_coords, voxel_num_points, the pillar's {key, row, n} record for the feature kernel, the BEV
+//                    voxel_coords, voxel_num_points, the pillar's {x, y, z, row, n} record for the feature kernel, the BEV
 //                    index-map entry (the count plane BECOMES the index map: empty cells already hold -1), and the
 //                    list base into the first-index plane (tagged with bit 31 so that it can never be mistaken for a
 //                    point index by a tile that is still testing "am I the first").
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
             }
             if (p.write_meta) {
                 // indexed by the list START POSITION, so the feature kernel needs nothing but its own position to find it
-                p.pillar_meta[base] = make_uint4(ukey, live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, 0u);
+                p.pillar_meta[base] = make_uint4(c.x | (c.y << 16), live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, c.z);
                 if (live) {
                     if (p.voxel_coords)
                         *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) = make_int4(

@@ -38,8 +38,6 @@ namespace pillars {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kFlagLast = 1;  // final point of its pillar
-constexpr int kFlagStop = 2;  // ... and the walk of this chunk ends here
 
 // per-warp shared memory (bytes)
 constexpr uint32_t kRecSlot = 32 * 32;             // one chunk of records
@@ -48,15 +46,17 @@ constexpr uint32_t kMetaSlot = 32 * 16;            // one chunk of pillar entrie
 constexpr uint32_t kMetaRing = 2 * kMetaSlot;
 constexpr uint32_t kPlBytes = 32 * 32;             // pillar constants of the chunk being walked
 constexpr uint32_t kSumBytes = 3 * 32 * 4;
+constexpr uint32_t kLongBytes = 32;                // hand-off of a long pillar: {start slot + 1 (0: none), n, row, -, cx, cy, cz, -}
 constexpr uint32_t kOffMeta = kRecRing;
 constexpr uint32_t kOffPl = kOffMeta + kMetaRing;
 constexpr uint32_t kOffSum = kOffPl + kPlBytes;
-constexpr uint32_t kWarpSmem = kOffSum + kSumBytes;  // 6528
+constexpr uint32_t kOffLong = kOffSum + kSumBytes;
+constexpr uint32_t kWarpSmem = kOffLong + kLongBytes;  // 6560
 
 struct WalkParams {
     const PointRecord *records;   // grouped by pillar, x,y,z relative to the pillar centre (place kernel)
     const Header *hdr;
-    const uint4 *pillar_meta;     // by list start position: {cell key, row, n, -}
+    const uint4 *pillar_meta;     // by list start position: {x | y << 16, row, n, z}
     const float *folded;          // [PILLARS_FOLDED_FLOATS], see launch_fold_pfn
     float *pillar_features;
     GridDev gd;
@@ -146,11 +146,35 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// 1 / n for the window sizes (n <= 32); index 0 unused
+__constant__ float kRcp[33] = {0.f, 1.f / 1, 1.f / 2, 1.f / 3, 1.f / 4, 1.f / 5, 1.f / 6, 1.f / 7, 1.f / 8, 1.f / 9, 1.f / 10,
+                               1.f / 11, 1.f / 12, 1.f / 13, 1.f / 14, 1.f / 15, 1.f / 16, 1.f / 17, 1.f / 18, 1.f / 19,
+                               1.f / 20, 1.f / 21, 1.f / 22, 1.f / 23, 1.f / 24, 1.f / 25, 1.f / 26, 1.f / 27, 1.f / 28,
+                               1.f / 29, 1.f / 30, 1.f / 31, 1.f / 32};
+
 struct LaneWeights {
     float2 w0, w1, w2, w3, w4;        // per point: x', y', z', intensity, time
     float2 k0, k1, k2, k3, k4, k5;    // per pillar: centre xyz, -(cluster weights) on (mean - centre)
     float2 sh, rsh;                   // BatchNorm shift, relu(shift)
 };
+
+// the lane's two channels of one staged point (before the per-pillar constant); NaN for a point beyond the first-P cap
+__device__ __forceinline__ float2 point_eval(const LaneWeights &w, uint32_t addr)
+{
+    const float4 a = lds4(addr);
+    const float t = __uint_as_float(lds1u(addr + 16));
+    float2 y = mul2s(w.w0, a.x);
+    y = fma2s(w.w1, a.y, y);
+    y = fma2s(w.w2, a.z, y);
+    y = fma2s(w.w3, a.w, y);
+    return fma2s(w.w4, t, y);
+}
+// fmaxf ignores NaN operands, so dropped points vanish
+__device__ __forceinline__ float2 max2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+__device__ __forceinline__ float2 max3(float2 a, float2 b, float2 c)
+{
+    return make_float2(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)));
+}
 
 __device__ __forceinline__ void point_step(const LaneWeights &w, const float4 a, const float t, float2 &acc)
 {
@@ -165,8 +189,8 @@ __device__ __forceinline__ void point_step(const LaneWeights &w, const float4 a,
 
 // per-pillar constant, ReLU, padded-slot term, one 256-byte row.  c4 = centre xyz + (1.0 when the pillar has empty slots),
 // m4 = mean - centre xyz + row as int bits (-1: pillar not emitted)
-__device__ __forceinline__ void pillar_finish(const LaneWeights &w, const float4 c4, const float4 m4, const float2 acc,
-                                              unsigned long long out_lane)
+__device__ __forceinline__ void pillar_finish(const LaneWeights &w, const float4 c4, const float4 m4, const bool padded,
+                                              const float2 acc, unsigned long long out_lane)
 {
     float2 kc = fma2s(w.k0, c4.x, w.sh);
     kc = fma2s(w.k1, c4.y, kc);
@@ -175,7 +199,7 @@ __device__ __forceinline__ void pillar_finish(const LaneWeights &w, const float4
     kc = fma2s(w.k4, m4.y, kc);
     kc = fma2s(w.k5, m4.z, kc);
     const float2 v = add2(acc, kc);
-    const float2 fl2 = mul2s(w.rsh, c4.w);  // relu(shift) when the pillar has padded slots, else 0
+    const float2 fl2 = mul2s(w.rsh, padded ? 1.f : 0.f);  // relu(shift) when the pillar has padded slots, else 0
     const int row = __float_as_int(m4.w);
     if (row >= 0)
         asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
@@ -186,10 +210,24 @@ __device__ __forceinline__ void pillar_finish(const LaneWeights &w, const float4
 // mean - centre with the reference's rounding of the ABSOLUTE mean to fp32 (pillar_vfe.py:97-98)
 __device__ __forceinline__ float rel_mean(float c, float s_rel_mean) { return __fsub_rn(__fadd_rn(c, s_rel_mean), c); }
 
-// A pillar of more than 32 points: straight from global memory, the whole warp on one pillar.
-__device__ __noinline__ void long_pillar(const WalkParams &p, const LaneWeights &w, uint32_t p0, uint32_t n, int row, float cx,
-                                         float cy, float cz, unsigned long long out_lane, int lane)
+__device__ __forceinline__ LaneWeights load_lane_weights(const float *folded, int lane)
 {
+    LaneWeights w;
+    const float2 *fw = reinterpret_cast<const float2 *>(folded) + lane;
+    w.w0 = __ldg(fw + 0 * 32); w.w1 = __ldg(fw + 1 * 32); w.w2 = __ldg(fw + 2 * 32); w.w3 = __ldg(fw + 3 * 32);
+    w.w4 = __ldg(fw + 4 * 32);
+    w.k0 = __ldg(fw + 5 * 32); w.k1 = __ldg(fw + 6 * 32); w.k2 = __ldg(fw + 7 * 32); w.k3 = __ldg(fw + 8 * 32);
+    w.k4 = __ldg(fw + 9 * 32); w.k5 = __ldg(fw + 10 * 32);
+    w.sh = __ldg(fw + 11 * 32); w.rsh = __ldg(fw + 12 * 32);
+    return w;
+}
+
+// A pillar of more than 32 points: straight from global memory, the whole warp on one pillar (rare: it reloads the lane's
+// weights instead of taking them from the caller, so that the caller's copy never needs an address).
+__device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t p0, uint32_t n, int row, float cx, float cy, float cz,
+                                         unsigned long long out_lane, int lane)
+{
+    const LaneWeights w = load_lane_weights(p.folded, lane);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
     const float qnan = __int_as_float(0x7fc00000);
     uint32_t thr = 0xFFFFFFFFu;
@@ -228,7 +266,7 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, const LaneWeights 
         sz += __shfl_xor_sync(kFull, sz, s);
     }
     const float rn = __frcp_rn(static_cast<float>(min(n, P)));
-    const float4 c4 = make_float4(cx, cy, cz, n < P ? 1.f : 0.f);
+    const float4 c4 = make_float4(cx, cy, cz, 0.f);
     const float4 m4 = make_float4(rel_mean(cx, static_cast<float>(sx) * rn), rel_mean(cy, static_cast<float>(sy) * rn),
                                   rel_mean(cz, static_cast<float>(sz) * rn), __int_as_float(row));
     float2 acc = make_float2(-INFINITY, -INFINITY);
@@ -249,11 +287,11 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, const LaneWeights 
             point_step(w, v, __shfl_sync(kFull, qt, l), acc);
         }
     }
-    pillar_finish(w, c4, m4, acc, out_lane);
+    pillar_finish(w, c4, m4, n < P, acc, out_lane);
 }
 
-template <int kWarps>
-__global__ void __launch_bounds__(32 * kWarps, 1024 / (32 * kWarps))
+template <int kWarps, int kMinBlocks>
+__global__ void __launch_bounds__(32 * kWarps, kMinBlocks)
 k_pillar_walk(const __grid_constant__ WalkParams p)
 {
     __shared__ __align__(16) unsigned char s_all[kWarps * kWarpSmem];
@@ -267,7 +305,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     if (c >= c_end) return;
 
     const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * kWarpSmem;
-    const uint32_t s_meta = s_warp + kOffMeta, s_pl = s_warp + kOffPl, s_sum = s_warp + kOffSum;
+    const uint32_t s_meta = s_warp + kOffMeta, s_pl = s_warp + kOffPl, s_sum = s_warp + kOffSum, s_long = s_warp + kOffLong;
     const float qnan = __int_as_float(0x7fc00000);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
 
@@ -297,15 +335,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     fetch_meta(c);
     cp_async_commit();
 
-    LaneWeights w;
-    {
-        const float2 *fw = reinterpret_cast<const float2 *>(p.folded) + lane;
-        w.w0 = __ldg(fw + 0 * 32); w.w1 = __ldg(fw + 1 * 32); w.w2 = __ldg(fw + 2 * 32); w.w3 = __ldg(fw + 3 * 32);
-        w.w4 = __ldg(fw + 4 * 32);
-        w.k0 = __ldg(fw + 5 * 32); w.k1 = __ldg(fw + 6 * 32); w.k2 = __ldg(fw + 7 * 32); w.k3 = __ldg(fw + 8 * 32);
-        w.k4 = __ldg(fw + 9 * 32); w.k5 = __ldg(fw + 10 * 32);
-        w.sh = __ldg(fw + 11 * 32); w.rsh = __ldg(fw + 12 * 32);
-    }
+    const LaneWeights w = load_lane_weights(p.folded, lane);
     // the lane's output base as a global-space address kept in registers (not recomputed per pillar)
     unsigned long long out_lane = static_cast<unsigned long long>(__cvta_generic_to_global(p.pillar_features + 2 * lane));
     asm volatile("" : "+l"(out_lane));
@@ -330,10 +360,11 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         const bool is_start = own_ok && rb.w == 0u;
         const unsigned bal = __ballot_sync(kFull, is_start);
         if (bal != 0u) {
-            const uint4 me = lds4u(s_meta + (c & 1u) * kMetaSlot + lane * 16u);  // {key, row, n, -}: valid on start lanes
+            const uint32_t ms = s_meta + (c & 1u) * kMetaSlot;
             sts1(s_sum + lane * 4u, 0u);
             sts1(s_sum + 128u + lane * 4u, 0u);
             sts1(s_sum + 256u + lane * 4u, 0u);
+            if (lane == 0) sts1(s_long, 0u);
             __syncwarp();
             // every position adds itself to the sums of its pillar (when that pillar starts in this chunk and fits the
             // window); positions beyond the first-P cap are found by rank counting and become NaN
@@ -341,7 +372,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
                 if (arrival > j) return;  // the pillar started in an earlier chunk
                 const uint32_t slot = j - arrival;
                 if (slot >= 32u) return;  // starts in the next chunk
-                const uint32_t np = lds1u(s_meta + (c & 1u) * kMetaSlot + slot * 16u + 8u);
+                const uint32_t np = lds1u(ms + slot * 16u + 8u);
                 if (np > 32u) return;     // long pillar: handled after the walk
                 bool keep = true;
                 if (np > P) {
@@ -362,75 +393,66 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
             if (la_ok) contribute(32u + lane, tb.w, tb.z);
             __syncwarp();
 
-            const uint32_t n = me.z;
-            const bool is_long = is_start && n > 32u;
-            float cx = 0.f, cy = 0.f, cz = 0.f;
-            if (is_start) {
-                const CellCoord cc = decode_key(p, me.x);
-                cx = __fadd_rn(__fmul_rn(static_cast<float>(cc.x), p.vsz[0]), p.off[0]);
-                cy = __fadd_rn(__fmul_rn(static_cast<float>(cc.y), p.vsz[1]), p.off[1]);
-                cz = __fadd_rn(__fmul_rn(static_cast<float>(cc.z), p.vsz[2]), p.off[2]);
-                if (!is_long) {
-                    const float rn = __frcp_rn(static_cast<float>(min(n, P)));
-                    const float mx = static_cast<float>(static_cast<int>(lds1u(s_sum + lane * 4u))) * p.fx_inv[0] * rn;
-                    const float my = static_cast<float>(static_cast<int>(lds1u(s_sum + 128u + lane * 4u))) * p.fx_inv[1] * rn;
-                    const float mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
-                    sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, n < P ? 1.f : 0.f));
-                    sts4(s_pl + lane * 32u + 16, make_float4(rel_mean(cx, mx), rel_mean(cy, my), rel_mean(cz, mz),
-                                                             __uint_as_float(me.y)));
-                    sts1(rs + (lane + n - 1u) * 32u + 20u, kFlagLast);  // walk control: the pillar's final point
+            // the lane on a list start publishes the pillar's constants.  A long pillar can only be the last start of the
+            // chunk; it is handed to the code after the walk through shared memory (nothing of it stays in registers).
+            unsigned rem = bal;
+            {
+                const uint4 me = lds4u(ms + lane * 16u);  // {x | y << 16, row, n, z}: valid on start lanes
+                const uint32_t n = me.z;
+                const bool is_long = is_start && n > 32u;
+                if (is_start) {
+                    const float cx = __fadd_rn(__fmul_rn(static_cast<float>(me.x & 0xFFFFu), p.vsz[0]), p.off[0]);
+                    const float cy = __fadd_rn(__fmul_rn(static_cast<float>(me.x >> 16), p.vsz[1]), p.off[1]);
+                    const float cz = __fadd_rn(__fmul_rn(static_cast<float>(me.w), p.vsz[2]), p.off[2]);
+                    if (!is_long) {
+                        const float rn = kRcp[min(n, P)];
+                        const float mx = static_cast<float>(static_cast<int>(lds1u(s_sum + lane * 4u))) * p.fx_inv[0] * rn;
+                        const float my = static_cast<float>(static_cast<int>(lds1u(s_sum + 128u + lane * 4u))) * p.fx_inv[1] * rn;
+                        const float mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
+                        // n with bit 31 set when the pillar has empty (padded) slots
+                        sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, __uint_as_float(n | (n < P ? 0x80000000u : 0u))));
+                        sts4(s_pl + lane * 32u + 16, make_float4(rel_mean(cx, mx), rel_mean(cy, my), rel_mean(cz, mz),
+                                                                 __uint_as_float(me.y)));
+                    } else {
+                        sts4(s_long, make_float4(__uint_as_float(lane + 1u), __uint_as_float(n), __uint_as_float(me.y), 0.f));
+                        sts4(s_long + 16, make_float4(cx, cy, cz, 0.f));
+                    }
                 }
+                if (__any_sync(kFull, is_long)) rem &= ~(1u << (31 - __clz(bal)));
+                __syncwarp();
             }
-            __syncwarp();
-            // the walk stops at the end of the last pillar that fits the window; a long pillar can only be the last start
-            const int first_start = __ffs(bal) - 1, last_start = 31 - __clz(bal);
-            const bool long_last = __shfl_sync(kFull, is_long ? 1 : 0, last_start) != 0;
-            if (lane == last_start) {
-                if (!long_last) sts1(rs + (lane + n - 1u) * 32u + 20u, kFlagLast | kFlagStop);
-                else if (last_start > first_start) sts1(rs + (lane - 1u) * 32u + 20u, kFlagLast | kFlagStop);
-            }
-            __syncwarp();
 
-            // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair -------------------
-            if (!(long_last && last_start == first_start)) {
-                const uint32_t pl_delta = s_pl - rs;
-                uint32_t sp = rs + 32u * first_start;  // the point being accumulated
-                uint32_t ss = sp;                      // first point of the pillar being accumulated
-                float2 acc = make_float2(-INFINITY, -INFINITY);
-                // two points per trip, registers ping-ponged so that the next point is always in flight
-                float4 a0 = lds4(sp);
-                float2 b0 = lds2(sp + 16);
-                int fl;
-                while (true) {
-                    const float4 a1 = lds4(sp + 32);
-                    const float2 b1 = lds2(sp + 48);
-                    point_step(w, a0, b0.x, acc);
-                    fl = __float_as_int(b0.y);
-                    if (fl != 0) {
-                        if (fl & kFlagStop) break;
-                        pillar_finish(w, lds4(ss + pl_delta), lds4(ss + pl_delta + 16), acc, out_lane);
-                        acc = make_float2(-INFINITY, -INFINITY);
-                        ss = sp + 32;
+            // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair.  Pillar by pillar,
+            //      straight-line code for 1..3 points and a two-point interleaved loop beyond: the point chains and the
+            //      per-pillar constant chain are independent, so the FMA pipe always has several FFMA2 chains in flight.
+            while (rem) {
+                const uint32_t slot = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t pa = rs + slot * 32u;
+                const float4 c4 = lds4(s_pl + slot * 32u), m4 = lds4(s_pl + slot * 32u + 16);
+                const uint32_t nb = __float_as_uint(c4.w);
+                const uint32_t n = nb & 0x7FFFFFFFu;
+                float2 acc = point_eval(w, pa);
+                if (n >= 2u) {
+                    const float2 y1 = point_eval(w, pa + 32u);
+                    if (n == 2u) {
+                        acc = max2(acc, y1);
+                    } else {
+                        const float2 y2 = point_eval(w, pa + 64u);
+                        acc = max3(acc, y1, y2);
+                        for (uint32_t k = 3; k + 1 < n; k += 2) {
+                            const float2 ya = point_eval(w, pa + k * 32u), yb = point_eval(w, pa + k * 32u + 32u);
+                            acc = max3(acc, ya, yb);
+                        }
+                        if ((n & 1u) == 0u) acc = max2(acc, point_eval(w, pa + (n - 1u) * 32u));
                     }
-                    a0 = lds4(sp + 64);
-                    b0 = lds2(sp + 80);
-                    point_step(w, a1, b1.x, acc);
-                    fl = __float_as_int(b1.y);
-                    if (fl != 0) {
-                        if (fl & kFlagStop) break;
-                        pillar_finish(w, lds4(ss + pl_delta), lds4(ss + pl_delta + 16), acc, out_lane);
-                        acc = make_float2(-INFINITY, -INFINITY);
-                        ss = sp + 64;
-                    }
-                    sp += 64;
                 }
-                pillar_finish(w, lds4(ss + pl_delta), lds4(ss + pl_delta + 16), acc, out_lane);
+                pillar_finish(w, c4, m4, static_cast<int>(nb) < 0, acc, out_lane);
             }
-            if (long_last) {
-                const uint32_t ln = __shfl_sync(kFull, n, last_start);
-                const int lrow = static_cast<int>(__shfl_sync(kFull, me.y, last_start));
-                long_pillar(p, w, (c << 5) + last_start, ln, lrow, __shfl_sync(kFull, cx, last_start),
-                            __shfl_sync(kFull, cy, last_start), __shfl_sync(kFull, cz, last_start), out_lane, lane);
+            const uint4 lg = lds4u(s_long);
+            if (lg.x != 0u) {
+                const float4 lc = lds4(s_long + 16);
+                long_pillar(p, (c << 5) + lg.x - 1u, lg.y, static_cast<int>(lg.z), lc.x, lc.y, lc.z, out_lane, lane);
             }
         }
         cp_async_wait_all();
@@ -510,10 +532,19 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     constexpr int kWarps = 4;
     const int64_t chunks = (job.n + 31) / 32;  // upper bound: listed points <= n
     int64_t warps = (chunks + cpw - 1) / cpw;
-    const int64_t wave = static_cast<int64_t>(sms) * 32;
+    static const int occ = [] {
+        const int v = env_int("PILLARS_WALK_OCC", 6);
+        return v < 5 ? 5 : (v > 8 ? 8 : v);
+    }();
+    const int64_t wave = static_cast<int64_t>(sms) * occ * kWarps;
     if (warps > wave) warps = wave;
     const unsigned grid = static_cast<unsigned>((warps + kWarps - 1) / kWarps);
-    k_pillar_walk<kWarps><<<grid, 32 * kWarps, 0, st>>>(p);
+    switch (occ) {
+    case 8: k_pillar_walk<kWarps, 8><<<grid, 32 * kWarps, 0, st>>>(p); break;
+    case 7: k_pillar_walk<kWarps, 7><<<grid, 32 * kWarps, 0, st>>>(p); break;
+    case 6: k_pillar_walk<kWarps, 6><<<grid, 32 * kWarps, 0, st>>>(p); break;
+    default: k_pillar_walk<kWarps, 5><<<grid, 32 * kWarps, 0, st>>>(p); break;
+    }
     note_launch();
     return cudaGetLastError();
 }

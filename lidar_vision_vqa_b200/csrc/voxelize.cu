@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ Plac
         const bool live = local < static_cast<uint32_t>(p.gd.max_voxels) && row < p.capacity;
         const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
         // indexed by the list START POSITION, so the consumer needs nothing but its own position to find it
-        p.pillar_meta[e.z] = make_uint4(e.y, live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, 0u);
+        p.pillar_meta[e.z] = make_uint4(c.x | (c.y << 16), live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, c.z);
         if (live) {
             if (p.voxel_coords)
                 *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) =
