@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "bulk1d", "tma2d", "wide", "persist", "patch"])
+    ap.add_argument("--scatter-variant", default="auto", choices=["auto", "plain", "wide"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through the timed loop")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the timed steps are pipelined over (independent batches overlap)")

@@ -139,8 +139,8 @@ int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_p
  * PointPillarScatter3d.forward (pointpillar_scatter.py:40-73) for nz > 1: bev[b][f][z*ny*nx + y*nx + x], which viewed as
  * [B, f*nz, ny, nx] is exactly the reference's output.
  * m_dev, when not NULL, is a device int32 holding the live row count (<= m); rows beyond it are ignored.
- * variant: 0 = default, 1 = plain vector stores, 2 = bulk async copies (1-D), 3 = TMA tensor stores (2-D),
- *          4 = 256-bit vector stores. */
+ * variant: 0 = default (channel-group 256-bit stores where the shape allows, else plain), 1 = plain vector stores,
+ *          4 = same as 0.  (The store paths that were measured slower are archived under profiles/micro/.) */
 int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
                         const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz, float *bev,
                         void *workspace, size_t workspace_bytes, int32_t variant, void *stream);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/pillars_b200.h"
 
 namespace pillars {
@@ -64,6 +66,8 @@ struct Workspace {
     uint32_t *frame_rowbase;        // [B+1] output row at each frame start (after the max_voxels cap)
     size_t zero_bytes;
     // 0xFF-initialised region
+    uint32_t *long_count;           // pillars of more than 32 points listed so far, minus one (counts up from 0xFFFFFFFF)
+    uint32_t *long_cursor;          // next entry of that list to be processed by the feature kernel, minus one
     HashEntry *table;               // hash: [cap]
     uint32_t *tile_counter;         // dense: dynamic tile ids, counts up from 0xFFFFFFFF
     uint32_t *frame_new;            // dense: [B] pillars opened in each frame, minus one
@@ -80,6 +84,7 @@ struct Workspace {
     uint32_t *sorted_idx;           // [n] point indices grouped by pillar
     PointRecord *records;           // [n] point records grouped by pillar
     uint4 *pillar_meta;             // [n] per pillar, at its list start position: {x | y << 16, row (-1: dropped), n, z}
+    uint4 *long_list;               // [2 * (n / 32 + 2)] pillars of more than 32 points: {list start, n, row, x | y << 16} {z, -, -, -}
     float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
     uint32_t *scan_scratch;         // [B * ny * nx / 2048 + 2] block sums of the cell-rank scan (dynamic variant)
     uint32_t cap;                   // hash slots
@@ -134,6 +139,8 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
         w.zero_bytes = off;
         w.ff_begin = p ? p + off : nullptr;
         const size_t ff0 = off;
+        w.long_count = reinterpret_cast<uint32_t *>(take(256));
+        w.long_cursor = w.long_count ? w.long_count + 16 : nullptr;
         w.table = reinterpret_cast<HashEntry *>(take(n > 0 ? sizeof(HashEntry) * cap : 0));
         w.cell_row = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * static_cast<size_t>(nb) * cells_xy));
         w.ff_bytes = off - ff0;
@@ -141,6 +148,8 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
         w.zero_bytes = 0;
         w.ff_begin = p ? p : nullptr;
         w.tile_counter = reinterpret_cast<uint32_t *>(take(64));
+        w.long_count = reinterpret_cast<uint32_t *>(take(256));
+        w.long_cursor = w.long_count ? w.long_count + 16 : nullptr;
         w.frame_new = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));
         w.tile_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
         w.tile_prefix = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * (w.n_tiles + 1)));
@@ -159,6 +168,7 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     w.sorted_idx = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     w.records = reinterpret_cast<PointRecord *>(take(sizeof(PointRecord) * (n + 64)));  // + a look-ahead chunk of slack
     w.pillar_meta = reinterpret_cast<uint4 *>(take(sizeof(uint4) * (n + 64)));
+    w.long_list = reinterpret_cast<uint4 *>(take(sizeof(uint4) * 2 * (n / 32 + 2)));
     w.folded = reinterpret_cast<float *>(take(sizeof(float) * PILLARS_FOLDED_FLOATS));
     w.scan_scratch = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (static_cast<size_t>(nb) * cells_xy / 2048 + 2)));
     w.total_bytes = off;
@@ -211,6 +221,31 @@ struct PfnDev {
     float off[3];
     float vsz[3];
 };
+
+// ---- programmatic dependent launch (sm_90+): the kernels of one call form a chain on one stream; each is launched with
+// the attribute below, so its CTAs may be scheduled while the previous kernel drains, and executes pdl_wait() before it
+// touches anything a predecessor wrote (griddepcontrol.wait returns once ALL prerequisite grids have completed and their
+// writes are visible).  pdl_trigger() lets the next kernel's CTAs start occupying SMs as this grid's CTAs retire.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // launch bookkeeping (api.cu)
 void note_launch(int n = 1);

@@ -54,6 +54,21 @@ __device__ __forceinline__ void load_point_tile(const float *__restrict__ src, i
     }
 }
 
+// Frames touched by a tile of points [lo_i, hi_i]: this thread's share of (number of frame starts <= lo_i / hi_i); summed
+// over the CTA, the frame index is that count minus one.  Every load is independent (a binary search would chain
+// ~log2(nb) dependent global round trips in front of the CTA's first barrier).
+__device__ __forceinline__ void count_frame_starts(const int32_t *__restrict__ frame_offsets, int nb, int64_t lo_i, int64_t hi_i,
+                                                   int tid, int threads, uint32_t &c_lo, uint32_t &c_hi)
+{
+    c_lo = 0;
+    c_hi = 0;
+    for (int f = tid; f < nb; f += threads) {
+        const int64_t o = __ldg(frame_offsets + f);
+        c_lo += o <= lo_i ? 1u : 0u;
+        c_hi += o <= hi_i ? 1u : 0u;
+    }
+}
+
 // frame holding point i: largest b with offsets[b] <= i (offsets[0] = 0, offsets[nb] = n)
 __device__ __forceinline__ int find_frame(const int32_t *__restrict__ frame_offsets, int nb, int64_t i)
 {
@@ -93,6 +108,8 @@ struct PlaceParams {
     uint32_t *sorted_idx;            // or NULL
     PointRecord *records;            // or NULL
     uint4 *pillar_meta;
+    uint4 *long_list;
+    uint32_t *long_count;
     const uint32_t *pillar_cnt, *frame_gstart, *frame_rowbase;
     GridDev gd;
     int sh_cells, sh_cells_xy, sh_nx;  // log2 of the divisor when it is a power of two, else -1
@@ -117,6 +134,8 @@ inline PlaceParams make_place_params(const float *points, int64_t n, int stride,
     pp.sorted_idx = want_index_lists ? ws.sorted_idx : nullptr;
     pp.records = extras.records ? ws.records : nullptr;
     pp.pillar_meta = ws.pillar_meta;
+    pp.long_list = ws.long_list;
+    pp.long_count = ws.long_count;
     pp.pillar_cnt = ws.pillar_cnt;
     pp.frame_gstart = ws.frame_gstart;
     pp.frame_rowbase = ws.frame_rowbase;
@@ -138,6 +157,20 @@ inline PlaceParams make_place_params(const float *points, int64_t n, int stride,
 struct CellCoord {
     uint32_t b, z, y, x;
 };
+
+// The per-pillar record of the streaming feature kernel, at the pillar's list start position; pillars that cannot fit its
+// 64-position window (more than 32 points) are also appended to a list that its warps drain after their own chunks.
+__device__ __forceinline__ void publish_pillar(uint4 *pillar_meta, uint4 *long_list, uint32_t *long_count, uint32_t base,
+                                               const CellCoord &c, uint32_t row_or_ff, uint32_t n)
+{
+    const uint32_t xy = c.x | (c.y << 16);
+    pillar_meta[base] = make_uint4(xy, row_or_ff, n, c.z);
+    if (n > 32u) {
+        const uint32_t slot = atomicAdd(long_count, 1u) + 1u;  // the counter starts at 0xFFFFFFFF
+        long_list[2 * slot] = make_uint4(base, n, row_or_ff, xy);
+        long_list[2 * slot + 1] = make_uint4(c.z, 0u, 0u, 0u);
+    }
+}
 
 template <typename P>
 __device__ __forceinline__ CellCoord decode_key(const P &p, uint32_t key)

@@ -37,19 +37,25 @@ k_insert_dense(const float *__restrict__ points, int64_t n, int stride, int col0
                int vec_ok)
 {
     extern __shared__ __align__(16) float s_pts[];  // [kGroupThreads * stride]
-    __shared__ int s_b0, s_b1;
+    __shared__ uint32_t s_cnt[2];
     __shared__ uint32_t s_claims;
 
+    pdl_trigger();  // the scan kernel may start taking SMs as this grid's CTAs retire
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kGroupThreads;
     const int count = static_cast<int>(tmin<int64_t>(kGroupThreads, n - tile_start));
-    load_point_tile(points + tile_start * stride, count, stride, vec_ok, s_pts, tid, kGroupThreads);
-    if (tid < 2) {  // frames touched by this tile: [b0, b1]
-        const int lo = find_frame(frame_offsets, nb, tid == 0 ? tile_start : tile_start + count - 1);
-        if (tid == 0) s_b0 = lo; else s_b1 = lo;
-    }
+    if (tid < 2) s_cnt[tid] = 0u;
     if (tid == 2) s_claims = 0u;
     __syncthreads();
+    load_point_tile(points + tile_start * stride, count, stride, vec_ok, s_pts, tid, kGroupThreads);
+    {  // frames touched by this tile: [b0, b1] = (frame starts <= first / last point of the tile) - 1; independent loads
+        uint32_t c_lo, c_hi;
+        count_frame_starts(frame_offsets, nb, tile_start, tile_start + count - 1, tid, kGroupThreads, c_lo, c_hi);
+        if (c_lo) atomicAdd(&s_cnt[0], c_lo);
+        if (c_hi) atomicAdd(&s_cnt[1], c_hi);
+    }
+    __syncthreads();
+    const int s_b0 = static_cast<int>(s_cnt[0]) - 1, s_b1 = static_cast<int>(s_cnt[1]) - 1;
 
     const int64_t i = tile_start + tid;
     bool valid = false;
@@ -154,7 +160,8 @@ struct ScanDenseParams {
     uint32_t *frame_gstart, *frame_rowbase;
     int32_t *pillar_count;
     uint32_t *pillar_key, *pillar_list, *pillar_cnt;  // when write_lists
-    uint4 *pillar_meta;                               // when write_meta
+    uint4 *pillar_meta, *long_list;                   // when write_meta
+    uint32_t *long_count;
     int32_t *voxel_coords, *voxel_num_points;         // when write_meta (may be NULL)
     GridDev gd;
     int sh_cells, sh_cells_xy, sh_nx;
@@ -171,6 +178,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
     __shared__ uint32_t s_gstart[kMaxFrames + 1], s_rowbase[kMaxFrames + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();     // everything below reads what the insert kernel (and the memset before it) wrote
+    pdl_trigger();
     // A tile spins on its predecessors, so they must be running: ids are handed out in scheduling order.
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1u) + 1u;
 
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
             }
             if (p.write_meta) {
                 // indexed by the list START POSITION, so the feature kernel needs nothing but its own position to find it
-                p.pillar_meta[base] = make_uint4(c.x | (c.y << 16), live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, c.z);
+                publish_pillar(p.pillar_meta, p.long_list, p.long_count, base, c, live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n);
                 if (live) {
                     if (p.voxel_coords)
                         *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) = make_int4(
@@ -309,6 +318,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
 
 __global__ void __launch_bounds__(kGroupThreads) k_place_dense(const __grid_constant__ PlaceParams p)
 {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kGroupThreads + threadIdx.x;
     if (i >= p.n) return;
     const int32_t key = p.point_slot[i];
@@ -368,6 +379,8 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     sp.pillar_list = ws.pillar_list;
     sp.pillar_cnt = ws.pillar_cnt;
     sp.pillar_meta = ws.pillar_meta;
+    sp.long_list = ws.long_list;
+    sp.long_count = ws.long_count;
     sp.voxel_coords = pp.voxel_coords;
     sp.voxel_num_points = pp.voxel_num_points;
     sp.gd = gd;
@@ -377,10 +390,10 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     sp.capacity = extras.records ? extras.capacity : (1ll << 62);
     sp.write_lists = want_index_lists ? 1 : 0;
     sp.write_meta = extras.records ? 1 : 0;
-    k_scan_dense<<<ws.n_tiles, kScanThreads, 0, st>>>(sp);
+    if ((err = launch_pdl(k_scan_dense, dim3(ws.n_tiles), dim3(kScanThreads), 0, st, sp)) != cudaSuccess) return err;
     note_launch();
     if (want_index_lists || extras.records) {
-        k_place_dense<<<pb, kGroupThreads, 0, st>>>(pp);
+        if ((err = launch_pdl(k_place_dense, dim3(pb), dim3(kGroupThreads), 0, st, pp)) != cudaSuccess) return err;
         note_launch();
     }
     return cudaGetLastError();

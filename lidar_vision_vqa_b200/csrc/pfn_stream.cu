@@ -11,10 +11,9 @@
 //
 // Mapping.  The kernel is bound by instruction issue, not by HBM, so everything is arranged to issue few instructions and
 // to never wait for memory:
-//   * persistent warps: a warp owns a CONTIGUOUS range of 32-position chunks of the record list and slides a shared-memory
-//     window over it.  Records and pillar entries are brought in by cp.async (LDGSTS, no registers) two chunks / one chunk
-//     AHEAD of the chunk being processed, so a chunk's loads are in flight during the previous chunk's arithmetic; every
-//     record is fetched once (the look-ahead half of a window is the next chunk's own half);
+//   * persistent warps: a warp owns a contiguous range of 32-position chunks of the record list.  A chunk's window is 64
+//     positions (32 own + 32 look-ahead); records and pillar entries are brought in by cp.async (LDGSTS, no registers)
+//     into the warp's second buffer while the current chunk is processed;
 //   * phase 1, one lane per list position, no loops: the per-pillar sums for the mean are accumulated with shared-memory
 //     integer atomics on fixed-point coordinates relative to the pillar centre (order independent => bit-reproducible,
 //     resolution 2^-29 of a metre at 0.2 m pillars, far below the fp32 rounding of the reference's own absolute-coordinate
@@ -25,9 +24,9 @@
 //     shared-memory loads + 5 packed FFMA2 (fma.rn.f32x2: two channels per instruction) + 2 FMNMX with the running max in
 //     registers; at a pillar end the lanes add the per-pillar constant (6 FFMA2), apply ReLU / the padded-slot term and
 //     store the 256-byte output row with one coalesced 8-byte store per lane.
-// A warp owns the pillars whose list STARTS inside its chunks.  A pillar of more than 32 points cannot fit the window; it
-// is necessarily the last pillar starting in its chunk and is handled after the walk by a warp-cooperative path that reads
-// its records from global memory (radix select of the P-th smallest point index when n > P).
+// A chunk owns the pillars whose list STARTS inside it.  A pillar of more than 32 points cannot fit the window: the grouping
+// stage lists those, and every warp that runs out of chunks takes entries from that list (warp-cooperative path reading the
+// records from global memory; 8-bit radix select of the P-th smallest point index when n > P).
 #include <cmath>
 #include <cstdlib>
 
@@ -39,24 +38,24 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// per-warp shared memory (bytes)
-constexpr uint32_t kRecSlot = 32 * 32;             // one chunk of records
-constexpr uint32_t kRecRing = 4 * kRecSlot;        // slots 0..2 = chunk % 3, slot 3 mirrors slot 0 (a window never wraps)
-constexpr uint32_t kMetaSlot = 32 * 16;            // one chunk of pillar entries
-constexpr uint32_t kMetaRing = 2 * kMetaSlot;
-constexpr uint32_t kPlBytes = 32 * 32;             // pillar constants of the chunk being walked
+// per-warp shared memory (bytes): two chunk buffers (the chunk being processed, the chunk in flight), each holding the 64
+// records of the window (32 own positions + 32 look-ahead) and the 32 pillar entries of the own positions
+constexpr uint32_t kRecBytes = 64 * 32;
+constexpr uint32_t kMetaBytes = 32 * 16;
+constexpr uint32_t kBufBytes = kRecBytes + kMetaBytes;  // 2560
+constexpr uint32_t kPlBytes = 32 * 32;                  // pillar constants of the chunk being walked
 constexpr uint32_t kSumBytes = 3 * 32 * 4;
-constexpr uint32_t kLongBytes = 32;                // hand-off of a long pillar: {start slot + 1 (0: none), n, row, -, cx, cy, cz, -}
-constexpr uint32_t kOffMeta = kRecRing;
-constexpr uint32_t kOffPl = kOffMeta + kMetaRing;
+constexpr uint32_t kOffPl = 2 * kBufBytes;
 constexpr uint32_t kOffSum = kOffPl + kPlBytes;
-constexpr uint32_t kOffLong = kOffSum + kSumBytes;
-constexpr uint32_t kWarpSmem = kOffLong + kLongBytes;  // 6560
+constexpr uint32_t kWarpSmem = kOffSum + kSumBytes;     // 6528
 
 struct WalkParams {
     const PointRecord *records;   // grouped by pillar, x,y,z relative to the pillar centre (place kernel)
     const Header *hdr;
     const uint4 *pillar_meta;     // by list start position: {x | y << 16, row, n, z}
+    const uint4 *long_list;       // pillars of more than 32 points: {list start, n, row, x | y << 16} {z, -, -, -}
+    const uint32_t *long_count;   // entries - 1
+    uint32_t *long_cursor;        // next entry to process - 1 (shared by all warps of the grid)
     const float *folded;          // [PILLARS_FOLDED_FLOATS], see launch_fold_pfn
     float *pillar_features;
     GridDev gd;
@@ -187,6 +186,40 @@ __device__ __forceinline__ void point_step(const LaneWeights &w, const float4 a,
     acc.y = fmaxf(acc.y, y.y);
 }
 
+// points 1..n-1 of a pillar: two at a time (independent chains), the running max combined with a 3-input max
+__device__ __forceinline__ float2 more_points(const LaneWeights &w, uint32_t pa, uint32_t n, float2 acc)
+{
+    uint32_t k = 1;
+    for (; k + 1 < n; k += 2) {
+        const float2 ya = point_eval(w, pa + k * 32u), yb = point_eval(w, pa + k * 32u + 32u);
+        acc = max3(acc, ya, yb);
+    }
+    if (k < n) acc = max2(acc, point_eval(w, pa + k * 32u));
+    return acc;
+}
+
+// the per-pillar constant  W_p.c - W_cl.(mean - c) + shift  for the lane's two channels
+__device__ __forceinline__ float2 pillar_const(const LaneWeights &w, const float4 c4, const float4 m4)
+{
+    float2 kc = fma2s(w.k0, c4.x, w.sh);
+    kc = fma2s(w.k1, c4.y, kc);
+    kc = fma2s(w.k2, c4.z, kc);
+    kc = fma2s(w.k3, m4.x, kc);
+    kc = fma2s(w.k4, m4.y, kc);
+    return fma2s(w.k5, m4.z, kc);
+}
+// + constant, ReLU / padded-slot term, one coalesced 256-byte row (row < 0: pillar not emitted)
+__device__ __forceinline__ void pillar_store(const LaneWeights &w, const float2 kc, const int row, const bool padded,
+                                             const float2 acc, unsigned long long out_lane)
+{
+    const float2 v = add2(acc, kc);
+    const float2 fl2 = mul2s(w.rsh, padded ? 1.f : 0.f);  // relu(shift) when the pillar has padded slots, else 0
+    if (row >= 0)
+        asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
+                     "f"(fmaxf(v.x, fl2.x)), "f"(fmaxf(v.y, fl2.y))
+                     : "memory");
+}
+
 // per-pillar constant, ReLU, padded-slot term, one 256-byte row.  c4 = centre xyz + (1.0 when the pillar has empty slots),
 // m4 = mean - centre xyz + row as int bits (-1: pillar not emitted)
 __device__ __forceinline__ void pillar_finish(const LaneWeights &w, const float4 c4, const float4 m4, const bool padded,
@@ -224,40 +257,100 @@ __device__ __forceinline__ LaneWeights load_lane_weights(const float *folded, in
 
 // A pillar of more than 32 points: straight from global memory, the whole warp on one pillar (rare: it reloads the lane's
 // weights instead of taking them from the caller, so that the caller's copy never needs an address).
-__device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t p0, uint32_t n, int row, float cx, float cy, float cz,
-                                         unsigned long long out_lane, int lane)
+__device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, uint32_t p0, uint32_t n, int row, float cx,
+                                         float cy, float cz, unsigned long long out_lane, int lane)
 {
     const LaneWeights w = load_lane_weights(p.folded, lane);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
     const float qnan = __int_as_float(0x7fc00000);
     uint32_t thr = 0xFFFFFFFFu;
-    if (n > P) {  // threshold = P-th smallest point index (radix select): the first P points in index order are kept
-        uint32_t prefix = 0, kk = P;
-        for (int bit = p.idx_bits - 1; bit >= 0; --bit) {
-            const uint32_t himask = bit >= 31 ? 0u : 0xFFFFFFFFu << (bit + 1);
-            uint32_t c0 = 0;
+    if (n > P) {
+        // threshold = P-th smallest point index: the first P points in index order are kept.  Radix select with 8-bit digits:
+        // one streaming pass over the pillar's indices per digit (3 passes for up to 16 M points), a 256-bin histogram in
+        // shared memory (s_hist: 1 KB of the warp's region that is free after the walk).
+        uint32_t prefix = 0, himask = 0, kk = P;
+        for (int shift = ((p.idx_bits + 7) / 8) * 8 - 8; shift >= 0; shift -= 8) {
+            sts4(s_hist + lane * 32u, make_float4(0.f, 0.f, 0.f, 0.f));
+            sts4(s_hist + lane * 32u + 16, make_float4(0.f, 0.f, 0.f, 0.f));
+            __syncwarp();
             for (uint32_t j = lane; j < n; j += 32) {
                 const uint32_t v = __ldg(&p.records[p0 + j].idx);
-                c0 += ((v & himask) == prefix && ((v >> bit) & 1u) == 0u) ? 1u : 0u;
+                if ((v & himask) == prefix) atoms_add(s_hist + ((v >> shift) & 255u) * 4u, 1);
             }
+            __syncwarp();
+            const uint4 h0 = lds4u(s_hist + lane * 32u), h1 = lds4u(s_hist + lane * 32u + 16);  // bins 8*lane .. 8*lane+7
+            const uint32_t bins[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint32_t mine = 0;
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) c0 += __shfl_xor_sync(kFull, c0, s);
-            if (kk > c0) {
-                prefix |= 1u << bit;
-                kk -= c0;
+            for (int k = 0; k < 8; ++k) mine += bins[k];
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += o;
             }
+            const uint32_t excl = incl - mine;
+            const bool owner = excl < kk && kk <= incl;  // exactly one lane: the matching indices number at least kk
+            uint32_t digit = 0, before = excl;
+            if (owner) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (before + bins[k] < kk) {
+                        before += bins[k];
+                        digit = k + 1;
+                    } else {
+                        break;
+                    }
+                }
+                digit += 8u * lane;
+            }
+            const int src = __ffs(__ballot_sync(kFull, owner)) - 1;
+            digit = __shfl_sync(kFull, digit, src);
+            before = __shfl_sync(kFull, before, src);
+            prefix |= digit << shift;
+            himask |= 255u << shift;
+            kk -= before;
+            __syncwarp();
         }
         thr = prefix;
     }
-    // mean of the kept points; double: the sum does not depend on the list order
+    // one pass over the records: sums for the mean of the kept points (double: independent of the list order) and the
+    // running max.  32 records per sweep go through the warp's shared-memory scratch and are evaluated two at a time
+    // (independent FFMA2 chains); the next sweep's loads are issued before the current one is evaluated.
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (uint32_t j = lane; j < n; j += 32) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(p.records + p0 + j));
-        if (__ldg(&p.records[p0 + j].idx) <= thr) {
-            sx += static_cast<double>(q.x);
-            sy += static_cast<double>(q.y);
-            sz += static_cast<double>(q.z);
+    float2 acc = make_float2(-INFINITY, -INFINITY);
+    float4 u = make_float4(qnan, 0.f, 0.f, 0.f), v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < n) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + lane);
+        u = __ldg(src);
+        v = __ldg(src + 1);
+    }
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+        const uint32_t cnt = min(32u, n - k0);
+        if (lane < cnt) {
+            if (__float_as_uint(v.z) > thr) {
+                u.x = qnan;
+            } else {
+                sx += static_cast<double>(u.x);
+                sy += static_cast<double>(u.y);
+                sz += static_cast<double>(u.z);
+            }
+        } else {
+            u.x = qnan;
         }
+        sts4(s_hist + lane * 32u, u);
+        sts4(s_hist + lane * 32u + 16, v);
+        if (k0 + 32u + lane < n) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + k0 + 32u + lane);
+            u = __ldg(src);
+            v = __ldg(src + 1);
+        }
+        __syncwarp();
+        for (uint32_t k = 0; k < cnt; k += 2) {  // an odd count ends on a NaN record, which the max ignores
+            const float2 ya = point_eval(w, s_hist + k * 32u), yb = point_eval(w, s_hist + k * 32u + 32u);
+            acc = max3(acc, ya, yb);
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -269,25 +362,27 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t p0, uint3
     const float4 c4 = make_float4(cx, cy, cz, 0.f);
     const float4 m4 = make_float4(rel_mean(cx, static_cast<float>(sx) * rn), rel_mean(cy, static_cast<float>(sy) * rn),
                                   rel_mean(cz, static_cast<float>(sz) * rn), __int_as_float(row));
-    float2 acc = make_float2(-INFINITY, -INFINITY);
-    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-        const int cnt = static_cast<int>(min(32u, n - k0));
-        float4 qa = make_float4(qnan, 0.f, 0.f, 0.f);
-        float qt = 0.f;
-        if (lane < cnt) {
-            const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + k0 + lane);
-            const float4 u = __ldg(src), v = __ldg(src + 1);
-            qa = u;
-            if (__float_as_uint(v.z) > thr) qa.x = qnan;
-            qt = v.x;
-        }
-        for (int l = 0; l < cnt; ++l) {
-            const float4 v = make_float4(__shfl_sync(kFull, qa.x, l), __shfl_sync(kFull, qa.y, l),
-                                         __shfl_sync(kFull, qa.z, l), __shfl_sync(kFull, qa.w, l));
-            point_step(w, v, __shfl_sync(kFull, qt, l), acc);
-        }
-    }
     pillar_finish(w, c4, m4, n < P, acc, out_lane);
+}
+
+// Pillars of more than 32 points, listed by the grouping stage: every warp, once its own chunks are done, takes entries
+// from the list through one grid-wide cursor, so the long tail is spread over the whole machine instead of serialising the
+// warps whose chunks happen to contain it.
+__device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t s_hist, unsigned long long out_lane, int lane)
+{
+    const uint32_t n_long = __ldcg(p.long_count) + 1u;
+    if (n_long == 0u) return;
+    while (true) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(p.long_cursor, 1u) + 1u;  // the cursor starts at 0xFFFFFFFF
+        i = __shfl_sync(kFull, i, 0);
+        if (i >= n_long) break;
+        const uint4 e0 = __ldcg(p.long_list + 2 * i), e1 = __ldcg(p.long_list + 2 * i + 1);
+        const float cx = __fadd_rn(__fmul_rn(static_cast<float>(e0.w & 0xFFFFu), p.vsz[0]), p.off[0]);
+        const float cy = __fadd_rn(__fmul_rn(static_cast<float>(e0.w >> 16), p.vsz[1]), p.off[1]);
+        const float cz = __fadd_rn(__fmul_rn(static_cast<float>(e1.x), p.vsz[2]), p.off[2]);
+        long_pillar(p, s_hist, e0.x, e0.y, static_cast<int>(e0.z), cx, cy, cz, out_lane, lane);
+    }
 }
 
 template <int kWarps, int kMinBlocks>
@@ -297,61 +392,56 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     __shared__ __align__(16) unsigned char s_all[kWarps * kWarpSmem];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();  // records, pillar entries and the list header come from the grouping kernels
+    pdl_trigger();
     const uint32_t total = __ldcg(&p.hdr->total_listed);
     const uint32_t n_chunks = (total + 31u) >> 5;
-    const uint32_t gw = blockIdx.x * kWarps + warp, n_warps = gridDim.x * kWarps;
-    uint32_t c = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * gw / n_warps);
-    const uint32_t c_end = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * (gw + 1) / n_warps);
-    if (c >= c_end) return;
-
     const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * kWarpSmem;
-    const uint32_t s_meta = s_warp + kOffMeta, s_pl = s_warp + kOffPl, s_sum = s_warp + kOffSum, s_long = s_warp + kOffLong;
+    const uint32_t s_pl = s_warp + kOffPl, s_sum = s_warp + kOffSum;
     const float qnan = __int_as_float(0x7fc00000);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
-
-    // chunk k -> record slot k % 3 (+ the mirror slot 3 when k % 3 == 0), pillar entries -> slot k % 2
-    auto fetch_records = [&](uint32_t k, uint32_t k3) {
-        const uint32_t pos = (k << 5) + lane;
-        const bool ok = pos < total;
-        const float4 *src = reinterpret_cast<const float4 *>(p.records + (ok ? pos : 0u));
-        const int nbytes = ok ? 16 : 0;
-        const uint32_t dst = s_warp + k3 * kRecSlot + lane * 32u;
-        cp_async16(dst, src, nbytes);
-        cp_async16(dst + 16, src + 1, nbytes);
-        if (k3 == 0) {
-            cp_async16(dst + 3 * kRecSlot, src, nbytes);
-            cp_async16(dst + 3 * kRecSlot + 16, src + 1, nbytes);
-        }
-    };
-    auto fetch_meta = [&](uint32_t k) {
-        const uint32_t pos = (k << 5) + lane;
-        const bool ok = pos < total;
-        cp_async16(s_meta + (k & 1u) * kMetaSlot + lane * 16u, p.pillar_meta + (ok ? pos : 0u), ok ? 16 : 0);
-    };
-
-    uint32_t c3 = c % 3u;  // slot of chunk c
-    fetch_records(c, c3);
-    fetch_records(c + 1, c3 == 2 ? 0u : c3 + 1);
-    fetch_meta(c);
-    cp_async_commit();
-
-    const LaneWeights w = load_lane_weights(p.folded, lane);
     // the lane's output base as a global-space address kept in registers (not recomputed per pillar)
     unsigned long long out_lane = static_cast<unsigned long long>(__cvta_generic_to_global(p.pillar_features + 2 * lane));
     asm volatile("" : "+l"(out_lane));
+
+    // A warp owns a contiguous range of chunks.  (Handing chunks out one at a time through a grid-wide cursor was measured
+    // SLOWER, 37-39 us against 33 us on cfg2, although per-warp times vary by +-40 %: neighbouring chunks then run on different
+    // SMs and every window is fetched twice.)
+    const uint32_t gw = blockIdx.x * kWarps + warp, n_warps = gridDim.x * kWarps;
+    uint32_t cur = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * gw / n_warps);
+    const uint32_t c_end = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * (gw + 1) / n_warps);
+    // chunk k -> buffer b: own records, look-ahead records, pillar entries (zero-filled beyond the end of the list)
+    auto fetch = [&](uint32_t k, uint32_t b) {
+        const uint32_t pos = (k << 5) + lane;
+        const uint32_t dst = s_warp + b * kBufBytes + lane * 32u;
+        const bool ok = pos < total, ok2 = pos + 32u < total;
+        const float4 *src = reinterpret_cast<const float4 *>(p.records + (ok ? pos : 0u));
+        cp_async16(dst, src, ok ? 16 : 0);
+        cp_async16(dst + 16, src + 1, ok ? 16 : 0);
+        const float4 *src2 = reinterpret_cast<const float4 *>(p.records + (ok2 ? pos + 32u : 0u));
+        cp_async16(dst + 1024, src2, ok2 ? 16 : 0);
+        cp_async16(dst + 1024 + 16, src2 + 1, ok2 ? 16 : 0);
+        cp_async16(s_warp + b * kBufBytes + kRecBytes + lane * 16u, p.pillar_meta + (ok ? pos : 0u), ok ? 16 : 0);
+    };
+
+    if (cur >= c_end) {
+        drain_long_pillars(p, s_pl, out_lane, lane);
+        return;
+    }
+    fetch(cur, 0);
+    cp_async_commit();
+    const LaneWeights w = load_lane_weights(p.folded, lane);
+    uint32_t buf = 0;
     cp_async_wait_all();
     __syncwarp();
 
-    for (; c < c_end; ++c) {
-        // loads for the chunks ahead fly during this chunk's arithmetic
-        {
-            const uint32_t k3 = c3 == 0 ? 2u : c3 - 1;  // (c + 2) % 3
-            fetch_records(c + 2, k3);
-            fetch_meta(c + 1);
-            cp_async_commit();
-        }
-        const uint32_t rs = s_warp + c3 * kRecSlot;  // window: 64 consecutive positions starting at chunk c
-        const uint32_t pos = (c << 5) + lane;
+    while (true) {
+        // the next chunk's loads fly during this chunk's arithmetic
+        if (cur + 1 < c_end) fetch(cur + 1, buf ^ 1u);
+        cp_async_commit();
+        const uint32_t rs = s_warp + buf * kBufBytes;  // window: 64 consecutive positions starting at chunk cur
+        const uint32_t ms = rs + kRecBytes;
+        const uint32_t pos = (cur << 5) + lane;
 
         // ---- phase 1 -----------------------------------------------------------------------------------------------------
         const uint4 rb = lds4u(rs + lane * 32u + 16);          // {time, flags, idx, arrival} of my own position
@@ -360,11 +450,9 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         const bool is_start = own_ok && rb.w == 0u;
         const unsigned bal = __ballot_sync(kFull, is_start);
         if (bal != 0u) {
-            const uint32_t ms = s_meta + (c & 1u) * kMetaSlot;
             sts1(s_sum + lane * 4u, 0u);
             sts1(s_sum + 128u + lane * 4u, 0u);
             sts1(s_sum + 256u + lane * 4u, 0u);
-            if (lane == 0) sts1(s_long, 0u);
             __syncwarp();
             // every position adds itself to the sums of its pillar (when that pillar starts in this chunk and fits the
             // window); positions beyond the first-P cap are found by rank counting and become NaN
@@ -373,7 +461,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
                 const uint32_t slot = j - arrival;
                 if (slot >= 32u) return;  // starts in the next chunk
                 const uint32_t np = lds1u(ms + slot * 16u + 8u);
-                if (np > 32u) return;     // long pillar: handled after the walk
+                if (np > 32u) return;     // long pillar: taken from the long-pillar list
                 bool keep = true;
                 if (np > P) {
                     uint32_t rank = 0;
@@ -393,72 +481,60 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
             if (la_ok) contribute(32u + lane, tb.w, tb.z);
             __syncwarp();
 
-            // the lane on a list start publishes the pillar's constants.  A long pillar can only be the last start of the
-            // chunk; it is handed to the code after the walk through shared memory (nothing of it stays in registers).
+            // the lane on a list start publishes the pillar's constants.  A pillar of more than 32 points does not fit the window
+            // (it can only be the last start of the chunk): it is skipped here and taken from the long-pillar list later.
             unsigned rem = bal;
             {
                 const uint4 me = lds4u(ms + lane * 16u);  // {x | y << 16, row, n, z}: valid on start lanes
                 const uint32_t n = me.z;
                 const bool is_long = is_start && n > 32u;
-                if (is_start) {
+                if (is_start && !is_long) {
                     const float cx = __fadd_rn(__fmul_rn(static_cast<float>(me.x & 0xFFFFu), p.vsz[0]), p.off[0]);
                     const float cy = __fadd_rn(__fmul_rn(static_cast<float>(me.x >> 16), p.vsz[1]), p.off[1]);
                     const float cz = __fadd_rn(__fmul_rn(static_cast<float>(me.w), p.vsz[2]), p.off[2]);
-                    if (!is_long) {
-                        const float rn = kRcp[min(n, P)];
-                        const float mx = static_cast<float>(static_cast<int>(lds1u(s_sum + lane * 4u))) * p.fx_inv[0] * rn;
-                        const float my = static_cast<float>(static_cast<int>(lds1u(s_sum + 128u + lane * 4u))) * p.fx_inv[1] * rn;
-                        const float mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
-                        // n with bit 31 set when the pillar has empty (padded) slots
-                        sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, __uint_as_float(n | (n < P ? 0x80000000u : 0u))));
-                        sts4(s_pl + lane * 32u + 16, make_float4(rel_mean(cx, mx), rel_mean(cy, my), rel_mean(cz, mz),
-                                                                 __uint_as_float(me.y)));
-                    } else {
-                        sts4(s_long, make_float4(__uint_as_float(lane + 1u), __uint_as_float(n), __uint_as_float(me.y), 0.f));
-                        sts4(s_long + 16, make_float4(cx, cy, cz, 0.f));
-                    }
+                    const float rn = kRcp[min(n, P)];
+                    const float mx = static_cast<float>(static_cast<int>(lds1u(s_sum + lane * 4u))) * p.fx_inv[0] * rn;
+                    const float my = static_cast<float>(static_cast<int>(lds1u(s_sum + 128u + lane * 4u))) * p.fx_inv[1] * rn;
+                    const float mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
+                    // n with bit 31 set when the pillar has empty (padded) slots
+                    sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, __uint_as_float(n | (n < P ? 0x80000000u : 0u))));
+                    sts4(s_pl + lane * 32u + 16, make_float4(rel_mean(cx, mx), rel_mean(cy, my), rel_mean(cz, mz),
+                                                             __uint_as_float(me.y)));
                 }
-                if (__any_sync(kFull, is_long)) rem &= ~(1u << (31 - __clz(bal)));
+                rem &= ~__ballot_sync(kFull, is_long);
                 __syncwarp();
             }
 
-            // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair.  Pillar by pillar,
-            //      straight-line code for 1..3 points and a two-point interleaved loop beyond: the point chains and the
-            //      per-pillar constant chain are independent, so the FMA pipe always has several FFMA2 chains in flight.
+            // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair.  TWO pillars per
+            //      trip: their first-point chains and constant chains are four independent FFMA2 chains in one straight-line
+            //      block; further points of a pillar are evaluated two at a time.
             while (rem) {
-                const uint32_t slot = __ffs(rem) - 1;
+                const uint32_t slot_a = __ffs(rem) - 1;
                 rem &= rem - 1;
-                const uint32_t pa = rs + slot * 32u;
-                const float4 c4 = lds4(s_pl + slot * 32u), m4 = lds4(s_pl + slot * 32u + 16);
-                const uint32_t nb = __float_as_uint(c4.w);
-                const uint32_t n = nb & 0x7FFFFFFFu;
-                float2 acc = point_eval(w, pa);
-                if (n >= 2u) {
-                    const float2 y1 = point_eval(w, pa + 32u);
-                    if (n == 2u) {
-                        acc = max2(acc, y1);
-                    } else {
-                        const float2 y2 = point_eval(w, pa + 64u);
-                        acc = max3(acc, y1, y2);
-                        for (uint32_t k = 3; k + 1 < n; k += 2) {
-                            const float2 ya = point_eval(w, pa + k * 32u), yb = point_eval(w, pa + k * 32u + 32u);
-                            acc = max3(acc, ya, yb);
-                        }
-                        if ((n & 1u) == 0u) acc = max2(acc, point_eval(w, pa + (n - 1u) * 32u));
-                    }
+                const bool has_b = rem != 0u;
+                const uint32_t slot_b = has_b ? static_cast<uint32_t>(__ffs(rem) - 1) : slot_a;
+                rem &= rem - 1;  // (0 & anything stays 0)
+                const uint32_t pa = rs + slot_a * 32u, pb = rs + slot_b * 32u;
+                const float4 c4a = lds4(s_pl + slot_a * 32u), m4a = lds4(s_pl + slot_a * 32u + 16);
+                const float4 c4b = lds4(s_pl + slot_b * 32u), m4b = lds4(s_pl + slot_b * 32u + 16);
+                float2 acc_a = point_eval(w, pa), acc_b = point_eval(w, pb);
+                const float2 kc_a = pillar_const(w, c4a, m4a), kc_b = pillar_const(w, c4b, m4b);
+                const uint32_t nba = __float_as_uint(c4a.w), nbb = __float_as_uint(c4b.w);
+                const uint32_t na = nba & 0x7FFFFFFFu, nb2 = nbb & 0x7FFFFFFFu;
+                if ((na | nb2) > 1u) {  // some pillar of the pair has more points
+                    if (na > 1u) acc_a = more_points(w, pa, na, acc_a);
+                    if (nb2 > 1u && has_b) acc_b = more_points(w, pb, nb2, acc_b);
                 }
-                pillar_finish(w, c4, m4, static_cast<int>(nb) < 0, acc, out_lane);
-            }
-            const uint4 lg = lds4u(s_long);
-            if (lg.x != 0u) {
-                const float4 lc = lds4(s_long + 16);
-                long_pillar(p, (c << 5) + lg.x - 1u, lg.y, static_cast<int>(lg.z), lc.x, lc.y, lc.z, out_lane, lane);
+                pillar_store(w, kc_a, __float_as_int(m4a.w), static_cast<int>(nba) < 0, acc_a, out_lane);
+                if (has_b) pillar_store(w, kc_b, __float_as_int(m4b.w), static_cast<int>(nbb) < 0, acc_b, out_lane);
             }
         }
         cp_async_wait_all();
         __syncwarp();
-        c3 = c3 == 2 ? 0u : c3 + 1;
+        if (++cur >= c_end) break;
+        buf ^= 1u;
     }
+    drain_long_pillars(p, s_pl, out_lane, lane);
 }
 
 // ---- folding of the layer's weights (once per model: pillars_fold_pfn) ------------------------------------------------
@@ -505,6 +581,9 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     p.records = ws.records;
     p.hdr = ws.hdr;
     p.pillar_meta = ws.pillar_meta;
+    p.long_list = ws.long_list;
+    p.long_count = ws.long_count;
+    p.long_cursor = ws.long_cursor;
     p.folded = folded;
     p.pillar_features = job.pillar_features;
     p.gd = gd;
@@ -523,28 +602,26 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
         p.fx_scale[k] = static_cast<float>(std::ldexp(1.0, s));
         p.fx_inv[k] = static_cast<float>(std::ldexp(1.0, -s));
     }
-    // Persistent warps: about `cpw` chunks of 32 list positions per warp, at most one full wave of warps.
+    // Persistent warps, at most one full wave; each takes 32-position chunks from the grid-wide cursor.
     const int sms = current_sm_count();
-    static const int cpw = [] {
-        const int v = env_int("PILLARS_WALK_CPW", 3);
-        return v < 1 ? 1 : v;
+    static const int occ = [] {
+        const int v = env_int("PILLARS_WALK_OCC", 5);
+        return v < 5 ? 5 : (v > 8 ? 8 : v);
     }();
     constexpr int kWarps = 4;
     const int64_t chunks = (job.n + 31) / 32;  // upper bound: listed points <= n
-    int64_t warps = (chunks + cpw - 1) / cpw;
-    static const int occ = [] {
-        const int v = env_int("PILLARS_WALK_OCC", 6);
-        return v < 5 ? 5 : (v > 8 ? 8 : v);
-    }();
+    int64_t warps = (chunks + 1) / 2;
     const int64_t wave = static_cast<int64_t>(sms) * occ * kWarps;
     if (warps > wave) warps = wave;
     const unsigned grid = static_cast<unsigned>((warps + kWarps - 1) / kWarps);
+    cudaError_t err;
     switch (occ) {
-    case 8: k_pillar_walk<kWarps, 8><<<grid, 32 * kWarps, 0, st>>>(p); break;
-    case 7: k_pillar_walk<kWarps, 7><<<grid, 32 * kWarps, 0, st>>>(p); break;
-    case 6: k_pillar_walk<kWarps, 6><<<grid, 32 * kWarps, 0, st>>>(p); break;
-    default: k_pillar_walk<kWarps, 5><<<grid, 32 * kWarps, 0, st>>>(p); break;
+    case 8: err = launch_pdl(k_pillar_walk<kWarps, 8>, dim3(grid), dim3(32 * kWarps), 0, st, p); break;
+    case 7: err = launch_pdl(k_pillar_walk<kWarps, 7>, dim3(grid), dim3(32 * kWarps), 0, st, p); break;
+    case 6: err = launch_pdl(k_pillar_walk<kWarps, 6>, dim3(grid), dim3(32 * kWarps), 0, st, p); break;
+    default: err = launch_pdl(k_pillar_walk<kWarps, 5>, dim3(grid), dim3(32 * kWarps), 0, st, p); break;
     }
+    if (err != cudaSuccess) return err;
     note_launch();
     return cudaGetLastError();
 }

@@ -68,20 +68,23 @@ k_quantize_insert(const float *__restrict__ points, int64_t n, int stride, int c
         for (uint32_t v = gtid; v < ff_vecs; v += gsz) ff_region[v] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
     extern __shared__ __align__(16) float s_pts[];  // [kThreads * stride]
-    __shared__ int s_b0, s_b1;
+    __shared__ uint32_t s_cnt[2];
 
+    pdl_trigger();
     const int tid = threadIdx.x;
     const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kThreads;
     const int count = static_cast<int>(tmin<int64_t>(kThreads, n - tile_start));
-
+    if (tid < 2) s_cnt[tid] = 0u;
+    __syncthreads();
     load_point_tile(points + tile_start * stride, count, stride, vec_ok, s_pts, tid, kThreads);
-    // frames touched by this tile: [b0, b1]; two binary searches per CTA instead of one per point
-    if (tid < 2) {
-        const int64_t i = tid == 0 ? tile_start : tile_start + count - 1;
-        const int lo = find_frame(frame_offsets, nb, i);
-        if (tid == 0) s_b0 = lo; else s_b1 = lo;
+    {  // frames touched by this tile: [b0, b1] = (frame starts <= first / last point of the tile) - 1; independent loads
+        uint32_t c_lo, c_hi;
+        count_frame_starts(frame_offsets, nb, tile_start, tile_start + count - 1, tid, kThreads, c_lo, c_hi);
+        if (c_lo) atomicAdd(&s_cnt[0], c_lo);
+        if (c_hi) atomicAdd(&s_cnt[1], c_hi);
     }
     __syncthreads();
+    const int s_b0 = static_cast<int>(s_cnt[0]) - 1, s_b1 = static_cast<int>(s_cnt[1]) - 1;
 
     const int64_t i = tile_start + tid;
     bool valid = false;
@@ -168,6 +171,8 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
     __shared__ uint8_t s_thr_flags[kThreads];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();
+    pdl_trigger();
     // A tile spins on its predecessors, so they must be running: guaranteed when the whole grid is co-resident
     // (blockIdx is then the tile id), otherwise ids are handed out in scheduling order.
     if (dynamic_ids) {
@@ -314,6 +319,8 @@ k_scan_assign(int64_t n, uint32_t n_tiles, const int32_t *__restrict__ point_slo
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ PlaceParams p)
 {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (i >= p.n) return;
     const int32_t s = p.point_slot[i];
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) k_place(const __grid_constant__ Plac
         const bool live = local < static_cast<uint32_t>(p.gd.max_voxels) && row < p.capacity;
         const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
         // indexed by the list START POSITION, so the consumer needs nothing but its own position to find it
-        p.pillar_meta[e.z] = make_uint4(c.x | (c.y << 16), live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n, c.z);
+        publish_pillar(p.pillar_meta, p.long_list, p.long_count, e.z, c, live ? static_cast<uint32_t>(row) : 0xFFFFFFFFu, n);
         if (live) {
             if (p.voxel_coords)
                 *reinterpret_cast<int4 *>(p.voxel_coords + row * 4) =
@@ -398,14 +405,15 @@ cudaError_t launch_group_points(const float *points, int64_t n, int stride, int 
     // Tile ids are always handed out in scheduling order (one atomic per CTA): with other streams sharing the GPU nothing
     // guarantees that blockIdx order is dispatch order, and a tile spins on its predecessors.
     const int dynamic_ids = 1;
-    k_scan_assign<<<ws.n_tiles, kThreads, 0, st>>>(n, ws.n_tiles, ws.point_slot, ws.table, ws.hdr, ws.tile_desc,
-                                                   ws.tile_prefix, ws.pillar_key, ws.pillar_list, ws.pillar_cnt,
-                                                   frame_offsets, nb, ws.frame_gstart, dynamic_ids, gd.max_voxels,
-                                                   ws.frame_rowbase, pillar_count);
+    if ((err = launch_pdl(k_scan_assign, dim3(ws.n_tiles), dim3(kThreads), 0, st, n, ws.n_tiles,
+                          static_cast<const int32_t *>(ws.point_slot), ws.table, ws.hdr, ws.tile_desc, ws.tile_prefix,
+                          ws.pillar_key, ws.pillar_list, ws.pillar_cnt, frame_offsets, nb, ws.frame_gstart, dynamic_ids,
+                          gd.max_voxels, ws.frame_rowbase, pillar_count)) != cudaSuccess)
+        return err;
     note_launch(2);
     if (want_index_lists || extras.records) {
         const PlaceParams pp = make_place_params(points, n, stride, col0, c_point, gd, ws, want_index_lists, extras);
-        k_place<<<pb, kThreads, 0, st>>>(pp);
+        if ((err = launch_pdl(k_place, dim3(pb), dim3(kThreads), 0, st, pp)) != cudaSuccess) return err;
         note_launch();
     }
     return cudaGetLastError();

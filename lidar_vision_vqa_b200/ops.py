@@ -14,7 +14,7 @@ from . import _native
 from ._native import NativeLibraryError, PillarsOutputs, PillarsPfn, PillarsPfnStack, check, make_grid
 
 FOLDED_FLOATS = 13 * 64  # PILLARS_FOLDED_FLOATS
-SCATTER_VARIANTS = {"auto": 0, "plain": 1, "bulk1d": 2, "tma2d": 3, "wide": 4, "persist": 5, "patch": 6}
+SCATTER_VARIANTS = {"auto": 0, "plain": 1, "wide": 4}
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
 _DEVICE_OK: Dict[int, bool] = {}
@@ -219,6 +219,7 @@ def voxelize(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, 
     nb = frame_offsets.numel() - 1
     c_point = stride - col0 if c_point is None else c_point
     cap = min(n, nb * grid.max_voxels) if capacity is None else capacity
+    cap = max(int(cap), 1)
     dev = points.device
     g = grid.native()
     out = PillarsOutputs()
@@ -392,6 +393,7 @@ class EncodeBuffers:
     def __init__(self, n_points: int, n_frames: int, grid: GridSpec, f_out: int, device, *, with_bev: bool = True,
                  capacity: Optional[int] = None, ws_slot: int = 0, bev_dtype: torch.dtype = torch.float32):
         cap = min(n_points, n_frames * grid.max_voxels) if capacity is None else capacity
+        cap = max(int(cap), 1)  # an empty batch still needs non-NULL output pointers
         nx, ny, nz = grid.grid_size
         self.capacity = cap
         self.pillar_features = torch.empty((cap, f_out), dtype=torch.float32, device=device)
