@@ -284,6 +284,11 @@ int pillars_set_scatter_stream(void *stream, int enable);
  * either choice. */
 int pillars_set_grouping(int mode);
 
+/* Measurement hook (thread-local): a zeroed device buffer of 32 uint64 that the grouping / feature kernels of subsequent calls
+ * stamp with %globaltimer nanoseconds per phase (even slot: earliest stamp, stored complemented; odd slot: latest stamp);
+ * NULL switches it off.  profiles/scripts/phase_times.py decodes it. */
+int pillars_set_debug_times(void *buffer32);
+
 /* Test / measurement hook: non-zero makes pillars_encode_bev ignore the host weight copies and run the generic feature
  * kernel (thread-local). */
 int pillars_force_generic_features(int on);

@@ -26,6 +26,9 @@ static void stage_mark(int i, cudaStream_t st)
 
 void note_launch(int n) { g_launches += n; }
 
+static thread_local unsigned long long *g_dbg_times = nullptr;
+unsigned long long *debug_times_ptr() { return g_dbg_times; }
+
 int current_sm_count()
 {
     static thread_local int cache[64] = {0};
@@ -150,6 +153,12 @@ int pillars_set_scatter_stream(void *stream, int enable)
 {
     g_scatter_stream = static_cast<cudaStream_t>(stream);
     g_scatter_stream_on = enable != 0;
+    return 0;
+}
+
+int pillars_set_debug_times(void *buffer32)
+{
+    g_dbg_times = static_cast<unsigned long long *>(buffer32);
     return 0;
 }
 

@@ -247,6 +247,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// ---- measurement hook: nanosecond stamps of kernel phases (pillars_set_debug_times) --------------------------------------
+// `dbg` is NULL in normal operation.  Even slots keep the EARLIEST stamp of a phase (stored complemented, so that a zeroed
+// buffer works with atomicMax), odd slots the LATEST.
+#ifdef __CUDACC__
+__device__ __forceinline__ void dbg_stamp(unsigned long long *dbg, int slot)
+{
+    if (!dbg) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(dbg + slot, (slot & 1) ? t : ~t);
+}
+#endif
+unsigned long long *debug_times_ptr();
+
 // launch bookkeeping (api.cu)
 void note_launch(int n = 1);
 // SM count of the calling thread's current device (cached per device)

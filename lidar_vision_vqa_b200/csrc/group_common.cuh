@@ -116,6 +116,7 @@ struct PlaceParams {
     float vsz[3], off[3];
     int32_t *voxel_coords, *voxel_num_points, *cell_row;
     int64_t capacity;
+    unsigned long long *dbg;
 };
 
 inline PlaceParams make_place_params(const float *points, int64_t n, int stride, int col0, int c_point, const GridDev &gd,
@@ -151,6 +152,7 @@ inline PlaceParams make_place_params(const float *points, int64_t n, int stride,
     pp.voxel_num_points = extras.records ? extras.voxel_num_points : nullptr;
     pp.cell_row = extras.records && extras.write_cell_row ? ws.cell_row : nullptr;
     pp.capacity = extras.capacity;
+    pp.dbg = debug_times_ptr();
     return pp;
 }
 

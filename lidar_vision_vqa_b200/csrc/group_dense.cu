@@ -5,9 +5,9 @@
 // cells for 0.5 M points), so the "hash table" can be the identity: one 8-byte entry per (frame, cell), split into two
 // 4-byte planes that a single 0xFF memset initialises and that stay L2 resident.
 //
-//   k_insert_dense   coalesced tile loads -> fp32 sub/div/floor -> key = frame * cells + cell.  __match_any_sync merges the
-//                    lanes of a warp that hit the same cell; the leader issues ONE atomicAdd on the count plane (returns
-//                    the arrival rank of the group) and one fire-and-forget atomicMin on the first-index plane.  No
+//   k_insert_dense   coalesced tile loads -> fp32 sub/div/floor -> key = frame * cells + cell.  Adjacent lanes that hit the
+//                    same cell (unshuffled sweeps) are merged; the run's first lane issues ONE atomicAdd on the count plane
+//                    (returns the arrival rank of the run) and one fire-and-forget atomicMin on the first-index plane.  No
 //                    probing, no CAS loop, no key compare: one dependent L2 round trip per point instead of two or more.
 //                    The claim of an empty cell also counts the frame's pillars (one atomic per CTA), so the scan kernel
 //                    knows every frame's row base before it starts.
@@ -30,23 +30,43 @@ constexpr int kScanPer = kTile / kScanThreads;  // 2
 constexpr uint32_t kBaseTag = 0x80000000u;
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// 0xFF fill of the cell table (+ counters and scan descriptors in front of it).  A kernel rather than a memset so that the
+// insert kernel can be launched behind it programmatically: its CTAs load and quantise their points while the fill drains.
+__global__ void __launch_bounds__(256) k_fill_ff(uint4 *__restrict__ dst, size_t n_vec, unsigned long long *dbg)
+{
+    pdl_trigger();
+    if (threadIdx.x == 0) dbg_stamp(dbg, 0);
+    const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) dst[i] = ff;
+    if (threadIdx.x == 0) dbg_stamp(dbg, 1);
+}
+
+constexpr int kInsPer = 2;                          // points per thread: two independent atomic round trips in flight
+constexpr int kInsTile = kGroupThreads * kInsPer;   // points per CTA
+
 __global__ void __launch_bounds__(kGroupThreads, 8)
 k_insert_dense(const float *__restrict__ points, int64_t n, int stride, int col0, const int32_t *__restrict__ frame_offsets,
                int nb, GridDev gd, uint32_t *__restrict__ cell_first, uint32_t *__restrict__ cell_cnt,
                int32_t *__restrict__ point_key, uint32_t *__restrict__ point_arrival, uint32_t *__restrict__ frame_new,
-               int vec_ok)
+               int vec_ok, unsigned long long *dbg)
 {
-    extern __shared__ __align__(16) float s_pts[];  // [kGroupThreads * stride]
+    extern __shared__ __align__(16) float s_pts[];  // [kInsTile * stride]
     __shared__ uint32_t s_cnt[2];
     __shared__ uint32_t s_claims;
 
     pdl_trigger();  // the scan kernel may start taking SMs as this grid's CTAs retire
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kGroupThreads;
-    const int count = static_cast<int>(tmin<int64_t>(kGroupThreads, n - tile_start));
+    const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kInsTile;
+    const int count = static_cast<int>(tmin<int64_t>(kInsTile, n - tile_start));
     if (tid < 2) s_cnt[tid] = 0u;
     if (tid == 2) s_claims = 0u;
+    if (tid == 0) {
+        dbg_stamp(dbg, 2);
+        dbg_stamp(dbg, 25);  // latest CTA start
+    }
     __syncthreads();
+    // (the points and the frame offsets are inputs of the call: no dependency on the fill kernel yet)
     load_point_tile(points + tile_start * stride, count, stride, vec_ok, s_pts, tid, kGroupThreads);
     {  // frames touched by this tile: [b0, b1] = (frame starts <= first / last point of the tile) - 1; independent loads
         uint32_t c_lo, c_hi;
@@ -55,54 +75,72 @@ k_insert_dense(const float *__restrict__ points, int64_t n, int stride, int col0
         if (c_hi) atomicAdd(&s_cnt[1], c_hi);
     }
     __syncthreads();
+    if (tid == 0) dbg_stamp(dbg, 27);  // latest tile loaded
     const int s_b0 = static_cast<int>(s_cnt[0]) - 1, s_b1 = static_cast<int>(s_cnt[1]) - 1;
 
-    const int64_t i = tile_start + tid;
-    bool valid = false;
-    uint32_t key = 0;
-    int b = s_b0;
-    if (tid < count) {
-        uint32_t cell = 0;
-        valid = quantize_point(s_pts + tid * stride + col0, gd, cell);
-        if (valid) {
-            const int b1 = s_b1;
-            while (b < b1 && __ldg(frame_offsets + b + 1) <= i) ++b;
-            key = static_cast<uint32_t>(b) * gd.cells + cell;
+    bool valid[kInsPer];
+    uint32_t key[kInsPer];
+    int fb[kInsPer];
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) {
+        const int t = tid + k * kGroupThreads;  // consecutive lanes hold consecutive points in every round
+        valid[k] = false;
+        key[k] = 0;
+        fb[k] = s_b0;
+        if (t < count) {
+            uint32_t cell = 0;
+            valid[k] = quantize_point(s_pts + t * stride + col0, gd, cell);
+            if (valid[k]) {
+                const int64_t i = tile_start + t;
+                while (fb[k] < s_b1 && __ldg(frame_offsets + fb[k] + 1) <= i) ++fb[k];
+                key[k] = static_cast<uint32_t>(fb[k]) * gd.cells + cell;
+            }
         }
     }
-    const unsigned active = __ballot_sync(kFullMask, valid);
-    int32_t key_out = -1;
-    uint32_t arrival = 0;
-    bool claimed = false;
-    if (valid) {
-        const unsigned peers = __match_any_sync(active, key);
-        const int leader = __ffs(peers) - 1;  // lowest lane == smallest point index of the group
-        uint32_t base = 0;
-        if (lane == leader) {
-            // count plane holds "points - 1" (0xFFFFFFFF = empty): the returned value + 1 is the group's arrival rank
-            const uint32_t old = atomicAdd(&cell_cnt[key], static_cast<uint32_t>(__popc(peers)));
-            atomicMin(&cell_first[key], static_cast<uint32_t>(i));
-            claimed = old == 0xFFFFFFFFu;
-            base = old + 1u;
+    if (tid == 0) dbg_stamp(dbg, 3);  // tile loaded and quantised
+    pdl_wait();  // the table must be filled before the first atomic
+    if (tid == 0) dbg_stamp(dbg, 4);  // (earliest) fill complete
+    // Lanes hold consecutive points, so an unshuffled sweep puts the points of a cell on ADJACENT lanes: runs of equal keys
+    // are merged (one atomic per run; two shuffles and a ballot -- __match_any_sync would also merge non-adjacent
+    // duplicates, but costs ~3 us per call on the MIO path and a shuffled sweep has next to none).
+    int head_lane[kInsPer];
+    uint32_t old[kInsPer];
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) {  // both rounds' atomics are issued before either result is used
+        const uint32_t kk = valid[k] ? key[k] : 0xFFFFFFFFu - static_cast<uint32_t>(lane);  // invalid lanes: unique keys
+        const uint32_t prev = __shfl_up_sync(kFullMask, kk, 1);
+        const unsigned heads = __ballot_sync(kFullMask, lane == 0 || kk != prev);
+        head_lane[k] = 31 - __clz(heads & (lanemask_lt() | (1u << lane)));
+        const unsigned above = head_lane[k] == 31 ? 0u : heads & ~((2u << head_lane[k]) - 1u);
+        const int run = (above ? __ffs(above) - 1 : 32) - head_lane[k];
+        old[k] = 0;
+        if (valid[k] && lane == head_lane[k]) {  // lowest lane == smallest point index of the run
+            // count plane holds "points - 1" (0xFFFFFFFF = empty): the returned value + 1 is the run's arrival rank
+            old[k] = atomicAdd(&cell_cnt[key[k]], static_cast<uint32_t>(run));
+            atomicMin(&cell_first[key[k]], static_cast<uint32_t>(tile_start + tid + k * kGroupThreads));
         }
-        base = __shfl_sync(peers, base, leader);
-        arrival = base + static_cast<uint32_t>(__popc(peers & lanemask_lt()));
-        key_out = static_cast<int32_t>(key);
     }
-    // pillars opened per frame: one atomic per CTA when the tile lies inside one frame (the rule), else one per claim
     const bool one_frame = s_b0 == s_b1;
-    const unsigned cl = __ballot_sync(kFullMask, claimed);
-    if (one_frame) {
-        if (lane == 0 && cl) atomicAdd(&s_claims, static_cast<uint32_t>(__popc(cl)));
-    } else if (claimed) {
-        atomicAdd(&frame_new[b], 1u);
-    }
-    if (tid < count) {
-        point_key[i] = key_out;
-        point_arrival[i] = arrival;
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) {
+        const int t = tid + k * kGroupThreads;
+        const uint32_t head_old = __shfl_sync(kFullMask, old[k], head_lane[k]);
+        const bool claimed = valid[k] && lane == head_lane[k] && old[k] == 0xFFFFFFFFu;
+        // pillars opened per frame: one atomic per CTA when the tile lies inside one frame (the rule), else one per claim
+        const unsigned cl = __ballot_sync(kFullMask, claimed);
+        if (one_frame) {
+            if (lane == 0 && cl) atomicAdd(&s_claims, static_cast<uint32_t>(__popc(cl)));
+        } else if (claimed) {
+            atomicAdd(&frame_new[fb[k]], 1u);
+        }
+        if (t < count) {
+            point_key[tile_start + t] = valid[k] ? static_cast<int32_t>(key[k]) : -1;
+            point_arrival[tile_start + t] = head_old + 1u + static_cast<uint32_t>(lane - head_lane[k]);
+        }
     }
     __syncthreads();
     if (one_frame && tid == 0 && s_claims) atomicAdd(&frame_new[s_b0], s_claims);
+    if (tid == 0) dbg_stamp(dbg, 5);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -167,6 +205,7 @@ struct ScanDenseParams {
     int sh_cells, sh_cells_xy, sh_nx;
     int64_t capacity;
     int write_lists, write_meta;
+    unsigned long long *dbg;
 };
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_constant__ ScanDenseParams p)
@@ -178,8 +217,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
     __shared__ uint32_t s_gstart[kMaxFrames + 1], s_rowbase[kMaxFrames + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_wait();     // everything below reads what the insert kernel (and the memset before it) wrote
+    if (tid == 0) dbg_stamp(p.dbg, 6);   // CTA resident
+    pdl_wait();     // everything below reads what the insert kernel (and the fill before it) wrote
     pdl_trigger();
+    if (tid == 0) dbg_stamp(p.dbg, 7);   // (latest) insert kernel complete
+    if (tid == 0) dbg_stamp(p.dbg, 8);   // (earliest) insert kernel complete
     // A tile spins on its predecessors, so they must be running: ids are handed out in scheduling order.
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1u) + 1u;
 
@@ -262,6 +304,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
     }
     unsigned long long tile_sum;
     const unsigned long long thr_excl = block_scan_excl<kWarps>(tsum, s_warp, lane, warp, tile_sum);
+    if (tid == 0) dbg_stamp(p.dbg, 9);   // gathers done, tile scanned
     if (tid == 0) st_relaxed_u64(&p.tile_agg[tile], pack_desc(tile_sum));  // visible to the successors at once
 
     // look-back: aggregates of the tiles of my group that precede me (one parallel read) + prefix of the previous group
@@ -279,6 +322,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
     if (tid == 0 && (tile & (kLookGroup - 1)) == kLookGroup - 1)
         st_relaxed_u64(&p.tile_prefix[tile], pack_desc(tile_excl + tile_sum));
 
+    if (tid == 0) dbg_stamp(p.dbg, 11);  // look-back resolved
     unsigned long long run = tile_excl + thr_excl;
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
 #pragma unroll
@@ -314,22 +358,36 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
     }
     if (tile == p.n_tiles - 1 && tid == 0)
         p.hdr->total_listed = static_cast<uint32_t>((tile_excl + tile_sum) & 0xFFFFFFFFull);
+    if (tid == 0) dbg_stamp(p.dbg, 13);
 }
 
 __global__ void __launch_bounds__(kGroupThreads) k_place_dense(const __grid_constant__ PlaceParams p)
 {
+    if (threadIdx.x == 0) dbg_stamp(p.dbg, 14);
     pdl_wait();
     pdl_trigger();
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * kGroupThreads + threadIdx.x;
-    if (i >= p.n) return;
-    const int32_t key = p.point_slot[i];
-    if (key < 0) return;
-    const uint32_t arrival = p.point_arrival[i];
-    const uint32_t base = __ldg(p.cell_first + key) & ~kBaseTag;
-    const uint32_t pos = base + arrival;
-    if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i);
-    if (!p.records) return;
-    write_record(p, i, decode_key(p, static_cast<uint32_t>(key)), pos, arrival);
+    if (threadIdx.x == 0) dbg_stamp(p.dbg, 16);
+    // two points per thread: both (key -> list base) gathers are in flight before either record is written
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kInsTile + threadIdx.x;
+    int32_t key[kInsPer];
+    uint32_t arrival[kInsPer], base[kInsPer];
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) {
+        const int64_t i = i0 + k * kGroupThreads;
+        key[k] = i < p.n ? p.point_slot[i] : -1;
+        arrival[k] = i < p.n ? p.point_arrival[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) base[k] = key[k] >= 0 ? (__ldg(p.cell_first + key[k]) & ~kBaseTag) : 0u;
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) {
+        if (key[k] < 0) continue;
+        const int64_t i = i0 + k * kGroupThreads;
+        const uint32_t pos = base[k] + arrival[k];
+        if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i);
+        if (p.records) write_record(p, i, decode_key(p, static_cast<uint32_t>(key[k])), pos, arrival[k]);
+    }
+    if (threadIdx.x == 0) dbg_stamp(p.dbg, 17);
 }
 
 }  // namespace
@@ -340,10 +398,14 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
                                       cudaStream_t st)
 {
     cudaError_t err;
-    // ONE memset per call: tile counter, per-frame pillar counters, scan descriptors and both planes of the cell table all
+    // ONE fill per call: tile counter, per-frame pillar counters, scan descriptors and both planes of the cell table all
     // start from 0xFF bytes (counters count up from -1, a descriptor is ready once bit 63 is clear).
-    if ((err = cudaMemsetAsync(ws.ff_begin, 0xFF, ws.ff_bytes, st)) != cudaSuccess) return err;
-    note_launch();
+    {
+        const size_t n_vec = ws.ff_bytes / 16;  // every piece of the region is 256-byte aligned
+        const unsigned fb = static_cast<unsigned>(tmin<size_t>((n_vec + 255) / 256, static_cast<size_t>(current_sm_count()) * 8));
+        k_fill_ff<<<fb, 256, 0, st>>>(reinterpret_cast<uint4 *>(ws.ff_begin), n_vec, debug_times_ptr());
+        note_launch();
+    }
     if (n == 0) {
         if (pillar_count) {
             if ((err = cudaMemsetAsync(pillar_count, 0, sizeof(int32_t) * (nb + 1), st)) != cudaSuccess) return err;
@@ -351,12 +413,13 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
         }
         return cudaSuccess;
     }
-    const size_t smem = sizeof(float) * kGroupThreads * stride;
-    const int vec_ok = (reinterpret_cast<uintptr_t>(points) % 16 == 0) ? 1 : 0;  // tile starts are 256 rows apart
-    const unsigned pb = static_cast<unsigned>((n + kGroupThreads - 1) / kGroupThreads);
-    k_insert_dense<<<pb, kGroupThreads, smem, st>>>(points, n, stride, col0, frame_offsets, nb, gd, ws.cell_first,
-                                                    reinterpret_cast<uint32_t *>(ws.cell_row), ws.point_slot,
-                                                    ws.point_arrival, ws.frame_new, vec_ok);
+    const size_t smem = sizeof(float) * kInsTile * stride;
+    const int vec_ok = (reinterpret_cast<uintptr_t>(points) % 16 == 0) ? 1 : 0;  // tile starts are 512 rows apart
+    const unsigned pb = static_cast<unsigned>((n + kInsTile - 1) / kInsTile);
+    if ((err = launch_pdl(k_insert_dense, dim3(pb), dim3(kGroupThreads), smem, st, points, n, stride, col0, frame_offsets, nb,
+                          gd, ws.cell_first, reinterpret_cast<uint32_t *>(ws.cell_row), ws.point_slot, ws.point_arrival,
+                          ws.frame_new, vec_ok, debug_times_ptr())) != cudaSuccess)
+        return err;
     note_launch();
 
     const PlaceParams pp = make_place_params(points, n, stride, col0, c_point, gd, ws, want_index_lists, extras);
@@ -390,6 +453,7 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     sp.capacity = extras.records ? extras.capacity : (1ll << 62);
     sp.write_lists = want_index_lists ? 1 : 0;
     sp.write_meta = extras.records ? 1 : 0;
+    sp.dbg = debug_times_ptr();
     if ((err = launch_pdl(k_scan_dense, dim3(ws.n_tiles), dim3(kScanThreads), 0, st, sp)) != cudaSuccess) return err;
     note_launch();
     if (want_index_lists || extras.records) {

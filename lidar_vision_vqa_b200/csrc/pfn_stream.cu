@@ -63,6 +63,7 @@ struct WalkParams {
     float vsz[3], off[3];
     float fx_scale[3], fx_inv[3];  // fixed-point scale of the mean sums per axis (a power of two) and its inverse
     int idx_bits;
+    unsigned long long *dbg;
 };
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2) ------------------------------------------------------------
@@ -392,8 +393,10 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     __shared__ __align__(16) unsigned char s_all[kWarps * kWarpSmem];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) dbg_stamp(p.dbg, 18);
     pdl_wait();  // records, pillar entries and the list header come from the grouping kernels
     pdl_trigger();
+    if (threadIdx.x == 0) dbg_stamp(p.dbg, 20);
     const uint32_t total = __ldcg(&p.hdr->total_listed);
     const uint32_t n_chunks = (total + 31u) >> 5;
     const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * kWarpSmem;
@@ -534,7 +537,9 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         if (++cur >= c_end) break;
         buf ^= 1u;
     }
+    if (lane == 0) dbg_stamp(p.dbg, 21);  // chunks done
     drain_long_pillars(p, s_pl, out_lane, lane);
+    if (lane == 0) dbg_stamp(p.dbg, 23);
 }
 
 // ---- folding of the layer's weights (once per model: pillars_fold_pfn) ------------------------------------------------
@@ -591,6 +596,7 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     p.sh_cells_xy = log2_exact(gd.cells_xy);
     p.sh_nx = log2_exact(static_cast<uint32_t>(gd.g[0]));
     p.idx_bits = job.idx_bits;
+    p.dbg = debug_times_ptr();
     const int window = gd.max_points < 32 ? gd.max_points : 32;  // points that can enter one sum
     for (int k = 0; k < 3; ++k) {
         p.vsz[k] = job.vsz[k];

@@ -13,6 +13,8 @@
 // profiles/r01_scatter_variants.md.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pillars {
@@ -325,8 +327,11 @@ cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, 
         constexpr int bs = 128, chan = 8;
         const int tpp = static_cast<int>((plane + bs * 8 - 1) / (bs * 8));
         const unsigned grid = static_cast<unsigned>(nb) * tpp * (f / chan);
-        const cudaError_t err = launch_pdl(k_scatter_wide<false, 8>, dim3(grid), dim3(bs), 0, st, feats, cell_row, f, plane,
-                                           tpp, chan, 0, bev);
+        static const bool cs = getenv("PILLARS_SCATTER_CS") != nullptr;
+        const cudaError_t err = cs ? launch_pdl(k_scatter_wide<true, 8>, dim3(grid), dim3(bs), 0, st, feats, cell_row, f, plane,
+                                                tpp, chan, 0, bev)
+                                   : launch_pdl(k_scatter_wide<false, 8>, dim3(grid), dim3(bs), 0, st, feats, cell_row, f,
+                                                plane, tpp, chan, 0, bev);
         if (err != cudaSuccess) return err;
     } else if (vec_ok) {
         const int tpp = static_cast<int>((plane + kThreads * 4 - 1) / (kThreads * 4));

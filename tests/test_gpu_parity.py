@@ -930,3 +930,23 @@ def test_fused_path_on_empty_batches(grouping, dev, L, oracle):
     bd = vfe({"points": torch.zeros((0, 6), device=dev), "batch_size": 2})
     assert bd["pillar_features"].shape == (0, 64) and bd["voxel_coords"].shape == (0, 4)
     assert bd["spatial_features"].shape == (2, 64, 64, 64) and not bool(bd["spatial_features"].any())
+
+
+def test_grouping_unshuffled_sweeps(grouping, dev, L, oracle):
+    """Sweeps in firing order (no shuffle_points): consecutive points fall into the same pillar, which is the case the
+    in-warp merging of the insert kernels exists for (one atomic per run of equal cells)."""
+    rng, vs, p, mv = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), (0.8, 0.8, 8.0), 6, 4000
+    frames = [synth.make_sweep(40 + b, synth.NUSCENES_32, 5, shuffle=False) for b in range(3)]
+    offs = np.zeros(4, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    pts = np.concatenate(frames, 0)
+    grid = L.GridSpec.from_range(rng, vs, p, mv)
+    got = _trim(L.ops.voxelize(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid, want_voxels=True,
+                               want_membership=True))
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    assert ref["num_points"].max() == p
+    np.testing.assert_array_equal(got["voxel_coords"], ref["coords"])
+    np.testing.assert_array_equal(got["voxel_num_points"], ref["num_points"])
+    np.testing.assert_array_equal(got["point_pillar"], ref["point_voxel"])
+    np.testing.assert_array_equal(got["point_slot"], ref["point_slot"])
+    np.testing.assert_array_equal(got["voxels"], ref["voxels"])
