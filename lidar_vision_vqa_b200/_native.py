@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "pillars_force_generic_features",
     "pillars_set_grouping",
     "pillars_set_debug_times",
+    "pillars_rebase_segments",
     "pillars_set_scatter_stream",
     "pillars_pfn_stack_in_features",
     "pillars_pfn_dense_stack",
@@ -148,6 +149,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_workspace_cell_row_offset.argtypes = [c_int64, c_int32, POINTER(PillarsGrid)]
     lib.pillars_set_scatter_stream.restype = c_int
     lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
+    lib.pillars_rebase_segments.restype = c_int
+    lib.pillars_rebase_segments.argtypes = [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_void_p]
     lib.pillars_set_debug_times.restype = c_int
     lib.pillars_set_debug_times.argtypes = [c_void_p]
     lib.pillars_set_grouping.restype = c_int

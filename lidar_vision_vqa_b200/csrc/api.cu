@@ -545,6 +545,21 @@ int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_i
     return 0;
 }
 
+int pillars_rebase_segments(int32_t *coords, int32_t n_segments, int64_t rows_per_segment, const int32_t *segment_counts,
+                            int32_t count_stride, int32_t frames_per_segment, void *stream)
+{
+    g_launches = 0;
+    if (n_segments < 0 || rows_per_segment < 0 || count_stride < 1 || frames_per_segment < 0)
+        return fail(PILLARS_E_BADARG, "pillars_rebase_segments: bad size");
+    if (static_cast<int64_t>(n_segments) * rows_per_segment > 0 && (!coords || !segment_counts))
+        return fail(PILLARS_E_BADARG, "pillars_rebase_segments: NULL pointer");
+    cudaError_t e = launch_rebase_segments(coords, n_segments, rows_per_segment, segment_counts, count_stride,
+                                           frames_per_segment, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "rebase_segments");
+    g_launches_last = g_launches;
+    return 0;
+}
+
 int pillars_scatter_bev_half(const float *feats, const void *coords, int32_t coords_is_float, int64_t m,
                              const int32_t *m_dev, int32_t n_frames, int32_t f, int32_t nx, int32_t ny, int32_t nz,
                              void *bev_half, void *workspace, size_t workspace_bytes, void *stream)

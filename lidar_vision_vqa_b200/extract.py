@@ -31,21 +31,35 @@ from .pipeline import PillarEncoderPipeline
 
 class BevExtractor:
     def __init__(self, vfe: PillarVFEFromPoints, batch_size: int, max_points_per_frame: int, depth: int = 3,
-                 out_dtype: torch.dtype = torch.float16):
+                 out_dtype: torch.dtype = torch.float16, ship: str = "dense"):
+        """``ship='dense'``: the float16 canvas crosses the host link (32 MiB per 512^2 frame), which is what the reference
+        stores.  ``ship='compact'``: only the occupied cells cross it -- float16 pillar rows ``[M, F]`` + int16 ``(y, x)``
+        ``[M, 2]`` per frame (~1.8 MB per frame at cfg2) -- and ``run`` yields ``(token, (rows, yx))``;
+        :func:`densify_compact` rebuilds the identical canvas on the consumer's side."""
+        if ship not in ("dense", "compact"):
+            raise ValueError("ship must be 'dense' or 'compact'")
+        self.ship = ship
         self.vfe = vfe
         self.batch_size = int(batch_size)
         self.depth = max(2, int(depth))
         self.c = vfe.num_raw_point_features
         self.max_points = int(max_points_per_frame) * self.batch_size
         self.pipe = PillarEncoderPipeline(vfe, n_frames=self.batch_size, max_points=self.max_points, depth=self.depth,
-                                          bev_dtype=out_dtype)
+                                          bev_dtype=out_dtype, with_bev=ship == "dense")
+        self.d2h_bytes_last = 0
         # pinned staging: collated points in, canvases out (one pair per pipeline slot)
         self._pts = [torch.empty((self.max_points, self.c + 1), dtype=torch.float32).pin_memory()
                      for _ in range(self.depth)]
         nx, ny, nz = vfe.grid.grid_size
         f = vfe.get_output_feature_dim()
-        self._bev = [torch.empty((self.batch_size, f * nz, ny, nx), dtype=out_dtype).pin_memory()
-                     for _ in range(self.depth)]
+        self._bev = self._rows = self._yx = None
+        if ship == "dense":
+            self._bev = [torch.empty((self.batch_size, f * nz, ny, nx), dtype=out_dtype).pin_memory()
+                         for _ in range(self.depth)]
+        else:
+            cap = self.pipe.slots[0].buffers.capacity
+            self._rows = [torch.empty((cap, f), dtype=torch.float16).pin_memory() for _ in range(self.depth)]
+            self._yx = [torch.empty((cap, 2), dtype=torch.int16).pin_memory() for _ in range(self.depth)]
         self._copied = [torch.cuda.Event() for _ in range(self.depth)]
 
     def _collate(self, frames: Sequence[np.ndarray], slot: int) -> torch.Tensor:
@@ -76,13 +90,31 @@ class BevExtractor:
         def collect():
             ticket, tokens, s = pending.pop(0)
             res = self.pipe.result(ticket)
-            with torch.cuda.stream(self.pipe.slots[ticket % len(self.pipe.slots)].stream):
-                self._bev[s].copy_(res["spatial_features"], non_blocking=True)
+            stream = self.pipe.slots[ticket % len(self.pipe.slots)].stream
+            if self.ship == "dense":
+                with torch.cuda.stream(stream):
+                    self._bev[s].copy_(res["spatial_features"], non_blocking=True)
+                    self._copied[s].record()
+                self._copied[s].synchronize()
+                self.d2h_bytes_last = self._bev[s].numel() * self._bev[s].element_size()
+                arr = self._bev[s].numpy()
+                for i, tok in enumerate(tokens):
+                    yield tok, arr[i]
+                return
+            counts = res["pillars_per_frame"].numpy()
+            m = int(counts.sum())
+            with torch.cuda.stream(stream):  # (the casts are plain dtype conversions of the rows that cross the link)
+                self._rows[s][:m].copy_(res["pillar_features"].to(torch.float16), non_blocking=True)
+                self._yx[s][:m].copy_(res["voxel_coords"][:, 2:4].to(torch.int16), non_blocking=True)
                 self._copied[s].record()
             self._copied[s].synchronize()
-            arr = self._bev[s].numpy()
+            self.d2h_bytes_last = m * (self._rows[s].shape[1] * 2 + 4)
+            rows, yx = self._rows[s].numpy(), self._yx[s].numpy()
+            lo = 0
             for i, tok in enumerate(tokens):
-                yield tok, arr[i]
+                hi = lo + int(counts[i])
+                yield tok, (rows[lo:hi], yx[lo:hi])
+                lo = hi
 
         def flush():
             nonlocal slot, batch_tokens, batch_frames
@@ -105,11 +137,21 @@ class BevExtractor:
         while pending:
             yield from collect()
 
+    @staticmethod
+    def densify_compact(rows: np.ndarray, yx: np.ndarray, ny: int, nx: int) -> np.ndarray:
+        """The ``[C, H, W]`` float16 map of one frame from its compact form (consumer side, numpy)."""
+        bev = np.zeros((rows.shape[1], ny, nx), dtype=np.float16)
+        bev[:, yx[:, 0].astype(np.int64), yx[:, 1].astype(np.int64)] = rows.T
+        return bev
+
     def run_to_dir(self, items: Iterable[Tuple[str, np.ndarray]], out_dir: str) -> int:
         """``np.save(<out_dir>/<token>.npy, bev)`` per sample, float16 ``[C, H, W]`` (precompute_bev_features.py:391-395)."""
         os.makedirs(out_dir, exist_ok=True)
         n = 0
+        nx, ny, _ = self.vfe.grid.grid_size
         for tok, bev in self.run(items):
+            if self.ship == "compact":
+                bev = self.densify_compact(bev[0], bev[1], ny, nx)
             np.save(os.path.join(out_dir, f"{tok}.npy"), bev)
             n += 1
         return n

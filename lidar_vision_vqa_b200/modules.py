@@ -213,7 +213,22 @@ class PillarVFEFromPoints(_PillarVFEBase):
     ``FUSE_SCATTER`` also ``spatial_features`` (the scatter then becomes a no-op).
 
     Extra model_cfg keys (all optional): MAX_POINTS_PER_VOXEL (32), MAX_NUMBER_OF_VOXELS (40000, int or
-    {'train','test'}), FUSE_SCATTER (False), SCATTER_VARIANT ('auto')."""
+    {'train','test'}), FUSE_SCATTER (False), SCATTER_VARIANT ('auto'), SYNC_COUNTS (True), OUTPUT_RING (0).
+
+    ``SYNC_COUNTS: False`` removes the call's only host synchronisation: the per-pillar outputs then keep their CAPACITY
+    (rows beyond the pillar count are undefined), and the counts stay on the
+    device as ``batch_dict['pillar_count'] [B+1] int32`` (per frame, total last).  ``PointPillarScatter`` and the BEV
+    tokeniser honour that count; with ``FUSE_SCATTER`` the canvas is already complete.  The default (True) reads the counts
+    back and returns exactly the reference's shapes -- the reference itself synchronises at the same place
+    (pointpillar_scatter.py:17).
+
+    ``OUTPUT_RING: n`` (n > 0) makes the module own ``n`` sets of output buffers + workspace and hand them out round-robin
+    instead of allocating fresh tensors per call: the outputs of call k stay valid until call k + n (issue those two calls on
+    the same stream, or synchronise in between).  This is what a streaming extractor wants -- the canvas alone is 1 GiB per
+    call at cfg2 -- and it is the configuration `bench.py` times end to end.
+
+    Optional input key ``points_frame_offsets`` (``[B+1]`` int32, host or device): ``points`` is then the PACKED ``[N, C]``
+    layout without the frame-index column (17 % fewer host->device bytes at C = 5)."""
 
     def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size, **kwargs):
         super().__init__(model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size, **kwargs)
@@ -221,19 +236,45 @@ class PillarVFEFromPoints(_PillarVFEBase):
         self.max_voxels = _mode_value(_cfg_get(model_cfg, "MAX_NUMBER_OF_VOXELS", 40000), training=False)
         self.fuse_scatter = bool(_cfg_get(model_cfg, "FUSE_SCATTER", False))
         self.scatter_variant = str(_cfg_get(model_cfg, "SCATTER_VARIANT", "auto"))
+        self.sync_counts = bool(_cfg_get(model_cfg, "SYNC_COUNTS", True))
+        self.output_ring = int(_cfg_get(model_cfg, "OUTPUT_RING", 0))
+        self._ring, self._ring_next = [], 0
         self.grid = ops.GridSpec(self.point_cloud_range, self.voxel_size, self.grid_size, self.max_points,
                                  self.max_voxels)
 
     def forward(self, batch_dict, **kwargs):
         points = _points_on_device(batch_dict["points"])
         batch_size = int(batch_dict["batch_size"])
-        offs = ops.frame_offsets_from_points(points, batch_size)
+        packed_offs = batch_dict.get("points_frame_offsets")
+        if packed_offs is not None:  # packed [N, C] rows + explicit offsets instead of the frame-index column
+            offs = torch.as_tensor(packed_offs, dtype=torch.int32)
+            if not offs.is_cuda:
+                offs = offs.to(points.device, non_blocking=True)
+            if offs.numel() != batch_size + 1:
+                raise ValueError("points_frame_offsets must have batch_size + 1 entries")
+            col0 = 0
+        else:
+            offs = ops.frame_offsets_from_points(points, batch_size)
+            col0 = 1
         if self._single_layer():
-            res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=1,
+            buffers = None
+            if self.output_ring > 0:
+                buffers = self._ring_buffers(points.shape[0], batch_size, points.device)
+            res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=col0, buffers=buffers,
                                  with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
         else:
-            res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=1,
+            res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=col0,
                                    with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
+        if self.fuse_scatter:
+            batch_dict["spatial_features"] = res["bev"]
+            batch_dict["_b200_scatter_done"] = True
+        batch_dict["pillar_count"] = res["pillar_count"]  # device, [B+1]
+        if not self.sync_counts:
+            # no host synchronisation: capacity-sized outputs, rows beyond the device-side count are padding
+            batch_dict["voxel_features"] = batch_dict["pillar_features"] = res["pillar_features"]
+            batch_dict["voxel_coords"] = res["voxel_coords"]
+            batch_dict["voxel_num_points"] = res["voxel_num_points"]
+            return batch_dict
         # the one host sync of the call: per-frame pillar counts (B+1 ints) size the returned views
         # (the reference syncs at the same place for the batch size, pointpillar_scatter.py:17)
         counts = res["pillar_count"].cpu()
@@ -244,10 +285,23 @@ class PillarVFEFromPoints(_PillarVFEBase):
         batch_dict["voxel_coords"] = res["voxel_coords"][:m]
         batch_dict["voxel_num_points"] = res["voxel_num_points"][:m]
         batch_dict["pillars_per_frame"] = counts[:-1]  # host tensor
-        if self.fuse_scatter:
-            batch_dict["spatial_features"] = res["bev"]
-            batch_dict["_b200_scatter_done"] = True
         return batch_dict
+
+
+    def _ring_buffers(self, n_points: int, batch_size: int, device) -> "ops.EncodeBuffers":
+        """OUTPUT_RING: the next of ``n`` module-owned buffer sets, grown when a batch has more points than any before."""
+        if len(self._ring) != self.output_ring:
+            self._ring = [None] * self.output_ring
+        i = self._ring_next % self.output_ring
+        self._ring_next += 1
+        b = self._ring[i]
+        if b is None or b.n_points < n_points or b.n_frames != batch_size or b.pillar_features.device != device \
+                or (b.bev is None) != (not self.fuse_scatter):
+            cap_points = int(n_points * 1.1) + 1024
+            b = ops.EncodeBuffers(cap_points, batch_size, self.grid, int(self.num_filters[-1]), device,
+                                  with_bev=self.fuse_scatter)
+            self._ring[i] = b
+        return b
 
 
 class DynamicPillarVFE(_PillarVFEBase):
@@ -347,7 +401,11 @@ class PointPillarScatter(nn.Module):
             batch_size = int(coords[:, 0].max().int().item()) + 1
         if feats.shape[-1] != self.num_bev_features:
             raise ValueError(f"pillar_features have {feats.shape[-1]} channels, NUM_BEV_FEATURES={self.num_bev_features}")
-        batch_dict["spatial_features"] = ops.scatter_bev(feats, coords, batch_size, self.nx, self.ny,
+        m_dev = None
+        pc = batch_dict.get("pillar_count")
+        if torch.is_tensor(pc) and pc.is_cuda and pc.numel() == batch_size + 1 and feats.shape[0] >= 1:
+            m_dev = pc[-1:]  # device-side live row count (PillarVFEFromPoints with SYNC_COUNTS false)
+        batch_dict["spatial_features"] = ops.scatter_bev(feats, coords, batch_size, self.nx, self.ny, m_dev=m_dev,
                                                          variant=self.variant, out_dtype=self.out_dtype)
         return batch_dict
 

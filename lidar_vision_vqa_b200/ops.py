@@ -396,6 +396,7 @@ class EncodeBuffers:
         cap = max(int(cap), 1)  # an empty batch still needs non-NULL output pointers
         nx, ny, nz = grid.grid_size
         self.capacity = cap
+        self.n_points, self.n_frames = int(n_points), int(n_frames)
         self.pillar_features = torch.empty((cap, f_out), dtype=torch.float32, device=device)
         self.voxel_coords = torch.empty((cap, 4), dtype=torch.int32, device=device)
         self.voxel_num_points = torch.empty((cap,), dtype=torch.int32, device=device)
@@ -472,6 +473,24 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
         if scatter_stream is not None:
             lib.pillars_set_scatter_stream(None, 0)
     return res
+
+
+def rebase_segments(coords: torch.Tensor, segment_counts: torch.Tensor, frames_per_segment: int) -> torch.Tensor:
+    """In place on gathered ``coords [S, R, 4]`` int32 (S rank segments of R rows, rank-local frame indices) with
+    ``segment_counts [S, k]`` int32 whose LAST column is each segment's live row count: live rows get
+    ``s * frames_per_segment`` added to their frame index, padding rows get frame ``-1`` (skipped by the scatter and the
+    tokeniser).  No host synchronisation."""
+    _require_device(coords)
+    if coords.dtype != torch.int32 or coords.dim() != 3 or coords.shape[2] != 4 or not coords.is_contiguous():
+        raise ValueError("coords must be a contiguous int32 [S, R, 4] tensor")
+    if segment_counts.dtype != torch.int32 or segment_counts.dim() != 2 or segment_counts.shape[0] != coords.shape[0] \
+            or not segment_counts.is_contiguous() or not segment_counts.is_cuda:
+        raise ValueError("segment_counts must be a contiguous int32 CUDA [S, k] tensor")
+    k = segment_counts.shape[1]
+    check(_native.load().pillars_rebase_segments(coords.data_ptr(), coords.shape[0], coords.shape[1],
+                                                 segment_counts.data_ptr() + 4 * (k - 1), k, int(frames_per_segment),
+                                                 _stream_ptr()), "pillars_rebase_segments")
+    return coords
 
 
 GROUPING_MODES = {"auto": 0, "hash": 1, "dense": 2}

@@ -56,7 +56,7 @@ def gather_bev_tokens(pillar_features: torch.Tensor, voxel_coords: torch.Tensor,
     all-gather of the row counts, then one gather of padded payloads (features and coordinates travel in one buffer:
     the int32 coordinates are bit-cast into four extra float columns)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        c = voxel_coords.clone()
+        c = voxel_coords.to(torch.int32).clone()
         c[:, 0] += frame_base
         return GatheredTokens(pillar_features, c, [pillar_features.shape[0]], n_frames_total)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -80,6 +80,131 @@ def gather_bev_tokens(pillar_features: torch.Tensor, voxel_coords: torch.Tensor,
         return GatheredTokens(feats, crd, counts_h, n_frames_total)
     dist.gather(payload, None, dst=dst, group=group)
     return None
+
+
+class TokenGatherer:
+    """Steady-state hand-over of compact BEV tokens to the fusion rank: no host synchronisation, no padding to the batch
+    maximum negotiated per step, no concatenation afterwards.
+
+    Every rank contributes the first ``rows`` rows of its ``pillar_features`` / ``voxel_coords`` output buffers (sent in
+    place, straight out of the encoder's buffers) and its ``pillar_count [B_r + 1]``; the destination receives them into
+    fixed segments of one buffer: ``feats [W, rows, F]``, ``coords [W, rows, 4]``, ``counts [W, B_r + 1]``.  ``rows`` is a
+    capacity agreed once (e.g. 1.15 x the pillar count of a warm-up batch); the counts travel with the payload and stay on
+    the device, where :func:`ops.rebase_segments` turns padding rows into frame ``-1`` (skipped by the scatter and by the
+    tokeniser) and shifts live rows to global frame numbers.  A rank whose count exceeds ``rows`` raises the device-side
+    ``overflow`` flag, read by :meth:`check` outside the hot loop.
+
+    All three transfers of a step are one NCCL group (``batch_isend_irecv``) issued on the gatherer's own stream, ordered
+    after the encoder by an event, so step k's transfer overlaps step k+1's kernels.  This is the shape of the reference's
+    variable-length gather helper (src/lidar-encoder/pcdet/utils/commu_utils.py:50-111: sizes first, then payloads padded to
+    the maximum, pickled) with its weaknesses removed.  Feature rows can optionally travel as float16 (``dtype``), halving
+    the bytes that bound the destination's NVLink ingress."""
+
+    def __init__(self, rows: int, f: int, frames_per_rank: int, device, dst: int = 0, dtype: torch.dtype = torch.float32,
+                 group: Optional[dist.ProcessGroup] = None, slots: int = 2):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dst, self.rows, self.f, self.frames_per_rank = int(dst), int(rows), int(f), int(frames_per_rank)
+        self.device, self.dtype = torch.device(device), dtype
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.slots = []
+        for _ in range(max(1, slots)):
+            slot = {"sent": torch.cuda.Event() if self.cuda else None, "ready": torch.cuda.Event() if self.cuda else None}
+            if dtype != torch.float32:  # the cast is the only copy on the sender
+                slot["send_feats"] = torch.empty((self.rows, self.f), dtype=dtype, device=self.device)
+            if self.rank == self.dst:
+                slot["feats"] = torch.empty((self.world, self.rows, self.f), dtype=dtype, device=self.device)
+                slot["coords"] = torch.empty((self.world, self.rows, 4), dtype=torch.int32, device=self.device)
+                slot["counts"] = torch.zeros((self.world, self.frames_per_rank + 1), dtype=torch.int32, device=self.device)
+            self.slots.append(slot)
+        self._k = 0
+
+    def bytes_per_rank(self) -> int:
+        return self.rows * (self.f * torch.empty((), dtype=self.dtype).element_size() + 16) + 4 * (self.frames_per_rank + 1)
+
+    def exchange(self, pillar_features: torch.Tensor, voxel_coords: torch.Tensor, pillar_count: torch.Tensor,
+                 after: Optional["torch.cuda.Event"] = None):
+        """Enqueues the transfer of one step.  ``pillar_features [>=rows, F]`` fp32, ``voxel_coords [>=rows, 4]`` int32 and
+        ``pillar_count [B_r+1]`` int32 are the encoder's output buffers (capacity-sized, rows beyond the count undefined);
+        they must stay untouched until the returned slot's ``sent`` event.  On the destination the slot's ``feats`` /
+        ``coords`` / ``counts`` are valid after its ``ready`` event (coords already rebased).  Returns the slot."""
+        from . import ops
+
+        slot = self.slots[self._k % len(self.slots)]
+        self._k += 1
+        if pillar_features.shape[0] < self.rows or voxel_coords.shape[0] < self.rows:
+            raise ValueError("encoder buffers are smaller than the gatherer's row capacity")
+        ctx = torch.cuda.stream(self.stream) if self.cuda else _null_ctx()
+        with ctx:
+            if self.cuda:
+                if after is not None:
+                    self.stream.wait_event(after)
+                else:
+                    self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            over = (pillar_count[-1:] > self.rows).to(torch.int32)
+            torch.maximum(self.overflow, over, out=self.overflow)
+            send_f = pillar_features[:self.rows]
+            if self.dtype != torch.float32:
+                slot["send_feats"].copy_(send_f)
+                send_f = slot["send_feats"]
+            send_c = voxel_coords[:self.rows]
+            if self.world == 1:
+                slot["feats"][0].copy_(send_f)
+                slot["coords"][0].copy_(send_c)
+                slot["counts"][0].copy_(pillar_count)
+            elif self.rank == self.dst:
+                slot["feats"][self.rank].copy_(send_f)
+                slot["coords"][self.rank].copy_(send_c)
+                slot["counts"][self.rank].copy_(pillar_count)
+                p2p = []
+                for r in range(self.world):
+                    if r == self.dst:
+                        continue
+                    p2p += [dist.P2POp(dist.irecv, slot["feats"][r], r, self.group),
+                            dist.P2POp(dist.irecv, slot["coords"][r], r, self.group),
+                            dist.P2POp(dist.irecv, slot["counts"][r], r, self.group)]
+                for w in dist.batch_isend_irecv(p2p):
+                    w.wait()
+            else:
+                p2p = [dist.P2POp(dist.isend, send_f, self.dst, self.group),
+                       dist.P2POp(dist.isend, send_c, self.dst, self.group),
+                       dist.P2POp(dist.isend, pillar_count, self.dst, self.group)]
+                for w in dist.batch_isend_irecv(p2p):
+                    w.wait()
+            if self.cuda:
+                slot["sent"].record(self.stream)
+            if self.rank == self.dst:
+                if self.cuda:
+                    ops.rebase_segments(slot["coords"], slot["counts"], self.frames_per_rank)
+                    slot["ready"].record(self.stream)
+        return slot
+
+    def check(self) -> None:
+        """Host-side check (synchronises): raises when some step's pillar count did not fit ``rows``."""
+        if int(self.overflow.item()) != 0:
+            raise RuntimeError(f"TokenGatherer: a rank produced more than rows={self.rows} pillars; rows were dropped")
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def densify_segments(slot: dict, n_frames_total: int, nx: int, ny: int, variant: str = "auto",
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dense ``[B, F, ny, nx]`` canvas of a :class:`TokenGatherer` slot on the destination (fp32 feature rows)."""
+    from . import ops
+
+    feats = slot["feats"].reshape(-1, slot["feats"].shape[-1])
+    if feats.dtype != torch.float32:
+        feats = feats.float()
+    return ops.scatter_bev(feats, slot["coords"].reshape(-1, 4), n_frames_total, nx, ny, 1, variant=variant, out=out)
 
 
 def densify(tokens: GatheredTokens, nx: int, ny: int, variant: str = "auto") -> torch.Tensor:

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference modules of the pillar hot path.
 
-Only usable where /root/reference exists (the build container).  It is used by
+Usable where /root/reference exists (the build container) or where ``oracle/make_ref.py`` left its verbatim copy under
+``oracle/_ref/`` (that directory is git-ignored but travels to the GPU box).  It is used by
 ``tests/golden/make_golden.py`` to generate the committed golden vectors and by the
 ``-m "not gpu"`` tests that re-check the oracle restatement against the live reference.
 Nothing under ``lidar_vision_vqa_b200/`` may import this file; ``bench.py`` and the ``-m gpu``
@@ -29,6 +30,12 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("LVVQA_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "lidar-encoder", "pcdet", "models", "backbones_3d", "vfe",
+                                   "pillar_vfe.py")):
+    # the GPU box: the verbatim copy that oracle/make_ref.py placed under oracle/_ref/ travels with the snapshot
+    _local = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if os.path.isdir(_local):
+        REFERENCE_ROOT = _local
 _PCDET = os.path.join(REFERENCE_ROOT, "src", "lidar-encoder", "pcdet")
 
 

@@ -99,3 +99,55 @@ def test_numa_binding_is_best_effort():
     assert got is None or (len(got) > 0 and set(got) <= before)
     assert len(after) > 0
     os.sched_setaffinity(0, before)
+
+
+def _gatherer_worker(rank, world, port, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows, f, frames = 40, 8, 3
+        gat = sharding.TokenGatherer(rows, f, frames, "cpu", dst=0, slots=2)
+        ok = True
+        for step in range(3):  # three steps through two slots, different counts every step
+            g = torch.Generator().manual_seed(10 * step + rank)
+            per_frame = torch.randint(0, 9, (frames,), generator=g).int()
+            m = int(per_frame.sum())
+            # capacity-sized encoder buffers: rows beyond the count hold stale garbage
+            feats = torch.randn(64, f, generator=g)
+            coords = torch.randint(0, 50, (64, 4), generator=g).int()
+            coords[:m, 0] = torch.repeat_interleave(torch.arange(frames), per_frame.long()).int()
+            count = torch.cat([per_frame, per_frame.sum(dim=0, keepdim=True)]).int()
+            slot = gat.exchange(feats, coords, count)
+            sent = [None] * world
+            dist.all_gather_object(sent, (feats[:rows].numpy(), coords[:rows].numpy(), count.numpy()))
+            if rank == 0:
+                for r in range(world):
+                    ok &= np.array_equal(slot["feats"][r].numpy(), sent[r][0])
+                    ok &= np.array_equal(slot["coords"][r].numpy(), sent[r][1])  # (rebasing is a device kernel)
+                    ok &= np.array_equal(slot["counts"][r].numpy(), sent[r][2])
+        gat.check()
+        # a count beyond the agreed capacity raises on check()
+        gat.exchange(torch.zeros(64, f), torch.zeros(64, 4, dtype=torch.int32),
+                     torch.tensor([0, 0, 0, rows + 1 if rank == 1 else 1], dtype=torch.int32))
+        raised = False
+        try:
+            gat.check()
+        except RuntimeError:
+            raised = True
+        ok &= raised == (rank == 1)
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        if rank == 0:
+            with open(result_path, "w") as fh:
+                fh.write("ok" if all(flags) else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_token_gatherer_world2_gloo(tmp_path):
+    """The steady-state gatherer on two gloo ranks: fixed-capacity segments, counts travelling with the payload, slots
+    reused across steps, overflow detection."""
+    result = tmp_path / "result.txt"
+    mp.spawn(_gatherer_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
+    assert result.read_text() == "ok"
