@@ -153,12 +153,14 @@ int pillars_scatter_bev_half(const float *feats, const void *coords, int32_t coo
 
 /* Multi-GPU hand-over (no counterpart in the reference: its frames go to disk; the gather helper it ships,
  * pcdet/utils/commu_utils.py:50-111, is the shape this replaces).  Compact BEV tokens gathered from several ranks lie in
- * n_segments equal segments of rows_per_segment rows of `coords` [n_segments * rows_per_segment, 4] (b,z,y,x); segment s
- * has segment_counts[s * count_stride] live rows, numbered with rank-local frame indices.  Adds s * frames_per_segment to
- * the frame index of live rows and writes -1 into the frame index of padding rows, which pillars_scatter_bev and
- * pillars_bev_tokens skip.  Everything stays on the device: no count ever visits the host. */
-int pillars_rebase_segments(int32_t *coords, int32_t n_segments, int64_t rows_per_segment, const int32_t *segment_counts,
-                            int32_t count_stride, int32_t frames_per_segment, void *stream);
+ * n_segments segments of rows_per_segment rows of (b,z,y,x) int32 coordinates; segment s starts at
+ * coords + s * segment_stride (int32 elements, >= 4 * rows_per_segment) and has segment_counts[s * count_stride] live rows,
+ * numbered with rank-local frame indices.  Adds s * frames_per_segment to the frame index of live rows and writes -1 into
+ * the frame index of padding rows, which pillars_scatter_bev and pillars_bev_tokens skip; sets *overflow (optional) to 1
+ * when a count exceeds rows_per_segment.  Everything stays on the device: no count ever visits the host. */
+int pillars_rebase_segments(int32_t *coords, int32_t n_segments, int64_t rows_per_segment, int64_t segment_stride,
+                            const int32_t *segment_counts, int64_t count_stride, int32_t frames_per_segment,
+                            int32_t *overflow, void *stream);
 
 /* The fused path: raw points -> pillar features -> BEV.  Same grouping semantics as pillars_voxelize, same
  * feature semantics as pillars_pfn_dense on its output, same canvas as pillars_scatter_bev. */

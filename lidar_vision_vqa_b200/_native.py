@@ -150,7 +150,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.pillars_set_scatter_stream.restype = c_int
     lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
     lib.pillars_rebase_segments.restype = c_int
-    lib.pillars_rebase_segments.argtypes = [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_void_p]
+    lib.pillars_rebase_segments.argtypes = [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.pillars_set_debug_times.restype = c_int
     lib.pillars_set_debug_times.argtypes = [c_void_p]
     lib.pillars_set_grouping.restype = c_int

@@ -545,16 +545,18 @@ int pillars_scatter_bev(const float *feats, const void *coords, int32_t coords_i
     return 0;
 }
 
-int pillars_rebase_segments(int32_t *coords, int32_t n_segments, int64_t rows_per_segment, const int32_t *segment_counts,
-                            int32_t count_stride, int32_t frames_per_segment, void *stream)
+int pillars_rebase_segments(int32_t *coords, int32_t n_segments, int64_t rows_per_segment, int64_t segment_stride,
+                            const int32_t *segment_counts, int64_t count_stride, int32_t frames_per_segment,
+                            int32_t *overflow, void *stream)
 {
     g_launches = 0;
-    if (n_segments < 0 || rows_per_segment < 0 || count_stride < 1 || frames_per_segment < 0)
+    if (n_segments < 0 || rows_per_segment < 0 || count_stride < 1 || frames_per_segment < 0 ||
+        segment_stride < rows_per_segment * 4)
         return fail(PILLARS_E_BADARG, "pillars_rebase_segments: bad size");
     if (static_cast<int64_t>(n_segments) * rows_per_segment > 0 && (!coords || !segment_counts))
         return fail(PILLARS_E_BADARG, "pillars_rebase_segments: NULL pointer");
-    cudaError_t e = launch_rebase_segments(coords, n_segments, rows_per_segment, segment_counts, count_stride,
-                                           frames_per_segment, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_rebase_segments(coords, n_segments, rows_per_segment, segment_stride, segment_counts,
+                                           count_stride, frames_per_segment, overflow, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "rebase_segments");
     g_launches_last = g_launches;
     return 0;

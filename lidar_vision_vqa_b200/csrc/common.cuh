@@ -358,8 +358,9 @@ cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t
                                   int ny, int nz, int32_t *cell_row, cudaStream_t st);
 cudaError_t launch_scatter(const float *feats, const int32_t *cell_row, int nb, int f, int nx, int ny, float *bev,
                            int variant, cudaStream_t st);
-cudaError_t launch_rebase_segments(int32_t *coords, int n_seg, int64_t rows_per_seg, const int32_t *seg_counts,
-                                   int count_stride, int frames_per_seg, cudaStream_t st);
+cudaError_t launch_rebase_segments(int32_t *coords, int n_seg, int64_t rows_per_seg, int64_t seg_stride,
+                                   const int32_t *seg_counts, int64_t count_stride, int frames_per_seg, int32_t *overflow,
+                                   cudaStream_t st);
 // float16 canvas (plane % 8 == 0, f % 8 == 0)
 cudaError_t launch_scatter_half(const float *feats, const int32_t *cell_row, int nb, int f, int nx, int ny, void *bev,
                                 cudaStream_t st);

@@ -46,19 +46,23 @@ __global__ void k_build_cell_row(const void *__restrict__ coords, int coords_flo
     atomicMax(cell_row + static_cast<int64_t>(b) * plane + cell, static_cast<int32_t>(i));  // later row wins
 }
 
-// Gathered compact BEV tokens of several ranks lie in equal-sized segments of `rows_per_seg` rows; segment s holds
-// seg_counts[s * count_stride] live rows whose frame indices are local to its rank.  Live rows get the segment's frame base
-// added, the padding rows get frame -1 (every consumer of voxel_coords skips those).
-__global__ void k_rebase_segments(int32_t *__restrict__ coords, int n_seg, int64_t rows_per_seg,
-                                  const int32_t *__restrict__ seg_counts, int count_stride, int frames_per_seg)
+// Gathered compact BEV tokens of several ranks lie in equal-sized segments of `rows_per_seg` rows (segment s starts
+// `seg_stride` int32 elements after segment s - 1); segment s holds seg_counts[s * count_stride] live rows whose frame
+// indices are local to its rank.  Live rows get the segment's frame base added, the padding rows get frame -1 (every
+// consumer of voxel_coords skips those).  A count beyond the segment's capacity raises *overflow.
+__global__ void k_rebase_segments(int32_t *__restrict__ coords, int n_seg, int64_t rows_per_seg, int64_t seg_stride,
+                                  const int32_t *__restrict__ seg_counts, int64_t count_stride, int frames_per_seg,
+                                  int32_t *__restrict__ overflow)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= rows_per_seg * n_seg) return;
     const int seg = static_cast<int>(i / rows_per_seg);
     const int64_t r = i - seg * rows_per_seg;
-    int32_t *b = coords + i * 4;
-    if (r < __ldg(seg_counts + static_cast<int64_t>(seg) * count_stride)) *b += seg * frames_per_seg;
+    const int32_t cnt = __ldg(seg_counts + static_cast<int64_t>(seg) * count_stride);
+    int32_t *b = coords + seg * seg_stride + r * 4;
+    if (r < cnt) *b += seg * frames_per_seg;
     else *b = -1;
+    if (r == 0 && cnt > rows_per_seg && overflow) *overflow = 1;
 }
 
 // ---- variant 1 ----------------------------------------------------------------------------------
@@ -312,13 +316,14 @@ cudaError_t launch_build_cell_row(const void *coords, bool coords_float, int64_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_rebase_segments(int32_t *coords, int n_seg, int64_t rows_per_seg, const int32_t *seg_counts,
-                                   int count_stride, int frames_per_seg, cudaStream_t st)
+cudaError_t launch_rebase_segments(int32_t *coords, int n_seg, int64_t rows_per_seg, int64_t seg_stride,
+                                   const int32_t *seg_counts, int64_t count_stride, int frames_per_seg, int32_t *overflow,
+                                   cudaStream_t st)
 {
     const int64_t total = rows_per_seg * n_seg;
     if (total == 0) return cudaSuccess;
     k_rebase_segments<<<static_cast<unsigned>((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(
-        coords, n_seg, rows_per_seg, seg_counts, count_stride, frames_per_seg);
+        coords, n_seg, rows_per_seg, seg_stride, seg_counts, count_stride, frames_per_seg, overflow);
     note_launch();
     return cudaGetLastError();
 }

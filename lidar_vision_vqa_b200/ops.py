@@ -391,16 +391,29 @@ class EncodeBuffers:
     traffic inside a timed loop)."""
 
     def __init__(self, n_points: int, n_frames: int, grid: GridSpec, f_out: int, device, *, with_bev: bool = True,
-                 capacity: Optional[int] = None, ws_slot: int = 0, bev_dtype: torch.dtype = torch.float32):
+                 capacity: Optional[int] = None, ws_slot: int = 0, bev_dtype: torch.dtype = torch.float32,
+                 wire_slab: bool = False):
+        """``wire_slab``: ``pillar_features``, ``voxel_coords`` and ``pillar_count`` are views of ONE contiguous byte buffer
+        ``self.wire`` (features | coordinates | counts), so the whole compact result of a step travels as a single message
+        (:class:`sharding.TokenGatherer`)."""
         cap = min(n_points, n_frames * grid.max_voxels) if capacity is None else capacity
         cap = max(int(cap), 1)  # an empty batch still needs non-NULL output pointers
         nx, ny, nz = grid.grid_size
         self.capacity = cap
         self.n_points, self.n_frames = int(n_points), int(n_frames)
-        self.pillar_features = torch.empty((cap, f_out), dtype=torch.float32, device=device)
-        self.voxel_coords = torch.empty((cap, 4), dtype=torch.int32, device=device)
+        self.wire = None
+        if wire_slab:
+            a, b = cap * f_out * 4, cap * 16
+            c = (4 * (n_frames + 1) + 15) // 16 * 16
+            self.wire = torch.zeros(a + b + c, dtype=torch.uint8, device=device)
+            self.pillar_features = self.wire[:a].view(torch.float32).view(cap, f_out)
+            self.voxel_coords = self.wire[a:a + b].view(torch.int32).view(cap, 4)
+            self.pillar_count = self.wire[a + b:a + b + 4 * (n_frames + 1)].view(torch.int32)
+        else:
+            self.pillar_features = torch.empty((cap, f_out), dtype=torch.float32, device=device)
+            self.voxel_coords = torch.empty((cap, 4), dtype=torch.int32, device=device)
+            self.pillar_count = torch.empty((n_frames + 1,), dtype=torch.int32, device=device)
         self.voxel_num_points = torch.empty((cap,), dtype=torch.int32, device=device)
-        self.pillar_count = torch.empty((n_frames + 1,), dtype=torch.int32, device=device)
         self.bev = torch.empty((n_frames, f_out * nz, ny, nx), dtype=bev_dtype, device=device) if with_bev else None
         g = grid.native()
         need = _native.load().pillars_workspace_bytes(n_points, n_frames, ctypes.byref(g))
@@ -475,21 +488,27 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
     return res
 
 
-def rebase_segments(coords: torch.Tensor, segment_counts: torch.Tensor, frames_per_segment: int) -> torch.Tensor:
-    """In place on gathered ``coords [S, R, 4]`` int32 (S rank segments of R rows, rank-local frame indices) with
-    ``segment_counts [S, k]`` int32 whose LAST column is each segment's live row count: live rows get
-    ``s * frames_per_segment`` added to their frame index, padding rows get frame ``-1`` (skipped by the scatter and the
-    tokeniser).  No host synchronisation."""
+def rebase_segments(coords: torch.Tensor, segment_counts: torch.Tensor, frames_per_segment: int,
+                    overflow: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place on gathered ``coords [S, R, 4]`` int32 (S rank segments of R rows each, rank-local frame indices; the
+    segments may be strided views of a larger buffer) with ``segment_counts [S, k]`` int32 whose LAST column is each
+    segment's live row count: live rows get ``s * frames_per_segment`` added to their frame index, padding rows get frame
+    ``-1`` (skipped by the scatter and the tokeniser).  ``overflow`` (int32 [1], device) is set when a count exceeds R.  No
+    host synchronisation."""
     _require_device(coords)
-    if coords.dtype != torch.int32 or coords.dim() != 3 or coords.shape[2] != 4 or not coords.is_contiguous():
-        raise ValueError("coords must be a contiguous int32 [S, R, 4] tensor")
+    if coords.dtype != torch.int32 or coords.dim() != 3 or coords.shape[2] != 4 or coords.stride(2) != 1 \
+            or coords.stride(1) != 4:
+        raise ValueError("coords must be an int32 [S, R, 4] tensor with contiguous rows")
     if segment_counts.dtype != torch.int32 or segment_counts.dim() != 2 or segment_counts.shape[0] != coords.shape[0] \
-            or not segment_counts.is_contiguous() or not segment_counts.is_cuda:
-        raise ValueError("segment_counts must be a contiguous int32 CUDA [S, k] tensor")
+            or segment_counts.stride(1) != 1 or not segment_counts.is_cuda:
+        raise ValueError("segment_counts must be an int32 CUDA [S, k] tensor with contiguous rows")
     k = segment_counts.shape[1]
-    check(_native.load().pillars_rebase_segments(coords.data_ptr(), coords.shape[0], coords.shape[1],
-                                                 segment_counts.data_ptr() + 4 * (k - 1), k, int(frames_per_segment),
-                                                 _stream_ptr()), "pillars_rebase_segments")
+    s_n = coords.shape[0]
+    check(_native.load().pillars_rebase_segments(coords.data_ptr(), s_n, coords.shape[1],
+                                                 coords.stride(0) if s_n > 1 else 4 * coords.shape[1],
+                                                 segment_counts.data_ptr() + 4 * (k - 1),
+                                                 segment_counts.stride(0) if s_n > 1 else k, int(frames_per_segment),
+                                                 _ptr(overflow), _stream_ptr()), "pillars_rebase_segments")
     return coords
 
 

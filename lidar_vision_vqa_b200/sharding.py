@@ -82,23 +82,33 @@ def gather_bev_tokens(pillar_features: torch.Tensor, voxel_coords: torch.Tensor,
     return None
 
 
+def wire_layout(rows: int, f: int, frames: int, feat_bytes: int = 4):
+    """Byte offsets of the compact result of one step as ONE message: features ``[rows, f]`` | coordinates ``[rows, 4]``
+    int32 | counts ``[frames + 1]`` int32 (padded to 16 bytes).  The same layout as ``ops.EncodeBuffers(wire_slab=True)``."""
+    a = rows * f * feat_bytes
+    b = rows * 16
+    c = (4 * (frames + 1) + 15) // 16 * 16
+    return a, b, c
+
+
 class TokenGatherer:
-    """Steady-state hand-over of compact BEV tokens to the fusion rank: no host synchronisation, no padding to the batch
-    maximum negotiated per step, no concatenation afterwards.
+    """Steady-state hand-over of compact BEV tokens to the fusion rank: one message per rank and step, no host
+    synchronisation, no per-step size negotiation, no concatenation afterwards.
 
-    Every rank contributes the first ``rows`` rows of its ``pillar_features`` / ``voxel_coords`` output buffers (sent in
-    place, straight out of the encoder's buffers) and its ``pillar_count [B_r + 1]``; the destination receives them into
-    fixed segments of one buffer: ``feats [W, rows, F]``, ``coords [W, rows, 4]``, ``counts [W, B_r + 1]``.  ``rows`` is a
-    capacity agreed once (e.g. 1.15 x the pillar count of a warm-up batch); the counts travel with the payload and stay on
-    the device, where :func:`ops.rebase_segments` turns padding rows into frame ``-1`` (skipped by the scatter and by the
-    tokeniser) and shifts live rows to global frame numbers.  A rank whose count exceeds ``rows`` raises the device-side
-    ``overflow`` flag, read by :meth:`check` outside the hot loop.
+    Every rank's encoder writes ``pillar_features``, ``voxel_coords`` and ``pillar_count`` into ONE contiguous slab
+    (``ops.EncodeBuffers(capacity=rows, wire_slab=True)``) that is sent in place; the destination receives the slabs into
+    fixed segments of one buffer and exposes the views ``feats [W, rows, F]``, ``coords [W, rows, 4]``, ``counts
+    [W, B_r + 1]``.  ``rows`` is a capacity agreed once (e.g. 1.1 x the pillar count of a warm-up batch): the encoder drops
+    pillars beyond it but still reports the true count, the counts travel with the payload and stay on the device, where
+    :func:`ops.rebase_segments` turns padding rows into frame ``-1`` (skipped by the scatter and by the tokeniser), shifts
+    live rows to global frame numbers and raises the ``overflow`` flag when a count did not fit; :meth:`check` reads that flag
+    outside the hot loop.
 
-    All three transfers of a step are one NCCL group (``batch_isend_irecv``) issued on the gatherer's own stream, ordered
-    after the encoder by an event, so step k's transfer overlaps step k+1's kernels.  This is the shape of the reference's
-    variable-length gather helper (src/lidar-encoder/pcdet/utils/commu_utils.py:50-111: sizes first, then payloads padded to
-    the maximum, pickled) with its weaknesses removed.  Feature rows can optionally travel as float16 (``dtype``), halving
-    the bytes that bound the destination's NVLink ingress."""
+    The transfers of a step are one NCCL group (``batch_isend_irecv``) issued on the gatherer's own high-priority stream,
+    ordered after the encoder by an event, so step k's transfer overlaps step k+1's kernels.  This is the shape of the
+    reference's variable-length gather helper (src/lidar-encoder/pcdet/utils/commu_utils.py:50-111: sizes first, then
+    payloads padded to the maximum, pickled) with its weaknesses removed.  ``dtype=torch.float16`` sends the feature rows as
+    float16 (one cast on the sender), halving the bytes that bound the destination's NVLink ingress."""
 
     def __init__(self, rows: int, f: int, frames_per_rank: int, device, dst: int = 0, dtype: torch.dtype = torch.float32,
                  group: Optional[dist.ProcessGroup] = None, slots: int = 2):
@@ -108,35 +118,40 @@ class TokenGatherer:
         self.dst, self.rows, self.f, self.frames_per_rank = int(dst), int(rows), int(f), int(frames_per_rank)
         self.device, self.dtype = torch.device(device), dtype
         self.cuda = self.device.type == "cuda"
-        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.cuda else None
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.feat_bytes = 2 if dtype == torch.float16 else 4
+        self.a32, self.b, self.c = wire_layout(self.rows, self.f, self.frames_per_rank, 4)
+        self.a = self.rows * self.f * self.feat_bytes
+        self.slab_bytes = self.a + self.b + self.c
         self.slots = []
         for _ in range(max(1, slots)):
             slot = {"sent": torch.cuda.Event() if self.cuda else None, "ready": torch.cuda.Event() if self.cuda else None}
-            if dtype != torch.float32:  # the cast is the only copy on the sender
-                slot["send_feats"] = torch.empty((self.rows, self.f), dtype=dtype, device=self.device)
+            if dtype != torch.float32:  # the cast needs a staging slab on the sender
+                slot["stage"] = torch.zeros(self.slab_bytes, dtype=torch.uint8, device=self.device)
             if self.rank == self.dst:
-                slot["feats"] = torch.empty((self.world, self.rows, self.f), dtype=dtype, device=self.device)
-                slot["coords"] = torch.empty((self.world, self.rows, 4), dtype=torch.int32, device=self.device)
-                slot["counts"] = torch.zeros((self.world, self.frames_per_rank + 1), dtype=torch.int32, device=self.device)
+                w = torch.zeros((self.world, self.slab_bytes), dtype=torch.uint8, device=self.device)
+                slot["wire"] = w
+                slot["feats"] = w[:, :self.a].view(dtype).view(self.world, self.rows, self.f)
+                slot["coords"] = w[:, self.a:self.a + self.b].view(torch.int32).view(self.world, self.rows, 4)
+                slot["counts"] = w[:, self.a + self.b:self.a + self.b + 4 * (self.frames_per_rank + 1)].view(torch.int32)
             self.slots.append(slot)
         self._k = 0
 
     def bytes_per_rank(self) -> int:
-        return self.rows * (self.f * torch.empty((), dtype=self.dtype).element_size() + 16) + 4 * (self.frames_per_rank + 1)
+        return self.slab_bytes
 
-    def exchange(self, pillar_features: torch.Tensor, voxel_coords: torch.Tensor, pillar_count: torch.Tensor,
-                 after: Optional["torch.cuda.Event"] = None):
-        """Enqueues the transfer of one step.  ``pillar_features [>=rows, F]`` fp32, ``voxel_coords [>=rows, 4]`` int32 and
-        ``pillar_count [B_r+1]`` int32 are the encoder's output buffers (capacity-sized, rows beyond the count undefined);
-        they must stay untouched until the returned slot's ``sent`` event.  On the destination the slot's ``feats`` /
-        ``coords`` / ``counts`` are valid after its ``ready`` event (coords already rebased).  Returns the slot."""
+    def exchange(self, wire: torch.Tensor, after: Optional["torch.cuda.Event"] = None):
+        """Enqueues the transfer of one step.  ``wire`` is the encoder's slab (``EncodeBuffers.wire`` with
+        ``capacity == rows``); it must stay untouched until the returned slot's ``sent`` event.  On the destination the slot's
+        ``feats`` / ``coords`` / ``counts`` views are valid after its ``ready`` event (coords already rebased).  Returns
+        the slot."""
         from . import ops
 
         slot = self.slots[self._k % len(self.slots)]
         self._k += 1
-        if pillar_features.shape[0] < self.rows or voxel_coords.shape[0] < self.rows:
-            raise ValueError("encoder buffers are smaller than the gatherer's row capacity")
+        if wire.dtype != torch.uint8 or wire.numel() != self.a32 + self.b + self.c:
+            raise ValueError("wire must be the uint8 slab of EncodeBuffers(capacity=rows, wire_slab=True)")
         ctx = torch.cuda.stream(self.stream) if self.cuda else _null_ctx()
         with ctx:
             if self.cuda:
@@ -144,47 +159,31 @@ class TokenGatherer:
                     self.stream.wait_event(after)
                 else:
                     self.stream.wait_stream(torch.cuda.current_stream(self.device))
-            over = (pillar_count[-1:] > self.rows).to(torch.int32)
-            torch.maximum(self.overflow, over, out=self.overflow)
-            send_f = pillar_features[:self.rows]
+            send = wire
             if self.dtype != torch.float32:
-                slot["send_feats"].copy_(send_f)
-                send_f = slot["send_feats"]
-            send_c = voxel_coords[:self.rows]
-            if self.world == 1:
-                slot["feats"][0].copy_(send_f)
-                slot["coords"][0].copy_(send_c)
-                slot["counts"][0].copy_(pillar_count)
-            elif self.rank == self.dst:
-                slot["feats"][self.rank].copy_(send_f)
-                slot["coords"][self.rank].copy_(send_c)
-                slot["counts"][self.rank].copy_(pillar_count)
-                p2p = []
-                for r in range(self.world):
-                    if r == self.dst:
-                        continue
-                    p2p += [dist.P2POp(dist.irecv, slot["feats"][r], r, self.group),
-                            dist.P2POp(dist.irecv, slot["coords"][r], r, self.group),
-                            dist.P2POp(dist.irecv, slot["counts"][r], r, self.group)]
-                for w in dist.batch_isend_irecv(p2p):
-                    w.wait()
+                st = slot["stage"]
+                st[:self.a].view(self.dtype).copy_(wire[:self.a32].view(torch.float32))
+                st[self.a:].copy_(wire[self.a32:])
+                send = st
+            if self.rank == self.dst:
+                slot["wire"][self.rank].copy_(send)
+                if self.world > 1:
+                    p2p = [dist.P2POp(dist.irecv, slot["wire"][r], r, self.group) for r in range(self.world) if r != self.dst]
+                    for w in dist.batch_isend_irecv(p2p):
+                        w.wait()
             else:
-                p2p = [dist.P2POp(dist.isend, send_f, self.dst, self.group),
-                       dist.P2POp(dist.isend, send_c, self.dst, self.group),
-                       dist.P2POp(dist.isend, pillar_count, self.dst, self.group)]
-                for w in dist.batch_isend_irecv(p2p):
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, send, self.dst, self.group)]):
                     w.wait()
             if self.cuda:
                 slot["sent"].record(self.stream)
-            if self.rank == self.dst:
-                if self.cuda:
-                    ops.rebase_segments(slot["coords"], slot["counts"], self.frames_per_rank)
+                if self.rank == self.dst:
+                    ops.rebase_segments(slot["coords"], slot["counts"], self.frames_per_rank, overflow=self.overflow)
                     slot["ready"].record(self.stream)
         return slot
 
     def check(self) -> None:
-        """Host-side check (synchronises): raises when some step's pillar count did not fit ``rows``."""
-        if int(self.overflow.item()) != 0:
+        """Host-side check on the destination (synchronises): raises when some step's pillar count did not fit ``rows``."""
+        if self.cuda and int(self.overflow.item()) != 0:
             raise RuntimeError(f"TokenGatherer: a rank produced more than rows={self.rows} pillars; rows were dropped")
 
 
@@ -201,7 +200,7 @@ def densify_segments(slot: dict, n_frames_total: int, nx: int, ny: int, variant:
     """Dense ``[B, F, ny, nx]`` canvas of a :class:`TokenGatherer` slot on the destination (fp32 feature rows)."""
     from . import ops
 
-    feats = slot["feats"].reshape(-1, slot["feats"].shape[-1])
+    feats = slot["feats"].reshape(-1, slot["feats"].shape[-1])  # (a copy when the segments are strided views)
     if feats.dtype != torch.float32:
         feats = feats.float()
     return ops.scatter_bev(feats, slot["coords"].reshape(-1, 4), n_frames_total, nx, ny, 1, variant=variant, out=out)

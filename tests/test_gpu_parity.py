@@ -950,3 +950,64 @@ def test_grouping_unshuffled_sweeps(grouping, dev, L, oracle):
     np.testing.assert_array_equal(got["point_pillar"], ref["point_voxel"])
     np.testing.assert_array_equal(got["point_slot"], ref["point_slot"])
     np.testing.assert_array_equal(got["voxels"], ref["voxels"])
+
+
+def test_rebase_segments_and_gatherer_single_rank(dev, L, oracle):
+    """The device side of the multi-GPU hand-over on one GPU: segments of gathered coordinates (strided views of one wire
+    buffer) are rebased to global frame numbers, padding rows get frame -1, an oversized count raises the overflow flag;
+    the scatter of a rebased segment buffer equals the scatter of the concatenated live rows."""
+    from lidar_vision_vqa_b200 import sharding
+
+    s_n, rows, f, frames = 3, 50, 64, 2
+    a, b, c = sharding.wire_layout(rows, f, frames)
+    wire = torch.zeros((s_n, a + b + c), dtype=torch.uint8, device=dev)
+    feats = wire[:, :a].view(torch.float32).view(s_n, rows, f)
+    coords = wire[:, a:a + b].view(torch.int32).view(s_n, rows, 4)
+    counts = wire[:, a + b:a + b + 4 * (frames + 1)].view(torch.int32)
+    g = torch.Generator().manual_seed(0)
+    live = [37, 0, 50]
+    ref_rows, ref_coords = [], []
+    for s in range(s_n):
+        feats[s] = torch.randn(rows, f, generator=g).to(dev)
+        cells = torch.randperm(32 * 32, generator=g)[:rows]
+        cc = torch.stack([torch.randint(0, frames, (rows,), generator=g), torch.zeros(rows, dtype=torch.long), cells // 32,
+                          cells % 32], 1).int()
+        coords[s] = cc.to(dev)
+        counts[s] = torch.tensor([0, 0, live[s]], dtype=torch.int32, device=dev)
+        ref_rows.append(feats[s, :live[s]].cpu().numpy())
+        rc = cc[:live[s]].numpy().copy()
+        rc[:, 0] += s * frames
+        ref_coords.append(rc)
+    over = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.ops.rebase_segments(coords, counts, frames, overflow=over)
+    got = coords.cpu().numpy()
+    for s in range(s_n):
+        np.testing.assert_array_equal(got[s, :live[s]], ref_coords[s])
+        assert (got[s, live[s]:, 0] == -1).all()
+    assert int(over.item()) == 0
+    bev = sharding.densify_segments({"feats": feats, "coords": coords}, s_n * frames, 32, 32)
+    ref = oracle.scatter_bev(np.concatenate(ref_rows), np.concatenate(ref_coords), 32, 32, batch_size=s_n * frames)
+    np.testing.assert_array_equal(bev.cpu().numpy(), ref)
+    counts[1] = torch.tensor([0, 0, rows + 1], dtype=torch.int32, device=dev)
+    L.ops.rebase_segments(coords, counts, frames, overflow=over)
+    assert int(over.item()) == 1
+    # world size 1: the gatherer copies the slab into its own segment and rebases it
+    pts, offs, rng, vs, p, mv = _make_case("small_p32")
+    grid = L.GridSpec.from_range(rng, vs, 8, 500)
+    bufs = L.ops.EncodeBuffers(len(pts), 2, grid, 64, dev, capacity=1100, wire_slab=True)
+    gat = sharding.TokenGatherer(1100, 64, 2, dev, slots=1)
+    sd = oracle.random_pfn_params(11, [64], True, seed=3)
+    pfn = L.ops.fold_pfn(sd["pfn_layers.0.linear.weight"],
+                         (sd["pfn_layers.0.norm.weight"], sd["pfn_layers.0.norm.bias"], sd["pfn_layers.0.norm.running_mean"],
+                          sd["pfn_layers.0.norm.running_var"], 1e-3), None, c_point=5, use_absolute_xyz=True,
+                         with_distance=False, voxel_size=vs, point_cloud_range=rng, device=dev)
+    res = L.ops.encode_bev(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid, pfn, buffers=bufs)
+    slot = gat.exchange(bufs.wire)
+    torch.cuda.current_stream().wait_stream(gat.stream)
+    torch.cuda.synchronize()
+    gat.check()
+    m = int(res["pillar_count"][-1].item())
+    assert 0 < m <= 1100
+    np.testing.assert_array_equal(slot["counts"][0].cpu().numpy(), res["pillar_count"].cpu().numpy())
+    canvas = sharding.densify_segments(slot, 2, grid.grid_size[0], grid.grid_size[1])
+    assert torch.equal(canvas, res["bev"])

@@ -107,34 +107,29 @@ def _gatherer_worker(rank, world, port, result_path):
     try:
         rows, f, frames = 40, 8, 3
         gat = sharding.TokenGatherer(rows, f, frames, "cpu", dst=0, slots=2)
+        a, b, c = sharding.wire_layout(rows, f, frames)
         ok = True
         for step in range(3):  # three steps through two slots, different counts every step
             g = torch.Generator().manual_seed(10 * step + rank)
             per_frame = torch.randint(0, 9, (frames,), generator=g).int()
             m = int(per_frame.sum())
-            # capacity-sized encoder buffers: rows beyond the count hold stale garbage
-            feats = torch.randn(64, f, generator=g)
-            coords = torch.randint(0, 50, (64, 4), generator=g).int()
+            # the encoder's slab: features | coords | counts, rows beyond the count hold stale garbage
+            wire = torch.zeros(a + b + c, dtype=torch.uint8)
+            feats = wire[:a].view(torch.float32).view(rows, f)
+            coords = wire[a:a + b].view(torch.int32).view(rows, 4)
+            count = wire[a + b:a + b + 4 * (frames + 1)].view(torch.int32)
+            feats.copy_(torch.randn(rows, f, generator=g))
+            coords.copy_(torch.randint(0, 50, (rows, 4), generator=g).int())
             coords[:m, 0] = torch.repeat_interleave(torch.arange(frames), per_frame.long()).int()
-            count = torch.cat([per_frame, per_frame.sum(dim=0, keepdim=True)]).int()
-            slot = gat.exchange(feats, coords, count)
+            count.copy_(torch.cat([per_frame, per_frame.sum(dim=0, keepdim=True)]).int())
+            slot = gat.exchange(wire)
             sent = [None] * world
-            dist.all_gather_object(sent, (feats[:rows].numpy(), coords[:rows].numpy(), count.numpy()))
+            dist.all_gather_object(sent, (feats.numpy().copy(), coords.numpy().copy(), count.numpy().copy()))
             if rank == 0:
                 for r in range(world):
                     ok &= np.array_equal(slot["feats"][r].numpy(), sent[r][0])
                     ok &= np.array_equal(slot["coords"][r].numpy(), sent[r][1])  # (rebasing is a device kernel)
                     ok &= np.array_equal(slot["counts"][r].numpy(), sent[r][2])
-        gat.check()
-        # a count beyond the agreed capacity raises on check()
-        gat.exchange(torch.zeros(64, f), torch.zeros(64, 4, dtype=torch.int32),
-                     torch.tensor([0, 0, 0, rows + 1 if rank == 1 else 1], dtype=torch.int32))
-        raised = False
-        try:
-            gat.check()
-        except RuntimeError:
-            raised = True
-        ok &= raised == (rank == 1)
         flags = [None] * world
         dist.all_gather_object(flags, bool(ok))
         if rank == 0:
@@ -146,8 +141,8 @@ def _gatherer_worker(rank, world, port, result_path):
 
 @pytest.mark.timeout(120)
 def test_token_gatherer_world2_gloo(tmp_path):
-    """The steady-state gatherer on two gloo ranks: fixed-capacity segments, counts travelling with the payload, slots
-    reused across steps, overflow detection."""
+    """The steady-state gatherer on two gloo ranks: one slab per rank and step into fixed segments, counts travelling with
+    the payload, slots reused across steps (rebasing and the overflow flag are a device kernel: GPU tests)."""
     result = tmp_path / "result.txt"
     mp.spawn(_gatherer_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
     assert result.read_text() == "ok"
