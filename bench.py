@@ -823,6 +823,32 @@ def e2e_numbers(args, wl, rank, world, K, R, numa_cpus):
         p_collect(k)
     ms_pipe = statistics.median(timed_regions(region_of(p_submit, p_collect), R, world, dev))
 
+    # (4) the ceiling of the host link: the SAME pinned batches copied host->device with nothing else running (no kernels),
+    #     `depth` copies in flight per rank, all ranks at once.  At N > 1 this is what the box's PCIe / host-memory fabric can
+    #     feed; the end-to-end number is reported as a fraction of it.
+    sinks = [torch.empty_like(pinned[0], device=dev) for _ in range(depth)]
+    n_max_rows = min(p.shape[0] for p in pinned)
+
+    def copy_region():
+        barrier()
+        t_c0 = time.perf_counter()
+        for k in range(K):
+            lane = lanes[k % depth]
+            with torch.cuda.stream(lane["stream"]):
+                sinks[k % depth][:n_max_rows].copy_(pinned[k % wl.rot][:n_max_rows], non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t_c0) * 1e3
+
+    wake_host_link()
+    for _ in range(2):
+        copy_region()
+    ms_copy = statistics.median(timed_regions(copy_region, R, world, dev))
+    copy_bytes = n_max_rows * pinned[0].shape[1] * 4
+    ceiling = {"sweeps_per_s": nb * world / (ms_copy / K * 1e-3), "ms_per_step": ms_copy / K,
+               "aggregate_h2d_gbs": copy_bytes * world / (ms_copy / K * 1e-3) / 1e9,
+               "what": "copy-only: the same pinned batches host->device on every rank at once, no kernels"}
+    del sinks
+
     main = results["forward"]
     return {"value": main["value"], "unit": UNIT, "ms_per_step": main["ms_per_step"],
             "h2d_bytes_per_step": main["h2d_bytes_per_step"], "d2h_bytes_per_step": (nb + 1) * 4,
@@ -832,6 +858,7 @@ def e2e_numbers(args, wl, rank, world, K, R, numa_cpus):
             "pillars_checksum": main["pillars_checksum"], "link_warmup_ms": args.link_warmup_ms,
             "statistic": f"median of {R} regions of {K} steps (max of CUDA-event and wall clock per region, max over ranks)",
             "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None,
+            "h2d_copy_ceiling": ceiling, "frac_of_h2d_copy_ceiling": main["value"] / ceiling["sweeps_per_s"],
             "packed_points": {**results["forward_packed"],
                               "api": "same call with batch_dict['points'] as packed [N, C] rows + 'points_frame_offsets'"},
             "module_forward_blocking": {"value": nb * world / (ms_block / K * 1e-3), "ms_per_step": ms_block / K,

@@ -281,12 +281,6 @@ int pillars_last_launch_count(void);
  * Thread-local; costs four cudaEventRecord per call while set. */
 int pillars_set_stage_events(void *const *events4);
 
-/* Pipelining hook (thread-local).  With enable != 0 the BEV scatter of subsequent pillars_encode_bev calls is enqueued on
- * `stream` instead of the call's stream, ordered after the feature kernel by an event.  The small latency-bound kernels of
- * the next batch (on a higher-priority stream) then run alongside the bandwidth-bound canvas write of this one.  The
- * caller owns the hazards: the next call that reuses the same outputs / workspace must first wait for `stream`. */
-int pillars_set_scatter_stream(void *stream, int enable);
-
 /* Grouping implementation used by pillars_voxelize / pillars_encode_bev / pillars_encode_stack (thread-local):
  *   0  automatic: the direct-mapped cell table when n_frames * cells <= 16 * n_points + 2^22 (every pillar grid of the
  *      reference's configs), else the open-addressing hash table;

@@ -27,7 +27,6 @@ EXPORTED_SYMBOLS = (
     "pillars_set_grouping",
     "pillars_set_debug_times",
     "pillars_rebase_segments",
-    "pillars_set_scatter_stream",
     "pillars_pfn_stack_in_features",
     "pillars_pfn_dense_stack",
     "pillars_encode_stack",
@@ -90,7 +89,12 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         from . import build as _build
 
         if _build.needs_build():
-            _build.build()
+            try:
+                _build.build()  # serialised across processes by a file lock, installed with an atomic rename
+            except RuntimeError:
+                if not os.path.isfile(LIB_PATH):  # no nvcc and nothing built: fail below with the library error
+                    pass
+                # (a shipped .so that is merely older than the sources is still loaded when nvcc is absent)
     if not os.path.isfile(LIB_PATH):
         raise NativeLibraryError(f"{LIB_PATH} is missing: run `python -m lidar_vision_vqa_b200.build` "
                                  "(there is no CPU/PyTorch fallback for the pillar path)")
@@ -147,8 +151,6 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                              c_void_p, c_size_t, c_void_p]
     lib.pillars_workspace_cell_row_offset.restype = c_size_t
     lib.pillars_workspace_cell_row_offset.argtypes = [c_int64, c_int32, POINTER(PillarsGrid)]
-    lib.pillars_set_scatter_stream.restype = c_int
-    lib.pillars_set_scatter_stream.argtypes = [c_void_p, c_int]
     lib.pillars_rebase_segments.restype = c_int
     lib.pillars_rebase_segments.argtypes = [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.pillars_set_debug_times.restype = c_int

@@ -36,9 +36,24 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Serialised across processes (torchrun ranks on a fresh checkout all arrive here) by an exclusive file lock; objects
+    and the library are written under temporary names and renamed into place, so nobody can dlopen a half-written file."""
+    import fcntl
+
     if not force and not needs_build():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -58,7 +73,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
+    tmp = LIB + f".tmp{os.getpid()}"
+    subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"])
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -15,10 +15,6 @@ static thread_local int g_launches_last = 0;
 static thread_local cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 static thread_local bool g_stage_on = false;
 
-static thread_local cudaStream_t g_scatter_stream = nullptr;
-static thread_local bool g_scatter_stream_on = false;
-static thread_local cudaEvent_t g_scatter_event = nullptr;
-
 static void stage_mark(int i, cudaStream_t st)
 {
     if (g_stage_on && g_stage_ev[i]) cudaEventRecord(g_stage_ev[i], st);
@@ -146,13 +142,6 @@ int pillars_set_stage_events(void *const *events4)
 {
     g_stage_on = events4 != nullptr;
     for (int i = 0; i < 4; ++i) g_stage_ev[i] = events4 ? static_cast<cudaEvent_t>(events4[i]) : nullptr;
-    return 0;
-}
-
-int pillars_set_scatter_stream(void *stream, int enable)
-{
-    g_scatter_stream = static_cast<cudaStream_t>(stream);
-    g_scatter_stream_on = enable != 0;
     return 0;
 }
 
@@ -310,13 +299,6 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
 
     if (want_bev) {
         cudaStream_t sst = st;
-        if (g_scatter_stream_on) {  // hand the bandwidth-bound canvas write to its own (lower priority) stream
-            if (!g_scatter_event && (e = cudaEventCreateWithFlags(&g_scatter_event, cudaEventDisableTiming)) != cudaSuccess)
-                return cuda_fail(e, "cudaEventCreate");
-            sst = g_scatter_stream;
-            if ((e = cudaEventRecord(g_scatter_event, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-            if ((e = cudaStreamWaitEvent(sst, g_scatter_event, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-        }
         if (out->bev &&
             (e = launch_scatter(out->pillar_features, ws.cell_row, n_frames, pfn->f_out, grid->grid[0], grid->grid[1],
                                 out->bev, scatter_variant, sst)) != cudaSuccess)

@@ -423,13 +423,12 @@ class EncodeBuffers:
 
 def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, pfn: PfnParams, *, col0: int = 0,
                buffers: Optional[EncodeBuffers] = None, with_bev: bool = True, scatter_variant: str = "auto",
-               want_membership: bool = False, want_voxels: bool = False, want_index_map: bool = False,
-               scatter_stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+               want_membership: bool = False, want_voxels: bool = False, want_index_map: bool = False
+               ) -> Dict[str, torch.Tensor]:
     """The fused path: raw points -> pillar_features / voxel_coords / voxel_num_points / pillar_count / bev.
     ``want_index_map`` adds ``cell_row`` [n_frames, ny, nx] int32 (row of the pillar in each cell, -1 = empty): a view of
     the workspace, valid until ``buffers`` is reused -- the input of the BEV tokeniser (tokens.py).
-    Everything is enqueued on the current stream; nothing synchronises.  With ``scatter_stream`` the canvas write goes to
-    that stream (ordered after the feature kernel); the caller then waits on it before reusing ``buffers``."""
+    Everything is enqueued on the current stream; nothing synchronises."""
     _check_points(points, frame_offsets)
     lib = _native.load()
     n, stride = points.shape
@@ -476,15 +475,9 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
         nx, ny, _ = grid.grid_size
         res["cell_row"] = buffers.ws[off:off + 4 * nb * ny * nx].view(torch.int32).view(nb, ny, nx)
     nat = pfn.native()
-    if scatter_stream is not None:
-        lib.pillars_set_scatter_stream(int(scatter_stream.cuda_stream), 1)
-    try:
-        check(lib.pillars_encode_bev(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
-                                     ctypes.byref(nat), ctypes.byref(out), buffers.ws.data_ptr(), buffers.ws.numel(),
-                                     SCATTER_VARIANTS[scatter_variant], _stream_ptr()), "pillars_encode_bev")
-    finally:
-        if scatter_stream is not None:
-            lib.pillars_set_scatter_stream(None, 0)
+    check(lib.pillars_encode_bev(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
+                                 ctypes.byref(nat), ctypes.byref(out), buffers.ws.data_ptr(), buffers.ws.numel(),
+                                 SCATTER_VARIANTS[scatter_variant], _stream_ptr()), "pillars_encode_bev")
     return res
 
 

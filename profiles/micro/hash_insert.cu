@@ -44,6 +44,66 @@ __global__ void k_hash(const uint32_t *keys, int n, Entry *table, uint32_t cap, 
     for (int j = 0; j < PPT; ++j) if (ok[j]) { const int i = t + j * T; slot_out[i] = (int)slot[j]; arr_out[i] = arr[j]; }
 }
 
+// The same table behind a per-CTA shared-memory stage (north_star's "shared-memory staging for the hot set"): the CTA's
+// TILE keys are first merged in a shared open-addressing set (key -> local count, local first index); one thread per
+// DISTINCT key of the tile then talks to the HBM table for the whole group.  Also counts how many keys the stage merged.
+template <int TILE>
+__global__ void k_hash_staged(const uint32_t *keys, int n, Entry *table, uint32_t cap, int32_t *slot_out, uint32_t *arr_out,
+                              unsigned long long *merged)
+{
+    constexpr int S = 2 * TILE;  // shared slots
+    __shared__ uint32_t s_key[S], s_cnt[S], s_first[S], s_base[S], s_slot[S];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < S; i += blockDim.x) { s_key[i] = 0xFFFFFFFFu; s_cnt[i] = 0; s_first[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    constexpr int PPT = TILE / 256;
+    int my_slot[PPT]; uint32_t my_rank[PPT];
+    const int base_i = blockIdx.x * TILE;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = base_i + tid + j * 256;
+        my_slot[j] = -1;
+        if (i >= n) continue;
+        const uint32_t k = keys[i];
+        uint32_t s = hash_key(k) % S;
+        while (true) {
+            const uint32_t cur = atomicCAS(&s_key[s], 0xFFFFFFFFu, k);
+            if (cur == 0xFFFFFFFFu || cur == k) break;
+            s = (s + 1 == S) ? 0u : s + 1;
+        }
+        my_slot[j] = (int)s;
+        my_rank[j] = atomicAdd(&s_cnt[s], 1u);
+        atomicMin(&s_first[s], (uint32_t)i);
+    }
+    __syncthreads();
+    unsigned local_merged = 0;
+    for (int s = tid; s < S; s += blockDim.x) {
+        if (s_key[s] == 0xFFFFFFFFu) continue;
+        const uint32_t k = s_key[s];
+        local_merged += s_cnt[s] - 1;
+        uint32_t g = (uint32_t)(((uint64_t)hash_key(k) * cap) >> 32);
+        const unsigned long long mine = ((unsigned long long)k << 32) | s_first[s];
+        while (true) {
+            unsigned long long *w = reinterpret_cast<unsigned long long *>(&table[g]);
+            const unsigned long long cur = atomicCAS(w, 0xFFFFFFFFFFFFFFFFull, mine);
+            if (cur == 0xFFFFFFFFFFFFFFFFull) break;
+            if ((uint32_t)(cur >> 32) == k) { if (mine < cur) atomicMin(w, mine); break; }
+            g = (g + 1 == cap) ? 0u : g + 1;
+        }
+        s_slot[s] = g;
+        s_base[s] = atomicAdd(&table[g].cnt, s_cnt[s]) + 1u;
+    }
+    if (local_merged) atomicAdd(merged, (unsigned long long)local_merged);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = base_i + tid + j * 256;
+        if (my_slot[j] < 0) continue;
+        slot_out[i] = (int)s_slot[my_slot[j]];
+        arr_out[i] = s_base[my_slot[j]] + my_rank[j];
+    }
+}
+
 // dense direct-address table {first, cnt}: RED.min + atomicAdd, independent of each other
 template <int PPT>
 __global__ void k_dense(const uint32_t *keys, int n, uint2 *table, uint32_t *arr_out)
@@ -96,6 +156,22 @@ int main()
         run("hash CAS+add, 4 pt/thread bs256", sizeof(Entry) * cap, d_tab, [&] { k_hash<4><<<grid(4, 256), 256>>>(d_keys, c.n, d_tab, cap, d_slot, d_arr); });
         run("hash CAS+add, 4 pt/thread bs128", sizeof(Entry) * cap, d_tab, [&] { k_hash<4><<<grid(4, 128), 128>>>(d_keys, c.n, d_tab, cap, d_slot, d_arr); });
         run("hash CAS+add, 8 pt/thread bs128", sizeof(Entry) * cap, d_tab, [&] { k_hash<8><<<grid(8, 128), 128>>>(d_keys, c.n, d_tab, cap, d_slot, d_arr); });
+        unsigned long long *d_merged; cudaMalloc(&d_merged, 8);
+        for (int tile : {256, 1024}) {
+            cudaMemset(d_merged, 0, 8);
+            char nm[96];
+            auto launch = [&] {
+                const unsigned g = (unsigned)((c.n + tile - 1) / tile);
+                if (tile == 256) k_hash_staged<256><<<g, 256>>>(d_keys, c.n, d_tab, cap, d_slot, d_arr, d_merged);
+                else k_hash_staged<1024><<<g, 256>>>(d_keys, c.n, d_tab, cap, d_slot, d_arr, d_merged);
+
+            };
+            snprintf(nm, sizeof(nm), "hash + smem stage, tile %d", tile);
+            run(nm, sizeof(Entry) * cap, d_tab, launch);
+            unsigned long long h = 0; cudaMemcpy(&h, d_merged, 8, cudaMemcpyDeviceToHost);
+            printf("      keys merged inside the CTA stage: %.2f %% of the points (8 timed runs)\n", 100.0 * h / 8.0 / c.n);
+        }
+        cudaFree(d_merged);
         run("dense min+add, 1 pt/thread bs256", 8ull * c.cells, d_dense, [&] { k_dense<1><<<grid(1, 256), 256>>>(d_keys, c.n, d_dense, d_arr); });
         run("dense min+add, 4 pt/thread bs256", 8ull * c.cells, d_dense, [&] { k_dense<4><<<grid(4, 256), 256>>>(d_keys, c.n, d_dense, d_arr); });
         run("dense min+add, 8 pt/thread bs128", 8ull * c.cells, d_dense, [&] { k_dense<8><<<grid(8, 128), 128>>>(d_keys, c.n, d_dense, d_arr); });
