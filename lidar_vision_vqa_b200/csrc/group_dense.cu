@@ -20,6 +20,7 @@
 //                    point index by a tile that is still testing "am I the first").
 //   k_place_dense    point -> its pillar's list (index list and/or 32-byte records): key -> base -> position.
 #include "group_common.cuh"
+#include <cstdlib>
 
 namespace pillars {
 
@@ -402,7 +403,8 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     // start from 0xFF bytes (counters count up from -1, a descriptor is ready once bit 63 is clear).
     {
         const size_t n_vec = ws.ff_bytes / 16;  // every piece of the region is 256-byte aligned
-        const unsigned fb = static_cast<unsigned>(tmin<size_t>((n_vec + 255) / 256, static_cast<size_t>(current_sm_count()) * 8));
+        static const int per_sm = getenv("PILLARS_FILL_PER_SM") ? atoi(getenv("PILLARS_FILL_PER_SM")) : 8;
+        const unsigned fb = static_cast<unsigned>(tmin<size_t>((n_vec + 255) / 256, static_cast<size_t>(current_sm_count()) * per_sm));
         k_fill_ff<<<fb, 256, 0, st>>>(reinterpret_cast<uint4 *>(ws.ff_begin), n_vec, debug_times_ptr());
         note_launch();
     }
