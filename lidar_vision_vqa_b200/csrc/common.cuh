@@ -35,7 +35,9 @@ struct Header {
     uint32_t total_pillars;  // G: distinct occupied cells over the batch, before the max_voxels cap
     uint32_t total_listed;   // points that fell into some cell (sum of all counts)
     uint32_t tiles_done;     // scan tiles that have finished (the last one turns frame starts into output rows)
-    uint32_t pad[12];
+    uint32_t ticket_seq;     // dense: tile tickets of the scan kernel; only ever counts up (any start value, wraps)
+    uint32_t ticket_base;    // dense: ticket_seq when this call's insert kernel started => tile id = ticket - ticket_base
+    uint32_t pad[10];
 };
 
 // One point, moved next to the other points of its pillar (32 B = one DRAM sector).
@@ -69,7 +71,6 @@ struct Workspace {
     uint32_t *long_count;           // pillars of more than 32 points listed so far, minus one (counts up from 0xFFFFFFFF)
     uint32_t *long_cursor;          // next entry of that list to be processed by the feature kernel, minus one
     HashEntry *table;               // hash: [cap]
-    uint32_t *tile_counter;         // dense: dynamic tile ids, counts up from 0xFFFFFFFF
     uint32_t *frame_new;            // dense: [B] pillars opened in each frame, minus one
     uint32_t *cell_first;           // dense: [B * cells] smallest point index of the cell; after the scan 0x80000000 | list base
     int32_t *cell_row;              // BEV index map, -1 = empty.  hash: [B * ny * nx].  dense: [B * cells], holds
@@ -147,7 +148,6 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     } else {
         w.zero_bytes = 0;
         w.ff_begin = p ? p : nullptr;
-        w.tile_counter = reinterpret_cast<uint32_t *>(take(64));
         w.long_count = reinterpret_cast<uint32_t *>(take(256));
         w.long_cursor = w.long_count ? w.long_count + 16 : nullptr;
         w.frame_new = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (nb + 1)));

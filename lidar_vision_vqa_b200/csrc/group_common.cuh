@@ -22,6 +22,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -190,13 +200,12 @@ __device__ __forceinline__ CellCoord decode_key(const P &p, uint32_t key)
 // The point's 32-byte record: coordinates relative to the pillar centre (coord * voxel + offset, two roundings as in the
 // reference, pillar_vfe.py:100-103), intensity, time, its index and its position inside the pillar's list.
 template <typename P>
-__device__ __forceinline__ void write_record(const P &p, int64_t i, const CellCoord &c, uint32_t pos, uint32_t arrival)
+__device__ __forceinline__ void make_record(const P &p, int64_t i, const CellCoord &c, uint32_t arrival, float4 &a, float4 &d)
 {
     const float cx = __fadd_rn(__fmul_rn(static_cast<float>(c.x), p.vsz[0]), p.off[0]);
     const float cy = __fadd_rn(__fmul_rn(static_cast<float>(c.y), p.vsz[1]), p.off[1]);
     const float cz = __fadd_rn(__fmul_rn(static_cast<float>(c.z), p.vsz[2]), p.off[2]);
     const float *q = p.points + i * p.stride + p.col0;
-    float4 a, d;
     a.x = __fsub_rn(__ldg(q), cx);
     a.y = __fsub_rn(__ldg(q + 1), cy);
     a.z = __fsub_rn(__ldg(q + 2), cz);
@@ -205,6 +214,13 @@ __device__ __forceinline__ void write_record(const P &p, int64_t i, const CellCo
     d.y = 0.f;  // walk-control flags, set by the feature kernel in its staged copy
     d.z = __uint_as_float(static_cast<uint32_t>(i));
     d.w = __uint_as_float(arrival);
+}
+
+template <typename P>
+__device__ __forceinline__ void write_record(const P &p, int64_t i, const CellCoord &c, uint32_t pos, uint32_t arrival)
+{
+    float4 a, d;
+    make_record(p, i, c, arrival, a, d);
     float4 *dst = reinterpret_cast<float4 *>(p.records + pos);
     dst[0] = a;
     dst[1] = d;

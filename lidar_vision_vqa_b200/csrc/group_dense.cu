@@ -20,7 +20,7 @@
 //                    point index by a tile that is still testing "am I the first").
 //   k_place_dense    point -> its pillar's list (index list and/or 32-byte records): key -> base -> position.
 #include "group_common.cuh"
-#include <cstdlib>
+
 
 namespace pillars {
 
@@ -28,6 +28,8 @@ namespace {
 
 constexpr int kScanThreads = 512;
 constexpr int kScanPer = kTile / kScanThreads;  // 2
+constexpr uint32_t kDenseLookGroup = kScanThreads;  // scan tiles per look-back group: one descriptor per thread
+
 constexpr uint32_t kBaseTag = 0x80000000u;
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -50,14 +52,23 @@ __global__ void __launch_bounds__(kGroupThreads, 8)
 k_insert_dense(const float *__restrict__ points, int64_t n, int stride, int col0, const int32_t *__restrict__ frame_offsets,
                int nb, GridDev gd, uint32_t *__restrict__ cell_first, uint32_t *__restrict__ cell_cnt,
                int32_t *__restrict__ point_key, uint32_t *__restrict__ point_arrival, uint32_t *__restrict__ frame_new,
-               int vec_ok, unsigned long long *dbg)
+               int vec_ok, Header *hdr, unsigned long long *dbg)
 {
     extern __shared__ __align__(16) float s_pts[];  // [kInsTile * stride]
     __shared__ uint32_t s_cnt[2];
     __shared__ uint32_t s_claims;
 
-    pdl_trigger();  // the scan kernel may start taking SMs as this grid's CTAs retire
     const int tid = threadIdx.x, lane = tid & 31;
+    // The scan kernel's CTAs draw their tile ids from a counter that is never reset: CTA 0 notes where it stands before any
+    // of them can exist (they are launched once every CTA of this grid has passed the trigger below).
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            st_relaxed_u32(&hdr->ticket_base, ld_relaxed_u32(&hdr->ticket_seq));
+            __threadfence();
+        }
+        __syncthreads();  // no thread of this CTA triggers before the base is out
+    }
+    pdl_trigger();  // the scan kernel may start taking SMs as this grid's CTAs retire
     const int64_t tile_start = static_cast<int64_t>(blockIdx.x) * kInsTile;
     const int count = static_cast<int>(tmin<int64_t>(kInsTile, n - tile_start));
     if (tid < 2) s_cnt[tid] = 0u;
@@ -154,10 +165,8 @@ __device__ __forceinline__ unsigned long long pack_desc(unsigned long long v)
 }
 __device__ __forceinline__ unsigned long long wait_desc(const unsigned long long *p)
 {
-    unsigned long long d;
-    do {
-        d = ld_relaxed_u64(p);
-    } while (d >> 63);
+    unsigned long long d = ld_relaxed_u64(p);
+    while (d >> 63) d = ld_relaxed_u64(p);  // (a __nanosleep back-off between polls measured no better: 0 / 100 / 300 ns)
     return ((d >> 31) << 32) | (d & 0x7FFFFFFFull);
 }
 
@@ -191,7 +200,6 @@ struct ScanDenseParams {
     const int32_t *point_key;
     uint32_t *cell_first;
     int32_t *cell_row;  // count plane on entry, BEV index map on exit
-    uint32_t *tile_counter;
     unsigned long long *tile_agg, *tile_prefix;
     const uint32_t *frame_new;
     int nb;
@@ -209,7 +217,7 @@ struct ScanDenseParams {
     unsigned long long *dbg;
 };
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_constant__ ScanDenseParams p)
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan_dense(const __grid_constant__ ScanDenseParams p)
 {
     constexpr int kWarps = kScanThreads / 32;
     __shared__ uint32_t s_tile;
@@ -219,25 +227,71 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) dbg_stamp(p.dbg, 6);   // CTA resident
+    // A tile spins on its predecessors, so they must be running: ids are handed out in scheduling order.  The ticket is
+    // drawn while the insert kernel is still running (the CTAs arrive spread out in time; hundreds of them hitting one
+    // address right after the wait took 4 us to serve), from a sequence that only ever counts up.
+    if (tid == 0) s_tile = atomicAdd(&p.hdr->ticket_seq, 1u) - ld_relaxed_u32(&p.hdr->ticket_base);
     pdl_wait();     // everything below reads what the insert kernel (and the fill before it) wrote
     pdl_trigger();
     if (tid == 0) dbg_stamp(p.dbg, 7);   // (latest) insert kernel complete
     if (tid == 0) dbg_stamp(p.dbg, 8);   // (earliest) insert kernel complete
-    // A tile spins on its predecessors, so they must be running: ids are handed out in scheduling order.
-    if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1u) + 1u;
+
+    // per-frame pillar counts of the insert kernel: loaded now, scanned after this tile's aggregate is published
+    const uint32_t mv = static_cast<uint32_t>(p.gd.max_voxels);
+    const int f0 = 2 * tid;
+    uint32_t g0 = 0, g1 = 0;
+    if (f0 < p.nb) g0 = __ldcg(p.frame_new + f0) + 1u;
+    if (f0 + 1 < p.nb) g1 = __ldcg(p.frame_new + f0 + 1) + 1u;
+    __syncthreads();  // s_tile
+    const uint32_t tile = s_tile;
+    const int64_t tile_start = static_cast<int64_t>(tile) * kTile;
+    const int64_t i0 = tile_start + tid * kScanPer;
+
+    int32_t key[kScanPer];
+    if (i0 + kScanPer <= p.n) {
+        const int2 v = *reinterpret_cast<const int2 *>(p.point_key + i0);
+        key[0] = v.x;
+        key[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) key[k] = (i0 + k < p.n) ? p.point_key[i0 + k] : -1;
+    }
+    uint32_t first[kScanPer], cntm1[kScanPer];
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k)  // all gathers in flight before the first use
+        first[k] = key[k] >= 0 ? __ldcg(p.cell_first + key[k]) : 0xFFFFFFFFu;
+    // only the point that opens the pillar needs its size: a second, dependent gather for under half of the points costs
+    // less than an unconditional one for all of them (the L2 serves ~40 scattered sectors per clock, whatever their size)
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k)
+        cntm1[k] = (key[k] >= 0 && first[k] == static_cast<uint32_t>(i0 + k))
+                       ? static_cast<uint32_t>(__ldcg(p.cell_row + key[k])) : 0u;
+    unsigned long long val[kScanPer];
+    unsigned flags = 0;
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        val[k] = 0;
+        // a tagged entry (list base already written by the pillar's owner) never equals a point index
+        if (key[k] >= 0 && first[k] == static_cast<uint32_t>(i0 + k)) {
+            val[k] = (1ull << 32) | static_cast<unsigned long long>(cntm1[k] + 1u);
+            flags |= 1u << k;
+        }
+        tsum += val[k];
+    }
+    unsigned long long tile_sum;
+    const unsigned long long thr_excl = block_scan_excl<kWarps>(tsum, s_warp, lane, warp, tile_sum);
+    if (tid == 0) dbg_stamp(p.dbg, 9);   // gathers done, tile scanned
+    if (tid == 0) st_relaxed_u64(&p.tile_agg[tile], pack_desc(tile_sum));  // visible to the successors at once
 
     // ---- per-frame tables from the insert kernel's pillar counts: first-appearance id and output row at each frame start
-    const uint32_t mv = static_cast<uint32_t>(p.gd.max_voxels);
+    // (off the critical path: the successors already have this tile's aggregate)
     {
-        const int f0 = 2 * tid;
-        uint32_t g0 = 0, g1 = 0;
-        if (f0 < p.nb) g0 = __ldcg(p.frame_new + f0) + 1u;
-        if (f0 + 1 < p.nb) g1 = __ldcg(p.frame_new + f0 + 1) + 1u;
         const uint32_t r0 = min(g0, mv), r1 = min(g1, mv);
         unsigned long long total;
         const unsigned long long ex = block_scan_excl<kWarps>(
             (static_cast<unsigned long long>(g0 + g1) << 32) | static_cast<unsigned long long>(r0 + r1), s_warp, lane, warp,
-            total);  // (also orders the s_tile store before its use)
+            total);
         const uint32_t eg = static_cast<uint32_t>(ex >> 32), er = static_cast<uint32_t>(ex & 0xFFFFFFFFull);
         if (f0 < p.nb) {
             s_gstart[f0] = eg;
@@ -251,7 +305,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
             s_gstart[p.nb] = static_cast<uint32_t>(total >> 32);
             s_rowbase[p.nb] = static_cast<uint32_t>(total & 0xFFFFFFFFull);
         }
-        if (s_tile == 0) {  // tile 0 publishes the tables for the later stages
+        if (tile == 0) {  // tile 0 publishes the tables for the later stages
             if (f0 < p.nb) {
                 p.frame_gstart[f0] = eg;
                 p.frame_rowbase[f0] = er;
@@ -271,48 +325,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
         }
     }
 
-    const uint32_t tile = s_tile;
-    const int64_t tile_start = static_cast<int64_t>(tile) * kTile;
-    const int64_t i0 = tile_start + tid * kScanPer;
-
-    int32_t key[kScanPer];
-    if (i0 + kScanPer <= p.n) {
-        const int2 v = *reinterpret_cast<const int2 *>(p.point_key + i0);
-        key[0] = v.x;
-        key[1] = v.y;
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanPer; ++k) key[k] = (i0 + k < p.n) ? p.point_key[i0 + k] : -1;
-    }
-    uint32_t first[kScanPer], cntm1[kScanPer];
-#pragma unroll
-    for (int k = 0; k < kScanPer; ++k) {  // all gathers in flight before the first use
-        first[k] = key[k] >= 0 ? __ldcg(p.cell_first + key[k]) : 0xFFFFFFFFu;
-        cntm1[k] = key[k] >= 0 ? static_cast<uint32_t>(__ldcg(p.cell_row + key[k])) : 0u;
-    }
-    unsigned long long val[kScanPer];
-    unsigned flags = 0;
-    unsigned long long tsum = 0;
-#pragma unroll
-    for (int k = 0; k < kScanPer; ++k) {
-        val[k] = 0;
-        // a tagged entry (list base already written by the pillar's owner) never equals a point index
-        if (key[k] >= 0 && first[k] == static_cast<uint32_t>(i0 + k)) {
-            val[k] = (1ull << 32) | static_cast<unsigned long long>(cntm1[k] + 1u);
-            flags |= 1u << k;
-        }
-        tsum += val[k];
-    }
-    unsigned long long tile_sum;
-    const unsigned long long thr_excl = block_scan_excl<kWarps>(tsum, s_warp, lane, warp, tile_sum);
-    if (tid == 0) dbg_stamp(p.dbg, 9);   // gathers done, tile scanned
-    if (tid == 0) st_relaxed_u64(&p.tile_agg[tile], pack_desc(tile_sum));  // visible to the successors at once
-
     // look-back: aggregates of the tiles of my group that precede me (one parallel read) + prefix of the previous group
-    const uint32_t group_first = tile & ~static_cast<uint32_t>(kLookGroup - 1);
+    // (a group is as many tiles as the CTA has threads: up to 512 K points resolve in ONE hop; the thread standing at the
+    // tile's own position has no aggregate to read and fetches the previous group's prefix instead)
+    const uint32_t group_first = tile & ~static_cast<uint32_t>(kDenseLookGroup - 1);
     unsigned long long look = 0;
-    if (tid < kLookGroup && group_first + tid < tile) look = wait_desc(&p.tile_agg[group_first + tid]);
-    if (tid == kScanThreads - 1 && group_first > 0) look += wait_desc(&p.tile_prefix[group_first - 1]);
+    if (group_first + tid < tile) look = wait_desc(&p.tile_agg[group_first + tid]);
+    else if (group_first + tid == tile && group_first > 0) look = wait_desc(&p.tile_prefix[group_first - 1]);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) look += __shfl_xor_sync(kFullMask, look, s);
     if (lane == 0) s_look[warp] = look;
@@ -320,7 +339,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
     unsigned long long tile_excl = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) tile_excl += s_look[w];
-    if (tid == 0 && (tile & (kLookGroup - 1)) == kLookGroup - 1)
+    if (tid == 0 && (tile & (kDenseLookGroup - 1)) == kDenseLookGroup - 1)
         st_relaxed_u64(&p.tile_prefix[tile], pack_desc(tile_excl + tile_sum));
 
     if (tid == 0) dbg_stamp(p.dbg, 11);  // look-back resolved
@@ -365,28 +384,41 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_dense(const __grid_consta
 __global__ void __launch_bounds__(kGroupThreads) k_place_dense(const __grid_constant__ PlaceParams p)
 {
     if (threadIdx.x == 0) dbg_stamp(p.dbg, 14);
-    pdl_wait();
-    pdl_trigger();
-    if (threadIdx.x == 0) dbg_stamp(p.dbg, 16);
-    // two points per thread: both (key -> list base) gathers are in flight before either record is written
+    // two points per thread.  Keys and arrival ranks were written by the insert kernel, which had completed before the
+    // first CTA of the scan kernel passed ITS wait -- and this grid is launched only after all of them did: they are
+    // loaded while the scan is still running, only the (key -> list base) gathers need the scan's results.
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kInsTile + threadIdx.x;
     int32_t key[kInsPer];
     uint32_t arrival[kInsPer], base[kInsPer];
 #pragma unroll
     for (int k = 0; k < kInsPer; ++k) {
         const int64_t i = i0 + k * kGroupThreads;
-        key[k] = i < p.n ? p.point_slot[i] : -1;
-        arrival[k] = i < p.n ? p.point_arrival[i] : 0u;
+        key[k] = i < p.n ? __ldcg(p.point_slot + i) : -1;
+        arrival[k] = i < p.n ? __ldcg(p.point_arrival + i) : 0u;
     }
+    // ... and so are the records themselves (the points are an input of the call), all but their position
+    float4 ra[kInsPer], rd[kInsPer];
+    if (p.records) {
 #pragma unroll
-    for (int k = 0; k < kInsPer; ++k) base[k] = key[k] >= 0 ? (__ldg(p.cell_first + key[k]) & ~kBaseTag) : 0u;
+        for (int k = 0; k < kInsPer; ++k)
+            if (key[k] >= 0)
+                make_record(p, i0 + k * kGroupThreads, decode_key(p, static_cast<uint32_t>(key[k])), arrival[k], ra[k], rd[k]);
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (threadIdx.x == 0) dbg_stamp(p.dbg, 16);
+#pragma unroll
+    for (int k = 0; k < kInsPer; ++k) base[k] = key[k] >= 0 ? (__ldcg(p.cell_first + key[k]) & ~kBaseTag) : 0u;
 #pragma unroll
     for (int k = 0; k < kInsPer; ++k) {
         if (key[k] < 0) continue;
-        const int64_t i = i0 + k * kGroupThreads;
         const uint32_t pos = base[k] + arrival[k];
-        if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i);
-        if (p.records) write_record(p, i, decode_key(p, static_cast<uint32_t>(key[k])), pos, arrival[k]);
+        if (p.sorted_idx) p.sorted_idx[pos] = static_cast<uint32_t>(i0 + k * kGroupThreads);
+        if (p.records) {
+            float4 *dst = reinterpret_cast<float4 *>(p.records + pos);
+            dst[0] = ra[k];
+            dst[1] = rd[k];
+        }
     }
     if (threadIdx.x == 0) dbg_stamp(p.dbg, 17);
 }
@@ -403,8 +435,8 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     // start from 0xFF bytes (counters count up from -1, a descriptor is ready once bit 63 is clear).
     {
         const size_t n_vec = ws.ff_bytes / 16;  // every piece of the region is 256-byte aligned
-        static const int per_sm = getenv("PILLARS_FILL_PER_SM") ? atoi(getenv("PILLARS_FILL_PER_SM")) : 8;
-        const unsigned fb = static_cast<unsigned>(tmin<size_t>((n_vec + 255) / 256, static_cast<size_t>(current_sm_count()) * per_sm));
+        // (a smaller grid, leaving SM room for the insert kernel's CTAs to stage their tiles meanwhile, measured the same)
+        const unsigned fb = static_cast<unsigned>(tmin<size_t>((n_vec + 255) / 256, static_cast<size_t>(current_sm_count()) * 8));
         k_fill_ff<<<fb, 256, 0, st>>>(reinterpret_cast<uint4 *>(ws.ff_begin), n_vec, debug_times_ptr());
         note_launch();
     }
@@ -420,7 +452,7 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     const unsigned pb = static_cast<unsigned>((n + kInsTile - 1) / kInsTile);
     if ((err = launch_pdl(k_insert_dense, dim3(pb), dim3(kGroupThreads), smem, st, points, n, stride, col0, frame_offsets, nb,
                           gd, ws.cell_first, reinterpret_cast<uint32_t *>(ws.cell_row), ws.point_slot, ws.point_arrival,
-                          ws.frame_new, vec_ok, debug_times_ptr())) != cudaSuccess)
+                          ws.frame_new, vec_ok, ws.hdr, debug_times_ptr())) != cudaSuccess)
         return err;
     note_launch();
 
@@ -431,7 +463,6 @@ cudaError_t launch_group_points_dense(const float *points, int64_t n, int stride
     sp.point_key = ws.point_slot;
     sp.cell_first = ws.cell_first;
     sp.cell_row = ws.cell_row;
-    sp.tile_counter = ws.tile_counter;
     sp.tile_agg = ws.tile_desc;
     sp.tile_prefix = ws.tile_prefix;
     sp.frame_new = ws.frame_new;
