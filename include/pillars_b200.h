@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PILLARS_ABI_VERSION 4
+#define PILLARS_ABI_VERSION 5
 
 /* error codes (negative; positive values are cudaError_t) */
 #define PILLARS_E_BADARG (-1)      /* NULL pointer, bad size, unsupported combination */
@@ -272,6 +272,43 @@ int pillars_bev_tokens_dense(const float *bev, int32_t n_frames, int32_t h, int3
 /* Byte offset, inside a workspace of pillars_encode_bev for the same (n_points, n_frames, grid), of the BEV index map
  * [n_frames, ny, nx] that call leaves behind when it wrote a canvas -- the cell_row argument of pillars_bev_tokens_map. */
 size_t pillars_workspace_cell_row_offset(int64_t n_points, int32_t n_frames, const pillars_grid_t *grid);
+
+/* ---- BEV backbone convolutions (BaseBEVBackbone, backbones_2d/base_bev_backbone.py:29-112) -------------
+ * One layer = Conv2d / ConvTranspose2d (bias=False) + eval-mode BatchNorm2d(eps=1e-3) + ReLU, as ONE implicit-GEMM kernel on
+ * the tcgen05 tensor cores (tf32 operands, fp32 accumulation: what nn.Conv2d itself does on this GPU under PyTorch's default
+ * cudnn.allow_tf32).  Activations between layers are NHWC fp32.  Supported: c_in a multiple of 32; c_out in {64,128,256};
+ * (k, stride, pad) in {(3,1,1), (1,1,0), (3,2,1), (2,2,0)}; up in {2, 4} = ConvTranspose2d(kernel = stride = up), given as k = 1. */
+typedef struct {
+    int32_t c_in, c_out;
+    int32_t k, stride, pad;
+    int32_t up;        /* 1 = convolution; 2 / 4 = transposed convolution with kernel = stride = up (k = 1, stride = 1, pad = 0) */
+    int32_t relu;      /* apply ReLU after the BatchNorm shift */
+    int32_t round_out; /* store tf32-rounded activations (for layers that feed another layer of this kind) */
+} pillars_conv_t;
+
+/* Bytes of the prepared weight image of a layer. */
+size_t pillars_conv_weight_bytes(const pillars_conv_t *cv);
+
+/* Builds the image: weight is the module's tensor ([c_out,c_in,k,k] for Conv2d, [c_in,c_out,up,up] for the transposed case);
+ * bn_scale [c_out] = gamma / sqrt(running_var + eps) is folded into it (NULL = 1).  The matching shift
+ * beta - running_mean * bn_scale is passed to pillars_conv_forward.  Replaces nn.Conv2d + nn.BatchNorm2d state
+ * (base_bev_backbone.py:31-45,50-58). */
+int pillars_conv_prepare(const pillars_conv_t *cv, const float *weight, const float *bn_scale, void *image, void *stream);
+
+/* Runs the layer.  Input: in_nhwc [n_frames, h_in, w_in, c_in], or (in_nhwc == NULL) pillar rows [m, c_in] plus the BEV index
+ * map cell_row [n_frames, h_in, w_in] (-1 = empty cell) -- the dense canvas is then never read.  Output pixel (oy, ox) of
+ * channel n goes to out[b, oy', ox', out_c_off + n] of an NHWC image with out_c_total channels (out_nchw == 0) or to
+ * out[b, out_c_off + n, oy', ox'] (out_nchw != 0), (oy', ox') = (oy, ox) or, for up == 2, the four phase positions.
+ * error_word: optional device uint32, set non-zero if a bounded wait inside the kernel expired (never in a correct run).
+ * Replaces blocks[i] / deblocks[i] of BaseBEVBackbone.forward (base_bev_backbone.py:92-106). */
+int pillars_conv_forward(const pillars_conv_t *cv, const void *image, const float *bn_shift, const float *in_nhwc,
+                         const float *rows, const int32_t *cell_row, int32_t n_frames, int32_t h_in, int32_t w_in, float *out,
+                         int32_t out_c_total, int32_t out_c_off, int32_t out_nchw, uint32_t *error_word, void *stream);
+
+/* Dense canvas [n_frames, c, h, w] -> (rows of its non-zero cells, index map): the input form pillars_conv_forward and the
+ * tokeniser gather from.  rows must hold n_frames*h*w*c floats in the worst case; counter is one device uint32 (row count). */
+int pillars_canvas_to_rows(const float *bev, int32_t n_frames, int32_t c, int32_t h, int32_t w, int32_t *cell_row, float *rows,
+                           uint32_t *counter, void *stream);
 
 /* Number of kernel launches (incl. memsets) the last successful compute call on this thread enqueued. */
 int pillars_last_launch_count(void);

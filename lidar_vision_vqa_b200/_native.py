@@ -37,9 +37,13 @@ EXPORTED_SYMBOLS = (
     "pillars_bev_tokens_map",
     "pillars_bev_tokens_dense",
     "pillars_workspace_cell_row_offset",
+    "pillars_conv_weight_bytes",
+    "pillars_conv_prepare",
+    "pillars_conv_forward",
+    "pillars_canvas_to_rows",
 )
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LAYOUT_PILLAR_VFE, LAYOUT_SIMPLE2D = 0, 1
 MODE_HARD, MODE_DYNAMIC = 0, 1
 
@@ -71,6 +75,11 @@ class PillarsTokenizer(Structure):
     _fields_ = [("c_in", c_int32), ("d_model", c_int32), ("dw_weight", c_void_p), ("dw_bias", c_void_p),
                 ("proj_weight_t", c_void_p), ("proj_bias", c_void_p), ("ln_weight", c_void_p), ("ln_bias", c_void_p),
                 ("ln_eps", c_float), ("pe", c_void_p), ("background", c_void_p), ("proj_frag", c_void_p), ("proj_umma", c_void_p)]
+
+
+class PillarsConv(Structure):
+    _fields_ = [("c_in", c_int32), ("c_out", c_int32), ("k", c_int32), ("stride", c_int32), ("pad", c_int32), ("up", c_int32),
+                ("relu", c_int32), ("round_out", c_int32)]
 
 
 class NativeLibraryError(RuntimeError):
@@ -151,6 +160,15 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                              c_void_p, c_size_t, c_void_p]
     lib.pillars_workspace_cell_row_offset.restype = c_size_t
     lib.pillars_workspace_cell_row_offset.argtypes = [c_int64, c_int32, POINTER(PillarsGrid)]
+    lib.pillars_conv_weight_bytes.restype = c_size_t
+    lib.pillars_conv_weight_bytes.argtypes = [POINTER(PillarsConv)]
+    lib.pillars_conv_prepare.restype = c_int
+    lib.pillars_conv_prepare.argtypes = [POINTER(PillarsConv), c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pillars_conv_forward.restype = c_int
+    lib.pillars_conv_forward.argtypes = [POINTER(PillarsConv), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                         c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.pillars_canvas_to_rows.restype = c_int
+    lib.pillars_canvas_to_rows.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pillars_rebase_segments.restype = c_int
     lib.pillars_rebase_segments.argtypes = [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.pillars_set_debug_times.restype = c_int

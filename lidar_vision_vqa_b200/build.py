@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libpillars_b200.so")
-SOURCES = ["api.cu", "voxelize.cu", "group_dense.cu", "pfn.cu", "pfn_stream.cu", "pfn_multi.cu", "scatter.cu", "tokens.cu", "tokens_umma.cu"]
+SOURCES = ["api.cu", "voxelize.cu", "group_dense.cu", "pfn.cu", "pfn_stream.cu", "pfn_multi.cu", "scatter.cu", "tokens.cu", "tokens_umma.cu", "conv_umma.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "group_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "pillars_b200.h")]
 
 # No -use_fast_math: voxel quantisation must be IEEE fp32 (sub, true division, floor) to be bit-exact.

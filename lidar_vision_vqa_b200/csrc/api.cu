@@ -727,6 +727,91 @@ int pillars_bev_tokens_dense(const float *bev, int32_t n_frames, int32_t h, int3
     return 0;
 }
 
+// ---- BEV backbone convolutions ------------------------------------------------------------------------------------------
+static bool conv_ok(const pillars_conv_t *cv)
+{
+    if (!cv || cv->c_in < 32 || cv->c_in % 32 != 0 || (cv->c_out != 64 && cv->c_out != 128 && cv->c_out != 256)) return false;
+    if (cv->up == 2 || cv->up == 4) return cv->k == 1 && cv->stride == 1 && cv->pad == 0;
+    if (cv->up != 1) return false;
+    return (cv->k == 3 && cv->stride == 1 && cv->pad == 1) || (cv->k == 1 && cv->stride == 1 && cv->pad == 0) ||
+           (cv->k == 3 && cv->stride == 2 && cv->pad == 1) || (cv->k == 2 && cv->stride == 2 && cv->pad == 0);
+}
+
+size_t pillars_conv_weight_bytes(const pillars_conv_t *cv)
+{
+    if (!conv_ok(cv)) return 0;
+    const size_t taps = cv->up > 1 ? 1 : static_cast<size_t>(cv->k) * cv->k;
+    return static_cast<size_t>(cv->up) * cv->up * (cv->c_in / 32) * taps * cv->c_out * 128;
+}
+
+int pillars_conv_prepare(const pillars_conv_t *cv, const float *weight, const float *bn_scale, void *image, void *stream)
+{
+    if (!conv_ok(cv)) return fail(PILLARS_E_UNSUPPORTED, "convolution shape outside the instantiated set");
+    if (!weight || !image) return fail(PILLARS_E_BADARG, "NULL weight / image");
+    g_launches = 0;
+    cudaError_t e = launch_conv_wimg(weight, bn_scale, cv->c_in, cv->c_out, cv->k, cv->up, static_cast<float *>(image),
+                                     static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "conv_prepare");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_conv_forward(const pillars_conv_t *cv, const void *image, const float *bn_shift, const float *in_nhwc,
+                         const float *rows, const int32_t *cell_row, int32_t n_frames, int32_t h_in, int32_t w_in, float *out,
+                         int32_t out_c_total, int32_t out_c_off, int32_t out_nchw, uint32_t *error_word, void *stream)
+{
+    if (!conv_ok(cv)) return fail(PILLARS_E_UNSUPPORTED, "convolution shape outside the instantiated set");
+    if (!image || !bn_shift || !out) return fail(PILLARS_E_BADARG, "NULL image / shift / out");
+    if (!in_nhwc && !(rows && cell_row)) return fail(PILLARS_E_BADARG, "neither a dense input nor (rows, cell_row)");
+    if (n_frames < 0 || h_in < 1 || w_in < 1) return fail(PILLARS_E_BADARG, "bad image shape");
+    if (out_c_off < 0 || out_c_off + cv->c_out > out_c_total || (out_nchw == 0 && (out_c_total % 4 != 0 || out_c_off % 4 != 0)))
+        return fail(PILLARS_E_BADARG, "bad output channel window");
+    g_launches = 0;
+    if (n_frames == 0) {
+        g_launches_last = 0;
+        return 0;
+    }
+    ConvJob j{};
+    j.in = in_nhwc;
+    j.rows = in_nhwc ? nullptr : rows;
+    j.cell_row = in_nhwc ? nullptr : cell_row;
+    j.wimg = image;
+    j.shift = bn_shift;
+    j.out = out;
+    j.nb = n_frames;
+    j.h_in = h_in;
+    j.w_in = w_in;
+    j.c_in = cv->c_in;
+    j.c_out = cv->c_out;
+    j.k = cv->k;
+    j.stride = cv->stride;
+    j.pad = cv->pad;
+    j.up = cv->up;
+    j.out_c_total = out_c_total;
+    j.out_c_off = out_c_off;
+    j.out_nchw = out_nchw;
+    j.relu = cv->relu;
+    j.round_out = cv->round_out;
+    j.error = error_word;
+    cudaError_t e = launch_conv_umma(j, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidValue) return fail(PILLARS_E_UNSUPPORTED, "convolution geometry not instantiated");
+    if (e != cudaSuccess) return cuda_fail(e, "conv_forward");
+    g_launches_last = g_launches;
+    return 0;
+}
+
+int pillars_canvas_to_rows(const float *bev, int32_t n_frames, int32_t c, int32_t h, int32_t w, int32_t *cell_row, float *rows,
+                           uint32_t *counter, void *stream)
+{
+    if (!bev || !cell_row || !rows || !counter) return fail(PILLARS_E_BADARG, "NULL argument");
+    if (n_frames < 0 || c < 1 || h < 1 || w < 1) return fail(PILLARS_E_BADARG, "bad canvas shape");
+    g_launches = 0;
+    cudaError_t e = launch_canvas_to_rows(bev, n_frames, c, h, w, cell_row, rows, counter, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "canvas_to_rows");
+    g_launches_last = g_launches;
+    return 0;
+}
+
 size_t pillars_workspace_cell_row_offset(int64_t n_points, int32_t n_frames, const pillars_grid_t *grid)
 {
     if (!grid || n_points < 0 || n_frames < 0) return 0;

@@ -385,6 +385,23 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
 cudaError_t launch_tokens_prepare(const TokenizerDev &tk, const float *geom, const int32_t *sid, int h, int w, const float *w1,
                                   const float *b1, const float *w2t, const float *b2, const float *view, float *pe, float *bg,
                                   float *wfrag, cudaStream_t st);
+// One convolution layer of the BEV backbone (conv_umma.cu)
+struct ConvJob {
+    const float *in;           // NHWC [nb, h_in, w_in, c_in], or NULL when the input is gathered:
+    const float *rows;         // [M, c_in] pillar rows + cell_row [nb, h_in, w_in] (-1 = empty cell)
+    const int32_t *cell_row;
+    const void *wimg;          // launch_conv_wimg's image
+    const float *shift;        // [c_out]
+    float *out;
+    int nb, h_in, w_in, c_in, c_out;
+    int k, stride, pad;        // (3,1,1) (3,2,1) (2,2,0) (1,1,0)
+    int up;                    // 1, or 2 = transposed convolution with kernel = stride = 2 (k = 1 per phase)
+    int out_c_total, out_c_off, out_nchw;
+    int relu, round_out;       // round_out: store tf32-rounded values (the next layer's tensor cores would truncate them)
+    uint32_t *error;
+};
+cudaError_t launch_conv_wimg(const float *weight, const float *scale, int c_in, int c_out, int k, int up, float *img, cudaStream_t st);
+cudaError_t launch_conv_umma(const ConvJob &job, cudaStream_t st);
 cudaError_t launch_canvas_to_rows(const float *bev, int nb, int c, int h, int w, int32_t *cell_row, float *rows,
                                   uint32_t *counter, cudaStream_t st);
 cudaError_t launch_bev_tokens(const TokenizerDev &tk, const float *feats, const int32_t *cell_row, int nb, int h, int w,

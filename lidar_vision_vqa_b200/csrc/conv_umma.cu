@@ -1,0 +1,450 @@
+// 2-D convolutions of the BEV backbone (base_bev_backbone.py:29-69) as implicit GEMMs on the 5th-generation tensor cores.
+//
+//   out[b, oy, ox, n] = relu( shift[n] + sum_{ky, kx, c} in[b, oy * s + ky - pad, ox * s + kx - pad, c] * w'[n, c, ky, kx] )
+//
+// with w' = bn_scale[n] * w (eval-mode BatchNorm folded into the weights, base_bev_backbone.py:36 eps = 1e-3) and tf32 operands /
+// fp32 accumulation (what the reference's own nn.Conv2d does on this GPU under torch.backends.cudnn.allow_tf32 = True).
+//
+// One CTA computes T stacked 16 x 8 patches of output pixels (M = 128 rows of the MMA each) for ALL output channels
+// (N = 64 / 128 / 256 accumulator columns each, T * N <= 512 columns of tensor memory).  Activations are NHWC, so the 32
+// channels of one pixel are one 128-byte row of a K-major, 128-byte-swizzled operand tile.  The point of the design:
+//
+//   * ONE halo tile per 32-channel block serves all k x k taps.  The tensor core applies the 128-byte swizzle to ABSOLUTE
+//     shared-memory address bits (profiles/micro/umma_shifted_desc.cu: any start row, any 16-byte-multiple group stride,
+//     base offset 0), so tap (ky, kx) is the same buffer behind a descriptor that starts (ky * pitch + kx) pixel rows further
+//     and strides `pitch` rows between its 8-row groups.  Activation traffic from L2 is (halo / patch) ~ 1.3x instead of 9x.
+//   * stride-2 layers store the halo as four parity planes (even/odd row x even/odd column); every tap is again a shifted
+//     view of one plane.  The first layer can gather its pixels from the PILLAR ROWS through the BEV index map: the dense
+//     canvas (1 GiB at 16 x 64 x 512^2) is never read -- or written, if nothing else wants it.
+//   * weights arrive as a ready-made shared-memory image (K-major, swizzled, BN scale folded, rounded to tf32), one bulk
+//     copy per (channel block, tap), shared by the T patches.
+//
+// Warp roles (192 threads): warps 0-3 load the halo with cp.async (zero fill = padding) and later run the epilogue out of
+// tensor memory (thread = accumulator lane = output pixel); warp 4 issues the MMAs; warp 5 issues the weight copies.
+#include "common.cuh"
+
+namespace pillars {
+
+namespace {
+
+constexpr int kConvThreads = 192;
+constexpr int kLoaders = 128;
+constexpr int kPatchW = 8, kPatchH = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// K-major, 128-byte swizzle; sbo = bytes between 8-row groups (any multiple of 16: the swizzle follows the absolute address)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo)
+{
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// bounded: a set-up mistake becomes an error code, not a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity, volatile uint32_t *abort_flag)
+{
+    for (uint32_t spin = 0; spin < (1u << 15); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+        if (ok) return true;
+        if (*abort_flag) return false;
+    }
+    *abort_flag = 1u;
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, bool valid)
+{
+    const uint32_t n = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\ttcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ float round_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct ConvParams {
+    const float *in;          // NHWC [nb, h_in, w_in, c_in] (dense input)
+    const float *rows;        // [M, c_in] pillar rows (gathered input), with cell_row [nb, h_in, w_in]
+    const int32_t *cell_row;
+    const uint8_t *wimg;      // [phase][c_in / 32][taps][N x 128 B] shared-memory images
+    const float *shift;       // [N]
+    float *out;
+    int nb, h_in, w_in, c_in;
+    int h_out, w_out;         // output pixels of the convolution proper
+    int stride, pad, taps;
+    int plane_rows;           // stride 2: pixel rows of one parity plane
+    int pitch;                // pixel rows between vertically adjacent pixels of the halo (or of a plane)
+    int stage_rows;           // pixel rows (128 B each) of one halo stage
+    int tap_off[9];           // start of each tap's view, in pixel rows
+    int tiles_x, tiles_y;
+    // where an output pixel goes: (oy * out_mul + ph_y, ox * out_mul + ph_x) of a [nb, out_h, out_w] image with out_c_total
+    // channels, this layer's starting at out_c_off; phases (transposed convolution) are blockIdx.z
+    int out_mul, out_h, out_w, out_c_total, out_c_off, out_nchw;
+    int relu, round_out;
+    uint32_t *error;          // device word: nonzero when a bounded wait expired
+};
+
+template <int N, int T, int SA, int SB>
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_constant__ ConvParams p)
+{
+    extern __shared__ __align__(1024) uint8_t s_raw[];
+    __shared__ uint64_t s_bar[2 * SA + 2 * SB + 1];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_abort_word;
+    __shared__ float s_shift[N];
+    volatile uint32_t *const s_abort = &s_abort_word;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *const s_al = s_raw + ((1024u - (smem_u32(s_raw) & 1023u)) & 1023u);
+    const uint32_t a_bytes = (static_cast<uint32_t>(p.stage_rows) * 128u + 1023u) & ~1023u;
+    constexpr uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
+    const uint32_t a0 = smem_u32(s_al), b0 = a0 + SA * a_bytes;
+    const uint32_t bar0 = smem_u32(s_bar);
+    const uint32_t a_full = bar0, a_empty = bar0 + 8u * SA, b_full = bar0 + 16u * SA, b_empty = b_full + 8u * SB,
+                   acc_full = b_empty + 8u * SB;
+    constexpr uint32_t tmem_cols = (T * N <= 32) ? 32u : (T * N <= 64) ? 64u : (T * N <= 128) ? 128u : (T * N <= 256) ? 256u : 512u;
+
+    // ---- tile of this CTA
+    const int tiles_per_frame = p.tiles_x * p.tiles_y;
+    const int b = blockIdx.x / tiles_per_frame, tr = blockIdx.x - b * tiles_per_frame;
+    const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+    const int y0 = ty * (kPatchH * T), x0 = tx * kPatchW;
+    const int phase = blockIdx.z;
+    const int cbn = p.c_in >> 5;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(a_full + 8u * i, kLoaders);
+            mbar_init(a_empty + 8u * i, 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(b_full + 8u * i, 1);
+            mbar_init(b_empty + 8u * i, 1);
+        }
+        mbar_init(acc_full, 1);
+        s_abort_word = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < N; i += kConvThreads) s_shift[i] = __ldg(p.shift + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < 4) {
+        // ================================ halo loaders ===========================================================================
+        const int ch = tid & 7;           // 16-byte chunk of the pixel's 128-byte row
+        const int items = p.stage_rows;   // pixel rows per stage; this thread takes rows (tid >> 3) + 16 j
+        for (int cb = 0; cb < cbn; ++cb) {
+            const int sa = cb % SA;
+            if (cb >= SA && !mbar_wait(a_empty + 8u * sa, ((cb / SA) - 1) & 1u, s_abort)) break;
+            const uint32_t stage = a0 + sa * a_bytes;
+            for (int px = tid >> 3; px < items; px += kLoaders / 8) {
+                int iy, ix;
+                if (p.stride == 1) {
+                    const int hy = px / p.pitch, hx = px - hy * p.pitch;
+                    iy = y0 - p.pad + hy;
+                    ix = x0 - p.pad + hx;
+                } else {
+                    const int plane = px / p.plane_rows, rem = px - plane * p.plane_rows;
+                    const int q = rem / p.pitch, qx = rem - q * p.pitch;
+                    iy = 2 * (y0 + q - 1) + (plane >> 1);
+                    ix = 2 * (x0 + qx - 1) + (plane & 1);
+                }
+                bool valid = iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in;
+                const float *src = p.in;
+                if (p.rows) {  // gathered input: the pixel's channels are a pillar row, or the cell is empty
+                    int32_t r = -1;
+                    if (valid) r = __ldg(p.cell_row + (static_cast<size_t>(b) * p.h_in + iy) * p.w_in + ix);
+                    valid = r >= 0;
+                    src = p.rows + static_cast<size_t>(valid ? r : 0) * p.c_in + cb * 32 + ch * 4;
+                } else {
+                    src = p.in + ((static_cast<size_t>(b) * p.h_in + (valid ? iy : 0)) * p.w_in + (valid ? ix : 0)) * p.c_in + cb * 32 + ch * 4;
+                }
+                cp_async16_zfill(stage + static_cast<uint32_t>(px) * 128u + (static_cast<uint32_t>(ch ^ (px & 7)) << 4), src, valid);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            fence_async_smem();  // this thread's writes are in shared memory: make them visible to the tensor core's proxy
+            mbar_arrive(a_full + 8u * sa);
+        }
+        // ================================ epilogue ===============================================================================
+        if (mbar_wait(acc_full, 0u, s_abort)) {
+            tc_fence_after();
+            const int r = tid >> 3, c = tid & 7;  // accumulator lane = MMA row = patch pixel (r, c)
+#pragma unroll 1
+            for (int t = 0; t < T; ++t) {
+                const int oy = y0 + kPatchH * t + r, ox = x0 + c;
+                const bool live = oy < p.h_out && ox < p.w_out;
+                const int py = oy * p.out_mul + phase / p.out_mul, pxo = ox * p.out_mul + phase % p.out_mul;
+#pragma unroll 1
+                for (int n0 = 0; n0 < N; n0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem + (static_cast<uint32_t>(32 * warp) << 16) + static_cast<uint32_t>(t * N + n0), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = v[j] + s_shift[n0 + j];
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (p.round_out) x = round_tf32(x);
+                        v[j] = x;
+                    }
+                    if (!live) continue;
+                    if (p.out_nchw) {
+                        float *dst = p.out + ((static_cast<size_t>(b) * p.out_c_total + p.out_c_off + n0) * p.out_h + py) * p.out_w + pxo;
+                        const size_t cs = static_cast<size_t>(p.out_h) * p.out_w;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[j * cs] = v[j];
+                    } else {
+                        float4 *dst = reinterpret_cast<float4 *>(
+                            p.out + ((static_cast<size_t>(b) * p.out_h + py) * p.out_w + pxo) * p.out_c_total + p.out_c_off + n0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issue ==============================================================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(N);
+            const uint32_t sbo = static_cast<uint32_t>(p.pitch) * 128u;
+            const uint32_t tile_step = static_cast<uint32_t>(kPatchH * p.pitch) * 128u;
+            uint32_t accumulate = 0;
+            bool ok = true;
+            int i = 0;
+            for (int cb = 0; cb < cbn && ok; ++cb) {
+                const int sa = cb % SA;
+                ok = mbar_wait(a_full + 8u * sa, (cb / SA) & 1u, s_abort);
+                const uint32_t stage = a0 + sa * a_bytes;
+                for (int tap = 0; tap < p.taps && ok; ++tap, ++i) {
+                    const int sb = i % SB;
+                    ok = mbar_wait(b_full + 8u * sb, (i / SB) & 1u, s_abort);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t av = stage + static_cast<uint32_t>(p.tap_off[tap]) * 128u, bv = b0 + sb * b_bytes;
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_tf32(tmem + static_cast<uint32_t>(t * N), umma_desc(av + t * tile_step + k * 32u, sbo),
+                                      umma_desc(bv + k * 32u, 1024u), idesc, k == 0 ? accumulate : 1u);
+                        }
+                    }
+                    accumulate = 1u;
+                    umma_commit(b_empty + 8u * sb);
+                }
+                umma_commit(a_empty + 8u * sa);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ================================ weight copies ==========================================================================
+        if (lane == 0) {
+            const uint8_t *src = p.wimg + static_cast<size_t>(phase) * cbn * p.taps * b_bytes;
+            const int total = cbn * p.taps;
+            for (int i = 0; i < total; ++i) {
+                const int sb = i % SB;
+                if (i >= SB && !mbar_wait(b_empty + 8u * sb, ((i / SB) - 1) & 1u, s_abort)) break;
+                mbar_expect_tx(b_full + 8u * sb, b_bytes);
+                bulk_g2s(b0 + sb * b_bytes, src + static_cast<size_t>(i) * b_bytes, b_bytes, b_full + 8u * sb);
+            }
+        }
+    }
+    if (*s_abort && tid == 0 && p.error) atomicExch(p.error, 0xC0DE0000u | static_cast<uint32_t>(blockIdx.x & 0xFFFF));
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// Shared-memory image of the weights: [phase][c_in / 32][tap][n][128 B], chunk c of row n at (c ^ (n & 7)) * 16 -- exactly what
+// one bulk copy per (channel block, tap) must put behind the B descriptor.  BN scale folded in, rounded to nearest tf32.
+//   conv:            weight [c_out, c_in, k, k]   (nn.Conv2d)
+//   transposed (up): weight [c_in, c_out, up, up] (nn.ConvTranspose2d with kernel = stride = up): phase = (dy, dx)
+__global__ void k_conv_wimg(const float *__restrict__ weight, const float *__restrict__ scale, int c_in, int c_out, int k, int up,
+                            float *__restrict__ img)
+{
+    const int taps = up > 1 ? 1 : k * k, phases = up * up, cbn = c_in >> 5;
+    const int64_t total = static_cast<int64_t>(phases) * cbn * taps * c_out * 8;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i & 7);
+    int64_t r = i >> 3;
+    const int n = static_cast<int>(r % c_out); r /= c_out;
+    const int tap = static_cast<int>(r % taps); r /= taps;
+    const int cb = static_cast<int>(r % cbn);
+    const int phase = static_cast<int>(r / cbn);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int ci = cb * 32 + c * 4 + e;
+        float w;
+        if (up > 1) w = weight[((static_cast<int64_t>(ci) * c_out + n) * up + phase / up) * up + phase % up];
+        else w = weight[(static_cast<int64_t>(n) * c_in + ci) * taps + tap];
+        v[e] = round_tf32(scale ? w * scale[n] : w);
+    }
+    const int64_t block = (static_cast<int64_t>(phase) * cbn + cb) * taps + tap;
+    float *dst = img + block * c_out * 32 + static_cast<int64_t>(n) * 32 + ((c ^ (n & 7)) << 2);
+    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int N, int T, int SA, int SB>
+cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
+{
+    const size_t a_bytes = (static_cast<size_t>(p.stage_rows) * 128 + 1023) & ~static_cast<size_t>(1023);
+    const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 1024;
+    if (smem > 226 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const dim3 grid(static_cast<unsigned>(p.nb * p.tiles_x * p.tiles_y), 1, static_cast<unsigned>(phases));
+    k_conv_umma<N, T, SA, SB><<<grid, kConvThreads, smem, st>>>(p);
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_conv_wimg(const float *weight, const float *scale, int c_in, int c_out, int k, int up, float *img, cudaStream_t st)
+{
+    const int taps = up > 1 ? 1 : k * k;
+    const int64_t total = static_cast<int64_t>(up) * up * (c_in >> 5) * taps * c_out * 8;
+    k_conv_wimg<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(weight, scale, c_in, c_out, k, up, img);
+    note_launch();
+    return cudaGetLastError();
+}
+
+// Geometry of one layer -> kernel parameters.  Returns cudaErrorInvalidValue for shapes outside the instantiated set.
+cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
+{
+    ConvParams p{};
+    p.in = j.in;
+    p.rows = j.rows;
+    p.cell_row = j.cell_row;
+    p.wimg = static_cast<const uint8_t *>(j.wimg);
+    p.shift = j.shift;
+    p.out = j.out;
+    p.nb = j.nb;
+    p.h_in = j.h_in;
+    p.w_in = j.w_in;
+    p.c_in = j.c_in;
+    p.stride = j.stride;
+    p.pad = j.pad;
+    p.taps = j.k * j.k;
+    p.relu = j.relu;
+    p.round_out = j.round_out;
+    p.error = j.error;
+    p.h_out = (j.h_in + 2 * j.pad - j.k) / j.stride + 1;
+    p.w_out = (j.w_in + 2 * j.pad - j.k) / j.stride + 1;
+    p.out_mul = j.up;
+    p.out_h = p.h_out * j.up;
+    p.out_w = p.w_out * j.up;
+    p.out_c_total = j.out_c_total;
+    p.out_c_off = j.out_c_off;
+    p.out_nchw = j.out_nchw;
+    const int phases = j.up * j.up;
+    if (j.c_in % 32 != 0 || j.c_in < 32 || (j.stride != 1 && j.stride != 2) || j.k < 1 || j.k > 3 || (j.up != 1 && j.up != 2 && j.up != 4) ||
+        (j.up > 1 && (j.k != 1 || j.stride != 1)) || (j.rows && !j.cell_row) || (!j.rows && !j.in) || p.h_out < 1 || p.w_out < 1)
+        return cudaErrorInvalidValue;
+    if (j.stride == 2 && !((j.k == 3 && j.pad == 1) || (j.k == 2 && j.pad == 0))) return cudaErrorInvalidValue;
+    if (j.stride == 1 && j.pad != (j.k - 1) / 2) return cudaErrorInvalidValue;
+
+    // patches per CTA: as many as tensor memory (512 columns) and shared memory allow
+    int T;
+    if (j.stride == 1) T = j.c_out == 256 ? 2 : 4;
+    else T = 1;
+    while (T > 1 && kPatchH * (T / 2) >= p.h_out) T /= 2;  // small images: do not pad the patch stack past the image
+    if (j.stride == 1) {
+        p.pitch = kPatchW + j.k - 1;
+        p.stage_rows = (kPatchH * T + j.k - 1) * p.pitch;
+        for (int ky = 0; ky < j.k; ++ky)
+            for (int kx = 0; kx < j.k; ++kx) p.tap_off[ky * j.k + kx] = ky * p.pitch + kx;
+    } else {
+        p.pitch = kPatchW + 1;
+        p.plane_rows = (kPatchH * T + 1) * p.pitch;
+        p.stage_rows = 4 * p.plane_rows;
+        for (int ky = 0; ky < j.k; ++ky)
+            for (int kx = 0; kx < j.k; ++kx) {
+                const int dy = ky - j.pad, dx = kx - j.pad;  // -1, 0, 1 (3x3 pad 1) or 0, 1 (2x2 pad 0)
+                const int py = dy & 1, px = dx & 1;
+                const int qy = (dy < 0 ? -1 : 0) + 1, qx = (dx < 0 ? -1 : 0) + 1;  // floor(d / 2) + 1: planes keep one leading row / column
+                p.tap_off[ky * j.k + kx] = (py * 2 + px) * p.plane_rows + qy * p.pitch + qx;
+            }
+    }
+    p.tiles_y = (p.h_out + kPatchH * T - 1) / (kPatchH * T);
+    p.tiles_x = (p.w_out + kPatchW - 1) / kPatchW;
+
+#define CONV_CASE(n, t, sa, sb) \
+    if (j.c_out == n && T == t) return launch_one<n, t, sa, sb>(p, phases, st)
+    if (j.stride == 1) {
+        CONV_CASE(64, 4, 2, 4);
+        CONV_CASE(64, 2, 2, 4);
+        CONV_CASE(64, 1, 2, 4);
+        CONV_CASE(128, 4, 2, 3);
+        CONV_CASE(128, 2, 2, 3);
+        CONV_CASE(128, 1, 2, 3);
+        CONV_CASE(256, 2, 2, 3);
+        CONV_CASE(256, 1, 2, 3);
+    } else {
+        CONV_CASE(64, 1, 2, 4);
+        CONV_CASE(128, 1, 2, 3);
+        CONV_CASE(256, 1, 1, 3);
+    }
+#undef CONV_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pillars

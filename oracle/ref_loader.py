@@ -141,6 +141,27 @@ def cuda_is_identity():
         torch.Tensor.cuda = orig
 
 
+def load_bev_backbone():
+    """The unmodified ``BaseBEVBackbone`` (pcdet/models/backbones_2d/base_bev_backbone.py:6).  The file uses ``np.int``
+    (:62), which numpy >= 1.24 no longer has: the alias is restored on the numpy module while the class is used -- a
+    numpy-version shim, not a change to the reference."""
+    if "bb" in _CACHE:
+        return _CACHE["bb"]
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+    import numpy as np
+
+    if not hasattr(np, "int"):
+        np.int = int  # noqa: NPY001
+    if "_ref_pcdet" not in sys.modules:
+        pkg = types.ModuleType("_ref_pcdet")
+        pkg.__path__ = []
+        sys.modules["_ref_pcdet"] = pkg
+    mod = _load("_ref_pcdet.base_bev_backbone", "models/backbones_2d/base_bev_backbone.py")
+    _CACHE["bb"] = mod.BaseBEVBackbone
+    return _CACHE["bb"]
+
+
 # ---- src/encoder-decoder: VATLiDAR (the first consumer of the BEV canvas, SURVEY 8f-2) ------------------------------
 _ED_MODELS = os.path.join(REFERENCE_ROOT, "src", "encoder-decoder", "training", "models")
 

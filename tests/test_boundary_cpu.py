@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_native.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pillars_abi_version() == _native.ABI_VERSION == 4
+    assert lib.pillars_abi_version() == _native.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header_sizes():
