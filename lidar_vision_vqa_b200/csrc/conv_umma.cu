@@ -30,6 +30,7 @@ namespace {
 constexpr int kConvThreads = 192;
 constexpr int kLoaders = 128;
 constexpr int kPatchW = 8, kPatchH = 16;
+constexpr int kMaxStageRows = 672;  // (16 * 4 + 2) * 10 = 660 (3x3 stride 1, four patches); 4 * 17 * 9 = 612 (stride 2)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 // K-major, 128-byte swizzle; sbo = bytes between 8-row groups (any multiple of 16: the swizzle follows the absolute address)
@@ -132,6 +133,7 @@ struct ConvParams {
     // channels, this layer's starting at out_c_off; phases (transposed convolution) are blockIdx.z
     int out_mul, out_h, out_w, out_c_total, out_c_off, out_nchw;
     int relu, round_out;
+    int pair;                 // transposed convolution: two dx phases per accumulator (N = 2 * c_out)
     uint32_t *error;          // device word: nonzero when a bounded wait expired
 };
 
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_cons
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_abort_word;
     __shared__ float s_shift[N];
+    __shared__ int32_t s_src[kMaxStageRows];
     volatile uint32_t *const s_abort = &s_abort_word;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_cons
         s_abort_word = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < N; i += kConvThreads) s_shift[i] = __ldg(p.shift + i);
+    for (int i = tid; i < (p.pair ? N / 2 : N); i += kConvThreads) s_shift[i] = __ldg(p.shift + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -188,35 +191,42 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_cons
 
     if (warp < 4) {
         // ================================ halo loaders ===========================================================================
-        const int ch = tid & 7;           // 16-byte chunk of the pixel's 128-byte row
-        const int items = p.stage_rows;   // pixel rows per stage; this thread takes rows (tid >> 3) + 16 j
+        // Where each pixel row of the stage comes from is the same for every channel block: worked out once per CTA (the
+        // divisions, the bounds checks and -- for a gathered input -- the index-map lookups, all independent loads), kept in
+        // shared memory as the pixel's index in the source array (-1 = zero fill: padding, empty cell, outside the image).
+        for (int px = tid; px < p.stage_rows; px += kLoaders) {
+            int iy, ix;
+            if (p.stride == 1) {
+                const int hy = px / p.pitch, hx = px - hy * p.pitch;
+                iy = y0 - p.pad + hy;
+                ix = x0 - p.pad + hx;
+            } else {
+                const int plane = px / p.plane_rows, rem = px - plane * p.plane_rows;
+                const int q = rem / p.pitch, qx = rem - q * p.pitch;
+                iy = 2 * (y0 + q - 1) + (plane >> 1);
+                ix = 2 * (x0 + qx - 1) + (plane & 1);
+            }
+            int32_t src = -1;
+            if (iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in) {
+                src = (b * p.h_in + iy) * p.w_in + ix;
+                if (p.rows) src = __ldg(p.cell_row + src);  // the pixel's channels are a pillar row, or the cell is empty
+            }
+            s_src[px] = src;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
+        const int ch = tid & 7;           // 16-byte chunk of the pixel's 128-byte row; this thread takes rows (tid >> 3) + 16 j
+        const float *const base = (p.rows ? p.rows : p.in) + ch * 4;
+        const uint32_t dst0 = static_cast<uint32_t>(tid >> 3) * 128u + (static_cast<uint32_t>(ch ^ ((tid >> 3) & 7)) << 4);
         for (int cb = 0; cb < cbn; ++cb) {
             const int sa = cb % SA;
             if (cb >= SA && !mbar_wait(a_empty + 8u * sa, ((cb / SA) - 1) & 1u, s_abort)) break;
-            const uint32_t stage = a0 + sa * a_bytes;
-            for (int px = tid >> 3; px < items; px += kLoaders / 8) {
-                int iy, ix;
-                if (p.stride == 1) {
-                    const int hy = px / p.pitch, hx = px - hy * p.pitch;
-                    iy = y0 - p.pad + hy;
-                    ix = x0 - p.pad + hx;
-                } else {
-                    const int plane = px / p.plane_rows, rem = px - plane * p.plane_rows;
-                    const int q = rem / p.pitch, qx = rem - q * p.pitch;
-                    iy = 2 * (y0 + q - 1) + (plane >> 1);
-                    ix = 2 * (x0 + qx - 1) + (plane & 1);
-                }
-                bool valid = iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in;
-                const float *src = p.in;
-                if (p.rows) {  // gathered input: the pixel's channels are a pillar row, or the cell is empty
-                    int32_t r = -1;
-                    if (valid) r = __ldg(p.cell_row + (static_cast<size_t>(b) * p.h_in + iy) * p.w_in + ix);
-                    valid = r >= 0;
-                    src = p.rows + static_cast<size_t>(valid ? r : 0) * p.c_in + cb * 32 + ch * 4;
-                } else {
-                    src = p.in + ((static_cast<size_t>(b) * p.h_in + (valid ? iy : 0)) * p.w_in + (valid ? ix : 0)) * p.c_in + cb * 32 + ch * 4;
-                }
-                cp_async16_zfill(stage + static_cast<uint32_t>(px) * 128u + (static_cast<uint32_t>(ch ^ (px & 7)) << 4), src, valid);
+            const uint32_t stage = a0 + sa * a_bytes + dst0;
+            const float *const src_cb = base + cb * 32;
+#pragma unroll 4
+            for (int px = tid >> 3; px < p.stage_rows; px += kLoaders / 8) {
+                const int32_t src = s_src[px];
+                cp_async16_zfill(stage + static_cast<uint32_t>(px - (tid >> 3)) * 128u,
+                                 src_cb + static_cast<size_t>(src < 0 ? 0 : src) * p.c_in, src >= 0);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -227,33 +237,52 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_cons
         if (mbar_wait(acc_full, 0u, s_abort)) {
             tc_fence_after();
             const int r = tid >> 3, c = tid & 7;  // accumulator lane = MMA row = patch pixel (r, c)
+            // transposed convolutions: the accumulator holds TWO horizontally adjacent output phases side by side (columns
+            // [0, cw) and [cw, 2 cw)), so a thread stores pairs of neighbouring pixels: full sectors, not every other float
+            const int cw = p.pair ? N / 2 : N;
+            const int half = p.out_mul >> 1;  // phase = dy * half + g;  output column = ox * up + 2 g + {0, 1}
+            const uint32_t lane_base = tmem + (static_cast<uint32_t>(32 * warp) << 16);
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int oy = y0 + kPatchH * t + r, ox = x0 + c;
                 const bool live = oy < p.h_out && ox < p.w_out;
-                const int py = oy * p.out_mul + phase / p.out_mul, pxo = ox * p.out_mul + phase % p.out_mul;
+                const int py = p.pair ? oy * p.out_mul + phase / half : oy;
+                const int pxo = p.pair ? ox * p.out_mul + 2 * (phase % half) : ox;
 #pragma unroll 1
-                for (int n0 = 0; n0 < N; n0 += 32) {
-                    float v[32];
-                    tmem_ld32(tmem + (static_cast<uint32_t>(32 * warp) << 16) + static_cast<uint32_t>(t * N + n0), v);
+                for (int n0 = 0; n0 < cw; n0 += 32) {
+                    float v[32], u[32];
+                    tmem_ld32(lane_base + static_cast<uint32_t>(t * N + n0), v);
+                    if (p.pair) tmem_ld32(lane_base + static_cast<uint32_t>(t * N + cw + n0), u);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float x = v[j] + s_shift[n0 + j];
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        if (p.round_out) x = round_tf32(x);
+                        const float sh = s_shift[n0 + j];
+                        float x = v[j] + sh, y = u[j] + sh;
+                        if (p.relu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
+                        if (p.round_out) { x = round_tf32(x); y = round_tf32(y); }
                         v[j] = x;
+                        u[j] = y;
                     }
                     if (!live) continue;
                     if (p.out_nchw) {
                         float *dst = p.out + ((static_cast<size_t>(b) * p.out_c_total + p.out_c_off + n0) * p.out_h + py) * p.out_w + pxo;
                         const size_t cs = static_cast<size_t>(p.out_h) * p.out_w;
+                        if (p.pair) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[j * cs] = v[j];
+                            for (int j = 0; j < 32; ++j) *reinterpret_cast<float2 *>(dst + j * cs) = make_float2(v[j], u[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dst[j * cs] = v[j];
+                        }
                     } else {
                         float4 *dst = reinterpret_cast<float4 *>(
                             p.out + ((static_cast<size_t>(b) * p.out_h + py) * p.out_w + pxo) * p.out_c_total + p.out_c_off + n0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (p.pair) {
+                            dst += p.out_c_total >> 2;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) dst[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                        }
                     }
                 }
             }
@@ -318,27 +347,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_cons
 __global__ void k_conv_wimg(const float *__restrict__ weight, const float *__restrict__ scale, int c_in, int c_out, int k, int up,
                             float *__restrict__ img)
 {
-    const int taps = up > 1 ? 1 : k * k, phases = up * up, cbn = c_in >> 5;
-    const int64_t total = static_cast<int64_t>(phases) * cbn * taps * c_out * 8;
+    const int taps = up > 1 ? 1 : k * k, phases = up > 1 ? up * up / 2 : 1, cbn = c_in >> 5;
+    const int rows = up > 1 ? 2 * c_out : c_out;  // transposed: the dx pair (2 g, 2 g + 1) side by side
+    const int64_t total = static_cast<int64_t>(phases) * cbn * taps * rows * 8;
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = static_cast<int>(i & 7);
     int64_t r = i >> 3;
-    const int n = static_cast<int>(r % c_out); r /= c_out;
+    const int row = static_cast<int>(r % rows); r /= rows;
     const int tap = static_cast<int>(r % taps); r /= taps;
     const int cb = static_cast<int>(r % cbn);
     const int phase = static_cast<int>(r / cbn);
+    const int n = row % c_out;
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int ci = cb * 32 + c * 4 + e;
         float w;
-        if (up > 1) w = weight[((static_cast<int64_t>(ci) * c_out + n) * up + phase / up) * up + phase % up];
-        else w = weight[(static_cast<int64_t>(n) * c_in + ci) * taps + tap];
+        if (up > 1) {
+            const int half = up / 2, dy = phase / half, dx = 2 * (phase % half) + row / c_out;
+            w = weight[((static_cast<int64_t>(ci) * c_out + n) * up + dy) * up + dx];
+        } else {
+            w = weight[(static_cast<int64_t>(n) * c_in + ci) * taps + tap];
+        }
         v[e] = round_tf32(scale ? w * scale[n] : w);
     }
     const int64_t block = (static_cast<int64_t>(phase) * cbn + cb) * taps + tap;
-    float *dst = img + block * c_out * 32 + static_cast<int64_t>(n) * 32 + ((c ^ (n & 7)) << 2);
+    float *dst = img + block * rows * 32 + static_cast<int64_t>(row) * 32 + ((c ^ (row & 7)) << 2);
     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
@@ -361,7 +396,7 @@ cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
 cudaError_t launch_conv_wimg(const float *weight, const float *scale, int c_in, int c_out, int k, int up, float *img, cudaStream_t st)
 {
     const int taps = up > 1 ? 1 : k * k;
-    const int64_t total = static_cast<int64_t>(up) * up * (c_in >> 5) * taps * c_out * 8;
+    const int64_t total = static_cast<int64_t>(up) * up * (c_in >> 5) * taps * c_out * 8;  // (= phases * rows, either way)
     k_conv_wimg<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(weight, scale, c_in, c_out, k, up, img);
     note_launch();
     return cudaGetLastError();
@@ -395,7 +430,9 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     p.out_c_total = j.out_c_total;
     p.out_c_off = j.out_c_off;
     p.out_nchw = j.out_nchw;
-    const int phases = j.up * j.up;
+    const int phases = j.up > 1 ? j.up * j.up / 2 : 1;
+    const int n_eff = j.up > 1 ? 2 * j.c_out : j.c_out;
+    p.pair = j.up > 1;
     if (j.c_in % 32 != 0 || j.c_in < 32 || (j.stride != 1 && j.stride != 2) || j.k < 1 || j.k > 3 || (j.up != 1 && j.up != 2 && j.up != 4) ||
         (j.up > 1 && (j.k != 1 || j.stride != 1)) || (j.rows && !j.cell_row) || (!j.rows && !j.in) || p.h_out < 1 || p.w_out < 1)
         return cudaErrorInvalidValue;
@@ -404,7 +441,8 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
 
     // patches per CTA: as many as tensor memory (512 columns) and shared memory allow
     int T;
-    if (j.stride == 1) T = j.c_out == 256 ? 2 : 4;
+    if (n_eff > 256) return cudaErrorInvalidValue;
+    if (j.stride == 1) T = n_eff == 256 ? 2 : 4;
     else T = 1;
     while (T > 1 && kPatchH * (T / 2) >= p.h_out) T /= 2;  // small images: do not pad the patch stack past the image
     if (j.stride == 1) {
@@ -428,7 +466,7 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     p.tiles_x = (p.w_out + kPatchW - 1) / kPatchW;
 
 #define CONV_CASE(n, t, sa, sb) \
-    if (j.c_out == n && T == t) return launch_one<n, t, sa, sb>(p, phases, st)
+    if (n_eff == n && T == t) return launch_one<n, t, sa, sb>(p, phases, st)
     if (j.stride == 1) {
         CONV_CASE(64, 4, 2, 4);
         CONV_CASE(64, 2, 2, 4);
