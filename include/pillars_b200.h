@@ -99,6 +99,9 @@ typedef struct pillars_outputs {
     float *bev;               /* [n_frames, F*nz, ny, nx]  batch_dict['spatial_features'] (encode_bev only) */
     void *bev_half;           /* same canvas as IEEE float16 (round to nearest even), the dtype the product stores:
                                  src/get-data/precompute_bev_features.py:394; may be given instead of or beside bev */
+    int32_t want_index_map;   /* non-zero: leave the BEV index map [n_frames, ny, nx] (row of the pillar in each cell, -1 =
+                                 empty) in the workspace at pillars_workspace_cell_row_offset() even when no canvas is asked
+                                 for -- the input of pillars_conv_forward / pillars_bev_tokens_map (nz == 1 grids) */
 } pillars_outputs_t;
 
 int pillars_abi_version(void);

@@ -68,7 +68,8 @@ class PillarsPfnStack(Structure):
 class PillarsOutputs(Structure):
     _fields_ = [("pillar_capacity", c_int64), ("pillar_features", c_void_p), ("voxel_coords", c_void_p),
                 ("voxel_num_points", c_void_p), ("voxels", c_void_p), ("point_pillar", c_void_p),
-                ("point_slot", c_void_p), ("pillar_count", c_void_p), ("bev", c_void_p), ("bev_half", c_void_p)]
+                ("point_slot", c_void_p), ("pillar_count", c_void_p), ("bev", c_void_p), ("bev_half", c_void_p),
+                ("want_index_map", c_int32)]
 
 
 class PillarsTokenizer(Structure):

@@ -211,7 +211,7 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
     if (pfn && pfn->c_point != c_point) return fail(PILLARS_E_BADARG, "pfn->c_point != c_point");
     if (pfn && !out->pillar_features) return fail(PILLARS_E_BADARG, "pillar_features output is required");
     if (want_bev && ((!out->bev && !out->bev_half) || !pfn)) return fail(PILLARS_E_BADARG, "bev output / pfn missing");
-    if (want_bev && grid->grid[2] != 1) return fail(PILLARS_E_UNSUPPORTED, "BEV scatter needs nz == 1");
+    if ((want_bev || out->want_index_map) && grid->grid[2] != 1) return fail(PILLARS_E_UNSUPPORTED, "BEV scatter / index map needs nz == 1");
     if (out->pillar_capacity < 0) return fail(PILLARS_E_BADARG, "pillar_capacity < 0");
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
     if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
@@ -248,7 +248,7 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         }
         px.voxel_coords = out->voxel_coords;
         px.voxel_num_points = out->voxel_num_points;
-        px.write_cell_row = want_bev;
+        px.write_cell_row = want_bev || out->want_index_map;
     }
     px.capacity = out->pillar_capacity;
     if ((e = launch_group_points(points, n, row_stride, col0, c_point, frame_offsets, n_frames, gd, ws, out->pillar_count,
@@ -273,7 +273,7 @@ static int group_and_emit(const float *points, int64_t n, int32_t row_stride, in
         job.f_out = pfn->f_out;
     }
     job.out = *out;
-    job.write_cell_row = want_bev && !fast;
+    job.write_cell_row = (want_bev || out->want_index_map) && !fast;
     if (!fast || membership) {
         if ((e = launch_pillar_features(job, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pillar_features");
     }

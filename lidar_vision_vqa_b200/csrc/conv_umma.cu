@@ -137,8 +137,8 @@ struct ConvParams {
     uint32_t *error;          // device word: nonzero when a bounded wait expired
 };
 
-template <int N, int T, int SA, int SB>
-__global__ void __launch_bounds__(kConvThreads, 1) k_conv_umma(const __grid_constant__ ConvParams p)
+template <int N, int T, int SA, int SB, int MB = 1>
+__global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_constant__ ConvParams p)
 {
     extern __shared__ __align__(1024) uint8_t s_raw[];
     __shared__ uint64_t s_bar[2 * SA + 2 * SB + 1];
@@ -377,16 +377,16 @@ __global__ void k_conv_wimg(const float *__restrict__ weight, const float *__res
     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-template <int N, int T, int SA, int SB>
+template <int N, int T, int SA, int SB, int MB = 1>
 cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
 {
     const size_t a_bytes = (static_cast<size_t>(p.stage_rows) * 128 + 1023) & ~static_cast<size_t>(1023);
     const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 1024;
     if (smem > 226 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const dim3 grid(static_cast<unsigned>(p.nb * p.tiles_x * p.tiles_y), 1, static_cast<unsigned>(phases));
-    k_conv_umma<N, T, SA, SB><<<grid, kConvThreads, smem, st>>>(p);
+    k_conv_umma<N, T, SA, SB, MB><<<grid, kConvThreads, smem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
@@ -442,6 +442,8 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     // patches per CTA: as many as tensor memory (512 columns) and shared memory allow
     int T;
     if (n_eff > 256) return cudaErrorInvalidValue;
+    // (measured on 16 x 512^2, profiles/r02_backbone.md: fewer patches with a deeper weight ring are SLOWER -- the weights'
+    // L2 traffic per output pixel is what counts, so T is as large as tensor memory allows)
     if (j.stride == 1) T = n_eff == 256 ? 2 : 4;
     else T = 1;
     while (T > 1 && kPatchH * (T / 2) >= p.h_out) T /= 2;  // small images: do not pad the patch stack past the image
@@ -477,7 +479,9 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
         CONV_CASE(256, 2, 2, 3);
         CONV_CASE(256, 1, 2, 3);
     } else {
-        CONV_CASE(64, 1, 2, 4);
+        // 64 output channels: one halo stage and two CTAs per SM (one loads while the other multiplies): 0.87 -> 0.52 ms on
+        // the gathered first layer; the same trade measured slightly worse at 128 channels
+        if (n_eff == 64) return launch_one<64, 1, 1, 4, 2>(p, phases, st);
         CONV_CASE(128, 1, 2, 3);
         CONV_CASE(256, 1, 1, 3);
     }

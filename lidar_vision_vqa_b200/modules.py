@@ -213,7 +213,12 @@ class PillarVFEFromPoints(_PillarVFEBase):
     ``FUSE_SCATTER`` also ``spatial_features`` (the scatter then becomes a no-op).
 
     Extra model_cfg keys (all optional): MAX_POINTS_PER_VOXEL (32), MAX_NUMBER_OF_VOXELS (40000, int or
-    {'train','test'}), FUSE_SCATTER (False), SCATTER_VARIANT ('auto'), SYNC_COUNTS (True), OUTPUT_RING (0).
+    {'train','test'}), FUSE_SCATTER (False), SCATTER_VARIANT ('auto'), SYNC_COUNTS (True), OUTPUT_RING (0),
+    EMIT_INDEX_MAP (False).
+
+    ``EMIT_INDEX_MAP: True`` adds ``batch_dict['bev_index_map'] [B, ny, nx] int32`` (row of the pillar in each cell, -1 =
+    empty; a view of the call's workspace): with it ``BaseBEVBackbone`` (backbone.py) and the BEV tokeniser read the pillar
+    rows directly and the dense canvas need not exist at all.
 
     ``SYNC_COUNTS: False`` removes the call's only host synchronisation: the per-pillar outputs then keep their CAPACITY
     (rows beyond the pillar count are undefined), and the counts stay on the
@@ -238,6 +243,7 @@ class PillarVFEFromPoints(_PillarVFEBase):
         self.scatter_variant = str(_cfg_get(model_cfg, "SCATTER_VARIANT", "auto"))
         self.sync_counts = bool(_cfg_get(model_cfg, "SYNC_COUNTS", True))
         self.output_ring = int(_cfg_get(model_cfg, "OUTPUT_RING", 0))
+        self.emit_index_map = bool(_cfg_get(model_cfg, "EMIT_INDEX_MAP", False))
         self._ring, self._ring_next = [], 0
         self.grid = ops.GridSpec(self.point_cloud_range, self.voxel_size, self.grid_size, self.max_points,
                                  self.max_voxels)
@@ -260,9 +266,17 @@ class PillarVFEFromPoints(_PillarVFEBase):
             buffers = None
             if self.output_ring > 0:
                 buffers = self._ring_buffers(points.shape[0], batch_size, points.device)
+            if self.emit_index_map and buffers is None:  # the map is a view of the workspace: keep that alive with the result
+                buffers = ops.EncodeBuffers(points.shape[0], batch_size, self.grid, int(self.num_filters[-1]), points.device,
+                                            with_bev=self.fuse_scatter)
             res = ops.encode_bev(points, offs, self.grid, self._params(points.device), col0=col0, buffers=buffers,
-                                 with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
+                                 with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant,
+                                 want_index_map=self.emit_index_map)
+            if self.emit_index_map:
+                batch_dict["bev_index_map"] = res["cell_row"]
         else:
+            if self.emit_index_map:
+                raise NotImplementedError("EMIT_INDEX_MAP is implemented for the single-layer PFN path")
             res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=col0,
                                    with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
         if self.fuse_scatter:

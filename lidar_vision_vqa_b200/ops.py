@@ -427,7 +427,8 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
                ) -> Dict[str, torch.Tensor]:
     """The fused path: raw points -> pillar_features / voxel_coords / voxel_num_points / pillar_count / bev.
     ``want_index_map`` adds ``cell_row`` [n_frames, ny, nx] int32 (row of the pillar in each cell, -1 = empty): a view of
-    the workspace, valid until ``buffers`` is reused -- the input of the BEV tokeniser (tokens.py).
+    the workspace, valid until ``buffers`` is reused -- the input of the BEV tokeniser (tokens.py) and of the backbone's
+    first layer (backbone.py); it does not need a canvas (``with_bev=False``).
     Everything is enqueued on the current stream; nothing synchronises."""
     _check_points(points, frame_offsets)
     lib = _native.load()
@@ -468,8 +469,7 @@ def encode_bev(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec
         res["voxels"] = torch.empty((buffers.capacity, grid.max_points, pfn.c_point), dtype=torch.float32, device=dev)
         out.voxels = res["voxels"].data_ptr()
     if want_index_map:
-        if not with_bev:
-            raise ValueError("the index map is only written together with a canvas")
+        out.want_index_map = 1
         # the workspace layout depends on the point count of THIS call
         off = lib.pillars_workspace_cell_row_offset(n, nb, ctypes.byref(g))
         nx, ny, _ = grid.grid_size

@@ -219,3 +219,36 @@ def test_backbone_refuses_training_mode_and_cpu_input():
         m({"spatial_features": torch.zeros(1, 64, 32, 32, device=_dev())})
     with pytest.raises(_native.NativeLibraryError):
         m.eval()({"spatial_features": torch.zeros(1, 64, 32, 32)})
+
+
+def test_points_to_backbone_without_a_canvas_equals_the_canvas_route():
+    """points -> PillarVFEFromPoints(EMIT_INDEX_MAP) -> BaseBEVBackbone reads pillar rows through the index map; the same
+    sweeps through FUSE_SCATTER's dense canvas must give the identical tensor (same operands, same order of accumulation)."""
+    from lidar_vision_vqa_b200 import synth
+    from lidar_vision_vqa_b200.backbone import BaseBEVBackbone
+    from lidar_vision_vqa_b200.modules import PillarVFEFromPoints
+
+    dev = _dev()
+    rng, vs = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], [0.2, 0.2, 8.0]
+    pts, offs = synth.make_batch(2, synth.NUSCENES_32, 5, seed0=3)
+    b = np.repeat(np.arange(2), np.diff(offs)).astype(np.float32)[:, None]
+    points = torch.from_numpy(np.concatenate([b, pts], axis=1)).to(dev)
+    base = dict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64], MAX_POINTS_PER_VOXEL=32,
+                MAX_NUMBER_OF_VOXELS=30000)
+    torch.manual_seed(0)
+    vfe_map = PillarVFEFromPoints(dict(base, EMIT_INDEX_MAP=True), 5, vs, rng, [512, 512, 1]).eval().to(dev)
+    vfe_canvas = PillarVFEFromPoints(dict(base, FUSE_SCATTER=True), 5, vs, rng, [512, 512, 1]).eval().to(dev)
+    vfe_canvas.load_state_dict(vfe_map.state_dict())
+    bb = BaseBEVBackbone(BACKBONE_CASES["nuscenes_multihead"], 64).eval().to(dev)
+    _randomise_bn(bb, 9)
+    with torch.inference_mode():
+        d1 = vfe_map({"points": points, "batch_size": 2})
+        assert "spatial_features" not in d1 and d1["bev_index_map"].shape == (2, 512, 512)
+        m = d1["pillar_features"].shape[0]
+        assert int((d1["bev_index_map"] >= 0).sum()) == m
+        out1 = bb(d1)["spatial_features_2d"].clone()
+        d2 = vfe_canvas({"points": points, "batch_size": 2})
+        out2 = bb({"spatial_features": d2["spatial_features"]})["spatial_features_2d"]
+    torch.cuda.synchronize()
+    assert out1.shape == (2, 384, 128, 128)
+    assert torch.equal(out1, out2)
