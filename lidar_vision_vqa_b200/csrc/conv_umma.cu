@@ -135,7 +135,17 @@ struct ConvParams {
     int relu, round_out;
     int pair;                 // transposed convolution: two dx phases per accumulator (N = 2 * c_out)
     uint32_t *error;          // device word: nonzero when a bounded wait expired
+    unsigned long long *timeline;  // measurement hook (pillars_set_debug_times): one CTA's phase stamps, %globaltimer ns
 };
+
+__device__ __forceinline__ void tl_stamp(const ConvParams &p, int slot)
+{
+    if (p.timeline && blockIdx.x == 200 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[slot] = t;
+    }
+}
 
 template <int N, int T, int SA, int SB, int MB = 1>
 __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_constant__ ConvParams p)
@@ -149,6 +159,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     volatile uint32_t *const s_abort = &s_abort_word;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) tl_stamp(p, 0);  // CTA start
     uint8_t *const s_al = s_raw + ((1024u - (smem_u32(s_raw) & 1023u)) & 1023u);
     const uint32_t a_bytes = (static_cast<uint32_t>(p.stage_rows) * 128u + 1023u) & ~1023u;
     constexpr uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
@@ -188,6 +199,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    if (tid == 0) tl_stamp(p, 1);  // set-up done
 
     if (warp < 4) {
         // ================================ halo loaders ===========================================================================
@@ -214,6 +226,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             s_src[px] = src;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
+        if (tid == 0) tl_stamp(p, 2);  // source table done
         const int ch = tid & 7;           // 16-byte chunk of the pixel's 128-byte row; this thread takes rows (tid >> 3) + 16 j
         const float *const base = (p.rows ? p.rows : p.in) + ch * 4;
         const uint32_t dst0 = static_cast<uint32_t>(tid >> 3) * 128u + (static_cast<uint32_t>(ch ^ ((tid >> 3) & 7)) << 4);
@@ -232,10 +245,12 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             fence_async_smem();  // this thread's writes are in shared memory: make them visible to the tensor core's proxy
             mbar_arrive(a_full + 8u * sa);
+            if (tid == 0 && cb < 8) tl_stamp(p, 8 + cb);  // halo stage cb landed
         }
         // ================================ epilogue ===============================================================================
         if (mbar_wait(acc_full, 0u, s_abort)) {
             tc_fence_after();
+            if (tid == 0) tl_stamp(p, 3);  // accumulators complete
             const int r = tid >> 3, c = tid & 7;  // accumulator lane = MMA row = patch pixel (r, c)
             // transposed convolutions: the accumulator holds TWO horizontally adjacent output phases side by side (columns
             // [0, cw) and [cw, 2 cw)), so a thread stores pairs of neighbouring pixels: full sectors, not every other float
@@ -262,8 +277,8 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                         v[j] = x;
                         u[j] = y;
                     }
-                    if (!live) continue;
                     if (p.out_nchw) {
+                        if (!live) continue;
                         float *dst = p.out + ((static_cast<size_t>(b) * p.out_c_total + p.out_c_off + n0) * p.out_h + py) * p.out_w + pxo;
                         const size_t cs = static_cast<size_t>(p.out_h) * p.out_w;
                         if (p.pair) {
@@ -273,15 +288,35 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
 #pragma unroll
                             for (int j = 0; j < 32; ++j) dst[j * cs] = v[j];
                         }
-                    } else {
+                    } else if (p.pair) {
+                        if (!live) continue;
                         float4 *dst = reinterpret_cast<float4 *>(
                             p.out + ((static_cast<size_t>(b) * p.out_h + py) * p.out_w + pxo) * p.out_c_total + p.out_c_off + n0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        if (p.pair) {
-                            dst += p.out_c_total >> 2;
+                        dst += p.out_c_total >> 2;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) dst[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                    } else {
+                        // NHWC: a thread owns one pixel, so its 128 bytes of this chunk are contiguous but the warp's 32 pixels
+                        // are not -- written directly, every store instruction scatters 32 sixteen-byte pieces (measured: the
+                        // epilogue took 14 us of a 47 us CTA).  The 32 x 32 tile goes through shared memory (the halo stages
+                        // are idle by now) so that eight lanes write one pixel's full 128-byte line.
+                        uint8_t *const stg = s_al + warp * 4096;
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = 4 * i + (lane >> 3);  // pixel of the warp's 32 (= 4 patch rows x 8 columns)
+                            const int oy2 = y0 + kPatchH * t + 4 * warp + (rr >> 3), ox2 = x0 + (rr & 7);
+                            const float4 val = *reinterpret_cast<const float4 *>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+                            if (oy2 < p.h_out && ox2 < p.w_out)
+                                *reinterpret_cast<float4 *>(p.out + ((static_cast<size_t>(b) * p.out_h + oy2) * p.out_w + ox2) * p.out_c_total +
+                                                            p.out_c_off + n0 + (lane & 7) * 4) = val;
                         }
                     }
                 }
@@ -299,6 +334,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             for (int cb = 0; cb < cbn && ok; ++cb) {
                 const int sa = cb % SA;
                 ok = mbar_wait(a_full + 8u * sa, (cb / SA) & 1u, s_abort);
+                if (cb < 8) tl_stamp(p, 16 + cb);  // MMA thread: halo stage cb available
                 const uint32_t stage = a0 + sa * a_bytes;
                 for (int tap = 0; tap < p.taps && ok; ++tap, ++i) {
                     const int sb = i % SB;
@@ -320,6 +356,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                 umma_commit(a_empty + 8u * sa);
             }
             umma_commit(acc_full);
+            tl_stamp(p, 4);  // last MMA issued
         }
     } else {
         // ================================ weight copies ==========================================================================
@@ -334,6 +371,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             }
         }
     }
+    if (tid == 0) tl_stamp(p, 5);  // epilogue done (this thread)
     if (*s_abort && tid == 0 && p.error) atomicExch(p.error, 0xC0DE0000u | static_cast<uint32_t>(blockIdx.x & 0xFFFF));
     tc_fence_before();
     __syncthreads();
@@ -422,6 +460,7 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     p.relu = j.relu;
     p.round_out = j.round_out;
     p.error = j.error;
+    p.timeline = debug_times_ptr();
     p.h_out = (j.h_in + 2 * j.pad - j.k) / j.stride + 1;
     p.w_out = (j.w_in + 2 * j.pad - j.k) / j.stride + 1;
     p.out_mul = j.up;
@@ -439,12 +478,12 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     if (j.stride == 2 && !((j.k == 3 && j.pad == 1) || (j.k == 2 && j.pad == 0))) return cudaErrorInvalidValue;
     if (j.stride == 1 && j.pad != (j.k - 1) / 2) return cudaErrorInvalidValue;
 
-    // patches per CTA: as many as tensor memory (512 columns) and shared memory allow
+    // patches per CTA
+    // 64 / 128 columns: two patches, one halo stage, TWO CTAs per SM (one CTA's prologue and epilogue hide behind the other's
+    // MMAs: 0.38 -> 0.31 ms and 0.200 -> 0.189 ms per layer at 16 x 512^2); 256 columns: two patches fill tensor memory, one CTA
     int T;
     if (n_eff > 256) return cudaErrorInvalidValue;
-    // (measured on 16 x 512^2, profiles/r02_backbone.md: fewer patches with a deeper weight ring are SLOWER -- the weights'
-    // L2 traffic per output pixel is what counts, so T is as large as tensor memory allows)
-    if (j.stride == 1) T = n_eff == 256 ? 2 : 4;
+    if (j.stride == 1) T = 2;
     else T = 1;
     while (T > 1 && kPatchH * (T / 2) >= p.h_out) T /= 2;  // small images: do not pad the patch stack past the image
     if (j.stride == 1) {
@@ -469,6 +508,10 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
 
 #define CONV_CASE(n, t, sa, sb) \
     if (n_eff == n && T == t) return launch_one<n, t, sa, sb>(p, phases, st)
+    if (j.stride == 1) {
+        if (n_eff == 64 && T == 2) return launch_one<64, 2, 1, 4, 2>(p, phases, st);
+        if (n_eff == 128 && T == 2) return launch_one<128, 2, 1, 2, 2>(p, phases, st);
+    }
     if (j.stride == 1) {
         CONV_CASE(64, 4, 2, 4);
         CONV_CASE(64, 2, 2, 4);
