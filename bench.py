@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-extra-workloads", action="store_true", help="skip the cfg3 / cfg4 sub-lines of the default run")
     ap.add_argument("--no-extractor", action="store_true", help="skip the BEV extractor (f-1) end-to-end measurement")
+    ap.add_argument("--no-backbone", action="store_true", help="skip the BaseBEVBackbone (f-3) measurement")
     ap.add_argument("--gather-dtype", default="float32", choices=["float32", "float16"],
                     help="dtype of the feature rows on the wire in the multi-GPU gather")
     ap.add_argument("--cfg5-mode", default="fusion", choices=["fusion", "sharded"],
@@ -586,6 +587,11 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_extractor and not args.no_e2e and nz == 1:
         extractor = extractor_numbers(args, wl, K)
 
+    # ---- the step after the scatter (f-3): BaseBEVBackbone on the tcgen05 convolution kernel ------------------------------------
+    backbone = None
+    if rank == 0 and world == 1 and not args.no_backbone and nz == 1 and nx % 8 == 0 and ny % 8 == 0:
+        backbone = backbone_numbers(args, wl, K)
+
     cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_arm(args.workload, args.cpu_frames, steps=4, warmup=1)
@@ -629,7 +635,7 @@ def run_b200(args, rank, world, local_rank):
                        "l2": f"no explicit flush: each step writes {4 * F_OUT * nx * ny * nb / 2**20:.0f} MiB (>> 126 MB L2) "
                              f"and cycles {wl.rot} distinct input batches"},
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "reference_eager_on_b200": eager, "e2e": e2e,
-            "gather_to_fusion_rank": gather, "extractor": extractor, "other_workloads": others,
+            "gather_to_fusion_rank": gather, "extractor": extractor, "backbone": backbone, "other_workloads": others,
             "gpu_launches": launches * K * R * 2, "gpu_launches_per_step": launches, "clocks": clocks,
         }
         if gather:
@@ -1028,6 +1034,128 @@ def extractor_numbers(args, wl, K):
                    "memory, 3 batches in flight); dense = the [B,64,ny,nx] float16 canvas the reference stores; compact = "
                    "float16 pillar rows + int16 (y,x) of the occupied cells only, BevExtractor.densify_compact rebuilds the "
                    "identical map on the consumer")
+    return out
+
+
+BACKBONE_CFG = dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256], UPSAMPLE_STRIDES=[0.5, 1, 2],
+                    NUM_UPSAMPLE_FILTERS=[128, 128, 128])  # cbgs_pp_multihead.yaml:39-46, the product's pillar model
+
+
+def backbone_flops(cfg, c_in, h, w, nb):
+    """Multiply-adds x 2 of every convolution of BaseBEVBackbone (base_bev_backbone.py:29-69) on an h x w input."""
+    total, c = 0.0, c_in
+    outs = []
+    for n, s, f in zip(cfg["LAYER_NUMS"], cfg["LAYER_STRIDES"], cfg["NUM_FILTERS"]):
+        h, w = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+        total += 2.0 * nb * h * w * f * c * 9 + n * 2.0 * nb * h * w * f * f * 9
+        c = f
+        outs.append((h, w, f))
+    for (hh, ww, f), us, uf in zip(outs, cfg["UPSAMPLE_STRIDES"], cfg["NUM_UPSAMPLE_FILTERS"]):
+        if us >= 1:
+            total += 2.0 * nb * hh * ww * f * uf * us * us          # ConvTranspose2d(kernel = stride = us)
+        else:
+            k = int(round(1 / us))
+            total += 2.0 * nb * (hh // k) * (ww // k) * f * uf * k * k  # Conv2d(kernel = stride = k)
+    return total
+
+
+def backbone_numbers(args, wl, K):
+    """f-3: points -> pillar rows + index map -> BaseBEVBackbone -> spatial_features_2d, the canvas never materialised; the
+    same backbone fed the dense canvas; and the reference's own module (oracle/_ref copy) eager on this GPU beside them."""
+    from lidar_vision_vqa_b200 import ops
+    from lidar_vision_vqa_b200.backbone import BaseBEVBackbone
+
+    dev, nb = wl.dev, wl.nb
+    torch.manual_seed(0)
+    bb = BaseBEVBackbone(BACKBONE_CFG, F_OUT).eval().to(dev)
+    g = torch.Generator().manual_seed(1)
+    for m in bb.modules():  # non-trivial BatchNorm statistics, as a trained checkpoint has
+        if isinstance(m, torch.nn.BatchNorm2d):
+            with torch.no_grad():
+                m.weight.copy_(0.5 + torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
+                m.running_mean.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
+                m.running_var.copy_(0.5 + 1.5 * torch.rand(m.bias.shape, generator=g))
+    buf_map = ops.EncodeBuffers(wl.n_max, nb, wl.grid, F_OUT, dev, with_bev=False)
+    buf_bev = ops.EncodeBuffers(wl.n_max, nb, wl.grid, F_OUT, dev)
+    n_it = max(5, min(K, 10))
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(n_it):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    def chain_rows(i):
+        p, o = wl.dev_batches[i % wl.rot]
+        r = ops.encode_bev(p, o, wl.grid, wl.pfn, buffers=buf_map, with_bev=False, want_index_map=True)
+        return bb({"pillar_features": r["pillar_features"], "bev_index_map": r["cell_row"]})
+
+    def chain_canvas(i):
+        p, o = wl.dev_batches[i % wl.rot]
+        r = ops.encode_bev(p, o, wl.grid, wl.pfn, buffers=buf_bev)
+        return bb({"spatial_features": r["bev"]})
+
+    with torch.inference_mode():
+        p0, o0 = wl.dev_batches[0]
+        r0 = ops.encode_bev(p0, o0, wl.grid, wl.pfn, buffers=buf_map, with_bev=False, want_index_map=True)
+        rows0, map0 = r0["pillar_features"], r0["cell_row"]
+        out = {"config": "BaseBEVBackbone cbgs_pp_multihead.yaml:39-46 (3+5+5 layers, 64/128/256 filters, 3 x 128 up-sampled)",
+               "frames": nb, "input": [F_OUT, wl.ny, wl.nx],
+               "backbone_only_ms": timed(lambda i: bb({"pillar_features": rows0, "bev_index_map": map0})),
+               "points_to_features2d_ms": timed(chain_rows),
+               "points_to_features2d_via_canvas_ms": timed(chain_canvas)}
+        err = bb({"pillar_features": rows0, "bev_index_map": map0})["_conv_error_word"]
+        out["kernel_error_word"] = int(err.item())
+        # (the timed chains recycled both buffer sets: encode batch 0 again before comparing with the reference)
+        r0 = ops.encode_bev(p0, o0, wl.grid, wl.pfn, buffers=buf_map, with_bev=False, want_index_map=True)
+        ours = bb({"pillar_features": r0["pillar_features"], "bev_index_map": r0["cell_row"]})["spatial_features_2d"]
+        canvas = ops.encode_bev(p0, o0, wl.grid, wl.pfn, buffers=buf_bev)["bev"]
+        fl = backbone_flops(BACKBONE_CFG, F_OUT, wl.ny, wl.nx, nb)
+        out["algorithmic_flops"] = fl
+        out["tflops"] = fl / (out["backbone_only_ms"] * 1e-3) / 1e12
+        bf16, bf16_src = 0.0, ""
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(mp):
+            with open(mp) as f:
+                d = json.load(f)
+            # a ~4 ms chain of tensor-core kernels runs at the sustained (power-limited) clock, not the burst one
+            bf16 = float(d.get("bf16_tflops_sustained") or d.get("bf16_tflops") or 0.0)
+            bf16_src = "bf16_tflops_sustained" if d.get("bf16_tflops_sustained") else "bf16_tflops"
+        tf32_peak = bf16 / 2 if bf16 > 0 else 1130.0
+        out["roofline"] = {"bound": "tensor", "achieved": out["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac": out["tflops"] / tf32_peak,
+                           "peak_source": (f"half of MEASURED_PEAKS.json's dense {bf16_src} (tf32 runs at half the bf16 rate)"
+                                           if bf16 > 0 else "nominal dense tf32 peak (B200_PROFILING.md)")}
+        out["sweeps_per_s_points_to_features2d"] = nb / (out["points_to_features2d_ms"] * 1e-3)
+        try:
+            from oracle import ref_loader as R  # the reference leg: its own module, unmodified, eager on this GPU
+
+            if R.reference_available():
+                ref = R.load_bev_backbone()(R.AttrDict(BACKBONE_CFG), F_OUT).eval().to(dev)
+                ref.load_state_dict(bb.state_dict())
+                torch.backends.cudnn.benchmark = True
+                want = ref({"spatial_features": canvas})["spatial_features_2d"]
+                scale = float(want.abs().max())
+                out["max_abs_err_vs_reference_eager_over_scale"] = float((ours - want).abs().max()) / scale
+                out["reference_eager_tf32_ms"] = timed(lambda i: ref({"spatial_features": canvas}))
+                torch.backends.cudnn.allow_tf32 = False
+                out["reference_eager_fp32_ms"] = timed(lambda i: ref({"spatial_features": canvas}))
+                torch.backends.cudnn.allow_tf32 = True
+                out["speedup_vs_reference_eager_tf32"] = out["reference_eager_tf32_ms"] / out["backbone_only_ms"]
+                del ref, want
+        except Exception as e:  # noqa: BLE001  (the reference leg is optional: report why it is missing)
+            out["reference_error"] = repr(e)
+    del bb, buf_map, buf_bev
+    torch.cuda.empty_cache()
     return out
 
 
