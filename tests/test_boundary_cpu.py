@@ -191,3 +191,43 @@ def test_tokenizer_without_gpu_fails_loudly():
         tk(torch.zeros(1, 8, 4, 4))
     with pytest.raises(L.NativeLibraryError):
         tk.forward_pillars(torch.zeros(2, 8), torch.zeros(2, 4), 1, (4, 4))
+
+
+BACKBONE_CFGS = [
+    dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256], UPSAMPLE_STRIDES=[0.5, 1, 2],
+         NUM_UPSAMPLE_FILTERS=[128, 128, 128]),                       # nuscenes_models/cbgs_pp_multihead.yaml:39-46
+    dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256], UPSAMPLE_STRIDES=[1, 2, 4],
+         NUM_UPSAMPLE_FILTERS=[128, 128, 128]),                       # kitti_models/pointpillar.yaml
+    dict(LAYER_NUMS=[2], LAYER_STRIDES=[1], NUM_FILTERS=[64], UPSAMPLE_STRIDES=[1], NUM_UPSAMPLE_FILTERS=[64],
+         USE_CONV_FOR_NO_STRIDE=True),
+]
+
+
+@pytest.mark.parametrize("cfg", BACKBONE_CFGS, ids=["multihead", "kitti", "conv_for_no_stride"])
+def test_backbone_mirrors_the_reference_module_tree(cfg):
+    """Same constructor, same sub-module tree => the reference's checkpoints load by key and shape (f-3 boundary)."""
+    from oracle import ref_loader as R
+    from lidar_vision_vqa_b200 import BaseBEVBackbone
+
+    if not R.reference_available():
+        pytest.skip("reference tree / oracle/_ref copy not present")
+    ref = R.load_bev_backbone()(R.AttrDict(cfg), 64)
+    mine = BaseBEVBackbone(cfg, 64)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    assert mine.num_bev_features == ref.num_bev_features
+    mine.load_state_dict(a, strict=True)
+    for m in mine.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            assert m.eps == 1e-3 and m.momentum == 0.01  # base_bev_backbone.py:36
+
+
+def test_backbone_has_no_cpu_or_training_path():
+    import lidar_vision_vqa_b200 as L
+
+    m = L.BaseBEVBackbone(BACKBONE_CFGS[0], 64)
+    with pytest.raises(NotImplementedError):
+        m({"spatial_features": torch.zeros(1, 64, 32, 32)})
+    with pytest.raises(L.NativeLibraryError):
+        m.eval()({"spatial_features": torch.zeros(1, 64, 32, 32)})

@@ -252,3 +252,31 @@ def test_points_to_backbone_without_a_canvas_equals_the_canvas_route():
     torch.cuda.synchronize()
     assert out1.shape == (2, 384, 128, 128)
     assert torch.equal(out1, out2)
+
+
+@pytest.mark.parametrize("name", ["bb_2level_half_stride", "bb_3level_up124"])
+def test_backbone_against_committed_reference_goldens(name):
+    """tests/golden/bb_*.npz: config, state dict, canvas and the output of the reference's own BaseBEVBackbone.forward
+    (made by tests/golden/make_golden_backbone.py in the build container).  Nothing here reads /root/reference."""
+    import json
+    import os
+
+    from lidar_vision_vqa_b200.backbone import BaseBEVBackbone
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg = json.loads(bytes(z["cfg"]).decode())
+    m = BaseBEVBackbone(cfg, 64).eval()
+    sd = {k[3:]: torch.from_numpy(z[k].astype(np.float32) if z[k].dtype == np.float16 else z[k]) for k in z.files if k.startswith("sd.")}
+    m.load_state_dict(sd, strict=True)
+    dev = _dev()
+    m = m.to(dev)
+    canvas = torch.from_numpy(z["canvas"].astype(np.float32)).to(dev)
+    with torch.inference_mode():
+        out = m({"spatial_features": canvas})
+    torch.cuda.synchronize()
+    assert int(out["_conv_error_word"].item()) == 0
+    got, want = out["spatial_features_2d"].cpu().numpy(), z["out"]
+    assert got.shape == want.shape
+    scale = float(np.abs(want).max())
+    assert float(np.abs(got - want).max()) <= 1e-2 * scale
+    assert float((np.abs(got - want) <= 2e-3 * scale).mean()) > 0.99
