@@ -27,7 +27,7 @@ namespace pillars {
 
 namespace {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;
 constexpr int kLoaders = 128;
 constexpr int kPatchW = 8, kPatchH = 16;
 constexpr int kMaxStageRows = 672;  // (16 * 4 + 2) * 10 = 660 (3x3 stride 1, four patches); 4 * 17 * 9 = 612 (stride 2)
@@ -147,11 +147,14 @@ __device__ __forceinline__ void tl_stamp(const ConvParams &p, int slot)
     }
 }
 
-template <int N, int T, int SA, int SB, int MB = 1>
+// Persistent: a CTA walks over tile sets (tile = blockIdx.x, += gridDim.x).  With NB = 2 the accumulator is double buffered in
+// tensor memory, so the epilogue of tile set i (warps 6-9) runs under the MMAs of tile set i + 1, and the loaders (warps 0-3)
+// run ahead into the next tile set's halo as soon as a stage is released -- no prologue or epilogue is exposed after the first.
+template <int N, int T, int SA, int SB, int NB, int MB = 1>
 __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_constant__ ConvParams p)
 {
     extern __shared__ __align__(1024) uint8_t s_raw[];
-    __shared__ uint64_t s_bar[2 * SA + 2 * SB + 1];
+    __shared__ uint64_t s_bar[2 * SA + 2 * SB + 2 * NB];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_abort_word;
     __shared__ float s_shift[N];
@@ -164,18 +167,25 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     const uint32_t a_bytes = (static_cast<uint32_t>(p.stage_rows) * 128u + 1023u) & ~1023u;
     constexpr uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
     const uint32_t a0 = smem_u32(s_al), b0 = a0 + SA * a_bytes;
+    uint8_t *const s_stage = s_al + SA * a_bytes + SB * b_bytes;  // 4 x 4 KB: the epilogue warps' transposition buffers
     const uint32_t bar0 = smem_u32(s_bar);
     const uint32_t a_full = bar0, a_empty = bar0 + 8u * SA, b_full = bar0 + 16u * SA, b_empty = b_full + 8u * SB,
-                   acc_full = b_empty + 8u * SB;
-    constexpr uint32_t tmem_cols = (T * N <= 32) ? 32u : (T * N <= 64) ? 64u : (T * N <= 128) ? 128u : (T * N <= 256) ? 256u : 512u;
+                   acc_full = b_empty + 8u * SB, acc_empty = acc_full + 8u * NB;
+    constexpr uint32_t acc_cols = T * N;
+    constexpr uint32_t tmem_cols = (NB * acc_cols <= 32) ? 32u : (NB * acc_cols <= 64) ? 64u : (NB * acc_cols <= 128) ? 128u
+                                   : (NB * acc_cols <= 256) ? 256u : 512u;
+    static_assert(NB * acc_cols <= 512, "tensor memory has 512 columns");
 
-    // ---- tile of this CTA
     const int tiles_per_frame = p.tiles_x * p.tiles_y;
-    const int b = blockIdx.x / tiles_per_frame, tr = blockIdx.x - b * tiles_per_frame;
-    const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
-    const int y0 = ty * (kPatchH * T), x0 = tx * kPatchW;
+    const int total_tiles = p.nb * tiles_per_frame;
     const int phase = blockIdx.z;
     const int cbn = p.c_in >> 5;
+    const auto tile_origin = [&](int tile, int &b, int &y0, int &x0) {
+        b = tile / tiles_per_frame;
+        const int tr = tile - b * tiles_per_frame, ty = tr / p.tiles_x;
+        y0 = ty * (kPatchH * T);
+        x0 = (tr - ty * p.tiles_x) * kPatchW;
+    };
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
@@ -190,7 +200,10 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             mbar_init(b_full + 8u * i, 1);
             mbar_init(b_empty + 8u * i, 1);
         }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < NB; ++i) {
+            mbar_init(acc_full + 8u * i, 1);
+            mbar_init(acc_empty + 8u * i, kLoaders);  // the 128 epilogue threads
+        }
         s_abort_word = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -203,60 +216,144 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
 
     if (warp < 4) {
         // ================================ halo loaders ===========================================================================
-        // Where each pixel row of the stage comes from is the same for every channel block: worked out once per CTA (the
-        // divisions, the bounds checks and -- for a gathered input -- the index-map lookups, all independent loads), kept in
-        // shared memory as the pixel's index in the source array (-1 = zero fill: padding, empty cell, outside the image).
-        for (int px = tid; px < p.stage_rows; px += kLoaders) {
-            int iy, ix;
-            if (p.stride == 1) {
-                const int hy = px / p.pitch, hx = px - hy * p.pitch;
-                iy = y0 - p.pad + hy;
-                ix = x0 - p.pad + hx;
-            } else {
-                const int plane = px / p.plane_rows, rem = px - plane * p.plane_rows;
-                const int q = rem / p.pitch, qx = rem - q * p.pitch;
-                iy = 2 * (y0 + q - 1) + (plane >> 1);
-                ix = 2 * (x0 + qx - 1) + (plane & 1);
-            }
-            int32_t src = -1;
-            if (iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in) {
-                src = (b * p.h_in + iy) * p.w_in + ix;
-                if (p.rows) src = __ldg(p.cell_row + src);  // the pixel's channels are a pillar row, or the cell is empty
-            }
-            s_src[px] = src;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
-        if (tid == 0) tl_stamp(p, 2);  // source table done
-        const int ch = tid & 7;           // 16-byte chunk of the pixel's 128-byte row; this thread takes rows (tid >> 3) + 16 j
+        // A thread loads chunk ch of the pixel rows px = (tid >> 3) + 16 j; a WARP therefore owns the rows with
+        // (px mod 16) / 4 == warp, fills exactly those entries of the source table and needs no barrier wider than itself.
+        // The table says where each pixel row comes from (the pixel's index in the source array, -1 = zero fill: padding,
+        // empty cell, outside the image): divisions, bounds and -- for a gathered input -- the index-map lookups are done once
+        // per tile set, not once per channel block.
+        const int ch = tid & 7;
         const float *const base = (p.rows ? p.rows : p.in) + ch * 4;
         const uint32_t dst0 = static_cast<uint32_t>(tid >> 3) * 128u + (static_cast<uint32_t>(ch ^ ((tid >> 3) & 7)) << 4);
-        for (int cb = 0; cb < cbn; ++cb) {
-            const int sa = cb % SA;
-            if (cb >= SA && !mbar_wait(a_empty + 8u * sa, ((cb / SA) - 1) & 1u, s_abort)) break;
-            const uint32_t stage = a0 + sa * a_bytes + dst0;
-            const float *const src_cb = base + cb * 32;
-#pragma unroll 4
-            for (int px = tid >> 3; px < p.stage_rows; px += kLoaders / 8) {
-                const int32_t src = s_src[px];
-                cp_async16_zfill(stage + static_cast<uint32_t>(px - (tid >> 3)) * 128u,
-                                 src_cb + static_cast<size_t>(src < 0 ? 0 : src) * p.c_in, src >= 0);
+        int ia = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+            int b, y0, x0;
+            tile_origin(tile, b, y0, x0);
+            __syncwarp();
+            for (int e = lane; e < ((p.stage_rows + 15) >> 4) * 4; e += 32) {
+                const int px = (e >> 2) * 16 + warp * 4 + (e & 3);
+                if (px >= p.stage_rows) continue;
+                int iy, ix;
+                if (p.stride == 1) {
+                    const int hy = px / p.pitch, hx = px - hy * p.pitch;
+                    iy = y0 - p.pad + hy;
+                    ix = x0 - p.pad + hx;
+                } else {
+                    const int plane = px / p.plane_rows, rem = px - plane * p.plane_rows;
+                    const int q = rem / p.pitch, qx = rem - q * p.pitch;
+                    iy = 2 * (y0 + q - 1) + (plane >> 1);
+                    ix = 2 * (x0 + qx - 1) + (plane & 1);
+                }
+                int32_t src = -1;
+                if (iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in) {
+                    src = (b * p.h_in + iy) * p.w_in + ix;
+                    if (p.rows) src = __ldg(p.cell_row + src);  // the pixel's channels are a pillar row, or the cell is empty
+                }
+                s_src[px] = src;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fence_async_smem();  // this thread's writes are in shared memory: make them visible to the tensor core's proxy
-            mbar_arrive(a_full + 8u * sa);
-            if (tid == 0 && cb < 8) tl_stamp(p, 8 + cb);  // halo stage cb landed
+            __syncwarp();
+            if (tid == 0 && tile == blockIdx.x) tl_stamp(p, 2);  // first source table done
+            for (int cb = 0; cb < cbn; ++cb, ++ia) {
+                const int sa = ia % SA;
+                if (ia >= SA && !mbar_wait(a_empty + 8u * sa, ((ia / SA) - 1) & 1u, s_abort)) {
+                    ok = false;
+                    break;
+                }
+                const uint32_t stage = a0 + sa * a_bytes + dst0;
+                const float *const src_cb = base + cb * 32;
+#pragma unroll 4
+                for (int px = tid >> 3; px < p.stage_rows; px += kLoaders / 8) {
+                    const int32_t src = s_src[px];
+                    cp_async16_zfill(stage + static_cast<uint32_t>(px - (tid >> 3)) * 128u,
+                                     src_cb + static_cast<size_t>(src < 0 ? 0 : src) * p.c_in, src >= 0);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fence_async_smem();  // this thread's writes are in shared memory: make them visible to the tensor core's proxy
+                mbar_arrive(a_full + 8u * sa);
+                if (tid == 0 && ia < 8) tl_stamp(p, 8 + ia);  // halo stage landed
+            }
         }
-        // ================================ epilogue ===============================================================================
-        if (mbar_wait(acc_full, 0u, s_abort)) {
+    } else if (warp == 4) {
+        // ================================ MMA issue ==============================================================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(N);
+            const uint32_t sbo = static_cast<uint32_t>(p.pitch) * 128u;
+            const uint32_t tile_step = static_cast<uint32_t>(kPatchH * p.pitch) * 128u;
+            bool ok = true;
+            int ia = 0, ib = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++it) {
+                const int buf = it % NB;
+                if (it >= NB) ok = mbar_wait(acc_empty + 8u * buf, ((it / NB) - 1) & 1u, s_abort);  // drained by the epilogue
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t acc = tmem + static_cast<uint32_t>(buf) * acc_cols;
+                uint32_t accumulate = 0;
+                for (int cb = 0; cb < cbn && ok; ++cb, ++ia) {
+                    const int sa = ia % SA;
+                    ok = mbar_wait(a_full + 8u * sa, (ia / SA) & 1u, s_abort);
+                    if (ia < 8) tl_stamp(p, 16 + ia);  // MMA thread: halo stage available
+                    const uint32_t stage = a0 + sa * a_bytes;
+                    for (int tap = 0; tap < p.taps && ok; ++tap, ++ib) {
+                        const int sb = ib % SB;
+                        ok = mbar_wait(b_full + 8u * sb, (ib / SB) & 1u, s_abort);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint64_t ad = umma_desc(stage + static_cast<uint32_t>(p.tap_off[tap]) * 128u, sbo);
+                        const uint64_t bd = umma_desc(b0 + sb * b_bytes, 1024u);
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)  // (+2 in the address field = +32 bytes = the next 8 channels)
+                                umma_tf32(acc + static_cast<uint32_t>(t * N), ad + ((t * tile_step + k * 32u) >> 4), bd + 2u * k, idesc,
+                                          k == 0 ? accumulate : 1u);
+                        }
+                        accumulate = 1u;
+                        umma_commit(b_empty + 8u * sb);
+                    }
+                    umma_commit(a_empty + 8u * sa);
+                }
+                umma_commit(acc_full + 8u * buf);
+                if (it == 0) tl_stamp(p, 4);  // last MMA of the first tile set issued
+            }
+        }
+    } else if (warp == 5) {
+        // ================================ weight copies ==========================================================================
+        if (lane == 0) {
+            const uint8_t *src = p.wimg + static_cast<size_t>(phase) * cbn * p.taps * b_bytes;
+            const int per_tile = cbn * p.taps;
+            int ib = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+                for (int i = 0; i < per_tile; ++i, ++ib) {
+                    const int sb = ib % SB;
+                    if (ib >= SB && !mbar_wait(b_empty + 8u * sb, ((ib / SB) - 1) & 1u, s_abort)) {
+                        ok = false;
+                        break;
+                    }
+                    mbar_expect_tx(b_full + 8u * sb, b_bytes);
+                    bulk_g2s(b0 + sb * b_bytes, src + static_cast<size_t>(i) * b_bytes, b_bytes, b_full + 8u * sb);
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 6-9) ===================================================================
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int r = 4 * q + (lane >> 3), c = lane & 7;  // accumulator lane = MMA row = patch pixel (r, c)
+        // transposed convolutions: the accumulator holds TWO horizontally adjacent output phases side by side (columns
+        // [0, cw) and [cw, 2 cw)), so a thread stores pairs of neighbouring pixels: full sectors, not every other float
+        const int cw = p.pair ? N / 2 : N;
+        const int half = p.out_mul >> 1;  // phase = dy * half + g;  output column = ox * up + 2 g + {0, 1}
+        uint8_t *const stg = s_stage + q * 4096;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it % NB;
+            if (!mbar_wait(acc_full + 8u * buf, (it / NB) & 1u, s_abort)) break;
             tc_fence_after();
-            if (tid == 0) tl_stamp(p, 3);  // accumulators complete
-            const int r = tid >> 3, c = tid & 7;  // accumulator lane = MMA row = patch pixel (r, c)
-            // transposed convolutions: the accumulator holds TWO horizontally adjacent output phases side by side (columns
-            // [0, cw) and [cw, 2 cw)), so a thread stores pairs of neighbouring pixels: full sectors, not every other float
-            const int cw = p.pair ? N / 2 : N;
-            const int half = p.out_mul >> 1;  // phase = dy * half + g;  output column = ox * up + 2 g + {0, 1}
-            const uint32_t lane_base = tmem + (static_cast<uint32_t>(32 * warp) << 16);
+            if (it == 0 && tid == 192) tl_stamp(p, 3);  // first accumulators complete
+            int b, y0, x0;
+            tile_origin(tile, b, y0, x0);
+            const uint32_t lane_base = tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(buf) * acc_cols;
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int oy = y0 + kPatchH * t + r, ox = x0 + c;
@@ -299,10 +396,8 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                         for (int j = 0; j < 8; ++j) dst[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
                     } else {
                         // NHWC: a thread owns one pixel, so its 128 bytes of this chunk are contiguous but the warp's 32 pixels
-                        // are not -- written directly, every store instruction scatters 32 sixteen-byte pieces (measured: the
-                        // epilogue took 14 us of a 47 us CTA).  The 32 x 32 tile goes through shared memory (the halo stages
-                        // are idle by now) so that eight lanes write one pixel's full 128-byte line.
-                        uint8_t *const stg = s_al + warp * 4096;
+                        // are not: the 32 x 32 tile goes through shared memory so that eight lanes write one pixel's full
+                        // 128-byte line.
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -312,7 +407,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = 4 * i + (lane >> 3);  // pixel of the warp's 32 (= 4 patch rows x 8 columns)
-                            const int oy2 = y0 + kPatchH * t + 4 * warp + (rr >> 3), ox2 = x0 + (rr & 7);
+                            const int oy2 = y0 + kPatchH * t + 4 * q + (rr >> 3), ox2 = x0 + (rr & 7);
                             const float4 val = *reinterpret_cast<const float4 *>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
                             if (oy2 < p.h_out && ox2 < p.w_out)
                                 *reinterpret_cast<float4 *>(p.out + ((static_cast<size_t>(b) * p.out_h + oy2) * p.out_w + ox2) * p.out_c_total +
@@ -321,57 +416,11 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                     }
                 }
             }
-        }
-    } else if (warp == 4) {
-        // ================================ MMA issue ==============================================================================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(N);
-            const uint32_t sbo = static_cast<uint32_t>(p.pitch) * 128u;
-            const uint32_t tile_step = static_cast<uint32_t>(kPatchH * p.pitch) * 128u;
-            uint32_t accumulate = 0;
-            bool ok = true;
-            int i = 0;
-            for (int cb = 0; cb < cbn && ok; ++cb) {
-                const int sa = cb % SA;
-                ok = mbar_wait(a_full + 8u * sa, (cb / SA) & 1u, s_abort);
-                if (cb < 8) tl_stamp(p, 16 + cb);  // MMA thread: halo stage cb available
-                const uint32_t stage = a0 + sa * a_bytes;
-                for (int tap = 0; tap < p.taps && ok; ++tap, ++i) {
-                    const int sb = i % SB;
-                    ok = mbar_wait(b_full + 8u * sb, (i / SB) & 1u, s_abort);
-                    if (!ok) break;
-                    tc_fence_after();
-                    const uint32_t av = stage + static_cast<uint32_t>(p.tap_off[tap]) * 128u, bv = b0 + sb * b_bytes;
-#pragma unroll
-                    for (int t = 0; t < T; ++t) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_tf32(tmem + static_cast<uint32_t>(t * N), umma_desc(av + t * tile_step + k * 32u, sbo),
-                                      umma_desc(bv + k * 32u, 1024u), idesc, k == 0 ? accumulate : 1u);
-                        }
-                    }
-                    accumulate = 1u;
-                    umma_commit(b_empty + 8u * sb);
-                }
-                umma_commit(a_empty + 8u * sa);
-            }
-            umma_commit(acc_full);
-            tl_stamp(p, 4);  // last MMA issued
-        }
-    } else {
-        // ================================ weight copies ==========================================================================
-        if (lane == 0) {
-            const uint8_t *src = p.wimg + static_cast<size_t>(phase) * cbn * p.taps * b_bytes;
-            const int total = cbn * p.taps;
-            for (int i = 0; i < total; ++i) {
-                const int sb = i % SB;
-                if (i >= SB && !mbar_wait(b_empty + 8u * sb, ((i / SB) - 1) & 1u, s_abort)) break;
-                mbar_expect_tx(b_full + 8u * sb, b_bytes);
-                bulk_g2s(b0 + sb * b_bytes, src + static_cast<size_t>(i) * b_bytes, b_bytes, b_full + 8u * sb);
-            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + 8u * buf);  // this thread has read its part of the accumulator
+            if (it == 0 && tid == 192) tl_stamp(p, 5);  // first epilogue done
         }
     }
-    if (tid == 0) tl_stamp(p, 5);  // epilogue done (this thread)
     if (*s_abort && tid == 0 && p.error) atomicExch(p.error, 0xC0DE0000u | static_cast<uint32_t>(blockIdx.x & 0xFFFF));
     tc_fence_before();
     __syncthreads();
@@ -415,16 +464,18 @@ __global__ void k_conv_wimg(const float *__restrict__ weight, const float *__res
     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-template <int N, int T, int SA, int SB, int MB = 1>
+template <int N, int T, int SA, int SB, int NB, int MB = 1>
 cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
 {
     const size_t a_bytes = (static_cast<size_t>(p.stage_rows) * 128 + 1023) & ~static_cast<size_t>(1023);
-    const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 1024;
-    if (smem > 226 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 4 * 4096 + 1024;
+    if (smem > 222 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB, NB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const dim3 grid(static_cast<unsigned>(p.nb * p.tiles_x * p.tiles_y), 1, static_cast<unsigned>(phases));
-    k_conv_umma<N, T, SA, SB, MB><<<grid, kConvThreads, smem, st>>>(p);
+    const int tiles = p.nb * p.tiles_x * p.tiles_y;
+    const int ctas = current_sm_count() * MB;
+    const dim3 grid(static_cast<unsigned>(tiles < ctas ? tiles : ctas), 1, static_cast<unsigned>(phases));
+    k_conv_umma<N, T, SA, SB, NB, MB><<<grid, kConvThreads, smem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
@@ -478,12 +529,10 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     if (j.stride == 2 && !((j.k == 3 && j.pad == 1) || (j.k == 2 && j.pad == 0))) return cudaErrorInvalidValue;
     if (j.stride == 1 && j.pad != (j.k - 1) / 2) return cudaErrorInvalidValue;
 
-    // patches per CTA
-    // 64 / 128 columns: two patches, one halo stage, TWO CTAs per SM (one CTA's prologue and epilogue hide behind the other's
-    // MMAs: 0.38 -> 0.31 ms and 0.200 -> 0.189 ms per layer at 16 x 512^2); 256 columns: two patches fill tensor memory, one CTA
+    // patches per tile set: two accumulator buffers of T * N columns must fit the 512 columns of tensor memory
     int T;
     if (n_eff > 256) return cudaErrorInvalidValue;
-    if (j.stride == 1) T = 2;
+    if (j.stride == 1) T = n_eff == 64 ? 4 : n_eff == 128 ? 2 : 1;
     else T = 1;
     while (T > 1 && kPatchH * (T / 2) >= p.h_out) T /= 2;  // small images: do not pad the patch stack past the image
     if (j.stride == 1) {
@@ -506,27 +555,19 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     p.tiles_y = (p.h_out + kPatchH * T - 1) / (kPatchH * T);
     p.tiles_x = (p.w_out + kPatchW - 1) / kPatchW;
 
-#define CONV_CASE(n, t, sa, sb) \
-    if (n_eff == n && T == t) return launch_one<n, t, sa, sb>(p, phases, st)
+#define CONV_CASE(n, t, sa, sb, nb, mb) \
+    if (n_eff == n && T == t) return launch_one<n, t, sa, sb, nb, mb>(p, phases, st)
     if (j.stride == 1) {
-        if (n_eff == 64 && T == 2) return launch_one<64, 2, 1, 4, 2>(p, phases, st);
-        if (n_eff == 128 && T == 2) return launch_one<128, 2, 1, 2, 2>(p, phases, st);
-    }
-    if (j.stride == 1) {
-        CONV_CASE(64, 4, 2, 4);
-        CONV_CASE(64, 2, 2, 4);
-        CONV_CASE(64, 1, 2, 4);
-        CONV_CASE(128, 4, 2, 3);
-        CONV_CASE(128, 2, 2, 3);
-        CONV_CASE(128, 1, 2, 3);
-        CONV_CASE(256, 2, 2, 3);
-        CONV_CASE(256, 1, 2, 3);
+        CONV_CASE(64, 4, 2, 4, 2, 1);
+        CONV_CASE(64, 2, 2, 4, 2, 1);
+        CONV_CASE(64, 1, 2, 4, 2, 1);
+        CONV_CASE(128, 2, 2, 4, 2, 1);
+        CONV_CASE(128, 1, 2, 4, 2, 1);
+        CONV_CASE(256, 1, 2, 4, 2, 1);
     } else {
-        // 64 output channels: one halo stage and two CTAs per SM (one loads while the other multiplies): 0.87 -> 0.52 ms on
-        // the gathered first layer; the same trade measured slightly worse at 128 channels
-        if (n_eff == 64) return launch_one<64, 1, 1, 4, 2>(p, phases, st);
-        CONV_CASE(128, 1, 2, 3);
-        CONV_CASE(256, 1, 1, 3);
+        CONV_CASE(64, 1, 2, 4, 2, 1);
+        CONV_CASE(128, 1, 2, 3, 2, 1);
+        CONV_CASE(256, 1, 1, 3, 2, 1);
     }
 #undef CONV_CASE
     return cudaErrorInvalidValue;
