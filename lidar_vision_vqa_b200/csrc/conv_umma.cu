@@ -27,7 +27,7 @@ namespace pillars {
 
 namespace {
 
-constexpr int kConvThreads = 320;
+constexpr int kConvThreads = 352;  // 4 loader warps, 2 MMA-issue warps (the second only when MW == 2), 1 weight warp, 4 epilogue warps
 constexpr int kLoaders = 128;
 constexpr int kPatchW = 8, kPatchH = 16;
 constexpr int kMaxStageRows = 672;  // (16 * 4 + 2) * 10 = 660 (3x3 stride 1, four patches); 4 * 17 * 9 = 612 (stride 2)
@@ -140,7 +140,7 @@ struct ConvParams {
 
 __device__ __forceinline__ void tl_stamp(const ConvParams &p, int slot)
 {
-    if (p.timeline && blockIdx.x == 200 && blockIdx.z == 0) {
+    if (p.timeline && blockIdx.x == 100 && blockIdx.z == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.timeline[slot] = t;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void tl_stamp(const ConvParams &p, int slot)
 // Persistent: a CTA walks over tile sets (tile = blockIdx.x, += gridDim.x).  With NB = 2 the accumulator is double buffered in
 // tensor memory, so the epilogue of tile set i (warps 6-9) runs under the MMAs of tile set i + 1, and the loaders (warps 0-3)
 // run ahead into the next tile set's halo as soon as a stage is released -- no prologue or epilogue is exposed after the first.
-template <int N, int T, int SA, int SB, int NB, int MB = 1>
+template <int N, int T, int SA, int SB, int NB, int MW = 1, int MB = 1>
 __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_constant__ ConvParams p)
 {
     extern __shared__ __align__(1024) uint8_t s_raw[];
@@ -194,14 +194,14 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     if (tid == 32) {
         for (int i = 0; i < SA; ++i) {
             mbar_init(a_full + 8u * i, kLoaders);
-            mbar_init(a_empty + 8u * i, 1);
+            mbar_init(a_empty + 8u * i, MW);
         }
         for (int i = 0; i < SB; ++i) {
             mbar_init(b_full + 8u * i, 1);
-            mbar_init(b_empty + 8u * i, 1);
+            mbar_init(b_empty + 8u * i, MW);
         }
         for (int i = 0; i < NB; ++i) {
-            mbar_init(acc_full + 8u * i, 1);
+            mbar_init(acc_full + 8u * i, MW);
             mbar_init(acc_empty + 8u * i, kLoaders);  // the 128 epilogue threads
         }
         s_abort_word = 0u;
@@ -274,9 +274,12 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                 if (tid == 0 && ia < 8) tl_stamp(p, 8 + ia);  // halo stage landed
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 4 || warp == 5) {
         // ================================ MMA issue ==============================================================================
-        if (lane == 0) {
+        // One thread issues; with MW == 2 a second warp's thread issues the other half of the patches (64-column MMAs last
+        // ~34 cycles, about what one thread needs to issue one: the stage barriers then count two commits).
+        const int mw = warp - 4;
+        if (lane == 0 && mw < MW) {
             const uint32_t idesc = umma_idesc_tf32(N);
             const uint32_t sbo = static_cast<uint32_t>(p.pitch) * 128u;
             const uint32_t tile_step = static_cast<uint32_t>(kPatchH * p.pitch) * 128u;
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                 for (int cb = 0; cb < cbn && ok; ++cb, ++ia) {
                     const int sa = ia % SA;
                     ok = mbar_wait(a_full + 8u * sa, (ia / SA) & 1u, s_abort);
-                    if (ia < 8) tl_stamp(p, 16 + ia);  // MMA thread: halo stage available
+                    if (ia < 8 && mw == 0) tl_stamp(p, 16 + ia);  // MMA thread: halo stage available
                     const uint32_t stage = a0 + sa * a_bytes;
                     for (int tap = 0; tap < p.taps && ok; ++tap, ++ib) {
                         const int sb = ib % SB;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                         const uint64_t bd = umma_desc(b0 + sb * b_bytes, 1024u);
 #pragma unroll
                         for (int t = 0; t < T; ++t) {
+                            if (MW == 2 && (t & 1) != mw) continue;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)  // (+2 in the address field = +32 bytes = the next 8 channels)
                                 umma_tf32(acc + static_cast<uint32_t>(t * N), ad + ((t * tile_step + k * 32u) >> 4), bd + 2u * k, idesc,
@@ -314,10 +318,10 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                     umma_commit(a_empty + 8u * sa);
                 }
                 umma_commit(acc_full + 8u * buf);
-                if (it == 0) tl_stamp(p, 4);  // last MMA of the first tile set issued
+                if (it == 0 && mw == 0) tl_stamp(p, 4);  // last MMA of the first tile set issued
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 6) {
         // ================================ weight copies ==========================================================================
         if (lane == 0) {
             const uint8_t *src = p.wimg + static_cast<size_t>(phase) * cbn * p.taps * b_bytes;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             }
         }
     } else {
-        // ================================ epilogue (warps 6-9) ===================================================================
+        // ================================ epilogue (warps 7-10) ==================================================================
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int r = 4 * q + (lane >> 3), c = lane & 7;  // accumulator lane = MMA row = patch pixel (r, c)
         // transposed convolutions: the accumulator holds TWO horizontally adjacent output phases side by side (columns
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             const int buf = it % NB;
             if (!mbar_wait(acc_full + 8u * buf, (it / NB) & 1u, s_abort)) break;
             tc_fence_after();
-            if (it == 0 && tid == 192) tl_stamp(p, 3);  // first accumulators complete
+            if (it == 0 && tid == 224) tl_stamp(p, 3);  // first accumulators complete
             int b, y0, x0;
             tile_origin(tile, b, y0, x0);
             const uint32_t lane_base = tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(buf) * acc_cols;
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             }
             tc_fence_before();
             mbar_arrive(acc_empty + 8u * buf);  // this thread has read its part of the accumulator
-            if (it == 0 && tid == 192) tl_stamp(p, 5);  // first epilogue done
+            if (it == 0 && tid == 224) tl_stamp(p, 5);  // first epilogue done
         }
     }
     if (*s_abort && tid == 0 && p.error) atomicExch(p.error, 0xC0DE0000u | static_cast<uint32_t>(blockIdx.x & 0xFFFF));
@@ -464,18 +468,18 @@ __global__ void k_conv_wimg(const float *__restrict__ weight, const float *__res
     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-template <int N, int T, int SA, int SB, int NB, int MB = 1>
+template <int N, int T, int SA, int SB, int NB, int MW, int MB = 1>
 cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
 {
     const size_t a_bytes = (static_cast<size_t>(p.stage_rows) * 128 + 1023) & ~static_cast<size_t>(1023);
     const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 4 * 4096 + 1024;
     if (smem > 222 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB, NB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB, NB, MW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int tiles = p.nb * p.tiles_x * p.tiles_y;
     const int ctas = current_sm_count() * MB;
     const dim3 grid(static_cast<unsigned>(tiles < ctas ? tiles : ctas), 1, static_cast<unsigned>(phases));
-    k_conv_umma<N, T, SA, SB, NB, MB><<<grid, kConvThreads, smem, st>>>(p);
+    k_conv_umma<N, T, SA, SB, NB, MW, MB><<<grid, kConvThreads, smem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
@@ -555,11 +559,11 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     p.tiles_y = (p.h_out + kPatchH * T - 1) / (kPatchH * T);
     p.tiles_x = (p.w_out + kPatchW - 1) / kPatchW;
 
-#define CONV_CASE(n, t, sa, sb, nb, mb) \
-    if (n_eff == n && T == t) return launch_one<n, t, sa, sb, nb, mb>(p, phases, st)
+#define CONV_CASE(n, t, sa, sb, nb, mw) \
+    if (n_eff == n && T == t) return launch_one<n, t, sa, sb, nb, mw>(p, phases, st)
     if (j.stride == 1) {
-        CONV_CASE(64, 4, 2, 4, 2, 1);
-        CONV_CASE(64, 2, 2, 4, 2, 1);
+        CONV_CASE(64, 4, 2, 4, 2, 2);
+        CONV_CASE(64, 2, 2, 4, 2, 2);
         CONV_CASE(64, 1, 2, 4, 2, 1);
         CONV_CASE(128, 2, 2, 4, 2, 1);
         CONV_CASE(128, 1, 2, 4, 2, 1);

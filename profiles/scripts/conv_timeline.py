@@ -13,8 +13,8 @@ x = torch.rand((nb, h, w, c_in), device=dev)
 oh, ow = B.BaseBEVBackbone._out_hw(h, w, l.desc)
 y = torch.empty((nb, oh, ow, c_out), device=dev)
 lib = _native.load()
-NAMES = {0: "CTA start", 1: "set-up done (TMEM, barriers)", 2: "source table done", 3: "epilogue: accumulators complete",
-         4: "MMA thread: last MMA issued", 5: "epilogue done"}
+NAMES = {0: "CTA start", 1: "set-up done (TMEM, barriers)", 2: "source table done", 3: "epilogue: first accumulators complete",
+         4: "MMA thread: last MMA of tile set 0 issued", 5: "epilogue of tile set 0 done"}
 NAMES.update({8 + i: f"loader: halo stage {i} landed" for i in range(8)})
 NAMES.update({16 + i: f"MMA thread: halo stage {i} available" for i in range(8)})
 rows = []
@@ -27,6 +27,6 @@ for rep in range(6):
     v = buf.cpu().numpy()
     if rep >= 2:
         rows.append({k_: int(v[k_]) - int(v[0]) for k_ in NAMES if v[k_] != 0})
-print(f"conv {c_in}->{c_out} k{k} s{stride} on 16 x {h} x {w}: microseconds since the CTA's start (CTA 200, median of {len(rows)})")
+print(f"conv {c_in}->{c_out} k{k} s{stride} on 16 x {h} x {w}: microseconds since the CTA's start (CTA 100, median of {len(rows)})")
 for k_ in sorted(rows[0], key=lambda q: np.median([r[q] for r in rows if q in r])):
     print(f"  {NAMES[k_]:40s} {np.median([r[k_] for r in rows if k_ in r]) / 1e3:8.2f}")
