@@ -231,9 +231,6 @@ typedef struct pillars_tokenizer {
     float ln_eps;               /* norm_tokens.eps (1e-5)                                             */
     const float *pe;            /* [h*w, d_model] written by pillars_tokens_prepare                   */
     const float *background;    /* [d_model]      written by pillars_tokens_prepare                   */
-    const float *proj_frag;     /* [2*c_in*d_model] optional: the projection in tensor-core fragment order, written by
-                                   pillars_tokens_prepare.  When set (and c_in % 8 == 0, d_model 128 or 256) the 1x1
-                                   projection runs on the tensor cores as a 3-term TF32 split (fp32-accurate); NULL: FMA pipes */
     const float *proj_umma;     /* [2*c_in*d_model] optional: the projection as the shared-memory image of the tcgen05 variant
                                    (tf32 hi | lo halves, K-major, 128-byte swizzle), written by pillars_tokens_prepare.  When set
                                    (c_in 32 or 64, d_model 128 or 256) and a workspace is given, the active cells of the batch are
@@ -244,12 +241,11 @@ typedef struct pillars_tokenizer {
  * background_out = LayerNorm(proj(GELU(refine bias))), the token (before PE) of a cell whose 3x3 window is all zero.
  * geom [h*w,5] / sector [h*w] are the tables of VATLiDAR._grid (:123-185), computed by the caller;
  * geo_w1 [d,5] = geo_mlp.0.weight, geo_w2_t [d,d] = geo_mlp.2.weight TRANSPOSED, view_embed [6,d].
- * proj_frag_out / proj_umma_out (2*c_in*d_model floats each, may be NULL) receive the tables for tk->proj_frag / proj_umma.
- * Reads tk->{c_in,d_model,dw_bias,proj_weight_t,proj_bias,ln_*}; tk->pe / background / proj_frag are not read. */
+ * proj_umma_out (2*c_in*d_model floats, may be NULL) receives the table for tk->proj_umma.
+ * Reads tk->{c_in,d_model,dw_bias,proj_weight_t,proj_bias,ln_*}; tk->pe / background / proj_umma are not read. */
 int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
                            const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
-                           const float *view_embed, float *pe_out, float *background_out, float *proj_frag_out,
-                           float *proj_umma_out, void *stream);
+                           const float *view_embed, float *pe_out, float *background_out, float *proj_umma_out, void *stream);
 
 /* Scratch bytes: index map + pair list (dense == 0, for pillars_bev_tokens / _map) or those + compacted rows (dense != 0). */
 size_t pillars_tokens_workspace_bytes(int32_t n_frames, int32_t c_in, int32_t h, int32_t w, int32_t dense);

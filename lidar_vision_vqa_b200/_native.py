@@ -75,7 +75,7 @@ class PillarsOutputs(Structure):
 class PillarsTokenizer(Structure):
     _fields_ = [("c_in", c_int32), ("d_model", c_int32), ("dw_weight", c_void_p), ("dw_bias", c_void_p),
                 ("proj_weight_t", c_void_p), ("proj_bias", c_void_p), ("ln_weight", c_void_p), ("ln_bias", c_void_p),
-                ("ln_eps", c_float), ("pe", c_void_p), ("background", c_void_p), ("proj_frag", c_void_p), ("proj_umma", c_void_p)]
+                ("ln_eps", c_float), ("pe", c_void_p), ("background", c_void_p), ("proj_umma", c_void_p)]
 
 
 class PillarsConv(Structure):
@@ -147,7 +147,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                          c_size_t, c_int32, c_void_p]
     lib.pillars_tokens_prepare.restype = c_int
     lib.pillars_tokens_prepare.argtypes = [POINTER(PillarsTokenizer), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
-                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pillars_tokens_workspace_bytes.restype = c_size_t
     lib.pillars_tokens_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
     lib.pillars_bev_tokens.restype = c_int

@@ -584,17 +584,14 @@ static int check_tokenizer(const pillars_tokenizer_t *tk, bool need_tables, Toke
     td->c = tk->c_in; td->d = tk->d_model;
     td->dw_w = tk->dw_weight; td->dw_b = tk->dw_bias; td->wt = tk->proj_weight_t; td->pb = tk->proj_bias;
     td->gamma = tk->ln_weight; td->beta = tk->ln_bias; td->eps = tk->ln_eps; td->pe = tk->pe; td->bg = tk->background;
-    td->wfrag = need_tables ? tk->proj_frag : nullptr;
     td->wimg = need_tables ? tk->proj_umma : nullptr;
     if (td->wimg && reinterpret_cast<uintptr_t>(td->wimg) % 16 != 0) return fail(PILLARS_E_BADARG, "proj_umma not 16-byte aligned");
-    if (td->wfrag && reinterpret_cast<uintptr_t>(td->wfrag) % 16 != 0) return fail(PILLARS_E_BADARG, "proj_frag not 16-byte aligned");
     return 0;
 }
 
 int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, const int32_t *sector, int32_t h, int32_t w,
                            const float *geo_w1, const float *geo_b1, const float *geo_w2_t, const float *geo_b2,
-                           const float *view_embed, float *pe_out, float *background_out, float *proj_frag_out,
-                           float *proj_umma_out, void *stream)
+                           const float *view_embed, float *pe_out, float *background_out, float *proj_umma_out, void *stream)
 {
     g_launches = 0;
     TokenizerDev td{};
@@ -606,7 +603,7 @@ int pillars_tokens_prepare(const pillars_tokenizer_t *tk, const float *geom, con
     if (static_cast<int64_t>(h) * w > 0 && (!geom || !sector || !pe_out))
         return fail(PILLARS_E_BADARG, "pillars_tokens_prepare: geom / sector / pe_out NULL");
     cudaError_t e = launch_tokens_prepare(td, geom, sector, h, w, geo_w1, geo_b1, geo_w2_t, geo_b2, view_embed, pe_out,
-                                          background_out, proj_frag_out, static_cast<cudaStream_t>(stream));
+                                          background_out, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "tokens_prepare");
     if (proj_umma_out && tokens_umma_supported(td.c, td.d) &&
         (e = launch_tokens_wimg(td.wt, td.c, td.d, proj_umma_out, static_cast<cudaStream_t>(stream))) != cudaSuccess)

@@ -373,18 +373,16 @@ struct TokenizerDev {
     const float *gamma, *beta; // LayerNorm
     float eps;
     const float *pe, *bg;      // [h*w, d], [d]
-    const float *wfrag;        // [2 * c * d] projection in mma.sync fragment order, or NULL
     const float *wimg;         // [2 * c * d] projection as the tcgen05 shared-memory image (tf32 hi | lo, swizzled), or NULL
 };
 bool tokens_shape_supported(int c, int d);
-bool tokens_mma_supported(int c, int d);
 bool tokens_umma_supported(int c, int d);
 cudaError_t launch_tokens_wimg(const float *wt, int c, int d, float *img, cudaStream_t st);
 cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, const int32_t *cell_row, int nb, int h, int w,
                                    float *out, uint32_t *list, uint32_t *count, cudaStream_t st);
 cudaError_t launch_tokens_prepare(const TokenizerDev &tk, const float *geom, const int32_t *sid, int h, int w, const float *w1,
                                   const float *b1, const float *w2t, const float *b2, const float *view, float *pe, float *bg,
-                                  float *wfrag, cudaStream_t st);
+                                  cudaStream_t st);
 // One convolution layer of the BEV backbone (conv_umma.cu)
 struct ConvJob {
     const float *in;           // NHWC [nb, h_in, w_in, c_in], or NULL when the input is gathered:

@@ -43,21 +43,6 @@ __device__ __forceinline__ void fma2s(float &c0, float &c1, float w0, float w1, 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(rc));
 }
 
-// ---- tensor-core projection: mma.sync m16n8k8 TF32 with the 3-term split  a.b ~ a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (each
-//      operand = tf32(x) + tf32(x - tf32(x)); the dropped a_lo.b_lo term is 2^-22 relative), fp32 accumulation ------------
-__device__ __forceinline__ uint32_t to_tf32(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 struct TokParams {
     const float *feats;      // [rows, c] pillar rows
     const int32_t *cell_row; // [nb, h, w], -1 = empty cell
@@ -71,7 +56,6 @@ struct TokParams {
     const float *pe;         // [h*w, d]
     const float *bg;         // [d]
     float *out;              // [nb, h*w, d]
-    const uint4 *wfrag;      // projection in mma fragment order (k_tok_wfrag), or NULL
 };
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -81,10 +65,9 @@ struct TokParams {
 // 2 CTAs/SM 1586 us, G = 4 at 3 CTAs/SM 1425 us; d = 512: G = 4 1475 us, G = 2 1645 us.
 // dynamic shared memory: s_dw [10][c] (depthwise weights transposed + bias) | s_a [warps][c/4][G] float4 (refined activations)
 // -------------------------------------------------------------------------------------------------------------------
-template <int NQ, int G, bool kMma>
-__global__ void __launch_bounds__(kTokThreads, (!kMma && NQ * G <= 8) ? 3 : 2) k_bev_tokens(const __grid_constant__ TokParams p)
+template <int NQ, int G>
+__global__ void __launch_bounds__(kTokThreads, (NQ * G <= 8) ? 3 : 2) k_bev_tokens(const __grid_constant__ TokParams p)
 {
-    static_assert(!kMma || (G == 8 && NQ <= 2), "the tensor-core variant keeps 8 cells x d <= 256 channels in registers");
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ int32_t s_map[kFrameChunk][3][kTileX + 2];
     __shared__ uint32_t s_act[kFrameChunk];                  // bit t: cell t of the tile has a non-empty window
@@ -94,8 +77,8 @@ __global__ void __launch_bounds__(kTokThreads, (!kMma && NQ * G <= 8) ? 3 : 2) k
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = p.c, d = p.d, w = p.w, h = p.h;
     float *const s_dw = s_dyn;
-    // activation tile of the warp's group: FMA variant [quad][G] float4, tensor-core variant [G][c + 4] (padded rows)
-    float *const s_a = s_dyn + 10 * c + warp * G * (c + (kMma ? 4 : 0));
+    // activation tile of the warp's group: [quad][G] float4
+    float *const s_a = s_dyn + 10 * c + warp * G * c;
     const int x0 = blockIdx.x * kTileX, y = blockIdx.y;
 
     for (int i = tid; i < 9 * c; i += kTokThreads) {
@@ -195,174 +178,82 @@ __global__ void __launch_bounds__(kTokThreads, (!kMma && NQ * G <= 8) ? 3 : 2) k
                         acc.w = fmaf(wk.w, f[k].w, acc.w);
                     }
                     const float4 act = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
-                    if constexpr (kMma) *reinterpret_cast<float4 *>(s_a + rg * (c + 4) + 4 * qd) = act;
-                    else reinterpret_cast<float4 *>(s_a)[qd * G + rg] = act;
+                    reinterpret_cast<float4 *>(s_a)[qd * G + rg] = act;
                 }
             }
             __syncwarp();
-            if constexpr (kMma) {
-                // projection on the tensor cores, transposed: D[channel][cell] = Wp[channel][k] . act[k][cell].  A = Wp tile
-                // (16 channels x 8 k) pre-split into hi/lo and stored in fragment order by k_tok_wfrag, B = activations of
-                // the group's 8 cells.  Lane (gq = lane / 4, tq = lane % 4) ends up with channels 16 m + gq (+ 8) of cells
-                // 2 tq and 2 tq + 1, i.e. a cell's d channels sit in the 8 lanes that share tq.
-                constexpr int MT = NQ * 8;  // 16-channel tiles
-                const int gq = lane >> 2, tq = lane & 3;
-                float acc[MT][4];
+            // projection (vat_lidar.py:88,222): acc[g][q] += a[g][ch] * Wp^T[ch][lane's channels]
+            float acc[G][NQ][4];
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const float b_lo = __ldg(p.pb + 16 * m + gq), b_hi = __ldg(p.pb + 16 * m + gq + 8);
-                    acc[m][0] = b_lo; acc[m][1] = b_lo; acc[m][2] = b_hi; acc[m][3] = b_hi;
-                }
-                const uint4 *wf = p.wfrag + lane * 2;
-                const float *arow = s_a + gq * (c + 4) + tq;  // B fragment: act[cell gq][8 ks + tq (+4)]
-                for (int ks = 0; ks < (c >> 3); ++ks) {
-                    const float x0 = arow[8 * ks], x1 = arow[8 * ks + 4];
-                    const uint32_t b0h = to_tf32(x0), b1h = to_tf32(x1);
-                    const uint32_t b0l = to_tf32(x0 - __uint_as_float(b0h)), b1l = to_tf32(x1 - __uint_as_float(b1h));
-#pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const uint4 hi = __ldg(wf), lo = __ldg(wf + 1);
-                        wf += 64;
-                        const uint32_t ah[4] = {hi.x, hi.y, hi.z, hi.w}, al[4] = {lo.x, lo.y, lo.z, lo.w};
-                        mma_tf32(acc[m], al, b0h, b1h);
-                        mma_tf32(acc[m], ah, b0l, b1l);
-                        mma_tf32(acc[m], ah, b0h, b1h);
-                    }
-                }
-                // LayerNorm per cell: the lane's 2 MT values of cell 2 tq (regs 0, 2) and of cell 2 tq + 1 (regs 1, 3), then the
-                // 8 lanes with the same tq (xor 4, 8, 16)
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    s0 += acc[m][0] + acc[m][2];
-                    s1 += acc[m][1] + acc[m][3];
-                }
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    s0 += __shfl_xor_sync(kFull, s0, o);
-                    s1 += __shfl_xor_sync(kFull, s1, o);
-                }
-                const float mean0 = s0 / static_cast<float>(d), mean1 = s1 / static_cast<float>(d);
-                float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    q0 = fmaf(acc[m][0] - mean0, acc[m][0] - mean0, q0);
-                    q0 = fmaf(acc[m][2] - mean0, acc[m][2] - mean0, q0);
-                    q1 = fmaf(acc[m][1] - mean1, acc[m][1] - mean1, q1);
-                    q1 = fmaf(acc[m][3] - mean1, acc[m][3] - mean1, q1);
-                }
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    q0 += __shfl_xor_sync(kFull, q0, o);
-                    q1 += __shfl_xor_sync(kFull, q1, o);
-                }
-                const float rstd0 = 1.f / sqrtf(q0 / static_cast<float>(d) + p.eps);
-                const float rstd1 = 1.f / sqrtf(q1 / static_cast<float>(d) + p.eps);
-                // + PE, store: per instruction the 8 lanes of one tq cover 32 contiguous bytes of one cell
-                const bool live0 = 2 * tq < cnt, live1 = 2 * tq + 1 < cnt;
-                size_t cell0 = 0, cell1 = 0;
-                float *dst0 = nullptr, *dst1 = nullptr;
-                if (live0) {
-                    const int e = s_list[i0 + 2 * tq];
-                    const int t = e / kFrameChunk, bb = e - t * kFrameChunk;
-                    cell0 = static_cast<size_t>(y) * w + x0 + t;
-                    dst0 = p.out + (static_cast<size_t>(b0 + bb) * h * w + cell0) * d + gq;
-                }
-                if (live1) {
-                    const int e = s_list[i0 + 2 * tq + 1];
-                    const int t = e / kFrameChunk, bb = e - t * kFrameChunk;
-                    cell1 = static_cast<size_t>(y) * w + x0 + t;
-                    dst1 = p.out + (static_cast<size_t>(b0 + bb) * h * w + cell1) * d + gq;
-                }
-                const float *pe0 = p.pe + cell0 * d + gq, *pe1 = p.pe + cell1 * d + gq;
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const int ch = 16 * m;
-                    const float ga = __ldg(p.gamma + ch + gq), gb = __ldg(p.gamma + ch + gq + 8);
-                    const float ba = __ldg(p.beta + ch + gq), bb2 = __ldg(p.beta + ch + gq + 8);
-                    if (live0) {
-                        __stcs(dst0 + ch, fmaf((acc[m][0] - mean0) * rstd0, ga, ba) + __ldg(pe0 + ch));
-                        __stcs(dst0 + ch + 8, fmaf((acc[m][2] - mean0) * rstd0, gb, bb2) + __ldg(pe0 + ch + 8));
-                    }
-                    if (live1) {
-                        __stcs(dst1 + ch, fmaf((acc[m][1] - mean1) * rstd1, ga, ba) + __ldg(pe1 + ch));
-                        __stcs(dst1 + ch + 8, fmaf((acc[m][3] - mean1) * rstd1, gb, bb2) + __ldg(pe1 + ch + 8));
-                    }
-                }
-            } else {
-                // projection (vat_lidar.py:88,222): acc[g][q] += a[g][ch] * Wp^T[ch][lane's channels]
-                float acc[G][NQ][4];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const float4 bq = __ldg(reinterpret_cast<const float4 *>(p.pb) + lane + 32 * q);
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        acc[g][q][0] = bq.x; acc[g][q][1] = bq.y; acc[g][q][2] = bq.z; acc[g][q][3] = bq.w;
-                    }
-                }
-                const float4 *wp = reinterpret_cast<const float4 *>(p.wt) + lane;
-                const int d4 = d >> 2;
-                const float4 *ap = reinterpret_cast<const float4 *>(s_a);          // [quad][G]: one running pointer, immediate offsets
-                const float4 *const ap_end = ap + static_cast<size_t>(quads) * G;
-                for (; ap != ap_end; ap += G) {
-                    float4 av[G];
-#pragma unroll
-                    for (int g = 0; g < G; ++g) av[g] = ap[g];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float4 wv[NQ];
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) wv[q] = __ldg(wp + 32 * q);
-                        wp += d4;
-#pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            const float a = cc == 0 ? av[g].x : cc == 1 ? av[g].y : cc == 2 ? av[g].z : av[g].w;
-#pragma unroll
-                            for (int q = 0; q < NQ; ++q) {
-                                fma2s(acc[g][q][0], acc[g][q][1], wv[q].x, wv[q].y, a);
-                                fma2s(acc[g][q][2], acc[g][q][3], wv[q].z, wv[q].w, a);
-                            }
-                        }
-                    }
-                }
-                // LayerNorm over d (two-pass, as ATen), + PE, store (vat_lidar.py:225,231,245)
+            for (int q = 0; q < NQ; ++q) {
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(p.pb) + lane + 32 * q);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    if (g < cnt) {
-                        float s = 0.f;
+                    acc[g][q][0] = bq.x; acc[g][q][1] = bq.y; acc[g][q][2] = bq.z; acc[g][q][3] = bq.w;
+                }
+            }
+            const float4 *wp = reinterpret_cast<const float4 *>(p.wt) + lane;
+            const int d4 = d >> 2;
+            const float4 *ap = reinterpret_cast<const float4 *>(s_a);          // [quad][G]: one running pointer, immediate offsets
+            const float4 *const ap_end = ap + static_cast<size_t>(quads) * G;
+            for (; ap != ap_end; ap += G) {
+                float4 av[G];
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q) s += (acc[g][q][0] + acc[g][q][1]) + (acc[g][q][2] + acc[g][q][3]);
+                for (int g = 0; g < G; ++g) av[g] = ap[g];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-                        const float mean = s / static_cast<float>(d);
-                        float ss = 0.f;
+                for (int cc = 0; cc < 4; ++cc) {
+                    float4 wv[NQ];
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q)
+                    for (int q = 0; q < NQ; ++q) wv[q] = __ldg(wp + 32 * q);
+                    wp += d4;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float dlt = acc[g][q][j] - mean;
-                                ss = fmaf(dlt, dlt, ss);
-                            }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
-                        const float rstd = 1.f / sqrtf(ss / static_cast<float>(d) + p.eps);
-                        const int e = s_list[i0 + g];
-                        const int t = e / kFrameChunk, bb = e - t * kFrameChunk;
-                        const size_t cell = static_cast<size_t>(y) * w + x0 + t;
-                        float4 *dst = reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(b0 + bb) * h * w + cell) * d) + lane;
-                        const float4 *pe4 = reinterpret_cast<const float4 *>(p.pe + cell * d) + lane;
+                    for (int g = 0; g < G; ++g) {
+                        const float a = cc == 0 ? av[g].x : cc == 1 ? av[g].y : cc == 2 ? av[g].z : av[g].w;
 #pragma unroll
                         for (int q = 0; q < NQ; ++q) {
-                            const float4 ga = __ldg(reinterpret_cast<const float4 *>(p.gamma) + lane + 32 * q);
-                            const float4 be = __ldg(reinterpret_cast<const float4 *>(p.beta) + lane + 32 * q);
-                            const float4 pe = __ldg(pe4 + 32 * q);
-                            float4 o4;
-                            o4.x = fmaf((acc[g][q][0] - mean) * rstd, ga.x, be.x) + pe.x;
-                            o4.y = fmaf((acc[g][q][1] - mean) * rstd, ga.y, be.y) + pe.y;
-                            o4.z = fmaf((acc[g][q][2] - mean) * rstd, ga.z, be.z) + pe.z;
-                            o4.w = fmaf((acc[g][q][3] - mean) * rstd, ga.w, be.w) + pe.w;
-                            __stcs(dst + 32 * q, o4);
+                            fma2s(acc[g][q][0], acc[g][q][1], wv[q].x, wv[q].y, a);
+                            fma2s(acc[g][q][2], acc[g][q][3], wv[q].z, wv[q].w, a);
                         }
+                    }
+                }
+            }
+            // LayerNorm over d (two-pass, as ATen), + PE, store (vat_lidar.py:225,231,245)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (g < cnt) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) s += (acc[g][q][0] + acc[g][q][1]) + (acc[g][q][2] + acc[g][q][3]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+                    const float mean = s / static_cast<float>(d);
+                    float ss = 0.f;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float dlt = acc[g][q][j] - mean;
+                            ss = fmaf(dlt, dlt, ss);
+                        }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+                    const float rstd = 1.f / sqrtf(ss / static_cast<float>(d) + p.eps);
+                    const int e = s_list[i0 + g];
+                    const int t = e / kFrameChunk, bb = e - t * kFrameChunk;
+                    const size_t cell = static_cast<size_t>(y) * w + x0 + t;
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + (static_cast<size_t>(b0 + bb) * h * w + cell) * d) + lane;
+                    const float4 *pe4 = reinterpret_cast<const float4 *>(p.pe + cell * d) + lane;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 ga = __ldg(reinterpret_cast<const float4 *>(p.gamma) + lane + 32 * q);
+                        const float4 be = __ldg(reinterpret_cast<const float4 *>(p.beta) + lane + 32 * q);
+                        const float4 pe = __ldg(pe4 + 32 * q);
+                        float4 o4;
+                        o4.x = fmaf((acc[g][q][0] - mean) * rstd, ga.x, be.x) + pe.x;
+                        o4.y = fmaf((acc[g][q][1] - mean) * rstd, ga.y, be.y) + pe.y;
+                        o4.z = fmaf((acc[g][q][2] - mean) * rstd, ga.z, be.z) + pe.z;
+                        o4.w = fmaf((acc[g][q][3] - mean) * rstd, ga.w, be.w) + pe.w;
+                        __stcs(dst + 32 * q, o4);
                     }
                 }
             }
@@ -608,54 +499,29 @@ __global__ void __launch_bounds__(32 * kRowsWarps) k_canvas_to_rows_v4(const flo
     }
 }
 
-// Projection matrix in mma.m16n8k8 A-fragment order, split into tf32 hi / lo: for k-step ks (8 input channels), channel tile
-// m (16 outputs) and lane l = 4 gq + tq:  {a0,a1,a2,a3} = Wp[16m + gq (+8)][8ks + tq (+4)]  as 4 hi words then 4 lo words.
-__global__ void k_tok_wfrag(const float *__restrict__ wt, int c, int d, uint32_t *__restrict__ frag)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per (ks, m, lane)
-    const int mt = d >> 4;
-    if (i >= static_cast<int64_t>(c >> 3) * mt * 32) return;
-    const int lane = static_cast<int>(i & 31), m = static_cast<int>((i >> 5) % mt), ks = static_cast<int>((i >> 5) / mt);
-    const int gq = lane >> 2, tq = lane & 3;
-    const int rows[4] = {gq, gq + 8, gq, gq + 8}, cols[4] = {tq, tq, tq + 4, tq + 4};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float v = wt[static_cast<size_t>(8 * ks + cols[j]) * d + 16 * m + rows[j]];
-        const uint32_t hi = to_tf32(v);
-        frag[i * 8 + j] = hi;
-        frag[i * 8 + 4 + j] = to_tf32(v - __uint_as_float(hi));
-    }
-}
-
-template <int NQ, int G, bool kMma = false>
+template <int NQ, int G>
 cudaError_t launch_tokens_t(const TokParams &p, cudaStream_t st)
 {
-    const size_t smem = sizeof(float) * (10 * static_cast<size_t>(p.c) + static_cast<size_t>(kTokWarps) * G * (p.c + (kMma ? 4 : 0)));
+    const size_t smem = sizeof(float) * (10 * static_cast<size_t>(p.c) + static_cast<size_t>(kTokWarps) * G * p.c);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_bev_tokens<NQ, G, kMma>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(k_bev_tokens<NQ, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
     const dim3 grid(static_cast<unsigned>((p.w + kTileX - 1) / kTileX), static_cast<unsigned>(p.h));
-    k_bev_tokens<NQ, G, kMma><<<grid, kTokThreads, smem, st>>>(p);
+    k_bev_tokens<NQ, G><<<grid, kTokThreads, smem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
 
 }  // namespace
 
-bool tokens_mma_supported(int c, int d) { return c % 8 == 0 && (d == 128 || d == 256); }
 bool tokens_shape_supported(int c, int d) { return c >= 4 && c % 4 == 0 && c <= 512 && d >= 128 && d % 128 == 0 && d <= 1024; }
 
 cudaError_t launch_tokens_prepare(const TokenizerDev &tk, const float *geom, const int32_t *sid, int h, int w, const float *w1,
                                   const float *b1, const float *w2t, const float *b2, const float *view, float *pe, float *bg,
-                                  float *wfrag, cudaStream_t st)
+                                  cudaStream_t st)
 {
-    if (wfrag && tokens_mma_supported(tk.c, tk.d)) {
-        const int64_t n = static_cast<int64_t>(tk.c >> 3) * (tk.d >> 4) * 32;
-        k_tok_wfrag<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(tk.wt, tk.c, tk.d, reinterpret_cast<uint32_t *>(wfrag));
-        note_launch();
-    }
     k_tok_background<<<1, kTokThreads, sizeof(float) * tk.c, st>>>(tk.dw_b, tk.wt, tk.pb, tk.gamma, tk.beta, tk.eps, tk.c,
                                                                    tk.d, bg);
     note_launch();
@@ -699,9 +565,6 @@ cudaError_t launch_bev_tokens(const TokenizerDev &tk, const float *feats, const 
     p.feats = feats; p.cell_row = cell_row; p.nb = nb; p.h = h; p.w = w; p.c = tk.c; p.d = tk.d;
     p.dw_w = tk.dw_w; p.dw_b = tk.dw_b; p.wt = tk.wt; p.pb = tk.pb; p.gamma = tk.gamma; p.beta = tk.beta; p.eps = tk.eps;
     p.pe = tk.pe; p.bg = tk.bg; p.out = out;
-    p.wfrag = reinterpret_cast<const uint4 *>(tk.wfrag);
-    if (tk.wfrag && tokens_mma_supported(tk.c, tk.d))
-        return tk.d == 128 ? launch_tokens_t<1, 8, true>(p, st) : launch_tokens_t<2, 8, true>(p, st);
     switch (tk.d / 128) {
         case 1: return launch_tokens_t<1, 8>(p, st);
         case 2: return launch_tokens_t<2, 4>(p, st);

@@ -55,15 +55,13 @@ class VATLiDARTokenizer(nn.Module):
         ``"umma"``  tcgen05.mma.kind::tf32 as a 3-term hi/lo split, accumulator in tensor memory, the active cells of the
                     batch compacted into 128-row tiles (c_in 32 or 64, d_model 128 or 256): 1.31 ms against 1.42 ms of
                     ``"fma"`` on 16 x 512^2 at d = 256, 0.79 against 0.96 ms at d = 128 (DESIGN.md 4b);
-        ``"mma"``   the same split with legacy ``mma.sync`` (c_in % 8 == 0, d_model 128 or 256) -- slower, kept as evidence;
         ``"auto"``  ``"umma"`` where it exists, else ``"fma"``."""
         super().__init__()
-        if projection not in ("auto", "fma", "mma", "umma"):
-            raise ValueError("projection must be one of auto / fma / mma / umma")
+        if projection not in ("auto", "fma", "umma"):
+            raise ValueError("projection must be one of auto / fma / umma")
         umma_ok = c_in in (32, 64) and d_model in (128, 256)
         self.projection = ("umma" if umma_ok else "fma") if projection == "auto" else projection
         self._umma: Optional[torch.Tensor] = None
-        self._frag: Optional[torch.Tensor] = None
         self.c_in, self.d_model = int(c_in), int(d_model)
         self.refine = nn.Sequential(nn.Conv2d(c_in, c_in, kernel_size=3, padding=1, groups=c_in), nn.GELU())
         self.proj = nn.Conv2d(c_in, d_model, kernel_size=1, bias=True)
@@ -75,11 +73,11 @@ class VATLiDARTokenizer(nn.Module):
 
     # ---- parameters in the layout the kernels read, rebuilt when the module moves or loads a checkpoint ---------------
     def _apply(self, fn, *a, **k):
-        self._packed, self._tables, self._frag, self._umma = None, {}, None, None
+        self._packed, self._tables, self._umma = None, {}, None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed, self._tables, self._frag, self._umma = None, {}, None, None
+        self._packed, self._tables, self._umma = None, {}, None
         return super().load_state_dict(*a, **k)
 
     def _pack(self, dev) -> Dict[str, torch.Tensor]:
@@ -109,7 +107,6 @@ class VATLiDARTokenizer(nn.Module):
         t.ln_weight, t.ln_bias, t.ln_eps = pk["gamma"].data_ptr(), pk["beta"].data_ptr(), float(self.norm_tokens.eps)
         t.pe = None if pe is None else pe.data_ptr()
         t.background = None if bg is None else bg.data_ptr()
-        t.proj_frag = self._frag.data_ptr() if (self._frag is not None and pe is not None) else None
         t.proj_umma = self._umma.data_ptr() if (self._umma is not None and pe is not None) else None
         return t
 
@@ -134,19 +131,14 @@ class VATLiDARTokenizer(nn.Module):
             pe = torch.empty((h * w, self.d_model), dtype=torch.float32, device=dev)
             bg = torch.empty((self.d_model,), dtype=torch.float32, device=dev)
             nat = self._native_struct(pk)
-            frag = umma = None
-            if self.projection == "mma" and self._frag is None and self.c_in % 8 == 0 and self.d_model in (128, 256):
-                frag = torch.empty((2 * self.c_in * self.d_model,), dtype=torch.float32, device=dev)
+            umma = None
             if self.projection == "umma" and self._umma is None and self.c_in in (32, 64) and self.d_model in (128, 256):
                 umma = torch.empty((2 * self.c_in * self.d_model,), dtype=torch.float32, device=dev)
             check(_native.load().pillars_tokens_prepare(ctypes.byref(nat), geom.data_ptr(), sid.data_ptr(), h, w,
                                                         pk["w1"].data_ptr(), pk["b1"].data_ptr(), pk["w2t"].data_ptr(),
                                                         pk["b2"].data_ptr(), pk["view"].data_ptr(), pe.data_ptr(),
-                                                        bg.data_ptr(), None if frag is None else frag.data_ptr(),
-                                                        None if umma is None else umma.data_ptr(),
+                                                        bg.data_ptr(), None if umma is None else umma.data_ptr(),
                                                         ops._stream_ptr()), "pillars_tokens_prepare")
-            if frag is not None:
-                self._frag = frag
             if umma is not None:
                 self._umma = umma
             self._tables[key] = (pe, bg)

@@ -42,7 +42,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_native.PillarsPfn) == 5 * 4 + 3 * 4 + 4 * 8
     assert ctypes.sizeof(_native.PillarsOutputs) == 10 * 8 + 8  # + want_index_map (int32, padded)
     assert ctypes.sizeof(_native.PillarsConv) == 8 * 4
-    assert ctypes.sizeof(_native.PillarsTokenizer) == 2 * 4 + 6 * 8 + 8 + 4 * 8  # eps padded to 8
+    assert ctypes.sizeof(_native.PillarsTokenizer) == 2 * 4 + 6 * 8 + 8 + 3 * 8  # eps padded to 8
 
 
 def test_workspace_query_and_argument_errors(lib):
