@@ -30,7 +30,6 @@ namespace {
 constexpr int kConvThreads = 352;  // 4 loader warps, 2 MMA-issue warps (the second only when MW == 2), 1 weight warp, 4 epilogue warps
 constexpr int kLoaders = 128;
 constexpr int kPatchW = 8, kPatchH = 16;
-constexpr int kMaxStageRows = 672;  // (16 * 4 + 2) * 10 = 660 (3x3 stride 1, four patches); 4 * 17 * 9 = 612 (stride 2)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 // K-major, 128-byte swizzle; sbo = bytes between 8-row groups (any multiple of 16: the swizzle follows the absolute address)
@@ -158,7 +157,6 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_abort_word;
     __shared__ float s_shift[N];
-    __shared__ int32_t s_src[kMaxStageRows];
     volatile uint32_t *const s_abort = &s_abort_word;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,6 +166,10 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     constexpr uint32_t b_bytes = static_cast<uint32_t>(N) * 128u;
     const uint32_t a0 = smem_u32(s_al), b0 = a0 + SA * a_bytes;
     uint8_t *const s_stage = s_al + SA * a_bytes + SB * b_bytes;  // 4 x 4 KB: the epilogue warps' transposition buffers
+    int32_t *const s_src = reinterpret_cast<int32_t *>(s_stage + 4 * 4096);  // [stage_rows] source of each pixel row
+    const int occ_cap = ((p.stage_rows + 15) >> 4) * 4 + 8;  // pixel rows one loader warp owns (+ slack)
+    // gathered input: per loader warp, the occupied pixel rows of this and of the previous tile set
+    uint16_t *const s_occ = reinterpret_cast<uint16_t *>(s_src + ((p.stage_rows + 15) & ~15));
     const uint32_t bar0 = smem_u32(s_bar);
     const uint32_t a_full = bar0, a_empty = bar0 + 8u * SA, b_full = bar0 + 16u * SA, b_empty = b_full + 8u * SB,
                    acc_full = b_empty + 8u * SB, acc_empty = acc_full + 8u * NB;
@@ -226,6 +228,14 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
         const uint32_t dst0 = static_cast<uint32_t>(tid >> 3) * 128u + (static_cast<uint32_t>(ch ^ ((tid >> 3) & 7)) << 4);
         int ia = 0;
         bool ok = true;
+        // (a stage's previous content must stem from this or the previous tile set: it is reused every SA channel blocks)
+        const bool sparse = p.rows != nullptr && cbn >= SA;
+        int n_prev = 0, n_tiles_done = 0;
+        if (sparse) {  // every pixel row of every stage starts as zeros; only occupied cells are ever written
+            for (uint32_t i = tid; i < (SA * a_bytes) >> 4; i += kLoaders)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a0 + (i << 4)), "r"(0) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");  // (before any wait that could fail: all 128 get here)
+        }
         for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
             int b, y0, x0;
             tile_origin(tile, b, y0, x0);
@@ -253,6 +263,49 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             }
             __syncwarp();
             if (tid == 0 && tile == blockIdx.x) tl_stamp(p, 2);  // first source table done
+            if (sparse) {
+                // Gathered input (pillar rows through the index map): ~95 % of the halo is empty cells.  The stages were zeroed
+                // once; per tile set a warp lists its occupied pixel rows, un-writes the ones the PREVIOUS tile set left in
+                // this stage and copies only the occupied ones -- a handful of cp.async per lane instead of one per pixel.
+                uint16_t *const cur = s_occ + (warp * 2 + (n_tiles_done & 1)) * occ_cap;
+                const uint16_t *const prev = s_occ + (warp * 2 + ((n_tiles_done & 1) ^ 1)) * occ_cap;
+                int n_cur = 0;
+                for (int e0 = 0; e0 < ((p.stage_rows + 15) >> 4) * 4; e0 += 32) {
+                    const int e = e0 + lane;
+                    const int px = (e >> 2) * 16 + warp * 4 + (e & 3);
+                    const bool occ = px < p.stage_rows && s_src[px] >= 0;
+                    const unsigned m = __ballot_sync(0xffffffffu, occ);
+                    if (occ) cur[n_cur + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(px);
+                    n_cur += __popc(m);
+                }
+                __syncwarp();
+                for (int cb = 0; cb < cbn; ++cb, ++ia) {
+                    const int sa = ia % SA;
+                    if (ia >= SA && !mbar_wait(a_empty + 8u * sa, ((ia / SA) - 1) & 1u, s_abort)) {
+                        ok = false;
+                        break;
+                    }
+                    const uint32_t stage = a0 + sa * a_bytes;
+                    // (with one stage the second channel block of a tile set finds its own pixels there: nothing to undo)
+                    for (int e = lane; e < ((SA == 1 && cb > 0) ? 0 : n_prev * 8); e += 32) {
+                        const int px = prev[e >> 3], c8 = e & 7;
+                        if (s_src[px] < 0)  // (a pixel occupied again is overwritten whole by the copy below)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(stage + px * 128u + ((c8 ^ (px & 7)) << 4)), "r"(0) : "memory");
+                    }
+                    for (int e = lane; e < n_cur * 8; e += 32) {
+                        const int px = cur[e >> 3], c8 = e & 7;
+                        cp_async16_zfill(stage + px * 128u + ((c8 ^ (px & 7)) << 4),
+                                         p.rows + static_cast<size_t>(s_src[px]) * p.c_in + cb * 32 + c8 * 4, true);
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    fence_async_smem();
+                    mbar_arrive(a_full + 8u * sa);
+                }
+                n_prev = n_cur;
+                ++n_tiles_done;
+                continue;
+            }
             for (int cb = 0; cb < cbn; ++cb, ++ia) {
                 const int sa = ia % SA;
                 if (ia >= SA && !mbar_wait(a_empty + 8u * sa, ((ia / SA) - 1) & 1u, s_abort)) {
@@ -472,8 +525,10 @@ template <int N, int T, int SA, int SB, int NB, int MW, int MB = 1>
 cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
 {
     const size_t a_bytes = (static_cast<size_t>(p.stage_rows) * 128 + 1023) & ~static_cast<size_t>(1023);
-    const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 4 * 4096 + 1024;
-    if (smem > 222 * 1024) return cudaErrorInvalidValue;
+    const size_t occ_cap = ((static_cast<size_t>(p.stage_rows) + 15) / 16) * 4 + 8;
+    const size_t smem = SA * a_bytes + static_cast<size_t>(SB) * N * 128 + 4 * 4096 + 1024 +
+                        4 * ((static_cast<size_t>(p.stage_rows) + 15) & ~static_cast<size_t>(15)) + (p.rows ? 16 * occ_cap : 0) + 64;
+    if (smem > 225 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_conv_umma<N, T, SA, SB, NB, MW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int tiles = p.nb * p.tiles_x * p.tiles_y;
@@ -537,7 +592,7 @@ cudaError_t launch_conv_umma(const ConvJob &j, cudaStream_t st)
     int T;
     if (n_eff > 256) return cudaErrorInvalidValue;
     if (j.stride == 1) T = n_eff == 64 ? 4 : n_eff == 128 ? 2 : 1;
-    else T = 1;
+    else T = 1;  // (two patches on ONE halo stage measured slower on the gathered first layer: 0.43 vs 0.38 ms)
     while (T > 1 && kPatchH * (T / 2) >= p.h_out) T /= 2;  // small images: do not pad the patch stack past the image
     if (j.stride == 1) {
         p.pitch = kPatchW + j.k - 1;

@@ -10,6 +10,13 @@ bn = torch.nn.BatchNorm2d(c_out, eps=1e-3)
 l = B._Layer(conv, bn.eval(), False); l.prepare(dev)
 nb = 16
 x = torch.rand((nb, h, w, c_in), device=dev)
+gather = len(sys.argv) > 7 and sys.argv[7] == "gather"
+if gather:  # 5 % occupied cells, given as pillar rows + index map
+    occ = torch.rand((nb, h, w), device=dev) < 0.05
+    idx = torch.full((nb, h, w), -1, dtype=torch.int32, device=dev)
+    n_occ = int(occ.sum())
+    idx[occ] = torch.arange(n_occ, dtype=torch.int32, device=dev)
+    rows_t = torch.rand((n_occ, c_in), device=dev)
 oh, ow = B.BaseBEVBackbone._out_hw(h, w, l.desc)
 y = torch.empty((nb, oh, ow, c_out), device=dev)
 lib = _native.load()
@@ -21,7 +28,10 @@ rows = []
 for rep in range(6):
     buf = torch.zeros(32, dtype=torch.int64, device=dev)
     lib.pillars_set_debug_times(buf.data_ptr())
-    B.conv_forward(l, y, c_out, 0, False, nb, h, w, x_nhwc=x)
+    if gather:
+        B.conv_forward(l, y, c_out, 0, False, nb, h, w, rows=rows_t, cell_row=idx)
+    else:
+        B.conv_forward(l, y, c_out, 0, False, nb, h, w, x_nhwc=x)
     torch.cuda.synchronize()
     lib.pillars_set_debug_times(None)
     v = buf.cpu().numpy()
