@@ -407,17 +407,7 @@ int grid_for(int64_t groups, int sms_x)
     return static_cast<int>(blocks);
 }
 
-int num_sms()
-{
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int num_sms() { return current_sm_count(); }  // per device (a process may drive more than one)
 
 template <int C>
 cudaError_t dispatch_features(const FeatParams &p, bool abs_xyz, bool dist, int grid, cudaStream_t st)

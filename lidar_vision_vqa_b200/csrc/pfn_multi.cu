@@ -737,17 +737,7 @@ __global__ void __launch_bounds__(256) k_apply_ranks(uint32_t *__restrict__ occ,
     }
 }
 
-int num_sms()
-{
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int num_sms() { return current_sm_count(); }  // per device (a process may drive more than one)
 
 void fill_layout(MultiParams &p, const StackDev &sd, int c_point)
 {

@@ -530,11 +530,10 @@ cudaError_t launch_bev_tokens_umma(const TokenizerDev &tk, const float *feats, c
     up.dw_w = tk.dw_w; up.dw_b = tk.dw_b; up.pb = tk.pb; up.gamma = tk.gamma; up.beta = tk.beta; up.eps = tk.eps; up.pe = tk.pe;
     up.wimg = reinterpret_cast<const uint4 *>(tk.wimg); up.list = list; up.count = count; up.out = out;
     const size_t smem = umma_smem_bytes(tk.c, tk.d) + 1024;  // slack for the 1024-byte alignment of the tiles
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // (function attributes are per device and a process may drive more than one: set every time, it is cheap)
+    const int sms = current_sm_count();
+    {
+        cudaError_t e;
         if ((e = cudaFuncSetAttribute(k_tok_umma<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_tok_umma<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(k_tok_umma<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
