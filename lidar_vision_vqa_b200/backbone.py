@@ -164,6 +164,21 @@ class BaseBEVBackbone(nn.Module):
             return d["up"] * h, d["up"] * w
         return (h + 2 * d["pad"] - d["k"]) // d["stride"] + 1, (w + 2 * d["pad"] - d["k"]) // d["stride"] + 1
 
+    def output_shape(self, h: int, w: int):
+        """(channels, height, width) of ``spatial_features_2d`` for an ``h x w`` input canvas."""
+        if self._plan is None:
+            self._build_plan()
+        blocks, de = self._plan
+        shapes = []
+        for layers in blocks:
+            for l in layers:
+                h, w = self._out_hw(h, w, l.desc)
+            shapes.append((h, w))
+        if de:
+            oh, ow = self._out_hw(*shapes[0], de[0].desc)
+            return sum(l.desc["c_out"] for l in de), oh, ow
+        return blocks[0][-1].desc["c_out"], shapes[0][0], shapes[0][1]
+
     def forward(self, data_dict):
         if self.training:
             raise NotImplementedError("BaseBEVBackbone (B200) is an inference path: call .eval(); training runs the reference module")

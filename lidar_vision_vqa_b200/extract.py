@@ -8,9 +8,10 @@ strictly serial, one ``cuda.synchronize`` per batch.  Here raw sweeps go in and 
 host->device copy of batch k+1, the kernels of batch k and the device->host copy of batch k-1 in flight at the same time;
 the float32 -> float16 conversion happens inside the scatter kernel (the canvas is written once, in its final dtype).
 
-What is tapped: ``spatial_features`` -- the tensor the reference's hook falls back to for a model without a 2-D backbone
-(:254: ``spatial_features_2d`` > ``encoded_spconv_tensor`` > ``spatial_features``).  ``BaseBEVBackbone`` (dense convolutions,
-cuDNN territory) is outside this path.
+What is tapped follows the reference's hook priority (:254: ``spatial_features_2d`` > ``encoded_spconv_tensor`` >
+``spatial_features``): with a ``backbone`` (``ship='features2d'``) the extractor saves ``spatial_features_2d`` -- what the
+product stores for a pillar model with a ``BACKBONE_2D`` -- computed by :class:`backbone.BaseBEVBackbone` straight from the
+pillar rows (the canvas is never materialised); without one it saves ``spatial_features``.
 
     ex = BevExtractor(vfe, batch_size=16, max_points_per_frame=40_000)
     for token, bev in ex.run(iter_of_(token, points[N, C])):      # bev: np.float16 [C, H, W]
@@ -31,13 +32,17 @@ from .pipeline import PillarEncoderPipeline
 
 class BevExtractor:
     def __init__(self, vfe: PillarVFEFromPoints, batch_size: int, max_points_per_frame: int, depth: int = 3,
-                 out_dtype: torch.dtype = torch.float16, ship: str = "dense"):
+                 out_dtype: torch.dtype = torch.float16, ship: str = "dense", backbone=None):
         """``ship='dense'``: the float16 canvas crosses the host link (32 MiB per 512^2 frame), which is what the reference
         stores.  ``ship='compact'``: only the occupied cells cross it -- float16 pillar rows ``[M, F]`` + int16 ``(y, x)``
         ``[M, 2]`` per frame (~1.8 MB per frame at cfg2) -- and ``run`` yields ``(token, (rows, yx))``;
-        :func:`densify_compact` rebuilds the identical canvas on the consumer's side."""
-        if ship not in ("dense", "compact"):
-            raise ValueError("ship must be 'dense' or 'compact'")
+        :func:`densify_compact` rebuilds the identical canvas on the consumer's side.  ``ship='features2d'`` (needs
+        ``backbone``, an eval-mode ``BaseBEVBackbone`` on the same device): ``run`` yields the float16
+        ``spatial_features_2d [C2, H2, W2]`` of each frame (12 MiB per frame for the nuScenes pillar model)."""
+        if ship not in ("dense", "compact", "features2d"):
+            raise ValueError("ship must be 'dense', 'compact' or 'features2d'")
+        if (ship == "features2d") != (backbone is not None):
+            raise ValueError("ship='features2d' and backbone= go together")
         self.ship = ship
         self.vfe = vfe
         self.batch_size = int(batch_size)
@@ -45,15 +50,18 @@ class BevExtractor:
         self.c = vfe.num_raw_point_features
         self.max_points = int(max_points_per_frame) * self.batch_size
         self.pipe = PillarEncoderPipeline(vfe, n_frames=self.batch_size, max_points=self.max_points, depth=self.depth,
-                                          bev_dtype=out_dtype, with_bev=ship == "dense")
+                                          bev_dtype=out_dtype, with_bev=ship == "dense", backbone=backbone)
         self.d2h_bytes_last = 0
         # pinned staging: collated points in, canvases out (one pair per pipeline slot)
         self._pts = [torch.empty((self.max_points, self.c + 1), dtype=torch.float32).pin_memory()
                      for _ in range(self.depth)]
         nx, ny, nz = vfe.grid.grid_size
         f = vfe.get_output_feature_dim()
-        self._bev = self._rows = self._yx = None
-        if ship == "dense":
+        self._bev = self._rows = self._yx = self._f2d = None
+        if ship == "features2d":
+            c2, h2, w2 = backbone.output_shape(ny, nx)
+            self._f2d = [torch.empty((self.batch_size, c2, h2, w2), dtype=torch.float16).pin_memory() for _ in range(self.depth)]
+        elif ship == "dense":
             self._bev = [torch.empty((self.batch_size, f * nz, ny, nx), dtype=out_dtype).pin_memory()
                          for _ in range(self.depth)]
         else:
@@ -81,7 +89,8 @@ class BevExtractor:
 
     def run(self, items: Iterable[Tuple[str, np.ndarray]]) -> Iterator[Tuple[str, np.ndarray]]:
         """Yields ``(token, bev)`` in input order; ``bev`` is a numpy view into a pinned buffer that stays valid until
-        ``depth - 1`` further batches have been yielded (copy it to keep it longer)."""
+        ``depth - 2`` further batches have been yielded (the buffer is refilled as soon as its slot is submitted again: copy
+        the array to keep it longer; ``run_to_dir`` writes it out at once)."""
         pending: List[Tuple[int, List[str], int]] = []  # (ticket, tokens, slot)
         batch_tokens: List[str] = []
         batch_frames: List[np.ndarray] = []
@@ -91,13 +100,11 @@ class BevExtractor:
             ticket, tokens, s = pending.pop(0)
             res = self.pipe.result(ticket)
             stream = self.pipe.slots[ticket % len(self.pipe.slots)].stream
-            if self.ship == "dense":
-                with torch.cuda.stream(stream):
-                    self._bev[s].copy_(res["spatial_features"], non_blocking=True)
-                    self._copied[s].record()
+            if self.ship in ("features2d", "dense"):  # the device->host copy was enqueued right behind the kernels (flush)
                 self._copied[s].synchronize()
-                self.d2h_bytes_last = self._bev[s].numel() * self._bev[s].element_size()
-                arr = self._bev[s].numpy()
+                buf = self._f2d[s] if self.ship == "features2d" else self._bev[s]
+                self.d2h_bytes_last = buf.numel() * buf.element_size()
+                arr = buf.numpy()
                 for i, tok in enumerate(tokens):
                     yield tok, arr[i]
                 return
@@ -119,7 +126,18 @@ class BevExtractor:
         def flush():
             nonlocal slot, batch_tokens, batch_frames
             pts = self._collate(batch_frames, slot)
-            pending.append((self.pipe.submit(pts), batch_tokens, slot))
+            ticket = self.pipe.submit(pts)
+            pslot = self.pipe.slots[ticket % len(self.pipe.slots)]
+            if self.ship in ("features2d", "dense"):
+                # what crosses the link does not depend on the pillar counts: copy it out on the batch's own stream, so the
+                # transfer of batch k runs under the kernels of batch k + 1 (the cast is a plain dtype conversion)
+                with torch.cuda.stream(pslot.stream):
+                    if self.ship == "features2d":
+                        self._f2d[slot].copy_(pslot.features_2d.to(torch.float16), non_blocking=True)
+                    else:
+                        self._bev[slot].copy_(pslot.buffers.bev, non_blocking=True)
+                    self._copied[slot].record()
+            pending.append((ticket, batch_tokens, slot))
             slot = (slot + 1) % self.depth
             batch_tokens, batch_frames = [], []
 

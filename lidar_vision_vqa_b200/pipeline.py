@@ -32,6 +32,7 @@ class _Slot:
                                          bev_dtype=bev_dtype, with_bev=with_bev)
         self.counts_host = torch.empty((n_frames + 1,), dtype=torch.int32).pin_memory()
         self.done = torch.cuda.Event()
+        self.features_2d = None
         self.n = 0
         self.ticket = -1
         self.busy = False
@@ -42,7 +43,9 @@ class PillarEncoderPipeline:
 
     def __init__(self, vfe: PillarVFEFromPoints, n_frames: int, max_points: int, depth: int = 2,
                  pillar_capacity: Optional[int] = None, scatter_variant: str = "auto",
-                 bev_dtype: torch.dtype = torch.float32, with_bev: bool = True):
+                 bev_dtype: torch.dtype = torch.float32, with_bev: bool = True, backbone=None):
+        """``backbone``: an eval-mode :class:`backbone.BaseBEVBackbone` run right after the encoder on the same stream, fed the
+        pillar rows through the BEV index map (no canvas unless ``with_bev``); results then carry ``spatial_features_2d``."""
         dev = next(vfe.parameters()).device
         if dev.type != "cuda":
             raise ops.NativeLibraryError("PillarEncoderPipeline needs the module on a CUDA device")
@@ -55,6 +58,9 @@ class PillarEncoderPipeline:
         self.scatter_variant = scatter_variant
         f_out = int(self.pfn.weight.shape[0])
         self.with_bev = bool(with_bev)
+        self.backbone = backbone
+        if backbone is not None and backbone.training:
+            raise ValueError("the backbone must be in eval mode")
         self.slots: List[_Slot] = [_Slot(self.n_frames, max_points, self.row, self.grid, f_out, dev, pillar_capacity,
                                          bev_dtype, self.with_bev) for _ in range(max(1, depth))]
         self._next = 0
@@ -83,8 +89,13 @@ class PillarEncoderPipeline:
                 offs.copy_(frame_offsets_host, non_blocking=True)
             else:
                 offs = ops.frame_offsets_from_points(dst, self.n_frames)
-            ops.encode_bev(dst, offs, self.grid, self.pfn, col0=0 if packed else 1, buffers=slot.buffers,
-                           with_bev=self.with_bev, scatter_variant=self.scatter_variant)
+            res = ops.encode_bev(dst, offs, self.grid, self.pfn, col0=0 if packed else 1, buffers=slot.buffers,
+                                 with_bev=self.with_bev, scatter_variant=self.scatter_variant,
+                                 want_index_map=self.backbone is not None)
+            if self.backbone is not None:
+                with torch.inference_mode():
+                    slot.features_2d = self.backbone({"pillar_features": res["pillar_features"],
+                                                      "bev_index_map": res["cell_row"]})["spatial_features_2d"]
             slot.counts_host.copy_(slot.buffers.pillar_count, non_blocking=True)
             slot.done.record(slot.stream)
         slot.n = n
@@ -103,5 +114,8 @@ class PillarEncoderPipeline:
         b = slot.buffers
         if m > b.capacity:
             raise RuntimeError("pillar capacity overflow")
-        return {"spatial_features": b.bev, "pillar_features": b.pillar_features[:m], "voxel_coords": b.voxel_coords[:m],
-                "voxel_num_points": b.voxel_num_points[:m], "pillars_per_frame": slot.counts_host[:-1].clone()}
+        out = {"spatial_features": b.bev, "pillar_features": b.pillar_features[:m], "voxel_coords": b.voxel_coords[:m],
+               "voxel_num_points": b.voxel_num_points[:m], "pillars_per_frame": slot.counts_host[:-1].clone()}
+        if self.backbone is not None:
+            out["spatial_features_2d"] = slot.features_2d
+        return out

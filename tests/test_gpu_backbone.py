@@ -280,3 +280,35 @@ def test_backbone_against_committed_reference_goldens(name):
     scale = float(np.abs(want).max())
     assert float(np.abs(got - want).max()) <= 1e-2 * scale
     assert float((np.abs(got - want) <= 2e-3 * scale).mean()) > 0.99
+
+
+def test_extractor_ships_spatial_features_2d():
+    """BevExtractor(ship='features2d'): per-token float16 [384, H/4, W/4] maps == float16 of BaseBEVBackbone run on the canvas of
+    the same frame alone (frames are independent: batching and pipelining change nothing)."""
+    from lidar_vision_vqa_b200 import synth
+    from lidar_vision_vqa_b200.backbone import BaseBEVBackbone
+    from lidar_vision_vqa_b200.extract import BevExtractor
+    from lidar_vision_vqa_b200.modules import PillarVFEFromPoints
+
+    dev = _dev()
+    rng, vs = [-25.6, -25.6, -5.0, 25.6, 25.6, 3.0], [0.2, 0.2, 8.0]
+    frames = [synth.make_sweep(700 + i, synth.NUSCENES_32, 5)[:7000 + 300 * i] for i in range(5)]
+    base = dict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64], MAX_POINTS_PER_VOXEL=32,
+                MAX_NUMBER_OF_VOXELS=20000)
+    torch.manual_seed(1)
+    vfe = PillarVFEFromPoints(dict(base), 5, vs, rng, [256, 256, 1]).eval().to(dev)
+    vfe_c = PillarVFEFromPoints(dict(base, FUSE_SCATTER=True), 5, vs, rng, [256, 256, 1]).eval().to(dev)
+    vfe_c.load_state_dict(vfe.state_dict())
+    bb = BaseBEVBackbone(BACKBONE_CASES["nuscenes_multihead"], 64).eval().to(dev)
+    _randomise_bn(bb, 4)
+    ex = BevExtractor(vfe, batch_size=2, max_points_per_frame=9000, depth=2, ship="features2d", backbone=bb)
+    items = [(f"t{i}", f) for i, f in enumerate(frames)]
+    got = {tok: np.array(arr) for tok, arr in ex.run(items)}
+    assert list(got) == [t for t, _ in items]
+    for tok, f in items:
+        pts = torch.from_numpy(np.concatenate([np.zeros((len(f), 1), np.float32), f], axis=1)).to(dev)
+        with torch.inference_mode():
+            canvas = vfe_c({"points": pts, "batch_size": 1})["spatial_features"]
+            want = bb({"spatial_features": canvas})["spatial_features_2d"][0].to(torch.float16).cpu().numpy()
+        assert got[tok].dtype == np.float16 and got[tok].shape == (384, 64, 64)
+        np.testing.assert_array_equal(got[tok].view(np.uint16), want.view(np.uint16))
