@@ -761,6 +761,10 @@ int pillars_conv_forward(const pillars_conv_t *cv, const void *image, const floa
     if (!image || !bn_shift || !out) return fail(PILLARS_E_BADARG, "NULL image / shift / out");
     if (!in_nhwc && !(rows && cell_row)) return fail(PILLARS_E_BADARG, "neither a dense input nor (rows, cell_row)");
     if (n_frames < 0 || h_in < 1 || w_in < 1) return fail(PILLARS_E_BADARG, "bad image shape");
+    if (static_cast<int64_t>(n_frames) * h_in * w_in >= (1ll << 31)) return fail(PILLARS_E_UNSUPPORTED, "more than 2^31 input pixels");
+    const auto misaligned = [](const void *q) { return q && reinterpret_cast<uintptr_t>(q) % 16 != 0; };
+    if (misaligned(image) || misaligned(in_nhwc) || misaligned(rows) || misaligned(out))
+        return fail(PILLARS_E_BADARG, "image / activations / rows / out must be 16-byte aligned");
     if (out_c_off < 0 || out_c_off + cv->c_out > out_c_total || (out_nchw == 0 && (out_c_total % 4 != 0 || out_c_off % 4 != 0)))
         return fail(PILLARS_E_BADARG, "bad output channel window");
     g_launches = 0;
