@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--no-backbone", action="store_true", help="skip the BaseBEVBackbone (f-3) measurement")
     ap.add_argument("--gather-dtype", default="float32", choices=["float32", "float16"],
                     help="dtype of the feature rows on the wire in the multi-GPU gather")
-    ap.add_argument("--cfg5-mode", default="fusion", choices=["fusion", "sharded"],
+    ap.add_argument("--cfg5-mode", default="fusion", choices=["fusion", "sharded", "backbone"],
                     help="cfg5: tokenise on the fusion rank after the gather, or on every rank (frames stay independent)")
     return ap.parse_args()
 
@@ -1167,6 +1167,91 @@ def backbone_numbers(args, wl, K):
     return out
 
 
+def run_cfg5_backbone(args, rank, world, dev, wl, nb, total_frames, d_tok, K, R, peak, peak_src):
+    """cfg5 the way the product's pillar model feeds VATLiDAR: every rank turns its sweeps into `spatial_features_2d`
+    (encoder -> BaseBEVBackbone, no canvas) and tokenises THAT map (384 x 128^2 per frame instead of 64 x 512^2: 16x fewer
+    tokens, SURVEY 8 f-3 "needed to make cfg5 tractable").  Frames stay independent up to VATLiDAR's queries, so nothing is
+    exchanged between ranks (weak point of the fusion mode: one rank tokenises everything)."""
+    import torch.distributed as dist
+
+    from lidar_vision_vqa_b200 import ops
+    from lidar_vision_vqa_b200 import tokens as T
+    from lidar_vision_vqa_b200.backbone import BaseBEVBackbone
+    from oracle import tokens_oracle as tor  # random weights only
+
+    torch.manual_seed(0)
+    bb = BaseBEVBackbone(BACKBONE_CFG, F_OUT).eval().to(dev)
+    c2, h2, w2 = bb.output_shape(wl.ny, wl.nx)
+    tk = T.VATLiDARTokenizer(c2, d_tok)
+    tk.load_state_dict({k: torch.from_numpy(v) for k, v in tor.random_token_params(c2, d_tok, seed=11).items()})
+    tk = tk.eval().to(dev)
+    tk.tables(h2, w2)
+    buf = ops.EncodeBuffers(wl.n_max, nb, wl.grid, F_OUT, dev, with_bev=False)
+    tok_out = torch.empty((nb, h2 * w2, d_tok), dtype=torch.float32, device=dev)
+    checksum = torch.zeros(1, dtype=torch.float64, device=dev)
+    K5 = max(2, min(K, 6))
+
+    def step(k):
+        p, o = wl.dev_batches[k % wl.rot]
+        r = ops.encode_bev(p, o, wl.grid, wl.pfn, buffers=buf, with_bev=False, want_index_map=True)
+        f2d = bb({"pillar_features": r["pillar_features"], "bev_index_map": r["cell_row"]})["spatial_features_2d"]
+        tk(f2d, out=tok_out)
+        checksum.add_(tok_out[:, ::1021, :].double().sum())
+        return f2d
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def region():
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s.record()
+        with torch.inference_mode():
+            for k in range(K5):
+                step(k)
+        e.record()
+        barrier()
+        return s.elapsed_time(e)
+
+    region()
+    ms_all = timed_regions(region, max(3, min(R, 5)), world, dev)
+    ms = statistics.median(ms_all) / K5
+    # stage split on this rank (serial, one step)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.inference_mode():
+        p, o = wl.dev_batches[0]
+        ev[0].record()
+        r = ops.encode_bev(p, o, wl.grid, wl.pfn, buffers=buf, with_bev=False, want_index_map=True)
+        ev[1].record()
+        f2d = bb({"pillar_features": r["pillar_features"], "bev_index_map": r["cell_row"]})["spatial_features_2d"]
+        ev[2].record()
+        tk(f2d, out=tok_out)
+        ev[3].record()
+    torch.cuda.synchronize()
+    if rank == 0:
+        tokens_bytes = total_frames * h2 * w2 * d_tok * 4
+        line = {
+            "metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K5, "warmup": 1,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (backbone: tf32 tensor cores)",
+            "data": "synthetic", "repeats": len(ms_all),
+            "config": {"workload": CFG5, "global_frames": total_frames, "frames_per_gpu": nb, "grid": [wl.nx, wl.ny, 1],
+                       "d_model": d_tok, "mode": "backbone", "features_2d": [c2, h2, w2],
+                       "parallelism": f"dp{world}: encoder, BaseBEVBackbone and tokeniser all sharded by frames (no exchange: frames "
+                                      "are independent up to VATLiDAR's queries)",
+                       "decision": f"tokens are built from spatial_features_2d ({c2} x {h2} x {w2}), the map the product stores for a "
+                                   f"pillar model: {total_frames * h2 * w2 / 1e6:.1f} M tokens = {tokens_bytes / 1e9:.1f} GB at d = {d_tok} "
+                                   "for the whole batch, against 67 M tokens / 68.7 GB from the raw 512^2 canvas"},
+            "stages": {"encode_ms": ev[0].elapsed_time(ev[1]), "backbone_ms": ev[1].elapsed_time(ev[2]),
+                       "tokenise_ms": ev[2].elapsed_time(ev[3]), "frames_per_rank_step": nb,
+                       "backbone_tflops": backbone_flops(BACKBONE_CFG, F_OUT, wl.ny, wl.nx, nb) / (ev[1].elapsed_time(ev[2]) * 1e-3) / 1e12},
+            "tokens_checksum": float(checksum.item()),
+            "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": None,
+        }
+        print(json.dumps(line), flush=True)
+
+
 def run_cfg5(args, rank, world, dev, lib, K, R, peak, peak_src):
     """BASELINE.json configs[4]: 256 sweeps sharded over the ranks, BEV tokens handed to the fusion rank and turned into the
     K/V tokens of VATLiDAR's cross-attention (src/encoder-decoder/training/core/trainer.py:581 feeds VATLiDAR,
@@ -1181,6 +1266,8 @@ def run_cfg5(args, rank, world, dev, lib, K, R, peak, peak_src):
     nb = total_frames // world
     wl = Workload(DEFAULT_WORKLOAD, rank, dev, rotate=2, nb_override=nb)
     d_tok = args.tokens_d_model
+    if args.cfg5_mode == "backbone":
+        return run_cfg5_backbone(args, rank, world, dev, wl, nb, total_frames, d_tok, K, R, peak, peak_src)
     tk = T.VATLiDARTokenizer(F_OUT, d_tok)
     tk.load_state_dict({k: torch.from_numpy(v) for k, v in tor.random_token_params(F_OUT, d_tok, seed=11).items()})
     tk = tk.eval().to(dev)
