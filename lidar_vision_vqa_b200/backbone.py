@@ -56,7 +56,13 @@ class _Layer:
 
     def prepare(self, device: torch.device) -> None:
         params = (self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
-        key = tuple((t.data_ptr(), t._version) for t in params) + (str(device),)
+        def version(t):  # inference tensors (a module moved under torch.inference_mode) do not track one
+            try:
+                return t._version
+            except RuntimeError:
+                return -1
+
+        key = tuple((t.data_ptr(), version(t)) for t in params) + (str(device),)
         if key == self._key:
             return
         lib = _native.load()

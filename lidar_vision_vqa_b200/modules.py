@@ -40,6 +40,15 @@ def _cfg_get(cfg, key, default=_MISSING):
     return default
 
 
+def _tensor_version(t: torch.Tensor) -> int:
+    """In-place modification counter, or -1 for inference tensors (a module moved under ``torch.inference_mode``), which do
+    not track one."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 def _dtype_of(name) -> torch.dtype:
     if isinstance(name, torch.dtype):
         return name
@@ -146,7 +155,7 @@ class _PillarVFEBase(VFETemplate):
         """The single-layer form consumed by the streaming / dense kernels."""
         self._check_eval()
         layer = self.pfn_layers[0]
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in self._layer_tensors())
+        key = (str(device),) + tuple((t.data_ptr(), _tensor_version(t)) for t in self._layer_tensors())
         if self._folded is None or key != self._folded_key:
             bn = None
             if self.use_norm:
@@ -164,7 +173,7 @@ class _PillarVFEBase(VFETemplate):
         self._check_eval()
         if len(self.pfn_layers) > 2:
             raise NotImplementedError("PFN stacks of more than two layers are not built (no reference config uses one)")
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in self._layer_tensors())
+        key = (str(device),) + tuple((t.data_ptr(), _tensor_version(t)) for t in self._layer_tensors())
         if self._stack_folded is None or key != self._stack_key:
             layers = []
             for layer in self.pfn_layers:
