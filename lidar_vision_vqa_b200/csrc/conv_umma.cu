@@ -53,6 +53,12 @@ __device__ __forceinline__ void umma_commit(uint32_t mbar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -159,7 +165,10 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     __shared__ float s_shift[N];
     volatile uint32_t *const s_abort = &s_abort_word;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // (the shuffle tells the compiler that the role branches below are warp-uniform: the MMA warp then runs converged and its
+    // tcgen05 instructions are issued under one elected lane instead of a per-instruction election loop)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) tl_stamp(p, 0);  // CTA start
     uint8_t *const s_al = s_raw + ((1024u - (smem_u32(s_raw) & 1023u)) & 1023u);
     const uint32_t a_bytes = (static_cast<uint32_t>(p.stage_rows) * 128u + 1023u) & ~1023u;
@@ -332,7 +341,8 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
         // One thread issues; with MW == 2 a second warp's thread issues the other half of the patches (64-column MMAs last
         // ~34 cycles, about what one thread needs to issue one: the stage barriers then count two commits).
         const int mw = warp - 4;
-        if (lane == 0 && mw < MW) {
+        if (mw < MW) {  // the whole warp walks the loop (waits included); one elected lane issues
+            const bool leader = elect_one();
             const uint32_t idesc = umma_idesc_tf32(N);
             const uint32_t sbo = static_cast<uint32_t>(p.pitch) * 128u;
             const uint32_t tile_step = static_cast<uint32_t>(kPatchH * p.pitch) * 128u;
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                 for (int cb = 0; cb < cbn && ok; ++cb, ++ia) {
                     const int sa = ia % SA;
                     ok = mbar_wait(a_full + 8u * sa, (ia / SA) & 1u, s_abort);
-                    if (ia < 8 && mw == 0) tl_stamp(p, 16 + ia);  // MMA thread: halo stage available
+                    if (ia < 8 && mw == 0 && lane == 0) tl_stamp(p, 16 + ia);  // MMA warp: halo stage available
                     const uint32_t stage = a0 + sa * a_bytes;
                     for (int tap = 0; tap < p.taps && ok; ++tap, ++ib) {
                         const int sb = ib % SB;
@@ -357,21 +367,24 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
                         tc_fence_after();
                         const uint64_t ad = umma_desc(stage + static_cast<uint32_t>(p.tap_off[tap]) * 128u, sbo);
                         const uint64_t bd = umma_desc(b0 + sb * b_bytes, 1024u);
+                        if (leader) {
 #pragma unroll
-                        for (int t = 0; t < T; ++t) {
-                            if (MW == 2 && (t & 1) != mw) continue;
+                            for (int t = 0; t < T; ++t) {
+                                if (MW == 2 && (t & 1) != mw) continue;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)  // (+2 in the address field = +32 bytes = the next 8 channels)
-                                umma_tf32(acc + static_cast<uint32_t>(t * N), ad + ((t * tile_step + k * 32u) >> 4), bd + 2u * k, idesc,
-                                          k == 0 ? accumulate : 1u);
+                                for (int k = 0; k < 4; ++k)  // (+2 in the address field = +32 bytes = the next 8 channels)
+                                    umma_tf32(acc + static_cast<uint32_t>(t * N), ad + ((t * tile_step + k * 32u) >> 4), bd + 2u * k, idesc,
+                                              k == 0 ? accumulate : 1u);
+                            }
+                            umma_commit(b_empty + 8u * sb);
                         }
                         accumulate = 1u;
-                        umma_commit(b_empty + 8u * sb);
+                        __syncwarp();
                     }
-                    umma_commit(a_empty + 8u * sa);
+                    if (leader) umma_commit(a_empty + 8u * sa);
                 }
-                umma_commit(acc_full + 8u * buf);
-                if (it == 0 && mw == 0) tl_stamp(p, 4);  // last MMA of the first tile set issued
+                if (leader) umma_commit(acc_full + 8u * buf);
+                if (it == 0 && mw == 0 && lane == 0) tl_stamp(p, 4);  // last MMA of the first tile set issued
             }
         }
     } else if (warp == 6) {
