@@ -112,6 +112,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
+// the same load without the wait, and the wait as a separate statement that "produces" the registers (so that no use of
+// them can be scheduled above it): the next chunk's load runs under this chunk's arithmetic and stores
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ float round_tf32(float x)
 {
     uint32_t r;
@@ -424,6 +448,57 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             int b, y0, x0;
             tile_origin(tile, b, y0, x0);
             const uint32_t lane_base = tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(buf) * acc_cols;
+            if (!p.out_nchw && !p.pair) {
+                // ---- the common case (NHWC between layers): chunks of 32 columns, the next chunk's tensor-memory load in flight
+                // while this one is shifted, clamped, rounded, transposed through shared memory (a thread owns one pixel, eight
+                // lanes then write one pixel's full 128-byte line) and stored; all addresses are increments of one base
+                constexpr int kChunks = T * (N / 32);  // even (N >= 64)
+                const int pl = lane >> 3, ch4 = (lane & 7) * 4;
+                const size_t row_stride = static_cast<size_t>(p.out_w) * p.out_c_total;
+                const bool col_ok0 = x0 + pl < p.w_out, col_ok1 = x0 + pl + 4 < p.w_out;
+                uint32_t va[32], vb[32];
+                const auto chunk = [&](uint32_t (&vr)[32], int ci) {
+                    const int t = ci / (N / 32), n0 = (ci - t * (N / 32)) * 32;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(vr[j]) + s_shift[n0 + j];
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (p.round_out) x = round_tf32(x);
+                        f[j] = x;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    __syncwarp();
+                    const int oyb = y0 + kPatchH * t + 4 * q;
+                    float *dst = p.out + (static_cast<size_t>(b) * p.out_h + oyb) * row_stride +
+                                 static_cast<size_t>(x0 + pl) * p.out_c_total + p.out_c_off + n0 + ch4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {  // pixel 4 i + pl of the warp's 32 = patch row 4 q + i / 2, column pl + 4 (i & 1)
+                        const int rr = 4 * i + pl;
+                        const float4 val = *reinterpret_cast<const float4 *>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+                        if (oyb + (i >> 1) < p.h_out && ((i & 1) ? col_ok1 : col_ok0))
+                            *reinterpret_cast<float4 *>(dst + (i >> 1) * row_stride + (i & 1) * 4 * p.out_c_total) = val;
+                    }
+                };
+                tmem_ld32_issue(lane_base, va);
+#pragma unroll 1
+                for (int ci = 0; ci < kChunks; ci += 2) {
+                    tmem_ld_wait(va);
+                    tmem_ld32_issue(lane_base + static_cast<uint32_t>((ci + 1) * 32), vb);
+                    chunk(va, ci);
+                    tmem_ld_wait(vb);
+                    if (ci + 2 < kChunks) tmem_ld32_issue(lane_base + static_cast<uint32_t>((ci + 2) * 32), va);
+                    chunk(vb, ci + 1);
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty + 8u * buf);
+                if (it == 0 && tid == 224) tl_stamp(p, 5);  // first epilogue done
+                continue;
+            }
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int oy = y0 + kPatchH * t + r, ox = x0 + c;
