@@ -312,3 +312,19 @@ def test_extractor_ships_spatial_features_2d():
             want = bb({"spatial_features": canvas})["spatial_features_2d"][0].to(torch.float16).cpu().numpy()
         assert got[tok].dtype == np.float16 and got[tok].shape == (384, 64, 64)
         np.testing.assert_array_equal(got[tok].view(np.uint16), want.view(np.uint16))
+
+
+@pytest.mark.parametrize("case", [(128, 128, 1, 1, 12, 64), (256, 128, 2, 2, 10, 40), (256, 128, 4, 4, 6, 33), (128, 64, 1, 1, 5, 96)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_wide_images_writing_nchw(case):
+    """1x1 / transposed layers writing an NCHW channel window on images wider than a few patches, ragged widths included."""
+    c_in, c_out, k, stride, h, w = case
+    conv = torch.nn.ConvTranspose2d(c_in, c_out, k, stride=stride, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(_int_tensor(tuple(conv.weight.shape), -3, 3, 41))
+    shift = _int_tensor((c_out,), -40, 40, 42)
+    x = _int_tensor((2, c_in, h, w), -4, 4, 43)
+    ref = _reference_layer(conv, shift, x)
+    got, _ = _run_layer(conv, shift, x, out_nchw=True, c_total=c_out + 64, c_off=32)
+    assert torch.equal(got[:, 32:32 + c_out], ref)
+    assert bool((got[:, :32] == -7.0).all()) and bool((got[:, 32 + c_out:] == -7.0).all())
