@@ -128,15 +128,17 @@ def test_conv_layer_nchw_channel_window_and_untouched_neighbours():
     assert bool((got[:, :128] == -7.0).all()) and bool((got[:, 256:] == -7.0).all())
 
 
-def test_first_layer_gathers_from_pillar_rows():
-    """Input given as (pillar rows, BEV index map): 5 % of the cells occupied, rows in random order."""
-    conv = torch.nn.Conv2d(64, 64, 3, stride=2, padding=0, bias=False)
+@pytest.mark.parametrize("stride,c_out", [(2, 64), (1, 64), (1, 128), (2, 128)])
+def test_first_layer_gathers_from_pillar_rows(stride, c_out):
+    """Input given as (pillar rows, BEV index map): 5 % of the cells occupied, rows in random order; several tile sets per CTA
+    would need > 148 tiles, so the image is tall: the sparse loader's un-write of the previous tile set is exercised."""
+    conv = torch.nn.Conv2d(64, c_out, 3, stride=stride, padding=0, bias=False)
     with torch.no_grad():
         conv.weight.copy_(_int_tensor(tuple(conv.weight.shape), -3, 3, 31))
-    shift = _int_tensor((64,), -40, 40, 32)
-    x = _int_tensor((2, 64, 96, 64), -4, 4, 33)
+    shift = _int_tensor((c_out,), -40, 40, 32)
+    x = _int_tensor((6, 64, 320, 72), -4, 4, 33)
     g = torch.Generator().manual_seed(34)
-    keep = (torch.rand((2, 1, 96, 64), generator=g) < 0.05).float()
+    keep = (torch.rand((6, 1, 320, 72), generator=g) < 0.05).float()
     x = x * keep
     ref = _reference_layer(conv, shift, x)
     got, _ = _run_layer(conv, shift, x, gather=True)
@@ -158,6 +160,9 @@ BACKBONE_CASES = {
     # cbgs_pp_multihead.yaml:41-46 (the product's pillar config), layer counts as in the file
     "nuscenes_multihead": dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256],
                                UPSAMPLE_STRIDES=[0.5, 1, 2], NUM_UPSAMPLE_FILTERS=[128, 128, 128]),
+    # first block without down-sampling, plain convolutions in the branches (USE_CONV_FOR_NO_STRIDE)
+    "stride1_first": dict(LAYER_NUMS=[1, 1], LAYER_STRIDES=[1, 2], NUM_FILTERS=[64, 128], UPSAMPLE_STRIDES=[1, 2],
+                          NUM_UPSAMPLE_FILTERS=[64, 64], USE_CONV_FOR_NO_STRIDE=True),
     # kitti pointpillar.yaml: strides [2,2,2] / up-sampling [1,2,4]
     "kitti_pointpillar": dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256],
                               UPSAMPLE_STRIDES=[1, 2, 4], NUM_UPSAMPLE_FILTERS=[128, 128, 128]),
