@@ -1157,6 +1157,12 @@ def backbone_numbers(args, wl, K):
                 out["reference_eager_tf32_ms"] = timed(lambda i: ref({"spatial_features": canvas}))
                 torch.backends.cudnn.allow_tf32 = False
                 out["reference_eager_fp32_ms"] = timed(lambda i: ref({"spatial_features": canvas}))
+                # how far the reference's own TF32 deployment is from its fp32 arithmetic, and how far this kernel is
+                want32 = ref({"spatial_features": canvas})["spatial_features_2d"]
+                scale32 = float(want32.abs().max())
+                out["reference_tf32_vs_reference_fp32_err_over_scale"] = float((want - want32).abs().max()) / scale32
+                out["ours_vs_reference_fp32_err_over_scale"] = float((ours - want32).abs().max()) / scale32
+                del want32
                 torch.backends.cudnn.allow_tf32 = True
                 out["speedup_vs_reference_eager_tf32"] = out["reference_eager_tf32_ms"] / out["backbone_only_ms"]
                 del ref, want

@@ -7,7 +7,8 @@ Two kinds of checks:
   * the whole `BaseBEVBackbone` against the reference's own module (oracle/_ref copy, CPU fp32) with random weights.  The kernel
     multiplies in tf32 -- as the reference's nn.Conv2d itself does on this GPU under PyTorch's default
     `torch.backends.cudnn.allow_tf32 = True` -- so the tolerance is stated against the output's scale:
-    |err| <= 1e-2 * max|ref| over the 11 / 16 stacked layers (measured: ~1e-3).
+    |err| <= 4e-3 * max|ref| over the 11 / 16 stacked layers (measured: 1.0e-3 at 16 x 512^2, where the reference's own TF32
+    run deviates from its fp32 run by 0.8e-3: bench.py `backbone`).
 """
 import numpy as np
 import pytest
@@ -210,7 +211,7 @@ def test_backbone_matches_reference_module(name, fused_input):
     assert got.shape == want.shape
     scale = float(want.abs().max())
     err = float((got - want).abs().max())
-    assert err <= 1e-2 * scale, (err, scale)
+    assert err <= 4e-3 * scale, (err, scale)
     # and not merely small on average: the bulk of the elements agree to tf32 accuracy
     assert float(((got - want).abs() <= 2e-3 * scale).float().mean()) > 0.99
 
@@ -283,7 +284,7 @@ def test_backbone_against_committed_reference_goldens(name):
     got, want = out["spatial_features_2d"].cpu().numpy(), z["out"]
     assert got.shape == want.shape
     scale = float(np.abs(want).max())
-    assert float(np.abs(got - want).max()) <= 1e-2 * scale
+    assert float(np.abs(got - want).max()) <= 4e-3 * scale
     assert float((np.abs(got - want) <= 2e-3 * scale).mean()) > 0.99
 
 
