@@ -81,8 +81,9 @@ class _Layer:
         image = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
         _native.check(lib.pillars_conv_prepare(cv, w.data_ptr(), scale.data_ptr(), image.data_ptr(), stream), "pillars_conv_prepare")
+        # built once, then read by every later call on ANY stream (a pipeline runs each batch on its own): finish it here
+        torch.cuda.current_stream(device).synchronize()
         self.image, self.shift, self._key = image, shift, key
-        self._keep = (w, scale)  # alive until the stream has consumed them
 
 
 def conv_forward(layer: _Layer, out: torch.Tensor, out_c_total: int, out_c_off: int, out_nchw: bool, n_frames: int, h_in: int,

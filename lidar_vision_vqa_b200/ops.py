@@ -106,6 +106,8 @@ class PfnParams:
             folded = torch.empty(FOLDED_FLOATS, dtype=torch.float32, device=self.weight.device)
             nat = self.native()
             check(_native.load().pillars_fold_pfn(ctypes.byref(nat), folded.data_ptr(), _stream_ptr()), "pillars_fold_pfn")
+            # built once, then read by every later call on ANY stream: finish it here (one-time cost)
+            torch.cuda.current_stream(self.weight.device).synchronize()
             self.folded = folded
         return self
 

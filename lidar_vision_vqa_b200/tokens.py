@@ -139,6 +139,8 @@ class VATLiDARTokenizer(nn.Module):
                                                         pk["b2"].data_ptr(), pk["view"].data_ptr(), pe.data_ptr(),
                                                         bg.data_ptr(), None if umma is None else umma.data_ptr(),
                                                         ops._stream_ptr()), "pillars_tokens_prepare")
+            # computed once, then read by every later call on ANY stream: finish it here (one-time cost)
+            torch.cuda.current_stream(dev).synchronize()
             if umma is not None:
                 self._umma = umma
             self._tables[key] = (pe, bg)

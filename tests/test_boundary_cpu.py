@@ -231,3 +231,37 @@ def test_backbone_has_no_cpu_or_training_path():
         m({"spatial_features": torch.zeros(1, 64, 32, 32)})
     with pytest.raises(L.NativeLibraryError):
         m.eval()({"spatial_features": torch.zeros(1, 64, 32, 32)})
+
+
+def test_backbone_output_shape_and_flop_count_match_the_reference_module():
+    """`output_shape` against the reference module's actual output, `bench.backbone_flops` against a count over its layers."""
+    import importlib.util
+    import os
+
+    from oracle import ref_loader as R
+    from lidar_vision_vqa_b200 import BaseBEVBackbone
+
+    if not R.reference_available():
+        pytest.skip("reference tree / oracle/_ref copy not present")
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for cfg in BACKBONE_CFGS[:2]:
+        ref = R.load_bev_backbone()(R.AttrDict(cfg), 64).eval()
+        h, w, nb = 64, 48, 2
+        flops = []
+
+        def hook(mod, inp, out):
+            if isinstance(mod, torch.nn.Conv2d):
+                flops.append(2.0 * out.numel() * mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1])
+            else:  # ConvTranspose2d with kernel == stride: every input pixel feeds k*k outputs once
+                flops.append(2.0 * inp[0].numel() // mod.in_channels * mod.in_channels * mod.out_channels
+                             * mod.kernel_size[0] * mod.kernel_size[1])
+
+        hs = [m.register_forward_hook(hook) for m in ref.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d))]
+        with torch.inference_mode():
+            out = ref({"spatial_features": torch.zeros(nb, 64, h, w)})["spatial_features_2d"]
+        for x in hs:
+            x.remove()
+        assert BaseBEVBackbone(cfg, 64).output_shape(h, w) == tuple(out.shape[1:])
+        assert abs(bench.backbone_flops(cfg, 64, h, w, nb) - sum(flops)) <= 1e-6 * sum(flops)
