@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     if (tid == 0) tl_stamp(p, 1);  // set-up done
+    // Programmatic dependent launch: the next layer's CTAs may take an SM as soon as one of this grid's CTAs retires, and do
+    // their own set-up (tensor-memory allocation, barriers, the first weight copies: weights are not produced by a
+    // predecessor) while the tail of this grid is still working; whatever reads or writes activations waits below.
+    pdl_trigger();
 
     if (warp < 4) {
         // ================================ halo loaders ===========================================================================
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
         // (a stage's previous content must stem from this or the previous tile set: it is reused every SA channel blocks)
         const bool sparse = p.rows != nullptr && cbn >= SA;
         int n_prev = 0, n_tiles_done = 0;
+        pdl_wait();  // the activations / pillar rows / index map are the predecessor's output
         if (sparse) {  // every pixel row of every stage starts as zeros; only occupied cells are ever written
             for (uint32_t i = tid; i < (SA * a_bytes) >> 4; i += kLoaders)
                 asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a0 + (i << 4)), "r"(0) : "memory");
@@ -440,6 +445,7 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
         const int half = p.out_mul >> 1;  // phase = dy * half + g;  output column = ox * up + 2 g + {0, 1}
         uint8_t *const stg = s_stage + q * 4096;
         int it = 0;
+        pdl_wait();  // the output buffer may be memory an earlier layer is still reading
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it % NB;
             if (!mbar_wait(acc_full + 8u * buf, (it / NB) & 1u, s_abort)) break;
@@ -566,7 +572,10 @@ __global__ void __launch_bounds__(kConvThreads, MB) k_conv_umma(const __grid_con
             if (it == 0 && tid == 224) tl_stamp(p, 5);  // first epilogue done
         }
     }
-    if (*s_abort && tid == 0 && p.error) atomicExch(p.error, 0xC0DE0000u | static_cast<uint32_t>(blockIdx.x & 0xFFFF));
+    if (*s_abort && tid == 0 && p.error) {
+        pdl_wait();
+        atomicExch(p.error, 0xC0DE0000u | static_cast<uint32_t>(blockIdx.x & 0xFFFF));
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
@@ -622,9 +631,9 @@ cudaError_t launch_one(const ConvParams &p, int phases, cudaStream_t st)
     const int tiles = p.nb * p.tiles_x * p.tiles_y;
     const int ctas = current_sm_count() * MB;
     const dim3 grid(static_cast<unsigned>(tiles < ctas ? tiles : ctas), 1, static_cast<unsigned>(phases));
-    k_conv_umma<N, T, SA, SB, NB, MW, MB><<<grid, kConvThreads, smem, st>>>(p);
+    e = launch_pdl(k_conv_umma<N, T, SA, SB, NB, MW, MB>, grid, dim3(kConvThreads), smem, st, p);
     note_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace
