@@ -615,6 +615,8 @@ def run_b200(args, rank, world, local_rank):
             others[name] = {"value": s2["sweeps_per_s"], "unit": UNIT, "ms_per_step": s2["ms_per_step"],
                             "points_per_sec": s2["points_per_s"], "frames": w2.nb, "grid": [w2.nx, w2.ny, w2.nz],
                             "stages": {k: v for k, v in s2["stages"].items() if k != "timing"}, "steps": min(K, 10), "repeats": 5}
+            if name.startswith("cfg4"):
+                others[name]["pfn_64_64"] = two_layer_numbers(w2)
             del w2, e2
             torch.cuda.empty_cache()
 
@@ -1047,6 +1049,42 @@ def extractor_numbers(args, wl, K):
 
 BACKBONE_CFG = dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[64, 128, 256], UPSAMPLE_STRIDES=[0.5, 1, 2],
                     NUM_UPSAMPLE_FILTERS=[128, 128, 128])  # cbgs_pp_multihead.yaml:39-46, the product's pillar model
+
+
+def two_layer_numbers(wl):
+    """cfg4 with Waymo's own PFN, NUM_FILTERS [64, 64] (waymo_models/pointpillar_1x.yaml:34): the general feature kernel
+    (csrc/pfn_multi.cu, a coverage kernel) instead of the streaming one the benched line uses.  Serial, one stream."""
+    from lidar_vision_vqa_b200 import ops
+    from oracle import pillar_oracle as po  # weights generator only
+
+    sd = po.random_pfn_params(11, [64, 64], True, seed=0)
+    layers = []
+    for i in range(2):
+        layers.append((torch.as_tensor(sd[f"pfn_layers.{i}.linear.weight"]),
+                       tuple(torch.as_tensor(sd[f"pfn_layers.{i}.norm.{k}"]) for k in ("weight", "bias", "running_mean", "running_var"))
+                       + (1e-3,), None))
+    st = ops.fold_pfn_stack(layers, c_point=5, use_absolute_xyz=True, with_distance=False, voxel_size=wl.grid.voxel_size,
+                            point_cloud_range=wl.grid.point_cloud_range, device=wl.dev)
+    p, o = wl.dev_batches[0]
+    out = {}
+    for with_bev in (False, True):
+        for _ in range(3):
+            ops.encode_stack(p, o, wl.grid, st, with_bev=with_bev)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.encode_stack(p, o, wl.grid, st, with_bev=with_bev)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        out["with_canvas_ms" if with_bev else "group_and_features_ms"] = float(np.median(ts))
+        torch.cuda.empty_cache()
+    out["sweeps_per_s_serial"] = wl.nb / (out["with_canvas_ms"] * 1e-3)
+    out["what"] = ("pillars_encode_stack, serial on one stream (fresh canvas per call); the benched cfg4 line above uses NUM_FILTERS "
+                   "[64] on the streaming kernel")
+    return out
 
 
 def backbone_flops(cfg, c_in, h, w, nb):
