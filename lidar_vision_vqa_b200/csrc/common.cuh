@@ -87,6 +87,7 @@ struct Workspace {
     uint4 *pillar_meta;             // [n] per pillar, at its list start position: {x | y << 16, row (-1: dropped), n, z}
     uint4 *long_list;               // [2 * (n / 32 + 2)] pillars of more than 32 points: {list start, n, row, x | y << 16} {z, -, -, -}
     float *folded;                  // [PILLARS_FOLDED_FLOATS] folded PFN table when the caller did not prepare one
+    float *folded2;                 // [kFolded2Floats] layer 1 of a two-layer stack, folded
     uint32_t *scan_scratch;         // [B * ny * nx / 2048 + 2] block sums of the cell-rank scan (dynamic variant)
     uint32_t cap;                   // hash slots
     uint32_t n_tiles;
@@ -170,6 +171,7 @@ inline Workspace carve_workspace(void *base, int64_t n, int nb, int64_t cells_xy
     w.pillar_meta = reinterpret_cast<uint4 *>(take(sizeof(uint4) * (n + 64)));
     w.long_list = reinterpret_cast<uint4 *>(take(sizeof(uint4) * 2 * (n / 32 + 2)));
     w.folded = reinterpret_cast<float *>(take(sizeof(float) * PILLARS_FOLDED_FLOATS));
+    w.folded2 = reinterpret_cast<float *>(take(sizeof(float) * (2 * 32 * 64 + 64)));
     w.scan_scratch = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (static_cast<size_t>(nb) * cells_xy / 2048 + 2)));
     w.total_bytes = off;
     return w;
@@ -313,12 +315,15 @@ struct FastJob {
     int idx_bits;
     float *pillar_features;
     float vsz[3], off[3];  // pillar centre = coord * vsz + off (pillar_vfe.py:79-81,101-103)
+    const float *folded2;  // two-layer stack [64, 64]: launch_fold_pfn2's table, else NULL
 };
 // The streaming feature kernel (pfn_stream.cu) and the folding of one PFN layer into its table:
 //   rows 0-4   per point   scale * (W_p + W_cluster + W_centre) for x,y,z;  scale * W for intensity, time
 //   rows 5-10  per pillar  scale * W_p (x,y,z) applied to the centre;  -scale * W_cluster applied to (mean - centre)
 //   row  11    shift       row 12  relu(shift)
-cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st);
+cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st, int f_out = 64);
+constexpr int kFolded2Floats = 2 * 32 * 64 + 64;
+cudaError_t launch_fold_pfn2(const float *weight, const float *scale, const float *shift, float *folded2, cudaStream_t st);
 cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folded, const GridDev &gd, const Workspace &ws,
                                           cudaStream_t st);
 

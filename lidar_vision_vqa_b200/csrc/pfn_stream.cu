@@ -48,6 +48,10 @@ constexpr uint32_t kSumBytes = 3 * 32 * 4;
 constexpr uint32_t kOffPl = 2 * kBufBytes;
 constexpr uint32_t kOffSum = kOffPl + kPlBytes;
 constexpr uint32_t kWarpSmem = kOffSum + kSumBytes;     // 6528
+// two-layer stacks: layer 0's outputs of two points (or of the pillar-wise max), double buffered: 4 x [64] floats
+constexpr uint32_t kOffX = kWarpSmem;
+constexpr uint32_t kXBytes = 256;
+constexpr uint32_t kWarpSmemTwo = kOffX + 4 * kXBytes;  // 7552
 
 struct WalkParams {
     const PointRecord *records;   // grouped by pillar, x,y,z relative to the pillar centre (place kernel)
@@ -58,6 +62,7 @@ struct WalkParams {
     uint32_t *long_cursor;        // next entry to process - 1 (shared by all warps of the grid)
     const float *folded;          // [PILLARS_FOLDED_FLOATS], see launch_fold_pfn
     float *pillar_features;
+    const float *folded2;         // two-layer stacks: [32][64] per-point half of layer 1 | [32][64] pillar-max half | [64] shift
     GridDev gd;
     int sh_cells, sh_cells_xy, sh_nx;
     float vsz[3], off[3];
@@ -256,10 +261,95 @@ __device__ __forceinline__ LaneWeights load_lane_weights(const float *folded, in
     return w;
 }
 
+// ---- second layer of a [64, 64] stack (pillar_vfe.py:18-19,44-49: layer 1 sees [x_p, max over the pillar of x]) ------------
+struct Layer1 {
+    float2 wa[32];    // the lane's two output channels of scale1 * W1[:, k], per-point inputs k = 0..31
+    float2 sh, upad;  // shift1;  W1a . relu(shift0): the per-point half of the row that stands for the padded slots
+};
+__device__ __forceinline__ Layer1 load_layer1(const float *folded, const float *folded2, int lane)
+{
+    Layer1 l;
+    const float2 *f2 = reinterpret_cast<const float2 *>(folded2) + lane;
+    l.sh = __ldg(reinterpret_cast<const float2 *>(folded2 + 4096) + lane);
+    float2 u0 = make_float2(0.f, 0.f), u1 = u0;
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+        l.wa[k] = __ldg(f2 + k * 32);
+        l.wa[k + 1] = __ldg(f2 + (k + 1) * 32);
+        u0 = fma2s(l.wa[k], __ldg(folded + 12 * 64 + k), u0);
+        u1 = fma2s(l.wa[k + 1], __ldg(folded + 12 * 64 + k + 1), u1);
+    }
+    l.upad = add2(u0, u1);
+    return l;
+}
+__device__ __forceinline__ void sts2(uint32_t addr, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+// cst = shift1 + (scale1 W1[:, 32:]) . m  for the lane's two channels: m = 32 floats at shared address xs, weights [32][64]
+// (shared memory in the walk, global memory on the long-pillar path); four independent chains
+__device__ __forceinline__ float2 layer1_const(const float *w1b, uint32_t xs, float2 sh1, int lane)
+{
+    float2 y0 = sh1, y1 = make_float2(0.f, 0.f), y2 = y1, y3 = y1;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 mv = lds4(xs + k4 * 16u);
+        const float2 *wb = reinterpret_cast<const float2 *>(w1b + (4 * k4) * 64) + lane;
+        y0 = fma2s(wb[0], mv.x, y0);
+        y1 = fma2s(wb[32], mv.y, y1);
+        y2 = fma2s(wb[64], mv.z, y2);
+        y3 = fma2s(wb[96], mv.w, y3);
+    }
+    return add2(add2(y0, y1), add2(y2, y3));
+}
+// Layer 1 over the n staged points at shared address pa (32-byte records, NaN x = beyond the first-P cap), two points per
+// trip: x = relu(layer 0) of both goes through the warp's x buffers (double buffered: one __syncwarp per trip), then four
+// independent FFMA2 chains (two per point) of 16.  Returns the running max of  W1a . x + cst  over the kept points.
+// The caller guarantees a __syncwarp() between the last read of the x buffers and this call.
+__device__ __forceinline__ float2 layer1_points(const LaneWeights &w, const float2 (&wa)[32], const float2 kc, const float2 cst,
+                                                uint32_t pa, uint32_t n, uint32_t s_x, int lane, float2 best)
+{
+    const uint32_t qnan_bits = 0x7fc00000u;
+    uint32_t half = 0;
+    for (uint32_t j = 0; j < n; j += 2) {
+        const uint32_t qa = pa + j * 32u;
+        const float4 a0 = lds4(qa), a1 = lds4(qa + 32u);
+        const float t0 = __uint_as_float(lds1u(qa + 16u)), t1 = __uint_as_float(lds1u(qa + 48u));
+        const bool ok0 = __float_as_uint(a0.x) != qnan_bits, ok1 = j + 1u < n && __float_as_uint(a1.x) != qnan_bits;
+        float2 x0 = make_float2(-INFINITY, -INFINITY), x1 = x0;
+        point_step(w, a0, t0, x0);
+        point_step(w, a1, t1, x1);
+        x0 = add2(x0, kc);
+        x1 = add2(x1, kc);
+        const uint32_t xs = s_x + half;
+        half ^= 2u * kXBytes;
+        sts2(xs + lane * 8u, make_float2(fmaxf(x0.x, 0.f), fmaxf(x0.y, 0.f)));
+        sts2(xs + kXBytes + lane * 8u, make_float2(fmaxf(x1.x, 0.f), fmaxf(x1.y, 0.f)));
+        __syncwarp();
+        float2 ya = cst, yb = make_float2(0.f, 0.f), yc = cst, yd = yb;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 u = lds4(xs + k4 * 16u), v = lds4(xs + kXBytes + k4 * 16u);
+            ya = fma2s(wa[4 * k4 + 0], u.x, ya);
+            yc = fma2s(wa[4 * k4 + 0], v.x, yc);
+            yb = fma2s(wa[4 * k4 + 1], u.y, yb);
+            yd = fma2s(wa[4 * k4 + 1], v.y, yd);
+            ya = fma2s(wa[4 * k4 + 2], u.z, ya);
+            yc = fma2s(wa[4 * k4 + 2], v.z, yc);
+            yb = fma2s(wa[4 * k4 + 3], u.w, yb);
+            yd = fma2s(wa[4 * k4 + 3], v.w, yd);
+        }
+        if (ok0) best = max2(best, add2(ya, yb));
+        if (ok1) best = max2(best, add2(yc, yd));
+    }
+    return best;
+}
+
 // A pillar of more than 32 points: straight from global memory, the whole warp on one pillar (rare: it reloads the lane's
 // weights instead of taking them from the caller, so that the caller's copy never needs an address).
-__device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, uint32_t p0, uint32_t n, int row, float cx,
-                                         float cy, float cz, unsigned long long out_lane, int lane)
+template <bool kTwo>
+__device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, uint32_t s_x, uint32_t p0, uint32_t n, int row,
+                                         float cx, float cy, float cz, unsigned long long out_lane, int lane)
 {
     const LaneWeights w = load_lane_weights(p.folded, lane);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
@@ -363,13 +453,51 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
     const float4 c4 = make_float4(cx, cy, cz, 0.f);
     const float4 m4 = make_float4(rel_mean(cx, static_cast<float>(sx) * rn), rel_mean(cy, static_cast<float>(sy) * rn),
                                   rel_mean(cz, static_cast<float>(sz) * rn), __int_as_float(row));
-    pillar_finish(w, c4, m4, n < P, acc, out_lane);
+    if constexpr (!kTwo) {
+        pillar_finish(w, c4, m4, n < P, acc, out_lane);
+    } else {
+        // two layers: the pillar-wise max of layer 0 -> layer 1's constant, then a second pass over the records
+        const Layer1 l1 = load_layer1(p.folded, p.folded2, lane);
+        const bool padded = n < P;
+        const float2 kc = pillar_const(w, c4, m4);
+        float2 m = add2(acc, kc);
+        m.x = fmaxf(m.x, padded ? w.rsh.x : 0.f);
+        m.y = fmaxf(m.y, padded ? w.rsh.y : 0.f);
+        __syncwarp();
+        sts2(s_x + 3u * kXBytes + lane * 8u, m);
+        __syncwarp();
+        const float2 cst = layer1_const(p.folded2 + 2048, s_x + 3u * kXBytes, l1.sh, lane);
+        float2 best = make_float2(-INFINITY, -INFINITY);
+        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+            const uint32_t cnt = min(32u, n - k0);
+            u = make_float4(qnan, 0.f, 0.f, 0.f);
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < cnt) {
+                const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + k0 + lane);
+                u = __ldg(src);
+                v = __ldg(src + 1);
+                if (__float_as_uint(v.z) > thr) u.x = qnan;
+            }
+            __syncwarp();  // the previous sweep has been read
+            sts4(s_hist + lane * 32u, u);
+            sts4(s_hist + lane * 32u + 16, v);
+            __syncwarp();
+            best = layer1_points(w, l1.wa, kc, cst, s_hist, cnt, s_x, lane, best);
+        }
+        if (padded) best = max2(best, add2(l1.upad, cst));
+        if (row >= 0)
+            asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
+                         "f"(fmaxf(best.x, 0.f)), "f"(fmaxf(best.y, 0.f))
+                         : "memory");
+    }
 }
 
 // Pillars of more than 32 points, listed by the grouping stage: every warp, once its own chunks are done, takes entries
 // from the list through one grid-wide cursor, so the long tail is spread over the whole machine instead of serialising the
 // warps whose chunks happen to contain it.
-__device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t s_hist, unsigned long long out_lane, int lane)
+template <bool kTwo>
+__device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t s_hist, uint32_t s_x, unsigned long long out_lane,
+                                                   int lane)
 {
     const uint32_t n_long = __ldcg(p.long_count) + 1u;
     if (n_long == 0u) return;
@@ -382,15 +510,24 @@ __device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t
         const float cx = __fadd_rn(__fmul_rn(static_cast<float>(e0.w & 0xFFFFu), p.vsz[0]), p.off[0]);
         const float cy = __fadd_rn(__fmul_rn(static_cast<float>(e0.w >> 16), p.vsz[1]), p.off[1]);
         const float cz = __fadd_rn(__fmul_rn(static_cast<float>(e1.x), p.vsz[2]), p.off[2]);
-        long_pillar(p, s_hist, e0.x, e0.y, static_cast<int>(e0.z), cx, cy, cz, out_lane, lane);
+        long_pillar<kTwo>(p, s_hist, s_x, e0.x, e0.y, static_cast<int>(e0.z), cx, cy, cz, out_lane, lane);
     }
 }
 
-template <int kWarps, int kMinBlocks>
+// kTwo: a two-layer stack NUM_FILTERS [64, 64] (waymo_models/pointpillar_1x.yaml:34; pillar_vfe.py:18-19,44-49,119-120).
+// Layer 0 (32 outputs: lanes 0-15 carry them, the folded table holds zeros for channels 32-63) is evaluated exactly like the
+// single layer; its pillar-wise max m goes through shared memory into  cst = shift1 + (scale1 W1[:, 32:]) m  (weights in
+// shared memory, once per pillar), then every kept point is evaluated again:  y = relu((scale1 W1[:, :32]) x_p + cst)  with
+// the lane's 2 x 32 weights in registers, x_p broadcast from shared memory; padded slots contribute one row with
+// x = relu(shift0) (NOT re-masked between the layers, as in the reference).  Pillars of more than 32 points: long_pillar<true>
+// makes a second pass over the records.
+template <int kWarps, int kMinBlocks, bool kTwo = false>
 __global__ void __launch_bounds__(32 * kWarps, kMinBlocks)
 k_pillar_walk(const __grid_constant__ WalkParams p)
 {
-    __shared__ __align__(16) unsigned char s_all[kWarps * kWarpSmem];
+    constexpr uint32_t kStride = kTwo ? kWarpSmemTwo : kWarpSmem;
+    __shared__ __align__(16) unsigned char s_all[kWarps * kStride];
+    __shared__ __align__(16) float s_w1b[kTwo ? 32 * 64 : 4];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) dbg_stamp(p.dbg, 18);
@@ -399,7 +536,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     if (threadIdx.x == 0) dbg_stamp(p.dbg, 20);
     const uint32_t total = __ldcg(&p.hdr->total_listed);
     const uint32_t n_chunks = (total + 31u) >> 5;
-    const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * kWarpSmem;
+    const uint32_t s_warp = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * kStride;
     const uint32_t s_pl = s_warp + kOffPl, s_sum = s_warp + kOffSum;
     const float qnan = __int_as_float(0x7fc00000);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
@@ -427,8 +564,16 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         cp_async16(s_warp + b * kBufBytes + kRecBytes + lane * 16u, p.pillar_meta + (ok ? pos : 0u), ok ? 16 : 0);
     };
 
+    const uint32_t s_x = s_warp + kOffX;
+    Layer1 l1;
+    if constexpr (kTwo) {
+        for (int i = threadIdx.x; i < 32 * 64 / 4; i += 32 * kWarps)
+            reinterpret_cast<float4 *>(s_w1b)[i] = __ldg(reinterpret_cast<const float4 *>(p.folded2 + 2048) + i);
+        __syncthreads();
+        l1 = load_layer1(p.folded, p.folded2, lane);
+    }
     if (cur >= c_end) {
-        drain_long_pillars(p, s_pl, out_lane, lane);
+        drain_long_pillars<kTwo>(p, s_pl, s_x, out_lane, lane);
         return;
     }
     fetch(cur, 0);
@@ -511,7 +656,36 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
             // ---- phase 2: the warp walks the pillars that start among its 32 positions; lane = channel pair.  TWO pillars per
             //      trip: their first-point chains and constant chains are four independent FFMA2 chains in one straight-line
             //      block; further points of a pillar are evaluated two at a time.
-            while (rem) {
+            if constexpr (kTwo) {
+                while (rem) {
+                    const uint32_t slot = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    const uint32_t pa = rs + slot * 32u;
+                    const float4 c4 = lds4(s_pl + slot * 32u), m4 = lds4(s_pl + slot * 32u + 16);
+                    const float2 kc = pillar_const(w, c4, m4);
+                    const uint32_t nbits = __float_as_uint(c4.w), n = nbits & 0x7FFFFFFFu;
+                    const bool padded = static_cast<int>(nbits) < 0;
+                    const int row = __float_as_int(m4.w);
+                    // pass A: pillar-wise max of layer 0 (ReLU and the constant commute with the max; dropped points are NaN)
+                    float2 acc = point_eval(w, pa);
+                    if (n > 1u) acc = more_points(w, pa, n, acc);
+                    float2 m = add2(acc, kc);
+                    m.x = fmaxf(m.x, padded ? w.rsh.x : 0.f);
+                    m.y = fmaxf(m.y, padded ? w.rsh.y : 0.f);
+                    __syncwarp();  // the previous pillar's reads of the x buffers
+                    sts2(s_x + 3u * kXBytes + lane * 8u, m);
+                    __syncwarp();
+                    const float2 cst = layer1_const(s_w1b, s_x + 3u * kXBytes, l1.sh, lane);
+                    // pass B: layer 1 on [x_p, m] for every kept point
+                    float2 best = layer1_points(w, l1.wa, kc, cst, pa, n, s_x, lane, make_float2(-INFINITY, -INFINITY));
+                    if (padded) best = max2(best, add2(l1.upad, cst));
+                    if (row >= 0)
+                        asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
+                                     "f"(fmaxf(best.x, 0.f)), "f"(fmaxf(best.y, 0.f))
+                                     : "memory");
+                }
+            }
+            while (!kTwo && rem) {
                 const uint32_t slot_a = __ffs(rem) - 1;
                 rem &= rem - 1;
                 const bool has_b = rem != 0u;
@@ -538,16 +712,20 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         buf ^= 1u;
     }
     if (lane == 0) dbg_stamp(p.dbg, 21);  // chunks done
-    drain_long_pillars(p, s_pl, out_lane, lane);
+    drain_long_pillars<kTwo>(p, s_pl, s_x, out_lane, lane);
     if (lane == 0) dbg_stamp(p.dbg, 23);
 }
 
 // ---- folding of the layer's weights (once per model: pillars_fold_pfn) ------------------------------------------------
 __global__ void k_fold_pfn(const float *__restrict__ weight, const float *__restrict__ scale,
-                           const float *__restrict__ shift, int c_point, int c_in, float *__restrict__ folded)
+                           const float *__restrict__ shift, int c_point, int c_in, int f_out, float *__restrict__ folded)
 {
     const int o = threadIdx.x;
     if (o >= 64) return;
+    if (o >= f_out) {  // a 32-output layer 0 of a two-layer stack: the upper channels are zeros throughout
+        for (int r = 0; r < 13; ++r) folded[r * 64 + o] = 0.f;
+        return;
+    }
     const float *w = weight + static_cast<size_t>(o) * c_in;  // feature order: p[0..c), cluster xyz, centre xyz
     const double s = scale[o];
     const int c = c_point;
@@ -571,9 +749,29 @@ int env_int(const char *name, int dflt)
 
 }  // namespace
 
-cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st)
+cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st, int f_out)
 {
-    k_fold_pfn<<<1, 64, 0, st>>>(pfn.weight, pfn.scale, pfn.shift, c_point, c_in, folded);
+    k_fold_pfn<<<1, 64, 0, st>>>(pfn.weight, pfn.scale, pfn.shift, c_point, c_in, f_out, folded);
+    note_launch();
+    return cudaGetLastError();
+}
+
+// layer 1 of a [64, 64] stack: weight [64][64] (inputs 0-31 per point, 32-63 the pillar-wise max), BatchNorm scale folded in
+__global__ void k_fold_pfn2(const float *__restrict__ weight, const float *__restrict__ scale, const float *__restrict__ shift,
+                            float *__restrict__ folded2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (k, j): input k of both halves, output j
+    if (i >= 32 * 64) return;
+    const int k = i >> 6, j = i & 63;
+    const float s = scale[j];
+    folded2[k * 64 + j] = s * weight[j * 64 + k];
+    folded2[2048 + k * 64 + j] = s * weight[j * 64 + 32 + k];
+    if (k == 0) folded2[4096 + j] = shift[j];
+}
+
+cudaError_t launch_fold_pfn2(const float *weight, const float *scale, const float *shift, float *folded2, cudaStream_t st)
+{
+    k_fold_pfn2<<<8, 256, 0, st>>>(weight, scale, shift, folded2);
     note_launch();
     return cudaGetLastError();
 }
@@ -590,6 +788,7 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     p.long_count = ws.long_count;
     p.long_cursor = ws.long_cursor;
     p.folded = folded;
+    p.folded2 = job.folded2;
     p.pillar_features = job.pillar_features;
     p.gd = gd;
     p.sh_cells = log2_exact(gd.cells);
@@ -621,6 +820,13 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     if (warps > wave) warps = wave;
     const unsigned grid = static_cast<unsigned>((warps + kWarps - 1) / kWarps);
     cudaError_t err;
+    if (job.folded2) {  // two-layer stack: 64 more weight registers per lane
+        err = launch_pdl(k_pillar_walk<kWarps, 3, true>, dim3(static_cast<unsigned>((tmin<int64_t>((chunks + 1) / 2, static_cast<int64_t>(sms) * 3 * kWarps) + kWarps - 1) / kWarps)),
+                         dim3(32 * kWarps), 0, st, p);
+        if (err != cudaSuccess) return err;
+        note_launch();
+        return cudaGetLastError();
+    }
     switch (occ) {
     case 8: err = launch_pdl(k_pillar_walk<kWarps, 8>, dim3(grid), dim3(32 * kWarps), 0, st, p); break;
     case 7: err = launch_pdl(k_pillar_walk<kWarps, 7>, dim3(grid), dim3(32 * kWarps), 0, st, p); break;
