@@ -1052,8 +1052,8 @@ BACKBONE_CFG = dict(LAYER_NUMS=[3, 5, 5], LAYER_STRIDES=[2, 2, 2], NUM_FILTERS=[
 
 
 def two_layer_numbers(wl):
-    """cfg4 with Waymo's own PFN, NUM_FILTERS [64, 64] (waymo_models/pointpillar_1x.yaml:34): the general feature kernel
-    (csrc/pfn_multi.cu, a coverage kernel) instead of the streaming one the benched line uses.  Serial, one stream."""
+    """cfg4 with Waymo's own PFN, NUM_FILTERS [64, 64] (waymo_models/pointpillar_1x.yaml:34): the streaming kernel's
+    two-layer variant (csrc/pfn_stream.cu, k_pillar_walk<.., true>) through pillars_encode_stack.  Serial, one stream."""
     from lidar_vision_vqa_b200 import ops
     from oracle import pillar_oracle as po  # weights generator only
 
@@ -1082,8 +1082,8 @@ def two_layer_numbers(wl):
         out["with_canvas_ms" if with_bev else "group_and_features_ms"] = float(np.median(ts))
         torch.cuda.empty_cache()
     out["sweeps_per_s_serial"] = wl.nb / (out["with_canvas_ms"] * 1e-3)
-    out["what"] = ("pillars_encode_stack, serial on one stream (fresh canvas per call); the benched cfg4 line above uses NUM_FILTERS "
-                   "[64] on the streaming kernel")
+    out["what"] = ("pillars_encode_stack (two-layer streaming kernel), serial on one stream (fresh canvas per call); the benched cfg4 "
+                   "line above uses NUM_FILTERS [64]")
     return out
 
 

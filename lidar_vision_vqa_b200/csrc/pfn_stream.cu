@@ -60,6 +60,7 @@ struct WalkParams {
     const uint4 *long_list;       // pillars of more than 32 points: {list start, n, row, x | y << 16} {z, -, -, -}
     const uint32_t *long_count;   // entries - 1
     uint32_t *long_cursor;        // next entry to process - 1 (shared by all warps of the grid)
+    uint32_t *chunk_cursor;       // two-layer stacks: next chunk to process - 1 (chunks are handed out one at a time)
     const float *folded;          // [PILLARS_FOLDED_FLOATS], see launch_fold_pfn
     float *pillar_features;
     const float *folded2;         // two-layer stacks: [32][64] per-point half of layer 1 | [32][64] pillar-max half | [64] shift
@@ -304,29 +305,36 @@ __device__ __forceinline__ float2 layer1_const(const float *w1b, uint32_t xs, fl
 }
 // Layer 1 over the n staged points at shared address pa (32-byte records, NaN x = beyond the first-P cap), two points per
 // trip: x = relu(layer 0) of both goes through the warp's x buffers (double buffered: one __syncwarp per trip), then four
-// independent FFMA2 chains (two per point) of 16.  Returns the running max of  W1a . x + cst  over the kept points.
-// The caller guarantees a __syncwarp() between the last read of the x buffers and this call.
+// independent FFMA2 chains (two per point) of 16; an odd last point takes a trip of its own (four chains of 8).  Returns the
+// running max of  W1a . x + cst  over the kept points.  The caller guarantees a __syncwarp() between the last read of the x
+// buffers and this call.
+__device__ __forceinline__ float2 point_lin(const LaneWeights &w, const float4 a, const float t)
+{
+    float2 y = mul2s(w.w0, a.x);
+    y = fma2s(w.w1, a.y, y);
+    y = fma2s(w.w2, a.z, y);
+    y = fma2s(w.w3, a.w, y);
+    return fma2s(w.w4, t, y);
+}
+__device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
 __device__ __forceinline__ float2 layer1_points(const LaneWeights &w, const float2 (&wa)[32], const float2 kc, const float2 cst,
                                                 uint32_t pa, uint32_t n, uint32_t s_x, int lane, float2 best)
 {
     const uint32_t qnan_bits = 0x7fc00000u;
-    uint32_t half = 0;
-    for (uint32_t j = 0; j < n; j += 2) {
+    const float2 zero = make_float2(0.f, 0.f);
+    uint32_t half = 0, j = 0;
+    for (; j + 1u < n; j += 2) {
         const uint32_t qa = pa + j * 32u;
         const float4 a0 = lds4(qa), a1 = lds4(qa + 32u);
         const float t0 = __uint_as_float(lds1u(qa + 16u)), t1 = __uint_as_float(lds1u(qa + 48u));
-        const bool ok0 = __float_as_uint(a0.x) != qnan_bits, ok1 = j + 1u < n && __float_as_uint(a1.x) != qnan_bits;
-        float2 x0 = make_float2(-INFINITY, -INFINITY), x1 = x0;
-        point_step(w, a0, t0, x0);
-        point_step(w, a1, t1, x1);
-        x0 = add2(x0, kc);
-        x1 = add2(x1, kc);
+        const bool ok0 = __float_as_uint(a0.x) != qnan_bits, ok1 = __float_as_uint(a1.x) != qnan_bits;
+        const float2 x0 = relu2(add2(point_lin(w, a0, t0), kc)), x1 = relu2(add2(point_lin(w, a1, t1), kc));
         const uint32_t xs = s_x + half;
         half ^= 2u * kXBytes;
-        sts2(xs + lane * 8u, make_float2(fmaxf(x0.x, 0.f), fmaxf(x0.y, 0.f)));
-        sts2(xs + kXBytes + lane * 8u, make_float2(fmaxf(x1.x, 0.f), fmaxf(x1.y, 0.f)));
+        sts2(xs + lane * 8u, x0);
+        sts2(xs + kXBytes + lane * 8u, x1);
         __syncwarp();
-        float2 ya = cst, yb = make_float2(0.f, 0.f), yc = cst, yd = yb;
+        float2 ya = cst, yb = zero, yc = cst, yd = zero;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
             const float4 u = lds4(xs + k4 * 16u), v = lds4(xs + kXBytes + k4 * 16u);
@@ -341,6 +349,26 @@ __device__ __forceinline__ float2 layer1_points(const LaneWeights &w, const floa
         }
         if (ok0) best = max2(best, add2(ya, yb));
         if (ok1) best = max2(best, add2(yc, yd));
+    }
+    if (j < n) {
+        const uint32_t qa = pa + j * 32u;
+        const float4 a0 = lds4(qa);
+        const float t0 = __uint_as_float(lds1u(qa + 16u));
+        if (__float_as_uint(a0.x) != qnan_bits) {  // warp-uniform
+            const uint32_t xs = s_x + half;
+            sts2(xs + lane * 8u, relu2(add2(point_lin(w, a0, t0), kc)));
+            __syncwarp();
+            float2 ya = cst, yb = zero, yc = zero, yd = zero;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 u = lds4(xs + k4 * 16u);
+                ya = fma2s(wa[4 * k4 + 0], u.x, ya);
+                yb = fma2s(wa[4 * k4 + 1], u.y, yb);
+                yc = fma2s(wa[4 * k4 + 2], u.z, yc);
+                yd = fma2s(wa[4 * k4 + 3], u.w, yd);
+            }
+            best = max2(best, add2(add2(ya, yb), add2(yc, yd)));
+        }
     }
     return best;
 }
@@ -547,9 +575,17 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     // A warp owns a contiguous range of chunks.  (Handing chunks out one at a time through a grid-wide cursor was measured
     // SLOWER, 37-39 us against 33 us on cfg2, although per-warp times vary by +-40 %: neighbouring chunks then run on different
     // SMs and every window is fetched twice.)
+    // Two-layer stacks are the opposite case: a chunk costs 5-10x more arithmetic (and 2.5x more when its pillars hold one
+    // point each than when they hold many), so static ranges left the last warp running at 196 us when the first was done at
+    // 18 us (cfg2); there the chunks are handed out one at a time through a grid-wide cursor.
     const uint32_t gw = blockIdx.x * kWarps + warp, n_warps = gridDim.x * kWarps;
-    uint32_t cur = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * gw / n_warps);
-    const uint32_t c_end = static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * (gw + 1) / n_warps);
+    auto grab = [&]() {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(p.chunk_cursor, 1u) + 1u;  // the cursor starts at 0xFFFFFFFF
+        return __shfl_sync(kFull, i, 0);
+    };
+    uint32_t cur = kTwo ? grab() : static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * gw / n_warps);
+    const uint32_t c_end = kTwo ? n_chunks : static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * (gw + 1) / n_warps);
     // chunk k -> buffer b: own records, look-ahead records, pillar entries (zero-filled beyond the end of the list)
     auto fetch = [&](uint32_t k, uint32_t b) {
         const uint32_t pos = (k << 5) + lane;
@@ -585,7 +621,8 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
 
     while (true) {
         // the next chunk's loads fly during this chunk's arithmetic
-        if (cur + 1 < c_end) fetch(cur + 1, buf ^ 1u);
+        const uint32_t nxt = kTwo ? grab() : cur + 1u;
+        if (nxt < c_end) fetch(nxt, buf ^ 1u);
         cp_async_commit();
         const uint32_t rs = s_warp + buf * kBufBytes;  // window: 64 consecutive positions starting at chunk cur
         const uint32_t ms = rs + kRecBytes;
@@ -708,12 +745,19 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         }
         cp_async_wait_all();
         __syncwarp();
-        if (++cur >= c_end) break;
+        cur = nxt;
+        if (cur >= c_end) break;
         buf ^= 1u;
     }
-    if (lane == 0) dbg_stamp(p.dbg, 21);  // chunks done
+    if (lane == 0) {
+        dbg_stamp(p.dbg, 21);  // chunks done (latest warp)
+        dbg_stamp(p.dbg, 22);  // (earliest warp)
+    }
     drain_long_pillars<kTwo>(p, s_pl, s_x, out_lane, lane);
-    if (lane == 0) dbg_stamp(p.dbg, 23);
+    if (lane == 0) {
+        dbg_stamp(p.dbg, 23);
+        dbg_stamp(p.dbg, 24);
+    }
 }
 
 // ---- folding of the layer's weights (once per model: pillars_fold_pfn) ------------------------------------------------
@@ -787,6 +831,7 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     p.long_list = ws.long_list;
     p.long_count = ws.long_count;
     p.long_cursor = ws.long_cursor;
+    p.chunk_cursor = ws.long_cursor ? ws.long_cursor + 16 : nullptr;  // same 0xFF-filled 256-byte block, own 64-byte line
     p.folded = folded;
     p.folded2 = job.folded2;
     p.pillar_features = job.pillar_features;
