@@ -60,7 +60,8 @@ struct WalkParams {
     const uint4 *long_list;       // pillars of more than 32 points: {list start, n, row, x | y << 16} {z, -, -, -}
     const uint32_t *long_count;   // entries - 1
     uint32_t *long_cursor;        // next entry to process - 1 (shared by all warps of the grid)
-    uint32_t *chunk_cursor;       // two-layer stacks: next chunk to process - 1 (chunks are handed out one at a time)
+    uint32_t *chunk_cursor;       // next chunk of the shared pool - 1 (chunks of the pool are handed out one at a time)
+    uint32_t pool_256;            // share of the chunks (in 1/256) that forms the pool at the end of the list
     const float *folded;          // [PILLARS_FOLDED_FLOATS], see launch_fold_pfn
     float *pillar_features;
     const float *folded2;         // two-layer stacks: [32][64] per-point half of layer 1 | [32][64] pillar-max half | [64] shift
@@ -575,17 +576,26 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     // A warp owns a contiguous range of chunks.  (Handing chunks out one at a time through a grid-wide cursor was measured
     // SLOWER, 37-39 us against 33 us on cfg2, although per-warp times vary by +-40 %: neighbouring chunks then run on different
     // SMs and every window is fetched twice.)
-    // Two-layer stacks are the opposite case: a chunk costs 5-10x more arithmetic (and 2.5x more when its pillars hold one
-    // point each than when they hold many), so static ranges left the last warp running at 196 us when the first was done at
-    // 18 us (cfg2); there the chunks are handed out one at a time through a grid-wide cursor.
+    // The LAST `pool_256`/256 of the chunks can be left unassigned: warps that finish their range take them one at a time
+    // from a grid-wide cursor.  One layer: measured without gain (cfg2 34.8 us static, 36.9 us with 19-62 % pooled, 38.9 us all
+    // pooled; cfg3 120.8 / 114.9 / 123.9 us; profiles/r02_walk_pool.txt) -- the late warps are not short of chunks, the SM is
+    // short of issue slots -- so the pool is empty by default (PILLARS_WALK_POOL).  Two-layer stacks are the opposite case (a
+    // chunk costs 5-10x more arithmetic, and 2.5x more when its pillars hold one point each; static ranges left the last
+    // warp running at 196 us when the first was done at 18 us): there every chunk comes from the cursor.
     const uint32_t gw = blockIdx.x * kWarps + warp, n_warps = gridDim.x * kWarps;
     auto grab = [&]() {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(p.chunk_cursor, 1u) + 1u;  // the cursor starts at 0xFFFFFFFF
         return __shfl_sync(kFull, i, 0);
     };
-    uint32_t cur = kTwo ? grab() : static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * gw / n_warps);
-    const uint32_t c_end = kTwo ? n_chunks : static_cast<uint32_t>(static_cast<unsigned long long>(n_chunks) * (gw + 1) / n_warps);
+    const uint32_t n_static = kTwo ? 0u : n_chunks - static_cast<uint32_t>((static_cast<unsigned long long>(n_chunks) * p.pool_256) >> 8);
+    uint32_t cur = static_cast<uint32_t>(static_cast<unsigned long long>(n_static) * gw / n_warps);
+    const uint32_t c_end = static_cast<uint32_t>(static_cast<unsigned long long>(n_static) * (gw + 1) / n_warps);
+    bool pooled = false;
+    if (cur >= c_end) {
+        pooled = true;
+        cur = n_static + grab();
+    }
     // chunk k -> buffer b: own records, look-ahead records, pillar entries (zero-filled beyond the end of the list)
     auto fetch = [&](uint32_t k, uint32_t b) {
         const uint32_t pos = (k << 5) + lane;
@@ -608,7 +618,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         __syncthreads();
         l1 = load_layer1(p.folded, p.folded2, lane);
     }
-    if (cur >= c_end) {
+    if (cur >= n_chunks) {
         drain_long_pillars<kTwo>(p, s_pl, s_x, out_lane, lane);
         return;
     }
@@ -621,8 +631,12 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
 
     while (true) {
         // the next chunk's loads fly during this chunk's arithmetic
-        const uint32_t nxt = kTwo ? grab() : cur + 1u;
-        if (nxt < c_end) fetch(nxt, buf ^ 1u);
+        uint32_t nxt = cur + 1u;
+        if (pooled || nxt >= c_end) {
+            pooled = true;
+            nxt = n_static + grab();
+        }
+        if (nxt < n_chunks) fetch(nxt, buf ^ 1u);
         cp_async_commit();
         const uint32_t rs = s_warp + buf * kBufBytes;  // window: 64 consecutive positions starting at chunk cur
         const uint32_t ms = rs + kRecBytes;
@@ -746,7 +760,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         cp_async_wait_all();
         __syncwarp();
         cur = nxt;
-        if (cur >= c_end) break;
+        if (cur >= n_chunks) break;
         buf ^= 1u;
     }
     if (lane == 0) {
@@ -858,6 +872,11 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
         const int v = env_int("PILLARS_WALK_OCC", 5);
         return v < 5 ? 5 : (v > 8 ? 8 : v);
     }();
+    static const int pool = [] {
+        const int v = env_int("PILLARS_WALK_POOL", 0);
+        return v < 0 ? 0 : (v > 256 ? 256 : v);
+    }();
+    p.pool_256 = job.folded2 ? 256u : static_cast<uint32_t>(pool);
     constexpr int kWarps = 4;
     const int64_t chunks = (job.n + 31) / 32;  // upper bound: listed points <= n
     int64_t warps = (chunks + 1) / 2;

@@ -29,8 +29,8 @@ NAMES = {0: "fill first CTA in", 1: "fill last CTA out", 2: "insert first CTA in
          4: "insert first past wait (fill done)", 5: "insert last CTA out", 6: "scan first CTA in",
          7: "scan last CTA past wait", 8: "scan first CTA past wait (insert done)", 9: "scan last tile scanned",
          11: "scan last look-back resolved", 13: "scan last CTA out", 14: "place first CTA in", 16: "place first past wait",
-         17: "place last CTA out", 18: "walk first CTA in", 20: "walk first past wait", 21: "walk last warp chunks done",
-         23: "walk last warp out", 25: "insert last CTA in", 27: "insert last tile in shared memory"}
+         17: "place last CTA out", 18: "walk first CTA in", 20: "walk first past wait", 21: "walk last warp chunks done", 22: "walk FIRST warp chunks done",
+         23: "walk last warp out", 24: "walk FIRST warp out", 25: "insert last CTA in", 27: "insert last tile in shared memory"}
 rows = []
 for rep in range(7):
     buf = torch.zeros(32, dtype=torch.int64, device=dev)
