@@ -306,7 +306,7 @@ __device__ __forceinline__ float2 layer1_const(const float *w1b, uint32_t xs, fl
 }
 // Layer 1 over the n staged points at shared address pa (32-byte records, NaN x = beyond the first-P cap), two points per
 // trip: x = relu(layer 0) of both goes through the warp's x buffers (double buffered: one __syncwarp per trip), then four
-// independent FFMA2 chains (two per point) of 16; an odd last point takes a trip of its own (four chains of 8).  Returns the
+// independent FFMA2 chains (two per point) of 16; an odd last point takes a trip of its own (the same two chains).  Returns the
 // running max of  W1a . x + cst  over the kept points.  The caller guarantees a __syncwarp() between the last read of the x
 // buffers and this call.
 __device__ __forceinline__ float2 point_lin(const LaneWeights &w, const float4 a, const float t)
@@ -359,16 +359,18 @@ __device__ __forceinline__ float2 layer1_points(const LaneWeights &w, const floa
             const uint32_t xs = s_x + half;
             sts2(xs + lane * 8u, relu2(add2(point_lin(w, a0, t0), kc)));
             __syncwarp();
-            float2 ya = cst, yb = zero, yc = zero, yd = zero;
+            // the same two chains and summation order as in a pair: a point's value must not depend on where the
+            // (unordered) list placed it, or the output would not be bit-reproducible from run to run
+            float2 ya = cst, yb = zero;
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
                 const float4 u = lds4(xs + k4 * 16u);
                 ya = fma2s(wa[4 * k4 + 0], u.x, ya);
                 yb = fma2s(wa[4 * k4 + 1], u.y, yb);
-                yc = fma2s(wa[4 * k4 + 2], u.z, yc);
-                yd = fma2s(wa[4 * k4 + 3], u.w, yd);
+                ya = fma2s(wa[4 * k4 + 2], u.z, ya);
+                yb = fma2s(wa[4 * k4 + 3], u.w, yb);
             }
-            best = max2(best, add2(add2(ya, yb), add2(yc, yd)));
+            best = max2(best, add2(ya, yb));
         }
     }
     return best;

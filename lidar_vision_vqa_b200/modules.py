@@ -286,8 +286,11 @@ class PillarVFEFromPoints(_PillarVFEBase):
         else:
             if self.emit_index_map:
                 raise NotImplementedError("EMIT_INDEX_MAP is implemented for the single-layer PFN path")
+            buffers = None
+            if self.output_ring > 0:
+                buffers = self._ring_buffers(points.shape[0], batch_size, points.device)
             res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=col0,
-                                   with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant)
+                                   with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant, buffers=buffers)
         if self.fuse_scatter:
             batch_dict["spatial_features"] = res["bev"]
             batch_dict["_b200_scatter_done"] = True

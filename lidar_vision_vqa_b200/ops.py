@@ -312,10 +312,13 @@ def pfn_dense_stack(voxels: torch.Tensor, num_points: torch.Tensor, coords: torc
 
 def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, stack: PfnStackParams, *,
                  col0: int = 0, dynamic: bool = False, coords_cols: int = 4, with_bev: bool = False,
-                 capacity: Optional[int] = None, scatter_variant: str = "auto", ws_slot: int = 0) -> Dict[str, torch.Tensor]:
-    """Raw points -> pillar features through the general feature kernel.  ``dynamic=False``: hard-voxeliser semantics
-    (the fused equivalent of ``transform_points_to_voxels`` + a multi-layer ``PillarVFE``); ``dynamic=True``:
-    DynamicPillarVFE / DynamicPillarVFESimple2D semantics (dynamic_pillar_vfe.py:90-142, :193-240)."""
+                 capacity: Optional[int] = None, scatter_variant: str = "auto", ws_slot: int = 0,
+                 buffers: Optional["EncodeBuffers"] = None) -> Dict[str, torch.Tensor]:
+    """Raw points -> pillar features through a feature stack.  ``dynamic=False``: hard-voxeliser semantics (the fused
+    equivalent of ``transform_points_to_voxels`` + a multi-layer ``PillarVFE``; NUM_FILTERS [64, 64] in the standard
+    feature layout runs on the streaming kernel's two-layer variant, everything else on the general kernel);
+    ``dynamic=True``: DynamicPillarVFE / DynamicPillarVFESimple2D semantics (dynamic_pillar_vfe.py:90-142, :193-240).
+    ``buffers`` (hard mode, 4-column coords): pre-allocated outputs + workspace, as for :func:`encode_bev`."""
     _check_points(points, frame_offsets)
     lib = _native.load()
     n, stride = points.shape
@@ -323,29 +326,49 @@ def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSp
     if stride - col0 < stack.c_point:
         raise ValueError("points have fewer channels than the PFN expects")
     dev = points.device
-    cap = capacity
-    if cap is None:
-        cap = n if dynamic else min(n, nb * grid.max_voxels)
-    cap = max(int(cap), 1)  # an empty batch still needs non-NULL output pointers
     nx, ny, nz = grid.grid_size
-    res = {
-        "pillar_features": torch.empty((cap, stack.f_out), dtype=torch.float32, device=dev),
-        "voxel_coords": torch.empty((cap, coords_cols), dtype=torch.int32, device=dev),
-        "voxel_num_points": torch.empty((cap,), dtype=torch.int32, device=dev),
-        "pillar_count": torch.empty((nb + 1,), dtype=torch.int32, device=dev),
-    }
+    g = grid.native()
+    need = lib.pillars_workspace_bytes(n, nb, ctypes.byref(g))
     out = PillarsOutputs()
-    out.pillar_capacity = cap
+    if buffers is not None:
+        if dynamic or coords_cols != 4:
+            raise ValueError("EncodeBuffers hold hard-mode outputs with (b, z, y, x) coordinates")
+        if buffers.pillar_features.shape[1] != stack.f_out or buffers.n_frames != nb:
+            raise ValueError("buffers were created for another feature width / batch size")
+        if buffers.ws.numel() < need:
+            raise ValueError("EncodeBuffers workspace too small for this batch")
+        res = {"pillar_features": buffers.pillar_features, "voxel_coords": buffers.voxel_coords,
+               "voxel_num_points": buffers.voxel_num_points, "pillar_count": buffers.pillar_count}
+        out.pillar_capacity = buffers.capacity
+        ws = buffers.ws
+        if with_bev:
+            if buffers.bev is None:
+                raise ValueError("buffers were created without a BEV canvas")
+            res["bev"] = buffers.bev
+    else:
+        cap = capacity
+        if cap is None:
+            cap = n if dynamic else min(n, nb * grid.max_voxels)
+        cap = max(int(cap), 1)  # an empty batch still needs non-NULL output pointers
+        res = {
+            "pillar_features": torch.empty((cap, stack.f_out), dtype=torch.float32, device=dev),
+            "voxel_coords": torch.empty((cap, coords_cols), dtype=torch.int32, device=dev),
+            "voxel_num_points": torch.empty((cap,), dtype=torch.int32, device=dev),
+            "pillar_count": torch.empty((nb + 1,), dtype=torch.int32, device=dev),
+        }
+        out.pillar_capacity = cap
+        if with_bev:
+            res["bev"] = torch.empty((nb, stack.f_out * nz, ny, nx), dtype=torch.float32, device=dev)
+        ws = workspace(need, dev, ws_slot)
     out.pillar_features = res["pillar_features"].data_ptr()
     out.voxel_coords = res["voxel_coords"].data_ptr()
     out.voxel_num_points = res["voxel_num_points"].data_ptr()
     out.pillar_count = res["pillar_count"].data_ptr()
     if with_bev:
-        res["bev"] = torch.empty((nb, stack.f_out * nz, ny, nx), dtype=torch.float32, device=dev)
-        out.bev = res["bev"].data_ptr()
-    g = grid.native()
-    need = lib.pillars_workspace_bytes(n, nb, ctypes.byref(g))
-    ws = workspace(need, dev, ws_slot)
+        if res["bev"].dtype == torch.float16:
+            out.bev_half = res["bev"].data_ptr()
+        else:
+            out.bev = res["bev"].data_ptr()
     nat = stack.native()
     check(lib.pillars_encode_stack(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
                                    ctypes.byref(nat), _native.MODE_DYNAMIC if dynamic else _native.MODE_HARD, coords_cols,

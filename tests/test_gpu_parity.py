@@ -1011,3 +1011,54 @@ def test_rebase_segments_and_gatherer_single_rank(dev, L, oracle):
     np.testing.assert_array_equal(slot["counts"][0].cpu().numpy(), res["pillar_count"].cpu().numpy())
     canvas = sharding.densify_segments(slot, 2, grid.grid_size[0], grid.grid_size[1])
     assert torch.equal(canvas, res["bev"])
+
+
+@pytest.mark.gpu
+def test_two_layer_stack_with_buffers_ring_and_reproducibility(dev, L):
+    """NUM_FILTERS [64, 64] through pre-allocated EncodeBuffers (ops.encode_stack(buffers=...), the module's OUTPUT_RING)
+    gives bit-identical rows, coordinates and canvas as the allocating call, call after call (the streaming two-layer
+    kernel is order independent: fixed-point mean sums, max over points, per-point chains that do not depend on the point's
+    place in the pillar's list)."""
+    from lidar_vision_vqa_b200 import ops, synth
+
+    g = load_golden("vfe_c5_2layer")
+    sd = _sd_t(g)
+    grid = L.GridSpec(tuple(float(v) for v in g["range"]), tuple(float(v) for v in g["voxel_size"]),
+                      tuple(int(v) for v in g["grid_size"]), int(g["max_points"]), int(g["max_voxels"]))
+    layers = []
+    for i in range(2):
+        bn = tuple(sd[f"pfn_layers.{i}.norm.{k}"] for k in ("weight", "bias", "running_mean", "running_var")) + (1e-3,)
+        layers.append((sd[f"pfn_layers.{i}.linear.weight"], bn, None))
+    stack = ops.fold_pfn_stack(layers, c_point=5, use_absolute_xyz=True, with_distance=False, voxel_size=grid.voxel_size,
+                               point_cloud_range=grid.point_cloud_range, device=dev)
+    p = torch.from_numpy(g["points"]).to(dev)
+    o = torch.from_numpy(g["frame_offsets"]).to(dev)
+    nb = o.numel() - 1
+    ref = ops.encode_stack(p, o, grid, stack, with_bev=True)
+    m = int(ref["pillar_count"][-1].item())
+    np.testing.assert_allclose(ref["pillar_features"][:m].cpu().numpy(), g["out.pillar_features"], rtol=1e-3, atol=1e-5)
+    bufs = ops.EncodeBuffers(p.shape[0], nb, grid, 64, dev)
+    for _ in range(3):
+        res = ops.encode_stack(p, o, grid, stack, with_bev=True, buffers=bufs)
+        torch.cuda.synchronize()
+        assert res["bev"] is bufs.bev
+        for k in ("pillar_count", "bev"):
+            assert torch.equal(res[k], ref[k]), k
+        for k in ("pillar_features", "voxel_coords", "voxel_num_points"):
+            assert torch.equal(res[k][:m], ref[k][:m]), k
+    with pytest.raises(ValueError):
+        ops.encode_stack(p, o, grid, stack, dynamic=True, buffers=bufs)
+    # the module with OUTPUT_RING and no host synchronisation returns the same rows
+    cfg = _cfg(g)
+    cfg.update(MAX_POINTS_PER_VOXEL=int(g["max_points"]), MAX_NUMBER_OF_VOXELS=int(g["max_voxels"]), FUSE_SCATTER=True,
+               OUTPUT_RING=2, SYNC_COUNTS=False)
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=[float(v) for v in g["voxel_size"]],
+                                point_cloud_range=g["range"], grid_size=g["grid_size"])
+    vfe.load_state_dict(sd, strict=True)
+    vfe.eval().to(dev)
+    pb = torch.from_numpy(synth.to_pcdet_points(g["points"], g["frame_offsets"])).to(dev)
+    for _ in range(3):
+        bd = vfe({"points": pb, "batch_size": nb})
+        torch.cuda.synchronize()
+        assert torch.equal(bd["pillar_features"][:m], ref["pillar_features"][:m])
+        assert torch.equal(bd["spatial_features"], ref["bev"])
