@@ -372,6 +372,20 @@ class Workload:
         self.stack = None  # a folded multi-layer PFN (two_layer_numbers): steps then go through pillars_encode_stack
 
 
+def guarded(what, fn):
+    """Optional side measurements (rank 0, no collectives inside) must not cost the run its main line."""
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] side measurement '{what}' failed: {type(e).__name__}: {e}", file=sys.stderr)
+        try:
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+        except Exception:  # noqa: BLE001
+            pass
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def timed_regions(fn_region, repeats, world, dev):
     """Runs fn_region() `repeats` times; each returns elapsed ms of a barrier/sync-bracketed region.  Max over ranks per
     region, then the list."""
@@ -578,7 +592,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- side measurement: the first consumer of the canvas, the BEV tokeniser of VATLiDAR --------------------------------
     if not args.no_tokens and nz == 1:
-        stages["tokens"] = tokens_side_measurement(args, wl, bufs[0], K, peak)
+        stages["tokens"] = guarded("tokens", lambda: tokens_side_measurement(args, wl, bufs[0], K, peak))
 
     # ---- end to end through the reference-facing modules, inputs in pinned host memory ---------------------------------
     e2e = None if args.no_e2e else e2e_numbers(args, wl, rank, world, K, R, numa_cpus)
@@ -589,12 +603,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- the product's caller (f-1): points on the host -> fp16 canvas on the host -------------------------------------------
     extractor = None
     if rank == 0 and world == 1 and not args.no_extractor and not args.no_e2e and nz == 1:
-        extractor = extractor_numbers(args, wl, K)
+        extractor = guarded("extractor", lambda: extractor_numbers(args, wl, K))
 
     # ---- the step after the scatter (f-3): BaseBEVBackbone on the tcgen05 convolution kernel ------------------------------------
     backbone = None
     if rank == 0 and world == 1 and not args.no_backbone and nz == 1 and nx % 8 == 0 and ny % 8 == 0:
-        backbone = backbone_numbers(args, wl, K)
+        backbone = guarded("backbone", lambda: backbone_numbers(args, wl, K))
 
     cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -604,7 +618,7 @@ def run_b200(args, rank, world, local_rank):
         cpu = {"value": r["sweeps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "points_per_sec": r["points_per_s"],
                "one_thread": {"value": r1["sweeps_per_s"], "cores": 1, "sample": r1["sample"]}}
-        eager = reference_eager_on_gpu(args.workload, nb, dev)
+        eager = guarded("reference eager on this GPU", lambda: reference_eager_on_gpu(args.workload, nb, dev))
 
     # ---- the other single-GPU configurations of BASELINE.json as short sub-lines (N = 1 only) ----------------------------------
     others = None
@@ -612,16 +626,21 @@ def run_b200(args, rank, world, local_rank):
         del enc, bufs, step
         torch.cuda.empty_cache()
         others = {}
-        for name in ("cfg3_10sweep_p32_b8", "cfg4_waymo64_pillar0.1_bev1024"):
+
+        def sub_line(name):
             w2 = Workload(name, 0, dev, rotate=2)
             e2 = encoder_numbers(w2, args, 0, 1, K=min(K, 10), R=5, lib=lib, n_streams=2)
             s2 = summarise(w2, e2, min(K, 10), 1, peak)
-            others[name] = {"value": s2["sweeps_per_s"], "unit": UNIT, "ms_per_step": s2["ms_per_step"],
-                            "points_per_sec": s2["points_per_s"], "frames": w2.nb, "grid": [w2.nx, w2.ny, w2.nz],
-                            "stages": {k: v for k, v in s2["stages"].items() if k != "timing"}, "steps": min(K, 10), "repeats": 5}
+            out = {"value": s2["sweeps_per_s"], "unit": UNIT, "ms_per_step": s2["ms_per_step"],
+                   "points_per_sec": s2["points_per_s"], "frames": w2.nb, "grid": [w2.nx, w2.ny, w2.nz],
+                   "stages": {k: v for k, v in s2["stages"].items() if k != "timing"}, "steps": min(K, 10), "repeats": 5}
+            del e2
             if name.startswith("cfg4"):
-                others[name]["pfn_64_64"] = two_layer_numbers(w2, args, min(K, 10), lib, peak)
-            del w2, e2
+                out["pfn_64_64"] = guarded("cfg4 [64,64]", lambda: two_layer_numbers(w2, args, min(K, 10), lib, peak))
+            return out
+
+        for name in ("cfg3_10sweep_p32_b8", "cfg4_waymo64_pillar0.1_bev1024"):
+            others[name] = guarded(name, lambda: sub_line(name))
             torch.cuda.empty_cache()
 
     if rank == 0:
