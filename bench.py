@@ -639,7 +639,7 @@ def run_b200(args, rank, world, local_rank):
                 out["pfn_64_64"] = guarded("cfg4 [64,64]", lambda: two_layer_numbers(w2, args, min(K, 10), lib, peak))
             return out
 
-        for name in ("cfg3_10sweep_p32_b8", "cfg4_waymo64_pillar0.1_bev1024"):
+        for name in ("cfg1_nuscenes32_b1", "cfg3_10sweep_p32_b8", "cfg4_waymo64_pillar0.1_bev1024"):
             others[name] = guarded(name, lambda: sub_line(name))
             torch.cuda.empty_cache()
 

@@ -121,12 +121,6 @@ __device__ __forceinline__ uint4 lds4u(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ float2 lds2(uint32_t addr)
-{
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ uint32_t lds1u(uint32_t addr)
 {
     uint32_t v;
@@ -181,17 +175,6 @@ __device__ __forceinline__ float2 max2(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 max3(float2 a, float2 b, float2 c)
 {
     return make_float2(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)));
-}
-
-__device__ __forceinline__ void point_step(const LaneWeights &w, const float4 a, const float t, float2 &acc)
-{
-    float2 y = mul2s(w.w0, a.x);
-    y = fma2s(w.w1, a.y, y);
-    y = fma2s(w.w2, a.z, y);
-    y = fma2s(w.w3, a.w, y);
-    y = fma2s(w.w4, t, y);
-    acc.x = fmaxf(acc.x, y.x);  // a NaN y (dropped point) leaves acc unchanged
-    acc.y = fmaxf(acc.y, y.y);
 }
 
 // points 1..n-1 of a pillar: two at a time (independent chains), the running max combined with a 3-input max
@@ -384,7 +367,15 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
 {
     const LaneWeights w = load_lane_weights(p.folded, lane);
     const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
-    const float qnan = __int_as_float(0x7fc00000);
+    // Pillars of up to 128 points (nearly all of them) keep their point indices in registers, 4 per lane: the radix select
+    // and both passes then run without touching the index column again (one round trip instead of one per digit and pass).
+    const bool small = n <= 128u;
+    uint32_t id0[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t j = q * 32u + lane;
+        id0[q] = (small && j < n) ? __ldg(&p.records[p0 + j].idx) : 0xFFFFFFFFu;
+    }
     uint32_t thr = 0xFFFFFFFFu;
     if (n > P) {
         // threshold = P-th smallest point index: the first P points in index order are kept.  Radix select with 8-bit digits:
@@ -395,9 +386,15 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
             sts4(s_hist + lane * 32u, make_float4(0.f, 0.f, 0.f, 0.f));
             sts4(s_hist + lane * 32u + 16, make_float4(0.f, 0.f, 0.f, 0.f));
             __syncwarp();
-            for (uint32_t j = lane; j < n; j += 32) {
-                const uint32_t v = __ldg(&p.records[p0 + j].idx);
-                if ((v & himask) == prefix) atoms_add(s_hist + ((v >> shift) & 255u) * 4u, 1);
+            if (small) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q * 32u + lane < n && (id0[q] & himask) == prefix) atoms_add(s_hist + ((id0[q] >> shift) & 255u) * 4u, 1);
+            } else {
+                for (uint32_t j = lane; j < n; j += 32) {
+                    const uint32_t v = __ldg(&p.records[p0 + j].idx);
+                    if ((v & himask) == prefix) atoms_add(s_hist + ((v >> shift) & 255u) * 4u, 1);
+                }
             }
             __syncwarp();
             const uint4 h0 = lds4u(s_hist + lane * 32u), h1 = lds4u(s_hist + lane * 32u + 16);  // bins 8*lane .. 8*lane+7
@@ -436,44 +433,70 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
         }
         thr = prefix;
     }
-    // one pass over the records: sums for the mean of the kept points (double: independent of the list order) and the
-    // running max.  32 records per sweep go through the warp's shared-memory scratch and are evaluated two at a time
-    // (independent FFMA2 chains); the next sweep's loads are issued before the current one is evaluated.
+    // The KEPT records (index <= thr; at most P of them when the cap binds, however long the pillar) are compacted into the
+    // warp's 32-record scratch and handed to `body` 32 at a time.  The scan reads only the 4-byte indices, 128 per round
+    // trip (4 independent loads per lane); the 32-byte records are fetched for kept points only.  (Before: every record of
+    // the pillar went through both layers and the dropped ones were discarded at the max -- a 1000-point pillar with
+    // P = 32 did 30x the work, and the drain of such pillars was the last 70-140 us of the two-layer kernel at cfg4 / cfg3.)
+    auto for_kept = [&](auto &&body) {
+        uint32_t fill = 0;
+        for (uint32_t k0 = 0; k0 < n; k0 += 128u) {
+            uint32_t id[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t j = k0 + q * 32u + lane;
+                id[q] = small ? id0[q] : (j < n ? __ldg(&p.records[p0 + j].idx) : 0xFFFFFFFFu);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t j = k0 + q * 32u + lane;
+                const bool keep = j < n && id[q] <= thr;
+                const unsigned kb = __ballot_sync(kFull, keep);
+                if (kb == 0u) continue;
+                const uint32_t k = __popc(kb);
+                if (fill + k > 32u) {
+                    cp_async_commit();
+                    cp_async_wait_all();
+                    __syncwarp();
+                    body(fill);
+                    __syncwarp();
+                    fill = 0;
+                }
+                if (keep) {  // global -> shared without registers: the kept records of a batch are all in flight together
+                    const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + j);
+                    const uint32_t dst = s_hist + (fill + __popc(kb & ((1u << lane) - 1u))) * 32u;
+                    cp_async16(dst, src, 16);
+                    cp_async16(dst + 16, src + 1, 16);
+                }
+                fill += k;
+            }
+        }
+        if (fill) {
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncwarp();
+            body(fill);
+            __syncwarp();
+        }
+    };
+    // pass 1: sums for the mean of the kept points (double: independent of the list order) and the running max of layer 0,
+    // two records at a time (independent FFMA2 chains)
     double sx = 0.0, sy = 0.0, sz = 0.0;
     float2 acc = make_float2(-INFINITY, -INFINITY);
-    float4 u = make_float4(qnan, 0.f, 0.f, 0.f), v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < n) {
-        const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + lane);
-        u = __ldg(src);
-        v = __ldg(src + 1);
-    }
-    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-        const uint32_t cnt = min(32u, n - k0);
+    for_kept([&](uint32_t cnt) {
         if (lane < cnt) {
-            if (__float_as_uint(v.z) > thr) {
-                u.x = qnan;
-            } else {
-                sx += static_cast<double>(u.x);
-                sy += static_cast<double>(u.y);
-                sz += static_cast<double>(u.z);
-            }
-        } else {
-            u.x = qnan;
+            const float4 a = lds4(s_hist + lane * 32u);
+            sx += static_cast<double>(a.x);
+            sy += static_cast<double>(a.y);
+            sz += static_cast<double>(a.z);
         }
-        sts4(s_hist + lane * 32u, u);
-        sts4(s_hist + lane * 32u + 16, v);
-        if (k0 + 32u + lane < n) {
-            const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + k0 + 32u + lane);
-            u = __ldg(src);
-            v = __ldg(src + 1);
-        }
-        __syncwarp();
-        for (uint32_t k = 0; k < cnt; k += 2) {  // an odd count ends on a NaN record, which the max ignores
+        uint32_t k = 0;
+        for (; k + 1u < cnt; k += 2) {
             const float2 ya = point_eval(w, s_hist + k * 32u), yb = point_eval(w, s_hist + k * 32u + 32u);
             acc = max3(acc, ya, yb);
         }
-        __syncwarp();
-    }
+        if (k < cnt) acc = max2(acc, point_eval(w, s_hist + k * 32u));
+    });
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         sx += __shfl_xor_sync(kFull, sx, s);
@@ -499,22 +522,10 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
         __syncwarp();
         const float2 cst = layer1_const(p.folded2 + 2048, s_x + 3u * kXBytes, l1.sh, lane);
         float2 best = make_float2(-INFINITY, -INFINITY);
-        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-            const uint32_t cnt = min(32u, n - k0);
-            u = make_float4(qnan, 0.f, 0.f, 0.f);
-            v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < cnt) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.records + p0 + k0 + lane);
-                u = __ldg(src);
-                v = __ldg(src + 1);
-                if (__float_as_uint(v.z) > thr) u.x = qnan;
-            }
-            __syncwarp();  // the previous sweep has been read
-            sts4(s_hist + lane * 32u, u);
-            sts4(s_hist + lane * 32u + 16, v);
-            __syncwarp();
-            best = layer1_points(w, l1.wa, kc, cst, s_hist, cnt, s_x, lane, best);
-        }
+        if (min(n, P) <= 32u)  // the kept records are still in the scratch, compacted by pass 1
+            best = layer1_points(w, l1.wa, kc, cst, s_hist, min(n, P), s_x, lane, best);
+        else
+            for_kept([&](uint32_t cnt) { best = layer1_points(w, l1.wa, kc, cst, s_hist, cnt, s_x, lane, best); });
         if (padded) best = max2(best, add2(l1.upad, cst));
         if (row >= 0)
             asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(out_lane + static_cast<unsigned long long>(static_cast<uint32_t>(row)) * 256ull),
@@ -585,10 +596,22 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     // chunk costs 5-10x more arithmetic, and 2.5x more when its pillars hold one point each; static ranges left the last
     // warp running at 196 us when the first was done at 18 us): there every chunk comes from the cursor.
     const uint32_t gw = blockIdx.x * kWarps + warp, n_warps = gridDim.x * kWarps;
+    // Bulk phase: the cursor is read one chunk ahead (lane 0 keeps the reply of the atomic issued a chunk earlier) and the
+    // next window is fetched during the current chunk, so a warp never waits for either round trip.  Tail phase (the last
+    // 3 chunks per warp of the grid, two-layer stacks only): a chunk reserved ahead would sit idle behind a 16 us chunk while
+    // other warps run dry -- with read-ahead everywhere the last warp finished at 142 us when the cursor ran out at 96 us --
+    // so there a warp asks for its next chunk only when it is done with the current one.
+    // A warp leaves only on an index >= n_chunks, and what it holds ahead is larger still.
+    const uint32_t bulk_end = kTwo ? (n_chunks > 3u * n_warps ? n_chunks - 3u * n_warps : 0u) : 0xFFFFFFFFu;
+    uint32_t ahead = 0;
+    bool primed = false;
     auto grab = [&]() {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(p.chunk_cursor, 1u) + 1u;  // the cursor starts at 0xFFFFFFFF
-        return __shfl_sync(kFull, i, 0);
+        if (!kTwo && p.pool_256 == 0u) return 0x7FFFFFFFu;  // no pool: nothing to wait for
+        if (!primed && lane == 0) ahead = atomicAdd(p.chunk_cursor, 1u) + 1u;  // the cursor starts at 0xFFFFFFFF
+        const uint32_t i = __shfl_sync(kFull, ahead, 0);
+        primed = i < bulk_end;
+        if (primed && lane == 0) ahead = atomicAdd(p.chunk_cursor, 1u) + 1u;
+        return i;
     };
     const uint32_t n_static = kTwo ? 0u : n_chunks - static_cast<uint32_t>((static_cast<unsigned long long>(n_chunks) * p.pool_256) >> 8);
     uint32_t cur = static_cast<uint32_t>(static_cast<unsigned long long>(n_static) * gw / n_warps);
@@ -634,11 +657,14 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     while (true) {
         // the next chunk's loads fly during this chunk's arithmetic
         uint32_t nxt = cur + 1u;
-        if (pooled || nxt >= c_end) {
-            pooled = true;
-            nxt = n_static + grab();
+        const bool lazy = kTwo && cur >= bulk_end;  // tail phase: ask for the next chunk after this one
+        if (!lazy) {
+            if (pooled || nxt >= c_end) {
+                pooled = true;
+                nxt = n_static + grab();
+            }
+            if (nxt < n_chunks) fetch(nxt, buf ^ 1u);
         }
-        if (nxt < n_chunks) fetch(nxt, buf ^ 1u);
         cp_async_commit();
         const uint32_t rs = s_warp + buf * kBufBytes;  // window: 64 consecutive positions starting at chunk cur
         const uint32_t ms = rs + kRecBytes;
@@ -758,6 +784,11 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
                 pillar_store(w, kc_a, __float_as_int(m4a.w), static_cast<int>(nba) < 0, acc_a, out_lane);
                 if (has_b) pillar_store(w, kc_b, __float_as_int(m4b.w), static_cast<int>(nbb) < 0, acc_b, out_lane);
             }
+        }
+        if (lazy) {
+            nxt = n_static + grab();
+            if (nxt < n_chunks) fetch(nxt, buf ^ 1u);
+            cp_async_commit();
         }
         cp_async_wait_all();
         __syncwarp();
