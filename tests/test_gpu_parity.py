@@ -319,7 +319,7 @@ def test_fused_huge_pillar_spanning_chunks(feature_kernel, grouping, dev, L, ora
                            r.uniform(0, 0.5, (6000, 1))], 1).astype(np.float32)
     pts = np.concatenate([big, rest])[r.permutation(26000)]
     offs = np.array([0, 9000, 9000, 26000], np.int32)
-    for p_max in (32, 5):
+    for p_max in (32, 5, 100):  # 100: more kept points than the long-pillar path's 32-record scratch holds at once
         grid = L.GridSpec.from_range(rng, vs, p_max, 60)
         sd = oracle.random_pfn_params(11, [64], True, seed=13)
         res = _run_fused(L, dev, pts, offs, grid, sd, 5)
@@ -1062,3 +1062,43 @@ def test_two_layer_stack_with_buffers_ring_and_reproducibility(dev, L):
         torch.cuda.synchronize()
         assert torch.equal(bd["pillar_features"][:m], ref["pillar_features"][:m])
         assert torch.equal(bd["spatial_features"], ref["bev"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c_point", [5, 4])
+def test_two_layer_huge_pillar_and_caps(c_point, dev, L, oracle):
+    """NUM_FILTERS [64, 64] on the streaming kernel where its long-pillar path matters: one cell with 20 000 points next to
+    ordinary pillars, P = 5 (cap binds inside the window), 32 and 100 (more kept points than one scratch batch: the
+    compaction flushes), 5- and 4-channel points; grouping bit-exact, rows rtol 1e-3 vs the CPU oracle."""
+    from lidar_vision_vqa_b200 import ops
+
+    rng, vs = (0.0, 0.0, 0.0, 8.0, 8.0, 2.0), (1.0, 1.0, 2.0)
+    r = np.random.default_rng(12)
+    big = np.concatenate([r.uniform(3.0, 4.0, (20000, 2)), r.uniform(0, 2, (20000, 1)), r.uniform(0, 255, (20000, 1)),
+                          r.uniform(0, 0.5, (20000, 1))], 1).astype(np.float32)
+    mid = np.concatenate([r.uniform(5.0, 6.0, (70, 2)), r.uniform(0, 2, (70, 1)), r.uniform(0, 255, (70, 1)),
+                          r.uniform(0, 0.5, (70, 1))], 1).astype(np.float32)  # a 70-point pillar: indices stay in registers
+    rest = np.concatenate([r.uniform(-1, 9, (6000, 2)), r.uniform(-0.5, 2.5, (6000, 1)), r.uniform(0, 255, (6000, 1)),
+                           r.uniform(0, 0.5, (6000, 1))], 1).astype(np.float32)
+    pts = np.ascontiguousarray(np.concatenate([big, mid, rest])[r.permutation(26070)][:, :c_point])
+    offs = np.array([0, 9000, 9000, 26070], np.int32)
+    sd = oracle.random_pfn_params(c_point + 6, [64, 64], True, seed=14)
+    layers = []
+    for i in range(2):
+        bn = tuple(torch.as_tensor(sd[f"pfn_layers.{i}.norm.{k}"]) for k in ("weight", "bias", "running_mean", "running_var")) + (1e-3,)
+        layers.append((torch.as_tensor(sd[f"pfn_layers.{i}.linear.weight"]), bn, None))
+    for p_max in (5, 32, 100):
+        grid = L.GridSpec.from_range(rng, vs, p_max, 60)
+        stack = ops.fold_pfn_stack(layers, c_point=c_point, use_absolute_xyz=True, with_distance=False,
+                                   voxel_size=grid.voxel_size, point_cloud_range=grid.point_cloud_range, device=dev)
+        res = ops.encode_stack(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), grid, stack, with_bev=True)
+        m = int(res["pillar_count"][-1].item())
+        ref_v = oracle.voxelize_batch(pts, offs, rng, vs, p_max, 60)
+        assert m == ref_v["coords"].shape[0]
+        np.testing.assert_array_equal(res["voxel_coords"][:m].cpu().numpy(), ref_v["coords"])
+        np.testing.assert_array_equal(res["voxel_num_points"][:m].cpu().numpy(), ref_v["num_points"])
+        ref_f = oracle.pillar_vfe(ref_v["voxels"], ref_v["num_points"], ref_v["coords"], sd, vs, rng).numpy()
+        got_f = res["pillar_features"][:m].cpu().numpy()
+        np.testing.assert_allclose(got_f, ref_f, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+        nx, ny, _ = grid.grid_size
+        np.testing.assert_array_equal(res["bev"].cpu().numpy(), oracle.scatter_bev(got_f, ref_v["coords"], nx, ny, batch_size=3))
