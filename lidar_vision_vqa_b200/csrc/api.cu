@@ -472,8 +472,21 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     const bool fast2 = fast_env && !dynamic && sd.n_layers == 2 && sd.out[0] == 32 && sd.out[1] == 64 && sd.layout == 0 &&
                        sd.use_abs && !sd.with_dist && stack->c_point <= 5 && coords_cols == 4 && grid->grid[0] <= 0xFFFF &&
                        grid->grid[1] <= 0xFFFF && n > 0;
+    // DynamicPillarVFE (dynamic_pillar_vfe.py:14-142) with NUM_FILTERS [64] or [64, 64] in the standard layout: the same
+    // streaming kernels in their dynamic variant; the pillar entries get their rows (sorted-key order) from
+    // launch_dynamic_rows between the grouping and the feature kernel.
+    const bool fast_dyn = fast_env && dynamic && sd.layout == 0 && sd.use_abs && !sd.with_dist && stack->c_point <= 5 &&
+                          coords_cols == 4 && grid->grid[0] <= 0xFFFF && grid->grid[1] <= 0xFFFF && n > 0 &&
+                          ((sd.n_layers == 1 && sd.out[0] == 64) || (sd.n_layers == 2 && sd.out[0] == 32 && sd.out[1] == 64));
     PlaceExtras px{};
     px.capacity = out->pillar_capacity;
+    if (fast_dyn) {
+        px.records = true;
+        for (int i = 0; i < 3; ++i) {
+            px.vsz[i] = grid->voxel[i];
+            px.off[i] = sd.off[i];
+        }
+    }
     if (fast2) {
         px.records = true;
         for (int i = 0; i < 3; ++i) {
@@ -485,10 +498,14 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
         px.write_cell_row = want_bev || out->want_index_map;
     }
     if ((e = launch_group_points(points, n, row_stride, col0, stack->c_point, frame_offsets, n_frames, gd, ws,
-                                 out->pillar_count, /*want_index_lists=*/!fast2, px, st)) != cudaSuccess)
+                                 out->pillar_count, /*want_index_lists=*/!fast2 && !fast_dyn, px, st)) != cudaSuccess)
         return cuda_fail(e, "group_points");
     stage_mark(1, st);
-    if (fast2) {
+    if (fast_dyn &&
+        (e = launch_dynamic_rows(gd, ws, n_frames, n, out->pillar_capacity, out->voxel_coords, out->voxel_num_points, st)) != cudaSuccess)
+        return cuda_fail(e, "dynamic_rows");
+    if (fast2 || fast_dyn) {
+        const bool two = sd.n_layers == 2;
         PfnDev l0{};
         l0.weight = sd.weight[0];
         l0.scale = sd.scale[0];
@@ -497,21 +514,22 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
             l0.off[i] = sd.off[i];
             l0.vsz[i] = sd.vsz[i];
         }
-        if ((e = launch_fold_pfn(l0, stack->c_point, stack_c_in(sd, stack->c_point), ws.folded, st, 32)) != cudaSuccess)
+        if ((e = launch_fold_pfn(l0, stack->c_point, stack_c_in(sd, stack->c_point), ws.folded, st, two ? 32 : 64)) != cudaSuccess)
             return cuda_fail(e, "fold_pfn");
-        if ((e = launch_fold_pfn2(sd.weight[1], sd.scale[1], sd.shift[1], ws.folded2, st)) != cudaSuccess)
+        if (two && (e = launch_fold_pfn2(sd.weight[1], sd.scale[1], sd.shift[1], ws.folded2, st)) != cudaSuccess)
             return cuda_fail(e, "fold_pfn2");
         FastJob fj{};
+        fj.dynamic = fast_dyn;
         fj.n = n;
         fj.idx_bits = idx_bits_for(n > 1 ? n : 2);
         fj.pillar_features = out->pillar_features;
-        fj.folded2 = ws.folded2;
+        fj.folded2 = two ? ws.folded2 : nullptr;
         for (int i = 0; i < 3; ++i) {
             fj.vsz[i] = grid->voxel[i];
             fj.off[i] = sd.off[i];
         }
         if ((e = launch_pillar_features_stream(fj, ws.folded, gd, ws, st)) != cudaSuccess)
-            return cuda_fail(e, "pillar_features_stream (two layers)");
+            return cuda_fail(e, "pillar_features_stream (stack)");
     }
     MultiJob job{};
     job.points = points;
@@ -528,7 +546,8 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     job.voxel_num_points = out->voxel_num_points;
     job.coords_cols = coords_cols;
     job.capacity = out->pillar_capacity;
-    if (!fast2 && (e = launch_pfn_multi_lists(job, sd, gd, ws, st)) != cudaSuccess) return cuda_fail(e, "pfn_multi");
+    if (!fast2 && !fast_dyn && (e = launch_pfn_multi_lists(job, sd, gd, ws, st)) != cudaSuccess)
+        return cuda_fail(e, "pfn_multi");
     stage_mark(2, st);
     if (want_bev) {
         const int f_last = sd.out[sd.n_layers - 1];

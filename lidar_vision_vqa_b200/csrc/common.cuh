@@ -316,6 +316,7 @@ struct FastJob {
     float *pillar_features;
     float vsz[3], off[3];  // pillar centre = coord * vsz + off (pillar_vfe.py:79-81,101-103)
     const float *folded2;  // two-layer stack [64, 64]: launch_fold_pfn2's table, else NULL
+    bool dynamic;          // DynamicPillarVFE semantics (rows patched into the pillar entries by launch_dynamic_rows)
 };
 // The streaming feature kernel (pfn_stream.cu) and the folding of one PFN layer into its table:
 //   rows 0-4   per point   scale * (W_p + W_cluster + W_centre) for x,y,z;  scale * W for intensity, time
@@ -353,6 +354,13 @@ struct MultiJob {
 };
 int stack_c_in(const StackDev &sd, int c_point);
 bool stack_supported(const StackDev &sd, int c_point);
+// Dynamic variant, after the grouping: ranks every occupied cell in (b, ix, iy) order (the order torch.unique gives the merged
+// key, dynamic_pillar_vfe.py:99-103) into the index-map region of the workspace (entry = rank | occupied << 31).
+cudaError_t launch_dynamic_ranks(const GridDev &gd, const Workspace &ws, int nb, int64_t n, cudaStream_t st);
+// ... and, for the streaming feature kernel, writes that rank as the row of every pillar entry (0xFFFFFFFF beyond `capacity`)
+// together with voxel_coords (b, 0, y, x) and the uncapped voxel_num_points of the row.
+cudaError_t launch_dynamic_rows(const GridDev &gd, const Workspace &ws, int nb, int64_t n, int64_t capacity,
+                                int32_t *voxel_coords, int32_t *voxel_num_points, cudaStream_t st);
 cudaError_t launch_pfn_multi_lists(const MultiJob &job, const StackDev &sd, const GridDev &gd, const Workspace &ws,
                                    cudaStream_t st);
 cudaError_t launch_pfn_multi_dense(const float *voxels, const void *num_points, bool np_float, const void *coords,

@@ -792,6 +792,59 @@ bool stack_supported(const StackDev &sd, int c_point)
     return sd.out[0] >= 1 && sd.out[0] <= 32 && sd.out[1] >= 1 && sd.out[1] <= kMaxOut;
 }
 
+cudaError_t launch_dynamic_ranks(const GridDev &gd, const Workspace &ws, int nb, int64_t n, cudaStream_t st)
+{
+    // the index-map region of the workspace holds the (b, ix, iy)-ordered occupancy, then the ranks
+    uint32_t *occ = reinterpret_cast<uint32_t *>(ws.cell_row);
+    const int64_t n_cells = static_cast<int64_t>(nb) * gd.cells_xy;
+    const int n_blocks = static_cast<int>((n_cells + kScanBlock - 1) / kScanBlock);
+    uint32_t *block_sum = ws.scan_scratch;
+    cudaError_t e = cudaMemsetAsync(occ, 0, sizeof(uint32_t) * n_cells, st);
+    if (e != cudaSuccess) return e;
+    note_launch();
+    const unsigned mb = static_cast<unsigned>((n + 255) / 256);
+    k_mark_cells<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, gd, occ);
+    k_block_counts<<<n_blocks, 256, 0, st>>>(occ, n_cells, block_sum);
+    k_scan_block_sums<<<1, 1024, 0, st>>>(block_sum, n_blocks);
+    k_apply_ranks<<<n_blocks, 256, 0, st>>>(occ, n_cells, block_sum);
+    note_launch(4);
+    return cudaGetLastError();
+}
+
+// one thread per pillar (grouping order): row = rank of its cell; patches the pillar entry the streaming kernel reads
+__global__ void k_dynamic_rows(const Header *__restrict__ hdr, const uint32_t *__restrict__ pillar_key,
+                               const uint32_t *__restrict__ pillar_list, const uint32_t *__restrict__ pillar_cnt, GridDev gd,
+                               const uint32_t *__restrict__ occ, int64_t capacity, uint4 *__restrict__ pillar_meta,
+                               int32_t *__restrict__ voxel_coords, int32_t *__restrict__ voxel_num_points)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= hdr->total_pillars) return;
+    const uint32_t key = pillar_key[g];
+    const uint32_t b = key / gd.cells, cell = key - b * gd.cells;  // nz == 1 in this mode
+    const uint32_t y = cell / static_cast<uint32_t>(gd.g[0]), x = cell - y * static_cast<uint32_t>(gd.g[0]);
+    const uint32_t row = occ[static_cast<size_t>(b) * gd.cells_xy + static_cast<size_t>(x) * gd.g[1] + y] & 0x7FFFFFFFu;
+    const bool live = static_cast<int64_t>(row) < capacity;
+    reinterpret_cast<uint32_t *>(pillar_meta + pillar_list[g])[1] = live ? row : 0xFFFFFFFFu;
+    if (!live) return;
+    if (voxel_coords)
+        *reinterpret_cast<int4 *>(voxel_coords + static_cast<size_t>(row) * 4) =
+            make_int4(static_cast<int>(b), 0, static_cast<int>(y), static_cast<int>(x));
+    if (voxel_num_points) voxel_num_points[row] = static_cast<int32_t>(pillar_cnt[g]);
+}
+
+cudaError_t launch_dynamic_rows(const GridDev &gd, const Workspace &ws, int nb, int64_t n, int64_t capacity,
+                                int32_t *voxel_coords, int32_t *voxel_num_points, cudaStream_t st)
+{
+    cudaError_t e = launch_dynamic_ranks(gd, ws, nb, n, st);
+    if (e != cudaSuccess) return e;
+    const unsigned mb = static_cast<unsigned>((n + 255) / 256);
+    k_dynamic_rows<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, ws.pillar_list, ws.pillar_cnt, gd,
+                                       reinterpret_cast<const uint32_t *>(ws.cell_row), capacity, ws.pillar_meta, voxel_coords,
+                                       voxel_num_points);
+    note_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pfn_multi_lists(const MultiJob &job, const StackDev &sd, const GridDev &gd, const Workspace &ws,
                                    cudaStream_t st)
 {
@@ -822,22 +875,9 @@ cudaError_t launch_pfn_multi_lists(const MultiJob &job, const StackDev &sd, cons
     p.cell_row = (!job.dynamic && job.write_cell_row) ? ws.cell_row : nullptr;
 
     if (job.dynamic) {
-        // the index-map region of the workspace holds the (b, ix, iy)-ordered occupancy, then the ranks
-        uint32_t *occ = reinterpret_cast<uint32_t *>(ws.cell_row);
-        const int64_t n_cells = static_cast<int64_t>(job.nb) * gd.cells_xy;
-        const int n_blocks = static_cast<int>((n_cells + kScanBlock - 1) / kScanBlock);
-        uint32_t *block_sum = ws.scan_scratch;
-        cudaError_t e = cudaMemsetAsync(occ, 0, sizeof(uint32_t) * n_cells, st);
+        cudaError_t e = launch_dynamic_ranks(gd, ws, job.nb, job.n, st);
         if (e != cudaSuccess) return e;
-        note_launch();
-        const unsigned mb = static_cast<unsigned>((job.n + 255) / 256);
-        k_mark_cells<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, gd, occ);
-        k_block_counts<<<n_blocks, 256, 0, st>>>(occ, n_cells, block_sum);
-        k_scan_block_sums<<<1, 1024, 0, st>>>(block_sum, n_blocks);
-        k_apply_ranks<<<n_blocks, 256, 0, st>>>(occ, n_cells, block_sum);
-        note_launch(4);
-        p.rank_xmajor = occ;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        p.rank_xmajor = reinterpret_cast<uint32_t *>(ws.cell_row);
     }
     int64_t blocks = (job.n + kWarps - 1) / kWarps;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;

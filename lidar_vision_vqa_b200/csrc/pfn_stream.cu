@@ -361,12 +361,15 @@ __device__ __forceinline__ float2 layer1_points(const LaneWeights &w, const floa
 
 // A pillar of more than 32 points: straight from global memory, the whole warp on one pillar (rare: it reloads the lane's
 // weights instead of taking them from the caller, so that the caller's copy never needs an address).
-template <bool kTwo>
+template <bool kTwo, bool kDyn>
 __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, uint32_t s_x, uint32_t p0, uint32_t n, int row,
                                          float cx, float cy, float cz, unsigned long long out_lane, int lane)
 {
     const LaneWeights w = load_lane_weights(p.folded, lane);
-    const uint32_t P = static_cast<uint32_t>(p.gd.max_points);
+    const uint32_t P = static_cast<uint32_t>(p.gd.max_points);  // 0x7FFFFFFF in the dynamic variant: nothing is dropped
+    // dynamic variant: the row (rank of the cell in sorted-key order) was patched into the pillar's entry after the grouping
+    if constexpr (kDyn) row = static_cast<int>(__ldcg(reinterpret_cast<const uint32_t *>(p.pillar_meta + p0) + 1));
+    const bool has_pad = !kDyn && n < P;  // the dynamic variant has no padded slots (dynamic_pillar_vfe.py:48-53)
     // Pillars of up to 128 points (nearly all of them) keep their point indices in registers, 4 per lane: the radix select
     // and both passes then run without touching the index column again (one round trip instead of one per digit and pass).
     const bool small = n <= 128u;
@@ -508,11 +511,11 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
     const float4 m4 = make_float4(rel_mean(cx, static_cast<float>(sx) * rn), rel_mean(cy, static_cast<float>(sy) * rn),
                                   rel_mean(cz, static_cast<float>(sz) * rn), __int_as_float(row));
     if constexpr (!kTwo) {
-        pillar_finish(w, c4, m4, n < P, acc, out_lane);
+        pillar_finish(w, c4, m4, has_pad, acc, out_lane);
     } else {
         // two layers: the pillar-wise max of layer 0 -> layer 1's constant, then a second pass over the records
         const Layer1 l1 = load_layer1(p.folded, p.folded2, lane);
-        const bool padded = n < P;
+        const bool padded = has_pad;
         const float2 kc = pillar_const(w, c4, m4);
         float2 m = add2(acc, kc);
         m.x = fmaxf(m.x, padded ? w.rsh.x : 0.f);
@@ -537,7 +540,7 @@ __device__ __noinline__ void long_pillar(const WalkParams &p, uint32_t s_hist, u
 // Pillars of more than 32 points, listed by the grouping stage: every warp, once its own chunks are done, takes entries
 // from the list through one grid-wide cursor, so the long tail is spread over the whole machine instead of serialising the
 // warps whose chunks happen to contain it.
-template <bool kTwo>
+template <bool kTwo, bool kDyn>
 __device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t s_hist, uint32_t s_x, unsigned long long out_lane,
                                                    int lane)
 {
@@ -552,7 +555,7 @@ __device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t
         const float cx = __fadd_rn(__fmul_rn(static_cast<float>(e0.w & 0xFFFFu), p.vsz[0]), p.off[0]);
         const float cy = __fadd_rn(__fmul_rn(static_cast<float>(e0.w >> 16), p.vsz[1]), p.off[1]);
         const float cz = __fadd_rn(__fmul_rn(static_cast<float>(e1.x), p.vsz[2]), p.off[2]);
-        long_pillar<kTwo>(p, s_hist, s_x, e0.x, e0.y, static_cast<int>(e0.z), cx, cy, cz, out_lane, lane);
+        long_pillar<kTwo, kDyn>(p, s_hist, s_x, e0.x, e0.y, static_cast<int>(e0.z), cx, cy, cz, out_lane, lane);
     }
 }
 
@@ -563,11 +566,15 @@ __device__ __forceinline__ void drain_long_pillars(const WalkParams &p, uint32_t
 // the lane's 2 x 32 weights in registers, x_p broadcast from shared memory; padded slots contribute one row with
 // x = relu(shift0) (NOT re-masked between the layers, as in the reference).  Pillars of more than 32 points: long_pillar<true>
 // makes a second pass over the records.
-template <int kWarps, int kMinBlocks, bool kTwo = false>
+// kDyn: DynamicPillarVFE / PFNLayerV2 semantics (dynamic_pillar_vfe.py:14-142): no cap and no padded slots, z neither range
+// checked nor part of the cell, so z - z_offset is unbounded: its sum for the mean is a 64-bit fixed-point shared-memory
+// atomic (2^-20 m); rows come from the pillar entries as patched by launch_dynamic_rows (sorted-key order).
+template <int kWarps, int kMinBlocks, bool kTwo = false, bool kDyn = false>
 __global__ void __launch_bounds__(32 * kWarps, kMinBlocks)
 k_pillar_walk(const __grid_constant__ WalkParams p)
 {
-    constexpr uint32_t kStride = kTwo ? kWarpSmemTwo : kWarpSmem;
+    constexpr uint32_t kOffZ64 = kTwo ? kWarpSmemTwo : kWarpSmem;  // dynamic variant: 32 x 8 bytes of z sums
+    constexpr uint32_t kStride = kOffZ64 + (kDyn ? 256u : 0u);
     __shared__ __align__(16) unsigned char s_all[kWarps * kStride];
     __shared__ __align__(16) float s_w1b[kTwo ? 32 * 64 : 4];
 
@@ -644,7 +651,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         l1 = load_layer1(p.folded, p.folded2, lane);
     }
     if (cur >= n_chunks) {
-        drain_long_pillars<kTwo>(p, s_pl, s_x, out_lane, lane);
+        drain_long_pillars<kTwo, kDyn>(p, s_pl, s_x, out_lane, lane);
         return;
     }
     fetch(cur, 0);
@@ -680,6 +687,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
             sts1(s_sum + lane * 4u, 0u);
             sts1(s_sum + 128u + lane * 4u, 0u);
             sts1(s_sum + 256u + lane * 4u, 0u);
+            if constexpr (kDyn) asm volatile("st.shared.u64 [%0], %1;" ::"r"(s_warp + kOffZ64 + lane * 8u), "l"(0ull) : "memory");
             __syncwarp();
             // every position adds itself to the sums of its pillar (when that pillar starts in this chunk and fits the
             // window); positions beyond the first-P cap are found by rank counting and become NaN
@@ -699,7 +707,12 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
                     const float4 q = lds4(rs + j * 32u);
                     atoms_add(s_sum + slot * 4u, __float2int_rn(q.x * p.fx_scale[0]));
                     atoms_add(s_sum + 128u + slot * 4u, __float2int_rn(q.y * p.fx_scale[1]));
-                    atoms_add(s_sum + 256u + slot * 4u, __float2int_rn(q.z * p.fx_scale[2]));
+                    if constexpr (kDyn)
+                        asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(s_warp + kOffZ64 + slot * 8u),
+                                     "l"(static_cast<unsigned long long>(__float2ll_rn(q.z * 1048576.f)))
+                                     : "memory");
+                    else
+                        atoms_add(s_sum + 256u + slot * 4u, __float2int_rn(q.z * p.fx_scale[2]));
                 } else {
                     sts1(rs + j * 32u, __float_as_uint(qnan));
                 }
@@ -722,9 +735,16 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
                     const float rn = kRcp[min(n, P)];
                     const float mx = static_cast<float>(static_cast<int>(lds1u(s_sum + lane * 4u))) * p.fx_inv[0] * rn;
                     const float my = static_cast<float>(static_cast<int>(lds1u(s_sum + 128u + lane * 4u))) * p.fx_inv[1] * rn;
-                    const float mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
+                    float mz;
+                    if constexpr (kDyn) {
+                        long long zs;
+                        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(zs) : "r"(s_warp + kOffZ64 + lane * 8u));
+                        mz = __ll2float_rn(zs) * 9.5367431640625e-07f * rn;  // 2^-20
+                    } else {
+                        mz = static_cast<float>(static_cast<int>(lds1u(s_sum + 256u + lane * 4u))) * p.fx_inv[2] * rn;
+                    }
                     // n with bit 31 set when the pillar has empty (padded) slots
-                    sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, __uint_as_float(n | (n < P ? 0x80000000u : 0u))));
+                    sts4(s_pl + lane * 32u, make_float4(cx, cy, cz, __uint_as_float(n | (!kDyn && n < P ? 0x80000000u : 0u))));
                     sts4(s_pl + lane * 32u + 16, make_float4(rel_mean(cx, mx), rel_mean(cy, my), rel_mean(cz, mz),
                                                              __uint_as_float(me.y)));
                 }
@@ -800,7 +820,7 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
         dbg_stamp(p.dbg, 21);  // chunks done (latest warp)
         dbg_stamp(p.dbg, 22);  // (earliest warp)
     }
-    drain_long_pillars<kTwo>(p, s_pl, s_x, out_lane, lane);
+    drain_long_pillars<kTwo, kDyn>(p, s_pl, s_x, out_lane, lane);
     if (lane == 0) {
         dbg_stamp(p.dbg, 23);
         dbg_stamp(p.dbg, 24);
@@ -917,6 +937,15 @@ cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folde
     if (warps > wave) warps = wave;
     const unsigned grid = static_cast<unsigned>((warps + kWarps - 1) / kWarps);
     cudaError_t err;
+    if (job.dynamic) {  // DynamicPillarVFE (one or two layers)
+        const unsigned g2 = static_cast<unsigned>((tmin<int64_t>((chunks + 1) / 2, static_cast<int64_t>(sms) * 3 * kWarps) + kWarps - 1) / kWarps);
+        err = job.folded2 ? launch_pdl(k_pillar_walk<kWarps, 3, true, true>, dim3(g2), dim3(32 * kWarps), 0, st, p)
+                          : launch_pdl(k_pillar_walk<kWarps, 5, false, true>, dim3(static_cast<unsigned>((tmin<int64_t>((chunks + 1) / 2, static_cast<int64_t>(sms) * 5 * kWarps) + kWarps - 1) / kWarps)),
+                                       dim3(32 * kWarps), 0, st, p);
+        if (err != cudaSuccess) return err;
+        note_launch();
+        return cudaGetLastError();
+    }
     if (job.folded2) {  // two-layer stack: 64 more weight registers per lane
         err = launch_pdl(k_pillar_walk<kWarps, 3, true>, dim3(static_cast<unsigned>((tmin<int64_t>((chunks + 1) / 2, static_cast<int64_t>(sms) * 3 * kWarps) + kWarps - 1) / kWarps)),
                          dim3(32 * kWarps), 0, st, p);
