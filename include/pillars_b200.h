@@ -205,6 +205,8 @@ int pillars_pfn_dense_stack(const float *voxels, const void *num_points, int32_t
                             const pillars_pfn_stack_t *stack, const float voxel_size[3], float *out, void *stream);
 
 /* Raw points -> pillar features (+ BEV in mode HARD when out->bev is set) through a feature stack.
+ * NUM_FILTERS [64, 64] (mode HARD) and [64] / [64, 64] (mode DYNAMIC, 4-column coords) in the standard feature layout
+ * (absolute xyz, no distance, <= 5 point channels) run on the streaming feature kernel; every other stack on the general one.
  * coords_cols: 4 writes out->voxel_coords as (b,z,y,x) -- (b,0,y,x) in mode DYNAMIC, dynamic_pillar_vfe.py:132-138;
  *              3 writes (b,y,x), the `pillar_coords` of DynamicPillarVFESimple2D (:232-238).
  * In mode DYNAMIC grid->max_points / max_voxels are ignored and out->voxel_num_points receives the uncapped counts. */
