@@ -443,8 +443,8 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
         return fail(PILLARS_E_UNSUPPORTED, "membership outputs come from pillars_voxelize");
     const bool dynamic = mode == PILLARS_MODE_DYNAMIC;
     const bool want_bev = out->bev != nullptr || out->bev_half != nullptr;
-    if (want_bev && (dynamic || grid->grid[2] != 1 || coords_cols != 4))
-        return fail(PILLARS_E_UNSUPPORTED, "the fused BEV canvas needs mode HARD, nz == 1 and 4-column coords");
+    if ((want_bev || out->want_index_map) && (dynamic || grid->grid[2] != 1 || coords_cols != 4))
+        return fail(PILLARS_E_UNSUPPORTED, "the fused BEV canvas / index map needs mode HARD, nz == 1 and 4-column coords");
     if (out->pillar_capacity < 0) return fail(PILLARS_E_BADARG, "pillar_capacity < 0");
     const int64_t cells_xy = static_cast<int64_t>(grid->grid[0]) * grid->grid[1];
     if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
@@ -540,7 +540,7 @@ int pillars_encode_stack(const float *points, int64_t n, int32_t row_stride, int
     job.nb = n_frames;
     job.idx_bits = idx_bits_for(n > 1 ? n : 2);
     job.dynamic = dynamic;
-    job.write_cell_row = want_bev;
+    job.write_cell_row = want_bev || out->want_index_map;
     job.pillar_features = out->pillar_features;
     job.voxel_coords = out->voxel_coords;
     job.voxel_num_points = out->voxel_num_points;

@@ -284,13 +284,17 @@ class PillarVFEFromPoints(_PillarVFEBase):
             if self.emit_index_map:
                 batch_dict["bev_index_map"] = res["cell_row"]
         else:
-            if self.emit_index_map:
-                raise NotImplementedError("EMIT_INDEX_MAP is implemented for the single-layer PFN path")
             buffers = None
             if self.output_ring > 0:
                 buffers = self._ring_buffers(points.shape[0], batch_size, points.device)
+            if self.emit_index_map and buffers is None:  # the map is a view of the workspace: keep that alive with the result
+                buffers = ops.EncodeBuffers(points.shape[0], batch_size, self.grid, int(self.num_filters[-1]), points.device,
+                                            with_bev=self.fuse_scatter)
             res = ops.encode_stack(points, offs, self.grid, self._stack(points.device), col0=col0,
-                                   with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant, buffers=buffers)
+                                   with_bev=self.fuse_scatter, scatter_variant=self.scatter_variant, buffers=buffers,
+                                   want_index_map=self.emit_index_map)
+            if self.emit_index_map:
+                batch_dict["bev_index_map"] = res["cell_row"]
         if self.fuse_scatter:
             batch_dict["spatial_features"] = res["bev"]
             batch_dict["_b200_scatter_done"] = True

@@ -313,12 +313,13 @@ def pfn_dense_stack(voxels: torch.Tensor, num_points: torch.Tensor, coords: torc
 def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSpec, stack: PfnStackParams, *,
                  col0: int = 0, dynamic: bool = False, coords_cols: int = 4, with_bev: bool = False,
                  capacity: Optional[int] = None, scatter_variant: str = "auto", ws_slot: int = 0,
-                 buffers: Optional["EncodeBuffers"] = None) -> Dict[str, torch.Tensor]:
+                 buffers: Optional["EncodeBuffers"] = None, want_index_map: bool = False) -> Dict[str, torch.Tensor]:
     """Raw points -> pillar features through a feature stack.  ``dynamic=False``: hard-voxeliser semantics (the fused
     equivalent of ``transform_points_to_voxels`` + a multi-layer ``PillarVFE``; NUM_FILTERS [64, 64] in the standard
     feature layout runs on the streaming kernel's two-layer variant, everything else on the general kernel);
     ``dynamic=True``: DynamicPillarVFE / DynamicPillarVFESimple2D semantics (dynamic_pillar_vfe.py:90-142, :193-240).
-    ``buffers`` (hard mode, 4-column coords): pre-allocated outputs + workspace, as for :func:`encode_bev`."""
+    ``buffers`` (hard mode, 4-column coords): pre-allocated outputs + workspace, as for :func:`encode_bev`;
+    ``want_index_map`` (needs ``buffers``, whose workspace it is a view of): ``cell_row`` as in :func:`encode_bev`."""
     _check_points(points, frame_offsets)
     lib = _native.load()
     n, stride = points.shape
@@ -369,6 +370,12 @@ def encode_stack(points: torch.Tensor, frame_offsets: torch.Tensor, grid: GridSp
             out.bev_half = res["bev"].data_ptr()
         else:
             out.bev = res["bev"].data_ptr()
+    if want_index_map:
+        if buffers is None:
+            raise ValueError("want_index_map needs EncodeBuffers (the map is a view of their workspace)")
+        out.want_index_map = 1
+        off = lib.pillars_workspace_cell_row_offset(n, nb, ctypes.byref(g))
+        res["cell_row"] = buffers.ws[off:off + 4 * nb * ny * nx].view(torch.int32).view(nb, ny, nx)
     nat = stack.native()
     check(lib.pillars_encode_stack(points.data_ptr(), n, stride, col0, frame_offsets.data_ptr(), nb, ctypes.byref(g),
                                    ctypes.byref(nat), _native.MODE_DYNAMIC if dynamic else _native.MODE_HARD, coords_cols,

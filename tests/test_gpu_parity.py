@@ -1140,3 +1140,37 @@ def test_dynamic_vfe_full_size_vs_oracle(wl, filters, dev, L, oracle):
     # twice the same rows, bit for bit
     bd2 = vfe({"points": torch.from_numpy(pb).to(dev), "batch_size": nb})
     assert torch.equal(bd2["pillar_features"], bd["pillar_features"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("filters", [[64, 64], [48, 40]])
+def test_two_layer_stack_emits_the_index_map(filters, dev, L, oracle):
+    """EMIT_INDEX_MAP with a two-layer PFN (streaming two-layer kernel and the general kernel): ``bev_index_map[b, y, x]`` is
+    the row of the pillar in that cell and -1 elsewhere, also where max_voxels dropped pillars -- the canvas-free input of
+    the tokeniser and of the backbone's first layer."""
+    from lidar_vision_vqa_b200 import synth
+
+    rng, vs, p, mv = (-12.8, -12.8, -5.0, 12.8, 12.8, 3.0), (0.4, 0.4, 8.0), 8, 900
+    frames = [synth.make_sweep(900 + i, synth.NUSCENES_32, 5)[:6000] for i in range(2)]
+    offs = np.zeros(3, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    pts = np.concatenate(frames, 0)
+    sd = oracle.random_pfn_params(11, filters, True, seed=31)
+    grid_size = oracle.grid_size_of(rng, vs)
+    cfg = C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=filters, MAX_POINTS_PER_VOXEL=p,
+            MAX_NUMBER_OF_VOXELS=mv, FUSE_SCATTER=False, EMIT_INDEX_MAP=True)
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=list(vs),
+                                point_cloud_range=np.asarray(rng, np.float32), grid_size=grid_size)
+    vfe.load_state_dict(sd)
+    vfe.eval().to(dev)
+    bd = vfe({"points": torch.from_numpy(synth.to_pcdet_points(pts, offs)).to(dev), "batch_size": 2})
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    assert (ref["pillars_per_frame"] == mv).all(), "max_voxels is meant to bind"
+    np.testing.assert_array_equal(bd["voxel_coords"].cpu().numpy(), ref["coords"])
+    nx, ny = int(grid_size[0]), int(grid_size[1])
+    want = np.full((2, ny, nx), -1, np.int32)
+    c = ref["coords"]
+    want[c[:, 0], c[:, 2], c[:, 3]] = np.arange(c.shape[0], dtype=np.int32)
+    np.testing.assert_array_equal(bd["bev_index_map"].cpu().numpy(), want)
+    ref_f = oracle.pillar_vfe(ref["voxels"], ref["num_points"], ref["coords"], sd, vs, rng).numpy()
+    np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), ref_f, rtol=1e-3, atol=1e-5)
