@@ -307,6 +307,39 @@ def reference_eager_on_gpu(workload: str, n_frames: int, dev, steps: int = 10):
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / steps
         res[name] = {"ms_per_step": ms, "sweeps_per_s": n_frames / (ms * 1e-3)}
+    # the same call on the same padded voxels through this repo's drop-in modules (PillarVFE on padded voxels is the literal
+    # replacement of pillar_vfe.py:86-123; kernel k_pfn_dense) -- same interface, same inputs, same GPU
+    import lidar_vision_vqa_b200 as L
+
+    ours_vfe = L.PillarVFE(model_cfg=Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[F_OUT]),
+                           num_point_features=5, voxel_size=list(gc.voxel_size),
+                           point_cloud_range=np.asarray(gc.point_cloud_range, np.float32), grid_size=np.asarray(gc.grid_size))
+    ours_vfe.load_state_dict(sd)
+    ours_vfe.eval().to(dev)
+    ours_sc = L.PointPillarScatter(model_cfg=Cfg(NUM_BEV_FEATURES=F_OUT), grid_size=np.asarray(gc.grid_size))
+    ref_out = out
+
+    def run_ours(src, copy):
+        with torch.inference_mode():
+            bd = {k: (v.to(dev, non_blocking=True) if copy else v) for k, v in src.items()}
+            bd["batch_size"] = n_frames
+            return ours_sc(ours_vfe(bd))["spatial_features"]
+
+    for name, src, copy in (("this_repo_modules_only", resident, False), ("this_repo_from_pinned_voxels", host, True)):
+        for _ in range(3):
+            got = run_ours(src, copy)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            got = run_ours(src, copy)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+        res[name] = {"ms_per_step": ms, "sweeps_per_s": n_frames / (ms * 1e-3)}
+    res["this_repo_max_abs_err_vs_reference"] = float((got - ref_out).abs().max().item())
+    res["this_repo_speedup_modules_only"] = res["modules_only"]["ms_per_step"] / res["this_repo_modules_only"]["ms_per_step"]
+    del got, ref_out
     res["cpu_voxelise_ms_per_step_one_core"] = vox_ms
     res["padded_voxel_bytes_h2d"] = int(voxels.nbytes + npts.nbytes + coords.nbytes)
     res["what"] = ("reference PillarVFE + PointPillarScatter (oracle/_ref, unmodified, eager PyTorch, fp32) on this B200, "

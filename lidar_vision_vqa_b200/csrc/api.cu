@@ -357,9 +357,15 @@ int pillars_pfn_dense(const float *voxels, const void *num_points, int32_t num_p
     if (reinterpret_cast<uintptr_t>(coords) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0)
         return fail(PILLARS_E_BADARG, "coords / out must be 16-byte aligned");
     const PfnDev pd = make_pfn_dev(*pfn, voxel_size);
-    cudaError_t e = launch_pfn_dense(voxels, num_points, num_points_is_float != 0, coords, coords_is_float != 0, m,
-                                     max_points, pfn->c_point, pfn->c_in, pfn->f_out, pfn->use_absolute_xyz != 0,
-                                     pfn->with_distance != 0, pd, out, static_cast<cudaStream_t>(stream));
+    // the folded form (table prepared by pillars_fold_pfn) where it applies, else the faithful 11-feature kernel
+    const bool folded_ok = pfn->folded && stream_kernel_covers(*pfn) && !g_force_generic && m < (int64_t(1) << 31) &&
+                           max_points <= 32;  // one slot per lane
+    cudaError_t e = folded_ok
+                        ? launch_pfn_padded(voxels, num_points, num_points_is_float != 0, coords, coords_is_float != 0, m,
+                                            max_points, pfn->c_point, pd, pfn->folded, out, static_cast<cudaStream_t>(stream))
+                        : launch_pfn_dense(voxels, num_points, num_points_is_float != 0, coords, coords_is_float != 0, m,
+                                           max_points, pfn->c_point, pfn->c_in, pfn->f_out, pfn->use_absolute_xyz != 0,
+                                           pfn->with_distance != 0, pd, out, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "pillars_pfn_dense");
     g_launches_last = g_launches;
     return 0;

@@ -325,6 +325,10 @@ struct FastJob {
 cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st, int f_out = 64);
 constexpr int kFolded2Floats = 2 * 32 * 64 + 64;
 cudaError_t launch_fold_pfn2(const float *weight, const float *scale, const float *shift, float *folded2, cudaStream_t st);
+// PillarVFE.forward on padded voxels in the streaming kernel's folded form (configurations stream_kernel_covers accepts)
+cudaError_t launch_pfn_padded(const float *voxels, const void *num_points, bool np_float, const void *coords, bool coords_float,
+                              int64_t m, int max_points, int c_point, const PfnDev &pfn, const float *folded, float *out,
+                              cudaStream_t st);
 cudaError_t launch_pillar_features_stream(const FastJob &job, const float *folded, const GridDev &gd, const Workspace &ws,
                                           cudaStream_t st);
 

@@ -827,6 +827,146 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     }
 }
 
+// ---- the reference's own padded input: voxels [M, P, C], num_points [M], coords [M, 4] (b, z, y, x) ----------------------
+// PillarVFE.forward on what the data processor's voxeliser hands over (pillar_vfe.py:86-123), in the same folded form as the
+// walk above: a warp takes one pillar at a time (pillars strided over the persistent warps), lane = slot while the pillar
+// is loaded -- 20-byte slots, 640 contiguous bytes per pillar at P = 32 -- and turned into the 32-byte records point_eval
+// reads, lane = channel pair while the valid points are evaluated.  The mean is the reference's: the sum over ALL P slots,
+// whatever the padding holds, divided by num_points (:97), in a fixed shuffle order (bit-reproducible).
+struct PaddedParams {
+    const float *voxels;
+    const void *num_points, *coords;
+    int np_float, coords_float;
+    int64_t m;
+    int P, C;
+    const float *folded;
+    float vsz[3], off[3];
+    float fx_scale[3], fx_inv[3], extent[3];  // fixed-point sums of the valid slots: scale, inverse, |x - centre| bound
+    float *out;
+};
+
+// what a warp needs of a pillar before it can start: the header and its slot (one per lane, P <= 32)
+struct PaddedHead {
+    float nf, fx, fy, fz, x, y, z, a, t;
+    int n;
+};
+
+__device__ __forceinline__ PaddedHead padded_fetch(const PaddedParams &p, int64_t g, int lane)
+{
+    PaddedHead h;
+    if (p.np_float) {
+        h.nf = __ldg(static_cast<const float *>(p.num_points) + g);
+        h.n = static_cast<int>(h.nf);  // .int() in get_paddings_indicator (pillar_vfe.py:91)
+    } else {
+        h.n = __ldg(static_cast<const int32_t *>(p.num_points) + g);
+        h.nf = static_cast<float>(h.n);  // .type_as(voxel_features) (pillar_vfe.py:97)
+    }
+    if (p.coords_float) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(static_cast<const float *>(p.coords) + g * 4));
+        h.fz = c4.y; h.fy = c4.z; h.fx = c4.w;
+    } else {
+        const int4 c4 = __ldg(reinterpret_cast<const int4 *>(static_cast<const int32_t *>(p.coords) + g * 4));
+        h.fz = static_cast<float>(c4.y); h.fy = static_cast<float>(c4.z); h.fx = static_cast<float>(c4.w);
+    }
+    h.x = h.y = h.z = h.a = h.t = 0.f;
+    if (lane < p.P) {
+        const float *q = p.voxels + (g * p.P + lane) * p.C;
+        h.x = __ldg(q);
+        h.y = __ldg(q + 1);
+        h.z = __ldg(q + 2);
+        if (p.C > 3) h.a = __ldg(q + 3);
+        if (p.C > 4) h.t = __ldg(q + 4);
+    }
+    return h;
+}
+
+__device__ __forceinline__ void padded_pillar(const PaddedParams &p, const LaneWeights &w, const PaddedHead &h, int64_t g,
+                                              uint32_t s_rec, unsigned long long out_lane, int lane)
+{
+    const float cx = __fadd_rn(__fmul_rn(h.fx, p.vsz[0]), p.off[0]);
+    const float cy = __fadd_rn(__fmul_rn(h.fy, p.vsz[1]), p.off[1]);
+    const float cz = __fadd_rn(__fmul_rn(h.fz, p.vsz[2]), p.off[2]);
+    const int n_valid = __shfl_sync(kFull, max(0, min(h.n, p.P)), 0);  // (uniform anyway; the shuffle tells the compiler)
+    const float rx = __fsub_rn(h.x, cx), ry = __fsub_rn(h.y, cy), rz = __fsub_rn(h.z, cz);
+    // Sum over ALL P slots (pillar_vfe.py:97).  What a voxeliser hands over -- valid points inside their pillar, zeros in
+    // the padding -- is summed exactly: fixed-point integers relative to the pillar centre, one redux.sync per axis.
+    // Anything else (non-zero padding, a "valid" point outside its pillar, num_points outside 1..P) takes the float path.
+    int ix = 0, iy = 0, iz = 0;
+    bool odd;
+    if (lane < n_valid) {
+        odd = !(fabsf(rx) <= p.extent[0] && fabsf(ry) <= p.extent[1] && fabsf(rz) <= p.extent[2]);
+        ix = __float2int_rn(rx * p.fx_scale[0]);
+        iy = __float2int_rn(ry * p.fx_scale[1]);
+        iz = __float2int_rn(rz * p.fx_scale[2]);
+    } else {
+        odd = h.x != 0.f || h.y != 0.f || h.z != 0.f;  // (lanes beyond P hold zeros)
+    }
+    odd |= h.n != n_valid || h.n < 1;
+    __syncwarp();  // the previous pillar's records have been read
+    sts4(s_rec + lane * 32u, make_float4(rx, ry, rz, h.a));
+    sts1(s_rec + lane * 32u + 16u, __float_as_uint(h.t));
+    __syncwarp();
+    float2 acc = make_float2(-INFINITY, -INFINITY);
+    int k = 0;
+    for (; k + 1 < n_valid; k += 2) {
+        const float2 ya = point_eval(w, s_rec + k * 32u), yb = point_eval(w, s_rec + k * 32u + 32u);
+        acc = max3(acc, ya, yb);
+    }
+    if (k < n_valid) acc = max2(acc, point_eval(w, s_rec + k * 32u));
+    float mrx, mry, mrz;  // mean - centre
+    if (!__any_sync(kFull, odd)) {
+        const float rn = __frcp_rn(h.nf);
+        mrx = rel_mean(cx, static_cast<float>(__reduce_add_sync(kFull, ix)) * p.fx_inv[0] * rn);
+        mry = rel_mean(cy, static_cast<float>(__reduce_add_sync(kFull, iy)) * p.fx_inv[1] * rn);
+        mrz = rel_mean(cz, static_cast<float>(__reduce_add_sync(kFull, iz)) * p.fx_inv[2] * rn);
+    } else {
+        float sx = h.x, sy = h.y, sz = h.z;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            sx = __fadd_rn(sx, __shfl_xor_sync(kFull, sx, s));
+            sy = __fadd_rn(sy, __shfl_xor_sync(kFull, sy, s));
+            sz = __fadd_rn(sz, __shfl_xor_sync(kFull, sz, s));
+        }
+        mrx = __fsub_rn(__fdiv_rn(sx, h.nf), cx);
+        mry = __fsub_rn(__fdiv_rn(sy, h.nf), cy);
+        mrz = __fsub_rn(__fdiv_rn(sz, h.nf), cz);
+    }
+    const float4 c4 = make_float4(cx, cy, cz, 0.f);
+    const float4 m4 = make_float4(mrx, mry, mrz, __int_as_float(static_cast<int>(g)));
+    pillar_finish(w, c4, m4, n_valid < p.P, acc, out_lane);
+}
+
+// P <= 32 (every pillar configuration of the reference: 20 / 32): one slot per lane.  The NEXT pillar's loads are issued
+// before the current one is processed (two heads in ping-pong, the loop unrolled by two so that neither is copied).
+template <int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, 6) k_pfn_padded(const __grid_constant__ PaddedParams p)
+{
+    __shared__ __align__(16) unsigned char s_all[kWarps * 1024];
+    const int lane = threadIdx.x & 31;
+    // warp-uniform by construction (a shuffle result), so the compiler sees the pillar loop as convergent and the *_sync
+    // operations inside it stay single instructions instead of convergence-barrier sequences
+    const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
+    const uint32_t s_rec = static_cast<uint32_t>(__cvta_generic_to_shared(s_all)) + warp * 1024u;
+    const LaneWeights w = load_lane_weights(p.folded, lane);
+    const unsigned long long out_lane = static_cast<unsigned long long>(__cvta_generic_to_global(p.out + 2 * lane));
+    const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarps;
+    int64_t g = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+    if (g >= p.m) return;
+    PaddedHead a = padded_fetch(p, g, lane), b = a;
+    while (true) {
+        const bool has_b = g + n_warps < p.m;
+        if (has_b) b = padded_fetch(p, g + n_warps, lane);
+        padded_pillar(p, w, a, g, s_rec, out_lane, lane);
+        if (!has_b) break;
+        g += n_warps;
+        const bool has_a = g + n_warps < p.m;
+        if (has_a) a = padded_fetch(p, g + n_warps, lane);
+        padded_pillar(p, w, b, g, s_rec, out_lane, lane);
+        if (!has_a) break;
+        g += n_warps;
+    }
+}
+
 // ---- folding of the layer's weights (once per model: pillars_fold_pfn) ------------------------------------------------
 __global__ void k_fold_pfn(const float *__restrict__ weight, const float *__restrict__ scale,
                            const float *__restrict__ shift, int c_point, int c_in, int f_out, float *__restrict__ folded)
@@ -883,6 +1023,43 @@ __global__ void k_fold_pfn2(const float *__restrict__ weight, const float *__res
 cudaError_t launch_fold_pfn2(const float *weight, const float *scale, const float *shift, float *folded2, cudaStream_t st)
 {
     k_fold_pfn2<<<8, 256, 0, st>>>(weight, scale, shift, folded2);
+    note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pfn_padded(const float *voxels, const void *num_points, bool np_float, const void *coords, bool coords_float,
+                              int64_t m, int max_points, int c_point, const PfnDev &pfn, const float *folded, float *out,
+                              cudaStream_t st)
+{
+    if (m == 0) return cudaSuccess;
+    PaddedParams p{};
+    p.voxels = voxels;
+    p.num_points = num_points;
+    p.coords = coords;
+    p.np_float = np_float ? 1 : 0;
+    p.coords_float = coords_float ? 1 : 0;
+    p.m = m;
+    p.P = max_points;
+    p.C = c_point;
+    p.folded = folded;
+    for (int k = 0; k < 3; ++k) {
+        p.vsz[k] = pfn.vsz[k];
+        p.off[k] = pfn.off[k];
+    }
+    p.out = out;
+    for (int k = 0; k < 3; ++k) {
+        // |x - centre| <= voxel / 2 (+ rounding) for a point inside its pillar; the sum of P such values stays below 2^31
+        const double extent = 0.5 * static_cast<double>(pfn.vsz[k]) * 1.01 + 1e-6;
+        int sc = static_cast<int>(std::floor(std::log2(2147483647.0 / (static_cast<double>(max_points) * extent))));
+        sc = sc < -60 ? -60 : (sc > 60 ? 60 : sc);
+        p.fx_scale[k] = static_cast<float>(std::ldexp(1.0, sc));
+        p.fx_inv[k] = static_cast<float>(std::ldexp(1.0, -sc));
+        p.extent[k] = static_cast<float>(extent);
+    }
+    constexpr int kWarps = 4;
+    const int64_t wave = static_cast<int64_t>(current_sm_count()) * 6;
+    const int64_t blocks = tmin<int64_t>((m + kWarps - 1) / kWarps, wave);
+    k_pfn_padded<kWarps><<<static_cast<unsigned>(blocks), 32 * kWarps, 0, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
