@@ -1174,3 +1174,43 @@ def test_two_layer_stack_emits_the_index_map(filters, dev, L, oracle):
     np.testing.assert_array_equal(bd["bev_index_map"].cpu().numpy(), want)
     ref_f = oracle.pillar_vfe(ref["voxels"], ref["num_points"], ref["coords"], sd, vs, rng).numpy()
     np.testing.assert_allclose(bd["pillar_features"].cpu().numpy(), ref_f, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_padded_voxels_with_nonzero_padding_and_stray_points(dev, L, oracle):
+    """PillarVFE.forward on padded voxels sums ALL P slots for the mean, whatever the padding holds (pillar_vfe.py:97), and
+    takes whatever points it is given.  The folded kernel's exact integer sums apply to clean voxeliser output only; pillars
+    with non-zero padding, with a "valid" point far outside their cell, or with a float num_points tensor must take its
+    float path and still match the reference arithmetic (CPU oracle), next to clean pillars in the same launch."""
+    from lidar_vision_vqa_b200 import ops, synth
+
+    rng, vs, p, mv = (-12.8, -12.8, -5.0, 12.8, 12.8, 3.0), (0.4, 0.4, 8.0), 12, 5000
+    pts = synth.make_sweep(77, synth.NUSCENES_32, 5)[:9000]
+    offs = np.array([0, len(pts)], np.int32)
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    voxels, npts, coords = ref["voxels"].copy(), ref["num_points"].copy(), ref["coords"].copy()
+    m = voxels.shape[0]
+    r = np.random.default_rng(3)
+    dirty = r.choice(m, m // 7, replace=False)           # garbage in the padding slots
+    for g in dirty:
+        if npts[g] < p:
+            voxels[g, npts[g]:, :] = r.normal(0, 3.0, (p - npts[g], 5)).astype(np.float32)
+    stray = r.choice(m, m // 11, replace=False)           # a valid point 7 m away from its pillar
+    voxels[stray, 0, :3] += np.float32(7.0)
+    sd = oracle.random_pfn_params(11, [64], True, seed=41)
+    want = oracle.pillar_vfe(voxels, npts, coords, sd, vs, rng).numpy()
+    pfn = ops.fold_pfn(sd["pfn_layers.0.linear.weight"], (sd["pfn_layers.0.norm.weight"], sd["pfn_layers.0.norm.bias"],
+                       sd["pfn_layers.0.norm.running_mean"], sd["pfn_layers.0.norm.running_var"], 1e-3), None, c_point=5,
+                       use_absolute_xyz=True, with_distance=False, voxel_size=vs, point_cloud_range=rng, device=dev)
+    assert pfn.folded is not None
+    v_d, c_d = torch.from_numpy(voxels).to(dev), torch.from_numpy(coords).to(dev)
+    for n_t in (torch.from_numpy(npts).to(dev), torch.from_numpy(npts.astype(np.float32)).to(dev)):
+        got = ops.pfn_dense(v_d, n_t, c_d, pfn, vs).cpu().numpy()
+        scale = np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))
+        assert (np.abs(got - want) <= 1e-3 * np.abs(want) + 1e-5 * scale).all()
+    ops.force_generic_features(True)
+    try:
+        faithful = ops.pfn_dense(v_d, torch.from_numpy(npts).to(dev), c_d, pfn, vs).cpu().numpy()
+    finally:
+        ops.force_generic_features(False)
+    assert (np.abs(faithful - want) <= 1e-3 * np.abs(want) + 1e-5 * np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))).all()
