@@ -578,7 +578,9 @@ k_pillar_walk(const __grid_constant__ WalkParams p)
     __shared__ __align__(16) unsigned char s_all[kWarps * kStride];
     __shared__ __align__(16) float s_w1b[kTwo ? 32 * 64 : 4];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // (a shuffle result is warp-uniform by construction: the compiler then treats the chunk loop as convergent)
+    const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
     if (threadIdx.x == 0) dbg_stamp(p.dbg, 18);
     pdl_wait();  // records, pillar entries and the list header come from the grouping kernels
     pdl_trigger();
