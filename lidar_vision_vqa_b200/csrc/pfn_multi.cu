@@ -811,10 +811,60 @@ cudaError_t launch_dynamic_ranks(const GridDev &gd, const Workspace &ws, int nb,
     return cudaGetLastError();
 }
 
+// ---- the same ranks for the streaming kernel, from a BITMAP of the occupied cells (1 bit per cell in (b, ix, iy) order: 0.5 MB
+//      at cfg2 instead of the 16.7 MB word-per-cell array above): mark, prefix of the word popcounts, one thread per pillar
+__device__ __forceinline__ uint32_t dyn_bit_index(const GridDev &gd, uint32_t key)
+{
+    const uint32_t b = key / gd.cells, cell = key - b * gd.cells;  // nz == 1 in this mode
+    const uint32_t y = cell / static_cast<uint32_t>(gd.g[0]), x = cell - y * static_cast<uint32_t>(gd.g[0]);
+    return b * static_cast<uint32_t>(gd.cells_xy) + x * static_cast<uint32_t>(gd.g[1]) + y;
+}
+
+__global__ void k_dyn_mark_bits(const Header *__restrict__ hdr, const uint32_t *__restrict__ pillar_key, GridDev gd,
+                                uint32_t *__restrict__ bm)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= hdr->total_pillars) return;
+    const uint32_t idx = dyn_bit_index(gd, pillar_key[g]);
+    atomicOr(bm + (idx >> 5), 1u << (idx & 31u));
+}
+
+// pre[w] <- occupied cells before word w inside its 2048-word block; block_sum[blk] <- occupied cells of the block
+__global__ void __launch_bounds__(256) k_dyn_word_prefix(const uint32_t *__restrict__ bm, int64_t n_words, uint32_t *__restrict__ pre,
+                                                         uint32_t *__restrict__ block_sum)
+{
+    __shared__ uint32_t s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x * 8;
+    uint32_t o[8], c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        o[k] = (i0 + k < n_words) ? __popc(bm[i0 + k]) : 0u;
+        c += o[k];
+    }
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - c;
+    for (int w = 0; w < warp; ++w) run += s_w[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (i0 + k < n_words) pre[i0 + k] = run;
+        run += o[k];
+    }
+    if (threadIdx.x == 255) block_sum[blockIdx.x] = run;
+}
+
 // one thread per pillar (grouping order): row = rank of its cell; patches the pillar entry the streaming kernel reads
 __global__ void k_dynamic_rows(const Header *__restrict__ hdr, const uint32_t *__restrict__ pillar_key,
                                const uint32_t *__restrict__ pillar_list, const uint32_t *__restrict__ pillar_cnt, GridDev gd,
-                               const uint32_t *__restrict__ occ, int64_t capacity, uint4 *__restrict__ pillar_meta,
+                               const uint32_t *__restrict__ bm, const uint32_t *__restrict__ pre,
+                               const uint32_t *__restrict__ block_sum, int64_t capacity, uint4 *__restrict__ pillar_meta,
                                int32_t *__restrict__ voxel_coords, int32_t *__restrict__ voxel_num_points)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -822,7 +872,8 @@ __global__ void k_dynamic_rows(const Header *__restrict__ hdr, const uint32_t *_
     const uint32_t key = pillar_key[g];
     const uint32_t b = key / gd.cells, cell = key - b * gd.cells;  // nz == 1 in this mode
     const uint32_t y = cell / static_cast<uint32_t>(gd.g[0]), x = cell - y * static_cast<uint32_t>(gd.g[0]);
-    const uint32_t row = occ[static_cast<size_t>(b) * gd.cells_xy + static_cast<size_t>(x) * gd.g[1] + y] & 0x7FFFFFFFu;
+    const uint32_t idx = b * static_cast<uint32_t>(gd.cells_xy) + x * static_cast<uint32_t>(gd.g[1]) + y, w = idx >> 5;
+    const uint32_t row = block_sum[w / kScanBlock] + pre[w] + __popc(bm[w] & ((1u << (idx & 31u)) - 1u));
     const bool live = static_cast<int64_t>(row) < capacity;
     reinterpret_cast<uint32_t *>(pillar_meta + pillar_list[g])[1] = live ? row : 0xFFFFFFFFu;
     if (!live) return;
@@ -835,13 +886,24 @@ __global__ void k_dynamic_rows(const Header *__restrict__ hdr, const uint32_t *_
 cudaError_t launch_dynamic_rows(const GridDev &gd, const Workspace &ws, int nb, int64_t n, int64_t capacity,
                                 int32_t *voxel_coords, int32_t *voxel_num_points, cudaStream_t st)
 {
-    cudaError_t e = launch_dynamic_ranks(gd, ws, nb, n, st);
+    // scratch in the index-map region of the workspace (4 bytes per cell; the bitmap and its prefix need 1/4 of a byte)
+    const int64_t n_cells = static_cast<int64_t>(nb) * gd.cells_xy;
+    if (n_cells >= (int64_t(1) << 32)) return cudaErrorInvalidValue;
+    const int64_t n_words = (n_cells + 31) / 32;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(ws.cell_row);
+    uint32_t *pre = bm + ((n_words + 3) & ~int64_t(3));
+    uint32_t *block_sum = ws.scan_scratch;
+    const int n_blocks = static_cast<int>((n_words + kScanBlock - 1) / kScanBlock);
+    cudaError_t e = cudaMemsetAsync(bm, 0, sizeof(uint32_t) * n_words, st);
     if (e != cudaSuccess) return e;
-    const unsigned mb = static_cast<unsigned>((n + 255) / 256);
-    k_dynamic_rows<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, ws.pillar_list, ws.pillar_cnt, gd,
-                                       reinterpret_cast<const uint32_t *>(ws.cell_row), capacity, ws.pillar_meta, voxel_coords,
-                                       voxel_num_points);
     note_launch();
+    const unsigned mb = static_cast<unsigned>((n + 255) / 256);
+    k_dyn_mark_bits<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, gd, bm);
+    k_dyn_word_prefix<<<n_blocks, 256, 0, st>>>(bm, n_words, pre, block_sum);
+    k_scan_block_sums<<<1, 1024, 0, st>>>(block_sum, n_blocks);
+    k_dynamic_rows<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, ws.pillar_list, ws.pillar_cnt, gd, bm, pre, block_sum, capacity,
+                                       ws.pillar_meta, voxel_coords, voxel_num_points);
+    note_launch(4);
     return cudaGetLastError();
 }
 
