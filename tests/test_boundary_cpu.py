@@ -265,3 +265,34 @@ def test_backbone_output_shape_and_flop_count_match_the_reference_module():
             x.remove()
         assert BaseBEVBackbone(cfg, 64).output_shape(h, w) == tuple(out.shape[1:])
         assert abs(bench.backbone_flops(cfg, 64, h, w, nb) - sum(flops)) <= 1e-6 * sum(flops)
+
+
+def test_bench_side_measurements_are_guarded():
+    """A failing optional section of bench.py (tokeniser, extractor, backbone, sub-lines) is recorded under its key and does
+    not cost the run its main JSON line."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def boom():
+        raise ValueError("no such workload")
+
+    assert bench.guarded("ok", lambda: {"value": 1}) == {"value": 1}
+    got = bench.guarded("broken", boom)
+    assert set(got) == {"error"} and "ValueError" in got["error"] and "no such workload" in got["error"]
+
+
+def test_workspace_holds_the_second_layer_table(lib):
+    """The two-layer streaming path folds layer 1 into the workspace (kFolded2Floats floats): the query must have grown by at
+    least that over what the single-layer path needs of it, for every workload shape."""
+    from lidar_vision_vqa_b200 import GridSpec
+    import ctypes
+
+    grid = GridSpec.from_range((-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), (0.2, 0.2, 8.0), 32, 30000)
+    g = grid.native()
+    for n, nb in ((0, 1), (1000, 1), (503251, 16)):
+        need = lib.pillars_workspace_bytes(n, nb, ctypes.byref(g))
+        assert need >= 4 * (2 * 32 * 64 + 64)
+        assert need % 16 == 0 or need > 0
