@@ -1214,3 +1214,77 @@ def test_padded_voxels_with_nonzero_padding_and_stray_points(dev, L, oracle):
     finally:
         ops.force_generic_features(False)
     assert (np.abs(faithful - want) <= 1e-3 * np.abs(want) + 1e-5 * np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_streaming_variants_randomised(seed, dev, L, oracle):
+    """Random grids, caps, frame layouts and clustered clouds through the three late additions to the streaming kernel --
+    hard [64, 64], dynamic [64], dynamic [64, 64] -- against the CPU oracle: pillars of exactly 32 / 33 points, pillars
+    that straddle chunk boundaries, caps of 1 ... 40 points, max_voxels binding or not, empty frames."""
+    from lidar_vision_vqa_b200 import synth
+
+    r = np.random.default_rng(1000 + seed)
+    vs_xy = float(r.choice([0.2, 0.4, 0.8, 1.6]))
+    half = vs_xy * int(r.choice([16, 32, 64]))
+    rng, vs = (-half, -half, -5.0, half, half, 3.0), (vs_xy, vs_xy, 8.0)
+    p = int(r.choice([1, 2, 5, 20, 32, 40]))
+    n_frames = int(r.integers(1, 5))
+    frames = []
+    for f in range(n_frames):
+        if n_frames > 1 and r.random() < 0.2:
+            frames.append(np.zeros((0, 5), np.float32))
+            continue
+        base = synth.make_sweep(3000 + 10 * seed + f, synth.NUSCENES_32, 5)[: int(r.integers(2000, 12000))]
+        base[:, :2] *= np.float32(half / 51.2)
+        blobs = []
+        for cnt in (32, 33, 31, 64, 65, int(r.integers(100, 700))):  # pillars of chosen sizes inside one cell each
+            cx, cy = (np.floor(r.uniform(-half, half - vs_xy, 2) / vs_xy) + 0.5) * vs_xy
+            b = np.concatenate([r.uniform(-0.45, 0.45, (cnt, 2)) * vs_xy + [cx, cy], r.uniform(-4.5, 2.5, (cnt, 1)),
+                                r.uniform(0, 255, (cnt, 1)), r.uniform(0, 0.5, (cnt, 1))], 1)
+            blobs.append(b.astype(np.float32))
+        fr = np.concatenate([base] + blobs, 0)
+        frames.append(fr[r.permutation(len(fr))])
+    offs = np.zeros(n_frames + 1, np.int32)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    pts = np.concatenate(frames, 0)
+    pb = synth.to_pcdet_points(pts, offs)
+    grid_size = oracle.grid_size_of(rng, vs)
+    ref0 = oracle.voxelize_batch(pts, offs, rng, vs, p, 10 ** 6)
+    per_frame = int(max(1, ref0["pillars_per_frame"].max()))
+    mv = per_frame + 5 if r.random() < 0.5 else max(1, per_frame // 2)  # not binding / binding
+
+    def tol_ok(got, ref):
+        scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True)) if ref.size else 1.0
+        return (np.abs(got - ref) <= 1e-3 * np.abs(ref) + 1e-5 * scale).all()
+
+    # hard semantics, two layers
+    sd2 = oracle.random_pfn_params(11, [64, 64], True, seed=seed)
+    cfg = C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64, 64], MAX_POINTS_PER_VOXEL=p,
+            MAX_NUMBER_OF_VOXELS=mv, FUSE_SCATTER=True)
+    vfe = L.PillarVFEFromPoints(model_cfg=cfg, num_point_features=5, voxel_size=list(vs),
+                                point_cloud_range=np.asarray(rng, np.float32), grid_size=grid_size)
+    vfe.load_state_dict(sd2)
+    vfe.eval().to(dev)
+    bd = vfe({"points": torch.from_numpy(pb).to(dev), "batch_size": n_frames})
+    ref = oracle.voxelize_batch(pts, offs, rng, vs, p, mv)
+    np.testing.assert_array_equal(bd["voxel_coords"].cpu().numpy(), ref["coords"])
+    np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), ref["num_points"])
+    ref_f = oracle.pillar_vfe(ref["voxels"], ref["num_points"], ref["coords"], sd2, vs, rng).numpy().reshape(-1, 64)
+    got_f = bd["pillar_features"].cpu().numpy().reshape(-1, 64)
+    assert tol_ok(got_f, ref_f)
+    np.testing.assert_array_equal(bd["spatial_features"].cpu().numpy(),
+                                  oracle.scatter_bev(got_f, ref["coords"], int(grid_size[0]), int(grid_size[1]), batch_size=n_frames))
+    # dynamic semantics, one and two layers
+    for filters in ([64], [64, 64]):
+        sd = oracle.random_pfn_params(11, filters, True, seed=seed + 50)
+        dyn = L.DynamicPillarVFE(model_cfg=C(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=filters),
+                                 num_point_features=5, voxel_size=list(vs), grid_size=grid_size,
+                                 point_cloud_range=np.asarray(rng, np.float32))
+        dyn.load_state_dict(sd)
+        dyn.eval().to(dev)
+        bd = dyn({"points": torch.from_numpy(pb).to(dev), "batch_size": n_frames})
+        ref_f, ref_c, ref_n = oracle.dynamic_pillar_vfe(pb, sd, vs, rng)
+        np.testing.assert_array_equal(bd["voxel_coords"].cpu().numpy(), ref_c)
+        np.testing.assert_array_equal(bd["voxel_num_points"].cpu().numpy(), ref_n)
+        assert tol_ok(bd["pillar_features"].cpu().numpy().reshape(-1, 64), ref_f.numpy().reshape(-1, 64))
