@@ -684,6 +684,8 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t *__restrict__
 {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
+    pdl_wait();  // (a no-op in a plain launch)
+    pdl_trigger();
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (int base = 0; base < n_blocks; base += 1024) {
@@ -823,6 +825,8 @@ __device__ __forceinline__ uint32_t dyn_bit_index(const GridDev &gd, uint32_t ke
 __global__ void k_dyn_mark_bits(const Header *__restrict__ hdr, const uint32_t *__restrict__ pillar_key, GridDev gd,
                                 uint32_t *__restrict__ bm)
 {
+    pdl_wait();
+    pdl_trigger();
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= hdr->total_pillars) return;
     const uint32_t idx = dyn_bit_index(gd, pillar_key[g]);
@@ -834,6 +838,8 @@ __global__ void __launch_bounds__(256) k_dyn_word_prefix(const uint32_t *__restr
                                                          uint32_t *__restrict__ block_sum)
 {
     __shared__ uint32_t s_w[8];
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x * 8;
     uint32_t o[8], c = 0;
@@ -867,6 +873,8 @@ __global__ void k_dynamic_rows(const Header *__restrict__ hdr, const uint32_t *_
                                const uint32_t *__restrict__ block_sum, int64_t capacity, uint4 *__restrict__ pillar_meta,
                                int32_t *__restrict__ voxel_coords, int32_t *__restrict__ voxel_num_points)
 {
+    pdl_wait();
+    pdl_trigger();
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= hdr->total_pillars) return;
     const uint32_t key = pillar_key[g];
@@ -898,11 +906,17 @@ cudaError_t launch_dynamic_rows(const GridDev &gd, const Workspace &ws, int nb, 
     if (e != cudaSuccess) return e;
     note_launch();
     const unsigned mb = static_cast<unsigned>((n + 255) / 256);
-    k_dyn_mark_bits<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, gd, bm);
-    k_dyn_word_prefix<<<n_blocks, 256, 0, st>>>(bm, n_words, pre, block_sum);
-    k_scan_block_sums<<<1, 1024, 0, st>>>(block_sum, n_blocks);
-    k_dynamic_rows<<<mb, 256, 0, st>>>(ws.hdr, ws.pillar_key, ws.pillar_list, ws.pillar_cnt, gd, bm, pre, block_sum, capacity,
-                                       ws.pillar_meta, voxel_coords, voxel_num_points);
+    // chained by programmatic dependent launch: every kernel waits for its predecessor at its first instruction, so the
+    // chain stays transitive, and its CTAs are resident before the predecessor has drained
+    const uint32_t *c_bm = bm, *c_pre = pre, *c_bs = block_sum;
+    const Header *c_hdr = ws.hdr;
+    const uint32_t *c_key = ws.pillar_key, *c_list = ws.pillar_list, *c_cnt = ws.pillar_cnt;
+    if ((e = launch_pdl(k_dyn_mark_bits, dim3(mb), dim3(256), 0, st, c_hdr, c_key, gd, bm)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_dyn_word_prefix, dim3(n_blocks), dim3(256), 0, st, c_bm, n_words, pre, block_sum)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_scan_block_sums, dim3(1), dim3(1024), 0, st, block_sum, n_blocks)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_dynamic_rows, dim3(mb), dim3(256), 0, st, c_hdr, c_key, c_list, c_cnt, gd, c_bm, c_pre, c_bs, capacity,
+                        ws.pillar_meta, voxel_coords, voxel_num_points)) != cudaSuccess)
+        return e;
     note_launch(4);
     return cudaGetLastError();
 }

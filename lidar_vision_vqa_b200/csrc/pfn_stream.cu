@@ -973,6 +973,8 @@ __global__ void __launch_bounds__(32 * kWarps, 6) k_pfn_padded(const __grid_cons
 __global__ void k_fold_pfn(const float *__restrict__ weight, const float *__restrict__ scale,
                            const float *__restrict__ shift, int c_point, int c_in, int f_out, float *__restrict__ folded)
 {
+    pdl_wait();  // a link of the stack paths' launch chain (a no-op in a plain launch)
+    pdl_trigger();
     const int o = threadIdx.x;
     if (o >= 64) return;
     if (o >= f_out) {  // a 32-output layer 0 of a two-layer stack: the upper channels are zeros throughout
@@ -1004,7 +1006,8 @@ int env_int(const char *name, int dflt)
 
 cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *folded, cudaStream_t st, int f_out)
 {
-    k_fold_pfn<<<1, 64, 0, st>>>(pfn.weight, pfn.scale, pfn.shift, c_point, c_in, f_out, folded);
+    const cudaError_t e = launch_pdl(k_fold_pfn, dim3(1), dim3(64), 0, st, pfn.weight, pfn.scale, pfn.shift, c_point, c_in, f_out, folded);
+    if (e != cudaSuccess) return e;
     note_launch();
     return cudaGetLastError();
 }
@@ -1013,6 +1016,8 @@ cudaError_t launch_fold_pfn(const PfnDev &pfn, int c_point, int c_in, float *fol
 __global__ void k_fold_pfn2(const float *__restrict__ weight, const float *__restrict__ scale, const float *__restrict__ shift,
                             float *__restrict__ folded2)
 {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (k, j): input k of both halves, output j
     if (i >= 32 * 64) return;
     const int k = i >> 6, j = i & 63;
@@ -1024,7 +1029,8 @@ __global__ void k_fold_pfn2(const float *__restrict__ weight, const float *__res
 
 cudaError_t launch_fold_pfn2(const float *weight, const float *scale, const float *shift, float *folded2, cudaStream_t st)
 {
-    k_fold_pfn2<<<8, 256, 0, st>>>(weight, scale, shift, folded2);
+    const cudaError_t e = launch_pdl(k_fold_pfn2, dim3(8), dim3(256), 0, st, weight, scale, shift, folded2);
+    if (e != cudaSuccess) return e;
     note_launch();
     return cudaGetLastError();
 }
